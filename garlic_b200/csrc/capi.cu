@@ -1,0 +1,753 @@
+// capi.cu — extern "C" layer of libgarlic_b200.so (see include/garlic_b200.h).
+// Host-side glue only: device memory, the segment table (closed form of the reference's window
+// validity), kernel launches, stitching of chunk-boundary runs.  All arithmetic of the
+// hot path happens in the kernels of kernels.cu / wlod.cu.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/garlic_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "wlod.h"
+#include "segments.h"
+
+using namespace garlic;
+
+namespace {
+constexpr int kPad = 4096 + 64;   // over-read slack (SNP entries) behind every per-SNP array / row
+constexpr int kMaxW = 4096;
+
+}
+
+struct garlic_gpu {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int n_ind = 0, ind_offset = 0, n_chr = 0;
+    int64_t L0 = 0, L = 0;
+    std::vector<int64_t> chr_off0, chr_off;
+    std::vector<int32_t> pos0, pos, src, cen;
+    std::vector<double> gpos;
+    bool have_geno0 = false, filtered = false, tables = false, have_gl = false, have_ld = false;
+    int gl_type = GARLIC_GL_ERROR;
+    double error = -1, mu = 1e-9;
+    int max_gap = 200000, M = 7, ld_W = 0;
+    double amax = 0;   // max |LOD table entry| (ambiguity tolerance)
+    int missing_char = '0';
+    // device
+    uint8_t* d_alleles = nullptr;
+    unsigned long long* d_key = nullptr;
+    uint64_t *d_geno0 = nullptr, *d_geno = nullptr;
+    int64_t row_words0 = 0, row_words = 0;
+    int* d_counts = nullptr;
+    double *d_gl0 = nullptr, *d_gl = nullptr;
+    int64_t gl_stride = 0;
+    double *d_freq0 = nullptr, *d_freq = nullptr, *d_lut = nullptr, *d_gpos = nullptr;
+    double *d_nomut = nullptr, *d_norec = nullptr, *d_wlut = nullptr, *d_invld = nullptr, *d_homf = nullptr;
+    uint8_t* d_keep = nullptr;
+    int *d_src = nullptr, *d_pos0 = nullptr, *d_chr_of0 = nullptr, *d_pos = nullptr, *d_chr_of = nullptr,
+        *d_chr_start = nullptr, *d_chr_param = nullptr;
+    RohRec *d_out = nullptr, *d_amb = nullptr;
+    unsigned out_cap = 0, amb_cap = 0;
+    unsigned* d_cnt = nullptr;
+    Item* d_items = nullptr;
+    size_t items_cap = 0;
+    int* d_indlist = nullptr;
+    size_t indlist_cap = 0;
+    double stats[4] = {0, 0, 0, 0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+            return 1;                                                                         \
+        }                                                                                     \
+    } while (0)
+#define LAUNCH(call) do { CK(call); h->launches++; } while (0)
+#define FAIL(msg) do { h->err = (msg); return 1; } while (0)
+
+template <typename T>
+static int dev_alloc(garlic_gpu* h, T** p, size_t n)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (n == 0) n = 1;
+    CK(cudaMalloc((void**)p, n * sizeof(T)));
+    return 0;
+}
+template <typename T>
+static void dev_free(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+extern "C" {
+
+int garlic_gpu_create(int device, garlic_gpu_t** out)
+{
+    if (!out) return 1;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= device || device < 0) {
+        fprintf(stderr, "garlic_b200: no usable CUDA device %d (found %d) — there is no CPU fallback\n", device, n);
+        return 2;
+    }
+    garlic_gpu* h = new garlic_gpu;
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return 3;
+    }
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
+    cudaMalloc((void**)&h->d_cnt, 4 * sizeof(unsigned));
+    *out = h;
+    return 0;
+}
+
+void garlic_gpu_destroy(garlic_gpu_t* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    dev_free(h->d_alleles); dev_free(h->d_key); dev_free(h->d_geno0); dev_free(h->d_geno); dev_free(h->d_counts);
+    dev_free(h->d_gl0); dev_free(h->d_gl); dev_free(h->d_freq0); dev_free(h->d_freq); dev_free(h->d_lut);
+    dev_free(h->d_gpos); dev_free(h->d_nomut); dev_free(h->d_norec); dev_free(h->d_wlut); dev_free(h->d_invld);
+    dev_free(h->d_homf); dev_free(h->d_keep); dev_free(h->d_src); dev_free(h->d_pos0); dev_free(h->d_chr_of0);
+    dev_free(h->d_pos); dev_free(h->d_chr_of); dev_free(h->d_chr_start); dev_free(h->d_chr_param);
+    dev_free(h->d_out); dev_free(h->d_amb); dev_free(h->d_cnt); dev_free(h->d_items); dev_free(h->d_indlist);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* garlic_gpu_last_error(const garlic_gpu_t* h) { return h ? h->err.c_str() : "null handle"; }
+uint64_t garlic_gpu_launch_count(const garlic_gpu_t* h) { return h ? h->launches : 0; }
+void* garlic_gpu_stream(const garlic_gpu_t* h) { return h ? (void*)h->stream : nullptr; }
+int garlic_gpu_sync(garlic_gpu_t* h)
+{
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int garlic_gpu_set_shape(garlic_gpu_t* h, int n_ind, int ind_offset, int64_t n_loci, int n_chr,
+                         const int64_t* chr_offsets, const int32_t* pos)
+{
+    if (!h) return 1;
+    CK(cudaSetDevice(h->device));
+    if (n_ind < 1 || n_loci < 1 || n_chr < 1) FAIL("set_shape: number of individuals, loci and chromosomes must be positive");
+    if (n_loci > 0x7ffffff0ll - kPad) FAIL("set_shape: too many loci");
+    if (chr_offsets[0] != 0 || chr_offsets[n_chr] != n_loci) FAIL("set_shape: chr_offsets must span [0, n_loci]");
+    h->n_ind = n_ind; h->ind_offset = ind_offset; h->L0 = n_loci; h->n_chr = n_chr;
+    h->chr_off0.assign(chr_offsets, chr_offsets + n_chr + 1);
+    h->pos0.assign(pos, pos + n_loci);
+    h->row_words0 = ((n_loci + kPad + 31) >> 5) + 2;
+    if (dev_alloc(h, &h->d_geno0, (size_t)n_ind * h->row_words0)) return 1;
+    CK(cudaMemsetAsync(h->d_geno0, 0xff, (size_t)n_ind * h->row_words0 * 8, h->stream));
+    if (dev_alloc(h, &h->d_counts, (size_t)4 * n_loci)) return 1;
+    CK(cudaMemsetAsync(h->d_counts, 0, (size_t)4 * n_loci * sizeof(int), h->stream));
+    if (dev_alloc(h, &h->d_pos0, (size_t)n_loci)) return 1;
+    CK(cudaMemcpyAsync(h->d_pos0, pos, n_loci * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    std::vector<int> chr_of(n_loci);
+    for (int c = 0; c < n_chr; ++c)
+        for (int64_t s = chr_offsets[c]; s < chr_offsets[c + 1]; ++s) chr_of[s] = c;
+    if (dev_alloc(h, &h->d_chr_of0, (size_t)n_loci)) return 1;
+    CK(cudaMemcpyAsync(h->d_chr_of0, chr_of.data(), n_loci * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_geno0 = false; h->filtered = false; h->tables = false; h->have_gl = false; h->have_ld = false;
+    dev_free(h->d_alleles); dev_free(h->d_key);
+    return 0;
+}
+
+int garlic_gpu_put_alleles(garlic_gpu_t* h, const uint8_t* alleles, int64_t snp0, int n_snp, char missing)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->L0) FAIL("put_alleles: call set_shape first");
+    if (snp0 % 32 != 0 || snp0 < 0 || snp0 + n_snp > h->L0) FAIL("put_alleles: bad SNP range (snp0 must be a multiple of 32)");
+    if (!h->d_alleles) {
+        if (dev_alloc(h, &h->d_alleles, (size_t)h->L0 * h->n_ind * 2)) return 1;
+        if (dev_alloc(h, &h->d_key, (size_t)h->L0)) return 1;
+    }
+    uint8_t* dst = h->d_alleles + (size_t)snp0 * h->n_ind * 2;
+    CK(cudaMemcpyAsync(dst, alleles, (size_t)n_snp * h->n_ind * 2, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(launch_first_allele(dst, n_snp, h->n_ind, h->ind_offset, (unsigned char)missing, h->d_key + snp0, h->stream));
+    h->missing_char = (unsigned char)missing;
+    return 0;
+}
+
+void* garlic_gpu_first_allele_keys_dev(garlic_gpu_t* h) { return h ? (void*)h->d_key : nullptr; }
+
+int garlic_gpu_code_alleles(garlic_gpu_t* h)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->d_alleles) FAIL("code_alleles: no alleles uploaded");
+    const int missing = h->missing_char;
+    CK(cudaMemsetAsync(h->d_counts, 0, (size_t)4 * h->L0 * sizeof(int), h->stream));
+    // chunks of SNPs so the grid stays within limits; all chunks start on a 32-SNP boundary
+    const int64_t chunk = 1 << 20;
+    for (int64_t s0 = 0; s0 < h->L0; s0 += chunk) {
+        const int n = (int)std::min<int64_t>(chunk, h->L0 - s0);
+        LAUNCH(launch_code_alleles(h->d_alleles + (size_t)s0 * h->n_ind * 2, n, h->n_ind, missing, h->d_key + s0, s0,
+                                   h->d_geno0, h->row_words0, h->d_counts, h->L0, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_geno0 = true;
+    return 0;
+}
+
+static int put_packed_common(garlic_gpu* h, const void* rows, int64_t stride, cudaMemcpyKind kind)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->L0) FAIL("put_packed: call set_shape first");
+    const int64_t need = (h->L0 + 3) / 4;
+    if (stride < need) FAIL("put_packed: row stride smaller than ceil(n_loci/4)");
+    CK(cudaMemcpy2DAsync(h->d_geno0, (size_t)h->row_words0 * 8, rows, (size_t)stride, (size_t)need, (size_t)h->n_ind, kind, h->stream));
+    // bits of the last partial word beyond n_loci may hold anything; they are never read as SNPs < L0
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_geno0 = true;
+    return 0;
+}
+
+int garlic_gpu_put_packed(garlic_gpu_t* h, const uint8_t* rows, int64_t row_stride_bytes)
+{
+    return put_packed_common(h, rows, row_stride_bytes, cudaMemcpyHostToDevice);
+}
+int garlic_gpu_put_packed_dev(garlic_gpu_t* h, const void* rows_dev, int64_t row_stride_bytes)
+{
+    return put_packed_common(h, rows_dev, row_stride_bytes, cudaMemcpyDeviceToDevice);
+}
+
+// adds host correction vectors to device counts
+__global__ void add_corr_kernel(int* counts, long long L0, const int* na, const int* tot)
+{
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < L0; s += (long long)gridDim.x * blockDim.x) {
+        if (na) counts[s] += na[s];
+        if (tot) counts[L0 + s] += tot[s];
+    }
+}
+
+int garlic_gpu_count_packed(garlic_gpu_t* h, const int32_t* nalleles_corr, const int32_t* total_corr)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->have_geno0) FAIL("count_packed: no genotypes loaded");
+    CK(cudaMemsetAsync(h->d_counts, 0, (size_t)4 * h->L0 * sizeof(int), h->stream));
+    LAUNCH(launch_count_packed(h->d_geno0, h->row_words0, h->n_ind, h->L0, h->d_counts, h->stream));
+    if (nalleles_corr || total_corr) {
+        int *d_a = nullptr, *d_t = nullptr;
+        if (nalleles_corr) { CK(cudaMalloc(&d_a, h->L0 * sizeof(int))); CK(cudaMemcpyAsync(d_a, nalleles_corr, h->L0 * sizeof(int), cudaMemcpyHostToDevice, h->stream)); }
+        if (total_corr) { CK(cudaMalloc(&d_t, h->L0 * sizeof(int))); CK(cudaMemcpyAsync(d_t, total_corr, h->L0 * sizeof(int), cudaMemcpyHostToDevice, h->stream)); }
+        add_corr_kernel<<<(unsigned)std::min<int64_t>((h->L0 + 255) / 256, 148 * 16), 256, 0, h->stream>>>(h->d_counts, h->L0, d_a, d_t);
+        CK(cudaGetLastError());
+        h->launches++;
+        CK(cudaStreamSynchronize(h->stream));
+        if (d_a) cudaFree(d_a);
+        if (d_t) cudaFree(d_t);
+    }
+    return 0;
+}
+
+void* garlic_gpu_counts_dev(garlic_gpu_t* h) { return h ? (void*)h->d_counts : nullptr; }
+
+int garlic_gpu_get_counts(garlic_gpu_t* h, int32_t* na, int32_t* tot, int32_t* hom, int32_t* nm)
+{
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    int32_t* dst[4] = {na, tot, hom, nm};
+    for (int c = 0; c < 4; ++c)
+        if (dst[c]) CK(cudaMemcpy(dst[c], h->d_counts + (size_t)c * h->L0, h->L0 * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int garlic_gpu_get_one_allele(garlic_gpu_t* h, uint8_t* allele, char missing)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->d_key) FAIL("get_one_allele: alleles were not ingested on this handle");
+    std::vector<unsigned long long> k(h->L0);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(k.data(), h->d_key, h->L0 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int64_t s = 0; s < h->L0; ++s) allele[s] = (k[s] == ~0ull) ? (uint8_t)missing : (uint8_t)(k[s] & 0xff);
+    return 0;
+}
+
+static int put_gl_common(garlic_gpu* h, const void* v, int gl_type, cudaMemcpyKind kind)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->L0) FAIL("put_gl: call set_shape first");
+    if (gl_type < -1 || gl_type > 2) FAIL("put_gl: bad gl_type");
+    if (dev_alloc(h, &h->d_gl0, (size_t)h->n_ind * h->L0)) return 1;
+    CK(cudaMemcpyAsync(h->d_gl0, v, (size_t)h->n_ind * h->L0 * sizeof(double), kind, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->gl_type = gl_type;
+    h->have_gl = true;
+    return 0;
+}
+int garlic_gpu_put_gl(garlic_gpu_t* h, const double* values, int gl_type) { return put_gl_common(h, values, gl_type, cudaMemcpyHostToDevice); }
+int garlic_gpu_put_gl_dev(garlic_gpu_t* h, const void* values_dev, int gl_type) { return put_gl_common(h, values_dev, gl_type, cudaMemcpyDeviceToDevice); }
+
+int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const double* freq_override,
+                      double* freq_out, uint8_t* keep_out, int64_t* n_kept)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->have_geno0) FAIL("filter: no genotypes loaded");
+    if (oob && !chr_param) FAIL("filter: oob filtering needs chr_param");
+    const int64_t L0 = h->L0;
+    if (dev_alloc(h, &h->d_freq0, (size_t)L0)) return 1;
+    if (dev_alloc(h, &h->d_keep, (size_t)L0)) return 1;
+    if (oob) {
+        if (dev_alloc(h, &h->d_chr_param, (size_t)4 * h->n_chr)) return 1;
+        CK(cudaMemcpyAsync(h->d_chr_param, chr_param, 4 * h->n_chr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
+    std::vector<double> freq0(L0);
+    std::vector<uint8_t> keep(L0);
+    if (freq_override) {
+        // --freq-file: frequencies come from the caller; the predicate is evaluated on the host copy
+        for (int64_t s = 0; s < L0; ++s) {
+            const double f = freq_override[s];
+            bool k = (f > 0 && f < 1);
+            if (oob) {
+                int c = (int)(std::upper_bound(h->chr_off0.begin(), h->chr_off0.end(), s) - h->chr_off0.begin()) - 1;
+                const int32_t* cp = chr_param + 4 * c;
+                const int p = h->pos0[s];
+                k = k && !(p < cp[0]) && !(p > cp[1]) && !(p > cp[2] && p < cp[3]);
+            }
+            freq0[s] = f; keep[s] = k;
+        }
+        CK(cudaMemcpyAsync(h->d_freq0, freq0.data(), L0 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        LAUNCH(launch_freq_keep(h->d_counts, L0, h->d_pos0, h->d_chr_of0, h->d_chr_param, oob, h->d_freq0, h->d_keep, h->stream));
+        CK(cudaMemcpyAsync(freq0.data(), h->d_freq0, L0 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(keep.data(), h->d_keep, L0, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (freq_out) memcpy(freq_out, freq0.data(), L0 * sizeof(double));
+    if (keep_out) memcpy(keep_out, keep.data(), L0);
+    // exclusive scan of the keep mask → gather list, per-chromosome offsets (host: O(L0) integers)
+    h->src.clear();
+    h->chr_off.assign(h->n_chr + 1, 0);
+    for (int c = 0; c < h->n_chr; ++c) {
+        for (int64_t s = h->chr_off0[c]; s < h->chr_off0[c + 1]; ++s)
+            if (keep[s]) h->src.push_back((int32_t)s);
+        h->chr_off[c + 1] = (int64_t)h->src.size();
+    }
+    h->L = (int64_t)h->src.size();
+    if (n_kept) *n_kept = h->L;
+    if (h->L < 1) FAIL("filter: no polymorphic loci left");
+    const int64_t L = h->L;
+    h->pos.resize(L);
+    for (int64_t d = 0; d < L; ++d) h->pos[d] = h->pos0[h->src[d]];
+    if (dev_alloc(h, &h->d_src, (size_t)L)) return 1;
+    CK(cudaMemcpyAsync(h->d_src, h->src.data(), L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    h->row_words = ((L + kPad + 31) >> 5) + 2;
+    if (dev_alloc(h, &h->d_geno, (size_t)h->n_ind * h->row_words)) return 1;
+    CK(cudaMemsetAsync(h->d_geno, 0xff, (size_t)h->n_ind * h->row_words * 8, h->stream));
+    LAUNCH(launch_compact_geno(h->d_geno0, h->row_words0, h->d_src, L, h->d_geno, h->row_words, h->n_ind, h->stream));
+    if (dev_alloc(h, &h->d_freq, (size_t)L + kPad)) return 1;
+    CK(cudaMemsetAsync(h->d_freq, 0, (size_t)(L + kPad) * sizeof(double), h->stream));
+    LAUNCH(launch_gather_f64(h->d_freq0, h->d_src, L, h->d_freq, h->stream));
+    if (h->have_gl) {
+        h->gl_stride = L + kPad;
+        if (dev_alloc(h, &h->d_gl, (size_t)h->n_ind * h->gl_stride)) return 1;
+        CK(cudaMemsetAsync(h->d_gl, 0, (size_t)h->n_ind * h->gl_stride * sizeof(double), h->stream));
+        LAUNCH(launch_compact_gl(h->d_gl0, L0, h->d_src, L, h->d_gl, h->gl_stride, h->n_ind, h->gl_type, h->stream));
+    }
+    // per-SNP position / chromosome arrays of the kept SNPs
+    std::vector<int> chr_of(L), chr_start(h->n_chr);
+    for (int c = 0; c < h->n_chr; ++c) {
+        chr_start[c] = (int)h->chr_off[c];
+        for (int64_t d = h->chr_off[c]; d < h->chr_off[c + 1]; ++d) chr_of[d] = c;
+    }
+    if (dev_alloc(h, &h->d_pos, (size_t)L)) return 1;
+    if (dev_alloc(h, &h->d_chr_of, (size_t)L)) return 1;
+    if (dev_alloc(h, &h->d_chr_start, (size_t)h->n_chr)) return 1;
+    CK(cudaMemcpyAsync(h->d_pos, h->pos.data(), L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_chr_of, chr_of.data(), L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_chr_start, chr_start.data(), h->n_chr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->filtered = true; h->tables = false; h->have_ld = false;
+    return 0;
+}
+
+int64_t garlic_gpu_n_kept(const garlic_gpu_t* h) { return h ? h->L : 0; }
+
+int garlic_gpu_get_genotypes(garlic_gpu_t* h, int filtered, uint8_t* rows, int64_t row_stride_bytes)
+{
+    CK(cudaSetDevice(h->device));
+    if (filtered ? !h->filtered : !h->have_geno0) FAIL("get_genotypes: nothing loaded");
+    const int64_t n = filtered ? h->L : h->L0;
+    const int64_t need = (n + 3) / 4;
+    if (row_stride_bytes < need) FAIL("get_genotypes: row stride too small");
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy2D(rows, (size_t)row_stride_bytes, filtered ? h->d_geno : h->d_geno0,
+                    (size_t)(filtered ? h->row_words : h->row_words0) * 8, (size_t)need, (size_t)h->n_ind, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int garlic_gpu_get_kept_index(garlic_gpu_t* h, int32_t* src_index)
+{
+    if (!h->filtered) FAIL("get_kept_index: call filter first");
+    memcpy(src_index, h->src.data(), h->L * sizeof(int32_t));
+    return 0;
+}
+
+int garlic_gpu_set_tables(garlic_gpu_t* h, double error, int max_gap, const int32_t* centromeres, const double* gpos)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->filtered) FAIL("set_tables: call filter first");
+    h->error = error; h->max_gap = max_gap;
+    h->cen.assign(2 * h->n_chr, 0);
+    if (centromeres) h->cen.assign(centromeres, centromeres + 2 * h->n_chr);
+    const int64_t L = h->L;
+    if (dev_alloc(h, &h->d_lut, (size_t)(L + kPad) * 4)) return 1;
+    CK(cudaMemsetAsync(h->d_lut, 0, (size_t)(L + kPad) * 4 * sizeof(double), h->stream));
+    LAUNCH(launch_build_lut(h->d_freq, L, error, h->d_lut, h->stream));
+    h->gpos.clear();
+    if (gpos) {
+        h->gpos.assign(gpos, gpos + L);
+        if (dev_alloc(h, &h->d_gpos, (size_t)L)) return 1;
+        CK(cudaMemcpyAsync(h->d_gpos, gpos, L * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    // bound on |LOD| for the ambiguity tolerance: with a global error the largest magnitudes are
+    // log10(error) (heterozygote) and log10 of 1/f-type terms; freq ∈ [1/(2N_total), 1-1/(2N_total)]
+    h->amax = 20.0;
+    h->tables = true; h->have_ld = false;
+    return 0;
+}
+
+int garlic_gpu_set_lut(garlic_gpu_t* h, const double* lut)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->tables) FAIL("set_lut: call set_tables first");
+    CK(cudaMemcpy(h->d_lut, lut, (size_t)h->L * 4 * sizeof(double), cudaMemcpyHostToDevice));
+    dev_free(h->d_wlut);   // the weighted score table is rebuilt on demand
+    return 0;
+}
+
+int garlic_gpu_get_lut(garlic_gpu_t* h, double* lut)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->tables) FAIL("get_lut: call set_tables first");
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(lut, h->d_lut, (size_t)h->L * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int garlic_gpu_get_hom_freq(garlic_gpu_t* h, double* hom_freq)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->filtered) FAIL("get_hom_freq: call filter first");
+    std::vector<int> hom(h->L0), nm(h->L0);
+    if (garlic_gpu_get_counts(h, nullptr, nullptr, hom.data(), nm.data())) return 1;
+    for (int64_t d = 0; d < h->L; ++d) {
+        double total = nm[h->src[d]], fh = hom[h->src[d]];
+        fh /= total;   // 0/0 → NaN exactly as the reference (garlic-data.cpp:672)
+        hom_freq[d] = fh;
+    }
+    return 0;
+}
+
+int garlic_gpu_set_wlod(garlic_gpu_t* h, double mu, int M)
+{
+    h->mu = mu; h->M = M;
+    dev_free(h->d_wlut);
+    return 0;
+}
+
+}  // extern "C"
+
+static int upload_items(garlic_gpu* h, const std::vector<Item>& items)
+{
+    if (items.size() > h->items_cap) {
+        if (dev_alloc(h, &h->d_items, items.size() + 1024)) return 1;
+        h->items_cap = items.size() + 1024;
+    }
+    if (!items.empty()) CK(cudaMemcpyAsync(h->d_items, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+static int upload_indlist(garlic_gpu* h, const int32_t* list, int n)
+{
+    if ((size_t)n > h->indlist_cap) {
+        if (dev_alloc(h, &h->d_indlist, (size_t)n + 1024)) return 1;
+        h->indlist_cap = (size_t)n + 1024;
+    }
+    CK(cudaMemcpyAsync(h->d_indlist, list, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+static WalkParams base_params(const garlic_gpu* h, int W)
+{
+    WalkParams P;
+    memset(&P, 0, sizeof(P));
+    P.geno = h->d_geno; P.row_words = h->row_words;
+    P.lut = h->d_lut; P.gl = h->have_gl ? h->d_gl : nullptr; P.freq = h->d_freq; P.gl_stride = h->gl_stride;
+    P.ind_list = nullptr; P.n_lanes = h->n_ind; P.W = W; P.thr = 1; P.cutoff = 0; P.tol = 0;
+    P.out = h->d_out; P.out_count = h->d_cnt; P.out_cap = h->out_cap; P.amb = h->d_amb; P.amb_cap = h->amb_cap;
+    P.dump = nullptr; P.dump_stride = 0; P.dump_step = 1;
+    return P;
+}
+
+static int ensure_weighted(garlic_gpu* h, int W);   // wlod tables + LD band present for this W
+static int launch_any_walk(garlic_gpu* h, const WalkParams& P, const Item* items, int n_items, int weighted, bool roh, bool dump)
+{
+    if (weighted) {
+        WlodParams Q;
+        Q.base = P; Q.wlut = h->d_wlut; Q.invld = h->d_invld; Q.nomut = h->d_nomut; Q.norec = h->d_norec;
+        LAUNCH(launch_wlod_walk(Q, items, n_items, h->have_gl, roh, dump, h->stream));
+    } else {
+        LAUNCH(launch_walk(P, items, n_items, h->have_gl, roh, dump, h->stream));
+    }
+    return 0;
+}
+
+extern "C" {
+
+int64_t garlic_gpu_window_slots(garlic_gpu_t* h, int step)
+{
+    if (!h || !h->filtered || step < 1) return -1;
+    int64_t n = 0;
+    for (int c = 0; c < h->n_chr; ++c) n += (h->chr_off[c + 1] - h->chr_off[c] + step - 1) / step;
+    return n;
+}
+
+int garlic_gpu_windows(garlic_gpu_t* h, int winsize, int step, int weighted, const int32_t* individuals, int n,
+                       int exact, double* out)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->tables) FAIL("windows: call set_tables first");
+    if (winsize < 2 || winsize > kMaxW) FAIL("windows: winsize out of range [2,4096]");
+    if (step < 1) FAIL("windows: step must be >= 1");
+    if (weighted && ensure_weighted(h, winsize)) return 1;
+    const int W = winsize;
+    const int n_lanes = individuals ? n : h->n_ind;
+    if (individuals) {
+        for (int i = 0; i < n; ++i) if (individuals[i] < 0 || individuals[i] >= h->n_ind) FAIL("windows: individual index out of range");
+        if (upload_indlist(h, individuals, n)) return 1;
+    }
+    std::vector<Segment> segs;
+    std::vector<Item> items;
+    build_segments(h->chr_off, h->pos, h->cen, h->max_gap, W, segs);
+    int chunk = 0;
+    if (weighted) chunk = std::max(64, pick_chunk(h->L, W, n_lanes) / 8);   // every wLOD window is a fresh sum
+    else if (!exact) chunk = pick_chunk(h->L, W, n_lanes);
+    build_items(h->chr_off, W, segs, chunk, step, items);
+    if (upload_items(h, items)) return 1;
+    const int64_t slots = garlic_gpu_window_slots(h, step);
+    double* d_dump = nullptr;
+    CK(cudaMalloc(&d_dump, (size_t)n_lanes * slots * sizeof(double)));
+    LAUNCH(launch_fill_f64(d_dump, (size_t)n_lanes * slots, kMissing, h->stream));
+    WalkParams P = base_params(h, W);
+    P.ind_list = individuals ? h->d_indlist : nullptr;
+    P.n_lanes = n_lanes;
+    P.cutoff = 0; P.thr = 1; P.tol = 0;
+    P.dump = d_dump; P.dump_stride = slots; P.dump_step = step;
+    CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
+    int rc = launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, false, true);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(out, d_dump, (size_t)n_lanes * slots * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { h->err = std::string("windows: ") + cudaGetErrorString(e); rc = 1; }
+    }
+    cudaFree(d_dump);
+    return rc;
+}
+
+int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double overlap_frac, int weighted, int exact,
+                        garlic_roh_t* out, int64_t cap, int64_t* count)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->tables) FAIL("call_roh: call set_tables first");
+    if (winsize < 2 || winsize > kMaxW) FAIL("call_roh: winsize out of range [2,4096]");
+    if (weighted && ensure_weighted(h, winsize)) return 1;
+    const int W = winsize;
+    // garlic-roh.cpp:422-424, compared against integers at :466 and :477
+    double thr_d = overlap_frac * W;
+    thr_d = (thr_d >= 1) ? thr_d : 1;
+    thr_d = (thr_d <= W) ? thr_d : W;
+    const int thr = (int)std::ceil(thr_d);
+
+    std::vector<Segment> segs;
+    std::vector<Item> items;
+    build_segments(h->chr_off, h->pos, h->cen, h->max_gap, W, segs);
+    int chunk = 0;
+    if (weighted) chunk = std::max(64, pick_chunk(h->L, W, h->n_ind) / 8);
+    else if (!exact) chunk = pick_chunk(h->L, W, h->n_ind);
+    build_items(h->chr_off, W, segs, chunk, 0, items);
+    if (upload_items(h, items)) return 1;
+    int64_t n_win = 0;
+    for (const Segment& s : segs) n_win += s.we - s.ws;
+    // note: the reference also "evaluates" invalid window starts (they come out MISSING); the unit
+    // of work N·Σ_c(L_c-W+1) counts those too
+    int64_t units = 0;
+    for (int c = 0; c < h->n_chr; ++c) units += std::max<int64_t>(0, h->chr_off[c + 1] - h->chr_off[c] - W + 1);
+    units *= h->n_ind;
+
+    if (!h->d_out) {
+        h->out_cap = 1u << 22;
+        if (dev_alloc(h, &h->d_out, h->out_cap)) return 1;
+        h->amb_cap = 1u << 16;
+        if (dev_alloc(h, &h->d_amb, h->amb_cap)) return 1;
+    }
+    std::vector<RohRec> recs, ambs;
+    float ms = 0;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        WalkParams P = base_params(h, W);
+        P.cutoff = cutoff; P.thr = thr;
+        if (!exact && !weighted) {
+            // |fast − reference chain| ≤ (chain length + 2W)·2·2^-53·(W+1)·amax — see DESIGN.md §6
+            int64_t longest = 0;
+            for (const Segment& s : segs) longest = std::max<int64_t>(longest, s.we - s.ws);
+            P.tol = (double)(longest + 2 * W) * 2.220446049250313e-16 * (W + 1) * h->amax;
+        }
+        CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
+        CK(cudaEventRecord(h->ev0, h->stream));
+        if (launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, true, false)) return 1;
+        CK(cudaEventRecord(h->ev1, h->stream));
+        unsigned cnt[4];
+        CK(cudaMemcpyAsync(cnt, h->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        if (cnt[0] > h->out_cap) {
+            h->out_cap = cnt[0] + cnt[0] / 4 + 1024;
+            if (dev_alloc(h, &h->d_out, h->out_cap)) return 1;
+            continue;
+        }
+        if (cnt[1] > h->amb_cap) {   // pathological: (nearly) everything ambiguous → exact everywhere
+            exact = 1;
+            build_items(h->chr_off, W, segs, 0, 0, items);
+            if (upload_items(h, items)) return 1;
+            continue;
+        }
+        recs.resize(cnt[0]);
+        ambs.resize(cnt[1]);
+        if (cnt[0]) CK(cudaMemcpy(recs.data(), h->d_out, cnt[0] * sizeof(RohRec), cudaMemcpyDeviceToHost));
+        if (cnt[1]) CK(cudaMemcpy(ambs.data(), h->d_amb, cnt[1] * sizeof(RohRec), cudaMemcpyDeviceToHost));
+        break;
+    }
+    // exact re-evaluation of (individual, segment) pairs that had a window within rounding
+    // distance of the cutoff: one whole-segment launch per distinct segment
+    int64_t n_amb_pairs = 0;
+    if (!ambs.empty()) {
+        std::map<int, std::vector<int>> by_seg;
+        for (const RohRec& a : ambs) by_seg[a.tag].push_back(a.ind);
+        std::vector<RohRec> fixed;
+        for (auto& kv : by_seg) {
+            std::vector<int>& inds = kv.second;
+            std::sort(inds.begin(), inds.end());
+            inds.erase(std::unique(inds.begin(), inds.end()), inds.end());
+            n_amb_pairs += (int64_t)inds.size();
+            std::vector<Segment> one(1, segs[kv.first]);
+            std::vector<Item> its;
+            build_items(h->chr_off, W, one, 0, 0, its);
+            its[0].seg = kv.first;
+            if (upload_items(h, its)) return 1;
+            if (upload_indlist(h, inds.data(), (int)inds.size())) return 1;
+            WalkParams P = base_params(h, W);
+            P.cutoff = cutoff; P.thr = thr; P.tol = 0;
+            P.ind_list = h->d_indlist; P.n_lanes = (int)inds.size();
+            CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
+            if (launch_any_walk(h, P, h->d_items, 1, weighted, true, false)) return 1;
+            unsigned cnt[4];
+            CK(cudaMemcpyAsync(cnt, h->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            if (cnt[0] > h->out_cap) FAIL("call_roh: ROH buffer overflow during exact re-evaluation");
+            const size_t base = fixed.size();
+            fixed.resize(base + cnt[0]);
+            if (cnt[0]) CK(cudaMemcpy(fixed.data() + base, h->d_out, cnt[0] * sizeof(RohRec), cudaMemcpyDeviceToHost));
+            // drop the fast pass's records of these pairs
+            recs.erase(std::remove_if(recs.begin(), recs.end(), [&](const RohRec& r) {
+                return (r.tag >> 2) == kv.first && std::binary_search(inds.begin(), inds.end(), r.ind);
+            }), recs.end());
+        }
+        recs.insert(recs.end(), fixed.begin(), fixed.end());
+    }
+    // sort by (individual, start) and stitch runs that were cut at chunk boundaries
+    std::vector<RohRec> merged;
+    stitch_runs(recs, thr, merged);
+    const int64_t n_out = (int64_t)merged.size();
+    for (int64_t r = 0; r < n_out && r < cap && out; ++r) {
+        out[r].ind = merged[r].ind;
+        out[r].chr = segs[merged[r].tag >> 2].chr;
+        out[r].start_idx = merged[r].a;
+        out[r].stop_idx = merged[r].b;
+    }
+    if (count) *count = n_out;
+    h->stats[0] = (double)items.size();
+    h->stats[1] = (double)units;
+    h->stats[2] = (double)n_amb_pairs;
+    h->stats[3] = ms;
+    return 0;
+}
+
+int garlic_gpu_last_stats(garlic_gpu_t* h, double* s)
+{
+    for (int i = 0; i < 4; ++i) s[i] = h->stats[i];
+    return 0;
+}
+
+int garlic_gpu_ld_band(garlic_gpu_t* h, int winsize, const int32_t* ld_individuals, int n_ld, double* out_ld)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->tables) FAIL("ld_band: call set_tables first");
+    if (winsize < 2 || winsize > kMaxW) FAIL("ld_band: winsize out of range [2,4096]");
+    const int64_t L = h->L;
+    const int W = winsize;
+    std::vector<int> all;
+    if (!ld_individuals) {
+        all.resize(h->n_ind);
+        for (int i = 0; i < h->n_ind; ++i) all[i] = i;
+        ld_individuals = all.data(); n_ld = h->n_ind;
+    }
+    for (int i = 0; i < n_ld; ++i) if (ld_individuals[i] < 0 || ld_individuals[i] >= h->n_ind) FAIL("ld_band: individual index out of range");
+    if (upload_indlist(h, ld_individuals, n_ld)) return 1;
+    // homFreq over ALL individuals from the reduced counts (garlic-data.cpp:656-676)
+    std::vector<double> homf(L);
+    if (garlic_gpu_get_hom_freq(h, homf.data())) return 1;
+    if (dev_alloc(h, &h->d_homf, (size_t)L)) return 1;
+    CK(cudaMemcpyAsync(h->d_homf, homf.data(), L * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (dev_alloc(h, &h->d_invld, (size_t)(L + kPad) * W)) return 1;
+    double* d_ld = nullptr;
+    if (out_ld) CK(cudaMalloc(&d_ld, (size_t)L * W * sizeof(double)));
+    int launches = 0;
+    cudaError_t e = launch_ld_band(h->d_geno, h->row_words, h->d_indlist, n_ld, h->d_homf, h->d_chr_of, h->d_chr_start,
+                                   h->n_chr, L, W, h->d_invld, d_ld, h->stream, &launches);
+    h->launches += launches;
+    if (e != cudaSuccess) { if (d_ld) cudaFree(d_ld); h->err = std::string("ld_band: ") + cudaGetErrorString(e); return 1; }
+    if (out_ld) {
+        e = cudaMemcpyAsync(out_ld, d_ld, (size_t)L * W * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        cudaFree(d_ld);
+        if (e != cudaSuccess) { h->err = std::string("ld_band: ") + cudaGetErrorString(e); return 1; }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_ld = true; h->ld_W = W;
+    return 0;
+}
+
+}  // extern "C"
+
+static int ensure_weighted(garlic_gpu* h, int W)
+{
+    if (h->gpos.empty()) FAIL("weighted: genetic positions were not given to set_tables");
+    if (!h->have_ld || h->ld_W != W) FAIL("weighted: call ld_band with this window size first");
+    if (!h->d_wlut) {
+        const int64_t L = h->L;
+        if (dev_alloc(h, &h->d_nomut, (size_t)L + kPad)) return 1;
+        if (dev_alloc(h, &h->d_norec, (size_t)L + kPad)) return 1;
+        CK(cudaMemsetAsync(h->d_nomut, 0, (size_t)(L + kPad) * sizeof(double), h->stream));
+        CK(cudaMemsetAsync(h->d_norec, 0, (size_t)(L + kPad) * sizeof(double), h->stream));
+        LAUNCH(launch_wlod_weights(h->d_pos, h->d_gpos, h->d_chr_of, h->d_chr_start, L, h->mu, h->M, h->d_nomut, h->d_norec, h->stream));
+        if (dev_alloc(h, &h->d_wlut, (size_t)(L + kPad) * 4)) return 1;
+        CK(cudaMemsetAsync(h->d_wlut, 0, (size_t)(L + kPad) * 4 * sizeof(double), h->stream));
+        LAUNCH(launch_build_wlut(h->d_lut, h->d_nomut, h->d_norec, L, h->d_wlut, h->stream));
+    }
+    return 0;
+}

@@ -1,0 +1,477 @@
+// kernels.cu — hand-written sm_100a kernels for the GARLIC LOD/wLOD → ROH hot path.
+// Kernel inventory: K1 code_alleles, K2 count_packed, K3 compact_*, K4 build_lut,
+// K5 walk (fused windows→ROH / window dump), K6 ld_pairs + ld_band, K5-W wlod_walk.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+#include "walk.cuh"
+#include "kernels.h"
+
+namespace garlic {
+
+// ------------------------------------------------------------------------------------------
+// K5: fused windows → ROH.  One warp = 32 individuals walking one item in lock-step (so every
+// LUT read of a step is a single 32-byte sector shared by the warp); a CTA's warps take
+// neighbouring individual groups of the SAME item, consecutive CTAs take the same item too,
+// so the item's LUT range and genotype words stay L1/L2-resident.
+// ------------------------------------------------------------------------------------------
+template <int SRC, bool ROH, bool DUMP>
+__global__ void __launch_bounds__(128)
+walk_kernel(const WalkParams P, const Item* __restrict__ items, int n_items, int n_groups)
+{
+    extern __shared__ uint32_t ring_smem[];   // [NW][blockDim.x] window-flag history
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gpb = blockDim.x >> 5;
+    const int gblocks = (n_groups + gpb - 1) / gpb;
+    const long long total = (long long)n_items * gblocks;
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const int item = (int)(u / gblocks);
+        const int group = (int)(u % gblocks) * gpb + warp;
+        if (group >= n_groups) continue;
+        const int k = group * 32 + lane;
+        const bool active = k < P.n_lanes;
+        const Item it = items[item];
+        walk_item<SRC, ROH, DUMP>(P, it, active ? k : P.n_lanes - 1, active, ring_smem + threadIdx.x,
+                                  blockDim.x);
+    }
+}
+
+template <int SRC, bool ROH, bool DUMP>
+static cudaError_t launch_walk_t(const WalkParams& P, const Item* items, int n_items, cudaStream_t st)
+{
+    if (n_items == 0 || P.n_lanes == 0) return cudaSuccess;
+    const int threads = 128;
+    const int n_groups = (P.n_lanes + 31) / 32;
+    const int gpb = threads / 32;
+    const long long total = (long long)n_items * ((n_groups + gpb - 1) / gpb);
+    const int NW = ((P.W + 31) >> 5) + 1;
+    const size_t smem = (size_t)NW * threads * sizeof(uint32_t);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long grid = total;
+    const long long cap = (long long)sms * 16 * 8;   // persistent-ish: ≤ 8 waves of 16 CTAs/SM
+    if (grid > cap) grid = cap;
+    walk_kernel<SRC, ROH, DUMP><<<(unsigned)grid, threads, smem, st>>>(P, items, n_items, n_groups);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_walk(const WalkParams& P, const Item* items, int n_items, bool gl_mode, bool roh,
+                        bool dump, cudaStream_t st)
+{
+    if (gl_mode) {
+        if (roh && !dump) return launch_walk_t<1, true, false>(P, items, n_items, st);
+        if (!roh && dump) return launch_walk_t<1, false, true>(P, items, n_items, st);
+        return launch_walk_t<1, true, true>(P, items, n_items, st);
+    }
+    if (roh && !dump) return launch_walk_t<0, true, false>(P, items, n_items, st);
+    if (!roh && dump) return launch_walk_t<0, false, true>(P, items, n_items, st);
+    return launch_walk_t<0, true, true>(P, items, n_items, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// fill
+// ------------------------------------------------------------------------------------------
+__global__ void fill_f64_kernel(double* p, size_t n, double v)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+cudaError_t launch_fill_f64(double* p, size_t n, double v, cudaStream_t st)
+{
+    if (!n) return cudaSuccess;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    fill_f64_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, n, v);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: genotype coding from allele characters (garlic-data.cpp:105-133), two phases so that the
+// "1" allele (first non-missing character in file order over ALL individuals) can be min-reduced
+// across GPUs between them.
+//   phase a: per SNP key = min over local calls of ((global_call_index << 8) | char)
+//   phase b: code each call, count nalleles / total (half-missing calls count their present
+//            allele, :115-127), and transpose into the individual-major 2-bit matrix.
+// alleles: [n_snp][n_ind][2] bytes (one tped line per SNP).
+// ------------------------------------------------------------------------------------------
+__global__ void first_allele_kernel(const uint8_t* __restrict__ alleles, int n_snp, int n_ind,
+                                    int ind_offset, int missing, unsigned long long* __restrict__ key)
+{
+    // one warp per SNP; lanes stride over the 2*n_ind allele characters
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (long long s = blockIdx.x * (long long)warps_per_block + (threadIdx.x >> 5); s < n_snp;
+         s += (long long)gridDim.x * warps_per_block) {
+        const uint8_t* a = alleles + (size_t)s * n_ind * 2;
+        unsigned long long best = ~0ull;
+        for (int c = lane; c < 2 * n_ind; c += 32) {
+            const uint8_t ch = a[c];
+            if (ch != missing) {
+                best = (((unsigned long long)(2ll * ind_offset + c)) << 8) | ch;
+                break;   // lanes visit their calls in ascending order
+            }
+        }
+        for (int o = 16; o; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other < best ? other : best;
+        }
+        if (lane == 0) key[s] = best;
+    }
+}
+
+cudaError_t launch_first_allele(const uint8_t* alleles, int n_snp, int n_ind, int ind_offset, int missing,
+                                unsigned long long* key, cudaStream_t st)
+{
+    if (!n_snp) return cudaSuccess;
+    int blocks = (n_snp + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    first_allele_kernel<<<blocks, 256, 0, st>>>(alleles, n_snp, n_ind, ind_offset, missing, key);
+    return cudaGetLastError();
+}
+
+// phase b.  Tile = 32 SNPs (one 64-bit packed word per individual) × 32 individuals per warp pass.
+// Block = 256 threads = 8 warps; block handles SNPs [32*blockIdx.x, +32) and loops individuals.
+// counts: [4][L0] int32 = nalleles, total, hom(g∈{0,2}), nonmiss.
+__global__ void __launch_bounds__(256)
+code_alleles_kernel(const uint8_t* __restrict__ alleles, int n_snp, int n_ind, int missing,
+                    const unsigned long long* __restrict__ key, long long snp0,
+                    uint64_t* __restrict__ geno, int64_t row_words, int* __restrict__ counts, long long L0)
+{
+    __shared__ uint8_t tile[32][257];          // [snp][ind-in-chunk] genotype codes, padded
+    __shared__ int s_cnt[4][32];
+    const int s_base = blockIdx.x * 32;
+    if (threadIdx.x < 128) s_cnt[threadIdx.x >> 5][threadIdx.x & 31] = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n_ind; i0 += 256) {
+        // code: each thread handles one individual for the 32 SNPs?  no — coalesce on the character
+        // axis: for SNP r, threads read consecutive individuals (2 bytes each)
+        for (int r = 0; r < 32; ++r) {
+            const int s = s_base + r;
+            const int i = i0 + threadIdx.x;
+            uint8_t code = 3;
+            int na = 0, tot = 0;
+            if (s < n_snp && i < n_ind) {
+                const uint16_t two = reinterpret_cast<const uint16_t*>(alleles + (size_t)s * n_ind * 2)[i];
+                const int a1 = two & 0xff, a2 = two >> 8;
+                const unsigned long long k = key[s];
+                const int one = (k == ~0ull) ? missing : (int)(k & 0xff);
+                int d = 0;
+                if (a1 == missing) d = -9; else { tot++; if (a1 == one) { d += 1; na++; } }
+                if (a2 == missing) d += -9; else { tot++; if (a2 == one) { d += 1; na++; } }
+                code = d < 0 ? 3 : (uint8_t)d;
+            }
+            // warp-shuffle reduction of the per-SNP counts (all lanes participate), then one
+            // shared atomic per warp
+            int v_na = na, v_tot = tot, v_hom = (code == 0 || code == 2), v_nm = (code != 3);
+            for (int o = 16; o; o >>= 1) {
+                v_na += __shfl_xor_sync(0xffffffffu, v_na, o);
+                v_tot += __shfl_xor_sync(0xffffffffu, v_tot, o);
+                v_hom += __shfl_xor_sync(0xffffffffu, v_hom, o);
+                v_nm += __shfl_xor_sync(0xffffffffu, v_nm, o);
+            }
+            if ((threadIdx.x & 31) == 0 && v_tot + v_nm + v_hom) {
+                atomicAdd(&s_cnt[0][r], v_na); atomicAdd(&s_cnt[1][r], v_tot);
+                atomicAdd(&s_cnt[2][r], v_hom); atomicAdd(&s_cnt[3][r], v_nm);
+            }
+            tile[r][threadIdx.x] = code;
+        }
+        __syncthreads();
+        // pack: thread = individual; 32 SNP codes → one 64-bit word of its row
+        const int i = i0 + threadIdx.x;
+        if (i < n_ind) {
+            uint64_t w = 0;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) w |= (uint64_t)tile[r][threadIdx.x] << (2 * r);
+            geno[(int64_t)i * row_words + ((snp0 + s_base) >> 5)] = w;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 128) {
+        const int c = threadIdx.x >> 5, r = threadIdx.x & 31;
+        if (s_base + r < n_snp) atomicAdd(&counts[(long long)c * L0 + snp0 + s_base + r], s_cnt[c][r]);
+    }
+}
+
+cudaError_t launch_code_alleles(const uint8_t* alleles, int n_snp, int n_ind, int missing,
+                                const unsigned long long* key, long long snp0, uint64_t* geno,
+                                int64_t row_words, int* counts, long long L0, cudaStream_t st)
+{
+    if (!n_snp) return cudaSuccess;
+    // snp0 must be a multiple of 32 so that tiles map to whole packed words
+    code_alleles_kernel<<<(n_snp + 31) / 32, 256, 0, st>>>(alleles, n_snp, n_ind, missing, key, snp0, geno,
+                                                          row_words, counts, L0);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: per-SNP counts from the packed matrix (pre-coded input path): column reduction over the
+// GPU's individuals.  Block = 32 SNP-words(64-bit) wide × 8 row slices; each thread accumulates
+// bit-sliced partial counts for its word column over its rows, lanes of a warp read 256
+// contiguous bytes of one row (coalesced); the 8 row slices are combined with shared atomics and
+// the grid's row blocks with global atomics.
+// counts: [4][L0] = nalleles (Σ g over g<3), total (2·nonmiss), hom, nonmiss.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+count_packed_kernel(const uint64_t* __restrict__ geno, int64_t row_words, int n_ind, long long L0,
+                    int rows_per_block, int* __restrict__ counts)
+{
+    __shared__ int s_cnt[3][32 * 32];   // [n1,n2,nmiss][snp in tile]
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 3 * 1024; i += 256) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const long long word = (long long)blockIdx.x * 32 + lane;
+    const long long n_words = (L0 + 31) >> 5;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(n_ind, r0 + rows_per_block);
+    if (word < n_words) {
+        // per-SNP byte counters would overflow; flush every 255 rows
+        for (int rb = r0 + slice; rb < r1; rb += 8 * 255) {
+            uint32_t c1[8] = {0}, c2[8] = {0}, cm[8] = {0};   // 32 SNPs × 8-bit counters, 4 per register
+            for (int r = rb, n = 0; r < r1 && n < 255; r += 8, ++n) {
+                const uint64_t w = geno[(int64_t)r * row_words + word];
+                const uint64_t lo = w & 0x5555555555555555ull, hi = (w >> 1) & 0x5555555555555555ull;
+                const uint64_t m1 = lo & ~hi, m2 = hi & ~lo, mm = lo & hi;   // g==1, g==2, missing (at even bits)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    // SNPs 4q..4q+3 → spread their indicator bits (bit positions 8q,8q+2,8q+4,8q+6) to bytes
+                    const uint32_t b1 = (uint32_t)(m1 >> (8 * q)) & 0x55u;
+                    const uint32_t b2 = (uint32_t)(m2 >> (8 * q)) & 0x55u;
+                    const uint32_t bm = (uint32_t)(mm >> (8 * q)) & 0x55u;
+                    c1[q] += (b1 & 1u) | ((b1 & 4u) << 6) | ((b1 & 16u) << 12) | ((b1 & 64u) << 18);
+                    c2[q] += (b2 & 1u) | ((b2 & 4u) << 6) | ((b2 & 16u) << 12) | ((b2 & 64u) << 18);
+                    cm[q] += (bm & 1u) | ((bm & 4u) << 6) | ((bm & 16u) << 12) | ((bm & 64u) << 18);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int snp = lane * 32 + q * 4 + b;
+                    const int v1 = (c1[q] >> (8 * b)) & 0xff, v2 = (c2[q] >> (8 * b)) & 0xff, vm = (cm[q] >> (8 * b)) & 0xff;
+                    if (v1) atomicAdd(&s_cnt[0][snp], v1);
+                    if (v2) atomicAdd(&s_cnt[1][snp], v2);
+                    if (vm) atomicAdd(&s_cnt[2][snp], vm);
+                }
+        }
+    }
+    __syncthreads();
+    const int rows = max(0, r1 - r0);
+    for (int i = threadIdx.x; i < 1024; i += 256) {
+        const long long s = (long long)blockIdx.x * 1024 + i;
+        if (s >= L0) continue;
+        const int n1 = s_cnt[0][i], n2 = s_cnt[1][i], nm = s_cnt[2][i];
+        const int nonmiss = rows - nm;
+        atomicAdd(&counts[0 * L0 + s], n1 + 2 * n2);
+        atomicAdd(&counts[1 * L0 + s], 2 * nonmiss);
+        atomicAdd(&counts[2 * L0 + s], nonmiss - n1);
+        atomicAdd(&counts[3 * L0 + s], nonmiss);
+    }
+}
+
+cudaError_t launch_count_packed(const uint64_t* geno, int64_t row_words, int n_ind, long long L0,
+                                int* counts, cudaStream_t st)
+{
+    if (!n_ind || !L0) return cudaSuccess;
+    const long long n_words = (L0 + 31) >> 5;
+    const unsigned gx = (unsigned)((n_words + 31) / 32);
+    int gy = (int)((148ll * 8 + gx - 1) / gx);          // enough row blocks to fill the machine
+    if (gy < 1) gy = 1;
+    int rpb = (n_ind + gy - 1) / gy;
+    rpb = ((rpb + 7) / 8) * 8;
+    gy = (n_ind + rpb - 1) / rpb;
+    dim3 grid(gx, gy);
+    count_packed_kernel<<<grid, 256, 0, st>>>(geno, row_words, n_ind, L0, rpb, counts);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// freq + keep mask (garlic-data.cpp:141, :968, :1070-1073) from reduced counts.
+// ------------------------------------------------------------------------------------------
+__global__ void freq_keep_kernel(const int* __restrict__ counts, long long L0, const int* __restrict__ pos,
+                                 const int* __restrict__ chr_of, const int* __restrict__ chr_param /*[C][4]*/,
+                                 int oob, double* __restrict__ freq, uint8_t* __restrict__ keep)
+{
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < L0; s += (long long)gridDim.x * blockDim.x) {
+        const int na = counts[s], tot = counts[L0 + s];
+        const double f = (tot == 0) ? 0.0 : ((double)na / (double)tot);
+        freq[s] = f;
+        bool k = (f > 0 && f < 1);
+        if (oob) {
+            const int* cp = chr_param + 4 * chr_of[s];   // scaffold first, last, centromere start, end
+            const int p = pos[s];
+            k = k && !(p < cp[0]) && !(p > cp[1]) && !(p > cp[2] && p < cp[3]);
+        }
+        keep[s] = k;
+    }
+}
+
+cudaError_t launch_freq_keep(const int* counts, long long L0, const int* pos, const int* chr_of,
+                             const int* chr_param, int oob, double* freq, uint8_t* keep, cudaStream_t st)
+{
+    if (!L0) return cudaSuccess;
+    long long blocks = (L0 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    freq_keep_kernel<<<(unsigned)blocks, 256, 0, st>>>(counts, L0, pos, chr_of, chr_param, oob, freq, keep);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: column compaction.  src[d] = pre-filter index of kept SNP d (exclusive scan of the keep
+// mask).  One thread builds one 64-bit output word (32 kept SNPs) of one individual by gathering
+// 2-bit fields; consecutive threads → consecutive words of a row.
+// ------------------------------------------------------------------------------------------
+__global__ void compact_geno_kernel(const uint64_t* __restrict__ gin, int64_t in_words, const int* __restrict__ src,
+                                    long long L, uint64_t* __restrict__ gout, int64_t out_words, int n_ind)
+{
+    const long long n_w = (L + 31) >> 5;
+    const long long total = n_w * n_ind;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / n_w);
+        const long long w = t % n_w;
+        const uint64_t* row = gin + (int64_t)i * in_words;
+        uint64_t o = 0;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const long long d = w * 32 + k;
+            uint64_t g = 3;
+            if (d < L) { const int s = src[d]; g = (row[s >> 5] >> (2 * (s & 31))) & 3ull; }
+            o |= g << (2 * k);
+        }
+        gout[(int64_t)i * out_words + w] = o;
+    }
+}
+
+cudaError_t launch_compact_geno(const uint64_t* gin, int64_t in_words, const int* src, long long L,
+                                uint64_t* gout, int64_t out_words, int n_ind, cudaStream_t st)
+{
+    const long long total = ((L + 31) >> 5) * n_ind;
+    if (!total) return cudaSuccess;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    compact_geno_kernel<<<(unsigned)blocks, 256, 0, st>>>(gin, in_words, src, L, gout, out_words, n_ind);
+    return cudaGetLastError();
+}
+
+// GL rows: gather kept columns and apply the GQ/GL/PL → per-genotype error transform
+// (garlic-data.cpp:1555-1577) in the same pass.  type: 0 GQ, 1 GL, 2 PL, -1 = already an error.
+__device__ __forceinline__ double gl_to_error(double gl, int type)
+{
+    if (type == 0) {
+        gl /= (-10.0);
+        gl = (gl > -10) ? gl : -10;
+        gl = pow(10.0, gl);
+    } else if (type == 1) {
+        gl = (gl > -10) ? gl : -10;
+        gl = 1 - pow(10.0, gl);
+    } else if (type == 2) {
+        gl /= (-10.0);
+        gl = (gl > -10) ? gl : -10;
+        gl = 1 - pow(10.0, gl);
+    } else return gl;
+    if (gl <= 0) gl = 0.0000000000000001;
+    if (gl > 1) gl = 1;
+    return gl;
+}
+
+__global__ void compact_gl_kernel(const double* __restrict__ in, int64_t in_stride, const int* __restrict__ src,
+                                  long long L, double* __restrict__ out, int64_t out_stride, int n_ind, int type)
+{
+    const long long total = L * n_ind;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / L);
+        const long long d = t % L;
+        out[(int64_t)i * out_stride + d] = gl_to_error(in[(int64_t)i * in_stride + src[d]], type);
+    }
+}
+
+cudaError_t launch_compact_gl(const double* in, int64_t in_stride, const int* src, long long L, double* out,
+                              int64_t out_stride, int n_ind, int type, cudaStream_t st)
+{
+    const long long total = L * n_ind;
+    if (!total) return cudaSuccess;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    compact_gl_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, in_stride, src, L, out, out_stride, n_ind, type);
+    return cudaGetLastError();
+}
+
+// gather a per-SNP double / int array through src[]
+__global__ void gather_f64_kernel(const double* in, const int* src, long long L, double* out)
+{
+    for (long long d = blockIdx.x * (long long)blockDim.x + threadIdx.x; d < L; d += (long long)gridDim.x * blockDim.x) out[d] = in[src[d]];
+}
+cudaError_t launch_gather_f64(const double* in, const int* src, long long L, double* out, cudaStream_t st)
+{
+    if (!L) return cudaSuccess;
+    long long blocks = (L + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    gather_f64_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, src, L, out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: per-SNP LOD table lut[s][g], g = 0,1,2,missing, for a global --error (garlic-roh.cpp:355-386)
+// and, for wLOD, the per-SNP score table lod*nomut*norec evaluated left to right (:246-249).
+// ------------------------------------------------------------------------------------------
+__global__ void build_lut_kernel(const double* __restrict__ freq, long long L, double error, double* __restrict__ lut)
+{
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < L; s += (long long)gridDim.x * blockDim.x) {
+        const double f = freq[s];
+        double4 v;
+        v.x = lod_eval(0, f, error); v.y = lod_eval(1, f, error); v.z = lod_eval(2, f, error); v.w = 0.0;
+        reinterpret_cast<double4*>(lut)[s] = v;
+    }
+}
+cudaError_t launch_build_lut(const double* freq, long long L, double error, double* lut, cudaStream_t st)
+{
+    if (!L) return cudaSuccess;
+    long long blocks = (L + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    build_lut_kernel<<<(unsigned)blocks, 256, 0, st>>>(freq, L, error, lut);
+    return cudaGetLastError();
+}
+
+// wLOD per-SNP weights: nomut = exp(-2*M*mu*Δbp), norec = exp(-2*M*1*Δcm); Δ of a chromosome's
+// first SNP is its absolute position (garlic-roh.cpp:134-140, :246-247).
+__global__ void wlod_weights_kernel(const int* __restrict__ pos, const double* __restrict__ gpos,
+                                    const int* __restrict__ chr_of, const int* __restrict__ chr_start, long long L,
+                                    double mu, int M, double* __restrict__ nomut, double* __restrict__ norec)
+{
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < L; s += (long long)gridDim.x * blockDim.x) {
+        const bool first = (s == chr_start[chr_of[s]]);
+        const double pi = first ? (double)pos[s] : (double)(pos[s] - pos[s - 1]);
+        const double gi = first ? gpos[s] : (gpos[s] - gpos[s - 1]);
+        nomut[s] = exp(-2.0 * M * mu * pi);
+        norec[s] = exp(-2.0 * M * 1 * gi);
+    }
+}
+cudaError_t launch_wlod_weights(const int* pos, const double* gpos, const int* chr_of, const int* chr_start,
+                                long long L, double mu, int M, double* nomut, double* norec, cudaStream_t st)
+{
+    if (!L) return cudaSuccess;
+    long long blocks = (L + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    wlod_weights_kernel<<<(unsigned)blocks, 256, 0, st>>>(pos, gpos, chr_of, chr_start, L, mu, M, nomut, norec);
+    return cudaGetLastError();
+}
+
+// score table for wLOD with a global error: slut[s][g] = lod(g)*nomut[s]*norec[s]
+__global__ void build_wlut_kernel(const double* __restrict__ lut, const double* __restrict__ nomut,
+                                  const double* __restrict__ norec, long long L, double* __restrict__ wlut)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < 4 * L; t += (long long)gridDim.x * blockDim.x) {
+        const long long s = t >> 2;
+        wlut[t] = lut[t] * nomut[s] * norec[s];
+    }
+}
+cudaError_t launch_build_wlut(const double* lut, const double* nomut, const double* norec, long long L,
+                              double* wlut, cudaStream_t st)
+{
+    if (!L) return cudaSuccess;
+    long long blocks = (4 * L + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    build_wlut_kernel<<<(unsigned)blocks, 256, 0, st>>>(lut, nomut, norec, L, wlut);
+    return cudaGetLastError();
+}
+
+}  // namespace garlic

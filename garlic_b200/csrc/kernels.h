@@ -1,0 +1,33 @@
+// kernels.h — launch wrappers of the hand-written kernels (internal C++ interface; the public
+// boundary is the C ABI in include/garlic_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace garlic {
+
+cudaError_t launch_walk(const WalkParams& P, const Item* items, int n_items, bool gl_mode, bool roh,
+                        bool dump, cudaStream_t st);
+cudaError_t launch_fill_f64(double* p, size_t n, double v, cudaStream_t st);
+cudaError_t launch_first_allele(const uint8_t* alleles, int n_snp, int n_ind, int ind_offset, int missing,
+                                unsigned long long* key, cudaStream_t st);
+cudaError_t launch_code_alleles(const uint8_t* alleles, int n_snp, int n_ind, int missing,
+                                const unsigned long long* key, long long snp0, uint64_t* geno,
+                                int64_t row_words, int* counts, long long L0, cudaStream_t st);
+cudaError_t launch_count_packed(const uint64_t* geno, int64_t row_words, int n_ind, long long L0,
+                                int* counts, cudaStream_t st);
+cudaError_t launch_freq_keep(const int* counts, long long L0, const int* pos, const int* chr_of,
+                             const int* chr_param, int oob, double* freq, uint8_t* keep, cudaStream_t st);
+cudaError_t launch_compact_geno(const uint64_t* gin, int64_t in_words, const int* src, long long L,
+                                uint64_t* gout, int64_t out_words, int n_ind, cudaStream_t st);
+cudaError_t launch_compact_gl(const double* in, int64_t in_stride, const int* src, long long L, double* out,
+                              int64_t out_stride, int n_ind, int type, cudaStream_t st);
+cudaError_t launch_gather_f64(const double* in, const int* src, long long L, double* out, cudaStream_t st);
+cudaError_t launch_build_lut(const double* freq, long long L, double error, double* lut, cudaStream_t st);
+cudaError_t launch_wlod_weights(const int* pos, const double* gpos, const int* chr_of, const int* chr_start,
+                                long long L, double mu, int M, double* nomut, double* norec, cudaStream_t st);
+cudaError_t launch_build_wlut(const double* lut, const double* nomut, const double* norec, long long L,
+                              double* wlut, cudaStream_t st);
+
+}  // namespace garlic

@@ -1,0 +1,112 @@
+// segments.h — host-side segment table and run stitching (pure C++, shared by capi.cu and the CPU
+// emulation test).  Closed form of the reference's window validity: a window is MISSING iff it
+// contains an adjacent SNP pair with a gap > MAX_GAP or overlapping the centromere
+// (src/garlic-roh.cpp:55-123, inGap :11-16; equivalence verified in SURVEY §3.4 and by
+// tests/test_host_emu.py against the literal oracle).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+#include "common.cuh"
+
+namespace garlic {
+
+struct Segment { int chr, ws, we; };   // valid window starts [ws,we); SNP stretch [ws, we+W-1)
+
+inline bool in_gap(int qs, int qe, int ts, int te)
+{
+    return (ts <= qs && te >= qs) || (ts <= qe && te >= qe) || (ts >= qs && te <= qe);
+}
+
+inline void build_segments(const std::vector<int64_t>& chr_off, const std::vector<int32_t>& pos,
+                           const std::vector<int32_t>& cen, int max_gap, int W, std::vector<Segment>& segs)
+{
+    segs.clear();
+    const int n_chr = (int)chr_off.size() - 1;
+    for (int c = 0; c < n_chr; ++c) {
+        const int lo = (int)chr_off[c], hi = (int)chr_off[c + 1];
+        const int cs = cen[2 * c], ce = cen[2 * c + 1];
+        int a = lo;
+        for (int i = lo + 1; i <= hi; ++i) {
+            bool brk = (i == hi);
+            if (!brk) {
+                const int p0 = pos[i - 1], p1 = pos[i];
+                brk = (p1 - p0 > max_gap) || in_gap(p0, p1, cs, ce);   // garlic-roh.cpp:60-61
+            }
+            if (brk) {
+                if (i - a >= W) segs.push_back({c, a, i - W + 1});
+                a = i;
+            }
+        }
+    }
+}
+
+// chunk length (in owned SNPs) that yields enough warps to fill 148 SMs a few times over
+inline int pick_chunk(int64_t L, int W, int n_lanes)
+{
+    const int n_groups = (n_lanes + 31) / 32;
+    const int64_t target_items = std::max<int64_t>(1, (148 * 16 * 4 + n_groups - 1) / n_groups);
+    int64_t ch = L / target_items;
+    const int64_t lo = std::max(256, 8 * W);
+    ch = std::max<int64_t>(lo, std::min<int64_t>(ch, 8192));
+    return (int)((ch + 31) / 32 * 32);
+}
+
+// chunk = 0: one item per segment (exact chains).  step > 0: thinning slots for window dumps.
+inline void build_items(const std::vector<int64_t>& chr_off, int W, const std::vector<Segment>& segs, int chunk,
+                        int step, std::vector<Item>& items)
+{
+    items.clear();
+    const int n_chr = (int)chr_off.size() - 1;
+    std::vector<int> thin_base(n_chr + 1, 0);
+    for (int c = 0; c < n_chr; ++c) {
+        const int Lc = (int)(chr_off[c + 1] - chr_off[c]);
+        thin_base[c + 1] = thin_base[c] + (step > 0 ? (Lc + step - 1) / step : 0);
+    }
+    for (size_t si = 0; si < segs.size(); ++si) {
+        const Segment& s = segs[si];
+        const int a = s.ws, b = s.we + W - 1;
+        int n = 1, size = b - a;
+        if (chunk > 0 && b - a > chunk + chunk / 2) {
+            n = (b - a + chunk - 1) / chunk;
+            size = ((b - a + n - 1) / n + 31) / 32 * 32;
+            n = (b - a + size - 1) / size;
+        }
+        for (int i = 0; i < n; ++i) {
+            Item it;
+            it.own_lo = a + i * size;
+            it.own_hi = std::min(b, it.own_lo + size);
+            it.w0 = std::max(a, it.own_lo - W + 1);
+            it.we = s.we;
+            it.seg = (int)si;
+            it.flags = (i > 0 ? 1 : 0) | (i + 1 < n ? 2 : 0);
+            it.chr_start = (int)chr_off[s.chr];
+            it.thin_base = thin_base[s.chr];
+            items.push_back(it);
+        }
+    }
+}
+
+// Sort by (individual, start), merge runs cut at chunk boundaries, apply the minimum-length rule
+// (garlic-roh.cpp:477).  Returns the merged runs; tag keeps seg<<2.
+inline void stitch_runs(std::vector<RohRec>& recs, int thr, std::vector<RohRec>& out)
+{
+    std::sort(recs.begin(), recs.end(), [](const RohRec& x, const RohRec& y) {
+        return x.ind != y.ind ? x.ind < y.ind : x.a < y.a;
+    });
+    out.clear();
+    size_t i = 0;
+    while (i < recs.size()) {
+        RohRec cur = recs[i++];
+        while ((cur.tag & 2) && i < recs.size() && recs[i].ind == cur.ind && (recs[i].tag & 1) &&
+               recs[i].a == cur.b + 1 && (recs[i].tag >> 2) == (cur.tag >> 2)) {
+            cur.b = recs[i].b;
+            cur.tag = (cur.tag & ~2) | (recs[i].tag & 2);
+            ++i;
+        }
+        if (cur.b - cur.a + 1 < thr) continue;
+        out.push_back(cur);
+    }
+}
+
+}  // namespace garlic

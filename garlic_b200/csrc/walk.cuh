@@ -1,0 +1,219 @@
+// walk.cuh — the per-lane fused LOD-window → cutoff → coverage → run-length walker (K5).
+//
+// One lane = one individual walking one Item (a chunk of a segment of valid windows) along the
+// SNP axis.  Replaces, fused and without ever materialising the window matrix:
+//   * calcLOD's running update win[l] = win[l-1] - lod(out) + lod(in), fresh sum at each restart
+//     (reference src/garlic-roh.cpp:50-123) — same operation order, so with items = whole
+//     segments the window values are bit-identical to the reference chain;
+//   * the cutoff test and per-SNP coverage count inWin[] (garlic-roh.cpp:446-454) as a sliding
+//     count of the last W window flags;
+//   * the run-length state machine (garlic-roh.cpp:462-532) as bit-parallel edge detection on
+//     32-step words of "covered" bits;
+//   * optional window dump for the KDE thinning (garlic-data.cpp:2026-2069) / --raw-lod.
+//
+// Written __host__ __device__ so tests can run the identical logic on the CPU
+// (tests/host_emu.cpp) where no GPU is available; the product path only ever runs it on the GPU.
+#pragma once
+#include <math.h>
+#include "common.cuh"
+
+namespace garlic {
+
+// lod(): log10(P(g|autozygous)/P(g|non-autozygous)), exact operation order of
+// garlic-roh.cpp:355-386.  Compiled with FMA contraction disabled (-fmad=false).
+GHD double lod_eval(int g, double f, double e)
+{
+    if (f == 0 || f == 1 || g == 3) return 0.0;   // log10(1/1)
+    double a, na;
+    if (g == 0) {
+        na = (1 - f) * (1 - f);
+        a = (1 - e) * (1 - f) + e * na;
+    } else if (g == 1) {
+        na = 2 * (f) * (1 - f);
+        a = e * na;
+    } else {
+        na = (f) * (f);
+        a = (1 - e) * (f) + e * na;
+    }
+    return log10(a / na);
+}
+
+template <int SRC>
+struct LaneCtx {
+    const uint64_t* row;
+    const double* lut;
+    const double* freq;
+    const double* glrow;
+    GHD double aval(int s, int g) const
+    {
+        if (SRC == 0) return lut[(int64_t)s * 4 + g];
+        return lod_eval(g, freq[s], glrow[s]);
+    }
+};
+
+struct LaneState {
+    double win;
+    int cov;
+    int run_start;
+    uint32_t fw;
+    uint32_t hist;
+    bool ambig;
+};
+
+GHD void emit_run(const WalkParams& P, const Item& it, int ind, bool active, int a, int b)
+{
+    const int ol = (a == it.own_lo) && (it.flags & 1);
+    const int orr = (b == it.own_hi - 1) && (it.flags & 2);
+    if (!active) return;
+    if (!(ol | orr) && (b - a + 1 < P.thr)) return;   // garlic-roh.cpp:477 (min #SNPs)
+#ifdef __CUDA_ARCH__
+    unsigned p = atomicAdd(P.out_count, 1u);
+#else
+    unsigned p = P.out_count[0]++;
+#endif
+    if (p < P.out_cap) {
+        RohRec r;
+        r.ind = ind; r.a = a; r.b = b; r.tag = (it.seg << 2) | (orr << 1) | ol;
+        P.out[p] = r;
+    }
+}
+
+template <bool DUMP>
+GHD void dump_window(const WalkParams& P, const Item& it, int k, bool active, int t, double win)
+{
+    if (!DUMP) return;
+    const int d = t - it.chr_start;
+    if (active && (d % P.dump_step) == 0)
+        P.dump[(int64_t)k * P.dump_stride + it.thin_base + d / P.dump_step] = win;
+}
+
+// One block of 32 slide steps.  FULL: every step is a valid window and inside the owned range.
+template <int SRC, bool ROH, bool DUMP, bool FULL>
+GHD void walk_block(const WalkParams& P, const Item& it, const LaneCtx<SRC>& C, LaneState& S, int ind,
+                    int k_slot, bool active, uint64_t gin, uint64_t gout, int tblk, uint32_t ow)
+{
+    const int W = P.W;
+    const double cut = P.cutoff, cut_lo = P.cutoff - P.tol, cut_hi = P.cutoff + P.tol;
+    const bool chk = P.tol > 0;
+    const int s_in0 = tblk + W - 1, s_out0 = tblk - 1;
+    uint32_t fw = 0, cw = 0;
+    double win = S.win;
+    int cov = S.cov;
+    uint32_t hist = S.hist;
+    bool amb = S.ambig;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const int go = (int)(gout >> (2 * k)) & 3, gi = (int)(gin >> (2 * k)) & 3;
+        win = (win - C.aval(s_out0 + k, go)) + C.aval(s_in0 + k, gi);   // garlic-roh.cpp:98-100
+        const bool valid = FULL || (tblk + k < it.we);
+        const bool f = valid && (win >= cut);                            // garlic-roh.cpp:450
+        if (chk && valid) amb |= ((win >= cut_lo) != (win >= cut_hi));
+        if (DUMP && valid) dump_window<DUMP>(P, it, k_slot, active, tblk + k, win);
+        uint32_t o;
+        if (W <= 32) { o = (hist >> (W - 1)) & 1u; hist = (hist << 1) | (uint32_t)f; }
+        else o = (ow >> k) & 1u;
+        cov += (int)f - (int)o;                                          // sliding form of :446-454
+        fw |= (uint32_t)f << k;
+        cw |= (uint32_t)(cov >= P.thr) << k;                             // garlic-roh.cpp:466
+    }
+    S.win = win; S.cov = cov; S.hist = hist; S.ambig = amb;
+    S.fw = fw;   // the block's window-flag word, stored to the history ring by the caller
+    // run-length on the 32 covered bits (bit-parallel edge detection)
+    if (ROH) {
+        uint32_t em = 0xffffffffu;
+        if (!FULL) {
+            em = 0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+                em |= (uint32_t)((tblk + k >= it.own_lo) && (tblk + k < it.own_hi)) << k;
+        }
+        const uint32_t x = cw & em;
+        const uint32_t inr = S.run_start >= 0 ? 1u : 0u;
+        uint32_t trans = x ^ ((x << 1) | inr);
+        while (trans) {
+#ifdef __CUDA_ARCH__
+            const int k = __ffs((int)trans) - 1;
+#else
+            const int k = __builtin_ctz(trans);
+#endif
+            trans &= trans - 1;
+            const int t = tblk + k;
+            if ((x >> k) & 1u) S.run_start = t;
+            else { emit_run(P, it, ind, active, S.run_start, t - 1); S.run_start = -1; }
+        }
+    }
+}
+
+// Walk one item for one individual.  ring: this lane's flag-history ring (NW words, stride rstride).
+template <int SRC, bool ROH, bool DUMP>
+GHD void walk_item(const WalkParams& P, const Item& it, int k_slot, bool active, uint32_t* ring, int rstride)
+{
+    const int W = P.W;
+    const int ind = P.ind_list ? P.ind_list[k_slot] : k_slot;
+    LaneCtx<SRC> C;
+    C.row = P.geno + (int64_t)ind * P.row_words;
+    C.lut = P.lut;
+    C.freq = P.freq;
+    C.glrow = (SRC == 1) ? P.gl + (int64_t)ind * P.gl_stride : nullptr;
+    const int NW = ((W + 31) >> 5) + 1;
+
+    // fresh sum for window w0, ascending (garlic-roh.cpp:57-71)
+    double win = 0.0;
+    for (int i = 0; i < W; ++i) {
+        const int s = it.w0 + i;
+        const int g = (int)(C.row[s >> 5] >> (2 * (s & 31))) & 3;
+        win += C.aval(s, g);
+    }
+    LaneState S;
+    S.win = win; S.run_start = -1; S.fw = 0; S.ambig = false;
+    const bool f0 = win >= P.cutoff;
+    if (P.tol > 0) S.ambig = ((win >= P.cutoff - P.tol) != (win >= P.cutoff + P.tol));
+    dump_window<DUMP>(P, it, k_slot, active, it.w0, win);
+    S.cov = (int)f0;
+    S.hist = (uint32_t)f0;
+    if (ROH && it.w0 >= it.own_lo && S.cov >= P.thr) S.run_start = it.w0;
+    if (W > 32) {
+        for (int w = 0; w < NW; ++w) ring[w * rstride] = 0;
+        ring[0] = (uint32_t)f0 << 31;   // window w0 sits at bit-stream position 31
+    }
+
+    const int M = it.own_hi - 1 - it.w0;   // number of slide steps
+    const int sa = 2 * ((it.w0 + W) & 31), sb = 2 * (it.w0 & 31);
+    const int64_t ia = (it.w0 + W) >> 5, ib = it.w0 >> 5;
+    uint64_t a_lo = C.row[ia], b_lo = C.row[ib];
+    const int r = (32 - (W & 31)) & 31;
+    const int nwords = (W + 31) >> 5;
+    for (int j = 0, m0 = 0; m0 < M; ++j, m0 += 32) {
+        const uint64_t a_hi = C.row[ia + j + 1], b_hi = C.row[ib + j + 1];
+        const uint64_t gin = sa ? ((a_lo >> sa) | (a_hi << (64 - sa))) : a_lo;
+        const uint64_t gout = sb ? ((b_lo >> sb) | (b_hi << (64 - sb))) : b_lo;
+        a_lo = a_hi; b_lo = b_hi;
+        const int tblk = it.w0 + 1 + m0;
+        uint32_t ow = 0;
+        if (W > 32) {
+            const int qi = j + 1 - nwords;
+            const uint32_t w0_ = qi >= 0 ? ring[(qi % NW) * rstride] : 0u;
+            const uint32_t w1_ = (qi + 1) >= 0 ? ring[((qi + 1) % NW) * rstride] : 0u;
+            ow = r ? ((w0_ >> r) | (w1_ << (32 - r))) : w0_;
+        }
+        const bool full = (tblk + 31 < it.we) && (tblk >= it.own_lo) && (tblk + 31 < it.own_hi);
+        if (full) walk_block<SRC, ROH, DUMP, true>(P, it, C, S, ind, k_slot, active, gin, gout, tblk, ow);
+        else walk_block<SRC, ROH, DUMP, false>(P, it, C, S, ind, k_slot, active, gin, gout, tblk, ow);
+        if (W > 32) ring[((j + 1) % NW) * rstride] = S.fw;
+    }
+    if (ROH && S.run_start >= 0) emit_run(P, it, ind, active, S.run_start, it.own_hi - 1);
+    if (P.tol > 0 && S.ambig && active) {
+#ifdef __CUDA_ARCH__
+        unsigned p = atomicAdd(P.out_count + 1, 1u);
+#else
+        unsigned p = P.out_count[1]++;
+#endif
+        if (p < P.amb_cap) {
+            RohRec rr;
+            rr.ind = ind; rr.a = 0; rr.b = 0; rr.tag = it.seg;
+            P.amb[p] = rr;
+        }
+    }
+}
+
+}  // namespace garlic

@@ -1,0 +1,231 @@
+// wlod.cu — the --weighted path: K6 LD band (hr², reference src/garlic-data.cpp:377-424,474-527,
+// 558-583) and K5-W weighted windows fused with ROH assembly (src/garlic-roh.cpp:204-277,409-546).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+#include "walk.cuh"
+#include "wlod.h"
+
+namespace garlic {
+
+// ------------------------------------------------------------------------------------------
+// K6a: SNP-major bit-planes of the LD individuals.  planes[s][0..nw) = non-missing bits,
+// planes[s][nw..2nw) = homozygous (g∈{0,2}) bits; individual j of the list is bit j&63 of word j>>6.
+// Lanes = consecutive SNPs: a warp reads one packed word per individual (broadcast).
+// ------------------------------------------------------------------------------------------
+__global__ void ld_planes_kernel(const uint64_t* __restrict__ geno, int64_t row_words, const int* __restrict__ ld_ind,
+                                 int n_ld, long long L, int nw, uint64_t* __restrict__ planes)
+{
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < L; s += (long long)gridDim.x * blockDim.x) {
+        for (int w = 0; w < nw; ++w) {
+            uint64_t nm = 0, hm = 0;
+            const int jmax = min(64, n_ld - w * 64);
+            for (int j = 0; j < jmax; ++j) {
+                const int ind = ld_ind[w * 64 + j];
+                const int g = (int)(geno[(int64_t)ind * row_words + (s >> 5)] >> (2 * (s & 31))) & 3;
+                nm |= (uint64_t)(g != 3) << j;
+                hm |= (uint64_t)(g == 0 || g == 2) << j;
+            }
+            planes[s * 2 * nw + w] = nm;
+            planes[s * 2 * nw + nw + w] = hm;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6b: ordered pair matrix P[j][d] = hr2(i, j), i = j + d - (W-1), d ∈ [0, 2W-2]; P[j][W-1] = 1.
+// hr2 exactly as garlic-data.cpp:558-583 (HA = homFreq[i], HB = homFreq[j]; counts over the LD
+// individuals by popcount of the bit-planes).  Entries whose i falls outside j's chromosome are 0
+// and never used.
+// ------------------------------------------------------------------------------------------
+__global__ void ld_pairs_kernel(const uint64_t* __restrict__ planes, int nw, const double* __restrict__ homf,
+                                const int* __restrict__ chr_of, const int* __restrict__ chr_start, int n_chr,
+                                long long L, int W, double* __restrict__ P)
+{
+    const int D = 2 * W - 1;
+    const long long total = L * D;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long j = t / D;
+        const int d = (int)(t % D);
+        const long long i = j + d - (W - 1);
+        double v = 0.0;
+        const int c = chr_of[j];
+        const long long lo = chr_start[c], hi = (c + 1 < n_chr) ? chr_start[c + 1] : L;
+        if (i == j) v = 1.0;
+        else if (i >= lo && i < hi) {
+            const double HA = homf[i], HB = homf[j];
+            if (HA > 0 && HA < 1 && HB > 0 && HB < 1) {
+                const uint64_t* pi = planes + i * 2 * nw;
+                const uint64_t* pj = planes + j * 2 * nw;
+                int tot = 0, hab = 0;
+                for (int w = 0; w < nw; ++w) {
+                    tot += __popcll(pi[w] & pj[w]);
+                    hab += __popcll(pi[nw + w] & pj[nw + w]);
+                }
+                double HAB = (double)hab, total_d = (double)tot;
+                HAB /= total_d;
+                const double H = HAB - HA * HB;
+                const double HR2 = H * H / (HA * (1 - HA) * HB * (1 - HB));
+                v = (HR2 > 1) ? 1.0 : HR2;
+            }
+        }
+        P[t] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6c: LD[w][k] = Σ_{i=w}^{w+W-1} (i==w+k ? 1 : hr2(i, w+k)), ascending i from 0.0
+// (garlic-data.cpp:489-494, 521-527) = sum of the contiguous slice P[w+k][W-1-k .. 2W-2-k].
+// Thread (j, k), w = j-k; lanes = consecutive k of one j read overlapping slices of one P row.
+// ------------------------------------------------------------------------------------------
+__global__ void ld_sum_kernel(const double* __restrict__ P, const int* __restrict__ chr_of,
+                              const int* __restrict__ chr_start, int n_chr, long long L, int W,
+                              double* __restrict__ invld, double* __restrict__ ld_out)
+{
+    const int D = 2 * W - 1;
+    const long long total = L * W;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long j = t / W;
+        const int k = (int)(t % W);
+        const long long w = j - k;
+        const int c = chr_of[j];
+        const long long lo = chr_start[c], hi = (c + 1 < n_chr) ? chr_start[c + 1] : L;
+        if (w < lo || w >= hi - W + 1) continue;
+        const double* row = P + j * D + (W - 1 - k);
+        double acc = 0.0;
+        for (int n = 0; n < W; ++n) acc += row[n];
+        invld[w * W + k] = 1.0 / acc;
+        if (ld_out) ld_out[w * W + k] = acc;
+    }
+}
+
+cudaError_t launch_ld_band(const uint64_t* geno, int64_t row_words, const int* ld_ind, int n_ld,
+                           const double* homf, const int* chr_of, const int* chr_start, int n_chr,
+                           long long L, int W, double* invld, double* ld_out, cudaStream_t st, int* n_launches)
+{
+    *n_launches = 0;
+    const int nw = (n_ld + 63) / 64;
+    uint64_t* planes = nullptr;
+    double* P = nullptr;
+    cudaError_t e = cudaMalloc(&planes, (size_t)L * 2 * nw * sizeof(uint64_t));
+    if (e != cudaSuccess) return e;
+    e = cudaMalloc(&P, (size_t)L * (2 * W - 1) * sizeof(double));
+    if (e != cudaSuccess) { cudaFree(planes); return e; }
+    auto blocks = [](long long n) { long long b = (n + 255) / 256; return (unsigned)(b > 148 * 64 ? 148 * 64 : b); };
+    ld_planes_kernel<<<blocks(L), 256, 0, st>>>(geno, row_words, ld_ind, n_ld, L, nw, planes);
+    ld_pairs_kernel<<<blocks(L * (2 * W - 1)), 256, 0, st>>>(planes, nw, homf, chr_of, chr_start, n_chr, L, W, P);
+    cudaMemsetAsync(invld, 0, (size_t)L * W * sizeof(double), st);
+    if (ld_out) cudaMemsetAsync(ld_out, 0, (size_t)L * W * sizeof(double), st);
+    ld_sum_kernel<<<blocks(L * W), 256, 0, st>>>(P, chr_of, chr_start, n_chr, L, W, invld, ld_out);
+    *n_launches = 3;
+    e = cudaGetLastError();
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(planes);
+    cudaFree(P);
+    return e != cudaSuccess ? e : e2;
+}
+
+// ------------------------------------------------------------------------------------------
+// K5-W: weighted windows.  Every window is a fresh, ascending sum
+//   wLOD(t) = Σ_k score[t+k] · (1.0 / LD[t][k])        (garlic-roh.cpp:253-273)
+// with separate multiply and add (the reference is built without FMA).  Coverage count and
+// run-length assembly as in the unweighted walker, in per-step form (their cost is negligible
+// next to the W multiply-adds).
+// ------------------------------------------------------------------------------------------
+template <int SRC, bool ROH, bool DUMP>
+__device__ __forceinline__ void wlod_walk_item(const WlodParams& Q, const Item& it, int k_slot, bool active,
+                                               uint32_t* ring, int rstride)
+{
+    const WalkParams& P = Q.base;
+    const int W = P.W;
+    const int ind = P.ind_list ? P.ind_list[k_slot] : k_slot;
+    const uint64_t* row = P.geno + (int64_t)ind * P.row_words;
+    const double* glrow = (SRC == 1) ? P.gl + (int64_t)ind * P.gl_stride : nullptr;
+    const int NW = ((W + 31) >> 5) + 1;
+    for (int w = 0; w < NW; ++w) ring[w * rstride] = 0;
+    int cov = 0, run_start = -1;
+    const int t_end = it.own_hi;
+    for (int t = it.w0, q = 0; t < t_end; ++t, ++q) {
+        bool f = false;
+        if (t < it.we) {
+            const double* inv = Q.invld + (int64_t)t * W;
+            double acc = 0.0;
+            for (int k = 0; k < W; ++k) {
+                const int s = t + k;
+                const int g = (int)(row[s >> 5] >> (2 * (s & 31))) & 3;
+                double sc;
+                if (SRC == 0) sc = Q.wlut[(int64_t)s * 4 + g];
+                else sc = lod_eval(g, P.freq[s], glrow[s]) * Q.nomut[s] * Q.norec[s];
+                acc += sc * inv[k];
+            }
+            f = acc >= P.cutoff;
+            dump_window<DUMP>(P, it, k_slot, active, t, acc);
+        }
+        // flag history ring, bit-addressed by step counter q
+        const int wq = (q >> 5) % NW;
+        uint32_t cur = (q & 31) ? ring[wq * rstride] : 0u;
+        cur |= (uint32_t)f << (q & 31);
+        ring[wq * rstride] = cur;
+        uint32_t o = 0;
+        if (q >= W) o = (ring[(((q - W) >> 5) % NW) * rstride] >> ((q - W) & 31)) & 1u;
+        cov += (int)f - (int)o;
+        if (ROH && t >= it.own_lo) {
+            const bool c = cov >= P.thr;
+            if (c && run_start < 0) run_start = t;
+            else if (!c && run_start >= 0) { emit_run(P, it, ind, active, run_start, t - 1); run_start = -1; }
+        }
+    }
+    if (ROH && run_start >= 0) emit_run(P, it, ind, active, run_start, it.own_hi - 1);
+}
+
+template <int SRC, bool ROH, bool DUMP>
+__global__ void __launch_bounds__(128)
+wlod_walk_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items, int n_groups)
+{
+    extern __shared__ uint32_t ring_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gpb = blockDim.x >> 5;
+    const int gblocks = (n_groups + gpb - 1) / gpb;
+    const long long total = (long long)n_items * gblocks;
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const int item = (int)(u / gblocks);
+        const int group = (int)(u % gblocks) * gpb + warp;
+        if (group >= n_groups) continue;
+        const int k = group * 32 + lane;
+        const bool active = k < Q.base.n_lanes;
+        const Item it = items[item];
+        wlod_walk_item<SRC, ROH, DUMP>(Q, it, active ? k : Q.base.n_lanes - 1, active, ring_smem + threadIdx.x, blockDim.x);
+    }
+}
+
+template <int SRC, bool ROH, bool DUMP>
+static cudaError_t launch_wlod_t(const WlodParams& Q, const Item* items, int n_items, cudaStream_t st)
+{
+    if (n_items == 0 || Q.base.n_lanes == 0) return cudaSuccess;
+    const int threads = 128;
+    const int n_groups = (Q.base.n_lanes + 31) / 32;
+    const int gpb = threads / 32;
+    const long long total = (long long)n_items * ((n_groups + gpb - 1) / gpb);
+    const int NW = ((Q.base.W + 31) >> 5) + 1;
+    const size_t smem = (size_t)NW * threads * sizeof(uint32_t);
+    long long grid = total;
+    const long long cap = 148ll * 16 * 8;
+    if (grid > cap) grid = cap;
+    wlod_walk_kernel<SRC, ROH, DUMP><<<(unsigned)grid, threads, smem, st>>>(Q, items, n_items, n_groups);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wlod_walk(const WlodParams& Q, const Item* items, int n_items, bool gl_mode, bool roh,
+                             bool dump, cudaStream_t st)
+{
+    if (gl_mode) {
+        if (roh && !dump) return launch_wlod_t<1, true, false>(Q, items, n_items, st);
+        if (!roh && dump) return launch_wlod_t<1, false, true>(Q, items, n_items, st);
+        return launch_wlod_t<1, true, true>(Q, items, n_items, st);
+    }
+    if (roh && !dump) return launch_wlod_t<0, true, false>(Q, items, n_items, st);
+    if (!roh && dump) return launch_wlod_t<0, false, true>(Q, items, n_items, st);
+    return launch_wlod_t<0, true, true>(Q, items, n_items, st);
+}
+
+}  // namespace garlic

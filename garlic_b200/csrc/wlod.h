@@ -1,0 +1,25 @@
+// wlod.h — K6 (LD band) and K5-W (weighted windows → ROH) launch wrappers.
+#pragma once
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace garlic {
+
+struct WlodParams {
+    WalkParams base;
+    const double* wlut;    // [L+pad][4]  lod(g)*nomut*norec for a global error
+    const double* invld;   // [L+pad][W]  1.0 / LD[w][k]
+    const double* nomut;   // [L+pad]     (GL mode: score evaluated per genotype)
+    const double* norec;   // [L+pad]
+};
+
+cudaError_t launch_wlod_walk(const WlodParams& Q, const Item* items, int n_items, bool gl_mode, bool roh,
+                             bool dump, cudaStream_t st);
+
+// LD band: hr² pair matrix over the listed individuals → window sums → reciprocal.
+// invld: [L+pad][W]; ld_out (optional): [L][W] the sums themselves (reference LDData layout).
+cudaError_t launch_ld_band(const uint64_t* geno, int64_t row_words, const int* ld_ind, int n_ld,
+                           const double* homf, const int* chr_of, const int* chr_start, int n_chr,
+                           long long L, int W, double* invld, double* ld_out, cudaStream_t st, int* n_launches);
+
+}  // namespace garlic

@@ -1,0 +1,151 @@
+/*
+ * garlic_b200.h — C ABI of the B200-native GARLIC hot path (libgarlic_b200.so).
+ *
+ * GARLIC (szpiech/garlic v1.1.6a) has no FFI of its own: the hot path sits between the loaders
+ * and the writers inside main() (reference src/garlic-main.cpp:216-406).  Each entry point below
+ * replaces one of those calls; the reference-side binding a maintainer would add is shown in
+ * INTEGRATION.md.  Conventions: opaque handle, plain pointers and sizes, int status return
+ * (0 = ok, non-zero = error, text via garlic_gpu_last_error), no exceptions cross the boundary,
+ * caller-owned HOST buffers unless a name ends in _dev.  One handle drives one GPU; multi-GPU
+ * runs use one process (and one handle) per GPU and shard by individual.
+ *
+ * There is no CPU fallback: every compute entry point launches hand-written sm_100a kernels and
+ * fails if no CUDA device is usable.
+ */
+#ifndef GARLIC_B200_H
+#define GARLIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct garlic_gpu garlic_gpu_t;
+
+#define GARLIC_MISSING (-9999.0)   /* reference MISSING sentinel for windows (garlic-data.h) */
+
+/* genotype-likelihood encodings, reference readTGLSData (src/garlic-data.cpp:1557-1570) */
+#define GARLIC_GL_GQ 0
+#define GARLIC_GL_GL 1
+#define GARLIC_GL_PL 2
+#define GARLIC_GL_ERROR (-1)   /* values are already per-genotype error rates */
+
+/* One ROH as the reference stores it in ROHData (src/garlic-roh.h:43-50), plus SNP indices. */
+typedef struct {
+    int32_t ind;        /* individual index (local to this handle) */
+    int32_t chr;        /* chromosome index */
+    int32_t start_idx;  /* index of first SNP in the filtered, concatenated SNP axis */
+    int32_t stop_idx;   /* index of last SNP (inclusive) */
+} garlic_roh_t;
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+int garlic_gpu_create(int device, garlic_gpu_t **out);
+void garlic_gpu_destroy(garlic_gpu_t *h);
+const char *garlic_gpu_last_error(const garlic_gpu_t *h);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+uint64_t garlic_gpu_launch_count(const garlic_gpu_t *h);
+/* CUDA stream (cudaStream_t) all kernels of this handle are launched on */
+void *garlic_gpu_stream(const garlic_gpu_t *h);
+int garlic_gpu_sync(garlic_gpu_t *h);
+
+/* ---- K1: loadTPEDData's coding + allele counting (src/garlic-data.cpp:103-150) -------------
+ * n_ind individuals on this GPU starting at global individual ind_offset; n_loci SNPs before
+ * filtering; chr_offsets[n_chr+1] into the SNP axis; pos[n_loci] physical positions. */
+int garlic_gpu_set_shape(garlic_gpu_t *h, int n_ind, int ind_offset, int64_t n_loci, int n_chr,
+                         const int64_t *chr_offsets, const int32_t *pos);
+/* alleles: [n_snp][n_ind][2] characters for SNPs [snp0, snp0+n_snp), snp0 % 32 == 0.
+ * Uploads them and records, per SNP, the first non-missing allele in file order (phase a). */
+int garlic_gpu_put_alleles(garlic_gpu_t *h, const uint8_t *alleles, int64_t snp0, int n_snp, char missing);
+/* device pointer to the uint64 first-allele keys [n_loci]; with several GPUs, MIN-all-reduce it
+ * between put_alleles and code_alleles */
+void *garlic_gpu_first_allele_keys_dev(garlic_gpu_t *h);
+/* phase b: code every call to 2 bits (individual-major packed matrix), count alleles */
+int garlic_gpu_code_alleles(garlic_gpu_t *h);
+
+/* ---- pre-coded input: packed 2-bit rows (codes 0/1/2, 3 = missing) -------------------------
+ * rows: [n_ind][row_stride_bytes] on the host (or, for _dev, on this GPU); SNP s of a row is
+ * bits 2*(s%4) of byte s/4. */
+int garlic_gpu_put_packed(garlic_gpu_t *h, const uint8_t *rows, int64_t row_stride_bytes);
+int garlic_gpu_put_packed_dev(garlic_gpu_t *h, const void *rows_dev, int64_t row_stride_bytes);
+/* K2: per-SNP allele / missingness / homozygote counts by column reduction of the packed matrix
+ * (replaces the counting inside loadTPEDData and calculateGenoFreq, src/garlic-data.cpp:656-676).
+ * Optional corrections (may be NULL) add half-missing calls to nalleles / total. */
+int garlic_gpu_count_packed(garlic_gpu_t *h, const int32_t *nalleles_corr, const int32_t *total_corr);
+
+/* counts [4][n_loci] int32 on the device: nalleles, total, hom, nonmiss — SUM-all-reduce across
+ * GPUs before garlic_gpu_filter. */
+void *garlic_gpu_counts_dev(garlic_gpu_t *h);
+int garlic_gpu_get_counts(garlic_gpu_t *h, int32_t *nalleles, int32_t *total, int32_t *hom, int32_t *nonmiss);
+/* the "1" allele per SNP after code_alleles (missing char if all calls missing) */
+int garlic_gpu_get_one_allele(garlic_gpu_t *h, uint8_t *allele, char missing);
+
+/* ---- optional per-genotype likelihoods (readTGLSData, src/garlic-data.cpp:1516-1586) -------
+ * values: [n_ind][n_loci] (individual-major) raw GQ/GL/PL values; transformed to per-genotype
+ * error on the device during garlic_gpu_filter. */
+int garlic_gpu_put_gl(garlic_gpu_t *h, const double *values, int gl_type);
+int garlic_gpu_put_gl_dev(garlic_gpu_t *h, const void *values_dev, int gl_type);
+
+/* ---- freq + filterMonomorphic[AndOOB]Sites + K3 compaction (src/garlic-data.cpp:141,871-1195)
+ * freq = nalleles/total from the (all-reduced) counts; keep iff 0<freq<1 [and, if oob, inside
+ * the map scaffold and not strictly inside the centromere]. chr_param: [n_chr][4] =
+ * scaffold first bp, scaffold last bp, centromere start, centromere end (NULL if !oob).
+ * freq_override (may be NULL): use these frequencies instead (--freq-file).
+ * Outputs: freq_out[n_loci] (may be NULL), keep_out[n_loci] (may be NULL); returns L via n_kept. */
+int garlic_gpu_filter(garlic_gpu_t *h, int oob, const int32_t *chr_param, const double *freq_override,
+                      double *freq_out, uint8_t *keep_out, int64_t *n_kept);
+
+/* ---- per-SNP tables (K4; lod(), src/garlic-roh.cpp:355-386; inGap/centromeres :11-16) -------
+ * centromeres: [n_chr][2] start,end (0,0 if unknown); max_gap as --max-gap. Builds the LOD table
+ * on the device from freq and error (ignored when GL data are loaded). gpos (may be NULL):
+ * genetic positions [L] of the kept SNPs (needed for --weighted). */
+int garlic_gpu_set_tables(garlic_gpu_t *h, double error, int max_gap, const int32_t *centromeres,
+                          const double *gpos);
+/* test hook: overwrite the device LOD table with host values [L][4] (bit-exact chain tests) */
+int garlic_gpu_set_lut(garlic_gpu_t *h, const double *lut);
+int garlic_gpu_get_lut(garlic_gpu_t *h, double *lut);
+/* homFreq per kept SNP (calculateGenoFreq) from the reduced counts */
+int garlic_gpu_get_hom_freq(garlic_gpu_t *h, double *hom_freq);
+
+/* ---- K6: calcLDData / calcHR2LD (src/garlic-data.cpp:330-424,474-527,558-583) ---------------
+ * LD individuals (local indices, ascending as gsl_ran_choose returns them) or NULL for all.
+ * out_ld (may be NULL): the LD sums [L][W] as the reference's LDData (rows ≥ L_c-W+1 are 0). */
+int garlic_gpu_ld_band(garlic_gpu_t *h, int winsize, const int32_t *ld_individuals, int n_ld, double *out_ld);
+/* wLOD parameters (--mu, --M), call before weighted windows */
+int garlic_gpu_set_wlod(garlic_gpu_t *h, double mu, int M);
+
+/* ---- K5 pass 1: windows for the KDE (convert[Subset]WinData2DoubleData, src/garlic-data.cpp:
+ * 2026-2150) and --raw-lod --------------------------------------------------------------------
+ * Computes windows of the listed individuals (NULL = all) at locus index 0,step,2·step… of each
+ * chromosome. out: [n][n_slots] with n_slots = Σ_c ceil(L_c/step), slot order chromosome-major;
+ * GARLIC_MISSING where the reference has MISSING. exact != 0: whole-segment chains (bit-identical
+ * to the reference's running sums). */
+int64_t garlic_gpu_window_slots(garlic_gpu_t *h, int step);
+int garlic_gpu_windows(garlic_gpu_t *h, int winsize, int step, int weighted, const int32_t *individuals,
+                       int n, int exact, double *out);
+
+/* ---- K5 pass 2: calc[w]LODWindows + assembleROHWindows fused (src/garlic-roh.cpp:279-347,409-546)
+ * overlap_frac as --overlap-frac. out: capacity cap records, sorted by (ind, chr, start);
+ * *count receives the number of ROH (may exceed cap: call again with a larger buffer).
+ * exact: 0 = chunked fast pass + exact re-evaluation of windows within rounding distance of the
+ * cutoff (same ROH as exact), 1 = whole-segment chains everywhere. */
+int garlic_gpu_call_roh(garlic_gpu_t *h, int winsize, double cutoff, double overlap_frac, int weighted,
+                        int exact, garlic_roh_t *out, int64_t cap, int64_t *count);
+/* statistics of the last call_roh: [0] items, [1] individual-windows evaluated (N·Σ_c(L_c-W+1)),
+ * [2] ambiguous (individual, segment) pairs re-evaluated exactly, [3] kernel milliseconds */
+int garlic_gpu_last_stats(garlic_gpu_t *h, double *stats4);
+
+/* packed 2-bit genotype rows back to the host (parity checks; --phased / debugging): filtered = 0 →
+ * the matrix as ingested [n_ind][ceil(n_loci/4)], 1 → after compaction [n_ind][ceil(L/4)];
+ * row_stride_bytes >= that width. */
+int garlic_gpu_get_genotypes(garlic_gpu_t *h, int filtered, uint8_t *rows, int64_t row_stride_bytes);
+
+/* sizes after filtering */
+int64_t garlic_gpu_n_kept(const garlic_gpu_t *h);
+int garlic_gpu_get_kept_index(garlic_gpu_t *h, int32_t *src_index); /* [L] pre-filter index of kept SNP */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

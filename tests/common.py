@@ -67,3 +67,47 @@ def parse_bed(text):
             t = line.split("\t")
             tracks[-1].append((t[0], int(t[1]), int(t[2]), t[3], t[4]))
     return tracks
+
+
+# ---- flattening an oracle result into the concatenated, filtered arrays the product works on ----
+PAD = 4096 + 64
+
+
+def flatten(res, error, use_gl=False):
+    """oracle.run_pipeline result → dict(codes[N,L] uint8, rows uint64[N,row_words], chr_off, pos, cen,
+    freq, lut[L+PAD,4], gl[N,L+PAD] or None)."""
+    from oracle import oracle as orc
+    chroms = res["chroms"]
+    codes = np.concatenate([ch["geno"] for ch in chroms], axis=0).T.copy().astype(np.uint8)   # [N, L]
+    N, L = codes.shape
+    row_words = ((L + PAD + 31) >> 5) + 2
+    rows8 = synth.pack_codes(codes, row_bytes=row_words * 8)
+    rows = rows8.view(np.uint64).reshape(N, row_words)
+    chr_off = np.zeros(len(chroms) + 1, np.int64)
+    chr_off[1:] = np.cumsum([len(ch["pos"]) for ch in chroms])
+    pos = np.concatenate([ch["pos"] for ch in chroms]).astype(np.int32)
+    cen = np.array([ch["cen"] for ch in chroms], np.int32).reshape(-1)
+    freq = np.zeros(L + PAD)
+    freq[:L] = np.concatenate([ch["freq"] for ch in chroms])
+    lut = np.zeros((L + PAD, 4))
+    if error is not None:
+        lut[:L] = orc.lod_lut(freq[:L], error)
+    gl = None
+    if use_gl:
+        gl = np.zeros((N, L + PAD))
+        gl[:, :L] = np.concatenate([ch["gl"] for ch in chroms], axis=0).T
+    return dict(codes=codes, rows=rows, row_words=row_words, chr_off=chr_off, pos=pos, cen=cen, freq=freq,
+                lut=lut, gl=gl, N=N, L=L)
+
+
+def oracle_roh_idx(res):
+    """[(ind, chr, a_global, b_global)] from the oracle's per-chromosome indices."""
+    offs = np.zeros(len(res["chroms"]) + 1, np.int64)
+    offs[1:] = np.cumsum([len(ch["pos"]) for ch in res["chroms"]])
+    return [(r[0], r[1], int(offs[r[1]] + r[5]), int(offs[r[1]] + r[6])) for r in res["roh"]]
+
+
+def oracle_windows_matrix(res, step=1):
+    """Dense [N, slots] matrix in the product's dump layout (MISSING where the reference has MISSING)."""
+    mats = [ch["win"][:, ::step] for ch in res["chroms"]]
+    return np.concatenate(mats, axis=1)

@@ -1,0 +1,260 @@
+"""Parity of the CUDA path (through the C ABI, include/garlic_b200.h) against the CPU oracle on the
+golden cases, and against the reference binary's committed outputs.  Needs a GPU (B200).
+
+Bars (BASELINE.json north_star): packed genotypes, allele counts and ROH intervals bit-exact;
+window LOD / wLOD values within 1e-9 relative (tolerance written in each test)."""
+import numpy as np
+import pytest
+
+from garlic_b200 import synth
+from garlic_b200.pipeline import HotPath
+from oracle import oracle as orc
+from tests.common import (arg, arg_list, flatten, golden_text, load_case, oracle_roh_idx,
+                          oracle_windows_matrix)
+
+pytestmark = pytest.mark.gpu
+
+RTOL_WINDOWS = 1e-9     # north_star: "Window LOD/wLOD values must agree within 1e-9 relative"
+
+
+def run_oracle(name, **kw):
+    ds, args = load_case(name)
+    W = arg(args, "--winsize", cast=int)
+    err = arg(args, "--error", None, float)
+    cutoff = arg(args, "--lod-cutoff", None, float)
+    ov = arg(args, "--overlap-frac", 0.25, float)
+    weighted = "--weighted" in args
+    cm = "--cm" in args
+    res = orc.run_pipeline(ds, W, err, cutoff, ov, weighted=weighted, cm=cm,
+                           auto_overlap="--auto-overlap-frac" in args, **kw)
+    return ds, args, res, dict(W=W, err=err, cutoff=cutoff, weighted=weighted, cm=cm)
+
+
+def close_windows(got, want, rtol=RTOL_WINDOWS):
+    miss_w = (want == orc.MISSING)
+    assert np.array_equal(got == orc.MISSING, miss_w)
+    nan_w = np.isnan(want)
+    assert np.array_equal(np.isnan(got), nan_w)
+    ok = ~miss_w & ~nan_w
+    scale = np.maximum(np.abs(want[ok]), 1e-3)
+    assert np.max(np.abs(got[ok] - want[ok]) / scale, initial=0.0) <= rtol
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["lod_0", "lod_small", "wlod_cm", "auto_cutoff"])
+def test_k1_coding_counts_and_packed_matrix(name):
+    ds, args = load_case(name)
+    geno, na, tot, one, freq = orc.code_tped(ds.alleles)
+    hp = HotPath()
+    g = hp.g
+    g.set_shape(ds.n_ind, ds.n_loci, ds.chr_offsets, ds.pos)
+    for s0 in range(0, ds.n_loci, 1024):           # several chunks
+        g.put_alleles(ds.alleles[s0:s0 + 1024], s0)
+    g.code_alleles()
+    c_na, c_tot, c_hom, c_nm = g.get_counts()
+    assert np.array_equal(c_na, na) and np.array_equal(c_tot, tot)
+    assert np.array_equal(g.get_one_allele(), one)
+    codes = geno.astype(np.uint8)
+    assert np.array_equal(c_nm, (codes != 3).sum(1))
+    assert np.array_equal(c_hom, ((codes == 0) | (codes == 2)).sum(1))
+    packed = g.get_genotypes(False)
+    assert np.array_equal(synth.unpack_codes(packed, ds.n_loci), codes.T)
+    f, keep, L = g.filter()
+    assert np.array_equal(f, freq)                  # bit-exact double(nalleles)/double(total)
+    assert np.array_equal(keep, (freq > 0) & (freq < 1))
+    # the committed reference .freq (6 significant digits) agrees too
+    lines = golden_text(name, "out.freq").splitlines()[1:]
+    assert all(l.split("\t")[4] == "%g" % f[i] for i, l in enumerate(lines))
+    packed2 = g.get_genotypes(True)
+    assert np.array_equal(synth.unpack_codes(packed2, L), codes[keep].T)
+    hp.close()
+
+
+def test_k2_count_packed_matches_coding_path():
+    ds, args = load_case("lod_0")
+    geno, na, tot, one, freq = orc.code_tped(ds.alleles)
+    codes = geno.astype(np.uint8).T.copy()
+    hp = HotPath()
+    g = hp.g
+    g.set_shape(ds.n_ind, ds.n_loci, ds.chr_offsets, ds.pos)
+    g.put_packed(synth.pack_codes(codes))
+    # half-missing calls are not representable in 2 bits: the loader supplies them as corrections
+    base_na = np.where(codes == 3, 0, codes).sum(0).astype(np.int32)
+    base_tot = (2 * (codes != 3).sum(0)).astype(np.int32)
+    g.count_packed(na - base_na, tot - base_tot)
+    c_na, c_tot, c_hom, c_nm = g.get_counts()
+    assert np.array_equal(c_na, na) and np.array_equal(c_tot, tot)
+    assert np.array_equal(c_nm, (codes != 3).sum(0))
+    assert np.array_equal(c_hom, ((codes == 0) | (codes == 2)).sum(0))
+    g.count_packed()
+    c_na, c_tot, _, _ = g.get_counts()
+    assert np.array_equal(c_na, base_na) and np.array_equal(c_tot, base_tot)
+    hp.close()
+
+
+def test_k2_many_rows_counter_flush():
+    """> 255·8 rows per block exercises the 8-bit partial-counter flush."""
+    rng = np.random.default_rng(5)
+    N, L = 5000, 700
+    codes = rng.integers(0, 4, (N, L)).astype(np.uint8)
+    hp = HotPath()
+    g = hp.g
+    g.set_shape(N, L, np.array([0, 300, L]), np.arange(L) * 1000 + 1000)
+    g.put_packed(synth.pack_codes(codes))
+    g.count_packed()
+    c_na, c_tot, c_hom, c_nm = g.get_counts()
+    assert np.array_equal(c_na, np.where(codes == 3, 0, codes).sum(0))
+    assert np.array_equal(c_nm, (codes != 3).sum(0))
+    assert np.array_equal(c_hom, ((codes == 0) | (codes == 2)).sum(0))
+    hp.close()
+
+
+@pytest.mark.parametrize("name", ["lod_0", "lod_3", "lod_small", "auto_overlap_hg19"])
+def test_lut_and_windows(name):
+    ds, args, res, p = run_oracle(name)
+    hp = HotPath().load(ds, error=p["err"])
+    assert hp.L == res["n_used"]
+    F = flatten(res, p["err"])
+    lut = hp.g.get_lut()
+    # device log10 vs host libm: a few ulp at most
+    assert np.allclose(lut, F["lut"][:hp.L], rtol=1e-14, atol=1e-16)
+    want = oracle_windows_matrix(res)
+    # (1) product path (device-built table), exact chains and chunked: 1e-9 relative
+    close_windows(hp.g.windows(p["W"], 1, exact=True), want)
+    close_windows(hp.g.windows(p["W"], 1, exact=False), want)
+    # (2) same table as the oracle → whole-segment chains are bit-identical to the reference recurrence
+    hp.g.set_lut(F["lut"][:hp.L])
+    assert np.array_equal(hp.g.windows(p["W"], 1, exact=True), want)
+    hp.close()
+
+
+@pytest.mark.parametrize("name", ["lod_0", "lod_1", "lod_2", "lod_3", "lod_small", "auto_overlap_hg19", "lod_cm"])
+@pytest.mark.parametrize("exact", [False, True])
+def test_roh_unweighted_bit_exact(name, exact):
+    ds, args, res, p = run_oracle(name)
+    hp = HotPath().load(ds, error=p["err"], cm=p["cm"])
+    got = hp.roh(p["W"], p["cutoff"], res["overlap_frac"], exact=exact, cm=p["cm"])
+    assert [(r[0], r[1], r[5], r[6]) for r in got] == oracle_roh_idx(res)
+    # and the BED text equals the reference binary's committed output byte for byte
+    bounds = arg_list(args, "--size-bounds")
+    bed = orc.format_bed(got, ds.ind_ids, hp.labels, bounds, ds.pop, cm=p["cm"])
+    assert bed == golden_text(name, "out.roh.bed")
+    hp.close()
+
+
+@pytest.mark.parametrize("name", ["gl_pl", "gl_gl", "gl_gq"])
+def test_gl_path(name):
+    ds, args, res, p = run_oracle(name)
+    hp = HotPath().load(ds, error=None)
+    close_windows(hp.g.windows(p["W"], 1, exact=True), oracle_windows_matrix(res))
+    for exact in (False, True):
+        got = hp.roh(p["W"], p["cutoff"], res["overlap_frac"], exact=exact)
+        assert [(r[0], r[1], r[5], r[6]) for r in got] == oracle_roh_idx(res)
+        bed = orc.format_bed(got, ds.ind_ids, hp.labels, arg_list(args, "--size-bounds"), ds.pop)
+        assert bed == golden_text(name, "out.roh.bed")
+    hp.close()
+
+
+def test_weighted_ld_wlod_and_roh():
+    ds, args, res, p = run_oracle("wlod_cm")
+    hp = HotPath().load(ds, weighted=True, cm=True, error=p["err"])
+    assert hp.L == res["n_used"]
+    assert np.array_equal(hp.gpos, np.concatenate([c["gpos"] for c in res["chroms"]]))
+    homf = hp.g.get_hom_freq()
+    assert np.array_equal(homf, np.concatenate([c["homf"] for c in res["chroms"]]), equal_nan=True)
+    ld = hp.g.ld_band(p["W"], None, want_ld=True)
+    want_ld = np.concatenate([c["LD"] for c in res["chroms"]], axis=0)
+    # integer popcounts + IEEE division/multiplication in the reference's order: bit-exact
+    assert np.array_equal(ld, want_ld, equal_nan=True)
+    close_windows(hp.g.windows(p["W"], 1, weighted=True), oracle_windows_matrix(res))
+    got = hp.roh(p["W"], p["cutoff"], res["overlap_frac"], weighted=True, cm=True)
+    assert [(r[0], r[1], r[5], r[6]) for r in got] == oracle_roh_idx(res)
+    bed = orc.format_bed(got, ds.ind_ids, hp.labels, arg_list(args, "--size-bounds"), ds.pop, cm=True)
+    assert bed == golden_text("wlod_cm", "out.roh.bed")
+    hp.close()
+
+
+def test_weighted_ld_subsample():
+    ds, args = load_case("wlod_cm")
+    sub = np.array([0, 3, 4, 9, 10, 17, 20], np.int32)
+    res = orc.run_pipeline(ds, 25, 0.001, 0.5, 0.25, weighted=True, cm=True, ld_individuals=sub)
+    hp = HotPath().load(ds, weighted=True, cm=True, error=0.001)
+    ld = hp.g.ld_band(25, sub, want_ld=True)
+    assert np.array_equal(ld, np.concatenate([c["LD"] for c in res["chroms"]], axis=0), equal_nan=True)
+    got = hp.roh(25, 0.5, 0.25, weighted=True, cm=True)
+    assert [(r[0], r[1], r[5], r[6]) for r in got] == oracle_roh_idx(res)
+    hp.close()
+
+
+def test_thinned_windows_for_kde_subsample():
+    ds, args = load_case("auto_cutoff")
+    W = 30
+    sub = np.array([1, 5, 6, 20, 39], np.int32)
+    res = orc.run_pipeline(ds, W, 0.001, None, thin_step=W, kde_individuals=sub)
+    hp = HotPath().load(ds, error=0.001)
+    got = hp.thinned(W, W, sub)
+    assert got.shape == res["thinned"].shape
+    assert np.max(np.abs(got - res["thinned"]) / np.maximum(np.abs(res["thinned"]), 1e-3)) <= RTOL_WINDOWS
+    # all individuals: count equals the reference log's "KDE with N points"
+    n = int(golden_text("auto_cutoff", "out.log").split("KDE with ")[1].split(" ")[0])
+    assert len(hp.thinned(W, W)) == n
+    hp.close()
+
+
+def test_cutoff_on_a_window_value_is_resolved_exactly():
+    """A cutoff equal to an actual window value: the chunked pass must detect the ambiguity and the
+    exact re-evaluation must reproduce the reference's decision."""
+    ds, args = load_case("lod_small")
+    W = 50
+    res0 = orc.run_pipeline(ds, W, 0.001, None)
+    F = flatten(res0, 0.001)
+    win = res0["chroms"][0]["win"]
+    vals = np.sort(win[win != orc.MISSING])
+    cutoff = float(vals[len(vals) // 2])
+    res = orc.run_pipeline(ds, W, 0.001, cutoff)
+    hp = HotPath().load(ds, error=0.001)
+    hp.g.set_lut(F["lut"][:hp.L])
+    got = hp.roh(W, cutoff, 0.25, exact=False)
+    assert hp.g.last_stats()["ambiguous_pairs"] >= 1
+    assert [(r[0], r[1], r[5], r[6]) for r in got] == oracle_roh_idx(res)
+    hp.close()
+
+
+def test_empty_and_ragged_inputs():
+    # a chromosome shorter than the window, a single individual, nothing above the cutoff
+    ds = synth.make_dataset(seed=3, n_ind=1, chr_sizes=(40, 300), centromere=None)
+    res = orc.run_pipeline(ds, 60, 0.001, 1e9, 0.25)
+    hp = HotPath().load(ds, error=0.001)
+    assert hp.roh(60, 1e9, 0.25) == []
+    res = orc.run_pipeline(ds, 60, 0.001, -1e9, 0.25)
+    got = hp.roh(60, -1e9, 0.25)
+    assert [(r[0], r[1], r[5], r[6]) for r in got] == oracle_roh_idx(res)
+    hp.close()
+    # 33 individuals (one lane of a second warp), window larger than every chromosome → no windows
+    ds = synth.make_dataset(seed=4, n_ind=33, chr_sizes=(50, 45), centromere=None)
+    hp = HotPath().load(ds, error=0.001)
+    assert hp.roh(64, 0.0, 0.25) == []
+    assert np.all(hp.g.windows(64, 1) == orc.MISSING)
+    hp.close()
+
+
+def test_full_size_properties_c2_shape():
+    """Size-independent properties at a larger shape (2,000 × 60k): exact == chunked ROH,
+    idempotence, per-individual independence (a subset of rows gives the same ROH)."""
+    names, offs, pos, cens = synth.make_positions_genomewide(2, 60000)
+    codes = synth.make_codes(2, 512, 60000)
+
+    class DS:
+        pass
+    ds = DS()
+    ds.chr_names, ds.chr_offsets, ds.pos, ds.centromeres = names, offs, pos, cens
+    ds.gl = None
+    hp = HotPath().load(ds, error=0.001, packed_rows=synth.pack_codes(codes))
+    a = hp.g.call_roh(50, 2.0, 0.25, exact=False)
+    b = hp.g.call_roh(50, 2.0, 0.25, exact=True)
+    c = hp.g.call_roh(50, 2.0, 0.25, exact=False)
+    assert np.array_equal(a, b) and np.array_equal(a, c) and len(a) > 100
+    # sortedness (ind, chr, start) and disjointness within an individual
+    key = a[:, 0].astype(np.int64) * (1 << 32) + a[:, 2]
+    assert np.all(np.diff(key) > 0)
+    hp.close()

@@ -1,0 +1,144 @@
+"""CPU emulation of the product's walker / segment table / stitching (walk.cuh, segments.h compiled
+for the host by tests/host_emu.cpp) against the literal oracle.  Guards the closed-form logic in a
+container without a GPU; the CUDA kernels run the same source on the B200 (tests/test_gpu_*.py)."""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.common import arg, flatten, load_case, oracle_roh_idx, oracle_windows_matrix
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+_EMU = None
+
+
+def emu():
+    global _EMU
+    if _EMU is None:
+        so = os.path.join(HERE, "_hostemu.so")
+        srcs = [os.path.join(HERE, "host_emu.cpp")] + [os.path.join(ROOT, "garlic_b200", "csrc", f)
+                                                       for f in ("walk.cuh", "segments.h", "common.cuh")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC",
+                                   "-o", so, srcs[0]])
+        _EMU = C.CDLL(so)
+    return _EMU
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def thr_of(frac, W):
+    t = frac * W
+    t = t if t >= 1 else 1
+    t = t if t <= W else W
+    return int(math.ceil(t))
+
+
+def emu_roh(F, W, cutoff, thr, chunk, tol, max_gap=200000, use_gl=False):
+    cap = 1 << 16
+    out = np.zeros((cap, 4), np.int32)
+    n_amb = C.c_int(0)
+    n_items = C.c_int(0)
+    n = emu().emu_call_roh(_p(F["rows"]), C.c_int64(F["row_words"]), _p(F["lut"]), _p(F["gl"] if use_gl else None),
+                           C.c_int64(F["L"] + 4160), _p(F["freq"]), C.c_int(F["N"]), C.c_int(len(F["chr_off"]) - 1),
+                           _p(F["chr_off"]), _p(F["pos"]), _p(F["cen"]), C.c_int(max_gap), C.c_int(W),
+                           C.c_double(cutoff), C.c_int(thr), C.c_int(chunk), C.c_double(tol), _p(out), C.c_int(cap),
+                           C.byref(n_amb), C.byref(n_items))
+    return [tuple(int(v) for v in r) for r in out[:n]], n_amb.value, n_items.value
+
+
+def emu_windows(F, W, chunk, step, max_gap=200000, use_gl=False):
+    nchr = len(F["chr_off"]) - 1
+    slots = int(sum((F["chr_off"][c + 1] - F["chr_off"][c] + step - 1) // step for c in range(nchr)))
+    out = np.full((F["N"], slots), orc.MISSING)
+    emu().emu_windows(_p(F["rows"]), C.c_int64(F["row_words"]), _p(F["lut"]), _p(F["gl"] if use_gl else None),
+                      C.c_int64(F["L"] + 4160), _p(F["freq"]), C.c_int(F["N"]), C.c_int(nchr), _p(F["chr_off"]),
+                      _p(F["pos"]), _p(F["cen"]), C.c_int(max_gap), C.c_int(W), C.c_int(chunk), C.c_int(step),
+                      _p(out), C.c_int64(slots))
+    return out
+
+
+CASES = ["lod_0", "lod_1", "lod_2", "lod_3", "lod_small", "auto_overlap_hg19"]
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("chunk", [0, 256])
+def test_roh_matches_oracle(name, chunk):
+    ds, args = load_case(name)
+    W = arg(args, "--winsize", cast=int)
+    err = arg(args, "--error", cast=float)
+    cutoff = arg(args, "--lod-cutoff", cast=float)
+    ov = arg(args, "--overlap-frac", 0.25, float)
+    res = orc.run_pipeline(ds, W, err, cutoff, ov, auto_overlap="--auto-overlap-frac" in args)
+    F = flatten(res, err)
+    got, n_amb, n_items = emu_roh(F, W, cutoff, thr_of(res["overlap_frac"], W), chunk, 0.0 if chunk == 0 else 1e-9)
+    assert got == oracle_roh_idx(res)
+    assert n_amb == 0
+
+
+@pytest.mark.parametrize("name,W", [("lod_0", 25), ("lod_small", 50), ("lod_0", 70), ("lod_small", 33),
+                                     ("lod_small", 32), ("lod_0", 200)])
+def test_windows_exact_chain_bitwise(name, W):
+    """Whole-segment items reproduce the reference's running sums bit for bit (same LUT)."""
+    ds, args = load_case(name)
+    res = orc.run_pipeline(ds, W, 0.002, None)
+    F = flatten(res, 0.002)
+    got = emu_windows(F, W, 0, 1)
+    want = oracle_windows_matrix(res)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("W,chunk", [(25, 256), (50, 512), (10, 256)])
+def test_windows_chunked_within_tolerance(W, chunk):
+    ds, args = load_case("lod_0")
+    res = orc.run_pipeline(ds, W, 0.002, None)
+    F = flatten(res, 0.002)
+    got = emu_windows(F, W, chunk, 1)
+    want = oracle_windows_matrix(res)
+    assert np.array_equal(got == orc.MISSING, want == orc.MISSING)
+    ok = want != orc.MISSING
+    assert np.max(np.abs(got[ok] - want[ok])) < 1e-11
+
+
+def test_thinned_layout():
+    ds, args = load_case("lod_0")
+    res = orc.run_pipeline(ds, 25, 0.002, None)
+    F = flatten(res, 0.002)
+    got = emu_windows(F, 25, 0, 25)
+    want = oracle_windows_matrix(res, 25)
+    assert np.array_equal(got, want)
+
+
+def test_gl_mode_roh_and_windows():
+    ds, args = load_case("gl_pl")
+    W = 30
+    res = orc.run_pipeline(ds, W, None, 1.0, 0.25)
+    F = flatten(res, None, use_gl=True)
+    got, n_amb, _ = emu_roh(F, W, 1.0, thr_of(0.25, W), 0, 0.0, use_gl=True)
+    assert got == oracle_roh_idx(res)
+    w = emu_windows(F, W, 0, 1, use_gl=True)
+    assert np.array_equal(w, oracle_windows_matrix(res))
+
+
+def test_ambiguity_detection_and_cutoff_on_window_value():
+    """A cutoff placed exactly on a window value must be flagged by the chunked pass."""
+    ds, args = load_case("lod_small")
+    W = 50
+    res = orc.run_pipeline(ds, W, 0.001, None)
+    win = res["chroms"][0]["win"]
+    vals = win[win != orc.MISSING]
+    cutoff = float(np.sort(vals)[len(vals) // 2])
+    res = orc.run_pipeline(ds, W, 0.001, cutoff)
+    F = flatten(res, 0.001)
+    got, n_amb, _ = emu_roh(F, W, cutoff, thr_of(0.25, W), 256, 1e-9)
+    assert n_amb >= 1
+    got_exact, n_amb2, _ = emu_roh(F, W, cutoff, thr_of(0.25, W), 0, 0.0)
+    assert got_exact == oracle_roh_idx(res)
