@@ -1,0 +1,440 @@
+#!/usr/bin/env python3
+"""bench.py — GARLIC LOD → ROH hot path on B200: individual-windows/s (BASELINE.json metric).
+
+Own arm (default):  python bench.py --gpus N --steps K --warmup W
+    Workload = BASELINE.json configs[1]: synthetic array, 2,000 individuals x 600k SNPs (22 autosomes,
+    hg19 centromeres, 0.1 % gaps > 200 kb), --winsize 50, --error 0.001, unweighted LOD, --overlap-frac 0.25,
+    fixed --lod-cutoff (host KDE excluded).  One step = one pass of the hot path over the batch:
+    [H2D of the packed genotypes, e2e only] -> K2 allele/missingness counts -> (N>1: NCCL all-reduce of the
+    counts) -> freq + monomorphic filter + K3 compaction -> K4 LOD table -> K5 pass 1 (thinned windows of the
+    20 KDE individuals -> host; N>1: all-gather) -> K5 pass 2 (windows -> cutoff -> coverage -> ROH, fused)
+    -> ROH records to the host.  Sharded by individual: every rank holds 2,000 individuals (weak scaling).
+    `value` has the packed matrix resident in HBM; `e2e` goes through the C ABI with pinned HOST buffers.
+
+Reference arm:      python bench.py --impl reference --gpus N --steps K --warmup W
+    The reference's own calcLODWindows + assembleROHWindows (oracle/_ref/ref_driver, compiled from
+    /root/reference/src) on the host cores, one process per core, each on a bounded sample of the same
+    workload (same SNPs, frequencies and genotypes).  Falls back to the C port (oracle/liboracle.so).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "individual_windows_per_sec"
+UNIT = "individual-windows/s"
+CFG = dict(n_ind=2000, n_loci=600_000, winsize=50, error=0.001, cutoff=2.0, overlap_frac=0.25, max_gap=200000,
+           kde_subsample=20, seed=2)
+WORKLOAD = "configs[1]: synthetic array 2000 ind x 600k SNPs, 22 autosomes, --winsize 50 --error 0.001 unweighted"
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic workload (device-side generation with torch: plumbing only)
+# ------------------------------------------------------------------------------------------------
+def make_rows_torch(torch, dev, n_ind, L, seed, ind_seed, row_bytes, chunk=250):
+    """Packed 2-bit rows uint8[n_ind, row_bytes] on `dev`: Binomial(2,p_l) genotypes, 2 % monomorphic columns,
+    5 planted homozygous tracts (200-2000 SNPs) per individual, 0.5 % missing."""
+    gp = torch.Generator(device=dev)
+    gp.manual_seed(seed)                       # per-SNP frequencies: identical on every rank
+    p = torch.rand(L, generator=gp, device=dev) * 0.9 + 0.05
+    mono = torch.rand(L, generator=gp, device=dev) < 0.02
+    p = torch.where(mono, torch.zeros_like(p), p)
+    gi = torch.Generator(device=dev)
+    gi.manual_seed(ind_seed)                   # genotypes: differ per rank
+    rows = torch.full((n_ind, row_bytes), 0xFF, dtype=torch.uint8, device=dev)
+    ar = torch.arange(L, device=dev)
+    L4 = (L + 3) // 4
+    for i0 in range(0, n_ind, chunk):
+        n = min(chunk, n_ind - i0)
+        h0 = torch.rand((n, L), generator=gi, device=dev) < p
+        h1 = torch.rand((n, L), generator=gi, device=dev) < p
+        for _ in range(5):
+            ln = torch.randint(200, 2000, (n, 1), generator=gi, device=dev)
+            st = (torch.rand((n, 1), generator=gi, device=dev) * (L - 2000)).long()
+            m = (ar >= st) & (ar < st + ln)
+            h1 = torch.where(m, h0, h1)
+        g = h0.to(torch.uint8) + h1.to(torch.uint8)
+        miss = torch.rand((n, L), generator=gi, device=dev) < 0.005
+        g = torch.where(miss, torch.full_like(g, 3), g)
+        if L % 4:
+            g = torch.nn.functional.pad(g, (0, 4 - L % 4), value=3)
+        q = g.view(n, L4, 4)
+        rows[i0:i0 + n, :L4] = q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6)
+    return rows
+
+
+class DevArray:
+    """__cuda_array_interface__ view of a raw device pointer (to hand library buffers to torch.distributed)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+def unpack_rows(rows_u8, L):
+    b = rows_u8[:, :(L + 3) // 4]
+    out = np.empty((b.shape[0], b.shape[1], 4), np.uint8)
+    for k in range(4):
+        out[:, :, k] = (b >> (2 * k)) & 3
+    return out.reshape(b.shape[0], -1)[:, :L]
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            t = [x.strip() for x in ln.split(",")]
+            if len(t) < 9:
+                continue
+            try:
+                sm.append(float(t[1])); mx.append(float(t[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if t[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm helpers (the checker / baseline; never on the product path)
+# ------------------------------------------------------------------------------------------------
+def cpu_chroms(codes_ind_major, keep, freq0, pos0, chr_off0, names, cens):
+    """Filtered per-chromosome SNP-major arrays for oracle/refdrv from the bench's own tables."""
+    chroms = []
+    for c, nm in enumerate(names):
+        lo, hi = int(chr_off0[c]), int(chr_off0[c + 1])
+        k = keep[lo:hi]
+        chroms.append(dict(name="chr" + nm, cen=cens["chr" + nm], pos=np.ascontiguousarray(pos0[lo:hi][k]),
+                           freq=np.ascontiguousarray(freq0[lo:hi][k]), gpos=None, gl=None,
+                           geno=np.ascontiguousarray(codes_ind_major[:, lo:hi][:, k].T.astype(np.int8))))
+    return chroms
+
+
+class CpuSample:
+    """The reference functions (oracle/_ref/ref_driver) or, if that binary is absent, the C port
+    (oracle/liboracle.so) on `n` individuals split over `procs` processes / threads."""
+
+    def __init__(self, chroms, n, W, error, cutoff, ov, max_gap, procs):
+        from oracle import refdrv
+        self.refdrv, self.chroms, self.n, self.W = refdrv, chroms, n, W
+        self.args = (error, cutoff, ov, max_gap)
+        self.units = n * sum(max(0, len(ch["pos"]) - W + 1) for ch in chroms)
+        self.bounds = np.linspace(0, n, procs + 1).astype(int)
+        self.procs = procs
+        self.kind = "reference" if refdrv.available() else "port"
+        self.tmp = None
+        if self.kind == "reference":
+            self.tmp = tempfile.TemporaryDirectory()
+            self.jobs = []
+            for p in range(procs):
+                a, b = int(self.bounds[p]), int(self.bounds[p + 1])
+                if b <= a:
+                    continue
+                sub = [dict(ch, geno=np.ascontiguousarray(ch["geno"][:, a:b])) for ch in chroms]
+                pin, pout = os.path.join(self.tmp.name, "in%d.bin" % p), os.path.join(self.tmp.name, "out%d.bin" % p)
+                refdrv.write_input(pin, sub, b - a, W, error, cutoff=cutoff, overlap_frac=ov, max_gap=max_gap,
+                                   dump_windows=False)
+                self.jobs.append((a, b, [dict(pos=ch["pos"]) for ch in sub], pin, pout))
+
+    def run(self):
+        """→ (seconds, roh).  seconds = compute time of calcLODWindows + assembleROHWindows in the slowest
+        process (input parsing and process start-up excluded)."""
+        error, cutoff, ov, max_gap = self.args
+        W = self.W
+        if self.kind == "reference":
+            ps = [subprocess.Popen([self.refdrv.BIN, j[3], j[4]], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                  for j in self.jobs]
+            if any(p.wait() for p in ps):
+                raise RuntimeError("ref_driver failed")
+            outs = [self.refdrv.read_output(j[4], j[2], j[1] - j[0], W, dump_windows=False) for j in self.jobs]
+            secs = max(o["t_windows"] + o["t_roh"] for o in outs)
+            roh = []
+            for j, o in zip(self.jobs, outs):
+                roh += [(r[0] + j[0], r[1], r[2], r[3]) for r in o["roh"]]
+            return secs, roh
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import oracle as orc
+
+        def work(p):
+            a, b = int(self.bounds[p]), int(self.bounds[p + 1])
+            roh = []
+            for ci, ch in enumerate(self.chroms):
+                if b <= a:
+                    continue
+                win = orc.calc_lod(np.ascontiguousarray(ch["geno"][:, a:b]), ch["freq"], ch["pos"], W, error, max_gap,
+                                   ch["cen"])
+                for i in range(b - a):
+                    s_, e_, _ = orc.assemble(win[i], ch["pos"], None, cutoff, W, max_gap, ov, False, ch["cen"])
+                    roh += [(a + i, ci, int(ch["pos"][x]), int(ch["pos"][y])) for x, y in zip(s_, e_)]
+            return roh
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(self.procs) as ex:
+            parts = list(ex.map(work, range(self.procs)))
+        return time.perf_counter() - t0, sorted(sum(parts, []))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-ind", type=int, default=CFG["n_ind"])
+    ap.add_argument("--n-loci", type=int, default=CFG["n_loci"])
+    ap.add_argument("--cpu-sample", type=int, default=64, help="individuals in the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--exact", action="store_true", help="whole-segment chains in pass 2")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import torch
+    from garlic_b200 import synth
+
+    W, err, cutoff, ov, max_gap = CFG["winsize"], CFG["error"], CFG["cutoff"], CFG["overlap_frac"], CFG["max_gap"]
+    n_ind, L0 = a.n_ind, a.n_loci
+    names, chr_off0, pos0, cens = synth.make_positions_genomewide(CFG["seed"], L0)
+    cen_arr = np.array([cens["chr" + nm] for nm in names], np.int32)
+    row_bytes = ((L0 + 3) // 4 + 15) // 16 * 16
+    config = dict(workload=WORKLOAD if (n_ind, L0) == (CFG["n_ind"], CFG["n_loci"]) else
+                  "REDUCED %d ind x %d SNPs (not the BASELINE config)" % (n_ind, L0),
+                  individuals_per_gpu=n_ind, snps=L0, winsize=W, error=err, lod_cutoff=cutoff, overlap_frac=ov,
+                  kde_subsample=CFG["kde_subsample"], sharding="by individual, %d GPU(s)" % world,
+                  l2="inputs (packed matrix %.0f MB per GPU) larger than the 126 MB L2" % (n_ind * row_bytes / 1e6))
+
+    # -------------------------------------------------------------------------------- reference arm
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        if not torch.cuda.is_available():
+            dev = "cpu"
+        else:
+            dev = "cuda:0"
+        procs = os.cpu_count() or 1
+        per = 4                                    # individuals per process per step (bounded sample)
+        n_s = procs * per
+        rows = make_rows_torch(torch, dev, max(n_s, 256), L0, CFG["seed"], 1000, row_bytes).cpu().numpy()
+        codes_all = unpack_rows(rows, L0)
+        # frequencies of the sample's population: the same tables the GPU arm derives, from these rows
+        nm_ = (codes_all != 3)
+        tot = 2 * nm_.sum(0)
+        na = np.where(nm_, codes_all, 0).sum(0)
+        freq0 = np.where(tot > 0, na / np.maximum(tot, 1), 0.0)
+        keep = (freq0 > 0) & (freq0 < 1)
+        chroms = cpu_chroms(codes_all[:n_s], keep, freq0, pos0, chr_off0, names, cens)
+        cs = CpuSample(chroms, n_s, W, err, cutoff, ov, max_gap, procs)
+        kind, times = cs.kind, []
+        for it in range(a.warmup + a.steps):
+            secs, _ = cs.run()
+            if it >= a.warmup:
+                times.append(secs)
+        units = cs.units
+        ms = 1e3 * float(np.mean(times))
+        val = units / (ms / 1e3)
+        sample = "%d individuals x %d SNPs (of the %d-individual workload) per step, %d processes x %d individuals" % (
+            n_s, int(keep.sum()), n_ind, procs, per)
+        print(json.dumps(dict(metric=METRIC, value=val, unit=UNIT, impl="reference", n_gpus=a.gpus, steps=a.steps,
+                              warmup=a.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                              vs_baseline=None, dtype="f64", data="synthetic", config=config,
+                              cpu_baseline=dict(value=val, unit=UNIT, cores=procs, kind=kind, sample=sample),
+                              e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return 0
+
+    # -------------------------------------------------------------------------------------- own arm
+    if not torch.cuda.is_available():
+        sys.stderr.write("bench.py: no CUDA device; garlic_b200 has no CPU fallback\n")
+        return 1
+    from garlic_b200.api import GarlicGPU
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rows_dev = make_rows_torch(torch, dev, n_ind, L0, CFG["seed"], 1000 + rank, row_bytes)
+    rows_host = torch.empty((n_ind, row_bytes), dtype=torch.uint8, pin_memory=True)
+    rows_host.copy_(rows_dev)
+    torch.cuda.synchronize()
+    rows_host_np = rows_host.numpy()
+
+    g = GarlicGPU(local)
+    g.set_shape(n_ind, L0, chr_off0, pos0, ind_offset=rank * n_ind)
+    stream = torch.cuda.ExternalStream(g.stream(), device=dev)
+    counts_t = None
+    if dist is not None:
+        counts_t = torch.as_tensor(DevArray(g.counts_dev(), (4, L0), "<i4"), device=dev)
+    # the KDE subsample: 20 individuals of the whole job, spread evenly; this rank computes its own
+    n_total = n_ind * world
+    kde_global = np.linspace(0, n_total - 1, CFG["kde_subsample"]).astype(np.int64)
+    kde_local = (kde_global[(kde_global // n_ind) == rank] - rank * n_ind).astype(np.int32)
+    kde_max = max(int(((kde_global // n_ind) == r).sum()) for r in range(world))
+    state = {}
+
+    def step(resident):
+        if not resident:
+            g.put_packed(rows_host_np)                       # H2D from pinned host memory
+        g.count_packed()                                     # K2
+        if dist is not None:
+            g.sync()
+            dist.all_reduce(counts_t)                        # the one data-path collective
+            torch.cuda.synchronize()
+        freq, keep, L = g.filter()                           # freq, keep mask -> host; K3 compaction
+        g.set_tables(err, max_gap, cen_arr)                  # K4
+        thin = g.windows(W, W, individuals=kde_local, exact=False) if len(kde_local) else np.empty((0, 0))
+        if dist is not None:                                 # small all-gather of the thinned LODs
+            slots = g.window_slots(W)
+            mine = torch.full((kde_max, slots), -9999.0, dtype=torch.float64, device=dev)
+            if len(kde_local):
+                mine[:len(kde_local)] = torch.from_numpy(np.ascontiguousarray(thin)).to(dev)
+            allv = torch.empty((world * kde_max, slots), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allv, mine)
+            thin = allv.cpu().numpy()                        # every rank holds the KDE input (host FIGTree)
+        roh = g.call_roh(W, cutoff, ov, exact=a.exact)       # K5 pass 2 (fused) -> ROH records on the host
+        st = g.last_stats()
+        state.update(freq=freq, keep=keep, L=L, thin=thin, roh=roh, stats=st,
+                     h2d=(0 if resident else rows_host_np.nbytes) + pos0.nbytes + chr_off0.nbytes,
+                     d2h=freq.nbytes + keep.nbytes + thin.nbytes + roh.nbytes + 16)
+        return st
+
+    def timed(resident, steps, warmup, sample_clocks):
+        for _ in range(warmup):
+            step(resident)
+        kms, launches0 = [], g.launch_count()
+        cs = ClockSampler(local) if sample_clocks else None
+        barrier()
+        if cs:
+            cs.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            kms.append(step(resident)["kernel_ms"])
+        e1.record(stream)
+        barrier()
+        clocks = cs.stop() if cs else None
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), float(np.mean(kms)), g.launch_count() - launches0, clocks
+
+    g.put_packed_dev(rows_dev.data_ptr(), row_bytes)
+    ms_res, kms, launches, clocks = timed(True, a.steps, a.warmup, True)
+    units_local = state["stats"]["units"]
+    units_total = units_local * world
+    value = units_total * a.steps / (ms_res / 1e3)
+    n_roh, n_amb, n_items, Lk = len(state["roh"]), state["stats"]["ambiguous_pairs"], state["stats"]["items"], state["L"]
+    roh_dev = state["roh"].copy()
+    ms_e2e, _, _, _ = timed(False, a.steps, min(a.warmup, 2) if a.warmup else 0, False)
+    e2e_val = units_total * a.steps / (ms_e2e / 1e3)
+    e2e = dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(state["h2d"]), d2h_bytes_per_step=int(state["d2h"]),
+               ms_per_step=ms_e2e / a.steps)
+    assert np.array_equal(roh_dev, state["roh"]), "resident and host-buffer runs disagree"
+
+    # roofline of the dominant kernel (K5 pass 2, walk_kernel): algorithmic bytes per launch
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = n_ind * Lk / 4.0 + Lk * 32.0 + n_items * 32.0 + n_roh * 16.0
+    achieved = alg_bytes / (kms / 1e3) / 1e9
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                    kernel="walk_kernel<0,true,false> (K5 pass 2: windows->cutoff->coverage->ROH)",
+                    kernel_ms=kms, algorithmic_bytes_per_launch=alg_bytes,
+                    bytes_per_individual_window=alg_bytes / units_local,
+                    peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                    kernel_units_per_s=units_local / (kms / 1e3),
+                    note="2-bit genotypes + per-SNP table: 0.27 B per individual-window, so this kernel is bound by "
+                         "fp64-add / L1 issue, not HBM (SURVEY §8d); frac is reported against HBM as the contract asks")
+    tr = os.path.join(ROOT, "profiles", "r01_walk_traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
+                ms_per_step=ms_res / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic", config=config, e2e=e2e, gpu_launches=int(launches), roofline=roofline,
+                clocks=clocks, roh_found=int(n_roh), loci_used=int(Lk), ambiguous_pairs_reevaluated=int(n_amb),
+                individual_windows_per_step=int(units_total))
+
+    # cpu_baseline: rank 0, N=1 only, bounded sample of the same workload; doubles as a parity check
+    if rank == 0 and world == 1 and not a.no_cpu:
+        n_s = min(a.cpu_sample, n_ind)
+        codes = unpack_rows(rows_host_np[:n_s], L0)
+        chroms = cpu_chroms(codes, state["keep"], state["freq"], pos0, chr_off0, names, cens)
+        cs = CpuSample(chroms, n_s, W, err, cutoff, ov, max_gap, 1)
+        secs, roh_cpu = cs.run()
+        rate, kind = cs.units / secs, cs.kind
+        line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=1, kind=kind, seconds=secs,
+                                    sample="first %d of the %d individuals x %d SNPs, same tables; the reference's "
+                                           "unweighted calcLOD/assembleROHWindows are single-threaded" % (n_s, n_ind, Lk))
+        pos_k = pos0[state["keep"]]
+        got = sorted((int(r[0]), int(r[1]), int(pos_k[r[2]]), int(pos_k[r[3]])) for r in roh_dev if r[0] < n_s)
+        line["parity_vs_cpu_sample"] = "identical ROH (%d)" % len(got) if got == sorted(roh_cpu) else \
+            "MISMATCH: gpu %d vs cpu %d" % (len(got), len(roh_cpu))
+    if rank == 0:
+        print(json.dumps(line))
+    g.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -58,10 +58,12 @@ struct garlic_gpu {
     unsigned out_cap = 0, amb_cap = 0;
     unsigned* d_cnt = nullptr;
     Item* d_items = nullptr;
+    double* d_dump = nullptr;
     size_t items_cap = 0;
     int* d_indlist = nullptr;
     size_t indlist_cap = 0;
     double stats[4] = {0, 0, 0, 0};
+    std::map<void*, size_t> cap;   // bytes behind each device pointer slot (keyed by the slot's address)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -76,12 +78,18 @@ struct garlic_gpu {
 #define LAUNCH(call) do { CK(call); h->launches++; } while (0)
 #define FAIL(msg) do { h->err = (msg); return 1; } while (0)
 
+// (re)allocate a device array; an existing allocation that is large enough is kept (repeated runs
+// of the path on the same shape — window-size scans, benchmark steps — then allocate nothing)
 template <typename T>
 static int dev_alloc(garlic_gpu* h, T** p, size_t n)
 {
-    if (*p) { cudaFree(*p); *p = nullptr; }
     if (n == 0) n = 1;
-    CK(cudaMalloc((void**)p, n * sizeof(T)));
+    const size_t bytes = n * sizeof(T);
+    auto it = h->cap.find((void*)p);
+    if (*p && it != h->cap.end() && it->second >= bytes) return 0;
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    CK(cudaMalloc((void**)p, bytes));
+    h->cap[(void*)p] = bytes;
     return 0;
 }
 template <typename T>
@@ -121,7 +129,7 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     dev_free(h->d_gpos); dev_free(h->d_nomut); dev_free(h->d_norec); dev_free(h->d_wlut); dev_free(h->d_invld);
     dev_free(h->d_homf); dev_free(h->d_keep); dev_free(h->d_src); dev_free(h->d_pos0); dev_free(h->d_chr_of0);
     dev_free(h->d_pos); dev_free(h->d_chr_of); dev_free(h->d_chr_start); dev_free(h->d_chr_param);
-    dev_free(h->d_out); dev_free(h->d_amb); dev_free(h->d_cnt); dev_free(h->d_items); dev_free(h->d_indlist);
+    dev_free(h->d_out); dev_free(h->d_amb); dev_free(h->d_cnt); dev_free(h->d_items); dev_free(h->d_indlist); dev_free(h->d_dump);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -541,8 +549,8 @@ int garlic_gpu_windows(garlic_gpu_t* h, int winsize, int step, int weighted, con
     build_items(h->chr_off, W, segs, chunk, step, items);
     if (upload_items(h, items)) return 1;
     const int64_t slots = garlic_gpu_window_slots(h, step);
-    double* d_dump = nullptr;
-    CK(cudaMalloc(&d_dump, (size_t)n_lanes * slots * sizeof(double)));
+    if (dev_alloc(h, &h->d_dump, (size_t)n_lanes * slots)) return 1;
+    double* d_dump = h->d_dump;
     LAUNCH(launch_fill_f64(d_dump, (size_t)n_lanes * slots, kMissing, h->stream));
     WalkParams P = base_params(h, W);
     P.ind_list = individuals ? h->d_indlist : nullptr;
@@ -556,7 +564,6 @@ int garlic_gpu_windows(garlic_gpu_t* h, int winsize, int step, int weighted, con
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) { h->err = std::string("windows: ") + cudaGetErrorString(e); rc = 1; }
     }
-    cudaFree(d_dump);
     return rc;
 }
 
@@ -566,6 +573,9 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     CK(cudaSetDevice(h->device));
     if (!h->tables) FAIL("call_roh: call set_tables first");
     if (winsize < 2 || winsize > kMaxW) FAIL("call_roh: winsize out of range [2,4096]");
+    // MISSING windows must fail the cutoff test (garlic-roh.cpp:450); at or below the sentinel the
+    // reference overruns inWin[] (:452), so there is no behaviour to reproduce
+    if (!(cutoff > kMissing)) FAIL("call_roh: LOD cutoff must be greater than the MISSING sentinel (-9999)");
     if (weighted && ensure_weighted(h, winsize)) return 1;
     const int W = winsize;
     // garlic-roh.cpp:422-424, compared against integers at :466 and :477

@@ -315,7 +315,10 @@ int orc_assemble(const double *w /*[L] windows of this individual*/, const int32
     double thr = overlap_frac * W;
     thr = (thr >= 1) ? thr : 1;
     thr = (thr <= W) ? thr : W;
-    short *inWin = (short *)calloc((size_t)L, sizeof(short));
+    /* the reference allocates L entries (:437) and writes inWin[k+i] only for non-MISSING windows,
+     * which end at L-1; a cutoff <= MISSING would make MISSING windows pass and overrun the array
+     * there (undefined behaviour) — the product rejects such cutoffs, the oracle pads. */
+    short *inWin = (short *)calloc((size_t)L + (size_t)W, sizeof(short));
     int n = 0;
     for (int k = 0; k < L; k++)
         if (w[k] >= cutoff)

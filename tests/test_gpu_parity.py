@@ -222,13 +222,19 @@ def test_cutoff_on_a_window_value_is_resolved_exactly():
 
 def test_empty_and_ragged_inputs():
     # a chromosome shorter than the window, a single individual, nothing above the cutoff
-    ds = synth.make_dataset(seed=3, n_ind=1, chr_sizes=(40, 300), centromere=None)
+    # (one individual: only heterozygous / half-missing sites survive the 0<freq<1 filter)
+    ds = synth.make_dataset(seed=3, n_ind=1, chr_sizes=(40, 2500), centromere=None)
     res = orc.run_pipeline(ds, 60, 0.001, 1e9, 0.25)
     hp = HotPath().load(ds, error=0.001)
+    assert hp.L == res["n_used"] and len(res["chroms"][0]["pos"]) < 60 < len(res["chroms"][1]["pos"])
     assert hp.roh(60, 1e9, 0.25) == []
-    res = orc.run_pipeline(ds, 60, 0.001, -1e9, 0.25)
-    got = hp.roh(60, -1e9, 0.25)
-    assert [(r[0], r[1], r[5], r[6]) for r in got] == oracle_roh_idx(res)
+    # every valid window passes (cutoff above the MISSING sentinel: at or below -9999 the reference
+    # itself overruns inWin[], garlic-roh.cpp:450-453, and the C ABI rejects it)
+    res = orc.run_pipeline(ds, 60, 0.001, -5000.0, 0.25)
+    got = hp.roh(60, -5000.0, 0.25)
+    assert len(got) >= 1 and [(r[0], r[1], r[5], r[6]) for r in got] == oracle_roh_idx(res)
+    with pytest.raises(Exception):
+        hp.roh(60, -1e9, 0.25)
     hp.close()
     # 33 individuals (one lane of a second warp), window larger than every chromosome → no windows
     ds = synth.make_dataset(seed=4, n_ind=33, chr_sizes=(50, 45), centromere=None)
