@@ -323,16 +323,30 @@ def main():
     kde_max = max(int(((kde_global // n_ind) == r).sum()) for r in range(world))
     state = {}
 
+    phases = {}
+
+    def lap(name, t0):
+        if phases is not None and "on" in phases:
+            g.sync()
+            phases[name] = phases.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return time.perf_counter()
+
     def step(resident):
+        t0 = time.perf_counter()
         if not resident:
             g.put_packed(rows_host_np)                       # H2D from pinned host memory
+            t0 = lap("put_packed_h2d", t0)
         g.count_packed()                                     # K2
+        t0 = lap("count_packed", t0)
         if dist is not None:
             g.sync()
             dist.all_reduce(counts_t)                        # the one data-path collective
             torch.cuda.synchronize()
+        t0 = lap("allreduce_counts", t0)
         freq, keep, L = g.filter()                           # freq, keep mask -> host; K3 compaction
+        t0 = lap("filter_compact", t0)
         g.set_tables(err, max_gap, cen_arr)                  # K4
+        t0 = lap("set_tables", t0)
         thin = g.windows(W, W, individuals=kde_local, exact=False) if len(kde_local) else np.empty((0, 0))
         if dist is not None:                                 # small all-gather of the thinned LODs
             slots = g.window_slots(W)
@@ -342,7 +356,9 @@ def main():
             allv = torch.empty((world * kde_max, slots), dtype=torch.float64, device=dev)
             dist.all_gather_into_tensor(allv, mine)
             thin = allv.cpu().numpy()                        # every rank holds the KDE input (host FIGTree)
+        t0 = lap("pass1_thinned_windows", t0)
         roh = g.call_roh(W, cutoff, ov, exact=a.exact)       # K5 pass 2 (fused) -> ROH records on the host
+        t0 = lap("pass2_call_roh", t0)
         st = g.last_stats()
         state.update(freq=freq, keep=keep, L=L, thin=thin, roh=roh, stats=st,
                      h2d=(0 if resident else rows_host_np.nbytes) + pos0.nbytes + chr_off0.nbytes,
@@ -382,6 +398,9 @@ def main():
     e2e = dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(state["h2d"]), d2h_bytes_per_step=int(state["d2h"]),
                ms_per_step=ms_e2e / a.steps)
     assert np.array_equal(roh_dev, state["roh"]), "resident and host-buffer runs disagree"
+    phases["on"] = 1                                         # one extra, untimed step with a sync after each call
+    step(False)
+    phases.pop("on")
 
     # roofline of the dominant kernel (K5 pass 2, walk_kernel): algorithmic bytes per launch
     peaks = {}
@@ -411,7 +430,8 @@ def main():
                 ms_per_step=ms_res / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                 data="synthetic", config=config, e2e=e2e, gpu_launches=int(launches), roofline=roofline,
                 clocks=clocks, roh_found=int(n_roh), loci_used=int(Lk), ambiguous_pairs_reevaluated=int(n_amb),
-                individual_windows_per_step=int(units_total))
+                individual_windows_per_step=int(units_total),
+                phases_ms_one_synchronised_step={k: round(v, 3) for k, v in phases.items()})
 
     # cpu_baseline: rank 0, N=1 only, bounded sample of the same workload; doubles as a parity check
     if rank == 0 and world == 1 and not a.no_cpu:

@@ -504,14 +504,15 @@ static WalkParams base_params(const garlic_gpu* h, int W)
 }
 
 static int ensure_weighted(garlic_gpu* h, int W);   // wlod tables + LD band present for this W
-static int launch_any_walk(garlic_gpu* h, const WalkParams& P, const Item* items, int n_items, int weighted, bool roh, bool dump)
+static int launch_any_walk(garlic_gpu* h, const WalkParams& P, const Item* items, int n_items, int weighted, bool roh, bool dump,
+                           int tile_snps)
 {
     if (weighted) {
         WlodParams Q;
         Q.base = P; Q.wlut = h->d_wlut; Q.invld = h->d_invld; Q.nomut = h->d_nomut; Q.norec = h->d_norec;
         LAUNCH(launch_wlod_walk(Q, items, n_items, h->have_gl, roh, dump, h->stream));
     } else {
-        LAUNCH(launch_walk(P, items, n_items, h->have_gl, roh, dump, h->stream));
+        LAUNCH(launch_walk(P, items, n_items, h->have_gl, roh, dump, tile_snps <= kTileSnpsMax ? tile_snps : 0, h->stream));
     }
     return 0;
 }
@@ -544,8 +545,8 @@ int garlic_gpu_windows(garlic_gpu_t* h, int winsize, int step, int weighted, con
     std::vector<Item> items;
     build_segments(h->chr_off, h->pos, h->cen, h->max_gap, W, segs);
     int chunk = 0;
-    if (weighted) chunk = std::max(64, pick_chunk(h->L, W, n_lanes) / 8);   // every wLOD window is a fresh sum
-    else if (!exact) chunk = pick_chunk(h->L, W, n_lanes);
+    if (weighted) chunk = std::max(64, pick_chunk(h->L, W, n_lanes, 0) / 8);   // every wLOD window is a fresh sum
+    else if (!exact) chunk = pick_chunk(h->L, W, n_lanes, kTileSnpsMax);
     build_items(h->chr_off, W, segs, chunk, step, items);
     if (upload_items(h, items)) return 1;
     const int64_t slots = garlic_gpu_window_slots(h, step);
@@ -558,7 +559,7 @@ int garlic_gpu_windows(garlic_gpu_t* h, int winsize, int step, int weighted, con
     P.cutoff = 0; P.thr = 1; P.tol = 0;
     P.dump = d_dump; P.dump_stride = slots; P.dump_step = step;
     CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
-    int rc = launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, false, true);
+    int rc = launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, false, true, items_tile_snps(items, W));
     if (!rc) {
         cudaError_t e = cudaMemcpyAsync(out, d_dump, (size_t)n_lanes * slots * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -588,8 +589,8 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     std::vector<Item> items;
     build_segments(h->chr_off, h->pos, h->cen, h->max_gap, W, segs);
     int chunk = 0;
-    if (weighted) chunk = std::max(64, pick_chunk(h->L, W, h->n_ind) / 8);
-    else if (!exact) chunk = pick_chunk(h->L, W, h->n_ind);
+    if (weighted) chunk = std::max(64, pick_chunk(h->L, W, h->n_ind, 0) / 8);
+    else if (!exact) chunk = pick_chunk(h->L, W, h->n_ind, kTileSnpsMax);
     build_items(h->chr_off, W, segs, chunk, 0, items);
     if (upload_items(h, items)) return 1;
     int64_t n_win = 0;
@@ -619,7 +620,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         }
         CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
         CK(cudaEventRecord(h->ev0, h->stream));
-        if (launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, true, false)) return 1;
+        if (launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, true, false, items_tile_snps(items, W))) return 1;
         CK(cudaEventRecord(h->ev1, h->stream));
         unsigned cnt[4];
         CK(cudaMemcpyAsync(cnt, h->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
@@ -664,7 +665,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
             P.cutoff = cutoff; P.thr = thr; P.tol = 0;
             P.ind_list = h->d_indlist; P.n_lanes = (int)inds.size();
             CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
-            if (launch_any_walk(h, P, h->d_items, 1, weighted, true, false)) return 1;
+            if (launch_any_walk(h, P, h->d_items, 1, weighted, true, false, items_tile_snps(its, W))) return 1;
             unsigned cnt[4];
             CK(cudaMemcpyAsync(cnt, h->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));

@@ -10,63 +10,132 @@
 namespace garlic {
 
 // ------------------------------------------------------------------------------------------
-// K5: fused windows → ROH.  One warp = 32 individuals walking one item in lock-step (so every
-// LUT read of a step is a single 32-byte sector shared by the warp); a CTA's warps take
-// neighbouring individual groups of the SAME item, consecutive CTAs take the same item too,
-// so the item's LUT range and genotype words stay L1/L2-resident.
+// K5: fused windows → ROH.  One warp = 32 individuals walking one item (a chunk of SNPs) in
+// lock-step; the warps of a CTA take neighbouring individual groups of the SAME item, so the item's
+// slice of the per-SNP LOD table is staged ONCE per CTA into shared memory by a TMA bulk copy
+// (cp.async.bulk + mbarrier) and every table lookup of the walk is a conflict-free LDS (all lanes of a
+// step read the same 32-byte entry).  Genotype words stream from HBM (each lane its own row; 8-byte
+// reads that hit the same 32-byte sector four blocks in a row).
+// TILE = false: table read from global memory (whole-segment exact chains, very large windows).
 // ------------------------------------------------------------------------------------------
-template <int SRC, bool ROH, bool DUMP>
-__global__ void __launch_bounds__(128)
-walk_kernel(const WalkParams P, const Item* __restrict__ items, int n_items, int n_groups)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
 {
-    extern __shared__ uint32_t ring_smem[];   // [NW][blockDim.x] window-flag history
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int SRC, bool ROH, bool DUMP, bool TILE>
+__global__ void __launch_bounds__(kWalkThreads, TILE ? 4 : 2)
+walk_kernel(const WalkParams P, const Item* __restrict__ items, int n_items, int n_groups, int tile_bytes)
+{
+    extern __shared__ __align__(128) unsigned char walk_smem[];
+    // layout: [tile (tile_bytes, TILE only)] [ring: NW * blockDim words] [mbarrier]
+    unsigned char* tile_s = walk_smem;
+    uint32_t* ring_smem = reinterpret_cast<uint32_t*>(walk_smem + (TILE ? tile_bytes : 0));
+    const int NW = ((P.W + 31) >> 5) + 1;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(ring_smem + NW * blockDim.x);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gpb = blockDim.x >> 5;
     const int gblocks = (n_groups + gpb - 1) / gpb;
     const long long total = (long long)n_items * gblocks;
+    if (TILE) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+    }
+    uint32_t phase = 0;
     for (long long u = blockIdx.x; u < total; u += gridDim.x) {
         const int item = (int)(u / gblocks);
         const int group = (int)(u % gblocks) * gpb + warp;
-        if (group >= n_groups) continue;
-        const int k = group * 32 + lane;
-        const bool active = k < P.n_lanes;
         const Item it = items[item];
-        walk_item<SRC, ROH, DUMP>(P, it, active ? k : P.n_lanes - 1, active, ring_smem + threadIdx.x,
-                                  blockDim.x);
+        const char* tile = reinterpret_cast<const char*>(P.lut);
+        int tile_lo = 0;
+        if (TILE) {
+            // SNPs the walk touches: [w0, w0 + 32*nblk + W) (fresh sum, slide-in / slide-out streams)
+            const int nblk = (it.own_hi - 1 - it.w0 + 31) >> 5;
+            const uint32_t bytes = (uint32_t)(32 * nblk + P.W) * 32u;
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(bar, bytes);
+                tma_load_1d(tile_s, P.lut + (int64_t)it.w0 * 4, bytes, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            tile = reinterpret_cast<const char*>(tile_s);
+            tile_lo = it.w0;
+        }
+        if (group < n_groups) {
+            const int k = group * 32 + lane;
+            const bool active = k < P.n_lanes;
+            walk_item<SRC, ROH, DUMP>(P, it, active ? k : P.n_lanes - 1, active, ring_smem + threadIdx.x,
+                                      blockDim.x, tile, tile_lo);
+        }
+        if (TILE) __syncthreads();   // every warp is done with the tile before the next copy lands
     }
 }
 
 template <int SRC, bool ROH, bool DUMP>
-static cudaError_t launch_walk_t(const WalkParams& P, const Item* items, int n_items, cudaStream_t st)
+static cudaError_t launch_walk_t(const WalkParams& P, const Item* items, int n_items, int tile_snps, cudaStream_t st)
 {
     if (n_items == 0 || P.n_lanes == 0) return cudaSuccess;
-    const int threads = 128;
+    const int threads = kWalkThreads;
     const int n_groups = (P.n_lanes + 31) / 32;
     const int gpb = threads / 32;
     const long long total = (long long)n_items * ((n_groups + gpb - 1) / gpb);
     const int NW = ((P.W + 31) >> 5) + 1;
-    const size_t smem = (size_t)NW * threads * sizeof(uint32_t);
+    const bool tile = (SRC == 0) && tile_snps > 0;
+    const int tile_bytes = tile ? tile_snps * 32 : 0;
+    const size_t smem = (size_t)tile_bytes + (size_t)NW * threads * sizeof(uint32_t) + 16;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long grid = total;
-    const long long cap = (long long)sms * 16 * 8;   // persistent-ish: ≤ 8 waves of 16 CTAs/SM
+    const long long cap = (long long)sms * 4 * 16;   // persistent-ish: ≤ 16 waves of 4 CTAs/SM
     if (grid > cap) grid = cap;
-    walk_kernel<SRC, ROH, DUMP><<<(unsigned)grid, threads, smem, st>>>(P, items, n_items, n_groups);
+    if (tile) {
+        auto kern = walk_kernel<SRC, ROH, DUMP, true>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<(unsigned)grid, threads, smem, st>>>(P, items, n_items, n_groups, tile_bytes);
+    } else {
+        walk_kernel<SRC, ROH, DUMP, false><<<(unsigned)grid, threads, smem, st>>>(P, items, n_items, n_groups, 0);
+    }
     return cudaGetLastError();
 }
 
 cudaError_t launch_walk(const WalkParams& P, const Item* items, int n_items, bool gl_mode, bool roh,
-                        bool dump, cudaStream_t st)
+                        bool dump, int tile_snps, cudaStream_t st)
 {
     if (gl_mode) {
-        if (roh && !dump) return launch_walk_t<1, true, false>(P, items, n_items, st);
-        if (!roh && dump) return launch_walk_t<1, false, true>(P, items, n_items, st);
-        return launch_walk_t<1, true, true>(P, items, n_items, st);
+        if (roh && !dump) return launch_walk_t<1, true, false>(P, items, n_items, 0, st);
+        if (!roh && dump) return launch_walk_t<1, false, true>(P, items, n_items, 0, st);
+        return launch_walk_t<1, true, true>(P, items, n_items, 0, st);
     }
-    if (roh && !dump) return launch_walk_t<0, true, false>(P, items, n_items, st);
-    if (!roh && dump) return launch_walk_t<0, false, true>(P, items, n_items, st);
-    return launch_walk_t<0, true, true>(P, items, n_items, st);
+    if (roh && !dump) return launch_walk_t<0, true, false>(P, items, n_items, tile_snps, st);
+    if (!roh && dump) return launch_walk_t<0, false, true>(P, items, n_items, tile_snps, st);
+    return launch_walk_t<0, true, true>(P, items, n_items, tile_snps, st);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -7,8 +7,12 @@
 
 namespace garlic {
 
+constexpr int kWalkThreads = 256;     // 8 individual groups (warps) of one item per CTA
+constexpr int kTileSnpsMax = 1536;    // table tile staged per CTA: 1536 SNPs × 32 B = 48 KB
+
+// tile_snps > 0: every item touches at most tile_snps SNPs → stage its table slice in shared memory
 cudaError_t launch_walk(const WalkParams& P, const Item* items, int n_items, bool gl_mode, bool roh,
-                        bool dump, cudaStream_t st);
+                        bool dump, int tile_snps, cudaStream_t st);
 cudaError_t launch_fill_f64(double* p, size_t n, double v, cudaStream_t st);
 cudaError_t launch_first_allele(const uint8_t* alleles, int n_snp, int n_ind, int ind_offset, int missing,
                                 unsigned long long* key, cudaStream_t st);

@@ -41,15 +41,27 @@ inline void build_segments(const std::vector<int64_t>& chr_off, const std::vecto
     }
 }
 
-// chunk length (in owned SNPs) that yields enough warps to fill 148 SMs a few times over
-inline int pick_chunk(int64_t L, int W, int n_lanes)
+// Chunk length (owned SNPs per item) of the chunked fast pass.  Preferred: the largest chunk whose
+// table slice (owned SNPs + W-1 lead-in windows + W slide-in SNPs + block rounding) fits the shared-
+// memory tile of tile_max SNPs; windows too large for that fall back to a chunk sized to fill the GPU.
+inline int pick_chunk(int64_t L, int W, int n_lanes, int tile_max)
 {
+    const int c_tile = (tile_max - 2 * W - 32) / 32 * 32;
+    if (c_tile >= 256) return c_tile;
     const int n_groups = (n_lanes + 31) / 32;
     const int64_t target_items = std::max<int64_t>(1, (148 * 16 * 4 + n_groups - 1) / n_groups);
     int64_t ch = L / target_items;
     const int64_t lo = std::max(256, 8 * W);
     ch = std::max<int64_t>(lo, std::min<int64_t>(ch, 8192));
     return (int)((ch + 31) / 32 * 32);
+}
+
+// SNPs an item's walk touches: [w0, w0 + 32*ceil((own_hi-1-w0)/32) + W)  (see walk_kernel)
+inline int items_tile_snps(const std::vector<Item>& items, int W)
+{
+    int m = 0;
+    for (const Item& it : items) m = std::max(m, 32 * ((it.own_hi - 1 - it.w0 + 31) >> 5) + W);
+    return m;
 }
 
 // chunk = 0: one item per segment (exact chains).  step > 0: thinning slots for window dumps.
@@ -67,9 +79,9 @@ inline void build_items(const std::vector<int64_t>& chr_off, int W, const std::v
         const Segment& s = segs[si];
         const int a = s.ws, b = s.we + W - 1;
         int n = 1, size = b - a;
-        if (chunk > 0 && b - a > chunk + chunk / 2) {
+        if (chunk > 0 && b - a > chunk) {
             n = (b - a + chunk - 1) / chunk;
-            size = ((b - a + n - 1) / n + 31) / 32 * 32;
+            size = std::min(chunk, ((b - a + n - 1) / n + 31) / 32 * 32);
             n = (b - a + size - 1) / size;
         }
         for (int i = 0; i < n; ++i) {

@@ -38,15 +38,20 @@ GHD double lod_eval(int g, double f, double e)
     return log10(a / na);
 }
 
+// Where a lane reads its per-SNP LOD from.  SRC 0: the per-SNP table (4 doubles per SNP: g=0,1,2,missing)
+// seen through `tile`, which holds the entries of SNPs tile_lo, tile_lo+1, … — either the whole table
+// in global memory (tile_lo = 0) or the item's slice staged into shared memory by TMA (kernels.cu).
+// SRC 1: per-genotype error rates (GL mode), lod() evaluated on the fly.
 template <int SRC>
 struct LaneCtx {
     const uint64_t* row;
-    const double* lut;
+    const char* tile;
+    int tile_lo;
     const double* freq;
     const double* glrow;
     GHD double aval(int s, int g) const
     {
-        if (SRC == 0) return lut[(int64_t)s * 4 + g];
+        if (SRC == 0) return *reinterpret_cast<const double*>(tile + ((uint32_t)(s - tile_lo) * 32u + (uint32_t)g * 8u));
         return lod_eval(g, freq[s], glrow[s]);
     }
 };
@@ -87,75 +92,133 @@ GHD void dump_window(const WalkParams& P, const Item& it, int k, bool active, in
         P.dump[(int64_t)k * P.dump_stride + it.thin_base + d / P.dump_step] = win;
 }
 
-// One block of 32 slide steps.  FULL: every step is a valid window and inside the owned range.
-template <int SRC, bool ROH, bool DUMP, bool FULL>
+// byte offset (g*8) of genotype k's table entry, straight from the packed word: no multiply
+GHD uint32_t lut_off(uint32_t w, int kk)
+{
+    return kk >= 2 ? ((w >> (2 * kk - 3)) & 24u) : ((w << (3 - 2 * kk)) & 24u);
+}
+
+// One block of 32 slide steps, in two phases.
+//   phase 1: the window chain win = (win - lod(out)) + lod(in) (garlic-roh.cpp:98-100) and the cutoff
+//            test (:450) for all 32 steps → flag word(s).  With CHK the test is made against
+//            cutoff±tol: where both agree they equal the test against the cutoff itself, where they
+//            differ the (individual, segment) pair is marked for exact re-evaluation.
+//   phase 2: coverage count (sliding form of :446-454) and run-length on the 32 flag bits — skipped by
+//            the whole warp when no lane has a flag in this block or a flag still inside its last W
+//            windows (the common case outside ROH).
+// FULL: every step is a valid window and inside the owned range.
+template <int SRC, bool ROH, bool DUMP, bool FULL, bool CHK>
 GHD void walk_block(const WalkParams& P, const Item& it, const LaneCtx<SRC>& C, LaneState& S, int ind,
                     int k_slot, bool active, uint64_t gin, uint64_t gout, int tblk, uint32_t ow)
 {
     const int W = P.W;
-    const double cut = P.cutoff, cut_lo = P.cutoff - P.tol, cut_hi = P.cutoff + P.tol;
-    const bool chk = P.tol > 0;
+    const double cut_hi = CHK ? P.cutoff + P.tol : P.cutoff, cut_lo = P.cutoff - P.tol;
     const int s_in0 = tblk + W - 1, s_out0 = tblk - 1;
-    uint32_t fw = 0, cw = 0;
+    uint32_t vm = 0xffffffffu;             // valid-window mask of the block
+    if (!FULL) {
+        const int n = it.we - tblk;
+        vm = n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
+    }
+    uint32_t fhi = 0, flo = 0;
     double win = S.win;
+    if (SRC == 0) {
+        const uint32_t bi = (uint32_t)(s_in0 - C.tile_lo) * 32u, bo = (uint32_t)(s_out0 - C.tile_lo) * 32u;
+        const uint32_t gi0 = (uint32_t)gin, gi1 = (uint32_t)(gin >> 32);
+        const uint32_t go0 = (uint32_t)gout, go1 = (uint32_t)(gout >> 32);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const uint32_t oi = lut_off(k < 16 ? gi0 : gi1, k & 15), oo = lut_off(k < 16 ? go0 : go1, k & 15);
+            const double a_in = *reinterpret_cast<const double*>(C.tile + ((bi | oi) + k * 32));
+            const double a_out = *reinterpret_cast<const double*>(C.tile + ((bo | oo) + k * 32));
+            // exact chains keep the reference's order (garlic-roh.cpp:98-100); the tolerance-checked
+            // pass takes the difference off the dependent chain (same error bound)
+            if (CHK) win = win + (a_in - a_out);
+            else win = (win - a_out) + a_in;
+            if (ROH) {
+                if (win >= cut_hi) fhi |= 1u << k;                           // garlic-roh.cpp:450
+                if (CHK) { if (win >= cut_lo) flo |= 1u << k; }
+            }
+            if (DUMP) { if ((vm >> k) & 1u) dump_window<DUMP>(P, it, k_slot, active, tblk + k, win); }
+        }
+    } else {
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            const int go = (int)(gout >> (2 * k)) & 3, gi = (int)(gin >> (2 * k)) & 3;
+            win = (win - C.aval(s_out0 + k, go)) + C.aval(s_in0 + k, gi);
+            if (ROH) {
+                if (win >= cut_hi) fhi |= 1u << k;
+                if (CHK) { if (win >= cut_lo) flo |= 1u << k; }
+            }
+            if (DUMP) { if ((vm >> k) & 1u) dump_window<DUMP>(P, it, k_slot, active, tblk + k, win); }
+        }
+    }
+    S.win = win;
+    if (!ROH) return;
+    fhi &= vm;
+    if (CHK) { flo &= vm; S.ambig |= (fhi != flo); }
+    const uint32_t fw = fhi;
+    S.fw = fw;   // the block's window-flag word, stored to the history ring by the caller
+
+    bool busy = (fw | (uint32_t)S.cov) != 0u;   // an open run implies cov >= thr >= 1
+#ifdef __CUDA_ARCH__
+    busy = __any_sync(0xffffffffu, busy);
+#endif
+    if (!busy) {
+        if (W <= 32) S.hist = 0;
+        return;
+    }
+    uint32_t cw = 0;
     int cov = S.cov;
     uint32_t hist = S.hist;
-    bool amb = S.ambig;
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
-        const int go = (int)(gout >> (2 * k)) & 3, gi = (int)(gin >> (2 * k)) & 3;
-        win = (win - C.aval(s_out0 + k, go)) + C.aval(s_in0 + k, gi);   // garlic-roh.cpp:98-100
-        const bool valid = FULL || (tblk + k < it.we);
-        const bool f = valid && (win >= cut);                            // garlic-roh.cpp:450
-        if (chk && valid) amb |= ((win >= cut_lo) != (win >= cut_hi));
-        if (DUMP && valid) dump_window<DUMP>(P, it, k_slot, active, tblk + k, win);
+        const uint32_t f = (fw >> k) & 1u;
         uint32_t o;
-        if (W <= 32) { o = (hist >> (W - 1)) & 1u; hist = (hist << 1) | (uint32_t)f; }
+        if (W <= 32) { o = (hist >> (W - 1)) & 1u; hist = (hist << 1) | f; }
         else o = (ow >> k) & 1u;
         cov += (int)f - (int)o;                                          // sliding form of :446-454
-        fw |= (uint32_t)f << k;
         cw |= (uint32_t)(cov >= P.thr) << k;                             // garlic-roh.cpp:466
     }
-    S.win = win; S.cov = cov; S.hist = hist; S.ambig = amb;
-    S.fw = fw;   // the block's window-flag word, stored to the history ring by the caller
+    S.cov = cov; S.hist = hist;
     // run-length on the 32 covered bits (bit-parallel edge detection)
-    if (ROH) {
-        uint32_t em = 0xffffffffu;
-        if (!FULL) {
-            em = 0;
-#pragma unroll
-            for (int k = 0; k < 32; ++k)
-                em |= (uint32_t)((tblk + k >= it.own_lo) && (tblk + k < it.own_hi)) << k;
-        }
-        const uint32_t x = cw & em;
-        const uint32_t inr = S.run_start >= 0 ? 1u : 0u;
-        uint32_t trans = x ^ ((x << 1) | inr);
-        while (trans) {
+    uint32_t em = 0xffffffffu;
+    if (!FULL) {
+        const int lo = it.own_lo - tblk, hi = it.own_hi - tblk;          // owned steps are [lo, hi)
+        const uint32_t mlo = lo <= 0 ? 0xffffffffu : (lo >= 32 ? 0u : ~((1u << lo) - 1u));
+        const uint32_t mhi = hi >= 32 ? 0xffffffffu : (hi <= 0 ? 0u : ((1u << hi) - 1u));
+        em = mlo & mhi;
+    }
+    const uint32_t x = cw & em;
+    const uint32_t inr = S.run_start >= 0 ? 1u : 0u;
+    uint32_t trans = x ^ ((x << 1) | inr);
+    while (trans) {
 #ifdef __CUDA_ARCH__
-            const int k = __ffs((int)trans) - 1;
+        const int k = __ffs((int)trans) - 1;
 #else
-            const int k = __builtin_ctz(trans);
+        const int k = __builtin_ctz(trans);
 #endif
-            trans &= trans - 1;
-            const int t = tblk + k;
-            if ((x >> k) & 1u) S.run_start = t;
-            else { emit_run(P, it, ind, active, S.run_start, t - 1); S.run_start = -1; }
-        }
+        trans &= trans - 1;
+        const int t = tblk + k;
+        if ((x >> k) & 1u) S.run_start = t;
+        else { emit_run(P, it, ind, active, S.run_start, t - 1); S.run_start = -1; }
     }
 }
 
 // Walk one item for one individual.  ring: this lane's flag-history ring (NW words, stride rstride).
 template <int SRC, bool ROH, bool DUMP>
-GHD void walk_item(const WalkParams& P, const Item& it, int k_slot, bool active, uint32_t* ring, int rstride)
+GHD void walk_item(const WalkParams& P, const Item& it, int k_slot, bool active, uint32_t* ring, int rstride,
+                   const char* tile, int tile_lo)
 {
     const int W = P.W;
     const int ind = P.ind_list ? P.ind_list[k_slot] : k_slot;
     LaneCtx<SRC> C;
     C.row = P.geno + (int64_t)ind * P.row_words;
-    C.lut = P.lut;
+    C.tile = tile;
+    C.tile_lo = tile_lo;
     C.freq = P.freq;
     C.glrow = (SRC == 1) ? P.gl + (int64_t)ind * P.gl_stride : nullptr;
     const int NW = ((W + 31) >> 5) + 1;
+    const bool chk = P.tol > 0;
 
     // fresh sum for window w0, ascending (garlic-roh.cpp:57-71)
     double win = 0.0;
@@ -166,8 +229,8 @@ GHD void walk_item(const WalkParams& P, const Item& it, int k_slot, bool active,
     }
     LaneState S;
     S.win = win; S.run_start = -1; S.fw = 0; S.ambig = false;
-    const bool f0 = win >= P.cutoff;
-    if (P.tol > 0) S.ambig = ((win >= P.cutoff - P.tol) != (win >= P.cutoff + P.tol));
+    const bool f0 = win >= (chk ? P.cutoff + P.tol : P.cutoff);
+    if (chk) S.ambig = (f0 != (win >= P.cutoff - P.tol));
     dump_window<DUMP>(P, it, k_slot, active, it.w0, win);
     S.cov = (int)f0;
     S.hist = (uint32_t)f0;
@@ -181,28 +244,35 @@ GHD void walk_item(const WalkParams& P, const Item& it, int k_slot, bool active,
     const int sa = 2 * ((it.w0 + W) & 31), sb = 2 * (it.w0 & 31);
     const int64_t ia = (it.w0 + W) >> 5, ib = it.w0 >> 5;
     uint64_t a_lo = C.row[ia], b_lo = C.row[ib];
+    uint64_t a_hi = C.row[ia + 1], b_hi = C.row[ib + 1];
     const int r = (32 - (W & 31)) & 31;
     const int nwords = (W + 31) >> 5;
     for (int j = 0, m0 = 0; m0 < M; ++j, m0 += 32) {
-        const uint64_t a_hi = C.row[ia + j + 1], b_hi = C.row[ib + j + 1];
+        // next block's words are requested before this block's arithmetic (rows are padded)
+        const uint64_t a_nx = C.row[ia + j + 2], b_nx = C.row[ib + j + 2];
         const uint64_t gin = sa ? ((a_lo >> sa) | (a_hi << (64 - sa))) : a_lo;
         const uint64_t gout = sb ? ((b_lo >> sb) | (b_hi << (64 - sb))) : b_lo;
-        a_lo = a_hi; b_lo = b_hi;
+        a_lo = a_hi; b_lo = b_hi; a_hi = a_nx; b_hi = b_nx;
         const int tblk = it.w0 + 1 + m0;
         uint32_t ow = 0;
-        if (W > 32) {
+        if (ROH && W > 32) {
             const int qi = j + 1 - nwords;
             const uint32_t w0_ = qi >= 0 ? ring[(qi % NW) * rstride] : 0u;
             const uint32_t w1_ = (qi + 1) >= 0 ? ring[((qi + 1) % NW) * rstride] : 0u;
             ow = r ? ((w0_ >> r) | (w1_ << (32 - r))) : w0_;
         }
         const bool full = (tblk + 31 < it.we) && (tblk >= it.own_lo) && (tblk + 31 < it.own_hi);
-        if (full) walk_block<SRC, ROH, DUMP, true>(P, it, C, S, ind, k_slot, active, gin, gout, tblk, ow);
-        else walk_block<SRC, ROH, DUMP, false>(P, it, C, S, ind, k_slot, active, gin, gout, tblk, ow);
-        if (W > 32) ring[((j + 1) % NW) * rstride] = S.fw;
+        if (chk) {
+            if (full) walk_block<SRC, ROH, DUMP, true, true>(P, it, C, S, ind, k_slot, active, gin, gout, tblk, ow);
+            else walk_block<SRC, ROH, DUMP, false, true>(P, it, C, S, ind, k_slot, active, gin, gout, tblk, ow);
+        } else {
+            if (full) walk_block<SRC, ROH, DUMP, true, false>(P, it, C, S, ind, k_slot, active, gin, gout, tblk, ow);
+            else walk_block<SRC, ROH, DUMP, false, false>(P, it, C, S, ind, k_slot, active, gin, gout, tblk, ow);
+        }
+        if (ROH && W > 32) ring[((j + 1) % NW) * rstride] = S.fw;
     }
     if (ROH && S.run_start >= 0) emit_run(P, it, ind, active, S.run_start, it.own_hi - 1);
-    if (P.tol > 0 && S.ambig && active) {
+    if (chk && S.ambig && active) {
 #ifdef __CUDA_ARCH__
         unsigned p = atomicAdd(P.out_count + 1, 1u);
 #else

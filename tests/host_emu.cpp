@@ -38,8 +38,8 @@ int emu_call_roh(const uint64_t* geno, int64_t row_words, const double* lut, con
     std::vector<uint32_t> ring(NW);
     for (const Item& it : items)
         for (int k = 0; k < n_ind; ++k) {
-            if (gl) walk_item<1, true, false>(P, it, k, true, ring.data(), 1);
-            else walk_item<0, true, false>(P, it, k, true, ring.data(), 1);
+            if (gl) walk_item<1, true, false>(P, it, k, true, ring.data(), 1, (const char*)lut, 0);
+            else walk_item<0, true, false>(P, it, k, true, ring.data(), 1, (const char*)lut, 0);
         }
     recs.resize(cnt[0]);
     *n_amb = (int)cnt[1];
@@ -75,8 +75,8 @@ int emu_windows(const uint64_t* geno, int64_t row_words, const double* lut, cons
     std::vector<uint32_t> ring(NW);
     for (const Item& it : items)
         for (int k = 0; k < n_ind; ++k) {
-            if (gl) walk_item<1, false, true>(P, it, k, true, ring.data(), 1);
-            else walk_item<0, false, true>(P, it, k, true, ring.data(), 1);
+            if (gl) walk_item<1, false, true>(P, it, k, true, ring.data(), 1, (const char*)lut, 0);
+            else walk_item<0, false, true>(P, it, k, true, ring.data(), 1, (const char*)lut, 0);
         }
     return (int)items.size();
 }
