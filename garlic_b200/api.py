@@ -206,18 +206,20 @@ class GarlicGPU:
                                              C.c_int(n), C.c_int(int(exact)), _p(out)))
         return out
 
-    def call_roh(self, W, cutoff, overlap_frac, weighted=False, exact=False, cap=1 << 20):
+    def call_roh(self, W, cutoff, overlap_frac, weighted=False, exact=False, cap=1 << 16):
+        """→ int32[n, 4] rows (ind, chr, start_idx, stop_idx), sorted by (ind, chr, start)."""
+        buf = getattr(self, "_roh_buf", None)
+        if buf is None or len(buf) < cap:
+            buf = self._roh_buf = np.empty((cap, 4), np.int32)
         while True:
-            buf = (RohRec * cap)()
             cnt = C.c_int64(0)
             self._ck(self.lib.garlic_gpu_call_roh(self.h, C.c_int(W), C.c_double(cutoff), C.c_double(overlap_frac),
-                                                  C.c_int(int(weighted)), C.c_int(int(exact)), buf, C.c_int64(cap),
-                                                  C.byref(cnt)))
-            if cnt.value <= cap:
+                                                  C.c_int(int(weighted)), C.c_int(int(exact)), _p(buf),
+                                                  C.c_int64(len(buf)), C.byref(cnt)))
+            if cnt.value <= len(buf):
                 break
-            cap = cnt.value + 1024
-        arr = np.frombuffer(buf, dtype=np.int32, count=4 * cnt.value).reshape(-1, 4).copy()
-        return arr
+            buf = self._roh_buf = np.empty((cnt.value + 1024, 4), np.int32)
+        return buf[:cnt.value].copy()
 
     def last_stats(self):
         s = (C.c_double * 4)()

@@ -35,6 +35,7 @@ struct garlic_gpu {
     std::vector<int64_t> chr_off0, chr_off;
     std::vector<int32_t> pos0, pos, src, cen;
     std::vector<double> gpos;
+    std::vector<Stretch> stretches;   // gap/centromere-free SNP stretches (built in set_tables)
     bool have_geno0 = false, filtered = false, tables = false, have_gl = false, have_ld = false;
     int gl_type = GARLIC_GL_ERROR;
     double error = -1, mu = 1e-9;
@@ -63,6 +64,11 @@ struct garlic_gpu {
     int* d_indlist = nullptr;
     size_t indlist_cap = 0;
     double stats[4] = {0, 0, 0, 0};
+    uint32_t* d_keepw = nullptr;
+    int* d_first_word = nullptr;
+    uint8_t* d_first_skip = nullptr;
+    uint8_t* pin = nullptr;        // pinned host staging buffer
+    size_t pin_cap = 0;
     std::map<void*, size_t> cap;   // bytes behind each device pointer slot (keyed by the slot's address)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -94,6 +100,15 @@ static int dev_alloc(garlic_gpu* h, T** p, size_t n)
 }
 template <typename T>
 static void dev_free(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+static int pin_alloc(garlic_gpu* h, size_t bytes)
+{
+    if (h->pin && h->pin_cap >= bytes) return 0;
+    if (h->pin) { cudaFreeHost(h->pin); h->pin = nullptr; h->pin_cap = 0; }
+    CK(cudaMallocHost((void**)&h->pin, bytes));
+    h->pin_cap = bytes;
+    return 0;
+}
 
 extern "C" {
 
@@ -130,6 +145,8 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     dev_free(h->d_homf); dev_free(h->d_keep); dev_free(h->d_src); dev_free(h->d_pos0); dev_free(h->d_chr_of0);
     dev_free(h->d_pos); dev_free(h->d_chr_of); dev_free(h->d_chr_start); dev_free(h->d_chr_param);
     dev_free(h->d_out); dev_free(h->d_amb); dev_free(h->d_cnt); dev_free(h->d_items); dev_free(h->d_indlist); dev_free(h->d_dump);
+    dev_free(h->d_keepw); dev_free(h->d_first_word); dev_free(h->d_first_skip);
+    if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -313,8 +330,18 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
         if (dev_alloc(h, &h->d_chr_param, (size_t)4 * h->n_chr)) return 1;
         CK(cudaMemcpyAsync(h->d_chr_param, chr_param, 4 * h->n_chr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     }
-    std::vector<double> freq0(L0);
-    std::vector<uint8_t> keep(L0);
+    // pinned staging: freq0[L0] doubles | keep[L0] bytes (device → host), then the gather tables
+    const int64_t n_in_words = (L0 + 31) >> 5;
+    const size_t off_keep = (size_t)L0 * 8, off_src = (off_keep + (size_t)L0 + 63) & ~(size_t)63;
+    const size_t off_keepw = off_src + (size_t)L0 * 4, off_fw = off_keepw + (size_t)n_in_words * 4;
+    const size_t off_fs = off_fw + (size_t)(n_in_words + 1) * 4, pin_bytes = off_fs + (size_t)n_in_words + 64;
+    if (pin_alloc(h, pin_bytes)) return 1;
+    double* freq0 = reinterpret_cast<double*>(h->pin);
+    uint8_t* keep = h->pin + off_keep;
+    int32_t* src = reinterpret_cast<int32_t*>(h->pin + off_src);
+    uint32_t* keepw = reinterpret_cast<uint32_t*>(h->pin + off_keepw);
+    int32_t* first_word = reinterpret_cast<int32_t*>(h->pin + off_fw);
+    uint8_t* first_skip = h->pin + off_fs;
     if (freq_override) {
         // --freq-file: frequencies come from the caller; the predicate is evaluated on the host copy
         for (int64_t s = 0; s < L0; ++s) {
@@ -328,35 +355,60 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
             }
             freq0[s] = f; keep[s] = k;
         }
-        CK(cudaMemcpyAsync(h->d_freq0, freq0.data(), L0 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_freq0, freq0, L0 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     } else {
         LAUNCH(launch_freq_keep(h->d_counts, L0, h->d_pos0, h->d_chr_of0, h->d_chr_param, oob, h->d_freq0, h->d_keep, h->stream));
-        CK(cudaMemcpyAsync(freq0.data(), h->d_freq0, L0 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(keep.data(), h->d_keep, L0, cudaMemcpyDeviceToHost, h->stream));
+        if (freq_out) CK(cudaMemcpyAsync(freq0, h->d_freq0, L0 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(keep, h->d_keep, L0, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
-    if (freq_out) memcpy(freq_out, freq0.data(), L0 * sizeof(double));
-    if (keep_out) memcpy(keep_out, keep.data(), L0);
-    // exclusive scan of the keep mask → gather list, per-chromosome offsets (host: O(L0) integers)
-    h->src.clear();
+    if (freq_out) memcpy(freq_out, freq0, L0 * sizeof(double));
+    if (keep_out) memcpy(keep_out, keep, L0);
+    // one host pass over the keep mask (O(L0) integers): gather list, kept positions, per-chromosome
+    // offsets, keep bits per 32-SNP input word, and per output word the input word it starts in
+    h->src.resize(L0);
+    h->pos.resize(L0);
     h->chr_off.assign(h->n_chr + 1, 0);
+    for (int64_t j = 0; j < n_in_words; ++j) keepw[j] = 0;
+    int64_t L = 0;
     for (int c = 0; c < h->n_chr; ++c) {
-        for (int64_t s = h->chr_off0[c]; s < h->chr_off0[c + 1]; ++s)
-            if (keep[s]) h->src.push_back((int32_t)s);
-        h->chr_off[c + 1] = (int64_t)h->src.size();
+        for (int64_t s = h->chr_off0[c]; s < h->chr_off0[c + 1]; ++s) {
+            if (!keep[s]) continue;
+            if ((L & 31) == 0) {
+                first_word[L >> 5] = (int32_t)(s >> 5);
+                first_skip[L >> 5] = (uint8_t)__builtin_popcount(keepw[s >> 5]);   // kept fields of that word already placed
+            }
+            keepw[s >> 5] |= 1u << (s & 31);
+            src[L] = (int32_t)s;
+            h->src[L] = (int32_t)s;
+            h->pos[L] = h->pos0[s];
+            ++L;
+        }
+        h->chr_off[c + 1] = L;
     }
-    h->L = (int64_t)h->src.size();
-    if (n_kept) *n_kept = h->L;
-    if (h->L < 1) FAIL("filter: no polymorphic loci left");
-    const int64_t L = h->L;
+    h->src.resize(L);
     h->pos.resize(L);
-    for (int64_t d = 0; d < L; ++d) h->pos[d] = h->pos0[h->src[d]];
+    h->L = L;
+    if (n_kept) *n_kept = L;
+    if (L < 1) FAIL("filter: no polymorphic loci left");
+    const int64_t n_out_words = (L + 31) >> 5;
     if (dev_alloc(h, &h->d_src, (size_t)L)) return 1;
-    CK(cudaMemcpyAsync(h->d_src, h->src.data(), L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (dev_alloc(h, &h->d_keepw, (size_t)n_in_words)) return 1;
+    if (dev_alloc(h, &h->d_first_word, (size_t)n_out_words)) return 1;
+    if (dev_alloc(h, &h->d_first_skip, (size_t)n_out_words)) return 1;
+    CK(cudaMemcpyAsync(h->d_src, src, L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_keepw, keepw, n_in_words * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_first_word, first_word, n_out_words * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_first_skip, first_skip, n_out_words, cudaMemcpyHostToDevice, h->stream));
     h->row_words = ((L + kPad + 31) >> 5) + 2;
+    // the slack words behind each row are only ever over-read (their lookups are masked), so they need
+    // no defined content; a fresh allocation is filled once so that dumps stay reproducible
+    const bool fresh = h->cap.find((void*)&h->d_geno) == h->cap.end() || !h->d_geno ||
+                       h->cap[(void*)&h->d_geno] < (size_t)h->n_ind * h->row_words * 8;
     if (dev_alloc(h, &h->d_geno, (size_t)h->n_ind * h->row_words)) return 1;
-    CK(cudaMemsetAsync(h->d_geno, 0xff, (size_t)h->n_ind * h->row_words * 8, h->stream));
-    LAUNCH(launch_compact_geno(h->d_geno0, h->row_words0, h->d_src, L, h->d_geno, h->row_words, h->n_ind, h->stream));
+    if (fresh) CK(cudaMemsetAsync(h->d_geno, 0xff, (size_t)h->n_ind * h->row_words * 8, h->stream));
+    LAUNCH(launch_compact_geno(h->d_geno0, h->row_words0, n_in_words, h->d_keepw, h->d_first_word, h->d_first_skip, L,
+                               h->d_geno, h->row_words, h->n_ind, h->stream));
     if (dev_alloc(h, &h->d_freq, (size_t)L + kPad)) return 1;
     CK(cudaMemsetAsync(h->d_freq, 0, (size_t)(L + kPad) * sizeof(double), h->stream));
     LAUNCH(launch_gather_f64(h->d_freq0, h->d_src, L, h->d_freq, h->stream));
@@ -366,17 +418,14 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
         CK(cudaMemsetAsync(h->d_gl, 0, (size_t)h->n_ind * h->gl_stride * sizeof(double), h->stream));
         LAUNCH(launch_compact_gl(h->d_gl0, L0, h->d_src, L, h->d_gl, h->gl_stride, h->n_ind, h->gl_type, h->stream));
     }
-    // per-SNP position / chromosome arrays of the kept SNPs
-    std::vector<int> chr_of(L), chr_start(h->n_chr);
-    for (int c = 0; c < h->n_chr; ++c) {
-        chr_start[c] = (int)h->chr_off[c];
-        for (int64_t d = h->chr_off[c]; d < h->chr_off[c + 1]; ++d) chr_of[d] = c;
-    }
+    // per-SNP position / chromosome arrays of the kept SNPs (device-side gathers)
+    std::vector<int> chr_start(h->n_chr);
+    for (int c = 0; c < h->n_chr; ++c) chr_start[c] = (int)h->chr_off[c];
     if (dev_alloc(h, &h->d_pos, (size_t)L)) return 1;
     if (dev_alloc(h, &h->d_chr_of, (size_t)L)) return 1;
     if (dev_alloc(h, &h->d_chr_start, (size_t)h->n_chr)) return 1;
-    CK(cudaMemcpyAsync(h->d_pos, h->pos.data(), L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_chr_of, chr_of.data(), L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(launch_gather_i32(h->d_pos0, h->d_src, L, h->d_pos, h->stream));
+    LAUNCH(launch_gather_i32(h->d_chr_of0, h->d_src, L, h->d_chr_of, h->stream));
     CK(cudaMemcpyAsync(h->d_chr_start, chr_start.data(), h->n_chr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->filtered = true; h->tables = false; h->have_ld = false;
@@ -426,6 +475,7 @@ int garlic_gpu_set_tables(garlic_gpu_t* h, double error, int max_gap, const int3
     // bound on |LOD| for the ambiguity tolerance: with a global error the largest magnitudes are
     // log10(error) (heterozygote) and log10 of 1/f-type terms; freq ∈ [1/(2N_total), 1-1/(2N_total)]
     h->amax = 20.0;
+    build_stretches(h->chr_off, h->pos, h->cen, h->max_gap, h->stretches);
     h->tables = true; h->have_ld = false;
     return 0;
 }
@@ -543,7 +593,7 @@ int garlic_gpu_windows(garlic_gpu_t* h, int winsize, int step, int weighted, con
     }
     std::vector<Segment> segs;
     std::vector<Item> items;
-    build_segments(h->chr_off, h->pos, h->cen, h->max_gap, W, segs);
+    segments_from_stretches(h->stretches, W, segs);
     int chunk = 0;
     if (weighted) chunk = std::max(64, pick_chunk(h->L, W, n_lanes, 0) / 8);   // every wLOD window is a fresh sum
     else if (!exact) chunk = pick_chunk(h->L, W, n_lanes, kTileSnpsMax);
@@ -561,9 +611,12 @@ int garlic_gpu_windows(garlic_gpu_t* h, int winsize, int step, int weighted, con
     CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
     int rc = launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, false, true, items_tile_snps(items, W));
     if (!rc) {
-        cudaError_t e = cudaMemcpyAsync(out, d_dump, (size_t)n_lanes * slots * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        const size_t bytes = (size_t)n_lanes * slots * sizeof(double);
+        const bool staged = bytes <= ((size_t)64 << 20) && !pin_alloc(h, bytes);
+        cudaError_t e = cudaMemcpyAsync(staged ? (void*)h->pin : (void*)out, d_dump, bytes, cudaMemcpyDeviceToHost, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) { h->err = std::string("windows: ") + cudaGetErrorString(e); rc = 1; }
+        else if (staged) memcpy(out, h->pin, bytes);
     }
     return rc;
 }
@@ -587,7 +640,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
 
     std::vector<Segment> segs;
     std::vector<Item> items;
-    build_segments(h->chr_off, h->pos, h->cen, h->max_gap, W, segs);
+    segments_from_stretches(h->stretches, W, segs);
     int chunk = 0;
     if (weighted) chunk = std::max(64, pick_chunk(h->L, W, h->n_ind, 0) / 8);
     else if (!exact) chunk = pick_chunk(h->L, W, h->n_ind, kTileSnpsMax);
@@ -639,8 +692,15 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         }
         recs.resize(cnt[0]);
         ambs.resize(cnt[1]);
-        if (cnt[0]) CK(cudaMemcpy(recs.data(), h->d_out, cnt[0] * sizeof(RohRec), cudaMemcpyDeviceToHost));
-        if (cnt[1]) CK(cudaMemcpy(ambs.data(), h->d_amb, cnt[1] * sizeof(RohRec), cudaMemcpyDeviceToHost));
+        if (cnt[0] + cnt[1]) {   // through the pinned staging buffer (a pageable copy is several times slower)
+            if (pin_alloc(h, ((size_t)cnt[0] + cnt[1]) * sizeof(RohRec))) return 1;
+            RohRec* stage = reinterpret_cast<RohRec*>(h->pin);
+            if (cnt[0]) CK(cudaMemcpyAsync(stage, h->d_out, cnt[0] * sizeof(RohRec), cudaMemcpyDeviceToHost, h->stream));
+            if (cnt[1]) CK(cudaMemcpyAsync(stage + cnt[0], h->d_amb, cnt[1] * sizeof(RohRec), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            memcpy(recs.data(), stage, cnt[0] * sizeof(RohRec));
+            memcpy(ambs.data(), stage + cnt[0], cnt[1] * sizeof(RohRec));
+        }
         break;
     }
     // exact re-evaluation of (individual, segment) pairs that had a window within rounding

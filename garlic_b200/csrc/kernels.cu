@@ -385,12 +385,19 @@ cudaError_t launch_freq_keep(const int* counts, long long L0, const int* pos, co
 }
 
 // ------------------------------------------------------------------------------------------
-// K3: column compaction.  src[d] = pre-filter index of kept SNP d (exclusive scan of the keep
-// mask).  One thread builds one 64-bit output word (32 kept SNPs) of one individual by gathering
-// 2-bit fields; consecutive threads → consecutive words of a row.
+// K3: column compaction of the packed matrix (filterMonomorphic[AndOOB]Sites, garlic-data.cpp:871-1195,
+// as a bit-level gather).  The keep mask is the same for every individual, so the host hands over, per
+// 32-SNP input word, its keep bits and, per output word, the input word it starts in and how many kept
+// fields of that word belong to earlier output words.  One thread builds one output word: it walks
+// 1-3 input words, squeezes the dropped 2-bit fields out of each (one masked shift per dropped SNP;
+// most words drop none) and ORs the survivors into place.  Lanes = consecutive words of one row, so
+// reads and writes are coalesced.
 // ------------------------------------------------------------------------------------------
-__global__ void compact_geno_kernel(const uint64_t* __restrict__ gin, int64_t in_words, const int* __restrict__ src,
-                                    long long L, uint64_t* __restrict__ gout, int64_t out_words, int n_ind)
+__global__ void __launch_bounds__(256)
+compact_geno_kernel(const uint64_t* __restrict__ gin, int64_t in_words, long long n_in_words,
+                    const uint32_t* __restrict__ keepw, const int* __restrict__ first_word,
+                    const uint8_t* __restrict__ first_skip, long long L, uint64_t* __restrict__ gout,
+                    int64_t out_words, int n_ind)
 {
     const long long n_w = (L + 31) >> 5;
     const long long total = n_w * n_ind;
@@ -398,26 +405,59 @@ __global__ void compact_geno_kernel(const uint64_t* __restrict__ gin, int64_t in
         const int i = (int)(t / n_w);
         const long long w = t % n_w;
         const uint64_t* row = gin + (int64_t)i * in_words;
+        long long j = first_word[w];
+        int skip = first_skip[w];
         uint64_t o = 0;
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-            const long long d = w * 32 + k;
-            uint64_t g = 3;
-            if (d < L) { const int s = src[d]; g = (row[s >> 5] >> (2 * (s & 31))) & 3ull; }
-            o |= g << (2 * k);
+        int pos = 0;
+        while (pos < 32 && j < n_in_words) {
+            const uint32_t m = keepw[j];
+            uint64_t x = row[j];
+            uint32_t drop = ~m;
+            while (drop) {                       // highest dropped field first: lower positions stay valid
+                const int d = 31 - __clz((int)drop);
+                drop &= ~(1u << d);
+                const uint64_t low = (1ull << (2 * d)) - 1ull;
+                x = (x & low) | ((x >> 2) & ~low);
+            }
+            int c = __popc(m) - skip;
+            x >>= 2 * skip;
+            skip = 0;
+            if (c > 0) {
+                if (c < 32) x &= (1ull << (2 * c)) - 1ull;
+                o |= x << (2 * pos);
+                pos += c;
+            }
+            ++j;
         }
+        if (pos < 32) o |= ~0ull << (2 * pos);   // fields past the last kept SNP read as missing
         gout[(int64_t)i * out_words + w] = o;
     }
 }
 
-cudaError_t launch_compact_geno(const uint64_t* gin, int64_t in_words, const int* src, long long L,
-                                uint64_t* gout, int64_t out_words, int n_ind, cudaStream_t st)
+cudaError_t launch_compact_geno(const uint64_t* gin, int64_t in_words, long long n_in_words, const uint32_t* keepw,
+                                const int* first_word, const uint8_t* first_skip, long long L, uint64_t* gout,
+                                int64_t out_words, int n_ind, cudaStream_t st)
 {
     const long long total = ((L + 31) >> 5) * n_ind;
     if (!total) return cudaSuccess;
     long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    compact_geno_kernel<<<(unsigned)blocks, 256, 0, st>>>(gin, in_words, src, L, gout, out_words, n_ind);
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    compact_geno_kernel<<<(unsigned)blocks, 256, 0, st>>>(gin, in_words, n_in_words, keepw, first_word, first_skip, L,
+                                                         gout, out_words, n_ind);
+    return cudaGetLastError();
+}
+
+// gather a per-SNP int array through src[]
+__global__ void gather_i32_kernel(const int* in, const int* src, long long L, int* out)
+{
+    for (long long d = blockIdx.x * (long long)blockDim.x + threadIdx.x; d < L; d += (long long)gridDim.x * blockDim.x) out[d] = in[src[d]];
+}
+cudaError_t launch_gather_i32(const int* in, const int* src, long long L, int* out, cudaStream_t st)
+{
+    if (!L) return cudaSuccess;
+    long long blocks = (L + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    gather_i32_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, src, L, out);
     return cudaGetLastError();
 }
 

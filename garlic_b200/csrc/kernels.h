@@ -23,8 +23,10 @@ cudaError_t launch_count_packed(const uint64_t* geno, int64_t row_words, int n_i
                                 int* counts, cudaStream_t st);
 cudaError_t launch_freq_keep(const int* counts, long long L0, const int* pos, const int* chr_of,
                              const int* chr_param, int oob, double* freq, uint8_t* keep, cudaStream_t st);
-cudaError_t launch_compact_geno(const uint64_t* gin, int64_t in_words, const int* src, long long L,
-                                uint64_t* gout, int64_t out_words, int n_ind, cudaStream_t st);
+cudaError_t launch_compact_geno(const uint64_t* gin, int64_t in_words, long long n_in_words, const uint32_t* keepw,
+                                const int* first_word, const uint8_t* first_skip, long long L, uint64_t* gout,
+                                int64_t out_words, int n_ind, cudaStream_t st);
+cudaError_t launch_gather_i32(const int* in, const int* src, long long L, int* out, cudaStream_t st);
 cudaError_t launch_compact_gl(const double* in, int64_t in_stride, const int* src, long long L, double* out,
                               int64_t out_stride, int n_ind, int type, cudaStream_t st);
 cudaError_t launch_gather_f64(const double* in, const int* src, long long L, double* out, cudaStream_t st);

@@ -18,10 +18,13 @@ inline bool in_gap(int qs, int qe, int ts, int te)
     return (ts <= qs && te >= qs) || (ts <= qe && te >= qe) || (ts >= qs && te <= qe);
 }
 
-inline void build_segments(const std::vector<int64_t>& chr_off, const std::vector<int32_t>& pos,
-                           const std::vector<int32_t>& cen, int max_gap, int W, std::vector<Segment>& segs)
+// Maximal stretches [a,b) of SNPs of one chromosome without a bad adjacent pair (independent of W).
+struct Stretch { int chr, a, b; };
+
+inline void build_stretches(const std::vector<int64_t>& chr_off, const std::vector<int32_t>& pos,
+                            const std::vector<int32_t>& cen, int max_gap, std::vector<Stretch>& out)
 {
-    segs.clear();
+    out.clear();
     const int n_chr = (int)chr_off.size() - 1;
     for (int c = 0; c < n_chr; ++c) {
         const int lo = (int)chr_off[c], hi = (int)chr_off[c + 1];
@@ -34,11 +37,26 @@ inline void build_segments(const std::vector<int64_t>& chr_off, const std::vecto
                 brk = (p1 - p0 > max_gap) || in_gap(p0, p1, cs, ce);   // garlic-roh.cpp:60-61
             }
             if (brk) {
-                if (i - a >= W) segs.push_back({c, a, i - W + 1});
+                if (i > a) out.push_back({c, a, i});
                 a = i;
             }
         }
     }
+}
+
+inline void segments_from_stretches(const std::vector<Stretch>& st, int W, std::vector<Segment>& segs)
+{
+    segs.clear();
+    for (const Stretch& s : st)
+        if (s.b - s.a >= W) segs.push_back({s.chr, s.a, s.b - W + 1});
+}
+
+inline void build_segments(const std::vector<int64_t>& chr_off, const std::vector<int32_t>& pos,
+                           const std::vector<int32_t>& cen, int max_gap, int W, std::vector<Segment>& segs)
+{
+    std::vector<Stretch> st;
+    build_stretches(chr_off, pos, cen, max_gap, st);
+    segments_from_stretches(st, W, segs);
 }
 
 // Chunk length (owned SNPs per item) of the chunked fast pass.  Preferred: the largest chunk whose
@@ -103,17 +121,21 @@ inline void build_items(const std::vector<int64_t>& chr_off, int W, const std::v
 // (garlic-roh.cpp:477).  Returns the merged runs; tag keeps seg<<2.
 inline void stitch_runs(std::vector<RohRec>& recs, int thr, std::vector<RohRec>& out)
 {
-    std::sort(recs.begin(), recs.end(), [](const RohRec& x, const RohRec& y) {
-        return x.ind != y.ind ? x.ind < y.ind : x.a < y.a;
-    });
+    // sort by (individual, start) through 64-bit keys (runs of one individual never share a start)
+    std::vector<std::pair<uint64_t, uint32_t>> key(recs.size());
+    for (size_t i = 0; i < recs.size(); ++i)
+        key[i] = {((uint64_t)(uint32_t)recs[i].ind << 32) | (uint32_t)recs[i].a, (uint32_t)i};
+    std::sort(key.begin(), key.end());
     out.clear();
+    out.reserve(recs.size());
     size_t i = 0;
-    while (i < recs.size()) {
-        RohRec cur = recs[i++];
-        while ((cur.tag & 2) && i < recs.size() && recs[i].ind == cur.ind && (recs[i].tag & 1) &&
-               recs[i].a == cur.b + 1 && (recs[i].tag >> 2) == (cur.tag >> 2)) {
-            cur.b = recs[i].b;
-            cur.tag = (cur.tag & ~2) | (recs[i].tag & 2);
+    while (i < key.size()) {
+        RohRec cur = recs[key[i++].second];
+        while ((cur.tag & 2) && i < key.size()) {
+            const RohRec& nx = recs[key[i].second];
+            if (!(nx.ind == cur.ind && (nx.tag & 1) && nx.a == cur.b + 1 && (nx.tag >> 2) == (cur.tag >> 2))) break;
+            cur.b = nx.b;
+            cur.tag = (cur.tag & ~2) | (nx.tag & 2);
             ++i;
         }
         if (cur.b - cur.a + 1 < thr) continue;

@@ -92,6 +92,27 @@ GHD void dump_window(const WalkParams& P, const Item& it, int k, bool active, in
         P.dump[(int64_t)k * P.dump_stride + it.thin_base + d / P.dump_step] = win;
 }
 
+GHD int popc32(uint32_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
+// position of the n-th (1-based) set bit of x; the caller guarantees 1 <= n <= popc(x)
+GHD int nth_set_bit(uint32_t x, int n)
+{
+    int pos = 0, c;
+    c = popc32(x & 0xffffu); if (n > c) { n -= c; pos += 16; x >>= 16; }
+    c = popc32(x & 0xffu);   if (n > c) { n -= c; pos += 8;  x >>= 8; }
+    c = popc32(x & 0xfu);    if (n > c) { n -= c; pos += 4;  x >>= 4; }
+    c = popc32(x & 0x3u);    if (n > c) { n -= c; pos += 2;  x >>= 2; }
+    c = (int)(x & 1u);       if (n > c) { pos += 1; }
+    return pos;
+}
+
 // byte offset (g*8) of genotype k's table entry, straight from the packed word: no multiply
 GHD uint32_t lut_off(uint32_t w, int kk)
 {
@@ -164,22 +185,40 @@ GHD void walk_block(const WalkParams& P, const Item& it, const LaneCtx<SRC>& C, 
     busy = __any_sync(0xffffffffu, busy);
 #endif
     if (!busy) {
-        if (W <= 32) S.hist = 0;
+        if (W <= 32) S.hist = 0;   // = fw
         return;
     }
-    uint32_t cw = 0;
+    // flags leaving the W-window during this block: the flag stream delayed by W steps
+    uint32_t owv = ow;
+    if (W <= 32) owv = (W == 32) ? S.hist : ((fw << W) | (S.hist >> (32 - W)));
+    // cov(k) = cov + #d1 bits ≤ k − #d2 bits ≤ k  (sliding form of garlic-roh.cpp:446-454); covered = cov ≥ thr (:466)
+    const uint32_t d1 = fw & ~owv, d2 = owv & ~fw;
     int cov = S.cov;
-    uint32_t hist = S.hist;
+    uint32_t cw;
+    bool mixed = (d1 != 0u) && (d2 != 0u);
+#ifdef __CUDA_ARCH__
+    mixed = __any_sync(0xffffffffu, mixed);
+#endif
+    if (mixed) {                 // a run starts and another ends within W steps of each other: per-step count
+        cw = 0;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        const uint32_t f = (fw >> k) & 1u;
-        uint32_t o;
-        if (W <= 32) { o = (hist >> (W - 1)) & 1u; hist = (hist << 1) | f; }
-        else o = (ow >> k) & 1u;
-        cov += (int)f - (int)o;                                          // sliding form of :446-454
-        cw |= (uint32_t)(cov >= P.thr) << k;                             // garlic-roh.cpp:466
+        for (int k = 0; k < 32; ++k) {
+            cov += (int)((d1 >> k) & 1u) - (int)((d2 >> k) & 1u);
+            cw |= (uint32_t)(cov >= P.thr) << k;
+        }
+    } else if (d1) {             // only increments: covered from the step of the (thr-cov)-th one on
+        const int n = P.thr - cov, c = popc32(d1);
+        cw = n <= 0 ? 0xffffffffu : (n > c ? 0u : (0xffffffffu << nth_set_bit(d1, n)));
+        cov += c;
+    } else if (d2) {             // only decrements: covered until the (cov-thr+1)-th one
+        const int m = cov - P.thr, c = popc32(d2);
+        cw = m < 0 ? 0u : (m >= c ? 0xffffffffu : ((1u << nth_set_bit(d2, m + 1)) - 1u));
+        cov -= c;
+    } else {
+        cw = cov >= P.thr ? 0xffffffffu : 0u;
     }
-    S.cov = cov; S.hist = hist;
+    S.cov = cov;
+    if (W <= 32) S.hist = fw;
     // run-length on the 32 covered bits (bit-parallel edge detection)
     uint32_t em = 0xffffffffu;
     if (!FULL) {
@@ -233,7 +272,7 @@ GHD void walk_item(const WalkParams& P, const Item& it, int k_slot, bool active,
     if (chk) S.ambig = (f0 != (win >= P.cutoff - P.tol));
     dump_window<DUMP>(P, it, k_slot, active, it.w0, win);
     S.cov = (int)f0;
-    S.hist = (uint32_t)f0;
+    S.hist = (uint32_t)f0 << 31;   // flag stream of the previous 32 steps: window w0 sits at position 31
     if (ROH && it.w0 >= it.own_lo && S.cov >= P.thr) S.run_start = it.w0;
     if (W > 32) {
         for (int w = 0; w < NW; ++w) ring[w * rstride] = 0;
@@ -242,23 +281,27 @@ GHD void walk_item(const WalkParams& P, const Item& it, int k_slot, bool active,
 
     const int M = it.own_hi - 1 - it.w0;   // number of slide steps
     const int sa = 2 * ((it.w0 + W) & 31), sb = 2 * (it.w0 & 31);
-    const int64_t ia = (it.w0 + W) >> 5, ib = it.w0 >> 5;
-    uint64_t a_lo = C.row[ia], b_lo = C.row[ib];
-    uint64_t a_hi = C.row[ia + 1], b_hi = C.row[ib + 1];
+    const uint64_t* pa = C.row + ((it.w0 + W) >> 5);   // slide-in stream
+    const uint64_t* pb = C.row + (it.w0 >> 5);         // slide-out stream
+    uint64_t a_lo = pa[0], b_lo = pb[0];
+    uint64_t a_hi = pa[1], b_hi = pb[1];
+    pa += 2; pb += 2;
     const int r = (32 - (W & 31)) & 31;
-    const int nwords = (W + 31) >> 5;
-    for (int j = 0, m0 = 0; m0 < M; ++j, m0 += 32) {
+    // ring of flag words (W > 32): block j writes slot (j+1) mod NW and reads the two slots after it,
+    // which hold stream words j+1-nwords and j+2-nwords (NW = nwords+1); indices advance by compare-and-wrap
+    int wr = 1 % NW;
+    int tblk = it.w0 + 1;
+    for (int m0 = 0; m0 < M; m0 += 32, tblk += 32) {
         // next block's words are requested before this block's arithmetic (rows are padded)
-        const uint64_t a_nx = C.row[ia + j + 2], b_nx = C.row[ib + j + 2];
+        const uint64_t a_nx = *pa++, b_nx = *pb++;
         const uint64_t gin = sa ? ((a_lo >> sa) | (a_hi << (64 - sa))) : a_lo;
         const uint64_t gout = sb ? ((b_lo >> sb) | (b_hi << (64 - sb))) : b_lo;
         a_lo = a_hi; b_lo = b_hi; a_hi = a_nx; b_hi = b_nx;
-        const int tblk = it.w0 + 1 + m0;
         uint32_t ow = 0;
         if (ROH && W > 32) {
-            const int qi = j + 1 - nwords;
-            const uint32_t w0_ = qi >= 0 ? ring[(qi % NW) * rstride] : 0u;
-            const uint32_t w1_ = (qi + 1) >= 0 ? ring[((qi + 1) % NW) * rstride] : 0u;
+            int r0 = wr + 1; if (r0 >= NW) r0 -= NW;
+            int r1 = r0 + 1; if (r1 >= NW) r1 -= NW;
+            const uint32_t w0_ = ring[r0 * rstride], w1_ = ring[r1 * rstride];
             ow = r ? ((w0_ >> r) | (w1_ << (32 - r))) : w0_;
         }
         const bool full = (tblk + 31 < it.we) && (tblk >= it.own_lo) && (tblk + 31 < it.own_hi);
@@ -269,7 +312,10 @@ GHD void walk_item(const WalkParams& P, const Item& it, int k_slot, bool active,
             if (full) walk_block<SRC, ROH, DUMP, true, false>(P, it, C, S, ind, k_slot, active, gin, gout, tblk, ow);
             else walk_block<SRC, ROH, DUMP, false, false>(P, it, C, S, ind, k_slot, active, gin, gout, tblk, ow);
         }
-        if (ROH && W > 32) ring[((j + 1) % NW) * rstride] = S.fw;
+        if (ROH && W > 32) {
+            ring[wr * rstride] = S.fw;
+            if (++wr >= NW) wr = 0;
+        }
     }
     if (ROH && S.run_start >= 0) emit_run(P, it, ind, active, S.run_start, it.own_hi - 1);
     if (chk && S.ambig && active) {
