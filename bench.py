@@ -73,13 +73,6 @@ def make_rows_torch(torch, dev, n_ind, L, seed, ind_seed, row_bytes, chunk=250):
     return rows
 
 
-class DevArray:
-    """__cuda_array_interface__ view of a raw device pointer (to hand library buffers to torch.distributed)."""
-
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
-
-
 def unpack_rows(rows_u8, L):
     b = rows_u8[:, :(L + 3) // 4]
     out = np.empty((b.shape[0], b.shape[1], 4), np.uint8)
@@ -292,6 +285,7 @@ def main():
         sys.stderr.write("bench.py: no CUDA device; garlic_b200 has no CPU fallback\n")
         return 1
     from garlic_b200.api import GarlicGPU
+    from garlic_b200 import shard
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
@@ -315,12 +309,13 @@ def main():
     stream = torch.cuda.ExternalStream(g.stream(), device=dev)
     counts_t = None
     if dist is not None:
-        counts_t = torch.as_tensor(DevArray(g.counts_dev(), (4, L0), "<i4"), device=dev)
+        counts_t = shard.dev_tensor(torch, g.counts_dev(), (4, L0), "<i4", dev)
     # the KDE subsample: 20 individuals of the whole job, spread evenly; this rank computes its own
     n_total = n_ind * world
-    kde_global = np.linspace(0, n_total - 1, CFG["kde_subsample"]).astype(np.int64)
-    kde_local = (kde_global[(kde_global // n_ind) == rank] - rank * n_ind).astype(np.int32)
-    kde_max = max(int(((kde_global // n_ind) == r).sum()) for r in range(world))
+    kde_global = np.unique(np.linspace(0, n_total - 1, CFG["kde_subsample"]).astype(np.int64))
+    kde_parts = [(kde_global[(kde_global // n_ind) == r] - r * n_ind).astype(np.int32) for r in range(world)]
+    kde_local = kde_parts[rank]
+    kde_max = max(len(x) for x in kde_parts)
     state = {}
 
     phases = {}
@@ -340,7 +335,7 @@ def main():
         t0 = lap("count_packed", t0)
         if dist is not None:
             g.sync()
-            dist.all_reduce(counts_t)                        # the one data-path collective
+            shard.allreduce_counts(dist, counts_t)           # the one data-path collective
             torch.cuda.synchronize()
         t0 = lap("allreduce_counts", t0)
         freq, keep, L = g.filter()                           # freq, keep mask -> host; K3 compaction
@@ -349,13 +344,10 @@ def main():
         t0 = lap("set_tables", t0)
         thin = g.windows(W, W, individuals=kde_local, exact=False) if len(kde_local) else np.empty((0, 0))
         if dist is not None:                                 # small all-gather of the thinned LODs
-            slots = g.window_slots(W)
-            mine = torch.full((kde_max, slots), -9999.0, dtype=torch.float64, device=dev)
-            if len(kde_local):
-                mine[:len(kde_local)] = torch.from_numpy(np.ascontiguousarray(thin)).to(dev)
-            allv = torch.empty((world * kde_max, slots), dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(allv, mine)
-            thin = allv.cpu().numpy()                        # every rank holds the KDE input (host FIGTree)
+            mine = torch.from_numpy(np.ascontiguousarray(thin).reshape(len(kde_local), -1)).to(dev)
+            if not len(kde_local):
+                mine = torch.empty((0, g.window_slots(W)), dtype=torch.float64, device=dev)
+            thin = shard.allgather_thinned(torch, dist, mine, kde_max).cpu().numpy()   # KDE input on every rank
         t0 = lap("pass1_thinned_windows", t0)
         roh = g.call_roh(W, cutoff, ov, exact=a.exact)       # K5 pass 2 (fused) -> ROH records on the host
         t0 = lap("pass2_call_roh", t0)

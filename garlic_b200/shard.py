@@ -1,0 +1,79 @@
+"""Sharding by individual across the GPUs of one box.
+
+One process per GPU; rank r owns a contiguous block of individuals.  The only data-path exchanges are
+  * a SUM all-reduce of the per-SNP counters int32[4][L0] (nalleles, total, hom, nonmiss) and, for text ingest,
+    a MIN all-reduce of the first-allele keys,
+  * a small all-gather of the thinned KDE windows,
+and ROH lists are concatenated in rank order (= individual order, the order of the reference's BED tracks,
+garlic-roh.cpp:426-431).  The functions take torch tensors so the same code runs over NCCL (device buffers of the
+library, see `dev_tensor`) and over gloo on CPU (tests/test_multi_rank.py)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n_total: int, world: int, rank: int):
+    """Contiguous block [lo, hi) of individuals of `rank`: ceil(n/world) per rank, last ranks may be short."""
+    per = -(-n_total // world)
+    lo = min(n_total, rank * per)
+    return lo, min(n_total, lo + per)
+
+
+def split_individuals(global_idx, n_total: int, world: int):
+    """Global individual indices (ascending, as gsl_ran_choose returns them) → per-rank LOCAL index arrays."""
+    g = np.asarray(global_idx, np.int64)
+    out = []
+    for r in range(world):
+        lo, hi = shard_range(n_total, world, r)
+        out.append((g[(g >= lo) & (g < hi)] - lo).astype(np.int32))
+    return out
+
+
+class DevArray:
+    """__cuda_array_interface__ view of a raw device pointer owned by libgarlic_b200."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+def dev_tensor(torch, ptr, shape, typestr, device):
+    return torch.as_tensor(DevArray(ptr, shape, typestr), device=device)
+
+
+def allreduce_counts(dist, counts):
+    """counts: int32[4, L0] tensor (device buffer of the library under NCCL, CPU tensor under gloo)."""
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    return counts
+
+
+def allreduce_first_allele_keys(dist, keys):
+    """keys: int64 view of the uint64 first-allele keys (all < 2^63, so signed MIN is the unsigned MIN)."""
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(keys, op=dist.ReduceOp.MIN)
+    return keys
+
+
+def allgather_thinned(torch, dist, mine, rows_per_rank: int, missing=-9999.0):
+    """mine: float64[k, slots] windows of this rank's KDE individuals (k ≤ rows_per_rank).  Returns the
+    float64[world*rows_per_rank, slots] stack (MISSING-padded), identical on every rank."""
+    slots = mine.shape[1]
+    pad = torch.full((rows_per_rank, slots), missing, dtype=torch.float64, device=mine.device)
+    if mine.shape[0]:
+        pad[:mine.shape[0]] = mine
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return pad
+    out = torch.empty((dist.get_world_size() * rows_per_rank, slots), dtype=torch.float64, device=mine.device)
+    dist.all_gather_into_tensor(out, pad)
+    return out
+
+
+def merge_roh(per_rank, n_total: int, world: int):
+    """per_rank[r]: int32[n_r, 4] rows (local ind, chr, start_idx, stop_idx) sorted by (ind, chr, start).
+    → one array with GLOBAL individual indices in the reference's (ind, chr, position) order."""
+    parts = []
+    for r, a in enumerate(per_rank):
+        a = np.asarray(a, np.int32).reshape(-1, 4).copy()
+        a[:, 0] += shard_range(n_total, world, r)[0]
+        parts.append(a)
+    return np.concatenate(parts, axis=0) if parts else np.empty((0, 4), np.int32)
