@@ -224,6 +224,14 @@ def main():
     ap.add_argument("--exact", action="store_true", help="whole-segment chains in pass 2")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 0)
+    # exactly one JSON line on stdout: libraries (NCCL prints its version) get stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -273,7 +281,7 @@ def main():
         val = units / (ms / 1e3)
         sample = "%d individuals x %d SNPs (of the %d-individual workload) per step, %d processes x %d individuals" % (
             n_s, int(keep.sum()), n_ind, procs, per)
-        print(json.dumps(dict(metric=METRIC, value=val, unit=UNIT, impl="reference", n_gpus=a.gpus, steps=a.steps,
+        emit((dict(metric=METRIC, value=val, unit=UNIT, impl="reference", n_gpus=a.gpus, steps=a.steps,
                               warmup=a.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
                               vs_baseline=None, dtype="f64", data="synthetic", config=config,
                               cpu_baseline=dict(value=val, unit=UNIT, cores=procs, kind=kind, sample=sample),
@@ -342,11 +350,15 @@ def main():
         t0 = lap("filter_compact", t0)
         g.set_tables(err, max_gap, cen_arr)                  # K4
         t0 = lap("set_tables", t0)
-        thin = g.windows(W, W, individuals=kde_local, exact=False) if len(kde_local) else np.empty((0, 0))
-        if dist is not None:                                 # small all-gather of the thinned LODs
-            mine = torch.from_numpy(np.ascontiguousarray(thin).reshape(len(kde_local), -1)).to(dev)
-            if not len(kde_local):
-                mine = torch.empty((0, g.window_slots(W)), dtype=torch.float64, device=dev)
+        if dist is None:
+            thin = g.windows(W, W, individuals=kde_local, exact=False)
+        else:                                                # thinned LODs stay on the GPU, one small all-gather
+            slots = g.window_slots(W)
+            if len(kde_local):
+                ptr, n_, _ = g.windows_dev(W, W, individuals=kde_local, exact=False)
+                mine = shard.dev_tensor(torch, ptr, (n_, slots), "<f8", dev)
+            else:
+                mine = torch.empty((0, slots), dtype=torch.float64, device=dev)
             thin = shard.allgather_thinned(torch, dist, mine, kde_max).cpu().numpy()   # KDE input on every rank
         t0 = lap("pass1_thinned_windows", t0)
         roh = g.call_roh(W, cutoff, ov, exact=a.exact)       # K5 pass 2 (fused) -> ROH records on the host
@@ -441,7 +453,7 @@ def main():
         line["parity_vs_cpu_sample"] = "identical ROH (%d)" % len(got) if got == sorted(roh_cpu) else \
             "MISMATCH: gpu %d vs cpu %d" % (len(got), len(roh_cpu))
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     g.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -25,7 +25,7 @@ EXPORTS = [
     "garlic_gpu_get_one_allele", "garlic_gpu_put_gl", "garlic_gpu_put_gl_dev", "garlic_gpu_filter",
     "garlic_gpu_set_tables", "garlic_gpu_set_lut", "garlic_gpu_get_lut", "garlic_gpu_get_hom_freq",
     "garlic_gpu_ld_band", "garlic_gpu_set_wlod", "garlic_gpu_window_slots", "garlic_gpu_windows",
-    "garlic_gpu_call_roh", "garlic_gpu_last_stats", "garlic_gpu_n_kept", "garlic_gpu_get_kept_index",
+    "garlic_gpu_windows_dev", "garlic_gpu_call_roh", "garlic_gpu_last_stats", "garlic_gpu_n_kept", "garlic_gpu_get_kept_index",
     "garlic_gpu_get_genotypes",
 ]
 
@@ -205,6 +205,15 @@ class GarlicGPU:
         self._ck(self.lib.garlic_gpu_windows(self.h, C.c_int(W), C.c_int(step), C.c_int(int(weighted)), _p(idx),
                                              C.c_int(n), C.c_int(int(exact)), _p(out)))
         return out
+
+    def windows_dev(self, W, step=1, weighted=False, individuals=None, exact=True):
+        """→ (device pointer, n, slots): the window matrix left on the GPU."""
+        idx = None if individuals is None else np.ascontiguousarray(individuals, np.int32)
+        n = self.n_ind if idx is None else len(idx)
+        ptr = C.c_void_p()
+        self._ck(self.lib.garlic_gpu_windows_dev(self.h, C.c_int(W), C.c_int(step), C.c_int(int(weighted)), _p(idx),
+                                                 C.c_int(n), C.c_int(int(exact)), C.byref(ptr)))
+        return ptr.value, n, self.window_slots(step)
 
     def call_roh(self, W, cutoff, overlap_frac, weighted=False, exact=False, cap=1 << 16):
         """→ int32[n, 4] rows (ind, chr, start_idx, stop_idx), sorted by (ind, chr, start)."""

@@ -577,8 +577,24 @@ int64_t garlic_gpu_window_slots(garlic_gpu_t* h, int step)
     return n;
 }
 
+static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, const int32_t* individuals, int n,
+                          int exact, double* out, void** out_dev);
+
 int garlic_gpu_windows(garlic_gpu_t* h, int winsize, int step, int weighted, const int32_t* individuals, int n,
                        int exact, double* out)
+{
+    return windows_common(h, winsize, step, weighted, individuals, n, exact, out, nullptr);
+}
+
+int garlic_gpu_windows_dev(garlic_gpu_t* h, int winsize, int step, int weighted, const int32_t* individuals, int n,
+                           int exact, void** out_dev)
+{
+    if (!out_dev) return 1;
+    return windows_common(h, winsize, step, weighted, individuals, n, exact, nullptr, out_dev);
+}
+
+static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, const int32_t* individuals, int n,
+                          int exact, double* out, void** out_dev)
 {
     CK(cudaSetDevice(h->device));
     if (!h->tables) FAIL("windows: call set_tables first");
@@ -610,7 +626,11 @@ int garlic_gpu_windows(garlic_gpu_t* h, int winsize, int step, int weighted, con
     P.dump = d_dump; P.dump_stride = slots; P.dump_step = step;
     CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
     int rc = launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, false, true, items_tile_snps(items, W));
-    if (!rc) {
+    if (!rc && out_dev) {
+        *out_dev = d_dump;
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { h->err = std::string("windows: ") + cudaGetErrorString(e); rc = 1; }
+    } else if (!rc) {
         const size_t bytes = (size_t)n_lanes * slots * sizeof(double);
         const bool staged = bytes <= ((size_t)64 << 20) && !pin_alloc(h, bytes);
         cudaError_t e = cudaMemcpyAsync(staged ? (void*)h->pin : (void*)out, d_dump, bytes, cudaMemcpyDeviceToHost, h->stream);

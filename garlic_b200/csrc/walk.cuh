@@ -88,7 +88,8 @@ GHD void dump_window(const WalkParams& P, const Item& it, int k, bool active, in
 {
     if (!DUMP) return;
     const int d = t - it.chr_start;
-    if (active && (d % P.dump_step) == 0)
+    // a window is dumped by the item that owns its first SNP (lead-in windows belong to the previous chunk)
+    if (active && t >= it.own_lo && (d % P.dump_step) == 0)
         P.dump[(int64_t)k * P.dump_stride + it.thin_base + d / P.dump_step] = win;
 }
 

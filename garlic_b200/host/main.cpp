@@ -1,0 +1,433 @@
+// main.cpp — `garlic_b200`: command-line driver with the reference's process boundary (flags, inputs, outputs,
+// order of operations and log lines of src/garlic-main.cpp:25-421), calling the hand-written kernels through
+// the C ABI of include/garlic_b200.h.  There is no CPU path for the per-genotype work: without a CUDA device
+// the program stops at garlic_gpu_create.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <random>
+
+#include "../../include/garlic_b200.h"
+#include "garlic_host.h"
+
+using namespace gh;
+
+namespace {
+
+struct Ctx {
+    Options o;
+    garlic_gpu_t* g = nullptr;
+    Tped tped;
+    Tfam tfam;
+    std::vector<Scaffold> scaffold;
+    std::map<std::string, std::pair<int, int>> cen;
+    std::vector<std::string> labels;            // chr labels ("chr1", …) in data order
+    std::vector<int32_t> cen_arr;               // [C][2]
+    int64_t L = 0;
+    std::vector<int32_t> pos;                   // kept positions
+    std::vector<int64_t> chr_off;               // kept offsets [C+1]
+    std::vector<double> gpos;                   // kept genetic positions (weighted / cm)
+    std::mt19937 rng;
+};
+
+bool gpu_ok(Ctx& c, int rc, const char* what)
+{
+    if (rc == 0) return true;
+    LOG.error(std::string("ERROR: ") + what + ": " + garlic_gpu_last_error(c.g));
+    return false;
+}
+
+// gsl_ran_choose (selection sampling, keeps source order) with gsl_rng_uniform = mt19937()/2^32
+std::vector<int32_t> choose(Ctx& c, int k, int n)
+{
+    std::vector<int32_t> out;
+    for (int i = 0; i < n && (int)out.size() < k; ++i)
+        if ((n - i) * (c.rng() / 4294967296.0) < k - (int)out.size()) out.push_back(i);
+    return out;
+}
+
+// convert[Subset]WinData2DoubleData (garlic-data.cpp:2026-2150): chr → individual → locus, MISSING/NaN dropped
+bool thinned_windows(Ctx& c, int W, int step, const std::vector<int32_t>* inds, std::vector<double>& out)
+{
+    const int n = inds ? (int)inds->size() : c.tped.n_ind;
+    const int64_t slots = garlic_gpu_window_slots(c.g, step);
+    std::vector<double> m((size_t)n * slots);
+    if (!gpu_ok(c, garlic_gpu_windows(c.g, W, step, c.o.weighted, inds ? inds->data() : nullptr, n, 1 /* whole-segment chains */, m.data()), "windows")) return false;
+    out.clear();
+    int64_t base = 0;
+    for (size_t ch = 0; ch + 1 < c.chr_off.size(); ++ch) {
+        const int64_t ns = (c.chr_off[ch + 1] - c.chr_off[ch] + step - 1) / step;
+        for (int i = 0; i < n; ++i)
+            for (int64_t s = 0; s < ns; ++s) {
+                const double v = m[(size_t)i * slots + base + s];
+                if (v != GARLIC_MISSING && !std::isnan(v)) out.push_back(v);
+            }
+        base += ns;
+    }
+    return true;
+}
+
+double lod_host(int g, double freq, double error)   // garlic-roh.cpp:355-386
+{
+    double a, na;
+    if (freq == 0 || freq == 1 || g == 3) { a = 1; na = 1; }
+    else if (g == 0) { na = (1 - freq) * (1 - freq); a = (1 - error) * (1 - freq) + error * na; }
+    else if (g == 1) { na = 2 * (freq) * (1 - freq); a = error * na; }
+    else { na = (freq) * (freq); a = (1 - error) * (freq) + error * na; }
+    return std::log10(a / na);
+}
+
+double calc_density(const Ctx& c)   // calcDensity, garlic-data.cpp:318-328
+{
+    double length = 0;
+    for (size_t ch = 0; ch + 1 < c.chr_off.size(); ++ch) {
+        const int64_t lo = c.chr_off[ch], hi = c.chr_off[ch + 1];
+        length += c.pos[hi - 1] - c.pos[lo] + 1 - (c.cen_arr[2 * ch + 1] - c.cen_arr[2 * ch]);
+    }
+    return double(c.L) / length;
+}
+
+std::string join(const std::vector<double>& v) { std::string s; for (double x : v) s += " " + fmt_g(x); return s; }
+std::string join(const std::vector<int>& v) { std::string s; for (int x : v) s += " " + std::to_string(x); return s; }
+
+}  // namespace
+
+int main(int argc, char** argv)
+{
+    Ctx c;
+    Options& o = c.o;
+    std::string cmdline;
+    const int pr = parse_cli(argc, argv, o, cmdline);
+    if (pr > 0) return 0;
+    if (pr < 0) return -1;
+    if (!LOG.open(o.out)) return -1;
+    LOG.line(cmdline);
+    LOG.line("Output file basename: " + o.out);
+
+    // ---- validation and parameter log, in the reference's order (garlic-main.cpp:39-183) ----
+    if (o.tped == "none" || o.tfam == "none") { LOG.error("ERROR: Must provide both a tped and tfam file."); return -1; }
+    LOG.line("TPED file: " + o.tped);
+    LOG.line(std::string("TPED missing data code: ") + o.tped_missing);
+    LOG.line("TFAM file: " + o.tfam);
+    LOG.line("TGLS file: " + o.tgls);
+    const bool use_gl = o.tgls != "none";
+    if (use_gl && o.gl_type != "GQ" && o.gl_type != "GL" && o.gl_type != "PL") {
+        LOG.error("ERROR: Must choose GQ/GL/PL for genotype likelihood format or provide a single error rate with --error.");
+        return -1;
+    }
+    LOG.line("Genotype likelihood format: " + o.gl_type);
+    if (o.cm && o.map == "none") { LOG.error("ERROR: Must provide mapfile if you wish to construct ROH in genetic map units."); return -1; }
+    LOG.line("Measure ROH in genetic distance units: " + fmt_bool(o.cm));
+    if (o.map == "none" && (o.weighted || o.cm)) { LOG.error("ERROR: Weighted LOD score method requires a map file."); return -1; }
+    LOG.line("Weighted LOD: " + fmt_bool(o.weighted));
+    if (o.weighted) LOG.line("Map file: " + o.map);
+    if (o.build != "hg18" && o.build != "hg19" && o.build != "hg38" && o.build != "none") {
+        LOG.error("ERROR: Must choose hg18/hg19/hg38 for build version or provide a custom centromere file.");
+        return -1;
+    }
+    LOG.line("Genome build: " + o.build);
+    if (o.build == "none" && o.centromere == "none") {
+        LOG.error("ERROR: Must choose hg18/hg19/hg38 for build version or provide a custom centromere file.");
+        return -1;
+    }
+    LOG.line("User defined centromere file: " + o.centromere);
+    if (o.freq_file != "none" || o.freq_only || o.resample > 0 || o.phased || o.raw_lod) {
+        LOG.error("ERROR: --freq-file, --freq-only, --resample, --phased and --raw-lod are not built in this round (DESIGN.md §9).");
+        return -1;
+    }
+    LOG.line("Calculate allele frequencies only: FALSE");
+    LOG.line("Calculate allele frequencies from data: TRUE");
+    LOG.line("Allele frequencies resampled: FALSE");
+    bool explore = false;
+    if (o.winsize_multi[0] != -1) {
+        for (int w : o.winsize_multi)
+            if (w <= 0) { LOG.error("ERROR: SNP window sizes must be > 1."); return -1; }
+        explore = true;
+    }
+    LOG.line("Explore window sizes: " + fmt_bool(explore));
+    if (explore) LOG.line("User defined window sizes:" + join(o.winsize_multi));
+    LOG.line("Automatic window size: " + fmt_bool(o.auto_winsize));
+    if (o.auto_winsize_step <= 0) { LOG.error("ERROR: Automatic window step size must be > 0."); return -1; }
+    LOG.line("Automatic window step size: " + std::to_string(o.auto_winsize_step));
+    int winsize = o.winsize;
+    if (winsize <= 1 && !explore && !(o.auto_winsize && o.weighted)) {
+        LOG.error("ERROR: SNP window size must be > 1. If using --auto-winsize, this is the starting value.");
+        return -1;
+    }
+    if (!explore && !o.auto_winsize) LOG.line("User defined window size: " + std::to_string(winsize));
+    double cutoff = o.lod_cutoff;
+    const bool auto_cutoff = (o.lod_cutoff == -999999);
+    LOG.line("Choose LOD score cutoff automatically: " + fmt_bool(auto_cutoff));
+    if (!auto_cutoff) LOG.line("User defined LOD score cutoff: " + fmt_g(cutoff));
+    std::vector<double> bounds = o.size_bounds;
+    bool auto_bounds = true;
+    if (!(bounds.size() == 1 && bounds[0] == -1)) {
+        for (size_t i = 0; i < bounds.size(); ++i)
+            if (bounds[i] <= 0 || (i && bounds[i] <= bounds[i - 1])) {
+                LOG.error("ERROR: ROH size boundaries must be positive and in increasing order.");
+                return -1;
+            }
+        auto_bounds = false;
+    }
+    LOG.line("Choose ROH class thresholds automatically: " + fmt_bool(auto_bounds));
+    if (!auto_bounds) LOG.line("User defined ROH class thresholds:" + join(bounds));
+    if (o.threads <= 0) { LOG.error("ERROR: Number of threads must be > 0."); return -1; }
+    LOG.line("Threads: " + std::to_string(o.threads));
+    if ((o.error <= 0 || o.error >= 1) && !use_gl) {
+        LOG.error("ERROR: Genotype error rate must be > 0 and < 1, or a TGLS file must be provided.");
+        return -1;
+    }
+    LOG.line("Genotyping error: " + fmt_g(o.error));
+    if (o.max_gap < 0) { LOG.error("ERROR: Max gap must be > 0."); return -1; }
+    LOG.line("Max gap: " + std::to_string(o.max_gap));
+    if (o.overlap_frac < 0 || o.overlap_frac > 1) { LOG.error("ERROR: Overlap fraction must be >= 0 and <= 1."); return -1; }
+    if (o.auto_overlap) LOG.line("Overlap fraction: automatic");
+    else if (o.overlap_frac != 0) LOG.line("Overlap fraction: " + fmt_g(o.overlap_frac));
+    else LOG.line("Overlap fraction: 1/winsize");
+    if (o.mu <= 0) { LOG.error("ERROR: Mutation rate must be > 0."); return -1; }
+    LOG.line("mu: " + fmt_g(o.mu));
+    if (o.M <= 0) { LOG.error("ERROR: Number of meioses must be > 0."); return -1; }
+    LOG.line("M: " + std::to_string(o.M));
+    if (o.nclust <= 0) { LOG.error("ERROR: Must choose positive number for number of GMM clusters."); return -1; }
+    LOG.line("# GMM clusters: " + std::to_string(o.nclust));
+    LOG.line(o.kde_subsample <= 0 ? std::string("# of rand individuals for KDE: ALL") : "# of rand individuals for KDE: " + std::to_string(o.kde_subsample));
+    LOG.line(o.ld_subsample <= 0 ? std::string("# of rand individuals for LD: ALL") : "# of rand individuals for LD: " + std::to_string(o.ld_subsample));
+    LOG.line("Output raw LOD scores: " + fmt_bool(o.raw_lod));
+    LOG.line("Use r2 for weighting phased data: " + fmt_bool(o.phased));
+    const bool thin = !o.no_kde_thinning;
+    LOG.line("Use thinning for KDE estimation: " + fmt_bool(thin));
+    c.rng.seed(o.seed >= 0 ? (o.seed == 0 ? 4357u : (unsigned)o.seed) : (unsigned)time(nullptr));
+
+    // ---- inputs ----
+    if (!load_centromeres(o.build, o.centromere, c.cen)) return -1;
+    if (!load_tped(o.tped, o.tped_missing, c.tped)) return 1;
+    Tped& t = c.tped;
+    LOG.line("Total loci: " + std::to_string(t.n_loci));
+    if (!load_tfam(o.tfam, c.tfam)) return 1;
+    if ((int)c.tfam.ids.size() != t.n_ind) { LOG.error("ERROR: tfam and tped disagree on the number of individuals."); return 1; }
+    LOG.line("Population: " + c.tfam.pop);
+    LOG.line("Total diploid individuals: " + std::to_string(t.n_ind));
+    std::vector<double> gl;
+    if (use_gl && !load_tgls(o.tgls, t, gl)) return 1;
+    const bool oob = o.weighted || o.cm;
+    if (oob) {
+        if (!load_map(o.map, c.scaffold)) return 1;
+        if (c.scaffold.size() != t.chr_names.size()) {
+            LOG.error("ERROR: Scaffold genetic map does not have the same number of chromosomes as data.");
+            return -1;
+        }
+    }
+    const int C = (int)t.chr_names.size();
+    bool warned = false;
+    for (int ch = 0; ch < C; ++ch) {
+        c.labels.push_back(chr_label(t.chr_names[ch]));
+        auto it = c.cen.find(c.labels.back());
+        if (it == c.cen.end()) {   // centromere::centromereStart/End: 0/0 + warning (garlic-centromeres.cpp:33-59)
+            LOG.error("WARNING: No centromere start information for chr: " + c.labels.back());
+            if (!warned) LOG.error("WARNING: If you provided custom centromeres check that chromosome names match between data files.");
+            warned = true;
+            c.cen_arr.push_back(0); c.cen_arr.push_back(0);
+        } else { c.cen_arr.push_back(it->second.first); c.cen_arr.push_back(it->second.second); }
+    }
+
+    // ---- GPU: coding, counts, freq, filter (K1-K3) ----
+    if (garlic_gpu_create(o.device, &c.g)) { LOG.error("ERROR: no usable CUDA device; garlic_b200 has no CPU path."); return 1; }
+    if (!gpu_ok(c, garlic_gpu_set_shape(c.g, t.n_ind, 0, t.n_loci, C, t.chr_off.data(), t.pos.data()), "set_shape")) return 1;
+    const int64_t blk = 1 << 16;
+    for (int64_t s0 = 0; s0 < t.n_loci; s0 += blk)
+        if (!gpu_ok(c, garlic_gpu_put_alleles(c.g, t.alleles.data() + (size_t)s0 * t.n_ind * 2, s0, (int)std::min(blk, t.n_loci - s0), o.tped_missing), "put_alleles")) return 1;
+    if (!gpu_ok(c, garlic_gpu_code_alleles(c.g), "code_alleles")) return 1;
+    std::vector<uint8_t>().swap(t.alleles);
+    if (use_gl) {
+        const int type = o.gl_type == "GQ" ? GARLIC_GL_GQ : o.gl_type == "GL" ? GARLIC_GL_GL : GARLIC_GL_PL;
+        if (!gpu_ok(c, garlic_gpu_put_gl(c.g, gl.data(), type), "put_gl")) return 1;
+        std::vector<double>().swap(gl);
+    }
+    std::vector<int32_t> chr_param;
+    if (oob)
+        for (int ch = 0; ch < C; ++ch) {
+            chr_param.push_back(c.scaffold[ch].pos.front()); chr_param.push_back(c.scaffold[ch].pos.back());
+            chr_param.push_back(c.cen_arr[2 * ch]); chr_param.push_back(c.cen_arr[2 * ch + 1]);
+        }
+    std::vector<double> freq0(t.n_loci);
+    if (!gpu_ok(c, garlic_gpu_filter(c.g, oob, oob ? chr_param.data() : nullptr, nullptr, freq0.data(), nullptr, &c.L), "filter")) return 1;
+    std::vector<uint8_t> one(t.n_loci);
+    if (!gpu_ok(c, garlic_gpu_get_one_allele(c.g, one.data(), o.tped_missing), "get_one_allele")) return 1;
+    if (!write_freq_gz(o.out + ".freq.gz", t, one, freq0)) return 1;
+    std::vector<int32_t> src(c.L);
+    garlic_gpu_get_kept_index(c.g, src.data());
+    c.pos.resize(c.L);
+    c.chr_off.assign(C + 1, 0);
+    {
+        int ch = 0;
+        for (int64_t d = 0; d < c.L; ++d) {
+            while (src[d] >= t.chr_off[ch + 1]) { ++ch; c.chr_off[ch] = d; }
+            c.pos[d] = t.pos[src[d]];
+        }
+        for (++ch; ch <= C; ++ch) c.chr_off[ch] = c.L;
+    }
+    if (oob) {
+        LOG.line("Monomorphic or out of bounds loci filtered: " + std::to_string(t.n_loci - c.L));
+        c.gpos.resize(c.L);
+        int n_interp = 0;
+        for (int ch = 0; ch < C; ++ch)
+            if (!interpolate_map(c.pos.data() + c.chr_off[ch], c.chr_off[ch + 1] - c.chr_off[ch], c.scaffold[ch], c.gpos.data() + c.chr_off[ch], n_interp)) {
+                LOG.error("ERROR: Sites outside of map scaffold should have been filtered out.");
+                return 1;
+            }
+        LOG.line("Number of genetic map locations interpolated: " + std::to_string(n_interp));
+    } else LOG.line("Monomorphic loci filtered: " + std::to_string(t.n_loci - c.L));
+    LOG.line("Total loci used for analysis: " + std::to_string(c.L));
+    if (!gpu_ok(c, garlic_gpu_set_tables(c.g, o.error, o.max_gap, c.cen_arr.data(), oob ? c.gpos.data() : nullptr), "set_tables")) return 1;
+    if (!use_gl && !o.device_lut) {
+        // per-SNP LOD table with the HOST libm (lod(), garlic-roh.cpp:355-386, same operation order): the
+        // reference's windows then come out bit-identical for whole-segment chains, which keeps the FIGTree
+        // input of the cutoff selection the reference's own.  --device-lut builds it with K4 instead (≤ 1 ulp).
+        std::vector<double> lut((size_t)c.L * 4);
+        for (int64_t d = 0; d < c.L; ++d)
+            for (int g = 0; g < 4; ++g) lut[(size_t)d * 4 + g] = lod_host(g, freq0[src[d]], o.error);
+        if (!gpu_ok(c, garlic_gpu_set_lut(c.g, lut.data()), "set_lut")) return 1;
+    }
+    double density = -1;
+    if ((o.auto_winsize && o.weighted) || o.auto_overlap) density = calc_density(c);
+
+    // ---- window size (garlic-main.cpp:295-336; garlic-roh.cpp:699-933) ----
+    Kde selected;
+    bool have_kde = false;
+    if (explore || (o.auto_winsize && !o.weighted)) {
+        std::vector<int32_t> sub;
+        const std::vector<int32_t>* subp = nullptr;
+        if (o.kde_subsample > 0 && o.kde_subsample < t.n_ind) {   // subsetData, garlic-data.cpp:2171-2244
+            sub = choose(c, o.kde_subsample, t.n_ind);
+            std::string s = "Individuals used for KDE: ";
+            for (int i : sub) s += c.tfam.ids[i] + " ";
+            LOG.line(s);
+            subp = &sub;
+        }
+        auto kde_for = [&](int W, Kde& k) -> bool {
+            if (o.weighted) {
+                std::vector<int32_t> ld;
+                if (o.ld_subsample > 0 && o.ld_subsample < t.n_ind) ld = choose(c, o.ld_subsample, t.n_ind);
+                garlic_gpu_set_wlod(c.g, o.mu, o.M);
+                if (!gpu_ok(c, garlic_gpu_ld_band(c.g, W, ld.empty() ? nullptr : ld.data(), (int)ld.size(), nullptr), "ld_band")) return false;
+            }
+            std::vector<double> data;
+            if (!thinned_windows(c, W, thin ? W : 1, subp, data)) return false;
+            if (data.size() < 2) { LOG.error("ERROR: no valid windows for window size " + std::to_string(W)); return false; }
+            compute_kde(data, k, o.kde_direct);
+            return true;
+        };
+        if (explore && !(o.auto_winsize && !o.weighted)) {          // exploreWinsizes: KDE files only
+            for (int W : o.winsize_multi) {
+                Kde k;
+                if (!kde_for(W, k)) return 1;
+                if (!write_kde(k, o.out + "." + std::to_string(W) + "SNPs.kde")) return 1;
+            }
+            garlic_gpu_destroy(c.g);
+            return 0;
+        }
+        LOG.line("Searching for acceptable window size, smoothness threshold: 0.5");
+        LOG.line("winsize\tsmoothness");
+        if (explore) {                                               // selectWinsizeFromList
+            for (size_t i = 0; i < o.winsize_multi.size(); ++i) {
+                Kde k;
+                const int W = o.winsize_multi[i];
+                if (!kde_for(W, k)) return 1;
+                const double mse = wiggle(k);
+                LOG.line(" " + std::to_string(W) + "\t " + fmt_g(mse));   // LOG.log("",W,false) + LOG.log("\t",mse)
+                if (mse <= 0.5 || i + 1 == o.winsize_multi.size()) { selected = k; winsize = W; have_kde = true; break; }
+            }
+        } else {                                                     // selectWinsize
+            for (int W = winsize;; W += o.auto_winsize_step) {
+                Kde k;
+                if (!kde_for(W, k)) return 1;
+                const double mse = wiggle(k);
+                LOG.line(" " + std::to_string(W) + "\t " + fmt_g(mse));
+                if (mse <= 0.5) { selected = k; winsize = W; have_kde = true; break; }
+            }
+        }
+        if (!write_kde(selected, o.out + "." + std::to_string(winsize) + "SNPs.kde")) return 1;
+        if (!explore) LOG.line("Selected window size: " + std::to_string(winsize));
+    } else if (o.auto_winsize) {                                     // selectWinsizeWeighted, garlic-roh.cpp:3-9
+        const int size = int(8.3235 * std::log(density) + 138.0521 + 0.5);
+        winsize = size >= 10 ? size : 10;
+        LOG.line("Selected window size: " + std::to_string(winsize));
+    }
+    printf("Window size: %d\n", winsize);
+    double overlap = o.overlap_frac;
+    if (o.auto_overlap) {                                            // selectOverlapFrac, garlic-data.cpp:3-8
+        overlap = (6.375 * std::log(density) + 63.888) / 100.0;
+        if (overlap > 1) overlap = 1.0;
+        if (overlap <= 0) overlap = 1.0 / double(winsize);
+        LOG.line("Selected overlap fraction: " + fmt_g(overlap));
+    }
+
+    // ---- LD band for wLOD (K6) ----
+    if (o.weighted) {
+        fprintf(stderr, "Calculating LD matrix.\n");
+        std::vector<int32_t> ld;
+        if (o.ld_subsample > 0 && o.ld_subsample < t.n_ind) ld = choose(c, o.ld_subsample, t.n_ind);
+        garlic_gpu_set_wlod(c.g, o.mu, o.M);
+        if (!gpu_ok(c, garlic_gpu_ld_band(c.g, winsize, ld.empty() ? nullptr : ld.data(), (int)ld.size(), nullptr), "ld_band")) return 1;
+    }
+
+    // ---- pass 1: thinned windows → KDE → cutoff (host, FIGTree) ----
+    if (auto_cutoff) {
+        if (!have_kde) {
+            std::vector<int32_t> sub;
+            const std::vector<int32_t>* subp = nullptr;
+            if (o.kde_subsample > 0) {
+                if (o.kde_subsample < t.n_ind) sub = choose(c, o.kde_subsample, t.n_ind);
+                else { sub.resize(t.n_ind); for (int i = 0; i < t.n_ind; ++i) sub[i] = i; }
+                std::string s = "Individuals used for KDE: ";
+                for (int i : sub) s += c.tfam.ids[i] + " ";
+                LOG.line(s);
+                subp = &sub;
+            }
+            std::vector<double> data;
+            if (!thinned_windows(c, winsize, thin ? winsize : 1, subp, data)) return 1;
+            if (data.size() < 2) { LOG.error("ERROR: no valid windows to estimate the LOD score density."); return 1; }
+            fprintf(stderr, "Estimating distribution of raw LOD score windows:\n");
+            compute_kde(data, selected, o.kde_direct);
+            if (!write_kde(selected, o.out + "." + std::to_string(winsize) + "SNPs.kde")) return -1;
+        }
+        cutoff = min_between_modes(selected, winsize);
+        LOG.line("Selected LOD score cutoff: " + fmt_g(cutoff));
+        printf("Selected LOD score cutoff (17 digits): %.17g\n", cutoff);
+    } else printf("User defined LOD score cutoff: %s\n", fmt_g(cutoff).c_str());
+
+    // ---- pass 2: windows → cutoff → coverage → ROH (fused K5) ----
+    printf("Assembling ROH windows\n");
+    std::vector<garlic_roh_t> rec(1 << 16);
+    int64_t n_roh = 0;
+    for (;;) {
+        if (!gpu_ok(c, garlic_gpu_call_roh(c.g, winsize, cutoff, overlap, o.weighted, o.exact, rec.data(), (int64_t)rec.size(), &n_roh), "call_roh")) return 1;
+        if (n_roh <= (int64_t)rec.size()) break;
+        rec.resize(n_roh + 1024);
+    }
+    std::vector<Roh> roh(n_roh);
+    std::vector<double> lengths(n_roh);
+    for (int64_t r = 0; r < n_roh; ++r) {
+        const int a = rec[r].start_idx, b = rec[r].stop_idx;
+        roh[r].ind = rec[r].ind; roh[r].chr = rec[r].chr;
+        roh[r].start = c.pos[a]; roh[r].stop = c.pos[b];
+        roh[r].length = o.cm ? c.gpos[b] - c.gpos[a] : double(c.pos[b] - c.pos[a] + 1);   // garlic-roh.cpp:478-484
+        lengths[r] = roh[r].length;
+    }
+    garlic_gpu_destroy(c.g);
+
+    // ---- size classes (host GMM) and output ----
+    if (auto_bounds) {
+        printf("Fitting %d-component GMM for size classification\n", o.nclust);
+        if (!size_classes(lengths, o.nclust, bounds)) return 1;
+        LOG.line("Selected ROH size boundaries = (" + join(bounds) + " )");
+    } else LOG.line("User provided ROH size boundaries = (" + join(bounds) + " )");
+    printf("Writing ROH tracts.\n");
+    if (!write_bed(o.out + ".roh.bed", roh, c.tfam.ids, c.labels, bounds, c.tfam.pop, o.cm)) return 1;
+    printf("Finished.\n");
+    LOG.close();
+    return 0;
+}

@@ -102,7 +102,8 @@ int garlic_gpu_filter(garlic_gpu_t *h, int oob, const int32_t *chr_param, const 
  * genetic positions [L] of the kept SNPs (needed for --weighted). */
 int garlic_gpu_set_tables(garlic_gpu_t *h, double error, int max_gap, const int32_t *centromeres,
                           const double *gpos);
-/* test hook: overwrite the device LOD table with host values [L][4] (bit-exact chain tests) */
+/* host-supplied LOD table [L][4] (g = 0,1,2,missing) replacing the device-built one: the C++ driver uses
+ * it to evaluate lod() with the host libm, so whole-segment chains are bit-identical to the reference's */
 int garlic_gpu_set_lut(garlic_gpu_t *h, const double *lut);
 int garlic_gpu_get_lut(garlic_gpu_t *h, double *lut);
 /* homFreq per kept SNP (calculateGenoFreq) from the reduced counts */
@@ -124,6 +125,10 @@ int garlic_gpu_set_wlod(garlic_gpu_t *h, double mu, int M);
 int64_t garlic_gpu_window_slots(garlic_gpu_t *h, int step);
 int garlic_gpu_windows(garlic_gpu_t *h, int winsize, int step, int weighted, const int32_t *individuals,
                        int n, int exact, double *out);
+/* same, but the [n][n_slots] matrix stays on the GPU (valid until the next windows call): *out_dev receives
+ * the device pointer — multi-GPU runs all-gather it before the one copy to the host */
+int garlic_gpu_windows_dev(garlic_gpu_t *h, int winsize, int step, int weighted, const int32_t *individuals,
+                           int n, int exact, void **out_dev);
 
 /* ---- K5 pass 2: calc[w]LODWindows + assembleROHWindows fused (src/garlic-roh.cpp:279-347,409-546)
  * overlap_frac as --overlap-frac. out: capacity cap records, sorted by (ind, chr, start);
