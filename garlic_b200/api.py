@@ -142,15 +142,20 @@ class GarlicGPU:
         self._ck(self.lib.garlic_gpu_put_gl(self.h, _p(v), C.c_int(GL_TYPES[gl_type])))
 
     # ---------------------------------------------------------------- filter / tables
-    def filter(self, oob=False, chr_param=None, freq_override=None):
-        freq = np.empty(self.L0, np.float64)
-        keep = np.empty(self.L0, np.uint8)
+    def filter(self, oob=False, chr_param=None, freq_override=None, want_freq=True, want_keep=True):
+        """→ (freq float64[L0], keep bool[L0], L).  The two arrays are views of buffers owned by this object and
+        are overwritten by the next filter() call (repeated runs then touch no fresh pages)."""
+        if getattr(self, "_freq_buf", None) is None or len(self._freq_buf) != self.L0:
+            self._freq_buf = np.empty(self.L0, np.float64)
+            self._keep_buf = np.empty(self.L0, np.uint8)
+        freq = self._freq_buf if want_freq else None
+        keep = self._keep_buf if want_keep else None
         n = C.c_int64(0)
         cp = None if chr_param is None else np.ascontiguousarray(chr_param, np.int32)
         fo = None if freq_override is None else np.ascontiguousarray(freq_override, np.float64)
         self._ck(self.lib.garlic_gpu_filter(self.h, C.c_int(int(oob)), _p(cp), _p(fo), _p(freq), _p(keep), C.byref(n)))
         self.L = n.value
-        return freq, keep.astype(bool), n.value
+        return freq, (keep.view(np.bool_) if keep is not None else None), n.value
 
     def set_tables(self, error, max_gap, centromeres, gpos=None):
         cen = np.ascontiguousarray(centromeres, np.int32).reshape(-1)

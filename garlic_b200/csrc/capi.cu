@@ -4,6 +4,7 @@
 // hot path happens in the kernels of kernels.cu / wlod.cu.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -65,12 +66,33 @@ struct garlic_gpu {
     size_t indlist_cap = 0;
     double stats[4] = {0, 0, 0, 0};
     uint32_t* d_keepw = nullptr;
+    int* d_scan = nullptr;         // block counts of the keep scan, total, kept chromosome offsets
+    int* d_breaks = nullptr;       // bad-pair list
     int* d_first_word = nullptr;
     uint8_t* d_first_skip = nullptr;
     uint8_t* pin = nullptr;        // pinned host staging buffer
     size_t pin_cap = 0;
     std::map<void*, size_t> cap;   // bytes behind each device pointer slot (keyed by the slot's address)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+// GARLIC_TIMING=1: wall-clock laps of the host-side phases of an entry point, to stderr
+struct Laps {
+    bool on;
+    const char* name;
+    std::chrono::steady_clock::time_point t0;
+    std::string out;
+    explicit Laps(const char* n) : on(getenv("GARLIC_TIMING") != nullptr), name(n), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* what)
+    {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        char b[96];
+        snprintf(b, sizeof b, " %s=%.3f", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        out += b;
+        t0 = t1;
+    }
+    ~Laps() { if (on) fprintf(stderr, "[garlic_b200] %s:%s ms\n", name, out.c_str()); }
 };
 
 #define CK(call)                                                                              \
@@ -110,6 +132,17 @@ static int pin_alloc(garlic_gpu* h, size_t bytes)
     return 0;
 }
 
+// host copy of the gather list (kept SNP → pre-filter index), fetched from the device on first use
+static int fetch_src(garlic_gpu* h)
+{
+    if ((int64_t)h->src.size() == h->L) return 0;
+    h->src.resize(h->L);
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->src.data(), h->d_src, h->L * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" {
 
 int garlic_gpu_create(int device, garlic_gpu_t** out)
@@ -145,7 +178,7 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     dev_free(h->d_homf); dev_free(h->d_keep); dev_free(h->d_src); dev_free(h->d_pos0); dev_free(h->d_chr_of0);
     dev_free(h->d_pos); dev_free(h->d_chr_of); dev_free(h->d_chr_start); dev_free(h->d_chr_param);
     dev_free(h->d_out); dev_free(h->d_amb); dev_free(h->d_cnt); dev_free(h->d_items); dev_free(h->d_indlist); dev_free(h->d_dump);
-    dev_free(h->d_keepw); dev_free(h->d_first_word); dev_free(h->d_first_skip);
+    dev_free(h->d_keepw); dev_free(h->d_first_word); dev_free(h->d_first_skip); dev_free(h->d_scan); dev_free(h->d_breaks);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -324,24 +357,21 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     if (!h->have_geno0) FAIL("filter: no genotypes loaded");
     if (oob && !chr_param) FAIL("filter: oob filtering needs chr_param");
     const int64_t L0 = h->L0;
+    Laps laps("filter");
     if (dev_alloc(h, &h->d_freq0, (size_t)L0)) return 1;
     if (dev_alloc(h, &h->d_keep, (size_t)L0)) return 1;
     if (oob) {
         if (dev_alloc(h, &h->d_chr_param, (size_t)4 * h->n_chr)) return 1;
         CK(cudaMemcpyAsync(h->d_chr_param, chr_param, 4 * h->n_chr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     }
-    // pinned staging: freq0[L0] doubles | keep[L0] bytes (device → host), then the gather tables
+    // pinned staging: freq0[L0] doubles | keep[L0] bytes | total, chr_off_kept[C+1] ints
     const int64_t n_in_words = (L0 + 31) >> 5;
-    const size_t off_keep = (size_t)L0 * 8, off_src = (off_keep + (size_t)L0 + 63) & ~(size_t)63;
-    const size_t off_keepw = off_src + (size_t)L0 * 4, off_fw = off_keepw + (size_t)n_in_words * 4;
-    const size_t off_fs = off_fw + (size_t)(n_in_words + 1) * 4, pin_bytes = off_fs + (size_t)n_in_words + 64;
-    if (pin_alloc(h, pin_bytes)) return 1;
+    const int n_blocks = (int)((L0 + 1023) / 1024);
+    const size_t off_keep = (size_t)L0 * 8, off_meta = (off_keep + (size_t)L0 + 63) & ~(size_t)63;
+    if (pin_alloc(h, off_meta + (size_t)(h->n_chr + 2) * 4 + 64)) return 1;
     double* freq0 = reinterpret_cast<double*>(h->pin);
     uint8_t* keep = h->pin + off_keep;
-    int32_t* src = reinterpret_cast<int32_t*>(h->pin + off_src);
-    uint32_t* keepw = reinterpret_cast<uint32_t*>(h->pin + off_keepw);
-    int32_t* first_word = reinterpret_cast<int32_t*>(h->pin + off_fw);
-    uint8_t* first_skip = h->pin + off_fs;
+    int32_t* meta = reinterpret_cast<int32_t*>(h->pin + off_meta);
     if (freq_override) {
         // --freq-file: frequencies come from the caller; the predicate is evaluated on the host copy
         for (int64_t s = 0; s < L0; ++s) {
@@ -356,50 +386,38 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
             freq0[s] = f; keep[s] = k;
         }
         CK(cudaMemcpyAsync(h->d_freq0, freq0, L0 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_keep, keep, L0, cudaMemcpyHostToDevice, h->stream));
     } else {
         LAUNCH(launch_freq_keep(h->d_counts, L0, h->d_pos0, h->d_chr_of0, h->d_chr_param, oob, h->d_freq0, h->d_keep, h->stream));
         if (freq_out) CK(cudaMemcpyAsync(freq0, h->d_freq0, L0 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(keep, h->d_keep, L0, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        if (keep_out) CK(cudaMemcpyAsync(keep, h->d_keep, L0, cudaMemcpyDeviceToHost, h->stream));
     }
+    // exclusive scan of the keep mask on the device: gather list, keep bits per input word, per output word
+    // the input word it starts in, kept offset of every chromosome
+    if (dev_alloc(h, &h->d_src, (size_t)L0)) return 1;
+    if (dev_alloc(h, &h->d_keepw, (size_t)n_in_words)) return 1;
+    if (dev_alloc(h, &h->d_first_word, (size_t)n_in_words)) return 1;
+    if (dev_alloc(h, &h->d_first_skip, (size_t)n_in_words)) return 1;
+    if (dev_alloc(h, &h->d_scan, (size_t)n_blocks + h->n_chr + 8)) return 1;
+    int* d_total = h->d_scan + n_blocks;
+    int* d_chr_off_kept = d_total + 1;
+    CK(launch_keep_scan(h->d_keep, L0, h->d_chr_of0, h->n_chr, h->d_scan, d_total, h->d_src, h->d_keepw, h->d_first_word,
+                        h->d_first_skip, d_chr_off_kept, h->stream));
+    h->launches += 3;
+    CK(cudaMemcpyAsync(meta, d_total, (size_t)(h->n_chr + 2) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    laps.lap("freq_keep+scan+d2h");
     if (freq_out) memcpy(freq_out, freq0, L0 * sizeof(double));
     if (keep_out) memcpy(keep_out, keep, L0);
-    // one host pass over the keep mask (O(L0) integers): gather list, kept positions, per-chromosome
-    // offsets, keep bits per 32-SNP input word, and per output word the input word it starts in
-    h->src.resize(L0);
-    h->pos.resize(L0);
+    laps.lap("copy_out");
+    const int64_t L = meta[0];
     h->chr_off.assign(h->n_chr + 1, 0);
-    for (int64_t j = 0; j < n_in_words; ++j) keepw[j] = 0;
-    int64_t L = 0;
-    for (int c = 0; c < h->n_chr; ++c) {
-        for (int64_t s = h->chr_off0[c]; s < h->chr_off0[c + 1]; ++s) {
-            if (!keep[s]) continue;
-            if ((L & 31) == 0) {
-                first_word[L >> 5] = (int32_t)(s >> 5);
-                first_skip[L >> 5] = (uint8_t)__builtin_popcount(keepw[s >> 5]);   // kept fields of that word already placed
-            }
-            keepw[s >> 5] |= 1u << (s & 31);
-            src[L] = (int32_t)s;
-            h->src[L] = (int32_t)s;
-            h->pos[L] = h->pos0[s];
-            ++L;
-        }
-        h->chr_off[c + 1] = L;
-    }
-    h->src.resize(L);
-    h->pos.resize(L);
+    for (int c = 0; c <= h->n_chr; ++c) h->chr_off[c] = meta[1 + c];
+    h->src.clear();          // host copies of the gather list / kept positions are fetched on demand
+    h->pos.clear();
     h->L = L;
     if (n_kept) *n_kept = L;
     if (L < 1) FAIL("filter: no polymorphic loci left");
-    const int64_t n_out_words = (L + 31) >> 5;
-    if (dev_alloc(h, &h->d_src, (size_t)L)) return 1;
-    if (dev_alloc(h, &h->d_keepw, (size_t)n_in_words)) return 1;
-    if (dev_alloc(h, &h->d_first_word, (size_t)n_out_words)) return 1;
-    if (dev_alloc(h, &h->d_first_skip, (size_t)n_out_words)) return 1;
-    CK(cudaMemcpyAsync(h->d_src, src, L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_keepw, keepw, n_in_words * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_first_word, first_word, n_out_words * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_first_skip, first_skip, n_out_words, cudaMemcpyHostToDevice, h->stream));
     h->row_words = ((L + kPad + 31) >> 5) + 2;
     // the slack words behind each row are only ever over-read (their lookups are masked), so they need
     // no defined content; a fresh allocation is filled once so that dumps stay reproducible
@@ -427,7 +445,7 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     LAUNCH(launch_gather_i32(h->d_pos0, h->d_src, L, h->d_pos, h->stream));
     LAUNCH(launch_gather_i32(h->d_chr_of0, h->d_src, L, h->d_chr_of, h->stream));
     CK(cudaMemcpyAsync(h->d_chr_start, chr_start.data(), h->n_chr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    laps.lap("enqueue");   // compaction and gathers run stream-ordered behind this call
     h->filtered = true; h->tables = false; h->have_ld = false;
     return 0;
 }
@@ -450,6 +468,7 @@ int garlic_gpu_get_genotypes(garlic_gpu_t* h, int filtered, uint8_t* rows, int64
 int garlic_gpu_get_kept_index(garlic_gpu_t* h, int32_t* src_index)
 {
     if (!h->filtered) FAIL("get_kept_index: call filter first");
+    if (fetch_src(h)) return 1;
     memcpy(src_index, h->src.data(), h->L * sizeof(int32_t));
     return 0;
 }
@@ -459,6 +478,7 @@ int garlic_gpu_set_tables(garlic_gpu_t* h, double error, int max_gap, const int3
     CK(cudaSetDevice(h->device));
     if (!h->filtered) FAIL("set_tables: call filter first");
     h->error = error; h->max_gap = max_gap;
+    Laps laps("set_tables");
     h->cen.assign(2 * h->n_chr, 0);
     if (centromeres) h->cen.assign(centromeres, centromeres + 2 * h->n_chr);
     const int64_t L = h->L;
@@ -475,7 +495,38 @@ int garlic_gpu_set_tables(garlic_gpu_t* h, double error, int max_gap, const int3
     // bound on |LOD| for the ambiguity tolerance: with a global error the largest magnitudes are
     // log10(error) (heterozygote) and log10 of 1/f-type terms; freq ∈ [1/(2N_total), 1-1/(2N_total)]
     h->amax = 20.0;
-    build_stretches(h->chr_off, h->pos, h->cen, h->max_gap, h->stretches);
+    laps.lap("lut");
+    // gap/centromere-free stretches: bad adjacent pairs found on the device (a short list), sorted here
+    {
+        const unsigned cap = 1u << 20;
+        if (dev_alloc(h, &h->d_breaks, (size_t)cap + 2 * h->n_chr + 4)) return 1;
+        int* d_cen = h->d_breaks + cap;
+        unsigned* d_n = reinterpret_cast<unsigned*>(d_cen + 2 * h->n_chr);
+        CK(cudaMemcpyAsync(d_cen, h->cen.data(), 2 * h->n_chr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemsetAsync(d_n, 0, sizeof(unsigned), h->stream));
+        LAUNCH(launch_bad_pairs(h->d_pos, h->d_chr_of, d_cen, max_gap, L, h->d_breaks, d_n, cap, h->stream));
+        if (pin_alloc(h, 64)) return 1;
+        unsigned* n_host = reinterpret_cast<unsigned*>(h->pin);
+        CK(cudaMemcpyAsync(n_host, d_n, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        const unsigned nb = *n_host;
+        if (nb > cap) FAIL("set_tables: more than 2^20 gaps; raise --max-gap");
+        std::vector<int> breaks(nb);
+        if (nb) CK(cudaMemcpy(breaks.data(), h->d_breaks, nb * sizeof(int), cudaMemcpyDeviceToHost));
+        std::sort(breaks.begin(), breaks.end());
+        h->stretches.clear();
+        size_t bi = 0;
+        for (int c = 0; c < h->n_chr; ++c) {
+            int a = (int)h->chr_off[c];
+            const int hi = (int)h->chr_off[c + 1];
+            while (bi < breaks.size() && breaks[bi] < hi) {
+                if (breaks[bi] > a) h->stretches.push_back({c, a, breaks[bi]});
+                a = breaks[bi++];
+            }
+            if (hi > a) h->stretches.push_back({c, a, hi});
+        }
+    }
+    laps.lap("stretches");
     h->tables = true; h->have_ld = false;
     return 0;
 }
@@ -504,6 +555,7 @@ int garlic_gpu_get_hom_freq(garlic_gpu_t* h, double* hom_freq)
     if (!h->filtered) FAIL("get_hom_freq: call filter first");
     std::vector<int> hom(h->L0), nm(h->L0);
     if (garlic_gpu_get_counts(h, nullptr, nullptr, hom.data(), nm.data())) return 1;
+    if (fetch_src(h)) return 1;
     for (int64_t d = 0; d < h->L; ++d) {
         double total = nm[h->src[d]], fh = hom[h->src[d]];
         fh /= total;   // 0/0 → NaN exactly as the reference (garlic-data.cpp:672)
@@ -652,6 +704,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     if (!(cutoff > kMissing)) FAIL("call_roh: LOD cutoff must be greater than the MISSING sentinel (-9999)");
     if (weighted && ensure_weighted(h, winsize)) return 1;
     const int W = winsize;
+    Laps laps("call_roh");
     // garlic-roh.cpp:422-424, compared against integers at :466 and :477
     double thr_d = overlap_frac * W;
     thr_d = (thr_d >= 1) ? thr_d : 1;
@@ -680,6 +733,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         h->amb_cap = 1u << 16;
         if (dev_alloc(h, &h->d_amb, h->amb_cap)) return 1;
     }
+    laps.lap("items");
     std::vector<RohRec> recs, ambs;
     float ms = 0;
     for (int attempt = 0; attempt < 3; ++attempt) {
@@ -723,6 +777,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         }
         break;
     }
+    laps.lap("kernel+d2h");
     // exact re-evaluation of (individual, segment) pairs that had a window within rounding
     // distance of the cutoff: one whole-segment launch per distinct segment
     int64_t n_amb_pairs = 0;
@@ -761,8 +816,10 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         recs.insert(recs.end(), fixed.begin(), fixed.end());
     }
     // sort by (individual, start) and stitch runs that were cut at chunk boundaries
+    laps.lap("ambiguous");
     std::vector<RohRec> merged;
     stitch_runs(recs, thr, merged);
+    laps.lap("stitch");
     const int64_t n_out = (int64_t)merged.size();
     for (int64_t r = 0; r < n_out && r < cap && out; ++r) {
         out[r].ind = merged[r].ind;
@@ -775,6 +832,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     h->stats[1] = (double)units;
     h->stats[2] = (double)n_amb_pairs;
     h->stats[3] = ms;
+    laps.lap("out");
     return 0;
 }
 

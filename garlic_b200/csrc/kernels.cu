@@ -447,6 +447,142 @@ cudaError_t launch_compact_geno(const uint64_t* gin, int64_t in_words, long long
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// Keep-mask bookkeeping on the device (the exclusive scan behind filterMonomorphic*Sites' compaction):
+// one thread per SNP, a warp = one 32-SNP input word, so the keep bits of a word are a ballot.
+//   keep_count_kernel   : kept SNPs per 1024-SNP block
+//   keep_scan_kernel    : exclusive scan of the block counts (single CTA), total → *total
+//   keep_scatter_kernel : gather list src[], keep bits per input word, per output word the input word it starts
+//                         in and the kept fields of that word already consumed, kept offset of each chromosome
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+keep_count_kernel(const uint8_t* __restrict__ keep, long long L0, int* __restrict__ block_counts)
+{
+    __shared__ int s_w[32];
+    const long long s = (long long)blockIdx.x * 1024 + threadIdx.x;
+    const bool k = s < L0 && keep[s];
+    const unsigned m = __ballot_sync(0xffffffffu, k);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = s_w[threadIdx.x];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) block_counts[blockIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+keep_scan_kernel(int* __restrict__ block_counts, int n_blocks, int* __restrict__ total)
+{
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_blocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_blocks ? block_counts[i] : 0;
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int w = s_w[threadIdx.x];
+            int wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (threadIdx.x >= o) wi += t;
+            }
+            s_w[threadIdx.x] = wi - w;   // exclusive warp offsets
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        if (i < n_blocks) block_counts[i] = carry + s_w[threadIdx.x >> 5] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_w[31] + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+
+__global__ void __launch_bounds__(1024)
+keep_scatter_kernel(const uint8_t* __restrict__ keep, long long L0, const int* __restrict__ block_offsets,
+                    const int* __restrict__ chr_of0, int n_chr, const int* __restrict__ total, int* __restrict__ src,
+                    uint32_t* __restrict__ keepw, int* __restrict__ first_word, uint8_t* __restrict__ first_skip,
+                    int* __restrict__ chr_off_kept)
+{
+    __shared__ int s_w[32];
+    const long long s = (long long)blockIdx.x * 1024 + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool k = s < L0 && keep[s];
+    const unsigned m = __ballot_sync(0xffffffffu, k);
+    const int before = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) {
+        s_w[warp] = __popc(m);
+        if (s < L0) keepw[s >> 5] = m;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int w = s_w[threadIdx.x];
+        int wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (threadIdx.x >= o) wi += t;
+        }
+        s_w[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    if (s >= L0) return;
+    const int d = block_offsets[blockIdx.x] + s_w[warp] + before;   // kept SNPs before s
+    if (k) {
+        src[d] = (int)s;
+        if ((d & 31) == 0) { first_word[d >> 5] = (int)(s >> 5); first_skip[d >> 5] = (uint8_t)before; }
+    }
+    if (s == 0 || chr_of0[s] != chr_of0[s - 1]) chr_off_kept[chr_of0[s]] = d;
+    if (s == 0) chr_off_kept[n_chr] = *total;
+}
+
+cudaError_t launch_keep_scan(const uint8_t* keep, long long L0, const int* chr_of0, int n_chr, int* block_counts,
+                             int* total, int* src, uint32_t* keepw, int* first_word, uint8_t* first_skip,
+                             int* chr_off_kept, cudaStream_t st)
+{
+    if (!L0) return cudaSuccess;
+    const int n_blocks = (int)((L0 + 1023) / 1024);
+    keep_count_kernel<<<n_blocks, 1024, 0, st>>>(keep, L0, block_counts);
+    keep_scan_kernel<<<1, 1024, 0, st>>>(block_counts, n_blocks, total);
+    keep_scatter_kernel<<<n_blocks, 1024, 0, st>>>(keep, L0, block_counts, chr_of0, n_chr, total, src, keepw, first_word,
+                                                  first_skip, chr_off_kept);
+    return cudaGetLastError();
+}
+
+// Bad adjacent pairs (gap > MAX_GAP or overlapping the centromere, inGap garlic-roh.cpp:11-16,60-61) of the kept
+// SNPs: appends i for every bad pair (i-1,i) inside a chromosome; the host sorts the short list into stretches.
+__global__ void bad_pairs_kernel(const int* __restrict__ pos, const int* __restrict__ chr_of, const int* __restrict__ cen,
+                                 int max_gap, long long L, int* __restrict__ list, unsigned* __restrict__ count, unsigned cap)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x + 1; i < L; i += (long long)gridDim.x * blockDim.x) {
+        const int c = chr_of[i];
+        if (c != chr_of[i - 1]) continue;
+        const int qs = pos[i - 1], qe = pos[i], ts = cen[2 * c], te = cen[2 * c + 1];
+        const bool gap = (ts <= qs && te >= qs) || (ts <= qe && te >= qe) || (ts >= qs && te <= qe);
+        if ((qe - qs > max_gap) || gap) {
+            const unsigned p = atomicAdd(count, 1u);
+            if (p < cap) list[p] = (int)i;
+        }
+    }
+}
+cudaError_t launch_bad_pairs(const int* pos, const int* chr_of, const int* cen, int max_gap, long long L, int* list,
+                             unsigned* count, unsigned cap, cudaStream_t st)
+{
+    if (L < 2) return cudaSuccess;
+    long long blocks = (L + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    bad_pairs_kernel<<<(unsigned)blocks, 256, 0, st>>>(pos, chr_of, cen, max_gap, L, list, count, cap);
+    return cudaGetLastError();
+}
+
 // gather a per-SNP int array through src[]
 __global__ void gather_i32_kernel(const int* in, const int* src, long long L, int* out)
 {

@@ -26,6 +26,11 @@ cudaError_t launch_freq_keep(const int* counts, long long L0, const int* pos, co
 cudaError_t launch_compact_geno(const uint64_t* gin, int64_t in_words, long long n_in_words, const uint32_t* keepw,
                                 const int* first_word, const uint8_t* first_skip, long long L, uint64_t* gout,
                                 int64_t out_words, int n_ind, cudaStream_t st);
+cudaError_t launch_keep_scan(const uint8_t* keep, long long L0, const int* chr_of0, int n_chr, int* block_counts,
+                             int* total, int* src, uint32_t* keepw, int* first_word, uint8_t* first_skip,
+                             int* chr_off_kept, cudaStream_t st);
+cudaError_t launch_bad_pairs(const int* pos, const int* chr_of, const int* cen, int max_gap, long long L, int* list,
+                             unsigned* count, unsigned cap, cudaStream_t st);
 cudaError_t launch_gather_i32(const int* in, const int* src, long long L, int* out, cudaStream_t st);
 cudaError_t launch_compact_gl(const double* in, int64_t in_stride, const int* src, long long L, double* out,
                               int64_t out_stride, int n_ind, int type, cudaStream_t st);

@@ -121,11 +121,20 @@ inline void build_items(const std::vector<int64_t>& chr_off, int W, const std::v
 // (garlic-roh.cpp:477).  Returns the merged runs; tag keeps seg<<2.
 inline void stitch_runs(std::vector<RohRec>& recs, int thr, std::vector<RohRec>& out)
 {
-    // sort by (individual, start) through 64-bit keys (runs of one individual never share a start)
+    // sort by (individual, start): counting sort on the individual, then each individual's few runs by start
+    int n_ind = 0;
+    for (const RohRec& r : recs) n_ind = std::max(n_ind, r.ind + 1);
+    std::vector<uint32_t> first(n_ind + 1, 0);
+    for (const RohRec& r : recs) first[r.ind + 1]++;
+    for (int i = 0; i < n_ind; ++i) first[i + 1] += first[i];
     std::vector<std::pair<uint64_t, uint32_t>> key(recs.size());
-    for (size_t i = 0; i < recs.size(); ++i)
-        key[i] = {((uint64_t)(uint32_t)recs[i].ind << 32) | (uint32_t)recs[i].a, (uint32_t)i};
-    std::sort(key.begin(), key.end());
+    {
+        std::vector<uint32_t> cur(first.begin(), first.end() - 1);
+        for (size_t i = 0; i < recs.size(); ++i)
+            key[cur[recs[i].ind]++] = {((uint64_t)(uint32_t)recs[i].ind << 32) | (uint32_t)recs[i].a, (uint32_t)i};
+    }
+    for (int i = 0; i < n_ind; ++i)
+        if (first[i + 1] - first[i] > 1) std::sort(key.begin() + first[i], key.begin() + first[i + 1]);
     out.clear();
     out.reserve(recs.size());
     size_t i = 0;
