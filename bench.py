@@ -421,6 +421,9 @@ def main():
                     bytes_per_individual_window=alg_bytes / units_local,
                     peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                     kernel_units_per_s=units_local / (kms / 1e3),
+                pruning_pass_ms=state["stats"]["coarse_ms"],
+                candidate_pair_fraction=(state["stats"]["candidate_pairs"] / state["stats"]["all_pairs"]
+                                         if state["stats"]["candidate_pairs"] >= 0 else None),
                     note="2-bit genotypes + per-SNP table: 0.27 B per individual-window, so this kernel is bound by "
                          "fp64-add / L1 issue, not HBM (SURVEY §8d); frac is reported against HBM as the contract asks")
     tr = os.path.join(ROOT, "profiles", "r01_walk_traffic.json")

@@ -236,9 +236,10 @@ class GarlicGPU:
         return buf[:cnt.value].copy()
 
     def last_stats(self):
-        s = (C.c_double * 4)()
+        s = (C.c_double * 8)()
         self.lib.garlic_gpu_last_stats(self.h, s)
-        return dict(items=s[0], units=s[1], ambiguous_pairs=s[2], kernel_ms=s[3])
+        return dict(items=s[0], units=s[1], ambiguous_pairs=s[2], kernel_ms=s[3], coarse_ms=s[4],
+                    candidate_pairs=s[5], all_pairs=s[6])
 
     def launch_count(self):
         return int(self.lib.garlic_gpu_launch_count(self.h))

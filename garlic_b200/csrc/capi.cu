@@ -17,6 +17,7 @@
 #include "kernels.h"
 #include "wlod.h"
 #include "segments.h"
+#include "coarse.cuh"
 
 using namespace garlic;
 
@@ -64,10 +65,17 @@ struct garlic_gpu {
     size_t items_cap = 0;
     int* d_indlist = nullptr;
     size_t indlist_cap = 0;
-    double stats[4] = {0, 0, 0, 0};
+    double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t* d_keepw = nullptr;
     int* d_scan = nullptr;         // block counts of the keep scan, total, kept chromosome offsets
     int* d_breaks = nullptr;       // bad-pair list
+    uint2* d_ctab = nullptr;       // pruning tables (coarse.cuh), valid for coarse_W
+    int* d_cbmax = nullptr;
+    int coarse_W = 0;
+    int* d_cand_list = nullptr;
+    unsigned* d_cand_cnt = nullptr;
+    bool prune = true;             // GARLIC_NO_PRUNE=1 disables the pruning pass
+    cudaEvent_t ev2 = nullptr;
     int* d_first_word = nullptr;
     uint8_t* d_first_skip = nullptr;
     uint8_t* pin = nullptr;        // pinned host staging buffer
@@ -162,6 +170,8 @@ int garlic_gpu_create(int device, garlic_gpu_t** out)
     }
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
+    cudaEventCreate(&h->ev2);
+    h->prune = getenv("GARLIC_NO_PRUNE") == nullptr;
     cudaMalloc((void**)&h->d_cnt, 4 * sizeof(unsigned));
     *out = h;
     return 0;
@@ -182,6 +192,8 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
+    dev_free(h->d_ctab); dev_free(h->d_cbmax); dev_free(h->d_cand_list); dev_free(h->d_cand_cnt);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -207,7 +219,7 @@ int garlic_gpu_set_shape(garlic_gpu_t* h, int n_ind, int ind_offset, int64_t n_l
     h->n_ind = n_ind; h->ind_offset = ind_offset; h->L0 = n_loci; h->n_chr = n_chr;
     h->chr_off0.assign(chr_offsets, chr_offsets + n_chr + 1);
     h->pos0.assign(pos, pos + n_loci);
-    h->row_words0 = ((n_loci + kPad + 31) >> 5) + 2;
+    h->row_words0 = (((n_loci + kPad + 31) >> 5) + 3) & ~(int64_t)1;
     if (dev_alloc(h, &h->d_geno0, (size_t)n_ind * h->row_words0)) return 1;
     CK(cudaMemsetAsync(h->d_geno0, 0xff, (size_t)n_ind * h->row_words0 * 8, h->stream));
     if (dev_alloc(h, &h->d_counts, (size_t)4 * n_loci)) return 1;
@@ -418,7 +430,7 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     h->L = L;
     if (n_kept) *n_kept = L;
     if (L < 1) FAIL("filter: no polymorphic loci left");
-    h->row_words = ((L + kPad + 31) >> 5) + 2;
+    h->row_words = (((L + kPad + 31) >> 5) + 3) & ~(int64_t)1;   // even: rows are whole 16-byte quads
     // the slack words behind each row are only ever over-read (their lookups are masked), so they need
     // no defined content; a fresh allocation is filled once so that dumps stay reproducible
     const bool fresh = h->cap.find((void*)&h->d_geno) == h->cap.end() || !h->d_geno ||
@@ -527,7 +539,7 @@ int garlic_gpu_set_tables(garlic_gpu_t* h, double error, int max_gap, const int3
         }
     }
     laps.lap("stretches");
-    h->tables = true; h->have_ld = false;
+    h->tables = true; h->have_ld = false; h->coarse_W = 0;
     return 0;
 }
 
@@ -537,6 +549,7 @@ int garlic_gpu_set_lut(garlic_gpu_t* h, const double* lut)
     if (!h->tables) FAIL("set_lut: call set_tables first");
     CK(cudaMemcpy(h->d_lut, lut, (size_t)h->L * 4 * sizeof(double), cudaMemcpyHostToDevice));
     dev_free(h->d_wlut);   // the weighted score table is rebuilt on demand
+    h->coarse_W = 0;       // and so are the pruning tables
     return 0;
 }
 
@@ -607,14 +620,14 @@ static WalkParams base_params(const garlic_gpu* h, int W)
 
 static int ensure_weighted(garlic_gpu* h, int W);   // wlod tables + LD band present for this W
 static int launch_any_walk(garlic_gpu* h, const WalkParams& P, const Item* items, int n_items, int weighted, bool roh, bool dump,
-                           int tile_snps)
+                           int tile_snps, const CandList& cl = CandList())
 {
     if (weighted) {
         WlodParams Q;
         Q.base = P; Q.wlut = h->d_wlut; Q.invld = h->d_invld; Q.nomut = h->d_nomut; Q.norec = h->d_norec;
         LAUNCH(launch_wlod_walk(Q, items, n_items, h->have_gl, roh, dump, h->stream));
     } else {
-        LAUNCH(launch_walk(P, items, n_items, h->have_gl, roh, dump, tile_snps <= kTileSnpsMax ? tile_snps : 0, h->stream));
+        LAUNCH(launch_walk(P, items, n_items, h->have_gl, roh, dump, tile_snps <= kTileSnpsMax ? tile_snps : 0, cl, h->stream));
     }
     return 0;
 }
@@ -735,7 +748,8 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     }
     laps.lap("items");
     std::vector<RohRec> recs, ambs;
-    float ms = 0;
+    float ms = 0, ms_coarse = 0;
+    bool pruned = false;
     for (int attempt = 0; attempt < 3; ++attempt) {
         WalkParams P = base_params(h, W);
         P.cutoff = cutoff; P.thr = thr;
@@ -746,13 +760,43 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
             P.tol = (double)(longest + 2 * W) * 2.220446049250313e-16 * (W + 1) * h->amax;
         }
         CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
+        // pruning pass (coarse.cuh): drop (individual, item) pairs that provably hold no window >= cutoff - tol
+        const int tile_snps = items_tile_snps(items, W);
+        const bool prune = h->prune && !exact && !weighted && !h->have_gl && W >= kCoarseMinW && W <= kCoarseMaxW &&
+                           tile_snps <= kTileSnpsMax && (int64_t)items.size() * h->n_ind < (1ll << 31);
+        CandList cl;
         CK(cudaEventRecord(h->ev0, h->stream));
-        if (launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, true, false, items_tile_snps(items, W))) return 1;
+        if (prune) {
+            const int64_t n_hw = (h->L + kPad - 512) >> 4;
+            if (h->coarse_W != W) {
+                if (dev_alloc(h, &h->d_ctab, (size_t)n_hw)) return 1;
+                if (dev_alloc(h, &h->d_cbmax, (size_t)n_hw)) return 1;
+                LAUNCH(launch_coarse_tables(h->d_lut, n_hw, W, h->d_ctab, h->d_cbmax, h->stream));
+                h->coarse_W = W;
+            }
+            if (dev_alloc(h, &h->d_cand_list, (size_t)items.size() * h->n_ind)) return 1;
+            if (dev_alloc(h, &h->d_cand_cnt, items.size() + 1)) return 1;
+            CK(cudaMemsetAsync(h->d_cand_cnt, 0, (items.size() + 1) * sizeof(unsigned), h->stream));
+            CoarseParams Q;
+            Q.geno = h->d_geno; Q.row_words = h->row_words; Q.tab = h->d_ctab; Q.bmax = h->d_cbmax;
+            Q.W = W; Q.c1 = (W - 16) >> 4; Q.c2 = (W + 14) >> 4; Q.n_lanes = h->n_ind;
+            // c_het = log10(error) (lod() of a heterozygote, garlic-roh.cpp:368-372), rounded toward zero
+            const double fx = (double)(1 << kCoarseShift);
+            Q.chet_fixed = (int)std::ceil((std::log10(h->error) + 1e-9) * fx);
+            const double cl_ = (cutoff - P.tol) * fx - 2.0;
+            Q.cut_fixed = cl_ > 2.0e9 ? 2000000000 : (cl_ < -2.0e9 ? -2000000000 : (int)std::floor(cl_));
+            LAUNCH(launch_coarse(Q, h->d_items, (int)items.size(), h->d_cand_list, h->d_cand_cnt, h->n_ind, h->stream));
+            cl.list = h->d_cand_list; cl.cnt = h->d_cand_cnt; cl.stride = h->n_ind;
+        }
+        CK(cudaEventRecord(h->ev2, h->stream));
+        if (launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, true, false, tile_snps, cl)) return 1;
         CK(cudaEventRecord(h->ev1, h->stream));
         unsigned cnt[4];
         CK(cudaMemcpyAsync(cnt, h->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        CK(cudaEventElapsedTime(&ms_coarse, h->ev0, h->ev2));
+        pruned = prune;
         if (cnt[0] > h->out_cap) {
             h->out_cap = cnt[0] + cnt[0] / 4 + 1024;
             if (dev_alloc(h, &h->d_out, h->out_cap)) return 1;
@@ -832,13 +876,23 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     h->stats[1] = (double)units;
     h->stats[2] = (double)n_amb_pairs;
     h->stats[3] = ms;
+    h->stats[4] = ms_coarse;
+    h->stats[5] = -1;
+    h->stats[6] = (double)items.size() * h->n_ind;
+    if (pruned) {   // candidate (individual, item) pairs that went to the exact walker
+        std::vector<unsigned> cc(items.size());
+        CK(cudaMemcpy(cc.data(), h->d_cand_cnt, items.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        double tot = 0;
+        for (unsigned v : cc) tot += v;
+        h->stats[5] = tot;
+    }
     laps.lap("out");
     return 0;
 }
 
 int garlic_gpu_last_stats(garlic_gpu_t* h, double* s)
 {
-    for (int i = 0; i < 4; ++i) s[i] = h->stats[i];
+    for (int i = 0; i < 8; ++i) s[i] = h->stats[i];
     return 0;
 }
 

@@ -6,6 +6,10 @@
 #define GHD __host__ __device__ __forceinline__
 #else
 #define GHD inline
+struct uint2 { unsigned x, y; };   // host-side stand-ins for the CUDA vector types used by shared code
+struct int2 { int x, y; };
+struct uint4 { unsigned x, y, z, w; };
+struct int4 { int x, y, z, w; };
 #endif
 
 namespace garlic {

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include "common.cuh"
 #include "walk.cuh"
+#include "coarse.cuh"
 #include "kernels.h"
 
 namespace garlic {
@@ -48,7 +49,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 
 template <int SRC, bool ROH, bool DUMP, bool TILE>
 __global__ void __launch_bounds__(kWalkThreads, TILE ? 4 : 2)
-walk_kernel(const WalkParams P, const Item* __restrict__ items, int n_items, int n_groups, int tile_bytes)
+walk_kernel(const WalkParams P, const Item* __restrict__ items, int n_items, int n_groups, int tile_bytes,
+            const int* __restrict__ cand_list, const unsigned* __restrict__ cand_cnt, int cand_stride)
 {
     extern __shared__ __align__(128) unsigned char walk_smem[];
     // layout: [tile (tile_bytes, TILE only)] [ring: NW * blockDim words] [mbarrier]
@@ -68,6 +70,14 @@ walk_kernel(const WalkParams P, const Item* __restrict__ items, int n_items, int
     for (long long u = blockIdx.x; u < total; u += gridDim.x) {
         const int item = (int)(u / gblocks);
         const int group = (int)(u % gblocks) * gpb + warp;
+        // pruned pass: this item's individuals are the dense candidate list written by coarse_kernel
+        int n_lanes = P.n_lanes;
+        const int* list = nullptr;
+        if (cand_list) {
+            n_lanes = (int)cand_cnt[item];
+            list = cand_list + (int64_t)item * cand_stride;
+            if ((int)(u % gblocks) * gpb * 32 >= n_lanes) continue;      // whole CTA: nothing left in this item
+        }
         const Item it = items[item];
         const char* tile = reinterpret_cast<const char*>(P.lut);
         int tile_lo = 0;
@@ -84,18 +94,113 @@ walk_kernel(const WalkParams P, const Item* __restrict__ items, int n_items, int
             tile = reinterpret_cast<const char*>(tile_s);
             tile_lo = it.w0;
         }
-        if (group < n_groups) {
+        if (group * 32 < n_lanes) {
             const int k = group * 32 + lane;
-            const bool active = k < P.n_lanes;
-            walk_item<SRC, ROH, DUMP>(P, it, active ? k : P.n_lanes - 1, active, ring_smem + threadIdx.x,
-                                      blockDim.x, tile, tile_lo);
+            const bool active = k < n_lanes;
+            const int kk = active ? k : n_lanes - 1;
+            walk_item<SRC, ROH, DUMP>(P, it, kk, active, ring_smem + threadIdx.x, blockDim.x, tile, tile_lo,
+                                      list ? list[kk] : -1);
         }
         if (TILE) __syncthreads();   // every warp is done with the tile before the next copy lands
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Pruning pass (coarse.cuh): tables per window size, then one warp = 32 individuals scanning one item.
+// ------------------------------------------------------------------------------------------
+__global__ void coarse_tables_kernel(const double* __restrict__ lut, long long n_hw, int W, int c2,
+                                     uint2* __restrict__ tab, int* __restrict__ bmax_out)
+{
+    const double scale = (double)(1 << kCoarseShift);
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n_hw; k += (long long)gridDim.x * blockDim.x) {
+        const long long s0 = k * 16;
+        // base[s] = min(lut[s][0], lut[s][2]); sliding window sums B(t), t = s0 .. s0+15
+        double b = 0.0;
+        for (int i = 0; i < W; ++i) { const double* e = lut + (s0 + i) * 4; b += fmin(e[0], e[2]); }
+        double bmax = b;
+        for (int j = 1; j < 16; ++j) {
+            const double* eo = lut + (s0 + j - 1) * 4;
+            const double* ei = lut + (s0 + j - 1 + W) * 4;
+            b = b - fmin(eo[0], eo[2]) + fmin(ei[0], ei[2]);
+            bmax = fmax(bmax, b);
+        }
+        double dlo = 0.0, dhi = 0.0;
+        const long long s_end = s0 + 16 * (c2 + 1);
+        for (long long s = s0; s < s_end; ++s) {
+            const double* e = lut + s * 4;
+            const double d = fabs(e[0] - e[2]);
+            if (d > kCoarseSplit) dhi = fmax(dhi, d); else dlo = fmax(dlo, d);
+        }
+        uint32_t m = 0u;
+        for (int j = 0; j < 16; ++j) {
+            const double* e = lut + (s0 + j) * 4;
+            if (e[2] > e[0]) m |= 1u << (2 * j);
+            if (fabs(e[0] - e[2]) > kCoarseSplit) m |= 2u << (2 * j);
+        }
+        const double qlo = fmin(ceil(dlo * scale) + 1.0, 65535.0), qhi = fmin(ceil(dhi * scale) + 1.0, 65535.0);
+        uint2 o;
+        o.x = m;
+        o.y = (uint32_t)qlo | ((uint32_t)qhi << 16);
+        tab[k] = o;
+        bmax_out[k] = (int)ceil(bmax * scale) + 2;
+    }
+}
+
+__global__ void __launch_bounds__(kWalkThreads)
+coarse_kernel(const CoarseParams P, const Item* __restrict__ items, int n_items, int n_groups,
+              int* __restrict__ cand_list, unsigned* __restrict__ cand_cnt, int cand_stride)
+{
+    extern __shared__ __align__(16) unsigned char coarse_smem[];
+    uint32_t* ring = reinterpret_cast<uint32_t*>(coarse_smem) + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gpb = blockDim.x >> 5;
+    const int gblocks = (n_groups + gpb - 1) / gpb;
+    const long long total = (long long)n_items * gblocks;
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const int item = (int)(u / gblocks);
+        const int group = (int)(u % gblocks) * gpb + warp;
+        if (group >= n_groups) continue;
+        const int ind = group * 32 + lane;
+        const bool active = ind < P.n_lanes;
+        const Item it = items[item];
+        const bool cand = coarse_item(P, it, active ? ind : P.n_lanes - 1, ring, blockDim.x) && active;
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (m) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&cand_cnt[item], (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (cand) cand_list[(int64_t)item * cand_stride + base + __popc(m & ((1u << lane) - 1u))] = ind;
+        }
+    }
+}
+
+cudaError_t launch_coarse_tables(const double* lut, long long n_hw, int W, uint2* tab, int* bmax, cudaStream_t st)
+{
+    if (!n_hw) return cudaSuccess;
+    long long blocks = (n_hw + 127) / 128;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    coarse_tables_kernel<<<(unsigned)blocks, 128, 0, st>>>(lut, n_hw, W, (W + 14) >> 4, tab, bmax);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_coarse(const CoarseParams& P, const Item* items, int n_items, int* cand_list, unsigned* cand_cnt,
+                          int cand_stride, cudaStream_t st)
+{
+    if (!n_items || !P.n_lanes) return cudaSuccess;
+    const int n_groups = (P.n_lanes + 31) / 32;
+    const int gpb = kWalkThreads / 32;
+    const long long total = (long long)n_items * ((n_groups + gpb - 1) / gpb);
+    const size_t smem = (size_t)coarse_ring_len(P.c2) * kWalkThreads * sizeof(uint32_t);
+    long long grid = total;
+    const long long cap = 148ll * 8 * 16;
+    if (grid > cap) grid = cap;
+    coarse_kernel<<<(unsigned)grid, kWalkThreads, smem, st>>>(P, items, n_items, n_groups, cand_list, cand_cnt, cand_stride);
+    return cudaGetLastError();
+}
+
 template <int SRC, bool ROH, bool DUMP>
-static cudaError_t launch_walk_t(const WalkParams& P, const Item* items, int n_items, int tile_snps, cudaStream_t st)
+static cudaError_t launch_walk_t(const WalkParams& P, const Item* items, int n_items, int tile_snps, const CandList& cl,
+                                 cudaStream_t st)
 {
     if (n_items == 0 || P.n_lanes == 0) return cudaSuccess;
     const int threads = kWalkThreads;
@@ -118,24 +223,24 @@ static cudaError_t launch_walk_t(const WalkParams& P, const Item* items, int n_i
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        kern<<<(unsigned)grid, threads, smem, st>>>(P, items, n_items, n_groups, tile_bytes);
+        kern<<<(unsigned)grid, threads, smem, st>>>(P, items, n_items, n_groups, tile_bytes, cl.list, cl.cnt, cl.stride);
     } else {
-        walk_kernel<SRC, ROH, DUMP, false><<<(unsigned)grid, threads, smem, st>>>(P, items, n_items, n_groups, 0);
+        walk_kernel<SRC, ROH, DUMP, false><<<(unsigned)grid, threads, smem, st>>>(P, items, n_items, n_groups, 0, cl.list, cl.cnt, cl.stride);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_walk(const WalkParams& P, const Item* items, int n_items, bool gl_mode, bool roh,
-                        bool dump, int tile_snps, cudaStream_t st)
+                        bool dump, int tile_snps, const CandList& cl, cudaStream_t st)
 {
     if (gl_mode) {
-        if (roh && !dump) return launch_walk_t<1, true, false>(P, items, n_items, 0, st);
-        if (!roh && dump) return launch_walk_t<1, false, true>(P, items, n_items, 0, st);
-        return launch_walk_t<1, true, true>(P, items, n_items, 0, st);
+        if (roh && !dump) return launch_walk_t<1, true, false>(P, items, n_items, 0, cl, st);
+        if (!roh && dump) return launch_walk_t<1, false, true>(P, items, n_items, 0, cl, st);
+        return launch_walk_t<1, true, true>(P, items, n_items, 0, cl, st);
     }
-    if (roh && !dump) return launch_walk_t<0, true, false>(P, items, n_items, tile_snps, st);
-    if (!roh && dump) return launch_walk_t<0, false, true>(P, items, n_items, tile_snps, st);
-    return launch_walk_t<0, true, true>(P, items, n_items, tile_snps, st);
+    if (roh && !dump) return launch_walk_t<0, true, false>(P, items, n_items, tile_snps, cl, st);
+    if (!roh && dump) return launch_walk_t<0, false, true>(P, items, n_items, tile_snps, cl, st);
+    return launch_walk_t<0, true, true>(P, items, n_items, tile_snps, cl, st);
 }
 
 // ------------------------------------------------------------------------------------------

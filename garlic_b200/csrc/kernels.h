@@ -10,9 +10,20 @@ namespace garlic {
 constexpr int kWalkThreads = 256;     // 8 individual groups (warps) of one item per CTA
 constexpr int kTileSnpsMax = 1536;    // table tile staged per CTA: 1536 SNPs × 32 B = 48 KB
 
+// dense per-item individual lists produced by the pruning pass (list == nullptr: every individual)
+struct CandList {
+    const int* list = nullptr;       // [n_items][stride]
+    const unsigned* cnt = nullptr;   // [n_items]
+    int stride = 0;
+};
+
 // tile_snps > 0: every item touches at most tile_snps SNPs → stage its table slice in shared memory
 cudaError_t launch_walk(const WalkParams& P, const Item* items, int n_items, bool gl_mode, bool roh,
-                        bool dump, int tile_snps, cudaStream_t st);
+                        bool dump, int tile_snps, const CandList& cl, cudaStream_t st);
+struct CoarseParams;
+cudaError_t launch_coarse_tables(const double* lut, long long n_hw, int W, uint2* tab, int* bmax, cudaStream_t st);
+cudaError_t launch_coarse(const CoarseParams& P, const Item* items, int n_items, int* cand_list, unsigned* cand_cnt,
+                          int cand_stride, cudaStream_t st);
 cudaError_t launch_fill_f64(double* p, size_t n, double v, cudaStream_t st);
 cudaError_t launch_first_allele(const uint8_t* alleles, int n_snp, int n_ind, int ind_offset, int missing,
                                 unsigned long long* key, cudaStream_t st);

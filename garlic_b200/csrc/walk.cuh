@@ -247,10 +247,10 @@ GHD void walk_block(const WalkParams& P, const Item& it, const LaneCtx<SRC>& C, 
 // Walk one item for one individual.  ring: this lane's flag-history ring (NW words, stride rstride).
 template <int SRC, bool ROH, bool DUMP>
 GHD void walk_item(const WalkParams& P, const Item& it, int k_slot, bool active, uint32_t* ring, int rstride,
-                   const char* tile, int tile_lo)
+                   const char* tile, int tile_lo, int ind_in = -1)
 {
     const int W = P.W;
-    const int ind = P.ind_list ? P.ind_list[k_slot] : k_slot;
+    const int ind = ind_in >= 0 ? ind_in : (P.ind_list ? P.ind_list[k_slot] : k_slot);
     LaneCtx<SRC> C;
     C.row = P.geno + (int64_t)ind * P.row_words;
     C.tile = tile;

@@ -137,9 +137,11 @@ int garlic_gpu_windows_dev(garlic_gpu_t *h, int winsize, int step, int weighted,
  * cutoff (same ROH as exact), 1 = whole-segment chains everywhere. */
 int garlic_gpu_call_roh(garlic_gpu_t *h, int winsize, double cutoff, double overlap_frac, int weighted,
                         int exact, garlic_roh_t *out, int64_t cap, int64_t *count);
-/* statistics of the last call_roh: [0] items, [1] individual-windows evaluated (N·Σ_c(L_c-W+1)),
- * [2] ambiguous (individual, segment) pairs re-evaluated exactly, [3] kernel milliseconds */
-int garlic_gpu_last_stats(garlic_gpu_t *h, double *stats4);
+/* statistics of the last call_roh, 8 doubles: [0] items, [1] individual-windows decided (N·Σ_c(L_c-W+1)),
+ * [2] ambiguous (individual, segment) pairs re-evaluated exactly, [3] kernel milliseconds (pruning pass +
+ * walker), [4] of which pruning pass, [5] (individual, item) pairs that went to the walker (-1: no pruning),
+ * [6] all (individual, item) pairs, [7] reserved */
+int garlic_gpu_last_stats(garlic_gpu_t *h, double *stats8);
 
 /* packed 2-bit genotype rows back to the host (parity checks; --phased / debugging): filtered = 0 →
  * the matrix as ingested [n_ind][ceil(n_loci/4)], 1 → after compaction [n_ind][ceil(L/4)];

@@ -80,7 +80,7 @@ def flatten(res, error, use_gl=False):
     chroms = res["chroms"]
     codes = np.concatenate([ch["geno"] for ch in chroms], axis=0).T.copy().astype(np.uint8)   # [N, L]
     N, L = codes.shape
-    row_words = ((L + PAD + 31) >> 5) + 2
+    row_words = (((L + PAD + 31) >> 5) + 3) & ~1
     rows8 = synth.pack_codes(codes, row_bytes=row_words * 8)
     rows = rows8.view(np.uint64).reshape(N, row_words)
     chr_off = np.zeros(len(chroms) + 1, np.int64)

@@ -8,6 +8,8 @@
 #include "../garlic_b200/csrc/common.cuh"
 #include "../garlic_b200/csrc/walk.cuh"
 #include "../garlic_b200/csrc/segments.h"
+#include "../garlic_b200/csrc/coarse.cuh"
+#include <cmath>
 
 using namespace garlic;
 
@@ -78,6 +80,67 @@ int emu_windows(const uint64_t* geno, int64_t row_words, const double* lut, cons
             if (gl) walk_item<1, false, true>(P, it, k, true, ring.data(), 1, (const char*)lut, 0);
             else walk_item<0, false, true>(P, it, k, true, ring.data(), 1, (const char*)lut, 0);
         }
+    return (int)items.size();
+}
+
+
+// pruning pass (coarse.cuh) on the CPU: out[n_items][n_ind] = candidate flag; items as the chunked fast pass
+// builds them.  The table construction restates coarse_tables_kernel (kernels.cu).
+int emu_coarse(const uint64_t* geno, int64_t row_words, const double* lut, int n_ind, int n_chr, const int64_t* chr_off_,
+               const int32_t* pos_, const int32_t* cen_, int max_gap, int W, double cutoff, double tol, double error,
+               int chunk, uint8_t* out, int32_t* item_bounds /* [n_items][3] = w0, own_hi, we */, int cap_items)
+{
+    std::vector<int64_t> chr_off(chr_off_, chr_off_ + n_chr + 1);
+    const int64_t L = chr_off[n_chr];
+    std::vector<int32_t> pos(pos_, pos_ + L), cen(cen_, cen_ + 2 * n_chr);
+    std::vector<Segment> segs;
+    std::vector<Item> items;
+    build_segments(chr_off, pos, cen, max_gap, W, segs);
+    build_items(chr_off, W, segs, chunk, 0, items);
+    if ((int)items.size() > cap_items) return -1;
+    const int c1 = (W - 16) >> 4, c2 = (W + 14) >> 4;
+    const int64_t n_hw = (L + 4160 - 512) >> 4;
+    const double scale = (double)(1 << kCoarseShift);
+    std::vector<uint2> tab(n_hw);
+    std::vector<int> bmaxv(n_hw);
+    for (int64_t k = 0; k < n_hw; ++k) {
+        const int64_t s0 = k * 16;
+        double b = 0.0;
+        for (int i = 0; i < W; ++i) { const double* e = lut + (s0 + i) * 4; b += std::fmin(e[0], e[2]); }
+        double bmax = b;
+        for (int j = 1; j < 16; ++j) {
+            const double* eo = lut + (s0 + j - 1) * 4;
+            const double* ei = lut + (s0 + j - 1 + W) * 4;
+            b = b - std::fmin(eo[0], eo[2]) + std::fmin(ei[0], ei[2]);
+            bmax = std::fmax(bmax, b);
+        }
+        double dlo = 0.0, dhi = 0.0;
+        for (int64_t s = s0; s < s0 + 16 * (c2 + 1); ++s) {
+            const double* e = lut + s * 4;
+            const double d = std::fabs(e[0] - e[2]);
+            if (d > kCoarseSplit) dhi = std::fmax(dhi, d); else dlo = std::fmax(dlo, d);
+        }
+        uint32_t m = 0;
+        for (int j = 0; j < 16; ++j) {
+            const double* e = lut + (s0 + j) * 4;
+            if (e[2] > e[0]) m |= 1u << (2 * j);
+            if (std::fabs(e[0] - e[2]) > kCoarseSplit) m |= 2u << (2 * j);
+        }
+        const double qlo = std::fmin(std::ceil(dlo * scale) + 1.0, 65535.0), qhi = std::fmin(std::ceil(dhi * scale) + 1.0, 65535.0);
+        tab[k].x = m;
+        tab[k].y = (uint32_t)qlo | ((uint32_t)qhi << 16);
+        bmaxv[k] = (int)std::ceil(bmax * scale) + 2;
+    }
+    CoarseParams P;
+    P.geno = geno; P.row_words = row_words; P.tab = tab.data(); P.bmax = bmaxv.data();
+    P.W = W; P.c1 = c1; P.c2 = c2; P.n_lanes = n_ind;
+    P.chet_fixed = (int)std::ceil((std::log10(error) + 1e-9) * scale);
+    P.cut_fixed = (int)std::floor((cutoff - tol) * scale - 2.0);
+    std::vector<uint32_t> ring(coarse_ring_len(c2));
+    for (size_t i = 0; i < items.size(); ++i) {
+        item_bounds[3 * i] = items[i].w0; item_bounds[3 * i + 1] = items[i].own_hi; item_bounds[3 * i + 2] = items[i].we;
+        for (int k = 0; k < n_ind; ++k) out[i * n_ind + k] = coarse_item(P, items[i], k, ring.data(), 1) ? 1 : 0;
+    }
     return (int)items.size();
 }
 

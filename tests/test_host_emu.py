@@ -142,3 +142,36 @@ def test_ambiguity_detection_and_cutoff_on_window_value():
     assert n_amb >= 1
     got_exact, n_amb2, _ = emu_roh(F, W, cutoff, thr_of(0.25, W), 0, 0.0)
     assert got_exact == oracle_roh_idx(res)
+
+
+@pytest.mark.parametrize("name,chunk", [("lod_2", 256), ("lod_small", 128), ("auto_overlap_hg19", 320), ("lod_2", 1376)])
+def test_pruning_bound_never_drops_a_flagged_window(name, chunk):
+    """coarse.cuh: every (individual, item) pair that holds a window >= cutoff - tol must survive the pruning
+    pass; and the pass must actually prune something on data with planted ROH."""
+    ds, args = load_case(name)
+    W = arg(args, "--winsize", cast=int)
+    err = arg(args, "--error", cast=float)
+    assert W >= 32
+    res = orc.run_pipeline(ds, W, err, None, cm="--cm" in args)
+    F = flatten(res, err)
+    win = oracle_windows_matrix(res)
+    vals = np.sort(win[win != orc.MISSING])
+    for cutoff in (float(vals[int(0.9 * len(vals))]), float(vals[int(0.5 * len(vals))]), 2.0, float(vals[-1])):
+        cap = 4096
+        out = np.zeros((cap, F["N"]), np.uint8)
+        bounds = np.zeros((cap, 3), np.int32)
+        n = emu().emu_coarse(_p(F["rows"]), C.c_int64(F["row_words"]), _p(F["lut"]), C.c_int(F["N"]),
+                             C.c_int(len(F["chr_off"]) - 1), _p(F["chr_off"]), _p(F["pos"]), _p(F["cen"]), C.c_int(200000),
+                             C.c_int(W), C.c_double(cutoff), C.c_double(1e-9), C.c_double(err), C.c_int(chunk), _p(out),
+                             _p(bounds), C.c_int(cap))
+        assert n > 0
+        dropped_flagged = 0
+        for i in range(n):
+            w0, own_hi, we = bounds[i]
+            hi = min(own_hi, we)
+            has = (win[:, w0:hi] >= cutoff - 1e-9) & (win[:, w0:hi] != orc.MISSING)
+            has = has.any(axis=1)
+            dropped_flagged += int((has & (out[i] == 0)).sum())
+        assert dropped_flagged == 0
+        if cutoff == float(vals[-1]):
+            assert out[:n].mean() < 0.9      # something is pruned when almost nothing passes the cutoff
