@@ -69,8 +69,8 @@ struct garlic_gpu {
     uint32_t* d_keepw = nullptr;
     int* d_scan = nullptr;         // block counts of the keep scan, total, kept chromosome offsets
     int* d_breaks = nullptr;       // bad-pair list
-    uint2* d_ctab = nullptr;       // pruning tables (coarse.cuh), valid for coarse_W
-    int* d_cbmax = nullptr;
+    uint32_t* d_cmask = nullptr;   // pruning tables (coarse.cuh), valid for coarse_W
+    int2* d_ccb = nullptr;         // 16 zero entries in front: blocks k >= -16 are addressable
     int coarse_W = 0;
     int* d_cand_list = nullptr;
     unsigned* d_cand_cnt = nullptr;
@@ -193,7 +193,7 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
-    dev_free(h->d_ctab); dev_free(h->d_cbmax); dev_free(h->d_cand_list); dev_free(h->d_cand_cnt);
+    dev_free(h->d_cmask); dev_free(h->d_ccb); dev_free(h->d_cand_list); dev_free(h->d_cand_cnt);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -769,16 +769,17 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         if (prune) {
             const int64_t n_hw = (h->L + kPad - 512) >> 4;
             if (h->coarse_W != W) {
-                if (dev_alloc(h, &h->d_ctab, (size_t)n_hw)) return 1;
-                if (dev_alloc(h, &h->d_cbmax, (size_t)n_hw)) return 1;
-                LAUNCH(launch_coarse_tables(h->d_lut, n_hw, W, h->d_ctab, h->d_cbmax, h->stream));
+                if (dev_alloc(h, &h->d_cmask, (size_t)n_hw)) return 1;
+                if (dev_alloc(h, &h->d_ccb, (size_t)n_hw + 16)) return 1;
+                CK(cudaMemsetAsync(h->d_ccb, 0, 16 * sizeof(int2), h->stream));
+                LAUNCH(launch_coarse_tables(h->d_lut, n_hw, W, h->d_cmask, h->d_ccb + 16, h->stream));
                 h->coarse_W = W;
             }
             if (dev_alloc(h, &h->d_cand_list, (size_t)items.size() * h->n_ind)) return 1;
             if (dev_alloc(h, &h->d_cand_cnt, items.size() + 1)) return 1;
             CK(cudaMemsetAsync(h->d_cand_cnt, 0, (items.size() + 1) * sizeof(unsigned), h->stream));
             CoarseParams Q;
-            Q.geno = h->d_geno; Q.row_words = h->row_words; Q.tab = h->d_ctab; Q.bmax = h->d_cbmax;
+            Q.geno = h->d_geno; Q.row_words = h->row_words; Q.mask = h->d_cmask; Q.cb = h->d_ccb + 16;
             Q.W = W; Q.c1 = (W - 16) >> 4; Q.c2 = (W + 14) >> 4; Q.n_lanes = h->n_ind;
             // c_het = log10(error) (lod() of a heterozygote, garlic-roh.cpp:368-372), rounded toward zero
             const double fx = (double)(1 << kCoarseShift);

@@ -35,65 +35,83 @@ constexpr double kCoarseSplit = 0.3;    // D above this is the "high" class of r
 struct CoarseParams {
     const uint64_t* geno;
     int64_t row_words;       // even, so that a row is a whole number of 16-byte quads
-    const uint2* tab;        // per half-word index j:
-                             //   x = rare-allele mask of half-word j: bit 2i set <=> at SNP 16j+i the genotype-2
-                             //       homozygote is the "rare" one; bit 2i+1 set <=> D[16j+i] > kCoarseSplit (high class)
-                             //   y = bound coefficients of block j: Dlo | Dhi << 16 (unsigned 16-bit, fixed point)
-    const int* bmax;         // per block k: Bmax in fixed point
+    const uint32_t* mask;    // per half-word q: bit 2i set <=> at SNP 16q+i the genotype-2 homozygote is the "rare"
+                             // one; bit 2i+1 set <=> D[16q+i] > kCoarseSplit (high class)
+    const int2* cb;          // per block k (valid for k >= -16): x = Bmax, y = Dlo | Dhi << 16 (fixed point)
     int chet_fixed;          // c_het in fixed point (negative), rounded toward zero
     int cut_fixed;           // (cutoff - tol) in fixed point, rounded down, minus slack
     int W, c1, c2;
     int n_lanes;
 };
 
-GHD int coarse_ring_len(int c2) { return c2 + 3; }
+constexpr int kCoarseC2Min = (kCoarseMinW + 14) >> 4, kCoarseC2Max = (kCoarseMaxW + 14) >> 4;   // 2 .. 13
 
 // Does individual `ind` have any block of item `it` whose bound reaches the cutoff?
-// ring: per-lane ring (stride rstride) of the last c2+2 half-words' packed counts
-//       p[q] = nhet | nrare_lo << 8 | nrare_hi << 16   (each <= 16).
-// Sliding sums over the span (half-words k..k+c2) and the core (k+1..k+c1) are kept in the same packed form
-// (every field stays < 256 for W <= kCoarseMaxW).  Rows are read one 16-byte quad (64 SNPs) at a time.
-GHD bool coarse_item(const CoarseParams& P, const Item& it, int ind, uint32_t* ring, int rstride)
+// The packed counts p[q] = nhet | nrare_lo << 8 | nrare_hi << 16 of the last 16 half-words live in registers
+// (the scan is unrolled over 16 half-words = 4 sixteen-byte quads, so every ring slot is a compile-time
+// register); sliding sums over the span (half-words k..k+C2) and the core (k+1..k+c1) are kept in the same
+// packed form (every field stays < 256 for W <= kCoarseMaxW).
+template <int C2>
+GHD bool coarse_item(const CoarseParams& P, const Item& it, int ind)
 {
     const uint4* row = reinterpret_cast<const uint4*>(P.geno + (int64_t)ind * P.row_words);
     const int k_lo = it.w0 >> 4, k_hi = (it.own_hi - 1) >> 4;      // blocks holding the item's windows
-    const int RL = coarse_ring_len(P.c2);
-    for (int i = 0; i < RL; ++i) ring[i * rstride] = 0u;
+    const int q_end = k_hi + C2;
+    const bool c1_near = (P.c1 == C2 - 1);                          // c1 is C2-1 or C2-2
+    const uint32_t k_span = (uint32_t)(k_hi - k_lo);
+    uint32_t r[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = 0u;
     uint32_t s_span = 0, s_core = 0;
     bool cand = false;
-    int wslot = 0;                                                  // slot of p[q]
-    const int q_end = k_hi + P.c2;
-    for (int q4 = k_lo >> 2; q4 * 4 <= q_end; ++q4) {
-        const uint4 quad = row[q4];
-        const uint32_t hw[4] = {quad.x, quad.y, quad.z, quad.w};
+    for (int qb = k_lo & ~15; qb <= q_end; qb += 16) {
+        const uint32_t* mq = P.mask + qb;
+        const int2* cbq = P.cb + (qb - C2);
+        const uint4* rq = row + (qb >> 2);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int q = q4 * 4 + j;
-            const uint32_t h = hw[j];
-            const uint2 tq = P.tab[q];
-            const uint32_t lo = h & 0x55555555u, hi = (h >> 1) & 0x55555555u;
-            const uint32_t het = lo & ~hi, hom2 = hi & ~lo, hom0 = ~(lo | hi) & 0x55555555u;
-            const uint32_t rare = (hom2 & tq.x) | (hom0 & ~tq.x);
-            const uint32_t high = (tq.x >> 1) & 0x55555555u;
-            const uint32_t p = (uint32_t)popc32(het) | ((uint32_t)popc32(rare & ~high) << 8) | ((uint32_t)popc32(rare & high) << 16);
-            ring[wslot * rstride] = p;
-            // block k = q - c2: span = half-words k..q, core = k+1..k+c1
-            int sl = wslot - (P.c2 + 1); if (sl < 0) sl += RL;      // p[k-1] leaves the span
-            int sk = sl + 1; if (sk >= RL) sk -= RL;                // p[k] leaves the core ...
-            int se = sk + P.c1; if (se >= RL) se -= RL;             // ... and p[k+c1] enters it
-            s_span += p - ring[sl * rstride];
-            s_core += ring[se * rstride] - ring[sk * rstride];
-            const int k = q - P.c2;
-            if (k >= k_lo && k <= k_hi) {
-                const uint32_t co = P.tab[k].y;
-                const int ub = P.bmax[k] + P.chet_fixed * (int)(s_core & 0xffu) + (int)(co & 0xffffu) * (int)((s_span >> 8) & 0xffu) +
-                               (int)(co >> 16) * (int)((s_span >> 16) & 0xffu);
-                cand |= (ub >= P.cut_fixed);
+        for (int i4 = 0; i4 < 4; ++i4) {
+            const uint4 quad = rq[i4];
+            const uint32_t hw[4] = {quad.x, quad.y, quad.z, quad.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i4 * 4 + j;                           // = q & 15, static after unrolling
+                const uint32_t h = hw[j], m = mq[i];
+                const uint32_t lo = h & 0x55555555u, hi = (h >> 1) & 0x55555555u;
+                const uint32_t het = lo & ~hi, hom2 = hi & ~lo, hom0 = ~(lo | hi) & 0x55555555u;
+                const uint32_t rare = (hom2 & m) | (hom0 & ~m);
+                const uint32_t high = (m >> 1) & 0x55555555u;
+                const uint32_t p = (uint32_t)popc32(het) | ((uint32_t)popc32(rare & ~high) << 8) | ((uint32_t)popc32(rare & high) << 16);
+                r[i] = p;
+                // block k = q - C2: span = half-words k..q, core = k+1..k+c1
+                s_span += p - r[(i - C2 - 1) & 15];                 // p[k-1] leaves the span
+                s_core += (c1_near ? r[(i - 1) & 15] : r[(i - 2) & 15]) - r[(i - C2) & 15];   // p[k+c1] enters, p[k] leaves
+                const int2 c = cbq[i];
+                const int ub = c.x + P.chet_fixed * (int)(s_core & 0xffu) + (int)((uint32_t)c.y & 0xffffu) * (int)((s_span >> 8) & 0xffu) +
+                               (int)((uint32_t)c.y >> 16) * (int)((s_span >> 16) & 0xffu);
+                cand |= (ub >= P.cut_fixed) && ((uint32_t)(qb + i - C2 - k_lo) <= k_span);
             }
-            if (++wslot >= RL) wslot = 0;
         }
     }
     return cand;
+}
+
+// run-time window size → compile-time C2
+GHD bool coarse_item_any(const CoarseParams& P, const Item& it, int ind)
+{
+    switch (P.c2) {
+        case 2: return coarse_item<2>(P, it, ind);
+        case 3: return coarse_item<3>(P, it, ind);
+        case 4: return coarse_item<4>(P, it, ind);
+        case 5: return coarse_item<5>(P, it, ind);
+        case 6: return coarse_item<6>(P, it, ind);
+        case 7: return coarse_item<7>(P, it, ind);
+        case 8: return coarse_item<8>(P, it, ind);
+        case 9: return coarse_item<9>(P, it, ind);
+        case 10: return coarse_item<10>(P, it, ind);
+        case 11: return coarse_item<11>(P, it, ind);
+        case 12: return coarse_item<12>(P, it, ind);
+        default: return coarse_item<13>(P, it, ind);
+    }
 }
 
 }  // namespace garlic

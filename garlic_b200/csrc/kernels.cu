@@ -109,7 +109,7 @@ walk_kernel(const WalkParams P, const Item* __restrict__ items, int n_items, int
 // Pruning pass (coarse.cuh): tables per window size, then one warp = 32 individuals scanning one item.
 // ------------------------------------------------------------------------------------------
 __global__ void coarse_tables_kernel(const double* __restrict__ lut, long long n_hw, int W, int c2,
-                                     uint2* __restrict__ tab, int* __restrict__ bmax_out)
+                                     uint32_t* __restrict__ mask, int2* __restrict__ cb)
 {
     const double scale = (double)(1 << kCoarseShift);
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n_hw; k += (long long)gridDim.x * blockDim.x) {
@@ -138,20 +138,19 @@ __global__ void coarse_tables_kernel(const double* __restrict__ lut, long long n
             if (fabs(e[0] - e[2]) > kCoarseSplit) m |= 2u << (2 * j);
         }
         const double qlo = fmin(ceil(dlo * scale) + 1.0, 65535.0), qhi = fmin(ceil(dhi * scale) + 1.0, 65535.0);
-        uint2 o;
-        o.x = m;
-        o.y = (uint32_t)qlo | ((uint32_t)qhi << 16);
-        tab[k] = o;
-        bmax_out[k] = (int)ceil(bmax * scale) + 2;
+        mask[k] = m;
+        int2 o;
+        o.x = (int)ceil(bmax * scale) + 2;
+        o.y = (int)((uint32_t)qlo | ((uint32_t)qhi << 16));
+        cb[k] = o;
     }
 }
 
+template <int C2>
 __global__ void __launch_bounds__(kWalkThreads)
 coarse_kernel(const CoarseParams P, const Item* __restrict__ items, int n_items, int n_groups,
               int* __restrict__ cand_list, unsigned* __restrict__ cand_cnt, int cand_stride)
 {
-    extern __shared__ __align__(16) unsigned char coarse_smem[];
-    uint32_t* ring = reinterpret_cast<uint32_t*>(coarse_smem) + threadIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gpb = blockDim.x >> 5;
     const int gblocks = (n_groups + gpb - 1) / gpb;
@@ -163,7 +162,7 @@ coarse_kernel(const CoarseParams P, const Item* __restrict__ items, int n_items,
         const int ind = group * 32 + lane;
         const bool active = ind < P.n_lanes;
         const Item it = items[item];
-        const bool cand = coarse_item(P, it, active ? ind : P.n_lanes - 1, ring, blockDim.x) && active;
+        const bool cand = coarse_item<C2>(P, it, active ? ind : P.n_lanes - 1) && active;
         const unsigned m = __ballot_sync(0xffffffffu, cand);
         if (m) {
             unsigned base = 0;
@@ -174,13 +173,20 @@ coarse_kernel(const CoarseParams P, const Item* __restrict__ items, int n_items,
     }
 }
 
-cudaError_t launch_coarse_tables(const double* lut, long long n_hw, int W, uint2* tab, int* bmax, cudaStream_t st)
+cudaError_t launch_coarse_tables(const double* lut, long long n_hw, int W, uint32_t* mask, int2* cb, cudaStream_t st)
 {
     if (!n_hw) return cudaSuccess;
     long long blocks = (n_hw + 127) / 128;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    coarse_tables_kernel<<<(unsigned)blocks, 128, 0, st>>>(lut, n_hw, W, (W + 14) >> 4, tab, bmax);
+    coarse_tables_kernel<<<(unsigned)blocks, 128, 0, st>>>(lut, n_hw, W, (W + 14) >> 4, mask, cb);
     return cudaGetLastError();
+}
+
+template <int C2>
+static void launch_coarse_t(const CoarseParams& P, const Item* items, int n_items, int n_groups, unsigned grid,
+                            int* cand_list, unsigned* cand_cnt, int cand_stride, cudaStream_t st)
+{
+    coarse_kernel<C2><<<grid, kWalkThreads, 0, st>>>(P, items, n_items, n_groups, cand_list, cand_cnt, cand_stride);
 }
 
 cudaError_t launch_coarse(const CoarseParams& P, const Item* items, int n_items, int* cand_list, unsigned* cand_cnt,
@@ -190,11 +196,25 @@ cudaError_t launch_coarse(const CoarseParams& P, const Item* items, int n_items,
     const int n_groups = (P.n_lanes + 31) / 32;
     const int gpb = kWalkThreads / 32;
     const long long total = (long long)n_items * ((n_groups + gpb - 1) / gpb);
-    const size_t smem = (size_t)coarse_ring_len(P.c2) * kWalkThreads * sizeof(uint32_t);
     long long grid = total;
     const long long cap = 148ll * 8 * 16;
     if (grid > cap) grid = cap;
-    coarse_kernel<<<(unsigned)grid, kWalkThreads, smem, st>>>(P, items, n_items, n_groups, cand_list, cand_cnt, cand_stride);
+    const unsigned g = (unsigned)grid;
+    switch (P.c2) {
+        case 2: launch_coarse_t<2>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
+        case 3: launch_coarse_t<3>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
+        case 4: launch_coarse_t<4>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
+        case 5: launch_coarse_t<5>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
+        case 6: launch_coarse_t<6>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
+        case 7: launch_coarse_t<7>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
+        case 8: launch_coarse_t<8>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
+        case 9: launch_coarse_t<9>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
+        case 10: launch_coarse_t<10>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
+        case 11: launch_coarse_t<11>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
+        case 12: launch_coarse_t<12>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
+        case 13: launch_coarse_t<13>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

@@ -21,7 +21,7 @@ struct CandList {
 cudaError_t launch_walk(const WalkParams& P, const Item* items, int n_items, bool gl_mode, bool roh,
                         bool dump, int tile_snps, const CandList& cl, cudaStream_t st);
 struct CoarseParams;
-cudaError_t launch_coarse_tables(const double* lut, long long n_hw, int W, uint2* tab, int* bmax, cudaStream_t st);
+cudaError_t launch_coarse_tables(const double* lut, long long n_hw, int W, uint32_t* mask, int2* cb, cudaStream_t st);
 cudaError_t launch_coarse(const CoarseParams& P, const Item* items, int n_items, int* cand_list, unsigned* cand_cnt,
                           int cand_stride, cudaStream_t st);
 cudaError_t launch_fill_f64(double* p, size_t n, double v, cudaStream_t st);

@@ -101,8 +101,9 @@ int emu_coarse(const uint64_t* geno, int64_t row_words, const double* lut, int n
     const int c1 = (W - 16) >> 4, c2 = (W + 14) >> 4;
     const int64_t n_hw = (L + 4160 - 512) >> 4;
     const double scale = (double)(1 << kCoarseShift);
-    std::vector<uint2> tab(n_hw);
-    std::vector<int> bmaxv(n_hw);
+    std::vector<uint32_t> mask(n_hw);
+    std::vector<int2> cbv(n_hw + 16);
+    for (int i = 0; i < 16; ++i) { cbv[i].x = 0; cbv[i].y = 0; }
     for (int64_t k = 0; k < n_hw; ++k) {
         const int64_t s0 = k * 16;
         double b = 0.0;
@@ -127,19 +128,18 @@ int emu_coarse(const uint64_t* geno, int64_t row_words, const double* lut, int n
             if (std::fabs(e[0] - e[2]) > kCoarseSplit) m |= 2u << (2 * j);
         }
         const double qlo = std::fmin(std::ceil(dlo * scale) + 1.0, 65535.0), qhi = std::fmin(std::ceil(dhi * scale) + 1.0, 65535.0);
-        tab[k].x = m;
-        tab[k].y = (uint32_t)qlo | ((uint32_t)qhi << 16);
-        bmaxv[k] = (int)std::ceil(bmax * scale) + 2;
+        mask[k] = m;
+        cbv[16 + k].x = (int)std::ceil(bmax * scale) + 2;
+        cbv[16 + k].y = (int)((uint32_t)qlo | ((uint32_t)qhi << 16));
     }
     CoarseParams P;
-    P.geno = geno; P.row_words = row_words; P.tab = tab.data(); P.bmax = bmaxv.data();
+    P.geno = geno; P.row_words = row_words; P.mask = mask.data(); P.cb = cbv.data() + 16;
     P.W = W; P.c1 = c1; P.c2 = c2; P.n_lanes = n_ind;
     P.chet_fixed = (int)std::ceil((std::log10(error) + 1e-9) * scale);
     P.cut_fixed = (int)std::floor((cutoff - tol) * scale - 2.0);
-    std::vector<uint32_t> ring(coarse_ring_len(c2));
     for (size_t i = 0; i < items.size(); ++i) {
         item_bounds[3 * i] = items[i].w0; item_bounds[3 * i + 1] = items[i].own_hi; item_bounds[3 * i + 2] = items[i].we;
-        for (int k = 0; k < n_ind; ++k) out[i * n_ind + k] = coarse_item(P, items[i], k, ring.data(), 1) ? 1 : 0;
+        for (int k = 0; k < n_ind; ++k) out[i * n_ind + k] = coarse_item_any(P, items[i], k) ? 1 : 0;
     }
     return (int)items.size();
 }
