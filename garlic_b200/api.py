@@ -19,7 +19,7 @@ GL_TYPES = {"GQ": 0, "GL": 1, "PL": 2, "ERROR": -1}
 
 EXPORTS = [
     "garlic_gpu_create", "garlic_gpu_destroy", "garlic_gpu_last_error", "garlic_gpu_launch_count",
-    "garlic_gpu_stream", "garlic_gpu_sync", "garlic_gpu_set_shape", "garlic_gpu_put_alleles",
+    "garlic_gpu_stream", "garlic_gpu_sync", "garlic_gpu_host_alloc", "garlic_gpu_host_free", "garlic_gpu_set_shape", "garlic_gpu_put_alleles",
     "garlic_gpu_first_allele_keys_dev", "garlic_gpu_code_alleles", "garlic_gpu_put_packed",
     "garlic_gpu_put_packed_dev", "garlic_gpu_count_packed", "garlic_gpu_counts_dev", "garlic_gpu_get_counts",
     "garlic_gpu_get_one_allele", "garlic_gpu_put_gl", "garlic_gpu_put_gl_dev", "garlic_gpu_filter",
@@ -49,6 +49,9 @@ def load_library():
     L.garlic_gpu_last_error.restype = C.c_char_p
     L.garlic_gpu_launch_count.restype = C.c_uint64
     L.garlic_gpu_stream.restype = C.c_void_p
+    L.garlic_gpu_host_alloc.restype = C.c_void_p
+    L.garlic_gpu_host_alloc.argtypes = [C.c_size_t]
+    L.garlic_gpu_host_free.argtypes = [C.c_void_p]
     L.garlic_gpu_first_allele_keys_dev.restype = C.c_void_p
     L.garlic_gpu_counts_dev.restype = C.c_void_p
     L.garlic_gpu_window_slots.restype = C.c_int64
@@ -77,7 +80,22 @@ class GarlicGPU:
         if rc != 0 or not self.h:
             raise GarlicError("garlic_gpu_create failed (rc=%d): no usable CUDA device; there is no CPU fallback" % rc)
 
+    def host_array(self, n, dtype):
+        """numpy array in page-locked host memory (garlic_gpu_host_alloc); freed with the handle."""
+        dt = np.dtype(dtype)
+        ptr = self.lib.garlic_gpu_host_alloc(C.c_size_t(max(1, n) * dt.itemsize))
+        if not ptr:
+            return np.empty(n, dt)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(ptr)
+        buf = (C.c_char * (max(1, n) * dt.itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dt, count=n)
+
     def close(self):
+        for ptr in getattr(self, "_pinned", []):
+            self.lib.garlic_gpu_host_free(C.c_void_p(ptr))
+        self._pinned = []
+        self._freq_buf = self._keep_buf = None
         if self.h:
             self.lib.garlic_gpu_destroy(self.h)
             self.h = C.c_void_p()
@@ -146,8 +164,8 @@ class GarlicGPU:
         """→ (freq float64[L0], keep bool[L0], L).  The two arrays are views of buffers owned by this object and
         are overwritten by the next filter() call (repeated runs then touch no fresh pages)."""
         if getattr(self, "_freq_buf", None) is None or len(self._freq_buf) != self.L0:
-            self._freq_buf = np.empty(self.L0, np.float64)
-            self._keep_buf = np.empty(self.L0, np.uint8)
+            self._freq_buf = self.host_array(self.L0, np.float64)      # page-locked: no staging copy
+            self._keep_buf = self.host_array(self.L0, np.uint8)
         freq = self._freq_buf if want_freq else None
         keep = self._keep_buf if want_keep else None
         n = C.c_int64(0)

@@ -66,9 +66,11 @@ struct garlic_gpu {
     int* d_indlist = nullptr;
     size_t indlist_cap = 0;
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t stats_items = 0;
     uint32_t* d_keepw = nullptr;
     int* d_scan = nullptr;         // block counts of the keep scan, total, kept chromosome offsets
     int* d_breaks = nullptr;       // bad-pair list
+    int* d_thin = nullptr;         // segment + chromosome tables of the thinned pass 1
     uint32_t* d_cmask = nullptr;   // pruning tables (coarse.cuh), valid for coarse_W
     int2* d_ccb = nullptr;         // 16 zero entries in front: blocks k >= -16 are addressable
     int coarse_W = 0;
@@ -140,6 +142,13 @@ static int pin_alloc(garlic_gpu* h, size_t bytes)
     return 0;
 }
 
+static bool is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 // host copy of the gather list (kept SNP → pre-filter index), fetched from the device on first use
 static int fetch_src(garlic_gpu* h)
 {
@@ -188,7 +197,7 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     dev_free(h->d_homf); dev_free(h->d_keep); dev_free(h->d_src); dev_free(h->d_pos0); dev_free(h->d_chr_of0);
     dev_free(h->d_pos); dev_free(h->d_chr_of); dev_free(h->d_chr_start); dev_free(h->d_chr_param);
     dev_free(h->d_out); dev_free(h->d_amb); dev_free(h->d_cnt); dev_free(h->d_items); dev_free(h->d_indlist); dev_free(h->d_dump);
-    dev_free(h->d_keepw); dev_free(h->d_first_word); dev_free(h->d_first_skip); dev_free(h->d_scan); dev_free(h->d_breaks);
+    dev_free(h->d_keepw); dev_free(h->d_first_word); dev_free(h->d_first_skip); dev_free(h->d_scan); dev_free(h->d_breaks); dev_free(h->d_thin);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -201,6 +210,14 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
 const char* garlic_gpu_last_error(const garlic_gpu_t* h) { return h ? h->err.c_str() : "null handle"; }
 uint64_t garlic_gpu_launch_count(const garlic_gpu_t* h) { return h ? h->launches : 0; }
 void* garlic_gpu_stream(const garlic_gpu_t* h) { return h ? (void*)h->stream : nullptr; }
+void* garlic_gpu_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void garlic_gpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int garlic_gpu_sync(garlic_gpu_t* h)
 {
     CK(cudaSetDevice(h->device));
@@ -370,6 +387,7 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     if (oob && !chr_param) FAIL("filter: oob filtering needs chr_param");
     const int64_t L0 = h->L0;
     Laps laps("filter");
+    bool freq_direct = false, keep_direct = false;
     if (dev_alloc(h, &h->d_freq0, (size_t)L0)) return 1;
     if (dev_alloc(h, &h->d_keep, (size_t)L0)) return 1;
     if (oob) {
@@ -401,8 +419,11 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
         CK(cudaMemcpyAsync(h->d_keep, keep, L0, cudaMemcpyHostToDevice, h->stream));
     } else {
         LAUNCH(launch_freq_keep(h->d_counts, L0, h->d_pos0, h->d_chr_of0, h->d_chr_param, oob, h->d_freq0, h->d_keep, h->stream));
-        if (freq_out) CK(cudaMemcpyAsync(freq0, h->d_freq0, L0 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        if (keep_out) CK(cudaMemcpyAsync(keep, h->d_keep, L0, cudaMemcpyDeviceToHost, h->stream));
+        // page-locked caller buffers (garlic_gpu_host_alloc) are written by the copy engine directly
+        freq_direct = freq_out && is_pinned(freq_out);
+        keep_direct = keep_out && is_pinned(keep_out);
+        if (freq_out) CK(cudaMemcpyAsync(freq_direct ? freq_out : freq0, h->d_freq0, L0 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (keep_out) CK(cudaMemcpyAsync(keep_direct ? keep_out : keep, h->d_keep, L0, cudaMemcpyDeviceToHost, h->stream));
     }
     // exclusive scan of the keep mask on the device: gather list, keep bits per input word, per output word
     // the input word it starts in, kept offset of every chromosome
@@ -419,8 +440,8 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     CK(cudaMemcpyAsync(meta, d_total, (size_t)(h->n_chr + 2) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     laps.lap("freq_keep+scan+d2h");
-    if (freq_out) memcpy(freq_out, freq0, L0 * sizeof(double));
-    if (keep_out) memcpy(keep_out, keep, L0);
+    if (freq_out && !freq_direct) memcpy(freq_out, freq0, L0 * sizeof(double));
+    if (keep_out && !keep_direct) memcpy(keep_out, keep, L0);
     laps.lap("copy_out");
     const int64_t L = meta[0];
     h->chr_off.assign(h->n_chr + 1, 0);
@@ -675,22 +696,43 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
     std::vector<Segment> segs;
     std::vector<Item> items;
     segments_from_stretches(h->stretches, W, segs);
+    const int64_t slots = garlic_gpu_window_slots(h, step);
+    if (dev_alloc(h, &h->d_dump, (size_t)n_lanes * slots)) return 1;
+    double* d_dump = h->d_dump;
+    LAUNCH(launch_fill_f64(d_dump, (size_t)n_lanes * slots, kMissing, h->stream));
+    // thinned pass 1 (unweighted, table mode, tolerance 1e-9): sum only the windows the KDE will look at
+    const bool direct = !weighted && !h->have_gl && !exact && step >= 8;
+    int rc = 0;
+    if (direct) {
+        static_assert(sizeof(Segment) == sizeof(int3), "Segment is uploaded as int3");
+        std::vector<int2> meta(h->n_chr);
+        int base = 0;
+        for (int c = 0; c < h->n_chr; ++c) {
+            meta[c].x = (int)h->chr_off[c]; meta[c].y = base;
+            base += (int)((h->chr_off[c + 1] - h->chr_off[c] + step - 1) / step);
+        }
+        const size_t bytes = segs.size() * sizeof(int3) + meta.size() * sizeof(int2);
+        if (dev_alloc(h, &h->d_thin, bytes / 4 + 8)) return 1;
+        int3* d_segs = reinterpret_cast<int3*>(h->d_thin);
+        int2* d_meta = reinterpret_cast<int2*>(h->d_thin + 3 * segs.size() + (segs.size() & 1));
+        if (!segs.empty()) CK(cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(int3), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+        LAUNCH(launch_thin_windows(h->d_geno, h->row_words, h->d_lut, individuals ? h->d_indlist : nullptr, n_lanes, d_segs,
+                                   (int)segs.size(), d_meta, h->n_chr, slots, step, W, d_dump, slots, h->stream));
+    } else {
     int chunk = 0;
     if (weighted) chunk = std::max(64, pick_chunk(h->L, W, n_lanes, 0) / 8);   // every wLOD window is a fresh sum
     else if (!exact) chunk = pick_chunk(h->L, W, n_lanes, kTileSnpsMax);
     build_items(h->chr_off, W, segs, chunk, step, items);
     if (upload_items(h, items)) return 1;
-    const int64_t slots = garlic_gpu_window_slots(h, step);
-    if (dev_alloc(h, &h->d_dump, (size_t)n_lanes * slots)) return 1;
-    double* d_dump = h->d_dump;
-    LAUNCH(launch_fill_f64(d_dump, (size_t)n_lanes * slots, kMissing, h->stream));
     WalkParams P = base_params(h, W);
     P.ind_list = individuals ? h->d_indlist : nullptr;
     P.n_lanes = n_lanes;
     P.cutoff = 0; P.thr = 1; P.tol = 0;
     P.dump = d_dump; P.dump_stride = slots; P.dump_step = step;
     CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
-    int rc = launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, false, true, items_tile_snps(items, W));
+    rc = launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, false, true, items_tile_snps(items, W));
+    }
     if (!rc && out_dev) {
         *out_dev = d_dump;
         cudaError_t e = cudaStreamSynchronize(h->stream);
@@ -880,19 +922,23 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     h->stats[4] = ms_coarse;
     h->stats[5] = -1;
     h->stats[6] = (double)items.size() * h->n_ind;
-    if (pruned) {   // candidate (individual, item) pairs that went to the exact walker
-        std::vector<unsigned> cc(items.size());
-        CK(cudaMemcpy(cc.data(), h->d_cand_cnt, items.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
-        double tot = 0;
-        for (unsigned v : cc) tot += v;
-        h->stats[5] = tot;
-    }
+    h->stats_items = pruned ? (int64_t)items.size() : 0;   // candidate counts are fetched by last_stats on demand
     laps.lap("out");
     return 0;
 }
 
 int garlic_gpu_last_stats(garlic_gpu_t* h, double* s)
 {
+    if (h->stats_items > 0) {   // candidate (individual, item) pairs that went to the exact walker
+        std::vector<unsigned> cc(h->stats_items);
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(cc.data(), h->d_cand_cnt, cc.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        double tot = 0;
+        for (unsigned v : cc) tot += v;
+        h->stats[5] = tot;
+        h->stats_items = 0;
+    }
     for (int i = 0; i < 8; ++i) s[i] = h->stats[i];
     return 0;
 }

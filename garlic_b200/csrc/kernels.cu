@@ -264,6 +264,51 @@ cudaError_t launch_walk(const WalkParams& P, const Item* items, int n_items, boo
 }
 
 // ------------------------------------------------------------------------------------------
+// K5 pass 1, thinned: the KDE only looks at windows at locus 0, step, 2·step, … of each chromosome
+// (convert[Subset]WinData2DoubleData, garlic-data.cpp:2026-2150) for a handful of individuals, so each of those
+// windows is summed directly (ascending, like a fresh sum of calcLOD, garlic-roh.cpp:57-71) by its own thread
+// instead of walking every window in between.  meta: per chromosome (first kept SNP, first slot).
+// Valid windows are those inside a segment [ws, we); the others keep the MISSING the buffer was filled with.
+// ------------------------------------------------------------------------------------------
+__global__ void thin_windows_kernel(const uint64_t* __restrict__ geno, int64_t row_words, const double* __restrict__ lut,
+                                    const int* __restrict__ ind_list, const int3* __restrict__ segs, int n_segs,
+                                    const int2* __restrict__ meta, int n_chr, long long n_slots, int step, int W,
+                                    double* __restrict__ dump, int64_t dump_stride)
+{
+    const int k = blockIdx.y;
+    const int ind = ind_list ? ind_list[k] : k;
+    const uint64_t* row = geno + (int64_t)ind * row_words;
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n_slots; j += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n_chr - 1;                       // chromosome of slot j: last c with meta[c].y <= j
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (meta[mid].y <= j) lo = mid; else hi = mid - 1; }
+        const int t = meta[lo].x + (int)(j - meta[lo].y) * step;
+        int a = 0, b = n_segs - 1, sg = -1;               // segment holding t: last segment with ws <= t
+        while (a <= b) { const int mid = (a + b) >> 1; if (segs[mid].y <= t) { sg = mid; a = mid + 1; } else b = mid - 1; }
+        if (sg < 0 || t >= segs[sg].z) continue;
+        double win = 0.0;
+        for (int i = 0; i < W; ++i) {
+            const int s = t + i;
+            const int g = (int)(row[s >> 5] >> (2 * (s & 31))) & 3;
+            win += lut[(int64_t)s * 4 + g];
+        }
+        dump[(int64_t)k * dump_stride + j] = win;
+    }
+}
+
+cudaError_t launch_thin_windows(const uint64_t* geno, int64_t row_words, const double* lut, const int* ind_list, int n_lanes,
+                                const int3* segs, int n_segs, const int2* meta, int n_chr, long long n_slots, int step, int W,
+                                double* dump, int64_t dump_stride, cudaStream_t st)
+{
+    if (!n_lanes || !n_slots || !n_segs) return cudaSuccess;
+    long long bx = (n_slots + 127) / 128;
+    if (bx > 4096) bx = 4096;
+    dim3 grid((unsigned)bx, (unsigned)n_lanes);
+    thin_windows_kernel<<<grid, 128, 0, st>>>(geno, row_words, lut, ind_list, segs, n_segs, meta, n_chr, n_slots, step, W, dump,
+                                               dump_stride);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // fill
 // ------------------------------------------------------------------------------------------
 __global__ void fill_f64_kernel(double* p, size_t n, double v)

@@ -24,6 +24,9 @@ struct CoarseParams;
 cudaError_t launch_coarse_tables(const double* lut, long long n_hw, int W, uint32_t* mask, int2* cb, cudaStream_t st);
 cudaError_t launch_coarse(const CoarseParams& P, const Item* items, int n_items, int* cand_list, unsigned* cand_cnt,
                           int cand_stride, cudaStream_t st);
+cudaError_t launch_thin_windows(const uint64_t* geno, int64_t row_words, const double* lut, const int* ind_list, int n_lanes,
+                                const int3* segs, int n_segs, const int2* meta, int n_chr, long long n_slots, int step, int W,
+                                double* dump, int64_t dump_stride, cudaStream_t st);
 cudaError_t launch_fill_f64(double* p, size_t n, double v, cudaStream_t st);
 cudaError_t launch_first_allele(const uint8_t* alleles, int n_snp, int n_ind, int ind_offset, int missing,
                                 unsigned long long* key, cudaStream_t st);

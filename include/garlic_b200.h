@@ -49,6 +49,10 @@ uint64_t garlic_gpu_launch_count(const garlic_gpu_t *h);
 /* CUDA stream (cudaStream_t) all kernels of this handle are launched on */
 void *garlic_gpu_stream(const garlic_gpu_t *h);
 int garlic_gpu_sync(garlic_gpu_t *h);
+/* page-locked host memory: buffers from here are read / written by the copy engine without staging
+ * (put_packed, filter's freq_out / keep_out); ordinary memory works everywhere, only slower */
+void *garlic_gpu_host_alloc(size_t bytes);
+void garlic_gpu_host_free(void *p);
 
 /* ---- K1: loadTPEDData's coding + allele counting (src/garlic-data.cpp:103-150) -------------
  * n_ind individuals on this GPU starting at global individual ind_offset; n_loci SNPs before
