@@ -443,13 +443,69 @@ cudaError_t launch_code_alleles(const uint8_t* alleles, int n_snp, int n_ind, in
 }
 
 // ------------------------------------------------------------------------------------------
-// K2: per-SNP counts from the packed matrix (pre-coded input path): column reduction over the
-// GPU's individuals.  Block = 32 SNP-words(64-bit) wide × 8 row slices; each thread accumulates
-// bit-sliced partial counts for its word column over its rows, lanes of a warp read 256
-// contiguous bytes of one row (coalesced); the 8 row slices are combined with shared atomics and
-// the grid's row blocks with global atomics.
+// K2: per-SNP counts from the packed matrix (pre-coded input path): column reduction over the GPU's
+// individuals (replaces the counting inside loadTPEDData, garlic-data.cpp:115-127, and calculateGenoFreq,
+// :656-676).  A thread owns one 64-bit word column (32 SNPs) for every 8th row of its block's row range; lanes of a
+// warp read 256 contiguous bytes of one row.  Counting is bit-sliced: per row two indicator words (g==1 / g==2
+// interleaved, and missing) are fed 8 rows at a time through a carry-save adder tree (LOP3: sum 0x96, carry 0xE8)
+// into vertical counters ones/twos/fours/eights…; every 248 rows the 8 bit-planes are turned into per-SNP byte
+// counts (nibble → 4 bytes by multiplication) and added to shared, then global, integer counters.
 // counts: [4][L0] = nalleles (Σ g over g<3), total (2·nonmiss), hom, nonmiss.
 // ------------------------------------------------------------------------------------------
+struct VCounter {
+    uint64_t p[8];   // bit-planes: ones, twos, fours, eights, …, 128s
+};
+
+__device__ __forceinline__ void csa(uint64_t& sum, uint64_t& carry, uint64_t a, uint64_t b, uint64_t c)
+{
+    const uint64_t u = a ^ b;
+    carry = (a & b) | (u & c);
+    sum = u ^ c;
+}
+
+__device__ __forceinline__ void vc_add8(VCounter& v, const uint64_t x[8])
+{
+    uint64_t t2a, t2b, t2c, t2d, t4a, t4b, e8;
+    csa(v.p[0], t2a, v.p[0], x[0], x[1]);
+    csa(v.p[0], t2b, v.p[0], x[2], x[3]);
+    csa(v.p[1], t4a, v.p[1], t2a, t2b);
+    csa(v.p[0], t2c, v.p[0], x[4], x[5]);
+    csa(v.p[0], t2d, v.p[0], x[6], x[7]);
+    csa(v.p[1], t4b, v.p[1], t2c, t2d);
+    csa(v.p[2], e8, v.p[2], t4a, t4b);
+#pragma unroll
+    for (int l = 3; l < 8; ++l) {   // ripple the eights into the higher planes
+        const uint64_t c = v.p[l] & e8;
+        v.p[l] ^= e8;
+        e8 = c;
+    }
+}
+
+// add the counts held in the 8 planes (64 bit positions) to dst[pos * stride_pos] for the positions selected by `even_only`
+__device__ __forceinline__ void vc_flush(VCounter& v, int* dst_even, int* dst_odd)
+{
+    // 4 bit positions at a time: nibble n of plane l → bytes (bit j → byte j) by (n * 0x00204081) & 0x01010101
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+            const uint32_t nib = (uint32_t)(v.p[l] >> (4 * g)) & 0xfu;
+            acc += ((nib * 0x00204081u) & 0x01010101u) << l;
+        }
+        // positions 4g..4g+3 = (SNP 2g: even, odd), (SNP 2g+1: even, odd)
+        const int e0 = acc & 0xff, o0 = (acc >> 8) & 0xff, e1 = (acc >> 16) & 0xff, o1 = acc >> 24;
+        if (e0) atomicAdd(dst_even + 2 * g, e0);
+        if (e1) atomicAdd(dst_even + 2 * g + 1, e1);
+        if (dst_odd) {
+            if (o0) atomicAdd(dst_odd + 2 * g, o0);
+            if (o1) atomicAdd(dst_odd + 2 * g + 1, o1);
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < 8; ++l) v.p[l] = 0;
+}
+
 __global__ void __launch_bounds__(256)
 count_packed_kernel(const uint64_t* __restrict__ geno, int64_t row_words, int n_ind, long long L0,
                     int rows_per_block, int* __restrict__ counts)
@@ -463,34 +519,32 @@ count_packed_kernel(const uint64_t* __restrict__ geno, int64_t row_words, int n_
     const int r0 = blockIdx.y * rows_per_block;
     const int r1 = min(n_ind, r0 + rows_per_block);
     if (word < n_words) {
-        // per-SNP byte counters would overflow; flush every 255 rows
-        for (int rb = r0 + slice; rb < r1; rb += 8 * 255) {
-            uint32_t c1[8] = {0}, c2[8] = {0}, cm[8] = {0};   // 32 SNPs × 8-bit counters, 4 per register
-            for (int r = rb, n = 0; r < r1 && n < 255; r += 8, ++n) {
-                const uint64_t w = geno[(int64_t)r * row_words + word];
-                const uint64_t lo = w & 0x5555555555555555ull, hi = (w >> 1) & 0x5555555555555555ull;
-                const uint64_t m1 = lo & ~hi, m2 = hi & ~lo, mm = lo & hi;   // g==1, g==2, missing (at even bits)
+        const uint64_t M = 0x5555555555555555ull;
+        VCounter va, vm;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    // SNPs 4q..4q+3 → spread their indicator bits (bit positions 8q,8q+2,8q+4,8q+6) to bytes
-                    const uint32_t b1 = (uint32_t)(m1 >> (8 * q)) & 0x55u;
-                    const uint32_t b2 = (uint32_t)(m2 >> (8 * q)) & 0x55u;
-                    const uint32_t bm = (uint32_t)(mm >> (8 * q)) & 0x55u;
-                    c1[q] += (b1 & 1u) | ((b1 & 4u) << 6) | ((b1 & 16u) << 12) | ((b1 & 64u) << 18);
-                    c2[q] += (b2 & 1u) | ((b2 & 4u) << 6) | ((b2 & 16u) << 12) | ((b2 & 64u) << 18);
-                    cm[q] += (bm & 1u) | ((bm & 4u) << 6) | ((bm & 16u) << 12) | ((bm & 64u) << 18);
-                }
+        for (int l = 0; l < 8; ++l) { va.p[l] = 0; vm.p[l] = 0; }
+        int groups = 0;
+        for (int rb = r0 + slice; rb < r1; rb += 64) {        // 8 of this thread's rows per group
+            uint64_t xa[8], xm[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = rb + 8 * i;
+                const uint64_t w = r < r1 ? geno[(int64_t)r * row_words + word] : 0ull;   // 0 = g==0: adds to nothing
+                const uint64_t lo = w & M, hi = (w >> 1) & M;
+                xa[i] = (lo & ~hi) | ((hi & ~lo) << 1);       // g==1 at the even bit, g==2 at the odd bit
+                xm[i] = lo & hi;                              // missing at the even bit
             }
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int snp = lane * 32 + q * 4 + b;
-                    const int v1 = (c1[q] >> (8 * b)) & 0xff, v2 = (c2[q] >> (8 * b)) & 0xff, vm = (cm[q] >> (8 * b)) & 0xff;
-                    if (v1) atomicAdd(&s_cnt[0][snp], v1);
-                    if (v2) atomicAdd(&s_cnt[1][snp], v2);
-                    if (vm) atomicAdd(&s_cnt[2][snp], vm);
-                }
+            vc_add8(va, xa);
+            vc_add8(vm, xm);
+            if (++groups == 31) {                             // 248 rows: the planes hold at most 255
+                vc_flush(va, &s_cnt[0][lane * 32], &s_cnt[1][lane * 32]);
+                vc_flush(vm, &s_cnt[2][lane * 32], nullptr);
+                groups = 0;
+            }
+        }
+        if (groups) {
+            vc_flush(va, &s_cnt[0][lane * 32], &s_cnt[1][lane * 32]);
+            vc_flush(vm, &s_cnt[2][lane * 32], nullptr);
         }
     }
     __syncthreads();
