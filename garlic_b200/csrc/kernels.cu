@@ -3,6 +3,7 @@
 // K5 walk (fused windows→ROH / window dump), K6 ld_pairs + ld_band, K5-W wlod_walk.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include "common.cuh"
 #include "walk.cuh"
 #include "coarse.cuh"
@@ -481,10 +482,12 @@ __device__ __forceinline__ void vc_add8(VCounter& v, const uint64_t x[8])
     }
 }
 
-// add the counts held in the 8 planes (64 bit positions) to dst[pos * stride_pos] for the positions selected by `even_only`
-__device__ __forceinline__ void vc_flush(VCounter& v, int* dst_even, int* dst_odd)
+// Turn the 8 planes (64 bit positions = 32 SNPs x {even, odd}) into counts and add them to this thread's slots of
+// the CTA's shared counters, laid out [kind][SNP within word (32)][column (256)] so that a warp's accesses are
+// consecutive and every slot has exactly one owner (plain adds, no atomics).
+// 4 bit positions at a time: nibble n of plane l → bytes (bit j → byte j) by (n * 0x00204081) & 0x01010101.
+__device__ __noinline__ void vc_flush(VCounter& v, int* __restrict__ even_cnt, int* __restrict__ odd_cnt)
 {
-    // 4 bit positions at a time: nibble n of plane l → bytes (bit j → byte j) by (n * 0x00204081) & 0x01010101
 #pragma unroll
     for (int g = 0; g < 16; ++g) {
         uint32_t acc = 0;
@@ -493,43 +496,44 @@ __device__ __forceinline__ void vc_flush(VCounter& v, int* dst_even, int* dst_od
             const uint32_t nib = (uint32_t)(v.p[l] >> (4 * g)) & 0xfu;
             acc += ((nib * 0x00204081u) & 0x01010101u) << l;
         }
-        // positions 4g..4g+3 = (SNP 2g: even, odd), (SNP 2g+1: even, odd)
-        const int e0 = acc & 0xff, o0 = (acc >> 8) & 0xff, e1 = (acc >> 16) & 0xff, o1 = acc >> 24;
-        if (e0) atomicAdd(dst_even + 2 * g, e0);
-        if (e1) atomicAdd(dst_even + 2 * g + 1, e1);
-        if (dst_odd) {
-            if (o0) atomicAdd(dst_odd + 2 * g, o0);
-            if (o1) atomicAdd(dst_odd + 2 * g + 1, o1);
+        even_cnt[(2 * g) * 256] += acc & 0xff;
+        even_cnt[(2 * g + 1) * 256] += (acc >> 16) & 0xff;
+        if (odd_cnt) {
+            odd_cnt[(2 * g) * 256] += (acc >> 8) & 0xff;
+            odd_cnt[(2 * g + 1) * 256] += acc >> 24;
         }
     }
 #pragma unroll
     for (int l = 0; l < 8; ++l) v.p[l] = 0;
 }
 
-__global__ void __launch_bounds__(256)
+// block = 256 consecutive word columns (2 KB of every row, contiguous), thread = one column, rows of the block's
+// row range in groups of 8.
+__global__ void __launch_bounds__(256, 2)
 count_packed_kernel(const uint64_t* __restrict__ geno, int64_t row_words, int n_ind, long long L0,
                     int rows_per_block, int* __restrict__ counts)
 {
-    __shared__ int s_cnt[3][32 * 32];   // [n1,n2,nmiss][snp in tile]
-    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 3 * 1024; i += 256) (&s_cnt[0][0])[i] = 0;
+    extern __shared__ int s_cnt[];             // [3][32][256]: n1, n2, missing
+    for (int i = threadIdx.x; i < 3 * 32 * 256; i += 256) s_cnt[i] = 0;
     __syncthreads();
-    const long long word = (long long)blockIdx.x * 32 + lane;
+    const long long word = (long long)blockIdx.x * 256 + threadIdx.x;
     const long long n_words = (L0 + 31) >> 5;
     const int r0 = blockIdx.y * rows_per_block;
     const int r1 = min(n_ind, r0 + rows_per_block);
-    if (word < n_words) {
+    if (word < n_words && r0 < r1) {
         const uint64_t M = 0x5555555555555555ull;
         VCounter va, vm;
 #pragma unroll
         for (int l = 0; l < 8; ++l) { va.p[l] = 0; vm.p[l] = 0; }
         int groups = 0;
-        for (int rb = r0 + slice; rb < r1; rb += 64) {        // 8 of this thread's rows per group
+        const uint64_t* col = geno + word;
+        int* mine = s_cnt + threadIdx.x;
+        for (int rb = r0; rb < r1; rb += 8) {
             uint64_t xa[8], xm[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int r = rb + 8 * i;
-                const uint64_t w = r < r1 ? geno[(int64_t)r * row_words + word] : 0ull;   // 0 = g==0: adds to nothing
+                const int r = rb + i;
+                const uint64_t w = r < r1 ? col[(int64_t)r * row_words] : 0ull;   // 0 = g==0: adds to no counter
                 const uint64_t lo = w & M, hi = (w >> 1) & M;
                 xa[i] = (lo & ~hi) | ((hi & ~lo) << 1);       // g==1 at the even bit, g==2 at the odd bit
                 xm[i] = lo & hi;                              // missing at the even bit
@@ -537,22 +541,23 @@ count_packed_kernel(const uint64_t* __restrict__ geno, int64_t row_words, int n_
             vc_add8(va, xa);
             vc_add8(vm, xm);
             if (++groups == 31) {                             // 248 rows: the planes hold at most 255
-                vc_flush(va, &s_cnt[0][lane * 32], &s_cnt[1][lane * 32]);
-                vc_flush(vm, &s_cnt[2][lane * 32], nullptr);
+                vc_flush(va, mine, mine + 32 * 256);
+                vc_flush(vm, mine + 2 * 32 * 256, nullptr);
                 groups = 0;
             }
         }
         if (groups) {
-            vc_flush(va, &s_cnt[0][lane * 32], &s_cnt[1][lane * 32]);
-            vc_flush(vm, &s_cnt[2][lane * 32], nullptr);
+            vc_flush(va, mine, mine + 32 * 256);
+            vc_flush(vm, mine + 2 * 32 * 256, nullptr);
         }
     }
     __syncthreads();
     const int rows = max(0, r1 - r0);
-    for (int i = threadIdx.x; i < 1024; i += 256) {
-        const long long s = (long long)blockIdx.x * 1024 + i;
+    for (int i = threadIdx.x; i < 32 * 256; i += 256) {       // i = SNP within the CTA's 8192: consecutive → coalesced
+        const long long s = (long long)blockIdx.x * 8192 + i;
         if (s >= L0) continue;
-        const int n1 = s_cnt[0][i], n2 = s_cnt[1][i], nm = s_cnt[2][i];
+        const int slot = (i & 31) * 256 + (i >> 5);
+        const int n1 = s_cnt[slot], n2 = s_cnt[32 * 256 + slot], nm = s_cnt[2 * 32 * 256 + slot];
         const int nonmiss = rows - nm;
         atomicAdd(&counts[0 * L0 + s], n1 + 2 * n2);
         atomicAdd(&counts[1 * L0 + s], 2 * nonmiss);
@@ -566,14 +571,17 @@ cudaError_t launch_count_packed(const uint64_t* geno, int64_t row_words, int n_i
 {
     if (!n_ind || !L0) return cudaSuccess;
     const long long n_words = (L0 + 31) >> 5;
-    const unsigned gx = (unsigned)((n_words + 31) / 32);
-    int gy = (int)((148ll * 8 + gx - 1) / gx);          // enough row blocks to fill the machine
-    if (gy < 1) gy = 1;
+    const unsigned gx = (unsigned)((n_words + 255) / 256);
+    int gy = (int)((148ll * 2 + gx - 1) / gx);            // about one wave of 2 CTAs per SM
+    gy = std::max(1, std::min(gy, (n_ind + 63) / 64));
     int rpb = (n_ind + gy - 1) / gy;
     rpb = ((rpb + 7) / 8) * 8;
     gy = (n_ind + rpb - 1) / rpb;
     dim3 grid(gx, gy);
-    count_packed_kernel<<<grid, 256, 0, st>>>(geno, row_words, n_ind, L0, rpb, counts);
+    const size_t smem = 3 * 32 * 256 * sizeof(int);           // 96 KB
+    cudaError_t e = cudaFuncSetAttribute(count_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    count_packed_kernel<<<grid, 256, smem, st>>>(geno, row_words, n_ind, L0, rpb, counts);
     return cudaGetLastError();
 }
 
@@ -610,51 +618,123 @@ cudaError_t launch_freq_keep(const int* counts, long long L0, const int* pos, co
 
 // ------------------------------------------------------------------------------------------
 // K3: column compaction of the packed matrix (filterMonomorphic[AndOOB]Sites, garlic-data.cpp:871-1195,
-// as a bit-level gather).  The keep mask is the same for every individual, so the host hands over, per
-// 32-SNP input word, its keep bits and, per output word, the input word it starts in and how many kept
-// fields of that word belong to earlier output words.  One thread builds one output word: it walks
-// 1-3 input words, squeezes the dropped 2-bit fields out of each (one masked shift per dropped SNP;
-// most words drop none) and ORs the survivors into place.  Lanes = consecutive words of one row, so
-// reads and writes are coalesced.
+// as a bit-level gather).  The keep mask is the same for every individual, so a thread that owns one OUTPUT word
+// column first turns the keep bits of its 1-3 source words into a short plan of segments
+//     out |= ((in[j] >> rs) & mask(len)) << ls          (one segment per run of kept SNPs)
+// held in registers, and then replays that plan for every row of its block's row range: per row a couple of
+// cached loads, a few shifts and one coalesced store (a CTA covers 2 KB of each row, contiguous).  Columns whose
+// plan needs more than kSegMax segments (many isolated drops) take the generic per-field path.
 // ------------------------------------------------------------------------------------------
+constexpr int kSegMax = 8;
+
+__device__ __forceinline__ uint64_t squeeze_generic(const uint64_t* __restrict__ row, long long n_in_words,
+                                                    const uint32_t* __restrict__ keepw, long long j, int skip)
+{
+    uint64_t o = 0;
+    int pos = 0;
+    while (pos < 32 && j < n_in_words) {
+        const uint32_t m = keepw[j];
+        uint64_t x = row[j];
+        uint32_t drop = ~m;
+        while (drop) {                       // highest dropped field first: lower positions stay valid
+            const int d = 31 - __clz((int)drop);
+            drop &= ~(1u << d);
+            const uint64_t low = (1ull << (2 * d)) - 1ull;
+            x = (x & low) | ((x >> 2) & ~low);
+        }
+        int c = __popc(m) - skip;
+        x >>= 2 * skip;
+        skip = 0;
+        if (c > 0) {
+            if (c < 32) x &= (1ull << (2 * c)) - 1ull;
+            o |= x << (2 * pos);
+            pos += c;
+        }
+        ++j;
+    }
+    if (pos < 32) o |= ~0ull << (2 * pos);   // fields past the last kept SNP read as missing
+    return o;
+}
+
 __global__ void __launch_bounds__(256)
 compact_geno_kernel(const uint64_t* __restrict__ gin, int64_t in_words, long long n_in_words,
                     const uint32_t* __restrict__ keepw, const int* __restrict__ first_word,
                     const uint8_t* __restrict__ first_skip, long long L, uint64_t* __restrict__ gout,
-                    int64_t out_words, int n_ind)
+                    int64_t out_words, int n_ind, int rows_per_block)
 {
     const long long n_w = (L + 31) >> 5;
-    const long long total = n_w * n_ind;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(t / n_w);
-        const long long w = t % n_w;
-        const uint64_t* row = gin + (int64_t)i * in_words;
-        long long j = first_word[w];
-        int skip = first_skip[w];
-        uint64_t o = 0;
-        int pos = 0;
-        while (pos < 32 && j < n_in_words) {
-            const uint32_t m = keepw[j];
-            uint64_t x = row[j];
-            uint32_t drop = ~m;
-            while (drop) {                       // highest dropped field first: lower positions stay valid
-                const int d = 31 - __clz((int)drop);
-                drop &= ~(1u << d);
-                const uint64_t low = (1ull << (2 * d)) - 1ull;
-                x = (x & low) | ((x >> 2) & ~low);
-            }
-            int c = __popc(m) - skip;
-            x >>= 2 * skip;
-            skip = 0;
-            if (c > 0) {
-                if (c < 32) x &= (1ull << (2 * c)) - 1ull;
-                o |= x << (2 * pos);
-                pos += c;
-            }
-            ++j;
+    const long long w = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(n_ind, r0 + rows_per_block);
+    if (w >= n_w || r0 >= r1) return;
+    // ---- plan (static slots so that it stays in registers) ----
+    int sj[kSegMax], sh[kSegMax];            // source word; rs | ls << 8 | len << 16
+    int nseg = 0, pos = 0;
+    const long long j0 = first_word[w];
+    long long j = j0;
+    uint32_t m = j < n_in_words ? keepw[j] : 0u;
+    for (int skip = first_skip[w]; skip > 0; --skip) m &= m - 1;      // kept fields that belong to earlier output words
+#pragma unroll
+    for (int s = 0; s < kSegMax; ++s) {
+        sj[s] = 0; sh[s] = 0;
+        while (m == 0u && pos < 32 && j + 1 < n_in_words) m = keepw[++j];
+        if (m != 0u && pos < 32) {
+            const int a = __ffs((int)m) - 1;
+            const uint32_t inv = ~(m >> a);
+            const int run = inv ? __ffs((int)inv) - 1 : 32 - a;
+            const int len = min(run, 32 - pos);
+            sj[s] = (int)j;
+            sh[s] = (2 * a) | ((2 * pos) << 8) | (len << 16);
+            nseg = s + 1;
+            pos += len;
+            m = (run + a >= 32) ? 0u : (m & ~(((1u << run) - 1u) << a));
         }
-        if (pos < 32) o |= ~0ull << (2 * pos);   // fields past the last kept SNP read as missing
-        gout[(int64_t)i * out_words + w] = o;
+    }
+    // anything left to place after kSegMax segments?
+    while (m == 0u && pos < 32 && j + 1 < n_in_words) m = keepw[++j];
+    if (m != 0u && pos < 32) nseg = kSegMax + 1;
+    const uint64_t tail = pos < 32 ? (~0ull << (2 * pos)) : 0ull;
+    if (nseg > kSegMax) {                    // rare: too fragmented for the register plan
+        const int skip0 = first_skip[w];
+        for (int r = r0; r < r1; ++r)
+            gout[(int64_t)r * out_words + w] = squeeze_generic(gin + (int64_t)r * in_words, n_in_words, keepw, j0, skip0);
+        return;
+    }
+    // ---- replay, four rows at a time (independent loads in flight) ----
+    int r = r0;
+    for (; r + 3 < r1; r += 4) {
+        const uint64_t* row = gin + (int64_t)r * in_words;
+        uint64_t o0 = tail, o1 = tail, o2 = tail, o3 = tail, x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+        int lastj = -1;
+#pragma unroll
+        for (int sg = 0; sg < kSegMax; ++sg) {
+            if (sg < nseg) {
+                if (sj[sg] != lastj) {
+                    lastj = sj[sg];
+                    x0 = row[lastj]; x1 = row[in_words + lastj]; x2 = row[2 * in_words + lastj]; x3 = row[3 * in_words + lastj];
+                }
+                const int rs = sh[sg] & 0xff, ls = (sh[sg] >> 8) & 0xff, len = sh[sg] >> 16;
+                const uint64_t mk = len >= 32 ? ~0ull : ((1ull << (2 * len)) - 1ull);
+                o0 |= ((x0 >> rs) & mk) << ls; o1 |= ((x1 >> rs) & mk) << ls;
+                o2 |= ((x2 >> rs) & mk) << ls; o3 |= ((x3 >> rs) & mk) << ls;
+            }
+        }
+        uint64_t* out = gout + (int64_t)r * out_words + w;
+        out[0] = o0; out[out_words] = o1; out[2 * out_words] = o2; out[3 * out_words] = o3;
+    }
+    for (; r < r1; ++r) {
+        const uint64_t* row = gin + (int64_t)r * in_words;
+        uint64_t o = tail, x = 0;
+        int lastj = -1;
+#pragma unroll
+        for (int sg = 0; sg < kSegMax; ++sg) {
+            if (sg < nseg) {
+                if (sj[sg] != lastj) { x = row[sj[sg]]; lastj = sj[sg]; }
+                const int rs = sh[sg] & 0xff, ls = (sh[sg] >> 8) & 0xff, len = sh[sg] >> 16;
+                const uint64_t mk = len >= 32 ? ~0ull : ((1ull << (2 * len)) - 1ull);
+                o |= ((x >> rs) & mk) << ls;
+            }
+        }
+        gout[(int64_t)r * out_words + w] = o;
     }
 }
 
@@ -662,12 +742,16 @@ cudaError_t launch_compact_geno(const uint64_t* gin, int64_t in_words, long long
                                 const int* first_word, const uint8_t* first_skip, long long L, uint64_t* gout,
                                 int64_t out_words, int n_ind, cudaStream_t st)
 {
-    const long long total = ((L + 31) >> 5) * n_ind;
-    if (!total) return cudaSuccess;
-    long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 64) blocks = 148 * 64;
-    compact_geno_kernel<<<(unsigned)blocks, 256, 0, st>>>(gin, in_words, n_in_words, keepw, first_word, first_skip, L,
-                                                         gout, out_words, n_ind);
+    const long long n_w = (L + 31) >> 5;
+    if (!n_w || !n_ind) return cudaSuccess;
+    const unsigned gx = (unsigned)((n_w + 255) / 256);
+    int gy = (int)((148ll * 8 + gx - 1) / gx);
+    gy = std::max(1, std::min(gy, (n_ind + 31) / 32));
+    const int rpb = (n_ind + gy - 1) / gy;
+    gy = (n_ind + rpb - 1) / rpb;
+    dim3 grid(gx, gy);
+    compact_geno_kernel<<<grid, 256, 0, st>>>(gin, in_words, n_in_words, keepw, first_word, first_skip, L, gout, out_words,
+                                              n_ind, rpb);
     return cudaGetLastError();
 }
 

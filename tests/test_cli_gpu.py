@@ -78,7 +78,7 @@ def test_cli_auto_cutoff_path(name):
         got = np.loadtxt(os.path.join(tmp, kde_name))           # same window size selected → same file name
         want = np.loadtxt(os.path.join(GOLDEN, name, kde_name))
         assert np.allclose(got[:, 0], want[:, 0], rtol=1e-5)
-        assert np.max(np.abs(got[:, 1] - want[:, 1])) <= 0.01 * want[:, 1].max()    # FIGTree ε = 1e-2
+        assert np.max(np.abs(got[:, 1] - want[:, 1])) <= 0.02 * want[:, 1].max()    # FIGTree ε = 1e-2, two runs
         cut = float(r.stdout.split("(17 digits): ")[1].split()[0])
         step = want[1, 0] - want[0, 0]
         assert abs(cut - float(log_value(name, "Selected LOD score cutoff:"))) <= 2.01 * step
@@ -86,7 +86,7 @@ def test_cli_auto_cutoff_path(name):
             ref = [l.split() for l in golden_text(name, "out.log").splitlines() if l.startswith(" ")]
             mine = [l.split() for l in log.splitlines() if l.startswith(" ")]
             assert [m[0] for m in mine] == [x[0] for x in ref]
-            assert np.allclose([float(m[1]) for m in mine], [float(x[1]) for x in ref], rtol=0.02)
+            assert np.allclose([float(m[1]) for m in mine], [float(x[1]) for x in ref], rtol=0.05)
         W = int(kde_name.split(".")[1].replace("SNPs", ""))
         res = orc.run_pipeline(ds, W, 0.001, cut, 0.25)
         bounds = arg_list(args, "--size-bounds")
