@@ -6,7 +6,7 @@ Own arm (default):  python bench.py --gpus N --steps K --warmup W
     hg19 centromeres, 0.1 % gaps > 200 kb), --winsize 50, --error 0.001, unweighted LOD, --overlap-frac 0.25,
     fixed --lod-cutoff (host KDE excluded).  One step = one pass of the hot path over the batch:
     [H2D of the packed genotypes, e2e only] -> K2 allele/missingness counts -> (N>1: NCCL all-reduce of the
-    counts) -> freq + monomorphic filter + K3 compaction -> K4 LOD table -> K5 pass 1 (thinned windows of the
+    counts, issued by the library on its own stream) -> freq + monomorphic filter + K3 compaction -> K4 LOD table -> K5 pass 1 (thinned windows of the
     20 KDE individuals -> host; N>1: all-gather) -> K5 pass 2 (windows -> cutoff -> coverage -> ROH, fused)
     -> ROH records to the host.  Sharded by individual: every rank holds 2,000 individuals (weak scaling).
     `value` has the packed matrix resident in HBM; `e2e` goes through the C ABI with pinned HOST buffers.
@@ -315,9 +315,12 @@ def main():
     g = GarlicGPU(local)
     g.set_shape(n_ind, L0, chr_off0, pos0, ind_offset=rank * n_ind)
     stream = torch.cuda.ExternalStream(g.stream(), device=dev)
-    counts_t = None
     if dist is not None:
-        counts_t = shard.dev_tensor(torch, g.counts_dev(), (4, L0), "<i4", dev)
+        # the library runs the path's collectives itself (NCCL on its own stream); torch.distributed only carries
+        # the 128-byte communicator id, the timing barrier and the max-over-ranks of the measured time
+        ids = [GarlicGPU.comm_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        g.comm_init(ids[0], rank, world)
     # the KDE subsample: 20 individuals of the whole job, spread evenly; this rank computes its own
     n_total = n_ind * world
     kde_global = np.unique(np.linspace(0, n_total - 1, CFG["kde_subsample"]).astype(np.int64))
@@ -341,10 +344,6 @@ def main():
             t0 = lap("put_packed_h2d", t0)
         g.count_packed()                                     # K2
         t0 = lap("count_packed", t0)
-        if dist is not None:
-            g.sync()
-            shard.allreduce_counts(dist, counts_t)           # the one data-path collective
-            torch.cuda.synchronize()
         t0 = lap("allreduce_counts", t0)
         freq, keep, L = g.filter()                           # freq, keep mask -> host; K3 compaction
         t0 = lap("filter_compact", t0)
@@ -352,14 +351,8 @@ def main():
         t0 = lap("set_tables", t0)
         if dist is None:
             thin = g.windows(W, W, individuals=kde_local, exact=False)
-        else:                                                # thinned LODs stay on the GPU, one small all-gather
-            slots = g.window_slots(W)
-            if len(kde_local):
-                ptr, n_, _ = g.windows_dev(W, W, individuals=kde_local, exact=False)
-                mine = shard.dev_tensor(torch, ptr, (n_, slots), "<f8", dev)
-            else:
-                mine = torch.empty((0, slots), dtype=torch.float64, device=dev)
-            thin = shard.allgather_thinned(torch, dist, mine, kde_max).cpu().numpy()   # KDE input on every rank
+        else:                                                # every rank gets all KDE individuals' thinned LODs
+            thin = g.windows_gather(W, W, kde_local, kde_max, world)
         t0 = lap("pass1_thinned_windows", t0)
         roh = g.call_roh(W, cutoff, ov, exact=a.exact)       # K5 pass 2 (fused) -> ROH records on the host
         t0 = lap("pass2_call_roh", t0)

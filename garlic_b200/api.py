@@ -25,7 +25,8 @@ EXPORTS = [
     "garlic_gpu_get_one_allele", "garlic_gpu_put_gl", "garlic_gpu_put_gl_dev", "garlic_gpu_filter",
     "garlic_gpu_set_tables", "garlic_gpu_set_lut", "garlic_gpu_get_lut", "garlic_gpu_get_hom_freq",
     "garlic_gpu_ld_band", "garlic_gpu_set_wlod", "garlic_gpu_window_slots", "garlic_gpu_windows",
-    "garlic_gpu_windows_dev", "garlic_gpu_call_roh", "garlic_gpu_last_stats", "garlic_gpu_n_kept", "garlic_gpu_get_kept_index",
+    "garlic_gpu_windows_dev", "garlic_gpu_windows_gather", "garlic_gpu_comm_id", "garlic_gpu_comm_init",
+    "garlic_gpu_call_roh", "garlic_gpu_last_stats", "garlic_gpu_n_kept", "garlic_gpu_get_kept_index",
     "garlic_gpu_get_genotypes",
 ]
 
@@ -237,6 +238,30 @@ class GarlicGPU:
         self._ck(self.lib.garlic_gpu_windows_dev(self.h, C.c_int(W), C.c_int(step), C.c_int(int(weighted)), _p(idx),
                                                  C.c_int(n), C.c_int(int(exact)), C.byref(ptr)))
         return ptr.value, n, self.window_slots(step)
+
+    def windows_gather(self, W, step, individuals, rows_per_rank, world, weighted=False, exact=False):
+        """All ranks' thinned windows: float64[world*rows_per_rank, slots] (MISSING rows = padding)."""
+        idx = np.ascontiguousarray(individuals, np.int32)
+        slots = self.window_slots(step)
+        key = (world * rows_per_rank, slots)
+        if getattr(self, "_gather_buf", None) is None or self._gather_buf.shape != key:
+            self._gather_buf = self.host_array(key[0] * key[1], np.float64).reshape(key)
+        self._ck(self.lib.garlic_gpu_windows_gather(self.h, C.c_int(W), C.c_int(step), C.c_int(int(weighted)), _p(idx),
+                                                    C.c_int(len(idx)), C.c_int(rows_per_rank), C.c_int(int(exact)),
+                                                    _p(self._gather_buf)))
+        return self._gather_buf
+
+    @staticmethod
+    def comm_id():
+        lib = load_library()
+        buf = np.zeros(128, np.uint8)
+        if lib.garlic_gpu_comm_id(_p(buf)) != 0:
+            raise GarlicError("ncclGetUniqueId failed")
+        return buf
+
+    def comm_init(self, comm_id, rank, world):
+        buf = np.ascontiguousarray(comm_id, np.uint8)
+        self._ck(self.lib.garlic_gpu_comm_init(self.h, _p(buf), C.c_int(rank), C.c_int(world)))
 
     def call_roh(self, W, cutoff, overlap_frac, weighted=False, exact=False, cap=1 << 16):
         """→ int32[n, 4] rows (ind, chr, start_idx, stop_idx), sorted by (ind, chr, start)."""

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgarlic_b200.so")
 SOURCES = ["kernels.cu", "wlod.cu", "capi.cu"]
-HEADERS = ["common.cuh", "walk.cuh", "kernels.h", "wlod.h", os.path.join("..", "..", "include", "garlic_b200.h")]
+HEADERS = ["common.cuh", "walk.cuh", "coarse.cuh", "segments.h", "kernels.h", "wlod.h", os.path.join("..", "..", "include", "garlic_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false",          # the reference is built without FMA; keep mul/add roundings separate
               "-Xcompiler", "-fPIC", "--shared"]
@@ -26,7 +26,7 @@ def build(force=False, verbose=False):
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-lnccl", "-o", OUT]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -3,6 +3,7 @@
 // validity), kernel launches, stitching of chunk-boundary runs.  All arithmetic of the
 // hot path happens in the kernels of kernels.cu / wlod.cu.
 #include <cuda_runtime.h>
+#include <nccl.h>
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -77,6 +78,10 @@ struct garlic_gpu {
     int* d_cand_list = nullptr;
     unsigned* d_cand_cnt = nullptr;
     bool prune = true;             // GARLIC_NO_PRUNE=1 disables the pruning pass
+    ncclComm_t comm = nullptr;     // one rank per GPU, individuals sharded across ranks
+    int comm_rank = 0, comm_world = 1;
+    bool counts_reduced = false;   // d_counts already holds the sum over all ranks
+    double* d_gather = nullptr;    // all-gathered thinned windows
     cudaEvent_t ev2 = nullptr;
     int* d_first_word = nullptr;
     uint8_t* d_first_skip = nullptr;
@@ -203,6 +208,8 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     dev_free(h->d_cmask); dev_free(h->d_ccb); dev_free(h->d_cand_list); dev_free(h->d_cand_cnt);
+    if (h->comm) ncclCommDestroy(h->comm);
+    dev_free(h->d_gather);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -217,6 +224,37 @@ void* garlic_gpu_host_alloc(size_t bytes)
     return p;
 }
 void garlic_gpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+#define NCK(call)                                                                             \
+    do {                                                                                      \
+        ncclResult_t r_ = (call);                                                             \
+        if (r_ != ncclSuccess) {                                                              \
+            h->err = std::string(#call) + ": " + ncclGetErrorString(r_);                      \
+            return 1;                                                                         \
+        }                                                                                     \
+    } while (0)
+
+int garlic_gpu_comm_id(uint8_t* id128)
+{
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return 1;
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+int garlic_gpu_comm_init(garlic_gpu_t* h, const uint8_t* id128, int rank, int world)
+{
+    CK(cudaSetDevice(h->device));
+    if (world < 1 || rank < 0 || rank >= world) FAIL("comm_init: bad rank / world size");
+    if (h->comm) { ncclCommDestroy(h->comm); h->comm = nullptr; }
+    h->comm_rank = rank; h->comm_world = world;
+    if (world == 1) return 0;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NCK(ncclCommInitRank(&h->comm, world, id, rank));
+    return 0;
+}
 
 int garlic_gpu_sync(garlic_gpu_t* h)
 {
@@ -277,6 +315,9 @@ int garlic_gpu_code_alleles(garlic_gpu_t* h)
     CK(cudaSetDevice(h->device));
     if (!h->d_alleles) FAIL("code_alleles: no alleles uploaded");
     const int missing = h->missing_char;
+    h->counts_reduced = false;
+    // the "1" allele is the first non-missing character over ALL individuals: MIN over the shards' keys
+    if (h->comm) NCK(ncclAllReduce(h->d_key, h->d_key, (size_t)h->L0, ncclUint64, ncclMin, h->comm, h->stream));
     CK(cudaMemsetAsync(h->d_counts, 0, (size_t)4 * h->L0 * sizeof(int), h->stream));
     // chunks of SNPs so the grid stays within limits; all chunks start on a 32-SNP boundary
     const int64_t chunk = 1 << 20;
@@ -325,6 +366,7 @@ int garlic_gpu_count_packed(garlic_gpu_t* h, const int32_t* nalleles_corr, const
 {
     CK(cudaSetDevice(h->device));
     if (!h->have_geno0) FAIL("count_packed: no genotypes loaded");
+    h->counts_reduced = false;
     CK(cudaMemsetAsync(h->d_counts, 0, (size_t)4 * h->L0 * sizeof(int), h->stream));
     LAUNCH(launch_count_packed(h->d_geno0, h->row_words0, h->n_ind, h->L0, h->d_counts, h->stream));
     if (nalleles_corr || total_corr) {
@@ -418,6 +460,11 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
         CK(cudaMemcpyAsync(h->d_freq0, freq0, L0 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->d_keep, keep, L0, cudaMemcpyHostToDevice, h->stream));
     } else {
+        // the one data-path collective: per-SNP counters of all shards, summed in place on this stream
+        if (h->comm && !h->counts_reduced) {
+            NCK(ncclAllReduce(h->d_counts, h->d_counts, (size_t)4 * L0, ncclInt32, ncclSum, h->comm, h->stream));
+            h->counts_reduced = true;
+        }
         LAUNCH(launch_freq_keep(h->d_counts, L0, h->d_pos0, h->d_chr_of0, h->d_chr_param, oob, h->d_freq0, h->d_keep, h->stream));
         // page-locked caller buffers (garlic_gpu_host_alloc) are written by the copy engine directly
         freq_direct = freq_out && is_pinned(freq_out);
@@ -677,6 +724,34 @@ int garlic_gpu_windows_dev(garlic_gpu_t* h, int winsize, int step, int weighted,
 {
     if (!out_dev) return 1;
     return windows_common(h, winsize, step, weighted, individuals, n, exact, nullptr, out_dev);
+}
+
+// Thinned windows of the KDE individuals of ALL shards: this rank computes the windows of its own individuals
+// (n <= rows_per_rank local indices), one ncclAllGather on the library's stream collects every rank's
+// MISSING-padded [rows_per_rank][n_slots] block, and out receives [world*rows_per_rank][n_slots] (rank order).
+int garlic_gpu_windows_gather(garlic_gpu_t* h, int winsize, int step, int weighted, const int32_t* individuals, int n,
+                              int rows_per_rank, int exact, double* out)
+{
+    if (n > rows_per_rank) FAIL("windows_gather: more individuals than rows_per_rank");
+    const int64_t slots = garlic_gpu_window_slots(h, step);
+    if (slots < 0) FAIL("windows_gather: call filter first");
+    void* dptr = nullptr;
+    if (n > 0 && windows_common(h, winsize, step, weighted, individuals, n, exact, nullptr, &dptr)) return 1;
+    CK(cudaSetDevice(h->device));
+    const size_t blk = (size_t)rows_per_rank * slots;
+    if (dev_alloc(h, &h->d_gather, blk * (h->comm_world + 1))) return 1;
+    double* send = h->d_gather + blk * h->comm_world;
+    LAUNCH(launch_fill_f64(send, blk, kMissing, h->stream));
+    if (n > 0) CK(cudaMemcpyAsync(send, dptr, (size_t)n * slots * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (h->comm) NCK(ncclAllGather(send, h->d_gather, blk, ncclDouble, h->comm, h->stream));
+    else CK(cudaMemcpyAsync(h->d_gather, send, blk * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    const size_t bytes = blk * h->comm_world * sizeof(double);
+    const bool direct = is_pinned(out);
+    const bool staged = !direct && bytes <= ((size_t)64 << 20) && !pin_alloc(h, bytes);
+    CK(cudaMemcpyAsync(direct ? (void*)out : (staged ? (void*)h->pin : (void*)out), h->d_gather, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (staged) memcpy(out, h->pin, bytes);
+    return 0;
 }
 
 static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, const int32_t* individuals, int n,

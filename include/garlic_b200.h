@@ -54,6 +54,15 @@ int garlic_gpu_sync(garlic_gpu_t *h);
 void *garlic_gpu_host_alloc(size_t bytes);
 void garlic_gpu_host_free(void *p);
 
+/* ---- multi-GPU: one handle (rank) per GPU, individuals sharded across ranks ---------------
+ * Rank 0 obtains 128 bytes with garlic_gpu_comm_id and hands them to the other ranks by any channel; every
+ * rank then calls garlic_gpu_comm_init.  With a communicator the library performs the path's exchanges itself,
+ * on its own stream, over NCCL: SUM all-reduce of the per-SNP counters inside garlic_gpu_filter, MIN all-reduce
+ * of the first-allele keys inside garlic_gpu_code_alleles, all-gather in garlic_gpu_windows_gather.  Without
+ * one (world = 1) those calls are local and the *_dev accessors below let the caller run the collectives. */
+int garlic_gpu_comm_id(uint8_t *id128);
+int garlic_gpu_comm_init(garlic_gpu_t *h, const uint8_t *id128, int rank, int world);
+
 /* ---- K1: loadTPEDData's coding + allele counting (src/garlic-data.cpp:103-150) -------------
  * n_ind individuals on this GPU starting at global individual ind_offset; n_loci SNPs before
  * filtering; chr_offsets[n_chr+1] into the SNP axis; pos[n_loci] physical positions. */
@@ -133,6 +142,10 @@ int garlic_gpu_windows(garlic_gpu_t *h, int winsize, int step, int weighted, con
  * the device pointer — multi-GPU runs all-gather it before the one copy to the host */
 int garlic_gpu_windows_dev(garlic_gpu_t *h, int winsize, int step, int weighted, const int32_t *individuals,
                            int n, int exact, void **out_dev);
+/* the KDE individuals of ALL ranks: this rank computes its n <= rows_per_rank local individuals, one all-gather
+ * collects every rank's MISSING-padded block; out: [world*rows_per_rank][n_slots] in rank order */
+int garlic_gpu_windows_gather(garlic_gpu_t *h, int winsize, int step, int weighted, const int32_t *individuals,
+                              int n, int rows_per_rank, int exact, double *out);
 
 /* ---- K5 pass 2: calc[w]LODWindows + assembleROHWindows fused (src/garlic-roh.cpp:279-347,409-546)
  * overlap_frac as --overlap-frac. out: capacity cap records, sorted by (ind, chr, start);
