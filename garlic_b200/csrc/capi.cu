@@ -514,7 +514,8 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
         h->gl_stride = L + kPad;
         if (dev_alloc(h, &h->d_gl, (size_t)h->n_ind * h->gl_stride)) return 1;
         CK(cudaMemsetAsync(h->d_gl, 0, (size_t)h->n_ind * h->gl_stride * sizeof(double), h->stream));
-        LAUNCH(launch_compact_gl(h->d_gl0, L0, h->d_src, L, h->d_gl, h->gl_stride, h->n_ind, h->gl_type, h->stream));
+        LAUNCH(launch_compact_gl(h->d_gl0, L0, h->d_src, L, h->d_geno0, h->row_words0, h->d_freq0, h->d_gl, h->gl_stride, h->n_ind,
+                                 h->gl_type, h->stream));
     }
     // per-SNP position / chromosome arrays of the kept SNPs (device-side gathers)
     std::vector<int> chr_start(h->n_chr);

@@ -42,7 +42,7 @@ struct WalkParams {
     const uint64_t* geno;   // packed rows, 32 genotypes per 64-bit word, SNP s at bits 2*(s&31) of word s>>5
     int64_t row_words;      // row stride in 64-bit words (>= ceil(L/32)+2, padded)
     const double* lut;      // [L+pad][4] per-SNP LOD of g=0,1,2,missing (unweighted, global --error)
-    const double* gl;       // [N][gl_stride] per-genotype error, or nullptr
+    const double* gl;       // [N][gl_stride] per-genotype LOD (GL mode: lod() of every genotype, built at compaction), or nullptr
     const double* freq;     // [L] (GL mode)
     int64_t gl_stride;
     const int* ind_list;    // optional indirection: lane k works on individual ind_list[k]

@@ -905,8 +905,9 @@ cudaError_t launch_gather_i32(const int* in, const int* src, long long L, int* o
     return cudaGetLastError();
 }
 
-// GL rows: gather kept columns and apply the GQ/GL/PL → per-genotype error transform
-// (garlic-data.cpp:1555-1577) in the same pass.  type: 0 GQ, 1 GL, 2 PL, -1 = already an error.
+// GL rows: gather kept columns, apply the GQ/GL/PL → per-genotype error transform (garlic-data.cpp:1555-1577) and
+// evaluate lod() of every genotype in the same pass, so that the walker only streams per-genotype LOD values.
+// type: 0 GQ, 1 GL, 2 PL, -1 = already an error.
 __device__ __forceinline__ double gl_to_error(double gl, int type)
 {
     if (type == 0) {
@@ -927,24 +928,30 @@ __device__ __forceinline__ double gl_to_error(double gl, int type)
 }
 
 __global__ void compact_gl_kernel(const double* __restrict__ in, int64_t in_stride, const int* __restrict__ src,
-                                  long long L, double* __restrict__ out, int64_t out_stride, int n_ind, int type)
+                                  long long L, const uint64_t* __restrict__ geno0, int64_t row_words0,
+                                  const double* __restrict__ freq0, double* __restrict__ out, int64_t out_stride,
+                                  int n_ind, int type)
 {
     const long long total = L * n_ind;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(t / L);
         const long long d = t % L;
-        out[(int64_t)i * out_stride + d] = gl_to_error(in[(int64_t)i * in_stride + src[d]], type);
+        const int s = src[d];
+        const int g = (int)(geno0[(int64_t)i * row_words0 + (s >> 5)] >> (2 * (s & 31))) & 3;
+        // per-genotype error (readTGLSData) → per-genotype LOD (lod(), garlic-roh.cpp:355-386), evaluated once here
+        out[(int64_t)i * out_stride + d] = lod_eval(g, freq0[s], gl_to_error(in[(int64_t)i * in_stride + s], type));
     }
 }
 
-cudaError_t launch_compact_gl(const double* in, int64_t in_stride, const int* src, long long L, double* out,
-                              int64_t out_stride, int n_ind, int type, cudaStream_t st)
+cudaError_t launch_compact_gl(const double* in, int64_t in_stride, const int* src, long long L, const uint64_t* geno0,
+                              int64_t row_words0, const double* freq0, double* out, int64_t out_stride, int n_ind, int type,
+                              cudaStream_t st)
 {
     const long long total = L * n_ind;
     if (!total) return cudaSuccess;
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    compact_gl_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, in_stride, src, L, out, out_stride, n_ind, type);
+    compact_gl_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, in_stride, src, L, geno0, row_words0, freq0, out, out_stride, n_ind, type);
     return cudaGetLastError();
 }
 

@@ -46,8 +46,9 @@ cudaError_t launch_keep_scan(const uint8_t* keep, long long L0, const int* chr_o
 cudaError_t launch_bad_pairs(const int* pos, const int* chr_of, const int* cen, int max_gap, long long L, int* list,
                              unsigned* count, unsigned cap, cudaStream_t st);
 cudaError_t launch_gather_i32(const int* in, const int* src, long long L, int* out, cudaStream_t st);
-cudaError_t launch_compact_gl(const double* in, int64_t in_stride, const int* src, long long L, double* out,
-                              int64_t out_stride, int n_ind, int type, cudaStream_t st);
+cudaError_t launch_compact_gl(const double* in, int64_t in_stride, const int* src, long long L, const uint64_t* geno0,
+                              int64_t row_words0, const double* freq0, double* out, int64_t out_stride, int n_ind, int type,
+                              cudaStream_t st);
 cudaError_t launch_gather_f64(const double* in, const int* src, long long L, double* out, cudaStream_t st);
 cudaError_t launch_build_lut(const double* freq, long long L, double error, double* lut, cudaStream_t st);
 cudaError_t launch_wlod_weights(const int* pos, const double* gpos, const int* chr_of, const int* chr_start,

@@ -41,7 +41,7 @@ GHD double lod_eval(int g, double f, double e)
 // Where a lane reads its per-SNP LOD from.  SRC 0: the per-SNP table (4 doubles per SNP: g=0,1,2,missing)
 // seen through `tile`, which holds the entries of SNPs tile_lo, tile_lo+1, … — either the whole table
 // in global memory (tile_lo = 0) or the item's slice staged into shared memory by TMA (kernels.cu).
-// SRC 1: per-genotype error rates (GL mode), lod() evaluated on the fly.
+// SRC 1: per-genotype LOD values (GL mode; lod() of each genotype's own error rate, evaluated at compaction).
 template <int SRC>
 struct LaneCtx {
     const uint64_t* row;
@@ -52,7 +52,7 @@ struct LaneCtx {
     GHD double aval(int s, int g) const
     {
         if (SRC == 0) return *reinterpret_cast<const double*>(tile + ((uint32_t)(s - tile_lo) * 32u + (uint32_t)g * 8u));
-        return lod_eval(g, freq[s], glrow[s]);
+        return glrow[s];   // GL mode: per-genotype LOD, evaluated once by compact_gl_kernel
     }
 };
 

@@ -155,7 +155,7 @@ __device__ __forceinline__ void wlod_walk_item(const WlodParams& Q, const Item& 
                 const int g = (int)(row[s >> 5] >> (2 * (s & 31))) & 3;
                 double sc;
                 if (SRC == 0) sc = Q.wlut[(int64_t)s * 4 + g];
-                else sc = lod_eval(g, P.freq[s], glrow[s]) * Q.nomut[s] * Q.norec[s];
+                else sc = glrow[s] * Q.nomut[s] * Q.norec[s];
                 acc += sc * inv[k];
             }
             f = acc >= P.cutoff;

@@ -142,6 +142,16 @@ double orc_lod(int g, double freq, double error)
     return log10(a / na);
 }
 
+/* per-genotype lod() for per-genotype error rates: out[l][i] = lod(geno[l][i], freq[l], err[l][i]) */
+void orc_lod_matrix(const int8_t *geno, const double *freq, const double *err, int L, int N, double *out)
+{
+    for (int l = 0; l < L; l++)
+        for (int i = 0; i < N; i++) {
+            const size_t k = (size_t)l * N + i;
+            out[k] = orc_lod(geno[k], freq[l], err[k]);
+        }
+}
+
 /* per-SNP table lut[L][4] for a global error rate (what K4 builds on the device) */
 void orc_lod_lut(const double *freq, int L, double error, double *lut)
 {

@@ -96,6 +96,15 @@ def lod_lut(freq, error):
     return lut
 
 
+def lod_matrix(geno, freq, err):
+    """per-genotype lod() for per-genotype error rates: geno int8[L,N], freq[L], err[L,N] → float64[L,N]."""
+    L, N = geno.shape
+    out = np.empty((L, N), np.float64)
+    lib().orc_lod_matrix(_p(np.ascontiguousarray(geno, np.int8)), _p(np.ascontiguousarray(freq, np.float64)),
+                         _p(np.ascontiguousarray(err, np.float64)), C.c_int(L), C.c_int(N), _p(out))
+    return out
+
+
 def calc_lod(geno, freq, pos, W, error, max_gap, cen, gl=None):
     L, N = geno.shape
     win = np.empty((N, L), np.float64)

@@ -94,8 +94,9 @@ def flatten(res, error, use_gl=False):
         lut[:L] = orc.lod_lut(freq[:L], error)
     gl = None
     if use_gl:
+        # GL mode: the product streams per-genotype LOD values (lod() of each genotype's own error rate)
         gl = np.zeros((N, L + PAD))
-        gl[:, :L] = np.concatenate([ch["gl"] for ch in chroms], axis=0).T
+        gl[:, :L] = np.concatenate([orc.lod_matrix(ch["geno"], ch["freq"], ch["gl"]) for ch in chroms], axis=0).T
     return dict(codes=codes, rows=rows, row_words=row_words, chr_off=chr_off, pos=pos, cen=cen, freq=freq,
                 lut=lut, gl=gl, N=N, L=L)
 

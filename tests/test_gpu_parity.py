@@ -264,3 +264,27 @@ def test_full_size_properties_c2_shape():
     key = a[:, 0].astype(np.int64) * (1 << 32) + a[:, 2]
     assert np.all(np.diff(key) > 0)
     hp.close()
+
+
+def test_repeated_runs_are_identical_and_equal_exact_chains():
+    """The same count → filter → tables → call_roh sequence, repeated on one handle, returns identical ROH every
+    time (no race between the stream-ordered phases, pruning pass included) and equals whole-segment chains."""
+    names, offs, pos, cens = synth.make_positions_genomewide(9, 80000)
+    codes = synth.make_codes(9, 300, 80000)
+    rows = synth.pack_codes(codes)
+    hp = HotPath()
+    g = hp.g
+    g.set_shape(300, 80000, offs, pos)
+    g.put_packed(rows)
+    cen = np.array([cens["chr" + n] for n in names], np.int32)
+    outs = []
+    for _ in range(6):
+        g.count_packed()
+        g.filter()
+        g.set_tables(0.001, 200000, cen)
+        outs.append(g.call_roh(50, 2.0, 0.25).copy())
+    st = g.last_stats()
+    assert 0 <= st["candidate_pairs"] < st["all_pairs"]          # the pruning pass ran and pruned
+    assert all(np.array_equal(o, outs[0]) for o in outs) and len(outs[0]) > 100
+    assert np.array_equal(outs[0], g.call_roh(50, 2.0, 0.25, exact=True))
+    hp.close()
