@@ -66,6 +66,8 @@ struct Scaffold { std::string chr; std::vector<int32_t> pos; std::vector<double>
 bool load_map(const std::string& path, std::vector<Scaffold>& s);
 // values individual-major [N][L0]
 bool load_tgls(const std::string& path, const Tped& t, std::vector<double>& values);
+// readFreqData (garlic-data.cpp:1345-1440): CHR SNP POS ALLELE FREQ rows in tped order; 1 - freq where ALLELE is not the tped's "1" allele
+bool load_freq_file(const std::string& path, const Tped& t, const std::vector<uint8_t>& one_allele, std::vector<double>& freq);
 std::string chr_label(const std::string& name);   // checkChrName, garlic-data.cpp:1886-1891
 // centromere table: build = hg18/hg19/hg38 or custom file "<chr> <start> <end>"
 bool load_centromeres(const std::string& build, const std::string& file, std::map<std::string, std::pair<int, int>>& cen);

@@ -201,6 +201,40 @@ bool load_tgls(const std::string& path, const Tped& t, std::vector<double>& v)
     return true;
 }
 
+bool load_freq_file(const std::string& path, const Tped& t, const std::vector<uint8_t>& one, std::vector<double>& freq)
+{
+    GzLines in;
+    if (!in.open(path)) { LOG.error("ERROR: Failed to open " + path); return false; }
+    fprintf(stderr, "Reading %s\n", path.c_str());
+    std::string line;
+    in.next(line);   // header
+    freq.assign(t.n_loci, 0.0);
+    int prev_cols = -1;
+    for (int64_t l = 0; l < t.n_loci; ++l) {
+        const int64_t line_no = l + 2;
+        if (!in.next(line)) { LOG.error("ERROR: at line " + std::to_string(line_no) + " in " + path + ". Perhaps too few lines?"); return false; }
+        const int cols = count_fields(line);
+        if (cols < 5) { LOG.error("ERROR: Found " + std::to_string(cols) + " in " + path + " on line " + std::to_string(line_no) + " but expected at least 5"); return false; }
+        if (cols != prev_cols && prev_cols != -1) { LOG.error("ERROR: Differing number of columns across rows found in " + path); return false; }
+        prev_cols = cols;
+        std::istringstream ss(line);
+        std::string chr, id;
+        double pos, f;
+        char allele;
+        ss >> chr >> id >> pos >> allele >> f;
+        if (id != t.snp_id[l]) {
+            LOG.error("ERROR: Loci appear mismatched in: " + path);
+            LOG.error("ERROR: at line: " + std::to_string(line_no));
+            LOG.error("ERROR: freq file locus name: " + id);
+            LOG.error("ERROR: tped file locus name: " + t.snp_id[l]);
+            return false;
+        }
+        freq[l] = ((uint8_t)allele != one[l]) ? 1 - f : f;
+    }
+    if (in.next(line) && !line.empty()) { LOG.error("ERROR: " + path + " has more rows than the tped file has loci."); return false; }
+    return true;
+}
+
 // class centromere (garlic-centromeres.cpp:3-101): built-in hg18/hg19/hg38 tables or a custom file.
 bool load_centromeres(const std::string& build, const std::string& file, std::map<std::string, std::pair<int, int>>& cen)
 {

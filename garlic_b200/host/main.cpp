@@ -10,6 +10,8 @@
 #include <ctime>
 #include <random>
 
+#include <zlib.h>
+
 #include "../../include/garlic_b200.h"
 #include "garlic_host.h"
 
@@ -90,6 +92,47 @@ double calc_density(const Ctx& c)   // calcDensity, garlic-data.cpp:318-328
     return double(c.L) / length;
 }
 
+// one gz file per chromosome, one line per individual, "NA" for MISSING, 6 significant digits; individuals are
+// streamed in blocks so that the window matrix never exists as a whole
+bool write_raw_lod(Ctx& c, int W)
+{
+    const int C = (int)c.labels.size(), N = c.tped.n_ind;
+    std::vector<gzFile> f(C);
+    for (int ch = 0; ch < C; ++ch) {
+        const std::string fn = c.o.out + "." + c.tfam.pop + "." + c.labels[ch] + ".raw.lod.windows.gz";
+        f[ch] = gzopen(fn.c_str(), "wb");
+        if (!f[ch]) { LOG.error("ERROR: Failed to open " + fn); return false; }
+    }
+    const int64_t slots = garlic_gpu_window_slots(c.g, 1);
+    const int blk = (int)std::max<int64_t>(1, std::min<int64_t>(N, (int64_t)(256 << 20) / (slots * 8)));
+    std::vector<double> m((size_t)blk * slots);
+    std::vector<int32_t> idx(blk);
+    std::string line;
+    for (int i0 = 0; i0 < N; i0 += blk) {
+        const int n = std::min(blk, N - i0);
+        for (int i = 0; i < n; ++i) idx[i] = i0 + i;
+        if (!gpu_ok(c, garlic_gpu_windows(c.g, W, 1, c.o.weighted, idx.data(), n, 1, m.data()), "windows")) return false;
+        for (int ch = 0; ch < C; ++ch) {
+            const int64_t lo = c.chr_off[ch], hi = c.chr_off[ch + 1];
+            for (int i = 0; i < n; ++i) {
+                line.clear();
+                for (int64_t s = lo; s < hi; ++s) {
+                    const double v = m[(size_t)i * slots + s];
+                    if (v == GARLIC_MISSING) line += "NA"; else line += fmt_g(v);
+                    if (s < hi - 1) line += ' ';
+                }
+                line += '\n';
+                gzwrite(f[ch], line.data(), (unsigned)line.size());
+            }
+        }
+    }
+    for (int ch = 0; ch < C; ++ch) {
+        gzclose(f[ch]);
+        fprintf(stderr, "Wrote %s.%s.%s.raw.lod.windows.gz\n", c.o.out.c_str(), c.tfam.pop.c_str(), c.labels[ch].c_str());
+    }
+    return true;
+}
+
 std::string join(const std::vector<double>& v) { std::string s; for (double x : v) s += " " + fmt_g(x); return s; }
 std::string join(const std::vector<int>& v) { std::string s; for (int x : v) s += " " + std::to_string(x); return s; }
 
@@ -134,13 +177,16 @@ int main(int argc, char** argv)
         return -1;
     }
     LOG.line("User defined centromere file: " + o.centromere);
-    if (o.freq_file != "none" || o.freq_only || o.resample > 0 || o.phased || o.raw_lod) {
-        LOG.error("ERROR: --freq-file, --freq-only, --resample, --phased and --raw-lod are not built in this round (DESIGN.md §9).");
+    if (o.resample > 0 || o.phased) {
+        LOG.error("ERROR: --resample and --phased are not built in this round (DESIGN.md §9).");
         return -1;
     }
-    LOG.line("Calculate allele frequencies only: FALSE");
-    LOG.line("Calculate allele frequencies from data: TRUE");
-    LOG.line("Allele frequencies resampled: FALSE");
+    const bool auto_freq = (o.freq_file == "none");
+    if (!auto_freq && o.freq_only) { LOG.error("ERROR: Specifying a frequency file and --freq-only is redundant."); return -1; }
+    LOG.line("Calculate allele frequencies only: " + fmt_bool(o.freq_only));
+    LOG.line("Calculate allele frequencies from data: " + fmt_bool(auto_freq));
+    if (!auto_freq) LOG.line("Allele frequencies file: " + o.freq_file);
+    else LOG.line("Allele frequencies resampled: FALSE");
     bool explore = false;
     if (o.winsize_multi[0] != -1) {
         for (int w : o.winsize_multi)
@@ -253,10 +299,18 @@ int main(int argc, char** argv)
             chr_param.push_back(c.cen_arr[2 * ch]); chr_param.push_back(c.cen_arr[2 * ch + 1]);
         }
     std::vector<double> freq0(t.n_loci);
-    if (!gpu_ok(c, garlic_gpu_filter(c.g, oob, oob ? chr_param.data() : nullptr, nullptr, freq0.data(), nullptr, &c.L), "filter")) return 1;
     std::vector<uint8_t> one(t.n_loci);
     if (!gpu_ok(c, garlic_gpu_get_one_allele(c.g, one.data(), o.tped_missing), "get_one_allele")) return 1;
-    if (!write_freq_gz(o.out + ".freq.gz", t, one, freq0)) return 1;
+    if (!auto_freq) {   // readFreqData (garlic-data.cpp:1345-1440): panel frequencies, flipped where the row names the other allele
+        printf("Loading user provided allele frequencies from %s\n", o.freq_file.c_str());
+        std::vector<double> panel;
+        if (!load_freq_file(o.freq_file, t, one, panel)) return -1;
+        if (!gpu_ok(c, garlic_gpu_filter(c.g, oob, oob ? chr_param.data() : nullptr, panel.data(), freq0.data(), nullptr, &c.L), "filter")) return 1;
+    } else {
+        if (!gpu_ok(c, garlic_gpu_filter(c.g, oob, oob ? chr_param.data() : nullptr, nullptr, freq0.data(), nullptr, &c.L), "filter")) return 1;
+        if (!write_freq_gz(o.out + ".freq.gz", t, one, freq0)) return 1;
+    }
+    if (o.freq_only) { garlic_gpu_destroy(c.g); return 0; }   // freqOnly (garlic-data.cpp:238-315): the .freq.gz is the output
     std::vector<int32_t> src(c.L);
     garlic_gpu_get_kept_index(c.g, src.data());
     c.pos.resize(c.L);
@@ -373,6 +427,9 @@ int main(int argc, char** argv)
         garlic_gpu_set_wlod(c.g, o.mu, o.M);
         if (!gpu_ok(c, garlic_gpu_ld_band(c.g, winsize, ld.empty() ? nullptr : ld.data(), (int)ld.size(), nullptr), "ld_band")) return 1;
     }
+
+    // ---- --raw-lod: every window of every individual (writeWinData, garlic-data.cpp:1704-1747) ----
+    if (o.raw_lod && !write_raw_lod(c, winsize)) return -1;
 
     // ---- pass 1: thinned windows → KDE → cutoff (host, FIGTree) ----
     if (auto_cutoff) {

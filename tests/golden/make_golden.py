@@ -42,7 +42,12 @@ def save_dataset(ds, path):
     np.savez_compressed(path, **d)
 
 
-def run_case(name, ds, args, build=None, raw=False, keep_kde=False):
+ONLY = set(sys.argv[1:])     # optional: names of the cases to (re)generate
+
+
+def run_case(name, ds, args, build=None, raw=False, keep_kde=False, freq_text=None):
+    if ONLY and name not in ONLY:
+        return
     cdir = os.path.join(OUT, name)
     if os.path.isdir(cdir):
         shutil.rmtree(cdir)
@@ -60,12 +65,19 @@ def run_case(name, ds, args, build=None, raw=False, keep_kde=False):
             cmd += ["--tgls", p["tgls"], "--gl-type", ds.gl_type]
         if raw:
             cmd += ["--raw-lod"]
+        if freq_text is not None:
+            with open(os.path.join(tmp, "syn.freq"), "w") as f:
+                f.write(freq_text)
+            cmd += ["--freq-file", os.path.join(tmp, "syn.freq")]
         cmd += args
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             print(r.stdout[-2000:], r.stderr[-2000:])
             raise SystemExit("reference failed for " + name)
         save_dataset(ds, os.path.join(cdir, "data.npz"))
+        if freq_text is not None:
+            with open(os.path.join(cdir, "in.freq"), "w") as f:
+                f.write(freq_text)
         shown = [a.replace(tmp, "<tmp>") for a in cmd]
         with open(os.path.join(cdir, "cmd.txt"), "w") as f:
             f.write(" ".join(shown) + "\n")
@@ -134,6 +146,29 @@ def main():
     ds = synth.make_dataset(seed=17, n_ind=24, chr_sizes=(3000, 2500), n_roh=6)
     run_case("winsize_multi", ds, ["--winsize-multi", "20", "30", "40", "--auto-winsize", "--error", "0.001",
                                   "--kde-subsample", "0"] + SB, keep_kde=True)
+    # 8. --freq-file: frequencies from a "panel" (differ from the sample's), 30 % of the rows name the other allele
+    #    (the program must flip them, garlic-data.cpp:1422), a few rows are 0 / 1 (filtered although polymorphic here)
+    ds = synth.make_dataset(seed=18, n_ind=20, chr_sizes=(2000, 1500))
+    from oracle import oracle as orc
+    geno, na, tot, one, freq = orc.code_tped(ds.alleles)
+    rng = np.random.default_rng(18)
+    panel = np.clip(freq + rng.normal(0, 0.05, len(freq)), 0.0, 1.0)
+    panel[rng.random(len(freq)) < 0.01] = 0.0
+    flip = rng.random(len(freq)) < 0.3
+    lines = ["CHR\tSNP\tPOS\tALLELE\tFREQ"]
+    c = 0
+    for l in range(ds.n_loci):
+        while l >= ds.chr_offsets[c + 1]:
+            c += 1
+        a = one[l]
+        f = panel[l]
+        if flip[l]:
+            others = [x for x in np.unique(ds.alleles[l]) if x != a and x != ord("0")]
+            a = others[0] if others else ord("N")
+            f = 1 - f
+        lines.append("chr%s\t%s\t%d\t%s\t%s" % (ds.chr_names[c], ds.snp_ids[l], ds.pos[l], chr(a), "%g" % f))
+    run_case("freq_file", ds, ["--winsize", "40", "--error", "0.001", "--lod-cutoff", "2.0"] + SB,
+             freq_text="\n".join(lines) + "\n")
 
 
 if __name__ == "__main__":

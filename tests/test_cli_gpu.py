@@ -19,12 +19,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "garlic_b200", "host", "garlic_b200")
 
 CASES = ["lod_0", "lod_1", "lod_2", "lod_3", "lod_small", "lod_cm", "wlod_cm", "gl_pl", "gl_gl", "gl_gq",
-         "auto_overlap_hg19", "auto_cutoff", "winsize_multi"]
+         "auto_overlap_hg19", "auto_cutoff", "winsize_multi", "freq_file"]
 
 
 def run_cli(name, tmp, extra=()):
     ds, args = load_case(name)
     ds.write(tmp)
+    if os.path.exists(os.path.join(GOLDEN, name, "in.freq")):
+        with open(os.path.join(GOLDEN, name, "in.freq")) as f, open(os.path.join(tmp, "syn.freq"), "w") as g:
+            g.write(f.read())
     with open(os.path.join(GOLDEN, name, "cmd.txt")) as f:
         cmd = f.readline().split()[1:]
     cmd = [a.replace("<tmp>", tmp) for a in cmd if a != "--raw-lod"]
@@ -51,7 +54,10 @@ def test_cli_outputs_match_reference_binary(name):
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         out = os.path.join(tmp, "out")
         assert open(out + ".roh.bed").read() == golden_text(name, "out.roh.bed")
-        assert gzip.open(out + ".freq.gz", "rt").read() == golden_text(name, "out.freq")
+        if os.path.exists(os.path.join(GOLDEN, name, "out.freq")):
+            assert gzip.open(out + ".freq.gz", "rt").read() == golden_text(name, "out.freq")
+        else:
+            assert not os.path.exists(out + ".freq.gz")      # --freq-file: no .freq.gz is written
         log = open(out + ".log").read()
         # the whole log is the reference's, line for line (paths differ)
         ref_lines = [l for l in golden_text(name, "out.log").splitlines()[1:] if "<tmp>" not in l and "raw LOD" not in l]
@@ -110,6 +116,38 @@ def test_cli_auto_cutoff_path(name):
             else:
                 assert a_.split("\t")[:3] == b_.split("\t")[:3]
             k += 1
+
+
+@pytest.mark.parametrize("name", ["lod_small", "gl_pl", "wlod_cm"])
+def test_cli_raw_lod(name):
+    """--raw-lod: one gz file per chromosome, a line per individual, NA for MISSING, 6 significant digits — compared
+    with the reference binary's own dump (tests/golden/*/rawlod.npz)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        ds, args, r = run_cli(name, tmp, extra=["--raw-lod"])
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        raw = np.load(os.path.join(GOLDEN, name, "rawlod.npz"))
+        for c, nm in enumerate(ds.chr_names):
+            lab = nm if nm[0] == "c" else "chr" + nm
+            fn = os.path.join(tmp, "out.%s.%s.raw.lod.windows.gz" % (ds.pop, lab))
+            rows = [[np.nan if t == "NA" else float(t) for t in line.split()] for line in gzip.open(fn, "rt")]
+            got = np.array(rows, np.float64)
+            want = raw["chr%d" % c]
+            assert got.shape == want.shape
+            assert np.array_equal(np.isnan(got), np.isnan(want))
+            ok = ~np.isnan(want)
+            assert np.allclose(got[ok], want[ok], rtol=3e-6, atol=1e-12)      # both printed with 6 digits
+        assert open(os.path.join(tmp, "out.roh.bed")).read() == golden_text(name, "out.roh.bed")
+
+
+def test_cli_freq_only():
+    with tempfile.TemporaryDirectory() as tmp:
+        ds, args = load_case("lod_small")
+        p = ds.write(tmp)
+        r = subprocess.run([BIN, "--tped", p["tped"], "--tfam", p["tfam"], "--centromere", p["centromere"], "--out",
+                            os.path.join(tmp, "f"), "--freq-only", "--winsize", "30", "--error", "0.001"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-1000:]
+        assert gzip.open(os.path.join(tmp, "f.freq.gz"), "rt").read() == golden_text("lod_small", "out.freq")
+        assert not os.path.exists(os.path.join(tmp, "f.roh.bed"))
 
 
 def test_cli_exact_mode_and_errors():
