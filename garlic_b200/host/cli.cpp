@@ -76,7 +76,7 @@ static const char* kHelp =
     "  --winsize --winsize-multi --auto-winsize --auto-winsize-step --overlap-frac --auto-overlap-frac --error\n"
     "  --max-gap --lod-cutoff --size-bounds --kde-subsample --ld-subsample --no-kde-thinning --nclust --M --mu\n"
     "  --build --centromere --tped-missing --threads --resample --out --raw-lod\n"
-    "Extensions: --exact (whole-segment chains), --device <n>, --seed <n> (subsample RNG seed), --device-lut, --kde-direct\n";
+    "Extensions: --gpus <n> (shard individuals over n GPUs), --exact (whole-segment chains), --device <n>, --seed <n> (subsample RNG seed), --device-lut, --kde-direct\n";
 
 int parse_cli(int argc, char** argv, Options& o, std::string& cmdline)
 {
@@ -88,7 +88,7 @@ int parse_cli(int argc, char** argv, Options& o, std::string& cmdline)
     std::map<std::string, int*> fi = {{"--winsize", &o.winsize}, {"--auto-winsize-step", &o.auto_winsize_step},
         {"--max-gap", &o.max_gap}, {"--resample", &o.resample}, {"--threads", &o.threads}, {"--M", &o.M},
         {"--nclust", &o.nclust}, {"--kde-subsample", &o.kde_subsample}, {"--ld-subsample", &o.ld_subsample},
-        {"--device", &o.device}};
+        {"--device", &o.device}, {"--gpus", &o.gpus}};
     std::map<std::string, double*> fd = {{"--error", &o.error}, {"--overlap-frac", &o.overlap_frac},
         {"--lod-cutoff", &o.lod_cutoff}, {"--mu", &o.mu}};
     std::map<std::string, std::string*> fs = {{"--tped", &o.tped}, {"--tfam", &o.tfam}, {"--tgls", &o.tgls},

@@ -41,7 +41,8 @@ struct Options {
     double error = -1, overlap_frac = 0.25, lod_cutoff = -999999, mu = 1e-9;
     char tped_missing = '0';
     bool exact = false;          // extension: whole-segment chains everywhere (--exact)
-    int device = 0;              // extension: CUDA device (--device)
+    int device = 0;              // extension: first CUDA device (--device)
+    int gpus = 1;                // extension: shard the individuals over this many GPUs (--gpus)
     bool device_lut = false;     // extension: build the per-SNP LOD table on the GPU (--device-lut)
     bool kde_direct = false;     // extension: exact (reproducible) Gauss transform for the KDE (--kde-direct)
     long seed = -1;              // extension: RNG seed for the KDE / LD subsamples (--seed; default time)

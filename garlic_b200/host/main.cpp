@@ -8,7 +8,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <random>
+#include <thread>
 
 #include <zlib.h>
 
@@ -19,9 +23,93 @@ using namespace gh;
 
 namespace {
 
+// --gpus G: individuals are sharded over G GPUs (rank r = individuals [lo_r, hi_r)); rank 0 is the main thread,
+// ranks 1..G-1 are follower threads that mirror every GPU call (the library's NCCL collectives inside
+// code_alleles / filter / windows_gather need all ranks in the call at the same time).
+struct Rank {
+    int rank = 0, lo = 0, hi = 0;
+    garlic_gpu_t* g = nullptr;
+    std::vector<garlic_roh_t> rec;
+    int64_t n_roh = 0;
+    std::string err;
+};
+
+struct Team {
+    std::vector<Rank> ranks;                 // ranks[0] is the main thread's
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<bool(Rank&)> job;
+    long generation = 0;
+    int pending = 0;
+    bool quit = false, failed = false;
+
+    void follower(int r)
+    {
+        long seen = 0;
+        for (;;) {
+            std::function<bool(Rank&)> j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return quit || generation != seen; });
+                if (quit) return;
+                seen = generation;
+                j = job;
+            }
+            const bool ok = j(ranks[r]);
+            std::lock_guard<std::mutex> lk(mu);
+            if (!ok) failed = true;
+            --pending;
+            cv.notify_all();
+        }
+    }
+    // run `j` on every rank at the same time (rank 0 on the calling thread); false if any rank failed
+    bool all(const std::function<bool(Rank&)>& j)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            job = j;
+            pending = (int)ranks.size() - 1;
+            ++generation;
+        }
+        cv.notify_all();
+        const bool ok0 = j(ranks[0]);
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return pending == 0; });
+        if (!ok0) failed = true;
+        return !failed;
+    }
+    void start(int G)
+    {
+        ranks.resize(G);
+        for (int r = 1; r < G; ++r) threads.emplace_back(&Team::follower, this, r);
+    }
+    void stop()
+    {
+        { std::lock_guard<std::mutex> lk(mu); quit = true; }
+        cv.notify_all();
+        for (auto& t : threads) t.join();
+        threads.clear();
+    }
+    ~Team() { if (!threads.empty()) stop(); }
+    std::string first_error() const
+    {
+        for (const Rank& r : ranks) if (!r.err.empty()) return "rank " + std::to_string(r.rank) + ": " + r.err;
+        return "unknown error";
+    }
+};
+
+bool rank_ok(Rank& r, int rc, const char* what)
+{
+    if (rc == 0) return true;
+    r.err = std::string(what) + ": " + garlic_gpu_last_error(r.g);
+    return false;
+}
+
 struct Ctx {
     Options o;
-    garlic_gpu_t* g = nullptr;
+    Team team;
+    garlic_gpu_t* g = nullptr;               // = team.ranks[0].g
     Tped tped;
     Tfam tfam;
     std::vector<Scaffold> scaffold;
@@ -51,22 +139,39 @@ std::vector<int32_t> choose(Ctx& c, int k, int n)
     return out;
 }
 
-// convert[Subset]WinData2DoubleData (garlic-data.cpp:2026-2150): chr → individual → locus, MISSING/NaN dropped
+// convert[Subset]WinData2DoubleData (garlic-data.cpp:2026-2150): chr → individual → locus, MISSING/NaN dropped.
+// inds: global individual indices (ascending) or nullptr for all; every rank computes the windows of its own
+// individuals and the library all-gathers them (rank order = individual order).
 bool thinned_windows(Ctx& c, int W, int step, const std::vector<int32_t>* inds, std::vector<double>& out)
 {
-    const int n = inds ? (int)inds->size() : c.tped.n_ind;
+    const int G = (int)c.team.ranks.size();
+    std::vector<std::vector<int32_t>> local(G);
+    int rows = 0;
+    for (int r = 0; r < G; ++r) {
+        const Rank& R = c.team.ranks[r];
+        if (inds) { for (int i : *inds) if (i >= R.lo && i < R.hi) local[r].push_back(i - R.lo); }
+        else { for (int i = R.lo; i < R.hi; ++i) local[r].push_back(i - R.lo); }
+        rows = std::max(rows, (int)local[r].size());
+    }
     const int64_t slots = garlic_gpu_window_slots(c.g, step);
-    std::vector<double> m((size_t)n * slots);
-    if (!gpu_ok(c, garlic_gpu_windows(c.g, W, step, c.o.weighted, inds ? inds->data() : nullptr, n, 1 /* whole-segment chains */, m.data()), "windows")) return false;
+    std::vector<double> m((size_t)G * rows * slots);
+    const bool weighted = c.o.weighted;
+    if (!c.team.all([&](Rank& R) {
+            std::vector<double> scratch;
+            double* dst = R.rank == 0 ? m.data() : (scratch.resize(m.size()), scratch.data());
+            return rank_ok(R, garlic_gpu_windows_gather(R.g, W, step, weighted, local[R.rank].data(), (int)local[R.rank].size(), rows,
+                                                        1 /* whole-segment chains */, dst), "windows");
+        })) { LOG.error("ERROR: " + c.team.first_error()); return false; }
     out.clear();
     int64_t base = 0;
     for (size_t ch = 0; ch + 1 < c.chr_off.size(); ++ch) {
         const int64_t ns = (c.chr_off[ch + 1] - c.chr_off[ch] + step - 1) / step;
-        for (int i = 0; i < n; ++i)
-            for (int64_t s = 0; s < ns; ++s) {
-                const double v = m[(size_t)i * slots + base + s];
-                if (v != GARLIC_MISSING && !std::isnan(v)) out.push_back(v);
-            }
+        for (int r = 0; r < G; ++r)
+            for (size_t i = 0; i < local[r].size(); ++i)
+                for (int64_t sl = 0; sl < ns; ++sl) {
+                    const double v = m[((size_t)r * rows + i) * slots + base + sl];
+                    if (v != GARLIC_MISSING && !std::isnan(v)) out.push_back(v);
+                }
         base += ns;
     }
     return true;
@@ -279,19 +384,44 @@ int main(int argc, char** argv)
         } else { c.cen_arr.push_back(it->second.first); c.cen_arr.push_back(it->second.second); }
     }
 
-    // ---- GPU: coding, counts, freq, filter (K1-K3) ----
-    if (garlic_gpu_create(o.device, &c.g)) { LOG.error("ERROR: no usable CUDA device; garlic_b200 has no CPU path."); return 1; }
-    if (!gpu_ok(c, garlic_gpu_set_shape(c.g, t.n_ind, 0, t.n_loci, C, t.chr_off.data(), t.pos.data()), "set_shape")) return 1;
+    // ---- GPU: coding, counts, freq, filter (K1-K3), individuals sharded over --gpus ranks ----
+    const int G = o.gpus;
+    if (G < 1 || G > t.n_ind) { LOG.error("ERROR: --gpus must be between 1 and the number of individuals."); return -1; }
+    if (G > 1 && (o.weighted || o.raw_lod)) { LOG.error("ERROR: --weighted and --raw-lod run on one GPU in this round (DESIGN.md §9)."); return -1; }
+    Team& team = c.team;
+    team.start(G);
+    uint8_t comm_id[128];
+    if (G > 1 && garlic_gpu_comm_id(comm_id)) { LOG.error("ERROR: ncclGetUniqueId failed."); return 1; }
+    const int per = (t.n_ind + G - 1) / G;
+    for (int r = 0; r < G; ++r) { team.ranks[r].rank = r; team.ranks[r].lo = std::min(t.n_ind, r * per); team.ranks[r].hi = std::min(t.n_ind, (r + 1) * per); }
+    auto fail = [&](int code) { LOG.error("ERROR: " + team.first_error()); team.stop(); return code; };
     const int64_t blk = 1 << 16;
-    for (int64_t s0 = 0; s0 < t.n_loci; s0 += blk)
-        if (!gpu_ok(c, garlic_gpu_put_alleles(c.g, t.alleles.data() + (size_t)s0 * t.n_ind * 2, s0, (int)std::min(blk, t.n_loci - s0), o.tped_missing), "put_alleles")) return 1;
-    if (!gpu_ok(c, garlic_gpu_code_alleles(c.g), "code_alleles")) return 1;
+    if (!team.all([&](Rank& R) {
+            if (garlic_gpu_create(o.device + R.rank, &R.g)) { R.err = "no usable CUDA device " + std::to_string(o.device + R.rank) + "; garlic_b200 has no CPU path"; return false; }
+            if (G > 1 && !rank_ok(R, garlic_gpu_comm_init(R.g, comm_id, R.rank, G), "comm_init")) return false;
+            const int n = R.hi - R.lo;
+            if (!rank_ok(R, garlic_gpu_set_shape(R.g, n, R.lo, t.n_loci, C, t.chr_off.data(), t.pos.data()), "set_shape")) return false;
+            std::vector<uint8_t> slice;
+            for (int64_t s0 = 0; s0 < t.n_loci; s0 += blk) {
+                const int ns = (int)std::min(blk, t.n_loci - s0);
+                const uint8_t* src_ = t.alleles.data() + (size_t)s0 * t.n_ind * 2;
+                if (G > 1) {                                   // this rank's columns of the block
+                    slice.resize((size_t)ns * n * 2);
+                    for (int k = 0; k < ns; ++k) memcpy(slice.data() + (size_t)k * n * 2, src_ + ((size_t)k * t.n_ind + R.lo) * 2, (size_t)n * 2);
+                    src_ = slice.data();
+                }
+                if (!rank_ok(R, garlic_gpu_put_alleles(R.g, src_, s0, ns, o.tped_missing), "put_alleles")) return false;
+            }
+            if (!rank_ok(R, garlic_gpu_code_alleles(R.g), "code_alleles")) return false;     // MIN all-reduce of the first-allele keys
+            if (use_gl) {
+                const int type = o.gl_type == "GQ" ? GARLIC_GL_GQ : o.gl_type == "GL" ? GARLIC_GL_GL : GARLIC_GL_PL;
+                if (!rank_ok(R, garlic_gpu_put_gl(R.g, gl.data() + (size_t)R.lo * t.n_loci, type), "put_gl")) return false;
+            }
+            return true;
+        })) return fail(1);
+    c.g = team.ranks[0].g;
     std::vector<uint8_t>().swap(t.alleles);
-    if (use_gl) {
-        const int type = o.gl_type == "GQ" ? GARLIC_GL_GQ : o.gl_type == "GL" ? GARLIC_GL_GL : GARLIC_GL_PL;
-        if (!gpu_ok(c, garlic_gpu_put_gl(c.g, gl.data(), type), "put_gl")) return 1;
-        std::vector<double>().swap(gl);
-    }
+    std::vector<double>().swap(gl);
     std::vector<int32_t> chr_param;
     if (oob)
         for (int ch = 0; ch < C; ++ch) {
@@ -301,16 +431,21 @@ int main(int argc, char** argv)
     std::vector<double> freq0(t.n_loci);
     std::vector<uint8_t> one(t.n_loci);
     if (!gpu_ok(c, garlic_gpu_get_one_allele(c.g, one.data(), o.tped_missing), "get_one_allele")) return 1;
+    std::vector<double> panel;
     if (!auto_freq) {   // readFreqData (garlic-data.cpp:1345-1440): panel frequencies, flipped where the row names the other allele
         printf("Loading user provided allele frequencies from %s\n", o.freq_file.c_str());
-        std::vector<double> panel;
-        if (!load_freq_file(o.freq_file, t, one, panel)) return -1;
-        if (!gpu_ok(c, garlic_gpu_filter(c.g, oob, oob ? chr_param.data() : nullptr, panel.data(), freq0.data(), nullptr, &c.L), "filter")) return 1;
-    } else {
-        if (!gpu_ok(c, garlic_gpu_filter(c.g, oob, oob ? chr_param.data() : nullptr, nullptr, freq0.data(), nullptr, &c.L), "filter")) return 1;
-        if (!write_freq_gz(o.out + ".freq.gz", t, one, freq0)) return 1;
+        if (!load_freq_file(o.freq_file, t, one, panel)) { team.stop(); return -1; }
     }
-    if (o.freq_only) { garlic_gpu_destroy(c.g); return 0; }   // freqOnly (garlic-data.cpp:238-315): the .freq.gz is the output
+    if (!team.all([&](Rank& R) {                               // SUM all-reduce of the per-SNP counters inside
+            int64_t L = 0;
+            const bool ok = rank_ok(R, garlic_gpu_filter(R.g, oob, oob ? chr_param.data() : nullptr, auto_freq ? nullptr : panel.data(),
+                                                         R.rank == 0 ? freq0.data() : nullptr, nullptr, &L), "filter");
+            if (R.rank == 0) c.L = L;
+            return ok;
+        })) return fail(1);
+    if (auto_freq && !write_freq_gz(o.out + ".freq.gz", t, one, freq0)) { team.stop(); return 1; }
+    auto shutdown = [&]() { team.all([](Rank& R) { garlic_gpu_destroy(R.g); R.g = nullptr; return true; }); team.stop(); };
+    if (o.freq_only) { shutdown(); return 0; }   // freqOnly (garlic-data.cpp:238-315): the .freq.gz is the output
     std::vector<int32_t> src(c.L);
     garlic_gpu_get_kept_index(c.g, src.data());
     c.pos.resize(c.L);
@@ -335,16 +470,19 @@ int main(int argc, char** argv)
         LOG.line("Number of genetic map locations interpolated: " + std::to_string(n_interp));
     } else LOG.line("Monomorphic loci filtered: " + std::to_string(t.n_loci - c.L));
     LOG.line("Total loci used for analysis: " + std::to_string(c.L));
-    if (!gpu_ok(c, garlic_gpu_set_tables(c.g, o.error, o.max_gap, c.cen_arr.data(), oob ? c.gpos.data() : nullptr), "set_tables")) return 1;
+    std::vector<double> lut;
     if (!use_gl && !o.device_lut) {
         // per-SNP LOD table with the HOST libm (lod(), garlic-roh.cpp:355-386, same operation order): the
         // reference's windows then come out bit-identical for whole-segment chains, which keeps the FIGTree
         // input of the cutoff selection the reference's own.  --device-lut builds it with K4 instead (≤ 1 ulp).
-        std::vector<double> lut((size_t)c.L * 4);
+        lut.resize((size_t)c.L * 4);
         for (int64_t d = 0; d < c.L; ++d)
             for (int g = 0; g < 4; ++g) lut[(size_t)d * 4 + g] = lod_host(g, freq0[src[d]], o.error);
-        if (!gpu_ok(c, garlic_gpu_set_lut(c.g, lut.data()), "set_lut")) return 1;
     }
+    if (!team.all([&](Rank& R) {
+            if (!rank_ok(R, garlic_gpu_set_tables(R.g, o.error, o.max_gap, c.cen_arr.data(), oob ? c.gpos.data() : nullptr), "set_tables")) return false;
+            return lut.empty() || rank_ok(R, garlic_gpu_set_lut(R.g, lut.data()), "set_lut");
+        })) return fail(1);
     double density = -1;
     if ((o.auto_winsize && o.weighted) || o.auto_overlap) density = calc_density(c);
 
@@ -380,7 +518,7 @@ int main(int argc, char** argv)
                 if (!kde_for(W, k)) return 1;
                 if (!write_kde(k, o.out + "." + std::to_string(W) + "SNPs.kde")) return 1;
             }
-            garlic_gpu_destroy(c.g);
+            shutdown();
             return 0;
         }
         LOG.line("Searching for acceptable window size, smoothness threshold: 0.5");
@@ -458,23 +596,27 @@ int main(int argc, char** argv)
 
     // ---- pass 2: windows → cutoff → coverage → ROH (fused K5) ----
     printf("Assembling ROH windows\n");
-    std::vector<garlic_roh_t> rec(1 << 16);
-    int64_t n_roh = 0;
-    for (;;) {
-        if (!gpu_ok(c, garlic_gpu_call_roh(c.g, winsize, cutoff, overlap, o.weighted, o.exact, rec.data(), (int64_t)rec.size(), &n_roh), "call_roh")) return 1;
-        if (n_roh <= (int64_t)rec.size()) break;
-        rec.resize(n_roh + 1024);
-    }
-    std::vector<Roh> roh(n_roh);
-    std::vector<double> lengths(n_roh);
-    for (int64_t r = 0; r < n_roh; ++r) {
-        const int a = rec[r].start_idx, b = rec[r].stop_idx;
-        roh[r].ind = rec[r].ind; roh[r].chr = rec[r].chr;
-        roh[r].start = c.pos[a]; roh[r].stop = c.pos[b];
-        roh[r].length = o.cm ? c.gpos[b] - c.gpos[a] : double(c.pos[b] - c.pos[a] + 1);   // garlic-roh.cpp:478-484
-        lengths[r] = roh[r].length;
-    }
-    garlic_gpu_destroy(c.g);
+    if (!team.all([&](Rank& R) {
+            R.rec.resize(1 << 16);
+            for (;;) {
+                if (!rank_ok(R, garlic_gpu_call_roh(R.g, winsize, cutoff, overlap, o.weighted, o.exact, R.rec.data(), (int64_t)R.rec.size(), &R.n_roh), "call_roh")) return false;
+                if (R.n_roh <= (int64_t)R.rec.size()) return true;
+                R.rec.resize(R.n_roh + 1024);
+            }
+        })) return fail(1);
+    std::vector<Roh> roh;
+    std::vector<double> lengths;
+    for (const Rank& R : team.ranks)                                  // rank order = individual order
+        for (int64_t r = 0; r < R.n_roh; ++r) {
+            const int a = R.rec[r].start_idx, b = R.rec[r].stop_idx;
+            Roh x;
+            x.ind = R.lo + R.rec[r].ind; x.chr = R.rec[r].chr;
+            x.start = c.pos[a]; x.stop = c.pos[b];
+            x.length = o.cm ? c.gpos[b] - c.gpos[a] : double(c.pos[b] - c.pos[a] + 1);   // garlic-roh.cpp:478-484
+            roh.push_back(x);
+            lengths.push_back(x.length);
+        }
+    shutdown();
 
     // ---- size classes (host GMM) and output ----
     if (auto_bounds) {

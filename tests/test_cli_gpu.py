@@ -87,7 +87,9 @@ def test_cli_auto_cutoff_path(name):
         assert np.max(np.abs(got[:, 1] - want[:, 1])) <= 0.02 * want[:, 1].max()    # FIGTree ε = 1e-2, two runs
         cut = float(r.stdout.split("(17 digits): ")[1].split()[0])
         step = want[1, 0] - want[0, 0]
-        assert abs(cut - float(log_value(name, "Selected LOD score cutoff:"))) <= 2.01 * step
+        # the reference binary's own cutoff over 8 runs of this input spans 5 grid points (winsize_multi:
+        # -2.03 … -1.17, spacing 0.214; auto_cutoff: -2.45 / -2.29), so "equal" means within that spread
+        assert abs(cut - float(log_value(name, "Selected LOD score cutoff:"))) <= 4.01 * step
         if name == "winsize_multi":
             ref = [l.split() for l in golden_text(name, "out.log").splitlines() if l.startswith(" ")]
             mine = [l.split() for l in log.splitlines() if l.startswith(" ")]
@@ -148,6 +150,82 @@ def test_cli_freq_only():
         assert r.returncode == 0, r.stderr[-1000:]
         assert gzip.open(os.path.join(tmp, "f.freq.gz"), "rt").read() == golden_text("lod_small", "out.freq")
         assert not os.path.exists(os.path.join(tmp, "f.roh.bed"))
+
+
+def _py_kde_cutoff(data, W):
+    """Restatement of computeKDE (exact Gauss transform, FIGTree's exp(-(t-x)^2/h^2) kernel) + get_min_btw_modes
+    (garlic-kde.cpp:14-234) for the deterministic --kde-direct check."""
+    x = np.sort(np.asarray(data, np.float64))
+    n = len(x)
+    sd = np.std(x, ddof=1)
+
+    def q(f):
+        idx = f * (n - 1)
+        lo = int(idx)
+        d = idx - lo
+        return x[lo] if lo == n - 1 else (1 - d) * x[lo] + d * x[lo + 1]
+    h = 0.9 * min(sd, (q(0.75) - q(0.25)) / 1.34) * n ** -0.2
+    mn, mx = x[0] - 3 * h, x[-1] + 3 * h
+    t = (np.arange(1, 513) / 512.0) * (mx - mn) + mn
+    y = np.array([np.exp(-((ti - x) / h) ** 2).sum() / n for ti in t])
+    y /= y.sum() * (t[1] - t[0])
+    size, win = 512, 20
+    m = size - win
+    umax, ucnt, index = np.zeros(m), np.zeros(m), 0
+    for i in range(m):
+        seg = y[i:i + win]
+        mxv = seg[np.argmax(seg)] if seg.max() > np.finfo(float).tiny else y[i - 1]
+        if i == 1:
+            umax[i] = mxv
+            ucnt[i] += 1
+        elif umax[index] == mxv:
+            ucnt[index] += 1
+        else:
+            index += 1
+            umax[index] = mxv
+            ucnt[index] += 1
+    c1, c2 = int(ucnt[0]), 0
+    for i in range(1, m):
+        if c1 <= ucnt[i]:
+            c2, c1 = c1, int(ucnt[i])
+        elif c2 <= ucnt[i]:
+            c2 = int(ucnt[i])
+    vals = [umax[i] for i in range(m) if ucnt[i] == c1 or ucnt[i] == c2]
+    first = second = -1.0
+    for v in vals:
+        if first <= v:
+            second, first = first, v
+        elif second <= v:
+            second = v
+    li = ri = -1
+    for i in range(size):
+        if y[i] == first:
+            li = i
+        if y[i] == second:
+            ri = i
+    if ri < li:
+        li, ri = ri, li
+    mi = int(np.argmin(y[li:ri + 1])) + li
+    return (t[mi] if abs(t[mi] / W) < 1 else 0.0), t, y
+
+
+def test_cli_kde_direct_is_deterministic_and_matches_restatement():
+    """--kde-direct (FIGTree's exact evaluation): the .kde file and the selected cutoff are reproducible and equal a
+    Python restatement of nrd0 / grid / normalisation / minimum-between-modes on the oracle's thinned windows."""
+    from oracle import oracle as orc
+    ds, args = load_case("auto_cutoff")
+    res = orc.run_pipeline(ds, 30, 0.001, None, thin_step=30)
+    want_cut, t, y = _py_kde_cutoff(res["thinned"], 30)
+    cuts = []
+    for _ in range(2):
+        with tempfile.TemporaryDirectory() as tmp:
+            _, _, r = run_cli("auto_cutoff", tmp, extra=["--kde-direct"])
+            assert r.returncode == 0, r.stderr[-1500:]
+            cuts.append(float(r.stdout.split("(17 digits): ")[1].split()[0]))
+            got = np.loadtxt(os.path.join(tmp, "out.30SNPs.kde"))
+            assert np.allclose(got[:, 0], t, rtol=1e-5) and np.allclose(got[:, 1], y, rtol=2e-5, atol=1e-9)
+    assert cuts[0] == cuts[1]
+    assert abs(cuts[0] - want_cut) <= 1e-9 * max(1.0, abs(want_cut))
 
 
 def test_cli_exact_mode_and_errors():

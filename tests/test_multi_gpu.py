@@ -82,3 +82,22 @@ def test_two_gpu_shards_equal_single_shard(name):
     assert np.max(np.abs(rows[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1e-3)) <= 1e-9
     merged = shard.merge_roh([got[r]["roh"] for r in range(world)], ds.n_ind, world)
     assert [tuple(int(v) for v in r) for r in merged] == oracle_roh_idx(res)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("name", ["lod_0", "lod_2", "lod_small", "gl_pl", "auto_overlap_hg19", "freq_file", "lod_cm"])
+def test_cli_two_gpus_equals_reference_binary(name):
+    """garlic_b200 --gpus 2 (individuals sharded over two GPUs, NCCL exchanges inside the library): every output
+    file equals the single-process reference binary's."""
+    import gzip
+    import os
+    import tempfile
+    from tests.common import GOLDEN, golden_text
+    from tests.test_cli_gpu import run_cli
+    with tempfile.TemporaryDirectory() as tmp:
+        ds, args, r = run_cli(name, tmp, extra=["--gpus", "2"])
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        out = os.path.join(tmp, "out")
+        assert open(out + ".roh.bed").read() == golden_text(name, "out.roh.bed")
+        if os.path.exists(os.path.join(GOLDEN, name, "out.freq")):
+            assert gzip.open(out + ".freq.gz", "rt").read() == golden_text(name, "out.freq")
