@@ -78,6 +78,7 @@ struct garlic_gpu {
     int* d_cand_list = nullptr;
     unsigned* d_cand_cnt = nullptr;
     bool prune = true;             // GARLIC_NO_PRUNE=1 disables the pruning pass
+    bool wlod_mma = true;          // GARLIC_NO_MMA=1: weighted pass 2 with the exact kernel only
     ncclComm_t comm = nullptr;     // one rank per GPU, individuals sharded across ranks
     int comm_rank = 0, comm_world = 1;
     bool counts_reduced = false;   // d_counts already holds the sum over all ranks
@@ -186,6 +187,7 @@ int garlic_gpu_create(int device, garlic_gpu_t** out)
     cudaEventCreate(&h->ev1);
     cudaEventCreate(&h->ev2);
     h->prune = getenv("GARLIC_NO_PRUNE") == nullptr;
+    h->wlod_mma = getenv("GARLIC_NO_MMA") == nullptr;
     cudaMalloc((void**)&h->d_cnt, 4 * sizeof(unsigned));
     *out = h;
     return 0;
@@ -694,7 +696,10 @@ static int launch_any_walk(garlic_gpu* h, const WalkParams& P, const Item* items
     if (weighted) {
         WlodParams Q;
         Q.base = P; Q.wlut = h->d_wlut; Q.invld = h->d_invld; Q.nomut = h->d_nomut; Q.norec = h->d_norec;
-        LAUNCH(launch_wlod_walk(Q, items, n_items, h->have_gl, roh, dump, h->stream));
+        // tolerance-checked fast pass on the FP64 tensor cores; exact mul-then-add sums otherwise (dumps, exact mode,
+        // re-evaluation of ambiguous pairs)
+        if (P.tol > 0 && roh && !dump && h->wlod_mma) LAUNCH(launch_wlod_mma(Q, items, n_items, h->have_gl, h->stream));
+        else LAUNCH(launch_wlod_walk(Q, items, n_items, h->have_gl, roh, dump, h->stream));
     } else {
         LAUNCH(launch_walk(P, items, n_items, h->have_gl, roh, dump, tile_snps <= kTileSnpsMax ? tile_snps : 0, cl, h->stream));
     }
@@ -876,6 +881,11 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
             int64_t longest = 0;
             for (const Segment& s : segs) longest = std::max<int64_t>(longest, s.we - s.ws);
             P.tol = (double)(longest + 2 * W) * 2.220446049250313e-16 * (W + 1) * h->amax;
+        }
+        if (!exact && weighted && h->wlod_mma) {
+            // |DMMA sum − reference mul-then-add sum| ≤ (W+8)·2ε·W·amax: scores are bounded by amax (nomut, norec ≤ 1)
+            // and 1/LD ≤ 1 because every LD sum contains the diagonal term 1 (garlic-data.cpp:521-527)
+            P.tol = (double)(W + 8) * 2.0 * 2.220446049250313e-16 * W * h->amax;
         }
         CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
         // pruning pass (coarse.cuh): drop (individual, item) pairs that provably hold no window >= cutoff - tol

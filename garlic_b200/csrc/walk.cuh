@@ -120,65 +120,13 @@ GHD uint32_t lut_off(uint32_t w, int kk)
     return kk >= 2 ? ((w >> (2 * kk - 3)) & 24u) : ((w << (3 - 2 * kk)) & 24u);
 }
 
-// One block of 32 slide steps, in two phases.
-//   phase 1: the window chain win = (win - lod(out)) + lod(in) (garlic-roh.cpp:98-100) and the cutoff
-//            test (:450) for all 32 steps → flag word(s).  With CHK the test is made against
-//            cutoff±tol: where both agree they equal the test against the cutoff itself, where they
-//            differ the (individual, segment) pair is marked for exact re-evaluation.
-//   phase 2: coverage count (sliding form of :446-454) and run-length on the 32 flag bits — skipped by
-//            the whole warp when no lane has a flag in this block or a flag still inside its last W
-//            windows (the common case outside ROH).
-// FULL: every step is a valid window and inside the owned range.
-template <int SRC, bool ROH, bool DUMP, bool FULL, bool CHK>
-GHD void walk_block(const WalkParams& P, const Item& it, const LaneCtx<SRC>& C, LaneState& S, int ind,
-                    int k_slot, bool active, uint64_t gin, uint64_t gout, int tblk, uint32_t ow)
+// Phase 2 of a 32-window block: from the block's window-flag word fw (bit k = window tblk+k reached the cutoff)
+// and ow (the flag stream delayed by W, only used when W > 32) to per-SNP coverage, covered bits and run records.
+template <bool FULL>
+GHD void cover_block(const WalkParams& P, const Item& it, LaneState& S, int ind, bool active, uint32_t fw, uint32_t ow,
+                     int tblk)
 {
     const int W = P.W;
-    const double cut_hi = CHK ? P.cutoff + P.tol : P.cutoff, cut_lo = P.cutoff - P.tol;
-    const int s_in0 = tblk + W - 1, s_out0 = tblk - 1;
-    uint32_t vm = 0xffffffffu;             // valid-window mask of the block
-    if (!FULL) {
-        const int n = it.we - tblk;
-        vm = n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
-    }
-    uint32_t fhi = 0, flo = 0;
-    double win = S.win;
-    if (SRC == 0) {
-        const uint32_t bi = (uint32_t)(s_in0 - C.tile_lo) * 32u, bo = (uint32_t)(s_out0 - C.tile_lo) * 32u;
-        const uint32_t gi0 = (uint32_t)gin, gi1 = (uint32_t)(gin >> 32);
-        const uint32_t go0 = (uint32_t)gout, go1 = (uint32_t)(gout >> 32);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const uint32_t oi = lut_off(k < 16 ? gi0 : gi1, k & 15), oo = lut_off(k < 16 ? go0 : go1, k & 15);
-            const double a_in = *reinterpret_cast<const double*>(C.tile + ((bi | oi) + k * 32));
-            const double a_out = *reinterpret_cast<const double*>(C.tile + ((bo | oo) + k * 32));
-            // exact chains keep the reference's order (garlic-roh.cpp:98-100); the tolerance-checked
-            // pass takes the difference off the dependent chain (same error bound, DESIGN.md §6)
-            if (CHK) win = win + (a_in - a_out);
-            else win = (win - a_out) + a_in;
-            if (ROH) {
-                if (win >= cut_hi) fhi |= 1u << k;                           // garlic-roh.cpp:450
-                if (CHK) { if (win >= cut_lo) flo |= 1u << k; }
-            }
-            if (DUMP) { if ((vm >> k) & 1u) dump_window<DUMP>(P, it, k_slot, active, tblk + k, win); }
-        }
-    } else {
-#pragma unroll 4
-        for (int k = 0; k < 32; ++k) {
-            const int go = (int)(gout >> (2 * k)) & 3, gi = (int)(gin >> (2 * k)) & 3;
-            win = (win - C.aval(s_out0 + k, go)) + C.aval(s_in0 + k, gi);
-            if (ROH) {
-                if (win >= cut_hi) fhi |= 1u << k;
-                if (CHK) { if (win >= cut_lo) flo |= 1u << k; }
-            }
-            if (DUMP) { if ((vm >> k) & 1u) dump_window<DUMP>(P, it, k_slot, active, tblk + k, win); }
-        }
-    }
-    S.win = win;
-    if (!ROH) return;
-    fhi &= vm;
-    if (CHK) { flo &= vm; S.ambig |= (fhi != flo); }
-    const uint32_t fw = fhi;
     S.fw = fw;   // the block's window-flag word, stored to the history ring by the caller
 
     bool busy = (fw | (uint32_t)S.cov) != 0u;   // an open run implies cov >= thr >= 1
@@ -242,6 +190,67 @@ GHD void walk_block(const WalkParams& P, const Item& it, const LaneCtx<SRC>& C, 
         if ((x >> k) & 1u) S.run_start = t;
         else { emit_run(P, it, ind, active, S.run_start, t - 1); S.run_start = -1; }
     }
+}
+
+// One block of 32 slide steps, in two phases.
+//   phase 1: the window chain win = (win - lod(out)) + lod(in) (garlic-roh.cpp:98-100) and the cutoff
+//            test (:450) for all 32 steps → flag word(s).  With CHK the test is made against
+//            cutoff±tol: where both agree they equal the test against the cutoff itself, where they
+//            differ the (individual, segment) pair is marked for exact re-evaluation.
+//   phase 2: coverage count (sliding form of :446-454) and run-length on the 32 flag bits — skipped by
+//            the whole warp when no lane has a flag in this block or a flag still inside its last W
+//            windows (the common case outside ROH).
+// FULL: every step is a valid window and inside the owned range.
+template <int SRC, bool ROH, bool DUMP, bool FULL, bool CHK>
+GHD void walk_block(const WalkParams& P, const Item& it, const LaneCtx<SRC>& C, LaneState& S, int ind,
+                    int k_slot, bool active, uint64_t gin, uint64_t gout, int tblk, uint32_t ow)
+{
+    const int W = P.W;
+    const double cut_hi = CHK ? P.cutoff + P.tol : P.cutoff, cut_lo = P.cutoff - P.tol;
+    const int s_in0 = tblk + W - 1, s_out0 = tblk - 1;
+    uint32_t vm = 0xffffffffu;             // valid-window mask of the block
+    if (!FULL) {
+        const int n = it.we - tblk;
+        vm = n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
+    }
+    uint32_t fhi = 0, flo = 0;
+    double win = S.win;
+    if (SRC == 0) {
+        const uint32_t bi = (uint32_t)(s_in0 - C.tile_lo) * 32u, bo = (uint32_t)(s_out0 - C.tile_lo) * 32u;
+        const uint32_t gi0 = (uint32_t)gin, gi1 = (uint32_t)(gin >> 32);
+        const uint32_t go0 = (uint32_t)gout, go1 = (uint32_t)(gout >> 32);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const uint32_t oi = lut_off(k < 16 ? gi0 : gi1, k & 15), oo = lut_off(k < 16 ? go0 : go1, k & 15);
+            const double a_in = *reinterpret_cast<const double*>(C.tile + ((bi | oi) + k * 32));
+            const double a_out = *reinterpret_cast<const double*>(C.tile + ((bo | oo) + k * 32));
+            // exact chains keep the reference's order (garlic-roh.cpp:98-100); the tolerance-checked
+            // pass takes the difference off the dependent chain (same error bound, DESIGN.md §6)
+            if (CHK) win = win + (a_in - a_out);
+            else win = (win - a_out) + a_in;
+            if (ROH) {
+                if (win >= cut_hi) fhi |= 1u << k;                           // garlic-roh.cpp:450
+                if (CHK) { if (win >= cut_lo) flo |= 1u << k; }
+            }
+            if (DUMP) { if ((vm >> k) & 1u) dump_window<DUMP>(P, it, k_slot, active, tblk + k, win); }
+        }
+    } else {
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            const int go = (int)(gout >> (2 * k)) & 3, gi = (int)(gin >> (2 * k)) & 3;
+            win = (win - C.aval(s_out0 + k, go)) + C.aval(s_in0 + k, gi);
+            if (ROH) {
+                if (win >= cut_hi) fhi |= 1u << k;
+                if (CHK) { if (win >= cut_lo) flo |= 1u << k; }
+            }
+            if (DUMP) { if ((vm >> k) & 1u) dump_window<DUMP>(P, it, k_slot, active, tblk + k, win); }
+        }
+    }
+    S.win = win;
+    if (!ROH) return;
+    fhi &= vm;
+    if (CHK) { flo &= vm; S.ambig |= (fhi != flo); }
+    cover_block<FULL>(P, it, S, ind, active, fhi, ow, tblk);
 }
 
 // Walk one item for one individual.  ring: this lane's flag-history ring (NW words, stride rstride).

@@ -178,6 +178,155 @@ __device__ __forceinline__ void wlod_walk_item(const WlodParams& Q, const Item& 
     if (ROH && run_start >= 0) emit_run(P, it, ind, active, run_start, it.own_hi - 1);
 }
 
+// ------------------------------------------------------------------------------------------
+// K5-W fast pass: weighted windows of pass 2 as a banded matrix product on the FP64 tensor cores.
+//   Win[i][t] = Σ_m Sc[i][m] · Wt[m][t],   m = s - t0 over the SNPs a tile of 8 windows t0..t0+7 touches,
+//   Sc[i][m] = score of individual i at SNP t0+m (wlut[s][g] or gl·nomut·norec), Wt[m][j] = 1/LD[t0+j][m-j] (0 outside).
+// One warp owns 32 individuals of one item.  Per k-step of 4 SNPs it loads ONE weight fragment (mma B operand,
+// one double per lane) and reuses it for four 8-individual row groups (mma.sync.m8n8k4.f64, A = one score per
+// lane): 1024 multiply-adds for 5 loads.  The 8x8 accumulator tiles become window flags (cutoff ± tol), the flag
+// bits are routed by shuffles to the lane that owns each individual, and four tiles make the 32-bit flag word that
+// cover_block (walk.cuh) turns into coverage and run records — exactly as the unweighted walker does.
+// DMMA fuses and reorders the sum, so values differ from the reference's mul-then-add chain in the last bits:
+// windows within tol of the cutoff mark their (individual, segment) pair ambiguous, and those pairs are re-walked
+// by the exact kernel above (garlic_gpu_call_roh).  Window dumps (KDE, --raw-lod) always use the exact kernel.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(128)
+wlod_mma_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items, int n_groups)
+{
+    extern __shared__ uint32_t ring_smem[];   // [NW][blockDim.x] flag-word history (W > 32)
+    const WalkParams& P = Q.base;
+    const int W = P.W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gpb = blockDim.x >> 5;
+    const int gblocks = (n_groups + gpb - 1) / gpb;
+    const long long total = (long long)n_items * gblocks;
+    const int NW = ((W + 31) >> 5) + 1, nwords = (W + 31) >> 5, r = (32 - (W & 31)) & 31;
+    uint32_t* ring = ring_smem + threadIdx.x;
+    const int rstride = blockDim.x;
+    const double cut_hi = P.cutoff + P.tol, cut_lo = P.cutoff - P.tol;
+    const int KK = (W + 7 + 3) >> 2;          // k-steps of 4 SNPs covering m = 0 .. W+6
+    const int j = lane >> 2, mq = lane & 3;    // window column / SNP-within-k-step of this lane's B element; row j of A
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const int item = (int)(u / gblocks);
+        const int group = (int)(u % gblocks) * gpb + warp;
+        if (group >= n_groups) continue;
+        const Item it = items[item];
+        const int k_own = group * 32 + lane;
+        const bool active = k_own < P.n_lanes;
+        const int ind = P.ind_list ? P.ind_list[active ? k_own : P.n_lanes - 1] : (active ? k_own : P.n_lanes - 1);
+        // the four individuals whose scores this lane supplies (row j of each 8-row group)
+        const uint64_t* rowA[4];
+        const double* glA[4];
+#pragma unroll
+        for (int rg = 0; rg < 4; ++rg) {
+            int k = group * 32 + 8 * rg + j;
+            if (k >= P.n_lanes) k = P.n_lanes - 1;
+            const int ia = P.ind_list ? P.ind_list[k] : k;
+            rowA[rg] = P.geno + (int64_t)ia * P.row_words;
+            glA[rg] = (SRC == 1) ? P.gl + (int64_t)ia * P.gl_stride : nullptr;
+        }
+        LaneState S;
+        S.win = 0; S.cov = 0; S.run_start = -1; S.fw = 0; S.hist = 0; S.ambig = false;
+        if (W > 32) for (int w = 0; w < NW; ++w) ring[w * rstride] = 0;
+        int wr = 1 % NW;
+        for (int tb = it.w0; tb < it.own_hi; tb += 32) {
+            uint32_t fhi = 0, flo = 0;
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                const int t0 = tb + 8 * q;
+                double c[4][2];
+#pragma unroll
+                for (int rg = 0; rg < 4; ++rg) { c[rg][0] = 0.0; c[rg][1] = 0.0; }
+                const int t = t0 + j;                                  // window of this lane's weight column
+                const double* invrow = Q.invld + (int64_t)t * W;
+                const bool tvalid = t < it.we;
+                for (int kk = 0; kk < KK; ++kk) {
+                    const int m = 4 * kk + mq, s = t0 + m, ko = m - j;
+                    const double b = (tvalid && ko >= 0 && ko < W) ? invrow[ko] : 0.0;
+                    const int64_t wi = s >> 5;
+                    const int sh = 2 * (s & 31);
+#pragma unroll
+                    for (int rg = 0; rg < 4; ++rg) {
+                        const int g = (int)(rowA[rg][wi] >> sh) & 3;
+                        double a;
+                        if (SRC == 0) a = Q.wlut[(int64_t)s * 4 + g];
+                        else a = glA[rg][s] * Q.nomut[s] * Q.norec[s];
+                        dmma_m8n8k4(c[rg][0], c[rg][1], a, b);
+                    }
+                }
+                // accumulator (row j, columns 2mq, 2mq+1) → flag bits of windows t0+2mq, t0+2mq+1 of individual 8rg+j
+                uint32_t myhi = 0, mylo = 0;
+#pragma unroll
+                for (int rg = 0; rg < 4; ++rg) {
+                    uint32_t bh = ((uint32_t)(c[rg][0] >= cut_hi) | ((uint32_t)(c[rg][1] >= cut_hi) << 1)) << (2 * mq);
+                    uint32_t bl = ((uint32_t)(c[rg][0] >= cut_lo) | ((uint32_t)(c[rg][1] >= cut_lo) << 1)) << (2 * mq);
+                    bh |= __shfl_xor_sync(0xffffffffu, bh, 1); bh |= __shfl_xor_sync(0xffffffffu, bh, 2);
+                    bl |= __shfl_xor_sync(0xffffffffu, bl, 1); bl |= __shfl_xor_sync(0xffffffffu, bl, 2);
+                    // owner lane o holds individual o = 8·(o/8) + (o%8): its byte sits in lanes 4·(o%8)..+3 of row group o/8
+                    const uint32_t gh = __shfl_sync(0xffffffffu, bh, 4 * (lane & 7));
+                    const uint32_t gl_ = __shfl_sync(0xffffffffu, bl, 4 * (lane & 7));
+                    if (rg == (lane >> 3)) { myhi = gh; mylo = gl_; }
+                }
+                fhi |= myhi << (8 * q);
+                flo |= mylo << (8 * q);
+            }
+            const int nv = it.we - tb;                                 // valid windows of the block
+            const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << nv) - 1u));
+            fhi &= vm; flo &= vm;
+            S.ambig |= (fhi != flo);
+            uint32_t ow = 0;
+            if (W > 32) {
+                int r0 = wr + 1; if (r0 >= NW) r0 -= NW;
+                int r1 = r0 + 1; if (r1 >= NW) r1 -= NW;
+                const uint32_t w0_ = ring[r0 * rstride], w1_ = ring[r1 * rstride];
+                ow = r ? ((w0_ >> r) | (w1_ << (32 - r))) : w0_;
+            }
+            const bool full = (tb + 31 < it.we) && (tb >= it.own_lo) && (tb + 31 < it.own_hi);
+            if (full) cover_block<true>(P, it, S, ind, active, fhi, ow, tb);
+            else cover_block<false>(P, it, S, ind, active, fhi, ow, tb);
+            if (W > 32) {
+                ring[wr * rstride] = fhi;
+                if (++wr >= NW) wr = 0;
+            }
+            (void)nwords;
+        }
+        if (S.run_start >= 0) emit_run(P, it, ind, active, S.run_start, it.own_hi - 1);
+        if (S.ambig && active) {
+            const unsigned p = atomicAdd(P.out_count + 1, 1u);
+            if (p < P.amb_cap) {
+                RohRec rr;
+                rr.ind = ind; rr.a = 0; rr.b = 0; rr.tag = it.seg;
+                P.amb[p] = rr;
+            }
+        }
+    }
+}
+
+cudaError_t launch_wlod_mma(const WlodParams& Q, const Item* items, int n_items, bool gl_mode, cudaStream_t st)
+{
+    if (n_items == 0 || Q.base.n_lanes == 0) return cudaSuccess;
+    const int threads = 128;
+    const int n_groups = (Q.base.n_lanes + 31) / 32;
+    const int gpb = threads / 32;
+    const long long total = (long long)n_items * ((n_groups + gpb - 1) / gpb);
+    const int NW = ((Q.base.W + 31) >> 5) + 1;
+    const size_t smem = (size_t)NW * threads * sizeof(uint32_t);
+    long long grid = total;
+    const long long cap = 148ll * 16 * 8;
+    if (grid > cap) grid = cap;
+    if (gl_mode) wlod_mma_kernel<1><<<(unsigned)grid, threads, smem, st>>>(Q, items, n_items, n_groups);
+    else wlod_mma_kernel<0><<<(unsigned)grid, threads, smem, st>>>(Q, items, n_items, n_groups);
+    return cudaGetLastError();
+}
+
 template <int SRC, bool ROH, bool DUMP>
 __global__ void __launch_bounds__(128)
 wlod_walk_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items, int n_groups)

@@ -16,6 +16,9 @@ struct WlodParams {
 cudaError_t launch_wlod_walk(const WlodParams& Q, const Item* items, int n_items, bool gl_mode, bool roh,
                              bool dump, cudaStream_t st);
 
+// fast pass of pass 2 on the FP64 tensor cores (tolerance-checked; needs base.tol > 0)
+cudaError_t launch_wlod_mma(const WlodParams& Q, const Item* items, int n_items, bool gl_mode, cudaStream_t st);
+
 // LD band: hr² pair matrix over the listed individuals → window sums → reciprocal.
 // invld: [L+pad][W]; ld_out (optional): [L][W] the sums themselves (reference LDData layout).
 cudaError_t launch_ld_band(const uint64_t* geno, int64_t row_words, const int* ld_ind, int n_ld,

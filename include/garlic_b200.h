@@ -79,7 +79,8 @@ int garlic_gpu_code_alleles(garlic_gpu_t *h);
 
 /* ---- pre-coded input: packed 2-bit rows (codes 0/1/2, 3 = missing) -------------------------
  * rows: [n_ind][row_stride_bytes] on the host (or, for _dev, on this GPU); SNP s of a row is
- * bits 2*(s%4) of byte s/4. */
+ * bits 2*(s%4) of byte s/4.  The library works on its own stream (garlic_gpu_stream): device buffers
+ * handed to a _dev entry point must be complete (producer stream synchronised) before the call. */
 int garlic_gpu_put_packed(garlic_gpu_t *h, const uint8_t *rows, int64_t row_stride_bytes);
 int garlic_gpu_put_packed_dev(garlic_gpu_t *h, const void *rows_dev, int64_t row_stride_bytes);
 /* K2: per-SNP allele / missingness / homozygote counts by column reduction of the packed matrix

@@ -174,15 +174,18 @@ def test_weighted_ld_wlod_and_roh():
     hp.close()
 
 
-def test_weighted_ld_subsample():
+@pytest.mark.parametrize("W", [25, 32, 72])
+def test_weighted_ld_subsample(W):
     ds, args = load_case("wlod_cm")
     sub = np.array([0, 3, 4, 9, 10, 17, 20], np.int32)
-    res = orc.run_pipeline(ds, 25, 0.001, 0.5, 0.25, weighted=True, cm=True, ld_individuals=sub)
+    res = orc.run_pipeline(ds, W, 0.001, 0.5, 0.25, weighted=True, cm=True, ld_individuals=sub)
     hp = HotPath().load(ds, weighted=True, cm=True, error=0.001)
-    ld = hp.g.ld_band(25, sub, want_ld=True)
+    ld = hp.g.ld_band(W, sub, want_ld=True)
     assert np.array_equal(ld, np.concatenate([c["LD"] for c in res["chroms"]], axis=0), equal_nan=True)
-    got = hp.roh(25, 0.5, 0.25, weighted=True, cm=True)
-    assert [(r[0], r[1], r[5], r[6]) for r in got] == oracle_roh_idx(res)
+    close_windows(hp.g.windows(W, 1, weighted=True), oracle_windows_matrix(res))
+    for exact in (False, True):      # tensor-core pass with exact re-evaluation / exact sums everywhere
+        got = hp.roh(W, 0.5, 0.25, weighted=True, cm=True, exact=exact)
+        assert len(got) > 0 and [(r[0], r[1], r[5], r[6]) for r in got] == oracle_roh_idx(res)
     hp.close()
 
 
@@ -287,4 +290,44 @@ def test_repeated_runs_are_identical_and_equal_exact_chains():
     assert 0 <= st["candidate_pairs"] < st["all_pairs"]          # the pruning pass ran and pruned
     assert all(np.array_equal(o, outs[0]) for o in outs) and len(outs[0]) > 100
     assert np.array_equal(outs[0], g.call_roh(50, 2.0, 0.25, exact=True))
+    hp.close()
+
+
+def _weighted_handle(n_ind, L0, seed, gl=False):
+    names, offs, pos, cens = synth.make_positions_genomewide(seed, L0, n_chr=3)
+    codes = synth.make_codes(seed, n_ind, L0)
+
+    class DS:
+        pass
+    ds = DS()
+    ds.chr_names, ds.chr_offsets, ds.pos, ds.centromeres = names, offs, pos, cens
+    C = len(names)
+    ds.map_pos = [pos[offs[c]:offs[c + 1]][2:-2:5].astype(np.int64) for c in range(C)]
+    ds.map_cm = [np.round(p * 1.2e-6, 9) for p in ds.map_pos]
+    ds.gl = None
+    if gl:
+        rng = np.random.default_rng(seed + 100)
+        ds.gl = rng.choice(np.array([0.0004, 0.004, 0.04, 0.5, 3.0, 0.0, 150.0]), size=(L0, n_ind))
+        ds.gl_type = "PL"
+    return HotPath().load(ds, weighted=True, cm=True, error=None if gl else 0.001, packed_rows=synth.pack_codes(codes))
+
+
+@pytest.mark.parametrize("W,gl", [(25, False), (72, False), (33, False), (40, True)])
+def test_weighted_tensor_core_pass_equals_exact_sums(W, gl):
+    """Pass 2 of the weighted path: the tolerance-checked DMMA pass (wlod_mma_kernel) returns the same ROH as the
+    exact mul-then-add kernel, also when the cutoff sits exactly on a window value (ambiguous pairs are re-walked
+    exactly), for W below / above one flag word, a ragged last individual group, and per-genotype likelihoods."""
+    hp = _weighted_handle(77, 30000, 21 + W, gl)
+    g = hp.g
+    ld_ind = np.arange(0, 77, 2, dtype=np.int32)
+    g.ld_band(W, ld_ind)
+    win = g.windows(W, 1, weighted=True, individuals=np.array([5], np.int32))[0]
+    vals = np.sort(win[(win != orc.MISSING) & ~np.isnan(win)])
+    for cutoff in (float(vals[int(len(vals) * 0.97)]), 0.5):
+        a = g.call_roh(W, cutoff, 0.25, weighted=True, exact=False).copy()
+        st = g.last_stats()
+        b = g.call_roh(W, cutoff, 0.25, weighted=True, exact=True)
+        assert np.array_equal(a, b) and len(a) > 0
+        if cutoff != 0.5:
+            assert st["ambiguous_pairs"] >= 1       # individual 5 holds a window equal to the cutoff
     hp.close()

@@ -39,6 +39,7 @@ def setup(n_ind, L0, seed):
     names, chr_off0, pos0, cens = synth.make_positions_genomewide(seed, L0)
     row_bytes = ((L0 + 3) // 4 + 15) // 16 * 16
     rows = bench.make_rows_torch(torch, dev, n_ind, L0, seed, 1000, row_bytes)
+    torch.cuda.synchronize()                     # the library copies on its own stream
     g = GarlicGPU(0)
     g.set_shape(n_ind, L0, chr_off0, pos0)
     g.put_packed_dev(rows.data_ptr(), row_bytes)
@@ -96,6 +97,7 @@ def c4(n_ind=500, L0=2_000_000):
     idx = torch.randint(0, 7, (n_ind, L0), generator=gen, device=dev)      # (multinomial is not reproducible at this size)
     idx = torch.where(idx >= 5, torch.randint(0, 7, (n_ind, L0), generator=gen, device=dev), idx)
     gl = vals[idx]
+    torch.cuda.synchronize()
     g._ck(g.lib.garlic_gpu_put_gl_dev(g.h, bench.C_void(gl.data_ptr()), 2))
     (freq, keep, L), ms_f = timed(g, lambda: g.filter(), reps=1)
     cen_arr = np.array([cens["chr" + nm] for nm in names], np.int32)

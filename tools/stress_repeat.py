@@ -16,6 +16,7 @@ def run(n_ind, L0, W, use_gl, cutoff):
     names, chr_off0, pos0, cens = synth.make_positions_genomewide(7, L0)
     row_bytes = ((L0 + 3) // 4 + 15) // 16 * 16
     rows = bench.make_rows_torch(torch, dev, n_ind, L0, 7, 1000, row_bytes)
+    torch.cuda.synchronize()                     # the library copies on its own stream
     g = GarlicGPU(0)
     g.set_shape(n_ind, L0, chr_off0, pos0)
     g.put_packed_dev(rows.data_ptr(), row_bytes)
