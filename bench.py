@@ -85,51 +85,54 @@ def unpack_rows(rows_u8, L):
 # clocks sampling during the timed region (B200_PROFILING.md)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Polls NVML (SM clock, clocks-event reasons) from a thread every millisecond while the timed region runs:
+    the region lasts tens of milliseconds, too short for `nvidia-smi -lms`.  Falls back to one nvidia-smi query."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20))
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.sm, self.mask, self.mx, self.h, self.t = index, [], 0, None, None, None
+        self.run = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        while self.run:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.h is None:
+            return
+        self.run = True
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            t = [x.strip() for x in ln.split(",")]
-            if len(t) < 9:
-                continue
+        if self.h is None:
             try:
-                sm.append(float(t[1])); mx.append(float(t[2]))
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if t[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+                a, b = [float(x) for x in out.strip().split(",")]
+                return dict(sm_mhz=a, sm_max_mhz=b, reasons=[], samples=1, how="one nvidia-smi query after the region")
+            except Exception:
+                return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvml and nvidia-smi unavailable"], samples=0)
+        self.run = False
+        self.t.join(timeout=2)
+        reasons = sorted(nm for nm, bit in self.REASONS if self.mask & bit)
+        return dict(sm_mhz=float(np.median(self.sm)) if self.sm else None, sm_max_mhz=self.mx, reasons=reasons,
+                    samples=len(self.sm), how="NVML polled every ms during the timed region")
 
 
 # ------------------------------------------------------------------------------------------------

@@ -514,8 +514,8 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     LAUNCH(launch_gather_f64(h->d_freq0, h->d_src, L, h->d_freq, h->stream));
     if (h->have_gl) {
         h->gl_stride = L + kPad;
-        if (dev_alloc(h, &h->d_gl, (size_t)h->n_ind * h->gl_stride)) return 1;
-        CK(cudaMemsetAsync(h->d_gl, 0, (size_t)h->n_ind * h->gl_stride * sizeof(double), h->stream));
+        // lane-interleaved [groups of 32 individuals][gl_stride][32] (common.cuh:gl_lane); the kernel writes every element
+        if (dev_alloc(h, &h->d_gl, (size_t)((h->n_ind + 31) / 32) * 32 * h->gl_stride)) return 1;
         LAUNCH(launch_compact_gl(h->d_gl0, L0, h->d_src, L, h->d_geno0, h->row_words0, h->d_freq0, h->d_gl, h->gl_stride, h->n_ind,
                                  h->gl_type, h->stream));
     }
@@ -782,7 +782,7 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
     double* d_dump = h->d_dump;
     LAUNCH(launch_fill_f64(d_dump, (size_t)n_lanes * slots, kMissing, h->stream));
     // thinned pass 1 (unweighted, table mode, tolerance 1e-9): sum only the windows the KDE will look at
-    const bool direct = !weighted && !h->have_gl && !exact && step >= 8;
+    const bool direct = !weighted && !exact && step >= 8;
     int rc = 0;
     if (direct) {
         static_assert(sizeof(Segment) == sizeof(int3), "Segment is uploaded as int3");
@@ -799,7 +799,8 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
         if (!segs.empty()) CK(cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(int3), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
         LAUNCH(launch_thin_windows(h->d_geno, h->row_words, h->d_lut, individuals ? h->d_indlist : nullptr, n_lanes, d_segs,
-                                   (int)segs.size(), d_meta, h->n_chr, slots, step, W, d_dump, slots, h->stream));
+                                   (int)segs.size(), d_meta, h->n_chr, slots, step, W, d_dump, slots,
+                                   h->have_gl ? h->d_gl : nullptr, h->gl_stride, h->stream));
     } else {
     int chunk = 0;
     if (weighted) chunk = std::max(64, pick_chunk(h->L, W, n_lanes, 0) / 8);   // every wLOD window is a fresh sum

@@ -42,7 +42,8 @@ struct WalkParams {
     const uint64_t* geno;   // packed rows, 32 genotypes per 64-bit word, SNP s at bits 2*(s&31) of word s>>5
     int64_t row_words;      // row stride in 64-bit words (>= ceil(L/32)+2, padded)
     const double* lut;      // [L+pad][4] per-SNP LOD of g=0,1,2,missing (unweighted, global --error)
-    const double* gl;       // [N][gl_stride] per-genotype LOD (GL mode: lod() of every genotype, built at compaction), or nullptr
+    const double* gl;       // per-genotype LOD (GL mode: lod() of every genotype, built at compaction), or nullptr;
+                            // lane-interleaved: [ceil(N/32)][gl_stride SNPs][32 individuals] — see gl_lane()
     const double* freq;     // [L] (GL mode)
     int64_t gl_stride;
     const int* ind_list;    // optional indirection: lane k works on individual ind_list[k]
@@ -61,5 +62,14 @@ struct WalkParams {
     int64_t dump_stride;
     int dump_step;          // keep windows with (t-chr_start) % dump_step == 0
 };
+
+// GL-mode value of individual `ind` at SNP s: gl_lane(P, ind)[s * kGlLanes].  The 32 individuals of a group sit
+// next to each other for every SNP, so a warp walking 32 consecutive individuals reads 256 contiguous bytes per SNP
+// and a group's SNP range is one contiguous slab (what gl_walk_kernel copies with cp.async.bulk).
+constexpr int kGlLanes = 32;
+GHD const double* gl_lane(const WalkParams& P, int ind)
+{
+    return P.gl + ((int64_t)(ind >> 5) * P.gl_stride) * kGlLanes + (ind & 31);
+}
 
 }  // namespace garlic

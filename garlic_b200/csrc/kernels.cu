@@ -2,6 +2,7 @@
 // Kernel inventory: K1 code_alleles, K2 count_packed, K3 compact_*, K4 build_lut,
 // K5 walk (fused windows→ROH / window dump), K6 ld_pairs + ld_band, K5-W wlod_walk.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdint.h>
 #include <algorithm>
 #include "common.cuh"
@@ -251,10 +252,207 @@ static cudaError_t launch_walk_t(const WalkParams& P, const Item* items, int n_i
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// K5-GL pass 2: the fused window → cutoff → coverage → ROH walker for per-genotype likelihoods (--tgls).
+// Here every genotype has its own LOD (8 bytes per individual-window of compulsory HBM traffic, SURVEY §8d: the
+// HBM-bound config), so the kernel is organised around the copy:
+//   * one CTA = one warp = the 32 individuals of a group walking one item, lane = individual;
+//   * the group's values for the item's SNPs are ONE contiguous slab of the lane-interleaved matrix
+//     (common.cuh:gl_lane).  It streams through a per-warp shared-memory ring in pieces of kGlPiece SNPs (4 KB) moved
+//     by cp.async.bulk, each completing on its own mbarrier.  The ring holds the last W SNPs (= the slide-out values
+//     of garlic-roh.cpp:98-100, so nothing is read twice from HBM or L2) plus the pieces in flight ahead;
+//   * per step: two conflict-free LDS.64 (slide-in, slide-out), the window update in the reference's order (exact) or
+//     win + (in − out) with the cutoff ± tol test (tolerance-checked pass), then cover_block as in the
+//     table-mode walker.
+// ------------------------------------------------------------------------------------------
+constexpr int kGlPiece = 16;                              // SNPs per bulk copy
+constexpr int kGlPieceBytes = kGlPiece * kGlLanes * 8;    // 4 KB
+
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <bool CHK>
+__global__ void __launch_bounds__(32)
+gl_walk_kernel(const WalkParams P, const Item* __restrict__ items, int n_items, int n_groups, int NS)
+{
+    extern __shared__ __align__(128) unsigned char gl_smem[];
+    const int lane = threadIdx.x;
+    const int W = P.W;
+    const int NW = ((W + 31) >> 5) + 1;
+    const double* ring = reinterpret_cast<const double*>(gl_smem);
+    uint32_t* fring = reinterpret_cast<uint32_t*>(gl_smem + (size_t)NS * kGlPieceBytes) + lane;   // flag-word history
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gl_smem + (size_t)NS * kGlPieceBytes + (size_t)NW * 128);
+    if (lane == 0) for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+    __syncwarp();
+    const int R = NS * kGlPiece;                           // ring length in SNPs (NS is even: R is a multiple of 32)
+    uint64_t par = 0;                                      // bit s: parity the next completion of slot s will have
+    const double cut_hi = CHK ? P.cutoff + P.tol : P.cutoff, cut_lo = P.cutoff - P.tol;
+    const int r = (32 - (W & 31)) & 31;
+    const long long total = (long long)n_items * n_groups;
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const int item = (int)(u / n_groups), group = (int)(u % n_groups);
+        const Item it = items[item];
+        const int ind = group * 32 + lane;
+        const bool active = ind < P.n_lanes;
+        const unsigned char* slab = reinterpret_cast<const unsigned char*>(P.gl + ((int64_t)group * P.gl_stride + it.w0) * kGlLanes);
+        const int M = it.own_hi - 1 - it.w0;               // slide steps
+        const int nblk = (M + 31) >> 5;
+        const int NQ = (W + 32 * nblk + kGlPiece - 1) / kGlPiece;   // pieces this walk consumes
+        int issued = 0, waited = 0;
+        // lanes are done reading a slot before lane 0 hands it back to the copy engine
+        auto issue_upto = [&](int qmax) {
+            const int hi = qmax + 1 < NQ ? qmax + 1 : NQ;
+            if (hi <= issued) return;
+            __syncwarp();
+            if (lane == 0) {
+                fence_proxy_async();
+                for (int q = issued; q < hi; ++q) {
+                    const int sl = q % NS;
+                    mbar_expect_tx(&bars[sl], kGlPieceBytes);
+                    tma_load_1d(gl_smem + (size_t)sl * kGlPieceBytes, slab + (size_t)q * kGlPieceBytes, kGlPieceBytes, &bars[sl]);
+                }
+            }
+            issued = hi;
+        };
+        auto wait_upto = [&](int q) {
+            for (; waited <= q; ++waited) {
+                const int sl = waited % NS;
+                mbar_wait(&bars[sl], (uint32_t)(par >> sl) & 1u);
+                par ^= 1ull << sl;
+            }
+        };
+        issue_upto(NS - 1);
+        // fresh sum for window w0, ascending (garlic-roh.cpp:57-71); these pieces sit in slots 0, 1, …
+        double win = 0.0;
+        for (int q = 0; q * kGlPiece < W; ++q) {
+            wait_upto(q);
+            const int n = W - q * kGlPiece < kGlPiece ? W - q * kGlPiece : kGlPiece;
+            const double* p = ring + (size_t)q * kGlPiece * kGlLanes + lane;
+            for (int i = 0; i < n; ++i) win += p[i * kGlLanes];
+        }
+        LaneState S;
+        S.win = win; S.run_start = -1; S.fw = 0; S.ambig = false;
+        const bool f0 = win >= cut_hi;
+        if (CHK) S.ambig = (f0 != (win >= cut_lo));
+        S.cov = (int)f0;
+        S.hist = (uint32_t)f0 << 31;
+        if (it.w0 >= it.own_lo && S.cov >= P.thr) S.run_start = it.w0;
+        if (W > 32) {
+            for (int w = 0; w < NW; ++w) fring[w * 32] = 0;
+            fring[0] = (uint32_t)f0 << 31;
+        }
+        int wr = 1 % NW;
+        int tblk = it.w0 + 1;
+        int pin = W % R, pout = 0;                         // ring positions of the block's first slide-in / slide-out SNP
+        for (int j = 0; j < nblk; ++j, tblk += 32) {
+            wait_upto((W + 32 * j + 31) / kGlPiece);
+            const int kwrap = R - pin;                     // slide-in steps k >= kwrap sit at the start of the ring
+            const double* p_in = ring + (size_t)pin * kGlLanes + lane;
+            const double* p_in2 = p_in - (size_t)R * kGlLanes;
+            const double* p_out = ring + (size_t)pout * kGlLanes + lane;
+            uint32_t vm = 0xffffffffu;
+            const int nv = it.we - tblk;
+            if (nv < 32) vm = nv <= 0 ? 0u : ((1u << nv) - 1u);
+            uint32_t fhi = 0, flo = 0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const double a_in = (k < kwrap ? p_in : p_in2)[k * kGlLanes];
+                const double a_out = p_out[k * kGlLanes];
+                if (CHK) win = win + (a_in - a_out);
+                else win = (win - a_out) + a_in;           // garlic-roh.cpp:98-100
+                if (win >= cut_hi) fhi |= 1u << k;         // garlic-roh.cpp:450
+                if (CHK) { if (win >= cut_lo) flo |= 1u << k; }
+            }
+            S.win = win;
+            fhi &= vm;
+            if (CHK) { flo &= vm; S.ambig |= (fhi != flo); }
+            uint32_t ow = 0;
+            if (W > 32) {
+                int r0 = wr + 1; if (r0 >= NW) r0 -= NW;
+                int r1 = r0 + 1; if (r1 >= NW) r1 -= NW;
+                const uint32_t w0_ = fring[r0 * 32], w1_ = fring[r1 * 32];
+                ow = r ? ((w0_ >> r) | (w1_ << (32 - r))) : w0_;
+            }
+            const bool full = (tblk + 31 < it.we) && (tblk >= it.own_lo) && (tblk + 31 < it.own_hi);
+            if (full) cover_block<true>(P, it, S, ind, active, fhi, ow, tblk);
+            else cover_block<false>(P, it, S, ind, active, fhi, ow, tblk);
+            if (W > 32) {
+                fring[wr * 32] = S.fw;
+                if (++wr >= NW) wr = 0;
+            }
+            pin += 32; if (pin >= R) pin -= R;
+            pout += 32; if (pout >= R) pout -= R;
+            // slide-out pieces 2j, 2j+1 are dead now: their slots take pieces 2j+NS, 2j+1+NS
+            issue_upto(2 * j + 1 + NS);
+        }
+        if (S.run_start >= 0) emit_run(P, it, ind, active, S.run_start, it.own_hi - 1);
+        if (CHK && S.ambig && active) {
+            const unsigned p = atomicAdd(P.out_count + 1, 1u);
+            if (p < P.amb_cap) {
+                RohRec rr;
+                rr.ind = ind; rr.a = 0; rr.b = 0; rr.tag = it.seg;
+                P.amb[p] = rr;
+            }
+        }
+        wait_upto(NQ - 1);                                 // nothing of this walk is still landing (only when nblk == 0)
+        __syncwarp();
+    }
+}
+
+// ring slots for window size W (even; 0 = the ring does not fit, use the generic walker)
+static int gl_ring_slots(int W, size_t* smem_bytes)
+{
+    const int span = (W + 31) / kGlPiece + 1;              // pieces a block's slide-out .. slide-in range touches
+    const int NW = ((W + 31) >> 5) + 1;
+    const size_t fixed = (size_t)NW * 128 + 64 * 8 + 128;
+    const size_t budget = 227 * 1024;
+    int ns_min = span + 3; ns_min += ns_min & 1;
+    if (ns_min > 56 || (size_t)ns_min * kGlPieceBytes + fixed > budget) return 0;
+    // as many CTAs per SM as the minimum ring allows, then spend the rest of that share on pieces in flight
+    const int ctas = (int)((budget - 1024) / ((size_t)ns_min * kGlPieceBytes + fixed + 1024));
+    int ns = (int)(((budget - 1024) / (ctas > 0 ? ctas : 1) - fixed - 1024) / kGlPieceBytes);
+    if (ns > span + 8) ns = span + 8;
+    if (ns > 56) ns = 56;
+    ns -= ns & 1;
+    if (ns < ns_min) ns = ns_min;
+    *smem_bytes = (size_t)ns * kGlPieceBytes + (size_t)NW * 128 + 64 * 8;
+    return ns;
+}
+
+static cudaError_t launch_gl_walk(const WalkParams& P, const Item* items, int n_items, int NS, size_t smem, cudaStream_t st)
+{
+    const int n_groups = (P.n_lanes + 31) / 32;
+    const long long total = (long long)n_items * n_groups;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int per_sm = (int)((227 * 1024) / (smem + 1024));
+    long long grid = (long long)sms * (per_sm > 0 ? per_sm : 1);   // persistent: every CTA slot of the chip, once
+    if (grid > total) grid = total;
+    cudaError_t e;
+    if (P.tol > 0) {
+        e = cudaFuncSetAttribute(gl_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        gl_walk_kernel<true><<<(unsigned)grid, 32, smem, st>>>(P, items, n_items, n_groups, NS);
+    } else {
+        e = cudaFuncSetAttribute(gl_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        gl_walk_kernel<false><<<(unsigned)grid, 32, smem, st>>>(P, items, n_items, n_groups, NS);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_walk(const WalkParams& P, const Item* items, int n_items, bool gl_mode, bool roh,
                         bool dump, int tile_snps, const CandList& cl, cudaStream_t st)
 {
     if (gl_mode) {
+        if (roh && !dump && !P.ind_list && n_items && P.n_lanes) {
+            size_t smem = 0;
+            const int NS = gl_ring_slots(P.W, &smem);
+            if (NS && !getenv("GARLIC_NO_GL_RING")) return launch_gl_walk(P, items, n_items, NS, smem, st);
+        }
         if (roh && !dump) return launch_walk_t<1, true, false>(P, items, n_items, 0, cl, st);
         if (!roh && dump) return launch_walk_t<1, false, true>(P, items, n_items, 0, cl, st);
         return launch_walk_t<1, true, true>(P, items, n_items, 0, cl, st);
@@ -274,11 +472,14 @@ cudaError_t launch_walk(const WalkParams& P, const Item* items, int n_items, boo
 __global__ void thin_windows_kernel(const uint64_t* __restrict__ geno, int64_t row_words, const double* __restrict__ lut,
                                     const int* __restrict__ ind_list, const int3* __restrict__ segs, int n_segs,
                                     const int2* __restrict__ meta, int n_chr, long long n_slots, int step, int W,
-                                    double* __restrict__ dump, int64_t dump_stride)
+                                    double* __restrict__ dump, int64_t dump_stride, const double* __restrict__ gl,
+                                    int64_t gl_stride)
 {
     const int k = blockIdx.y;
     const int ind = ind_list ? ind_list[k] : k;
     const uint64_t* row = geno + (int64_t)ind * row_words;
+    // GL mode: per-genotype LOD values, lane-interleaved (common.cuh:gl_lane)
+    const double* glrow = gl ? gl + ((int64_t)(ind >> 5) * gl_stride) * kGlLanes + (ind & 31) : nullptr;
     for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n_slots; j += (long long)gridDim.x * blockDim.x) {
         int lo = 0, hi = n_chr - 1;                       // chromosome of slot j: last c with meta[c].y <= j
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (meta[mid].y <= j) lo = mid; else hi = mid - 1; }
@@ -287,10 +488,14 @@ __global__ void thin_windows_kernel(const uint64_t* __restrict__ geno, int64_t r
         while (a <= b) { const int mid = (a + b) >> 1; if (segs[mid].y <= t) { sg = mid; a = mid + 1; } else b = mid - 1; }
         if (sg < 0 || t >= segs[sg].z) continue;
         double win = 0.0;
-        for (int i = 0; i < W; ++i) {
-            const int s = t + i;
-            const int g = (int)(row[s >> 5] >> (2 * (s & 31))) & 3;
-            win += lut[(int64_t)s * 4 + g];
+        if (glrow) {
+            for (int i = 0; i < W; ++i) win += glrow[(int64_t)(t + i) * kGlLanes];
+        } else {
+            for (int i = 0; i < W; ++i) {
+                const int s = t + i;
+                const int g = (int)(row[s >> 5] >> (2 * (s & 31))) & 3;
+                win += lut[(int64_t)s * 4 + g];
+            }
         }
         dump[(int64_t)k * dump_stride + j] = win;
     }
@@ -298,14 +503,14 @@ __global__ void thin_windows_kernel(const uint64_t* __restrict__ geno, int64_t r
 
 cudaError_t launch_thin_windows(const uint64_t* geno, int64_t row_words, const double* lut, const int* ind_list, int n_lanes,
                                 const int3* segs, int n_segs, const int2* meta, int n_chr, long long n_slots, int step, int W,
-                                double* dump, int64_t dump_stride, cudaStream_t st)
+                                double* dump, int64_t dump_stride, const double* gl, int64_t gl_stride, cudaStream_t st)
 {
     if (!n_lanes || !n_slots || !n_segs) return cudaSuccess;
     long long bx = (n_slots + 127) / 128;
     if (bx > 4096) bx = 4096;
     dim3 grid((unsigned)bx, (unsigned)n_lanes);
     thin_windows_kernel<<<grid, 128, 0, st>>>(geno, row_words, lut, ind_list, segs, n_segs, meta, n_chr, n_slots, step, W, dump,
-                                               dump_stride);
+                                               dump_stride, gl, gl_stride);
     return cudaGetLastError();
 }
 
@@ -927,19 +1132,47 @@ __device__ __forceinline__ double gl_to_error(double gl, int type)
     return gl;
 }
 
-__global__ void compact_gl_kernel(const double* __restrict__ in, int64_t in_stride, const int* __restrict__ src,
-                                  long long L, const uint64_t* __restrict__ geno0, int64_t row_words0,
-                                  const double* __restrict__ freq0, double* __restrict__ out, int64_t out_stride,
-                                  int n_ind, int type)
+// K3-GL: compaction of the per-genotype likelihood matrix fused with readTGLSData's error transform and lod()
+// (evaluated once per genotype here instead of twice per window step in the walker), written lane-interleaved
+// (common.cuh:gl_lane): out[group][d][lane].  A CTA transposes a tile of 32 individuals x 64 kept SNPs through shared
+// memory: reads run along the SNP axis of the caller's individual-major matrix, writes are whole 16 KB slabs.
+// Covers d in [0, out_stride) and all 32 lanes of the last group: pad SNPs and absent individuals are written as 0.
+constexpr int kGlTile = 64;
+__global__ void __launch_bounds__(256)
+compact_gl_kernel(const double* __restrict__ in, int64_t in_stride, const int* __restrict__ src,
+                  long long L, const uint64_t* __restrict__ geno0, int64_t row_words0,
+                  const double* __restrict__ freq0, double* __restrict__ out, int64_t out_stride,
+                  int n_ind, int type)
 {
-    const long long total = L * n_ind;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(t / L);
-        const long long d = t % L;
-        const int s = src[d];
-        const int g = (int)(geno0[(int64_t)i * row_words0 + (s >> 5)] >> (2 * (s & 31))) & 3;
-        // per-genotype error (readTGLSData) → per-genotype LOD (lod(), garlic-roh.cpp:355-386), evaluated once here
-        out[(int64_t)i * out_stride + d] = lod_eval(g, freq0[s], gl_to_error(in[(int64_t)i * in_stride + s], type));
+    __shared__ double tile[kGlTile][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long tiles_per_group = (out_stride + kGlTile - 1) / kGlTile;
+    const long long total = tiles_per_group * ((n_ind + 31) / 32);
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const int group = (int)(u / tiles_per_group);
+        const long long d0 = (u % tiles_per_group) * kGlTile;
+#pragma unroll
+        for (int h = 0; h < kGlTile / 32; ++h) {
+            const long long d = d0 + lane + 32 * h;
+            const int s = d < L ? src[d] : -1;
+            const double f = s >= 0 ? freq0[s] : 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int il = warp + 8 * r, i = group * 32 + il;
+                double v = 0.0;
+                if (s >= 0 && i < n_ind) {
+                    const int g = (int)(geno0[(int64_t)i * row_words0 + (s >> 5)] >> (2 * (s & 31))) & 3;
+                    // per-genotype error (readTGLSData) → per-genotype LOD (lod(), garlic-roh.cpp:355-386)
+                    v = lod_eval(g, f, gl_to_error(in[(int64_t)i * in_stride + s], type));
+                }
+                tile[lane + 32 * h][il] = v;
+            }
+        }
+        __syncthreads();
+        double* o = out + ((int64_t)group * out_stride + d0) * kGlLanes;
+        const int rows = (int)((out_stride - d0) < kGlTile ? (out_stride - d0) : kGlTile);
+        for (int e = threadIdx.x; e < rows * 32; e += 256) o[e] = tile[e >> 5][e & 31];
+        __syncthreads();
     }
 }
 
@@ -947,10 +1180,9 @@ cudaError_t launch_compact_gl(const double* in, int64_t in_stride, const int* sr
                               int64_t row_words0, const double* freq0, double* out, int64_t out_stride, int n_ind, int type,
                               cudaStream_t st)
 {
-    const long long total = L * n_ind;
-    if (!total) return cudaSuccess;
-    long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 64) blocks = 148 * 64;
+    if (!n_ind) return cudaSuccess;
+    long long blocks = ((out_stride + kGlTile - 1) / kGlTile) * ((n_ind + 31) / 32);
+    if (blocks > 148 * 32) blocks = 148 * 32;
     compact_gl_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, in_stride, src, L, geno0, row_words0, freq0, out, out_stride, n_ind, type);
     return cudaGetLastError();
 }

@@ -26,7 +26,7 @@ cudaError_t launch_coarse(const CoarseParams& P, const Item* items, int n_items,
                           int cand_stride, cudaStream_t st);
 cudaError_t launch_thin_windows(const uint64_t* geno, int64_t row_words, const double* lut, const int* ind_list, int n_lanes,
                                 const int3* segs, int n_segs, const int2* meta, int n_chr, long long n_slots, int step, int W,
-                                double* dump, int64_t dump_stride, cudaStream_t st);
+                                double* dump, int64_t dump_stride, const double* gl, int64_t gl_stride, cudaStream_t st);
 cudaError_t launch_fill_f64(double* p, size_t n, double v, cudaStream_t st);
 cudaError_t launch_first_allele(const uint8_t* alleles, int n_snp, int n_ind, int ind_offset, int missing,
                                 unsigned long long* key, cudaStream_t st);

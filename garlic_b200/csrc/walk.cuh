@@ -52,7 +52,7 @@ struct LaneCtx {
     GHD double aval(int s, int g) const
     {
         if (SRC == 0) return *reinterpret_cast<const double*>(tile + ((uint32_t)(s - tile_lo) * 32u + (uint32_t)g * 8u));
-        return glrow[s];   // GL mode: per-genotype LOD, evaluated once by compact_gl_kernel
+        return glrow[(int64_t)s * kGlLanes];   // GL mode: per-genotype LOD, evaluated once by compact_gl_kernel
     }
 };
 
@@ -265,7 +265,7 @@ GHD void walk_item(const WalkParams& P, const Item& it, int k_slot, bool active,
     C.tile = tile;
     C.tile_lo = tile_lo;
     C.freq = P.freq;
-    C.glrow = (SRC == 1) ? P.gl + (int64_t)ind * P.gl_stride : nullptr;
+    C.glrow = (SRC == 1) ? gl_lane(P, ind) : nullptr;
     const int NW = ((W + 31) >> 5) + 1;
     const bool chk = P.tol > 0;
 

@@ -140,7 +140,7 @@ __device__ __forceinline__ void wlod_walk_item(const WlodParams& Q, const Item& 
     const int W = P.W;
     const int ind = P.ind_list ? P.ind_list[k_slot] : k_slot;
     const uint64_t* row = P.geno + (int64_t)ind * P.row_words;
-    const double* glrow = (SRC == 1) ? P.gl + (int64_t)ind * P.gl_stride : nullptr;
+    const double* glrow = (SRC == 1) ? gl_lane(P, ind) : nullptr;
     const int NW = ((W + 31) >> 5) + 1;
     for (int w = 0; w < NW; ++w) ring[w * rstride] = 0;
     int cov = 0, run_start = -1;
@@ -155,7 +155,7 @@ __device__ __forceinline__ void wlod_walk_item(const WlodParams& Q, const Item& 
                 const int g = (int)(row[s >> 5] >> (2 * (s & 31))) & 3;
                 double sc;
                 if (SRC == 0) sc = Q.wlut[(int64_t)s * 4 + g];
-                else sc = glrow[s] * Q.nomut[s] * Q.norec[s];
+                else sc = glrow[(int64_t)s * kGlLanes] * Q.nomut[s] * Q.norec[s];
                 acc += sc * inv[k];
             }
             f = acc >= P.cutoff;
@@ -231,7 +231,7 @@ wlod_mma_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items,
             if (k >= P.n_lanes) k = P.n_lanes - 1;
             const int ia = P.ind_list ? P.ind_list[k] : k;
             rowA[rg] = P.geno + (int64_t)ia * P.row_words;
-            glA[rg] = (SRC == 1) ? P.gl + (int64_t)ia * P.gl_stride : nullptr;
+            glA[rg] = (SRC == 1) ? gl_lane(P, ia) : nullptr;
         }
         LaneState S;
         S.win = 0; S.cov = 0; S.run_start = -1; S.fw = 0; S.hist = 0; S.ambig = false;
@@ -258,7 +258,7 @@ wlod_mma_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items,
                         const int g = (int)(rowA[rg][wi] >> sh) & 3;
                         double a;
                         if (SRC == 0) a = Q.wlut[(int64_t)s * 4 + g];
-                        else a = glA[rg][s] * Q.nomut[s] * Q.norec[s];
+                        else a = glA[rg][(int64_t)s * kGlLanes] * Q.nomut[s] * Q.norec[s];
                         dmma_m8n8k4(c[rg][0], c[rg][1], a, b);
                     }
                 }

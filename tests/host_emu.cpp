@@ -13,6 +13,17 @@
 
 using namespace garlic;
 
+// the walker reads GL-mode values lane-interleaved (common.cuh:gl_lane); tests hand a row-major [n_ind][gl_stride] matrix
+static std::vector<double> interleave_gl(const double* gl, int64_t gl_stride, int n_ind)
+{
+    std::vector<double> t;
+    if (!gl) return t;
+    t.assign((size_t)((n_ind + 31) / 32) * gl_stride * kGlLanes, 0.0);
+    for (int i = 0; i < n_ind; ++i)
+        for (int64_t s = 0; s < gl_stride; ++s) t[((size_t)(i >> 5) * gl_stride + s) * kGlLanes + (i & 31)] = gl[(size_t)i * gl_stride + s];
+    return t;
+}
+
 extern "C" {
 
 // returns number of ROH written (≤ cap); out4 = (ind, chr, a, b) quadruples; *n_amb = ambiguous pairs
@@ -33,7 +44,8 @@ int emu_call_roh(const uint64_t* geno, int64_t row_words, const double* lut, con
     unsigned cnt[4] = {0, 0, 0, 0};
     WalkParams P;
     memset(&P, 0, sizeof(P));
-    P.geno = geno; P.row_words = row_words; P.lut = lut; P.gl = gl; P.gl_stride = gl_stride; P.freq = freq;
+    const std::vector<double> glt = interleave_gl(gl, gl_stride, n_ind);
+    P.geno = geno; P.row_words = row_words; P.lut = lut; P.gl = gl ? glt.data() : nullptr; P.gl_stride = gl_stride; P.freq = freq;
     P.n_lanes = n_ind; P.W = W; P.thr = thr; P.cutoff = cutoff; P.tol = tol;
     P.out = recs.data(); P.out_count = cnt; P.out_cap = (unsigned)recs.size(); P.amb = amb.data(); P.amb_cap = (unsigned)amb.size();
     const int NW = ((W + 31) >> 5) + 1;
@@ -70,7 +82,8 @@ int emu_windows(const uint64_t* geno, int64_t row_words, const double* lut, cons
     unsigned cnt[4] = {0, 0, 0, 0};
     WalkParams P;
     memset(&P, 0, sizeof(P));
-    P.geno = geno; P.row_words = row_words; P.lut = lut; P.gl = gl; P.gl_stride = gl_stride; P.freq = freq;
+    const std::vector<double> glt = interleave_gl(gl, gl_stride, n_ind);
+    P.geno = geno; P.row_words = row_words; P.lut = lut; P.gl = gl ? glt.data() : nullptr; P.gl_stride = gl_stride; P.freq = freq;
     P.n_lanes = n_ind; P.W = W; P.thr = 1; P.cutoff = 0; P.tol = 0; P.out_count = cnt;
     P.dump = out; P.dump_stride = slots; P.dump_step = step;
     const int NW = ((W + 31) >> 5) + 1;

@@ -331,3 +331,49 @@ def test_weighted_tensor_core_pass_equals_exact_sums(W, gl):
         if cutoff != 0.5:
             assert st["ambiguous_pairs"] >= 1       # individual 5 holds a window equal to the cutoff
     hp.close()
+
+
+@pytest.mark.parametrize("W", [200, 50, 16, 31, 330])
+def test_gl_ring_walker_equals_generic_walker(W):
+    """GL mode, pass 2: gl_walk_kernel (bulk-copied shared-memory ring over the lane-interleaved likelihood matrix)
+    returns the same ROH as the generic per-lane walker and as whole-segment chains; 77 individuals leave a ragged
+    last group; cutoff on an actual window value forces exact re-evaluation of an ambiguous pair."""
+    import os
+    names, offs, pos, cens = synth.make_positions_genomewide(31, 40000, n_chr=3)
+    codes = synth.make_codes(31, 77, 40000)
+
+    class DS:
+        pass
+    ds = DS()
+    ds.chr_names, ds.chr_offsets, ds.pos, ds.centromeres = names, offs, pos, cens
+    rng = np.random.default_rng(5)
+    ds.gl = rng.choice(np.array([0.0004, 0.004, 0.04, 0.5, 3.0, 0.0, 150.0]), size=(40000, 77))
+    ds.gl_type = "PL"
+    hp = HotPath().load(ds, error=None, packed_rows=synth.pack_codes(codes))
+    g = hp.g
+    win = g.windows(W, 1, individuals=np.array([70], np.int32), exact=True)[0]
+    vals = np.sort(win[win != orc.MISSING])
+    thin = g.windows(W, W, individuals=np.array([3, 70], np.int32), exact=False)       # thinned pass 1 (direct sums)
+    full = g.windows(W, 1, individuals=np.array([3, 70], np.int32), exact=True)
+    base = 0
+    for c in range(3):
+        n = int(hp.chr_off[c + 1] - hp.chr_off[c])
+        a, b = thin[:, base:base + (n + W - 1) // W], full[:, hp.chr_off[c]:hp.chr_off[c + 1]][:, ::W]
+        ok = b != orc.MISSING
+        assert np.array_equal(a == orc.MISSING, ~ok)
+        assert np.max(np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), 1e-3), initial=0.0) <= RTOL_WINDOWS
+        base += (n + W - 1) // W
+    for cutoff in (float(vals[int(len(vals) * 0.98)]), 1.0):
+        a = g.call_roh(W, cutoff, 0.25, exact=False).copy()
+        st = g.last_stats()
+        b = g.call_roh(W, cutoff, 0.25, exact=True).copy()
+        os.environ["GARLIC_NO_GL_RING"] = "1"
+        try:
+            c = g.call_roh(W, cutoff, 0.25, exact=True).copy()
+            d = g.call_roh(W, cutoff, 0.25, exact=False).copy()
+        finally:
+            del os.environ["GARLIC_NO_GL_RING"]
+        assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, d) and len(a) > 0
+        if cutoff != 1.0:
+            assert st["ambiguous_pairs"] >= 1
+    hp.close()
