@@ -804,7 +804,7 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
     } else {
     int chunk = 0;
     if (weighted) chunk = std::max(64, pick_chunk(h->L, W, n_lanes, 0) / 8);   // every wLOD window is a fresh sum
-    else if (!exact) chunk = pick_chunk(h->L, W, n_lanes, kTileSnpsMax);
+    else if (!exact) chunk = pick_chunk(h->L, W, n_lanes, h->have_gl ? 0 : kTileSnpsMax);   // GL mode has no table tile
     build_items(h->chr_off, W, segs, chunk, step, items);
     if (upload_items(h, items)) return 1;
     WalkParams P = base_params(h, W);
@@ -853,7 +853,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     segments_from_stretches(h->stretches, W, segs);
     int chunk = 0;
     if (weighted) chunk = std::max(64, pick_chunk(h->L, W, h->n_ind, 0) / 8);
-    else if (!exact) chunk = pick_chunk(h->L, W, h->n_ind, kTileSnpsMax);
+    else if (!exact) chunk = pick_chunk(h->L, W, h->n_ind, h->have_gl ? 0 : kTileSnpsMax);
     build_items(h->chr_off, W, segs, chunk, 0, items);
     if (upload_items(h, items)) return 1;
     int64_t n_win = 0;

@@ -301,26 +301,27 @@ gl_walk_kernel(const WalkParams P, const Item* __restrict__ items, int n_items, 
         const int nblk = (M + 31) >> 5;
         const int NQ = (W + 32 * nblk + kGlPiece - 1) / kGlPiece;   // pieces this walk consumes
         int issued = 0, waited = 0;
+        int islot = 0, wslot = 0;                          // ring slots of piece `issued` / `waited` (no runtime modulo)
         // lanes are done reading a slot before lane 0 hands it back to the copy engine
         auto issue_upto = [&](int qmax) {
             const int hi = qmax + 1 < NQ ? qmax + 1 : NQ;
             if (hi <= issued) return;
             __syncwarp();
-            if (lane == 0) {
-                fence_proxy_async();
-                for (int q = issued; q < hi; ++q) {
-                    const int sl = q % NS;
-                    mbar_expect_tx(&bars[sl], kGlPieceBytes);
-                    tma_load_1d(gl_smem + (size_t)sl * kGlPieceBytes, slab + (size_t)q * kGlPieceBytes, kGlPieceBytes, &bars[sl]);
+            if (lane == 0) fence_proxy_async();
+            for (; issued < hi; ++issued) {
+                if (lane == 0) {
+                    mbar_expect_tx(&bars[islot], kGlPieceBytes);
+                    tma_load_1d(gl_smem + (size_t)islot * kGlPieceBytes, slab + (size_t)issued * kGlPieceBytes, kGlPieceBytes,
+                                &bars[islot]);
                 }
+                if (++islot == NS) islot = 0;
             }
-            issued = hi;
         };
         auto wait_upto = [&](int q) {
             for (; waited <= q; ++waited) {
-                const int sl = waited % NS;
-                mbar_wait(&bars[sl], (uint32_t)(par >> sl) & 1u);
-                par ^= 1ull << sl;
+                mbar_wait(&bars[wslot], (uint32_t)(par >> wslot) & 1u);
+                par ^= 1ull << wslot;
+                if (++wslot == NS) wslot = 0;
             }
         };
         issue_upto(NS - 1);
@@ -355,15 +356,43 @@ gl_walk_kernel(const WalkParams P, const Item* __restrict__ items, int n_items, 
             uint32_t vm = 0xffffffffu;
             const int nv = it.we - tblk;
             if (nv < 32) vm = nv <= 0 ? 0u : ((1u << nv) - 1u);
+            // all 64 shared-memory reads of the block are issued before the dependent chain starts (one warp per
+            // scheduler: nothing else hides the LDS latency); d[] then holds the block's window values.  Only one block
+            // in NS/2 has its slide-in range wrap around the ring: the others read at compile-time offsets.
             uint32_t fhi = 0, flo = 0;
+            double d[32], o[CHK ? 1 : 32];
+            if (kwrap >= 32) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                const double a_in = (k < kwrap ? p_in : p_in2)[k * kGlLanes];
-                const double a_out = p_out[k * kGlLanes];
-                if (CHK) win = win + (a_in - a_out);
-                else win = (win - a_out) + a_in;           // garlic-roh.cpp:98-100
-                if (win >= cut_hi) fhi |= 1u << k;         // garlic-roh.cpp:450
-                if (CHK) { if (win >= cut_lo) flo |= 1u << k; }
+                for (int k = 0; k < 32; ++k) {
+                    if (CHK) d[k] = p_in[k * kGlLanes] - p_out[k * kGlLanes];
+                    else { d[k] = p_in[k * kGlLanes]; o[k] = p_out[k * kGlLanes]; }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const double a_in = (k < kwrap ? p_in : p_in2)[k * kGlLanes];
+                    if (CHK) d[k] = a_in - p_out[k * kGlLanes];
+                    else { d[k] = a_in; o[k] = p_out[k * kGlLanes]; }
+                }
+            }
+            if (CHK) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    win = win + d[k];
+                    d[k] = win;
+                    if (win >= cut_lo) flo |= 1u << k;
+                }
+                // a window at or above cutoff + tol is also above cutoff − tol: the second test only runs where needed
+                if (__any_sync(0xffffffffu, flo != 0u)) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) if (d[k] >= cut_hi) fhi |= 1u << k;   // garlic-roh.cpp:450
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    win = (win - o[k]) + d[k];             // garlic-roh.cpp:98-100
+                    if (win >= cut_hi) fhi |= 1u << k;     // garlic-roh.cpp:450
+                }
             }
             S.win = win;
             fhi &= vm;
@@ -411,9 +440,10 @@ static int gl_ring_slots(int W, size_t* smem_bytes)
     int ns_min = span + 3; ns_min += ns_min & 1;
     if (ns_min > 56 || (size_t)ns_min * kGlPieceBytes + fixed > budget) return 0;
     // as many CTAs per SM as the minimum ring allows, then spend the rest of that share on pieces in flight
-    const int ctas = (int)((budget - 1024) / ((size_t)ns_min * kGlPieceBytes + fixed + 1024));
+    int ctas = (int)((budget - 1024) / ((size_t)ns_min * kGlPieceBytes + fixed + 1024));
+    if (const char* e = getenv("GARLIC_GL_CTAS")) { const int c = atoi(e); if (c >= 1 && c < ctas) ctas = c; }
     int ns = (int)(((budget - 1024) / (ctas > 0 ? ctas : 1) - fixed - 1024) / kGlPieceBytes);
-    if (ns > span + 8) ns = span + 8;
+    if (ns > span + 24) ns = span + 24;
     if (ns > 56) ns = 56;
     ns -= ns & 1;
     if (ns < ns_min) ns = ns_min;
