@@ -430,12 +430,199 @@ gl_walk_kernel(const WalkParams P, const Item* __restrict__ items, int n_items, 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K5-GL pass 2, relay form (tolerance-checked pass only).  One warp per scheduler cannot hide its own instruction
+// latencies, and shared memory (the W-SNP history) caps the CTAs per SM at about three.  Here K warps (2..4) share ONE
+// ring and take the item's 32-window blocks in turn (block j → warp j mod K).  A warp loads its block's 64 values,
+// forms d = in − out and their running sum P inside the block without waiting for anybody; only then does it take the
+// window value at the end of block j−1 (`base`, 32 doubles handed through shared memory), publishes base + P[31] for
+// the next warp at once, and tests base + P[k] against cutoff ± tol.  The coverage / run state (cover_block) travels
+// the same way one step behind.  Sums are re-associated (base + prefix instead of one chain): same error bound as the
+// chunked chain, windows within tol of the cutoff are re-walked exactly.
+// Safety of slot reuse with K warps (a warp may lag K−1 blocks): floor(W/16) >= 2K, checked by the launcher.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void seq_wait(const volatile int* p, int v)
+{
+    while (*p < v) { }
+    __threadfence_block();
+}
+__device__ __forceinline__ void seq_post(volatile int* p, int v, int lane)
+{
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) *p = v;
+}
+
+__global__ void __launch_bounds__(128)
+gl_relay_kernel(const WalkParams P, const Item* __restrict__ items, int n_items, int n_groups, int NS)
+{
+    extern __shared__ __align__(128) unsigned char gl_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, K = blockDim.x >> 5;
+    const int W = P.W;
+    const int NW = ((W + 31) >> 5) + 1;
+    const double* ring = reinterpret_cast<const double*>(gl_smem);
+    unsigned char* aux = gl_smem + (size_t)NS * kGlPieceBytes;
+    uint32_t* fring = reinterpret_cast<uint32_t*>(aux) + lane;                       // [NW][32] flag-word history
+    uint64_t* bars = reinterpret_cast<uint64_t*>(aux + (size_t)NW * 128);           // [64]
+    double* sbase = reinterpret_cast<double*>(aux + (size_t)NW * 128 + 512) + lane;   // [32] window value handed on
+    int* scov = reinterpret_cast<int*>(aux + (size_t)NW * 128 + 512 + 256) + lane;    // [3][32] cov, run_start, hist
+    volatile int* seq = reinterpret_cast<volatile int*>(aux + (size_t)NW * 128 + 512 + 256 + 384);   // [0] base, [1] cover
+    if (threadIdx.x == 0) for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+    __syncthreads();
+    const int R = NS * kGlPiece;
+    uint64_t par = 0;                                      // every warp follows every piece: same parity history
+    const double cut_hi = P.cutoff + P.tol, cut_lo = P.cutoff - P.tol;
+    const int r = (32 - (W & 31)) & 31;
+    const long long total = (long long)n_items * n_groups;
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const int item = (int)(u / n_groups), group = (int)(u % n_groups);
+        const Item it = items[item];
+        const int ind = group * 32 + lane;
+        const bool active = ind < P.n_lanes;
+        const unsigned char* slab = reinterpret_cast<const unsigned char*>(P.gl + ((int64_t)group * P.gl_stride + it.w0) * kGlLanes);
+        const int M = it.own_hi - 1 - it.w0;
+        const int nblk = (M + 31) >> 5;
+        const int NQ = (W + 32 * nblk + kGlPiece - 1) / kGlPiece;
+        __syncthreads();                                   // every warp is done with the previous walk's shared state
+        if (threadIdx.x == 0) { seq[0] = -1; seq[1] = -1; }
+        __syncthreads();
+        int waited = 0, wslot = 0;
+        auto wait_upto = [&](int q) {
+            for (; waited <= q; ++waited) {
+                mbar_wait(&bars[wslot], (uint32_t)(par >> wslot) & 1u);
+                par ^= 1ull << wslot;
+                if (++wslot == NS) wslot = 0;
+            }
+        };
+        auto issue = [&](int q0, int q1) {                 // pieces [q0, q1) ∩ [0, NQ), by this warp's lane 0
+            if (q1 > NQ) q1 = NQ;
+            if (q0 >= q1) return;
+            __syncwarp();
+            if (lane == 0) {
+                fence_proxy_async();
+                int sl = q0 % NS;
+                for (int q = q0; q < q1; ++q) {
+                    mbar_expect_tx(&bars[sl], kGlPieceBytes);
+                    tma_load_1d(gl_smem + (size_t)sl * kGlPieceBytes, slab + (size_t)q * kGlPieceBytes, kGlPieceBytes, &bars[sl]);
+                    if (++sl == NS) sl = 0;
+                }
+            }
+        };
+        if (warp == 0) issue(0, NS);
+        // every warp sees the first pieces land before any slot can be reused (keeps the parity history in step)
+        wait_upto((W + 31) / kGlPiece < NQ ? (W + 31) / kGlPiece : NQ - 1);
+        bool ambig = false;
+        if (warp == 0) {
+            // fresh sum for window w0, ascending (garlic-roh.cpp:57-71); these pieces sit in slots 0, 1, …
+            double win = 0.0;
+            for (int q = 0; q * kGlPiece < W; ++q) {
+                const int n = W - q * kGlPiece < kGlPiece ? W - q * kGlPiece : kGlPiece;
+                const double* p = ring + (size_t)q * kGlPiece * kGlLanes + lane;
+                for (int i = 0; i < n; ++i) win += p[i * kGlLanes];
+            }
+            const bool f0 = win >= cut_hi;
+            ambig = (f0 != (win >= cut_lo));
+            const int cov0 = (int)f0;
+            sbase[0] = win;
+            scov[0] = cov0;
+            scov[32] = (it.w0 >= it.own_lo && cov0 >= P.thr) ? it.w0 : -1;
+            scov[64] = (int)((uint32_t)f0 << 31);
+            if (W > 32) {
+                for (int w = 0; w < NW; ++w) fring[w * 32] = 0;
+                fring[0] = (uint32_t)f0 << 31;
+            }
+            seq_post(&seq[0], 0, lane);
+            seq_post(&seq[1], 0, lane);
+        }
+        __syncthreads();                                   // no slot is handed back while the fresh sum still reads the ring
+        int wr = (1 + warp) % NW;
+        int pin = (W + 32 * warp) % R, pout = (32 * warp) % R;
+        for (int j = warp; j < nblk; j += K) {
+            const int tblk = it.w0 + 1 + 32 * j;
+            wait_upto((W + 32 * j + 31) / kGlPiece);
+            const int kwrap = R - pin;
+            const double* p_in = ring + (size_t)pin * kGlLanes + lane;
+            const double* p_in2 = p_in - (size_t)R * kGlLanes;
+            const double* p_out = ring + (size_t)pout * kGlLanes + lane;
+            double d[32];
+            if (kwrap >= 32) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) d[k] = p_in[k * kGlLanes] - p_out[k * kGlLanes];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) d[k] = (k < kwrap ? p_in : p_in2)[k * kGlLanes] - p_out[k * kGlLanes];
+            }
+#pragma unroll
+            for (int k = 1; k < 32; ++k) d[k] = d[k - 1] + d[k];
+            // this block's slide-out pieces 2j, 2j+1 are dead: their slots take pieces 2j+NS, 2j+1+NS
+            issue(2 * j + NS, 2 * j + 2 + NS);
+            seq_wait(&seq[0], j);
+            const double base = sbase[0];
+            sbase[0] = base + d[31];
+            seq_post(&seq[0], j + 1, lane);
+            uint32_t vm = 0xffffffffu;
+            const int nv = it.we - tblk;
+            if (nv < 32) vm = nv <= 0 ? 0u : ((1u << nv) - 1u);
+            uint32_t fhi = 0, flo = 0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                d[k] = base + d[k];
+                if (d[k] >= cut_lo) flo |= 1u << k;
+            }
+            if (__any_sync(0xffffffffu, flo != 0u)) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) if (d[k] >= cut_hi) fhi |= 1u << k;   // garlic-roh.cpp:450
+            }
+            fhi &= vm; flo &= vm;
+            ambig |= (fhi != flo);
+            // coverage / run state of block j−1 → this block
+            seq_wait(&seq[1], j);
+            LaneState S;
+            S.win = 0; S.fw = 0; S.ambig = false;
+            S.cov = scov[0]; S.run_start = scov[32]; S.hist = (uint32_t)scov[64];
+            uint32_t ow = 0;
+            if (W > 32) {
+                int r0 = wr + 1; if (r0 >= NW) r0 -= NW;
+                int r1 = r0 + 1; if (r1 >= NW) r1 -= NW;
+                const uint32_t w0_ = fring[r0 * 32], w1_ = fring[r1 * 32];
+                ow = r ? ((w0_ >> r) | (w1_ << (32 - r))) : w0_;
+            }
+            const bool full = (tblk + 31 < it.we) && (tblk >= it.own_lo) && (tblk + 31 < it.own_hi);
+            if (full) cover_block<true>(P, it, S, ind, active, fhi, ow, tblk);
+            else cover_block<false>(P, it, S, ind, active, fhi, ow, tblk);
+            if (W > 32) fring[wr * 32] = S.fw;
+            if (j == nblk - 1) {
+                if (S.run_start >= 0) emit_run(P, it, ind, active, S.run_start, it.own_hi - 1);
+            } else {
+                scov[0] = S.cov; scov[32] = S.run_start; scov[64] = (int)S.hist;
+                seq_post(&seq[1], j + 1, lane);
+            }
+            wr += K; while (wr >= NW) wr -= NW;
+            pin += 32 * K; while (pin >= R) pin -= R;
+            pout += 32 * K; while (pout >= R) pout -= R;
+        }
+        if (nblk == 0 && warp == 0) {
+            const int rs = scov[32];
+            if (rs >= 0) emit_run(P, it, ind, active, rs, it.own_hi - 1);
+        }
+        if (ambig && active) {
+            const unsigned p = atomicAdd(P.out_count + 1, 1u);
+            if (p < P.amb_cap) {
+                RohRec rr;
+                rr.ind = ind; rr.a = 0; rr.b = 0; rr.tag = it.seg;
+                P.amb[p] = rr;
+            }
+        }
+        wait_upto(NQ - 1);                                 // every warp has followed every piece of this walk
+    }
+}
+
 // ring slots for window size W (even; 0 = the ring does not fit, use the generic walker)
 static int gl_ring_slots(int W, size_t* smem_bytes)
 {
     const int span = (W + 31) / kGlPiece + 1;              // pieces a block's slide-out .. slide-in range touches
     const int NW = ((W + 31) >> 5) + 1;
-    const size_t fixed = (size_t)NW * 128 + 64 * 8 + 128;
+    const size_t fixed = (size_t)NW * 128 + 64 * 8 + 256 + 384 + 128;     // flag ring, mbarriers, relay hand-over area
     const size_t budget = 227 * 1024;
     int ns_min = span + 3; ns_min += ns_min & 1;
     if (ns_min > 56 || (size_t)ns_min * kGlPieceBytes + fixed > budget) return 0;
@@ -447,7 +634,7 @@ static int gl_ring_slots(int W, size_t* smem_bytes)
     if (ns > 56) ns = 56;
     ns -= ns & 1;
     if (ns < ns_min) ns = ns_min;
-    *smem_bytes = (size_t)ns * kGlPieceBytes + (size_t)NW * 128 + 64 * 8;
+    *smem_bytes = (size_t)ns * kGlPieceBytes + fixed;
     return ns;
 }
 
@@ -463,6 +650,17 @@ static cudaError_t launch_gl_walk(const WalkParams& P, const Item* items, int n_
     if (grid > total) grid = total;
     cudaError_t e;
     if (P.tol > 0) {
+        // relay warps per ring: floor(W/16) >= 2K keeps slot reuse safe with a warp lagging K-1 blocks
+        int K = 1;
+        // and (W+31)/16 >= 4K-1 keeps every warp's mbarrier parity history in step (a slot completes at most once unseen)
+        while (K < 4 && (P.W / kGlPiece) >= 2 * (K + 1) && (P.W + 31) / kGlPiece >= 4 * (K + 1) - 1) ++K;
+        if (const char* ev = getenv("GARLIC_GL_WARPS")) { const int k = atoi(ev); if (k >= 1 && k < K) K = k; }
+        if (K >= 2) {
+            e = cudaFuncSetAttribute(gl_relay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            gl_relay_kernel<<<(unsigned)grid, 32 * K, smem, st>>>(P, items, n_items, n_groups, NS);
+            return cudaGetLastError();
+        }
         e = cudaFuncSetAttribute(gl_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         gl_walk_kernel<true><<<(unsigned)grid, 32, smem, st>>>(P, items, n_items, n_groups, NS);

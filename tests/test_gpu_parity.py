@@ -377,3 +377,36 @@ def test_gl_ring_walker_equals_generic_walker(W):
         if cutoff != 1.0:
             assert st["ambiguous_pairs"] >= 1
     hp.close()
+
+
+@pytest.mark.parametrize("W,n_ind,L0", [(200, 77, 40000), (330, 200, 60000), (64, 40, 30000)])
+def test_gl_relay_warps_equal_single_warp(W, n_ind, L0):
+    """GL mode, pass 2: the relay kernel (K warps sharing one ring, base + in-block prefix) returns the same ROH for
+    every K as the single-warp ring walker, repeatedly (cache-resident data makes the bulk copies land early: the
+    hand-over and slot-reuse ordering is what this exercises)."""
+    import os
+    names, offs, pos, cens = synth.make_positions_genomewide(31, L0, n_chr=3)
+    codes = synth.make_codes(31, n_ind, L0)
+
+    class DS:
+        pass
+    ds = DS()
+    ds.chr_names, ds.chr_offsets, ds.pos, ds.centromeres = names, offs, pos, cens
+    rng = np.random.default_rng(5)
+    ds.gl = rng.choice(np.array([0.0004, 0.004, 0.04, 0.5, 3.0, 0.0, 150.0]), size=(L0, n_ind))
+    ds.gl_type = "PL"
+    hp = HotPath().load(ds, error=None, packed_rows=synth.pack_codes(codes))
+    g = hp.g
+    try:
+        os.environ["GARLIC_GL_WARPS"] = "1"
+        ref = g.call_roh(W, 1.0, 0.25).copy()
+        assert len(ref) > 50
+        for K in (2, 3, 4):
+            os.environ["GARLIC_GL_WARPS"] = str(K)
+            for _ in range(3):
+                assert np.array_equal(g.call_roh(W, 1.0, 0.25), ref)
+    finally:
+        del os.environ["GARLIC_GL_WARPS"]
+    assert np.array_equal(g.call_roh(W, 1.0, 0.25), ref)          # default K
+    assert np.array_equal(g.call_roh(W, 1.0, 0.25, exact=True), ref)
+    hp.close()
