@@ -698,7 +698,7 @@ static int launch_any_walk(garlic_gpu* h, const WalkParams& P, const Item* items
         Q.base = P; Q.wlut = h->d_wlut; Q.invld = h->d_invld; Q.nomut = h->d_nomut; Q.norec = h->d_norec;
         // tolerance-checked fast pass on the FP64 tensor cores; exact mul-then-add sums otherwise (dumps, exact mode,
         // re-evaluation of ambiguous pairs)
-        if (P.tol > 0 && roh && !dump && h->wlod_mma) LAUNCH(launch_wlod_mma(Q, items, n_items, h->have_gl, h->stream));
+        if (P.tol > 0 && roh && !dump && h->wlod_mma && P.W >= kWlodMmaMinW) LAUNCH(launch_wlod_mma(Q, items, n_items, h->have_gl, h->stream));
         else LAUNCH(launch_wlod_walk(Q, items, n_items, h->have_gl, roh, dump, h->stream));
     } else {
         LAUNCH(launch_walk(P, items, n_items, h->have_gl, roh, dump, tile_snps <= kTileSnpsMax ? tile_snps : 0, cl, h->stream));
@@ -852,7 +852,10 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     std::vector<Item> items;
     segments_from_stretches(h->stretches, W, segs);
     int chunk = 0;
-    if (weighted) chunk = std::max(64, pick_chunk(h->L, W, h->n_ind, 0) / 8);
+    // weighted windows are fresh sums: a chunk only pays its W-1 lead-in windows, so chunks are kept long for the
+    // tensor-core pass and short (more parallel items) for the exact kernel
+    if (weighted) chunk = (!exact && h->wlod_mma && W >= kWlodMmaMinW) ? std::max(256, pick_chunk(h->L, W, h->n_ind, 0) / 2)
+                                                                      : std::max(64, pick_chunk(h->L, W, h->n_ind, 0) / 8);
     else if (!exact) chunk = pick_chunk(h->L, W, h->n_ind, h->have_gl ? 0 : kTileSnpsMax);
     build_items(h->chr_off, W, segs, chunk, 0, items);
     if (upload_items(h, items)) return 1;
@@ -883,7 +886,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
             for (const Segment& s : segs) longest = std::max<int64_t>(longest, s.we - s.ws);
             P.tol = (double)(longest + 2 * W) * 2.220446049250313e-16 * (W + 1) * h->amax;
         }
-        if (!exact && weighted && h->wlod_mma) {
+        if (!exact && weighted && h->wlod_mma && W >= kWlodMmaMinW) {
             // |DMMA sum − reference mul-then-add sum| ≤ (W+8)·2ε·W·amax: scores are bounded by amax (nomut, norec ≤ 1)
             // and 1/LD ≤ 1 because every LD sum contains the diagonal term 1 (garlic-data.cpp:521-527)
             P.tol = (double)(W + 8) * 2.0 * 2.220446049250313e-16 * W * h->amax;
@@ -1050,7 +1053,9 @@ int garlic_gpu_ld_band(garlic_gpu_t* h, int winsize, const int32_t* ld_individua
     if (garlic_gpu_get_hom_freq(h, homf.data())) return 1;
     if (dev_alloc(h, &h->d_homf, (size_t)L)) return 1;
     CK(cudaMemcpyAsync(h->d_homf, homf.data(), L * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if (dev_alloc(h, &h->d_invld, (size_t)(L + kPad) * W)) return 1;
+    // zero-padded weight rows (wlod.h); rows of windows that do not exist stay all-zero
+    if (dev_alloc(h, &h->d_invld, (size_t)(L + kPad) * inv_stride(W))) return 1;
+    CK(cudaMemsetAsync(h->d_invld, 0, (size_t)(L + kPad) * inv_stride(W) * sizeof(double), h->stream));
     double* d_ld = nullptr;
     if (out_ld) CK(cudaMalloc(&d_ld, (size_t)L * W * sizeof(double)));
     int launches = 0;

@@ -2,6 +2,7 @@
 // 558-583) and K5-W weighted windows fused with ROH assembly (src/garlic-roh.cpp:204-277,409-546).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "common.cuh"
 #include "walk.cuh"
 #include "wlod.h"
@@ -94,7 +95,7 @@ __global__ void ld_sum_kernel(const double* __restrict__ P, const int* __restric
         const double* row = P + j * D + (W - 1 - k);
         double acc = 0.0;
         for (int n = 0; n < W; ++n) acc += row[n];
-        invld[w * W + k] = 1.0 / acc;
+        invld[w * (W + kInvFront + kInvBack) + kInvFront + k] = 1.0 / acc;
         if (ld_out) ld_out[w * W + k] = acc;
     }
 }
@@ -114,7 +115,6 @@ cudaError_t launch_ld_band(const uint64_t* geno, int64_t row_words, const int* l
     auto blocks = [](long long n) { long long b = (n + 255) / 256; return (unsigned)(b > 148 * 64 ? 148 * 64 : b); };
     ld_planes_kernel<<<blocks(L), 256, 0, st>>>(geno, row_words, ld_ind, n_ld, L, nw, planes);
     ld_pairs_kernel<<<blocks(L * (2 * W - 1)), 256, 0, st>>>(planes, nw, homf, chr_of, chr_start, n_chr, L, W, P);
-    cudaMemsetAsync(invld, 0, (size_t)L * W * sizeof(double), st);
     if (ld_out) cudaMemsetAsync(ld_out, 0, (size_t)L * W * sizeof(double), st);
     ld_sum_kernel<<<blocks(L * W), 256, 0, st>>>(P, chr_of, chr_start, n_chr, L, W, invld, ld_out);
     *n_launches = 3;
@@ -148,7 +148,7 @@ __device__ __forceinline__ void wlod_walk_item(const WlodParams& Q, const Item& 
     for (int t = it.w0, q = 0; t < t_end; ++t, ++q) {
         bool f = false;
         if (t < it.we) {
-            const double* inv = Q.invld + (int64_t)t * W;
+            const double* inv = Q.invld + (int64_t)t * (W + kInvFront + kInvBack) + kInvFront;
             double acc = 0.0;
             for (int k = 0; k < W; ++k) {
                 const int s = t + k;
@@ -212,7 +212,6 @@ wlod_mma_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items,
     uint32_t* ring = ring_smem + threadIdx.x;
     const int rstride = blockDim.x;
     const double cut_hi = P.cutoff + P.tol, cut_lo = P.cutoff - P.tol;
-    const int KK = (W + 7 + 3) >> 2;          // k-steps of 4 SNPs covering m = 0 .. W+6
     const int j = lane >> 2, mq = lane & 3;    // window column / SNP-within-k-step of this lane's B element; row j of A
     for (long long u = blockIdx.x; u < total; u += gridDim.x) {
         const int item = (int)(u / gblocks);
@@ -237,37 +236,93 @@ wlod_mma_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items,
         S.win = 0; S.cov = 0; S.run_start = -1; S.fw = 0; S.hist = 0; S.ambig = false;
         if (W > 32) for (int w = 0; w < NW; ++w) ring[w * rstride] = 0;
         int wr = 1 % NW;
-        for (int tb = it.w0; tb < it.own_hi; tb += 32) {
+        // Quads (4 SNPs) of a block: tile q (windows tb+8q..+7) holds quads 2q .. E+2q, E = (W+6)/4.  Rounded to pairs of
+        // quads (E2 odd) the tile sets are compile-time constants: ramp-up {0},{0,1},{0,1,2}, steady {0..3}, ramp-down
+        // {1,2,3},{2,3},{3} — no predicated tensor-core instructions; the operand loads need no predicates either
+        // because weight rows are zero-padded (wlod.h) and windows past the segment end are masked afterwards.
+        const int E2 = ((W + 6) / 4) | 1;
+        const int ldw = W + kInvFront + kInvBack;
+        // blocks start on a multiple of 4 SNPs (windows before w0 are masked off below): a quad then never straddles a
+        // packed 64-bit genotype word and the word reload is a warp-uniform branch taken every 8th quad
+        for (int tb = it.w0 & ~3; tb < it.own_hi; tb += 32) {
             uint32_t fhi = 0, flo = 0;
-#pragma unroll 1
-            for (int q = 0; q < 4; ++q) {
-                const int t0 = tb + 8 * q;
-                double c[4][2];
+            // c[q][rg]: 8 windows tb+8q.. x 8 individuals 8rg.. (two accumulator columns per lane)
+            double c[4][4][2];
 #pragma unroll
-                for (int rg = 0; rg < 4; ++rg) { c[rg][0] = 0.0; c[rg][1] = 0.0; }
-                const int t = t0 + j;                                  // window of this lane's weight column
-                const double* invrow = Q.invld + (int64_t)t * W;
-                const bool tvalid = t < it.we;
-                for (int kk = 0; kk < KK; ++kk) {
-                    const int m = 4 * kk + mq, s = t0 + m, ko = m - j;
-                    const double b = (tvalid && ko >= 0 && ko < W) ? invrow[ko] : 0.0;
-                    const int64_t wi = s >> 5;
-                    const int sh = 2 * (s & 31);
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
-                    for (int rg = 0; rg < 4; ++rg) {
-                        const int g = (int)(rowA[rg][wi] >> sh) & 3;
-                        double a;
-                        if (SRC == 0) a = Q.wlut[(int64_t)s * 4 + g];
-                        else a = glA[rg][(int64_t)s * kGlLanes] * Q.nomut[s] * Q.norec[s];
-                        dmma_m8n8k4(c[rg][0], c[rg][1], a, b);
-                    }
+                for (int rg = 0; rg < 4; ++rg) { c[q][rg][0] = 0.0; c[q][rg][1] = 0.0; }
+            // this lane's weight rows: window tb+8q+j of each tile; element for block-relative SNP m is invq[q][m]
+            const double* invq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) invq[q] = Q.invld + (int64_t)(tb + 8 * q + j) * ldw + kInvFront - (8 * q + j);
+            uint64_t gw[4];
+            {
+                const int s0 = tb + mq;
+#pragma unroll
+                for (int rg = 0; rg < 4; ++rg) gw[rg] = rowA[rg][s0 >> 5];
+            }
+            // operands of quad kq: ONE A fragment (scores) per row group, shared by every tile of the mask, one B
+            // fragment (weights) per tile
+            auto load_quad = [&](auto mask, int kq, double (&a)[4], double (&b)[4]) {
+                constexpr int MB = decltype(mask)::value;
+                const int m = 4 * kq + mq, s = tb + m;
+                const int sh = 2 * (s & 31);
+                if (kq > 0 && ((tb + 4 * kq) & 31) == 0) {
+#pragma unroll
+                    for (int rg = 0; rg < 4; ++rg) gw[rg] = rowA[rg][s >> 5];
                 }
+#pragma unroll
+                for (int rg = 0; rg < 4; ++rg) {
+                    const uint32_t g8 = ((uint32_t)(gw[rg] >> sh) & 3u) * 8u;
+                    if (SRC == 0) a[rg] = __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(Q.wlut + (int64_t)s * 4) + g8));
+                    else a[rg] = glA[rg][(int64_t)s * kGlLanes] * Q.nomut[s] * Q.norec[s];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if ((MB >> q) & 1) b[q] = __ldg(invq[q] + m);
+            };
+            auto mma_quad = [&](auto mask, const double (&a)[4], const double (&b)[4]) {
+                constexpr int MB = decltype(mask)::value;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if ((MB >> q) & 1) {
+#pragma unroll
+                        for (int rg = 0; rg < 4; ++rg) dmma_m8n8k4(c[q][rg][0], c[q][rg][1], a[rg], b[q]);
+                    }
+            };
+            using M1 = std::integral_constant<int, 0x1>; using M3 = std::integral_constant<int, 0x3>;
+            using M7 = std::integral_constant<int, 0x7>; using MF = std::integral_constant<int, 0xF>;
+            using ME = std::integral_constant<int, 0xE>; using MC = std::integral_constant<int, 0xC>;
+            using M8 = std::integral_constant<int, 0x8>;
+            double a0[4], b0[4], a1[4], b1[4];
+            // loads run one quad ahead of the tensor-core work
+            load_quad(M1(), 0, a0, b0);
+            load_quad(M1(), 1, a1, b1); mma_quad(M1(), a0, b0);
+            load_quad(M3(), 2, a0, b0); mma_quad(M1(), a1, b1);
+            load_quad(M3(), 3, a1, b1); mma_quad(M3(), a0, b0);
+            load_quad(M7(), 4, a0, b0); mma_quad(M3(), a1, b1);
+            load_quad(M7(), 5, a1, b1); mma_quad(M7(), a0, b0);
+            load_quad(MF(), 6, a0, b0); mma_quad(M7(), a1, b1);
+            int kq = 6;
+#pragma unroll 1
+            for (; kq < E2; kq += 2) {
+                load_quad(MF(), kq + 1, a1, b1); mma_quad(MF(), a0, b0);
+                load_quad(MF(), kq + 2, a0, b0); mma_quad(MF(), a1, b1);
+            }
+            load_quad(ME(), kq + 1, a1, b1); mma_quad(ME(), a0, b0);
+            load_quad(MC(), kq + 2, a0, b0); mma_quad(ME(), a1, b1);
+            load_quad(MC(), kq + 3, a1, b1); mma_quad(MC(), a0, b0);
+            load_quad(M8(), kq + 4, a0, b0); mma_quad(MC(), a1, b1);
+            load_quad(M8(), kq + 5, a1, b1); mma_quad(M8(), a0, b0);
+            mma_quad(M8(), a1, b1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
                 // accumulator (row j, columns 2mq, 2mq+1) → flag bits of windows t0+2mq, t0+2mq+1 of individual 8rg+j
                 uint32_t myhi = 0, mylo = 0;
 #pragma unroll
                 for (int rg = 0; rg < 4; ++rg) {
-                    uint32_t bh = ((uint32_t)(c[rg][0] >= cut_hi) | ((uint32_t)(c[rg][1] >= cut_hi) << 1)) << (2 * mq);
-                    uint32_t bl = ((uint32_t)(c[rg][0] >= cut_lo) | ((uint32_t)(c[rg][1] >= cut_lo) << 1)) << (2 * mq);
+                    uint32_t bh = ((uint32_t)(c[q][rg][0] >= cut_hi) | ((uint32_t)(c[q][rg][1] >= cut_hi) << 1)) << (2 * mq);
+                    uint32_t bl = ((uint32_t)(c[q][rg][0] >= cut_lo) | ((uint32_t)(c[q][rg][1] >= cut_lo) << 1)) << (2 * mq);
                     bh |= __shfl_xor_sync(0xffffffffu, bh, 1); bh |= __shfl_xor_sync(0xffffffffu, bh, 2);
                     bl |= __shfl_xor_sync(0xffffffffu, bl, 1); bl |= __shfl_xor_sync(0xffffffffu, bl, 2);
                     // owner lane o holds individual o = 8·(o/8) + (o%8): its byte sits in lanes 4·(o%8)..+3 of row group o/8
@@ -279,7 +334,8 @@ wlod_mma_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items,
                 flo |= mylo << (8 * q);
             }
             const int nv = it.we - tb;                                 // valid windows of the block
-            const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << nv) - 1u));
+            uint32_t vm = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << nv) - 1u));
+            if (tb < it.w0) vm &= ~((1u << (it.w0 - tb)) - 1u);
             fhi &= vm; flo &= vm;
             S.ambig |= (fhi != flo);
             uint32_t ow = 0;

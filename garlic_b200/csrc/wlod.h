@@ -5,10 +5,16 @@
 
 namespace garlic {
 
+// A weight row is kInvFront zeros, the W reciprocals, then zeros up to the stride: the tensor-core pass reads a few
+// elements either side of the band and must find 0 there (no predicates on its operand loads).
+constexpr int kInvFront = 8, kInvBack = 24;
+constexpr int kWlodMmaMinW = 10;   // the tensor-core pass's tile schedule needs (W+6)/4 >= 4
+inline int inv_stride(int W) { return W + kInvFront + kInvBack; }
+
 struct WlodParams {
     WalkParams base;
     const double* wlut;    // [L+pad][4]  lod(g)*nomut*norec for a global error
-    const double* invld;   // [L+pad][W]  1.0 / LD[w][k]
+    const double* invld;   // weight rows, one per window: invld[w * kInvStride(W) + kInvFront + k] = 1.0 / LD[w][k]; zeros around
     const double* nomut;   // [L+pad]     (GL mode: score evaluated per genotype)
     const double* norec;   // [L+pad]
 };
@@ -20,7 +26,8 @@ cudaError_t launch_wlod_walk(const WlodParams& Q, const Item* items, int n_items
 cudaError_t launch_wlod_mma(const WlodParams& Q, const Item* items, int n_items, bool gl_mode, cudaStream_t st);
 
 // LD band: hr² pair matrix over the listed individuals → window sums → reciprocal.
-// invld: [L+pad][W]; ld_out (optional): [L][W] the sums themselves (reference LDData layout).
+// invld: padded weight rows (see above), zero-filled by the caller; ld_out (optional): [L][W] the sums themselves
+// (reference LDData layout).
 cudaError_t launch_ld_band(const uint64_t* geno, int64_t row_words, const int* ld_ind, int n_ld,
                            const double* homf, const int* chr_of, const int* chr_start, int n_chr,
                            long long L, int W, double* invld, double* ld_out, cudaStream_t st, int* n_launches);
