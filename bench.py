@@ -222,7 +222,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-ind", type=int, default=CFG["n_ind"])
     ap.add_argument("--n-loci", type=int, default=CFG["n_loci"])
-    ap.add_argument("--cpu-sample", type=int, default=64, help="individuals in the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=400, help="individuals in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--exact", action="store_true", help="whole-segment chains in pass 2")
     a = ap.parse_args()

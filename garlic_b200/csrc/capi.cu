@@ -1040,13 +1040,26 @@ int garlic_gpu_ld_band(garlic_gpu_t* h, int winsize, const int32_t* ld_individua
     if (winsize < 2 || winsize > kMaxW) FAIL("ld_band: winsize out of range [2,4096]");
     const int64_t L = h->L;
     const int W = winsize;
+    // sharded run: indices address the whole sample (this rank holds [ind_offset, ind_offset + n_ind))
+    int n_total = h->n_ind;
+    if (h->comm) {
+        int* d_n = reinterpret_cast<int*>(h->d_cnt);
+        CK(cudaMemcpyAsync(d_n, &h->n_ind, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        NCK(ncclAllReduce(d_n, d_n, 1, ncclInt32, ncclSum, h->comm, h->stream));
+        CK(cudaMemcpyAsync(&n_total, d_n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     std::vector<int> all;
     if (!ld_individuals) {
-        all.resize(h->n_ind);
-        for (int i = 0; i < h->n_ind; ++i) all[i] = i;
-        ld_individuals = all.data(); n_ld = h->n_ind;
+        all.resize(n_total);
+        for (int i = 0; i < n_total; ++i) all[i] = i;
+        ld_individuals = all.data(); n_ld = n_total;
     }
-    for (int i = 0; i < n_ld; ++i) if (ld_individuals[i] < 0 || ld_individuals[i] >= h->n_ind) FAIL("ld_band: individual index out of range");
+    for (int i = 0; i < n_ld; ++i)
+        if (ld_individuals[i] < 0 || ld_individuals[i] >= n_total) {
+            h->err = "ld_band: individual index " + std::to_string(ld_individuals[i]) + " out of range [0, " + std::to_string(n_total) + ")";
+            return 1;
+        }
     if (upload_indlist(h, ld_individuals, n_ld)) return 1;
     // homFreq over ALL individuals from the reduced counts (garlic-data.cpp:656-676)
     std::vector<double> homf(L);
@@ -1060,7 +1073,8 @@ int garlic_gpu_ld_band(garlic_gpu_t* h, int winsize, const int32_t* ld_individua
     if (out_ld) CK(cudaMalloc(&d_ld, (size_t)L * W * sizeof(double)));
     int launches = 0;
     cudaError_t e = launch_ld_band(h->d_geno, h->row_words, h->d_indlist, n_ld, h->d_homf, h->d_chr_of, h->d_chr_start,
-                                   h->n_chr, L, W, h->d_invld, d_ld, h->stream, &launches);
+                                   h->n_chr, L, W, h->d_invld, d_ld, h->stream, &launches, h->comm,
+                                   h->comm ? h->ind_offset : 0, h->n_ind);
     h->launches += launches;
     if (e != cudaSuccess) { if (d_ld) cudaFree(d_ld); h->err = std::string("ld_band: ") + cudaGetErrorString(e); return 1; }
     if (out_ld) {

@@ -14,15 +14,18 @@ namespace garlic {
 // planes[s][nw..2nw) = homozygous (g∈{0,2}) bits; individual j of the list is bit j&63 of word j>>6.
 // Lanes = consecutive SNPs: a warp reads one packed word per individual (broadcast).
 // ------------------------------------------------------------------------------------------
+// ld_ind holds indices into the WHOLE sample; this GPU owns individuals [ind_lo, ind_lo + n_local) (its rows 0..) and
+// fills only their bits — the other ranks' bits are zero here and arrive by the all-reduce in launch_ld_band.
 __global__ void ld_planes_kernel(const uint64_t* __restrict__ geno, int64_t row_words, const int* __restrict__ ld_ind,
-                                 int n_ld, long long L, int nw, uint64_t* __restrict__ planes)
+                                 int n_ld, long long L, int nw, uint64_t* __restrict__ planes, int ind_lo, int n_local)
 {
     for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < L; s += (long long)gridDim.x * blockDim.x) {
         for (int w = 0; w < nw; ++w) {
             uint64_t nm = 0, hm = 0;
             const int jmax = min(64, n_ld - w * 64);
             for (int j = 0; j < jmax; ++j) {
-                const int ind = ld_ind[w * 64 + j];
+                const int ind = ld_ind[w * 64 + j] - ind_lo;
+                if (ind < 0 || ind >= n_local) continue;
                 const int g = (int)(geno[(int64_t)ind * row_words + (s >> 5)] >> (2 * (s & 31))) & 3;
                 nm |= (uint64_t)(g != 3) << j;
                 hm |= (uint64_t)(g == 0 || g == 2) << j;
@@ -102,7 +105,8 @@ __global__ void ld_sum_kernel(const double* __restrict__ P, const int* __restric
 
 cudaError_t launch_ld_band(const uint64_t* geno, int64_t row_words, const int* ld_ind, int n_ld,
                            const double* homf, const int* chr_of, const int* chr_start, int n_chr,
-                           long long L, int W, double* invld, double* ld_out, cudaStream_t st, int* n_launches)
+                           long long L, int W, double* invld, double* ld_out, cudaStream_t st, int* n_launches,
+                           ncclComm_t comm, int ind_lo, int n_local)
 {
     *n_launches = 0;
     const int nw = (n_ld + 63) / 64;
@@ -113,7 +117,13 @@ cudaError_t launch_ld_band(const uint64_t* geno, int64_t row_words, const int* l
     e = cudaMalloc(&P, (size_t)L * (2 * W - 1) * sizeof(double));
     if (e != cudaSuccess) { cudaFree(planes); return e; }
     auto blocks = [](long long n) { long long b = (n + 255) / 256; return (unsigned)(b > 148 * 64 ? 148 * 64 : b); };
-    ld_planes_kernel<<<blocks(L), 256, 0, st>>>(geno, row_words, ld_ind, n_ld, L, nw, planes);
+    ld_planes_kernel<<<blocks(L), 256, 0, st>>>(geno, row_words, ld_ind, n_ld, L, nw, planes, ind_lo, n_local);
+    // individuals are sharded over GPUs: every rank sets the bits of the LD individuals it holds, the planes are
+    // combined over NVLink (bits are disjoint, so SUM is OR) and each rank then builds the whole band itself
+    if (comm) {
+        const ncclResult_t nr = ncclAllReduce(planes, planes, (size_t)L * 2 * nw, ncclUint64, ncclSum, comm, st);
+        if (nr != ncclSuccess) { cudaFree(planes); cudaFree(P); return cudaErrorUnknown; }
+    }
     ld_pairs_kernel<<<blocks(L * (2 * W - 1)), 256, 0, st>>>(planes, nw, homf, chr_of, chr_start, n_chr, L, W, P);
     if (ld_out) cudaMemsetAsync(ld_out, 0, (size_t)L * W * sizeof(double), st);
     ld_sum_kernel<<<blocks(L * W), 256, 0, st>>>(P, chr_of, chr_start, n_chr, L, W, invld, ld_out);

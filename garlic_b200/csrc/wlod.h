@@ -1,6 +1,7 @@
 // wlod.h — K6 (LD band) and K5-W (weighted windows → ROH) launch wrappers.
 #pragma once
 #include <cuda_runtime.h>
+#include <nccl.h>
 #include "common.cuh"
 
 namespace garlic {
@@ -25,11 +26,13 @@ cudaError_t launch_wlod_walk(const WlodParams& Q, const Item* items, int n_items
 // fast pass of pass 2 on the FP64 tensor cores (tolerance-checked; needs base.tol > 0)
 cudaError_t launch_wlod_mma(const WlodParams& Q, const Item* items, int n_items, bool gl_mode, cudaStream_t st);
 
-// LD band: hr² pair matrix over the listed individuals → window sums → reciprocal.
+// LD band: hr² pair matrix over the listed individuals → window sums → reciprocal.  ld_ind indexes the whole sample;
+// this GPU holds individuals [ind_lo, ind_lo+n_local); with comm the bit-planes are all-reduced across ranks.
 // invld: padded weight rows (see above), zero-filled by the caller; ld_out (optional): [L][W] the sums themselves
 // (reference LDData layout).
 cudaError_t launch_ld_band(const uint64_t* geno, int64_t row_words, const int* ld_ind, int n_ld,
                            const double* homf, const int* chr_of, const int* chr_start, int n_chr,
-                           long long L, int W, double* invld, double* ld_out, cudaStream_t st, int* n_launches);
+                           long long L, int W, double* invld, double* ld_out, cudaStream_t st, int* n_launches,
+                           ncclComm_t comm, int ind_lo, int n_local);
 
 }  // namespace garlic

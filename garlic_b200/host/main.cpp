@@ -139,6 +139,17 @@ std::vector<int32_t> choose(Ctx& c, int k, int n)
     return out;
 }
 
+// calcLDData (garlic-data.cpp:330-375) on every rank at once: `ld` lists individuals of the whole sample (empty =
+// all); each GPU contributes the bit-planes of the LD individuals it holds and the library all-reduces them.
+bool ld_band_all(Ctx& c, int W, const std::vector<int32_t>& ld)
+{
+    if (!c.team.all([&](Rank& R) {
+            garlic_gpu_set_wlod(R.g, c.o.mu, c.o.M);
+            return rank_ok(R, garlic_gpu_ld_band(R.g, W, ld.empty() ? nullptr : ld.data(), (int)ld.size(), nullptr), "ld_band");
+        })) { LOG.error("ERROR: " + c.team.first_error()); return false; }
+    return true;
+}
+
 // convert[Subset]WinData2DoubleData (garlic-data.cpp:2026-2150): chr → individual → locus, MISSING/NaN dropped.
 // inds: global individual indices (ascending) or nullptr for all; every rank computes the windows of its own
 // individuals and the library all-gathers them (rank order = individual order).
@@ -387,7 +398,7 @@ int main(int argc, char** argv)
     // ---- GPU: coding, counts, freq, filter (K1-K3), individuals sharded over --gpus ranks ----
     const int G = o.gpus;
     if (G < 1 || G > t.n_ind) { LOG.error("ERROR: --gpus must be between 1 and the number of individuals."); return -1; }
-    if (G > 1 && (o.weighted || o.raw_lod)) { LOG.error("ERROR: --weighted and --raw-lod run on one GPU in this round (DESIGN.md §9)."); return -1; }
+    if (G > 1 && o.raw_lod) { LOG.error("ERROR: --raw-lod runs on one GPU in this round (DESIGN.md §9)."); return -1; }
     Team& team = c.team;
     team.start(G);
     uint8_t comm_id[128];
@@ -503,8 +514,7 @@ int main(int argc, char** argv)
             if (o.weighted) {
                 std::vector<int32_t> ld;
                 if (o.ld_subsample > 0 && o.ld_subsample < t.n_ind) ld = choose(c, o.ld_subsample, t.n_ind);
-                garlic_gpu_set_wlod(c.g, o.mu, o.M);
-                if (!gpu_ok(c, garlic_gpu_ld_band(c.g, W, ld.empty() ? nullptr : ld.data(), (int)ld.size(), nullptr), "ld_band")) return false;
+                if (!ld_band_all(c, W, ld)) return false;
             }
             std::vector<double> data;
             if (!thinned_windows(c, W, thin ? W : 1, subp, data)) return false;
@@ -562,8 +572,7 @@ int main(int argc, char** argv)
         fprintf(stderr, "Calculating LD matrix.\n");
         std::vector<int32_t> ld;
         if (o.ld_subsample > 0 && o.ld_subsample < t.n_ind) ld = choose(c, o.ld_subsample, t.n_ind);
-        garlic_gpu_set_wlod(c.g, o.mu, o.M);
-        if (!gpu_ok(c, garlic_gpu_ld_band(c.g, winsize, ld.empty() ? nullptr : ld.data(), (int)ld.size(), nullptr), "ld_band")) return 1;
+        if (!ld_band_all(c, winsize, ld)) return 1;
     }
 
     // ---- --raw-lod: every window of every individual (writeWinData, garlic-data.cpp:1704-1747) ----

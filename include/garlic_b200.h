@@ -124,7 +124,9 @@ int garlic_gpu_get_lut(garlic_gpu_t *h, double *lut);
 int garlic_gpu_get_hom_freq(garlic_gpu_t *h, double *hom_freq);
 
 /* ---- K6: calcLDData / calcHR2LD (src/garlic-data.cpp:330-424,474-527,558-583) ---------------
- * LD individuals (local indices, ascending as gsl_ran_choose returns them) or NULL for all.
+ * LD individuals (ascending as gsl_ran_choose returns them) or NULL for all.  With a communicator attached
+ * (garlic_gpu_comm_init) the indices address the WHOLE sample, every rank passes the same list, and the LD bit-planes
+ * of the ranks' shards are combined by one ncclAllReduce inside the call; otherwise they are this handle's rows.
  * out_ld (may be NULL): the LD sums [L][W] as the reference's LDData (rows ≥ L_c-W+1 are 0). */
 int garlic_gpu_ld_band(garlic_gpu_t *h, int winsize, const int32_t *ld_individuals, int n_ld, double *out_ld);
 /* wLOD parameters (--mu, --M), call before weighted windows */

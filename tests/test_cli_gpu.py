@@ -31,7 +31,7 @@ def run_cli(name, tmp, extra=()):
     with open(os.path.join(GOLDEN, name, "cmd.txt")) as f:
         cmd = f.readline().split()[1:]
     cmd = [a.replace("<tmp>", tmp) for a in cmd if a != "--raw-lod"]
-    r = subprocess.run([BIN] + cmd + list(extra), capture_output=True, text=True, timeout=600)
+    r = subprocess.run([BIN] + cmd + list(extra), capture_output=True, text=True, timeout=180)
     return ds, args, r
 
 
@@ -89,7 +89,15 @@ def test_cli_auto_cutoff_path(name):
         step = want[1, 0] - want[0, 0]
         # the reference binary's own cutoff over 8 runs of this input spans 5 grid points (winsize_multi:
         # -2.03 … -1.17, spacing 0.214; auto_cutoff: -2.45 / -2.29), so "equal" means within that spread
-        assert abs(cut - float(log_value(name, "Selected LOD score cutoff:"))) <= 4.01 * step
+        # … and what is required of the selected cutoff is what the heuristic promises on THIS run's KDE (garlic-kde.cpp:
+        # 142-234): a grid point at a local minimum of the density lying between its two modes; the distance to the
+        # golden run's value is only a sanity bound
+        assert abs(cut - float(log_value(name, "Selected LOD score cutoff:"))) <= 8.01 * step
+        i = int(np.argmin(np.abs(got[:, 0] - cut)))
+        assert abs(got[i, 0] - cut) <= 1e-5 * max(1.0, abs(cut))
+        y = got[:, 1]
+        assert y[i] <= y[i - 1] and y[i] <= y[i + 1]
+        assert y[:i].max() > y[i] and y[i + 1:].max() > y[i]
         if name == "winsize_multi":
             ref = [l.split() for l in golden_text(name, "out.log").splitlines() if l.startswith(" ")]
             mine = [l.split() for l in log.splitlines() if l.startswith(" ")]

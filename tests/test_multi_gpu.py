@@ -12,7 +12,41 @@ from tests.common import arg, load_case, oracle_roh_idx
 pytestmark = pytest.mark.gpu
 
 
+def _run_ranks(target, world, extra, timeout=150):
+    """Spawn one process per rank and collect one result each; a rank that dies or stalls fails the test instead of
+    blocking it (workers also arm faulthandler so a stall leaves a traceback)."""
+    import queue as _queue
+    import time
+    from garlic_b200.api import GarlicGPU
+    comm_id = GarlicGPU.comm_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=target, args=(r, world, comm_id, q) + tuple(extra)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, t0 = {}, time.time()
+    try:
+        while len(got) < world:
+            try:
+                r, val = q.get(timeout=2.0)
+                got[r] = val
+            except _queue.Empty:
+                dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+                assert not dead, "a rank exited with %s" % dead
+                assert time.time() - t0 < timeout, "ranks stalled"
+        for p in procs:
+            p.join(60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+    return got
+
+
 def _worker(rank, world, comm_id, q, name):
+    import faulthandler
+    faulthandler.dump_traceback_later(100, exit=True)
     from garlic_b200 import shard
     from garlic_b200.api import GarlicGPU
     ds, args = load_case(name)
@@ -48,16 +82,7 @@ def test_two_gpu_shards_equal_single_shard(name):
     from garlic_b200.api import GarlicGPU
     from oracle import oracle as orc
     world = 2
-    comm_id = GarlicGPU.comm_id()
-    ctx = mp.get_context("spawn")
-    q = ctx.SimpleQueue()
-    procs = [ctx.Process(target=_worker, args=(r, world, comm_id, q, name)) for r in range(world)]
-    for p in procs:
-        p.start()
-    got = dict(q.get() for _ in range(world))
-    for p in procs:
-        p.join(120)
-        assert p.exitcode == 0
+    got = _run_ranks(_worker, world, (name,))
     ds, args = load_case(name)
     W = arg(args, "--winsize", cast=int)
     err = arg(args, "--error", cast=float)
@@ -84,8 +109,60 @@ def test_two_gpu_shards_equal_single_shard(name):
     assert [tuple(int(v) for v in r) for r in merged] == oracle_roh_idx(res)
 
 
+def _weighted_worker(rank, world, comm_id, q, ld_list):
+    import faulthandler
+    faulthandler.dump_traceback_later(100, exit=True)
+    from garlic_b200 import shard
+    from garlic_b200.api import GarlicGPU
+    from garlic_b200.pipeline import interpolate_map
+    ds, args = load_case("wlod_cm")
+    lo, hi = shard.shard_range(ds.n_ind, world, rank)
+    g = GarlicGPU(rank)
+    g.comm_init(comm_id, rank, world)
+    g.set_shape(hi - lo, ds.n_loci, ds.chr_offsets, ds.pos, ind_offset=lo)
+    g.put_alleles(np.ascontiguousarray(ds.alleles[:, lo:hi]), 0)
+    g.code_alleles()
+    cens = [ds.centromeres.get("chr" + n, (0, 0)) for n in ds.chr_names]
+    C = len(ds.chr_names)
+    chr_param = np.array([[ds.map_pos[c][0], ds.map_pos[c][-1], cens[c][0], cens[c][1]] for c in range(C)], np.int32)
+    freq, keep, L = g.filter(True, chr_param)
+    kept = g.get_kept_index()
+    pos = np.asarray(ds.pos)[kept]
+    off = np.searchsorted(kept, np.asarray(ds.chr_offsets))
+    gpos = np.empty(L)
+    for c in range(C):
+        gpos[off[c]:off[c + 1]], _ = interpolate_map(pos[off[c]:off[c + 1]], ds.map_pos[c], ds.map_cm[c])
+    g.set_tables(0.001, 200000, np.array(cens, np.int32), gpos)
+    g.set_wlod(1e-9, 7)
+    ld = g.ld_band(25, None if ld_list is None else np.asarray(ld_list, np.int32), want_ld=True).copy()
+    roh = g.call_roh(25, 0.5, 0.25, weighted=True)
+    q.put((rank, dict(ld=ld, roh=roh, L=L)))
+    g.close()
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("name", ["lod_0", "lod_2", "lod_small", "gl_pl", "auto_overlap_hg19", "freq_file", "lod_cm"])
+@pytest.mark.parametrize("ld_list", [None, [0, 3, 4, 9, 10, 17, 20, 23]])
+def test_two_gpu_weighted_ld_band_and_roh(ld_list):
+    """--weighted over two shards: the LD individuals' bit-planes are all-reduced inside ld_band, every rank builds the
+    same band (bit-identical to the single-shard oracle) and the merged wLOD ROH equal the oracle's."""
+    from garlic_b200 import shard
+    from garlic_b200.api import GarlicGPU
+    from oracle import oracle as orc
+    world = 2
+    got = _run_ranks(_weighted_worker, world, (ld_list,))
+    ds, args = load_case("wlod_cm")
+    res = orc.run_pipeline(ds, 25, 0.001, 0.5, 0.25, weighted=True, cm=True,
+                           ld_individuals=None if ld_list is None else np.asarray(ld_list, np.int32))
+    want_ld = np.concatenate([c["LD"] for c in res["chroms"]], axis=0)
+    for r in range(world):
+        assert got[r]["L"] == res["n_used"]
+        assert np.array_equal(got[r]["ld"], want_ld, equal_nan=True)
+    merged = shard.merge_roh([got[r]["roh"] for r in range(world)], ds.n_ind, world)
+    assert [tuple(int(v) for v in r) for r in merged] == oracle_roh_idx(res)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("name", ["lod_0", "lod_2", "lod_small", "gl_pl", "auto_overlap_hg19", "freq_file", "lod_cm", "wlod_cm"])
 def test_cli_two_gpus_equals_reference_binary(name):
     """garlic_b200 --gpus 2 (individuals sharded over two GPUs, NCCL exchanges inside the library): every output
     file equals the single-process reference binary's."""
