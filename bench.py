@@ -262,7 +262,7 @@ def main():
         else:
             dev = "cuda:0"
         procs = os.cpu_count() or 1
-        per = 4                                    # individuals per process per step (bounded sample)
+        per = max(1, min(16, n_ind // procs))      # individuals per process per step (bounded sample)
         n_s = procs * per
         rows = make_rows_torch(torch, dev, max(n_s, 256), L0, CFG["seed"], 1000, row_bytes).cpu().numpy()
         codes_all = unpack_rows(rows, L0)

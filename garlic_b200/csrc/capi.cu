@@ -55,6 +55,8 @@ struct garlic_gpu {
     int64_t gl_stride = 0;
     double *d_freq0 = nullptr, *d_freq = nullptr, *d_lut = nullptr, *d_gpos = nullptr;
     double *d_nomut = nullptr, *d_norec = nullptr, *d_wlut = nullptr, *d_invld = nullptr, *d_homf = nullptr;
+    uint64_t* d_ldplanes = nullptr;   // LD scratch: bit-planes and the ordered pair matrix (kept between calls)
+    double* d_ldpairs = nullptr;
     uint8_t* d_keep = nullptr;
     int *d_src = nullptr, *d_pos0 = nullptr, *d_chr_of0 = nullptr, *d_pos = nullptr, *d_chr_of = nullptr,
         *d_chr_start = nullptr, *d_chr_param = nullptr;
@@ -200,6 +202,7 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     cudaStreamSynchronize(h->stream);
     dev_free(h->d_alleles); dev_free(h->d_key); dev_free(h->d_geno0); dev_free(h->d_geno); dev_free(h->d_counts);
     dev_free(h->d_gl0); dev_free(h->d_gl); dev_free(h->d_freq0); dev_free(h->d_freq); dev_free(h->d_lut);
+    dev_free(h->d_ldplanes); dev_free(h->d_ldpairs);
     dev_free(h->d_gpos); dev_free(h->d_nomut); dev_free(h->d_norec); dev_free(h->d_wlut); dev_free(h->d_invld);
     dev_free(h->d_homf); dev_free(h->d_keep); dev_free(h->d_src); dev_free(h->d_pos0); dev_free(h->d_chr_of0);
     dev_free(h->d_pos); dev_free(h->d_chr_of); dev_free(h->d_chr_start); dev_free(h->d_chr_param);
@@ -1061,21 +1064,23 @@ int garlic_gpu_ld_band(garlic_gpu_t* h, int winsize, const int32_t* ld_individua
             return 1;
         }
     if (upload_indlist(h, ld_individuals, n_ld)) return 1;
+    Laps laps("ld_band");
     // homFreq over ALL individuals from the reduced counts (garlic-data.cpp:656-676)
-    std::vector<double> homf(L);
-    if (garlic_gpu_get_hom_freq(h, homf.data())) return 1;
     if (dev_alloc(h, &h->d_homf, (size_t)L)) return 1;
-    CK(cudaMemcpyAsync(h->d_homf, homf.data(), L * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(launch_hom_freq(h->d_counts, h->L0, h->d_src, L, h->d_homf, h->stream));
     // zero-padded weight rows (wlod.h); rows of windows that do not exist stay all-zero
     if (dev_alloc(h, &h->d_invld, (size_t)(L + kPad) * inv_stride(W))) return 1;
     CK(cudaMemsetAsync(h->d_invld, 0, (size_t)(L + kPad) * inv_stride(W) * sizeof(double), h->stream));
+    if (dev_alloc(h, &h->d_ldplanes, ld_planes_words(L, n_ld))) return 1;
+    if (dev_alloc(h, &h->d_ldpairs, ld_pairs_doubles(L, W))) return 1;
     double* d_ld = nullptr;
     if (out_ld) CK(cudaMalloc(&d_ld, (size_t)L * W * sizeof(double)));
+    laps.lap("alloc");
     int launches = 0;
     cudaError_t e = launch_ld_band(h->d_geno, h->row_words, h->d_indlist, n_ld, h->d_homf, h->d_chr_of, h->d_chr_start,
                                    h->n_chr, L, W, h->d_invld, d_ld, h->stream, &launches, h->comm,
-                                   h->comm ? h->ind_offset : 0, h->n_ind);
-    h->launches += launches;
+                                   h->comm ? h->ind_offset : 0, h->n_ind, h->d_ldplanes, h->d_ldpairs);
+    h->launches += launches + 1;
     if (e != cudaSuccess) { if (d_ld) cudaFree(d_ld); h->err = std::string("ld_band: ") + cudaGetErrorString(e); return 1; }
     if (out_ld) {
         e = cudaMemcpyAsync(out_ld, d_ld, (size_t)L * W * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
@@ -1084,6 +1089,7 @@ int garlic_gpu_ld_band(garlic_gpu_t* h, int winsize, const int32_t* ld_individua
         if (e != cudaSuccess) { h->err = std::string("ld_band: ") + cudaGetErrorString(e); return 1; }
     }
     CK(cudaStreamSynchronize(h->stream));
+    laps.lap("kernels");
     h->have_ld = true; h->ld_W = W;
     return 0;
 }

@@ -103,36 +103,49 @@ __global__ void ld_sum_kernel(const double* __restrict__ P, const int* __restric
     }
 }
 
+// homFreq[d] = #(g in {0,2}) / #(non-missing) over ALL individuals, from the reduced per-SNP counters
+// (calculateGenoFreq, garlic-data.cpp:656-676; 0/0 gives NaN exactly as there)
+__global__ void hom_freq_kernel(const int* __restrict__ counts, long long L0, const int* __restrict__ src, long long L,
+                                double* __restrict__ homf)
+{
+    for (long long d = blockIdx.x * (long long)blockDim.x + threadIdx.x; d < L; d += (long long)gridDim.x * blockDim.x) {
+        const int s = src[d];
+        double fh = (double)counts[2 * L0 + s];
+        fh /= (double)counts[3 * L0 + s];
+        homf[d] = fh;
+    }
+}
+cudaError_t launch_hom_freq(const int* counts, long long L0, const int* src, long long L, double* homf, cudaStream_t st)
+{
+    if (!L) return cudaSuccess;
+    long long b = (L + 255) / 256;
+    hom_freq_kernel<<<(unsigned)(b > 148 * 16 ? 148 * 16 : b), 256, 0, st>>>(counts, L0, src, L, homf);
+    return cudaGetLastError();
+}
+
+size_t ld_planes_words(long long L, int n_ld) { return (size_t)L * 2 * ((n_ld + 63) / 64); }
+size_t ld_pairs_doubles(long long L, int W) { return (size_t)L * (2 * W - 1); }
+
 cudaError_t launch_ld_band(const uint64_t* geno, int64_t row_words, const int* ld_ind, int n_ld,
                            const double* homf, const int* chr_of, const int* chr_start, int n_chr,
                            long long L, int W, double* invld, double* ld_out, cudaStream_t st, int* n_launches,
-                           ncclComm_t comm, int ind_lo, int n_local)
+                           ncclComm_t comm, int ind_lo, int n_local, uint64_t* planes, double* P)
 {
     *n_launches = 0;
     const int nw = (n_ld + 63) / 64;
-    uint64_t* planes = nullptr;
-    double* P = nullptr;
-    cudaError_t e = cudaMalloc(&planes, (size_t)L * 2 * nw * sizeof(uint64_t));
-    if (e != cudaSuccess) return e;
-    e = cudaMalloc(&P, (size_t)L * (2 * W - 1) * sizeof(double));
-    if (e != cudaSuccess) { cudaFree(planes); return e; }
     auto blocks = [](long long n) { long long b = (n + 255) / 256; return (unsigned)(b > 148 * 64 ? 148 * 64 : b); };
     ld_planes_kernel<<<blocks(L), 256, 0, st>>>(geno, row_words, ld_ind, n_ld, L, nw, planes, ind_lo, n_local);
     // individuals are sharded over GPUs: every rank sets the bits of the LD individuals it holds, the planes are
     // combined over NVLink (bits are disjoint, so SUM is OR) and each rank then builds the whole band itself
     if (comm) {
         const ncclResult_t nr = ncclAllReduce(planes, planes, (size_t)L * 2 * nw, ncclUint64, ncclSum, comm, st);
-        if (nr != ncclSuccess) { cudaFree(planes); cudaFree(P); return cudaErrorUnknown; }
+        if (nr != ncclSuccess) return cudaErrorUnknown;
     }
     ld_pairs_kernel<<<blocks(L * (2 * W - 1)), 256, 0, st>>>(planes, nw, homf, chr_of, chr_start, n_chr, L, W, P);
     if (ld_out) cudaMemsetAsync(ld_out, 0, (size_t)L * W * sizeof(double), st);
     ld_sum_kernel<<<blocks(L * W), 256, 0, st>>>(P, chr_of, chr_start, n_chr, L, W, invld, ld_out);
     *n_launches = 3;
-    e = cudaGetLastError();
-    cudaError_t e2 = cudaStreamSynchronize(st);
-    cudaFree(planes);
-    cudaFree(P);
-    return e != cudaSuccess ? e : e2;
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------

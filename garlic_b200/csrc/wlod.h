@@ -33,6 +33,10 @@ cudaError_t launch_wlod_mma(const WlodParams& Q, const Item* items, int n_items,
 cudaError_t launch_ld_band(const uint64_t* geno, int64_t row_words, const int* ld_ind, int n_ld,
                            const double* homf, const int* chr_of, const int* chr_start, int n_chr,
                            long long L, int W, double* invld, double* ld_out, cudaStream_t st, int* n_launches,
-                           ncclComm_t comm, int ind_lo, int n_local);
+                           ncclComm_t comm, int ind_lo, int n_local, uint64_t* planes, double* P);
+// scratch the caller provides: bit-planes [L][2][ceil(n_ld/64)] words, ordered pair matrix [L][2W-1] doubles
+size_t ld_planes_words(long long L, int n_ld);
+size_t ld_pairs_doubles(long long L, int W);
+cudaError_t launch_hom_freq(const int* counts, long long L0, const int* src, long long L, double* homf, cudaStream_t st);
 
 }  // namespace garlic

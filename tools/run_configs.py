@@ -40,6 +40,7 @@ def setup(n_ind, L0, seed):
     row_bytes = ((L0 + 3) // 4 + 15) // 16 * 16
     rows = bench.make_rows_torch(torch, dev, n_ind, L0, seed, 1000, row_bytes)
     torch.cuda.synchronize()                     # the library copies on its own stream
+    torch.cuda.empty_cache()
     g = GarlicGPU(0)
     g.set_shape(n_ind, L0, chr_off0, pos0)
     g.put_packed_dev(rows.data_ptr(), row_bytes)
@@ -94,16 +95,25 @@ def c4(n_ind=500, L0=2_000_000):
     gen = torch.Generator(device=dev)
     gen.manual_seed(44)
     vals = torch.tensor([0.0004, 0.004, 0.04, 0.5, 3.0, 0.0, 150.0], dtype=torch.float64, device=dev)
-    idx = torch.randint(0, 7, (n_ind, L0), generator=gen, device=dev)      # (multinomial is not reproducible at this size)
-    idx = torch.where(idx >= 5, torch.randint(0, 7, (n_ind, L0), generator=gen, device=dev), idx)
-    gl = vals[idx]
+    gl = torch.empty((n_ind, L0), dtype=torch.float64, device=dev)         # C4: 40 GB; filled 25 individuals at a time
+    for i0 in range(0, n_ind, 25):
+        n = min(25, n_ind - i0)
+        idx = torch.randint(0, 7, (n, L0), generator=gen, device=dev)      # (multinomial is not reproducible at this size)
+        idx = torch.where(idx >= 5, torch.randint(0, 7, (n, L0), generator=gen, device=dev), idx)
+        gl[i0:i0 + n] = vals[idx]
+    del idx
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     g._ck(g.lib.garlic_gpu_put_gl_dev(g.h, bench.C_void(gl.data_ptr()), 2))
+    n_s = min(16 if L0 > 4_000_000 else 40, n_ind)
+    gl_sample = gl[:n_s].cpu().numpy()
+    del gl
+    torch.cuda.empty_cache()                                               # the library holds its own copy now
     (freq, keep, L), ms_f = timed(g, lambda: g.filter(), reps=1)
     cen_arr = np.array([cens["chr" + nm] for nm in names], np.int32)
     g.set_tables(None, 200000, cen_arr)
     W = 200
-    res = dict(config="C4 reduced: %d ind x %d SNPs, PL likelihoods, W=%d" % (n_ind, L0, W), loci_used=int(L),
+    res = dict(config="C4%s: %d ind x %d SNPs, PL likelihoods, W=%d" % ("" if L0 >= 10_000_000 else " reduced", n_ind, L0, W), loci_used=int(L),
                filter_ms=ms_f)
     kde = np.linspace(0, n_ind - 1, 20).astype(np.int32)
     _, ms = timed(g, lambda: g.windows(W, W, individuals=kde, exact=False))
@@ -113,11 +123,11 @@ def c4(n_ind=500, L0=2_000_000):
     bytes_unit = 8.25
     res["pass2"] = dict(ms=ms, kernel_ms=st["kernel_ms"], roh=len(roh), units=st["units"],
                         units_per_s_kernel=st["units"] / (st["kernel_ms"] / 1e3),
-                        hbm_gbs_algorithmic=st["units"] * bytes_unit / (st["kernel_ms"] / 1e3) / 1e9, ambiguous=st["ambiguous_pairs"])
-    n_s = 40
+                        hbm_gbs_algorithmic=st["units"] * bytes_unit / (st["kernel_ms"] / 1e3) / 1e9,
+                        hbm_gbs_at_8_bytes=st["units"] * 8.0 / (st["kernel_ms"] / 1e3) / 1e9, ambiguous=st["ambiguous_pairs"])
     codes = bench.unpack_rows(rows[:n_s].cpu().numpy(), L0)
     chroms = bench.cpu_chroms(codes, keep.copy(), freq.copy(), pos0, chr_off0, names, cens)
-    glh = orc.gl_error(gl[:n_s].cpu().numpy(), "PL")
+    glh = orc.gl_error(gl_sample, "PL")
     for c, ch in enumerate(chroms):
         lo, hi = int(chr_off0[c]), int(chr_off0[c + 1])
         ch["gl"] = np.ascontiguousarray(glh[:, lo:hi][:, keep[lo:hi]].T)
@@ -127,7 +137,7 @@ def c4(n_ind=500, L0=2_000_000):
         out = refdrv.run(chroms, n_s, W, None, cutoff=5.0, overlap_frac=0.25, dump_windows=False)
         want = sorted((r[0], r[1], r[2], r[3]) for r in out["roh"])
         got = sorted((int(r[0]), int(r[1]), int(pos_k[r[2]]), int(pos_k[r[3]])) for r in roh if r[0] < n_s)
-        res["parity_40_individuals"] = "identical ROH (%d) vs reference functions" % len(got) if got == want else "MISMATCH %d vs %d" % (len(got), len(want))
+        res["parity_%d_individuals" % n_s] = "identical ROH (%d) vs reference functions" % len(got) if got == want else "MISMATCH %d vs %d" % (len(got), len(want))
     g.close()
     return res
 
@@ -153,13 +163,17 @@ def c3(n_ind=5000, L0=200_000, n_ld=500):
     W = 72
     ld_ind = np.sort(np.random.default_rng(3).choice(n_ind, n_ld, replace=False)).astype(np.int32)
     _, ms_ld = timed(g, lambda: g.ld_band(W, ld_ind), reps=2)
-    res = dict(config="C3 reduced: %d ind x %d SNPs, --weighted --cm --ld-subsample %d, W=%d" % (n_ind, L0, n_ld, W),
+    res = dict(config="C3%s: %d ind x %d SNPs, --weighted --cm --ld-subsample %d, W=%d" % ("" if L0 >= 1_000_000 else " reduced", n_ind, L0, n_ld, W),
                loci_used=int(L), ld_band_ms=ms_ld, ld_pair_evaluations=float(L) * W * W * n_ld)
     roh, ms = timed(g, lambda: g.call_roh(W, 1.0, 0.25, weighted=True), reps=2)
     st = g.last_stats()
     res["pass2_wlod"] = dict(ms=ms, kernel_ms=st["kernel_ms"], roh=len(roh), units=st["units"],
                              units_per_s_kernel=st["units"] / (st["kernel_ms"] / 1e3),
-                             fp64_gflops=st["units"] * 2 * W / (st["kernel_ms"] / 1e3) / 1e9)
+                             fp64_gflops=st["units"] * 2 * W / (st["kernel_ms"] / 1e3) / 1e9, ambiguous=st["ambiguous_pairs"])
+    # the tensor-core pass against exact mul-then-add sums on the same handle (whole result, every individual)
+    roh_exact, ms_x = timed(g, lambda: g.call_roh(W, 1.0, 0.25, weighted=True, exact=True), reps=1)
+    res["exact_kernel_ms"] = g.last_stats()["kernel_ms"]
+    res["parity_all_individuals"] = "tensor-core pass == exact sums (%d ROH)" % len(roh) if np.array_equal(roh, roh_exact) else "MISMATCH"
     g.close()
     return res
 
@@ -167,6 +181,8 @@ def c3(n_ind=5000, L0=200_000, n_ld=500):
 if __name__ == "__main__":
     import ctypes
     bench.C_void = ctypes.c_void_p
+    # e.g.  c4   c4:500:10000000   c3:5000:1000000   c5:12500:600000   (name[:individuals[:SNPs]])
     which = sys.argv[1:] or ["c5", "c4", "c3"]
     for w in which:
-        print(json.dumps({"c3": c3, "c4": c4, "c5": c5}[w]()))
+        parts = w.split(":")
+        print(json.dumps({"c3": c3, "c4": c4, "c5": c5}[parts[0]](*[int(x) for x in parts[1:]])), flush=True)
