@@ -205,11 +205,15 @@ __device__ __forceinline__ void wlod_walk_item(const WlodParams& Q, const Item& 
 // K5-W fast pass: weighted windows of pass 2 as a banded matrix product on the FP64 tensor cores.
 //   Win[i][t] = Σ_m Sc[i][m] · Wt[m][t],   m = s - t0 over the SNPs a tile of 8 windows t0..t0+7 touches,
 //   Sc[i][m] = score of individual i at SNP t0+m (wlut[s][g] or gl·nomut·norec), Wt[m][j] = 1/LD[t0+j][m-j] (0 outside).
-// One warp owns 32 individuals of one item.  Per k-step of 4 SNPs it loads ONE weight fragment (mma B operand,
-// one double per lane) and reuses it for four 8-individual row groups (mma.sync.m8n8k4.f64, A = one score per
-// lane): 1024 multiply-adds for 5 loads.  The 8x8 accumulator tiles become window flags (cutoff ± tol), the flag
-// bits are routed by shuffles to the lane that owns each individual, and four tiles make the 32-bit flag word that
-// cover_block (walk.cuh) turns into coverage and run records — exactly as the unweighted walker does.
+// One warp owns 32 individuals of one item and works on blocks of 32 windows = 4 tiles of 8.  It walks the block's
+// SNPs in quads (the k = 4 of mma.sync.m8n8k4.f64): per quad ONE score fragment per 8-individual row group (A: one
+// double per lane, a table lookup through the packed genotype word) is shared by every window tile whose band holds
+// the quad, each tile adding one weight fragment (B: one double per lane, read without predicates from zero-padded
+// weight rows) — 16 DMMA = 4096 multiply-adds for 8 loads in the steady state, operands loaded one quad ahead.  Which
+// tiles hold which quads is a compile-time schedule (ramp-up, steady, ramp-down), so no DMMA is predicated.
+// The 8x8 accumulator tiles become window flags (cutoff ± tol), the flag bits are routed by shuffles to the lane that
+// owns each individual, and four tiles make the 32-bit flag word that cover_block (walk.cuh) turns into coverage and
+// run records — exactly as the unweighted walker does.
 // DMMA fuses and reorders the sum, so values differ from the reference's mul-then-add chain in the last bits:
 // windows within tol of the cutoff mark their (individual, segment) pair ambiguous, and those pairs are re-walked
 // by the exact kernel above (garlic_gpu_call_roh).  Window dumps (KDE, --raw-lod) always use the exact kernel.
@@ -279,11 +283,11 @@ wlod_mma_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items,
             const double* invq[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) invq[q] = Q.invld + (int64_t)(tb + 8 * q + j) * ldw + kInvFront - (8 * q + j);
-            uint64_t gw[4];
+            uint64_t gw[4], gwn[4];                                    // packed genotype word in use / the next one, in flight
             {
                 const int s0 = tb + mq;
 #pragma unroll
-                for (int rg = 0; rg < 4; ++rg) gw[rg] = rowA[rg][s0 >> 5];
+                for (int rg = 0; rg < 4; ++rg) { gw[rg] = rowA[rg][s0 >> 5]; gwn[rg] = rowA[rg][(s0 >> 5) + 1]; }
             }
             // operands of quad kq: ONE A fragment (scores) per row group, shared by every tile of the mask, one B
             // fragment (weights) per tile
@@ -293,7 +297,7 @@ wlod_mma_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items,
                 const int sh = 2 * (s & 31);
                 if (kq > 0 && ((tb + 4 * kq) & 31) == 0) {
 #pragma unroll
-                    for (int rg = 0; rg < 4; ++rg) gw[rg] = rowA[rg][s >> 5];
+                    for (int rg = 0; rg < 4; ++rg) { gw[rg] = gwn[rg]; gwn[rg] = rowA[rg][(s >> 5) + 1]; }
                 }
 #pragma unroll
                 for (int rg = 0; rg < 4; ++rg) {
