@@ -55,6 +55,8 @@ struct garlic_gpu {
     int64_t gl_stride = 0;
     double *d_freq0 = nullptr, *d_freq = nullptr, *d_lut = nullptr, *d_gpos = nullptr;
     double *d_nomut = nullptr, *d_norec = nullptr, *d_wlut = nullptr, *d_invld = nullptr, *d_homf = nullptr;
+    StitchScratch stitch_scratch;     // host buffers of call_roh kept between calls
+    std::vector<RohRec> recs_buf, ambs_buf, merged_buf;
     uint64_t* d_ldplanes = nullptr;   // LD scratch: bit-planes and the ordered pair matrix (kept between calls)
     double* d_ldpairs = nullptr;
     uint8_t* d_keep = nullptr;
@@ -877,7 +879,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         if (dev_alloc(h, &h->d_amb, h->amb_cap)) return 1;
     }
     laps.lap("items");
-    std::vector<RohRec> recs, ambs;
+    std::vector<RohRec>&recs = h->recs_buf, &ambs = h->ambs_buf;
     float ms = 0, ms_coarse = 0;
     bool pruned = false;
     for (int attempt = 0; attempt < 3; ++attempt) {
@@ -997,8 +999,8 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     }
     // sort by (individual, start) and stitch runs that were cut at chunk boundaries
     laps.lap("ambiguous");
-    std::vector<RohRec> merged;
-    stitch_runs(recs, thr, merged);
+    std::vector<RohRec>& merged = h->merged_buf;
+    stitch_runs(recs, thr, merged, &h->stitch_scratch);
     laps.lap("stitch");
     const int64_t n_out = (int64_t)merged.size();
     for (int64_t r = 0; r < n_out && r < cap && out; ++r) {

@@ -117,24 +117,45 @@ inline void build_items(const std::vector<int64_t>& chr_off, int W, const std::v
     }
 }
 
+// buffers of stitch_runs kept between calls (a fresh 400 KB vector per call costs more than the sort)
+struct StitchScratch {
+    std::vector<uint32_t> first, cur;
+    std::vector<std::pair<uint64_t, uint32_t>> key;
+};
+
 // Sort by (individual, start), merge runs cut at chunk boundaries, apply the minimum-length rule
 // (garlic-roh.cpp:477).  Returns the merged runs; tag keeps seg<<2.
-inline void stitch_runs(std::vector<RohRec>& recs, int thr, std::vector<RohRec>& out)
+
+inline void stitch_runs(std::vector<RohRec>& recs, int thr, std::vector<RohRec>& out, StitchScratch* scratch = nullptr)
 {
+    StitchScratch local;
+    StitchScratch& S = scratch ? *scratch : local;
     // sort by (individual, start): counting sort on the individual, then each individual's few runs by start
     int n_ind = 0;
     for (const RohRec& r : recs) n_ind = std::max(n_ind, r.ind + 1);
-    std::vector<uint32_t> first(n_ind + 1, 0);
+    std::vector<uint32_t>& first = S.first;
+    first.assign(n_ind + 1, 0);
     for (const RohRec& r : recs) first[r.ind + 1]++;
     for (int i = 0; i < n_ind; ++i) first[i + 1] += first[i];
-    std::vector<std::pair<uint64_t, uint32_t>> key(recs.size());
+    std::vector<std::pair<uint64_t, uint32_t>>& key = S.key;
+    key.resize(recs.size());
     {
-        std::vector<uint32_t> cur(first.begin(), first.end() - 1);
+        std::vector<uint32_t>& cur = S.cur;
+        cur.assign(first.begin(), first.end() - 1);
         for (size_t i = 0; i < recs.size(); ++i)
             key[cur[recs[i].ind]++] = {((uint64_t)(uint32_t)recs[i].ind << 32) | (uint32_t)recs[i].a, (uint32_t)i};
     }
-    for (int i = 0; i < n_ind; ++i)
-        if (first[i + 1] - first[i] > 1) std::sort(key.begin() + first[i], key.begin() + first[i + 1]);
+    for (int i = 0; i < n_ind; ++i) {
+        const uint32_t lo = first[i], hi = first[i + 1];
+        if (hi - lo > 24) std::sort(key.begin() + lo, key.begin() + hi);
+        else
+            for (uint32_t a = lo + 1; a < hi; ++a) {          // insertion sort: a handful of runs per individual
+                const auto v = key[a];
+                uint32_t b = a;
+                while (b > lo && key[b - 1] > v) { key[b] = key[b - 1]; --b; }
+                key[b] = v;
+            }
+    }
     out.clear();
     out.reserve(recs.size());
     size_t i = 0;
