@@ -20,7 +20,7 @@ GL_TYPES = {"GQ": 0, "GL": 1, "PL": 2, "ERROR": -1}
 EXPORTS = [
     "garlic_gpu_create", "garlic_gpu_destroy", "garlic_gpu_last_error", "garlic_gpu_launch_count",
     "garlic_gpu_stream", "garlic_gpu_sync", "garlic_gpu_host_alloc", "garlic_gpu_host_free", "garlic_gpu_set_shape", "garlic_gpu_put_alleles",
-    "garlic_gpu_first_allele_keys_dev", "garlic_gpu_code_alleles", "garlic_gpu_put_packed",
+    "garlic_gpu_first_allele_keys_dev", "garlic_gpu_code_alleles", "garlic_gpu_put_tped_text", "garlic_gpu_put_packed",
     "garlic_gpu_put_packed_dev", "garlic_gpu_count_packed", "garlic_gpu_counts_dev", "garlic_gpu_get_counts",
     "garlic_gpu_get_one_allele", "garlic_gpu_put_gl", "garlic_gpu_put_gl_dev", "garlic_gpu_filter",
     "garlic_gpu_set_tables", "garlic_gpu_set_lut", "garlic_gpu_get_lut", "garlic_gpu_get_hom_freq",
@@ -123,6 +123,16 @@ class GarlicGPU:
         a = np.ascontiguousarray(alleles, np.uint8)
         self._ck(self.lib.garlic_gpu_put_alleles(self.h, _p(a), C.c_int64(snp0), C.c_int(a.shape[0]),
                                                  C.c_char(missing.encode())))
+
+    def put_tped_text(self, text: bytes, line_off, snp0=0, missing="0"):
+        """K0: raw tped line tails → alleles on the device; returns the non-blank character count per line."""
+        off = np.ascontiguousarray(line_off, np.int64)
+        n = len(off) - 1
+        nb = np.empty(n, np.int32)
+        buf = np.frombuffer(text, np.uint8)
+        self._ck(self.lib.garlic_gpu_put_tped_text(self.h, _p(buf), _p(off), C.c_int64(snp0), C.c_int(n),
+                                                   C.c_char(missing.encode()), _p(nb)))
+        return nb
 
     def code_alleles(self):
         self._ck(self.lib.garlic_gpu_code_alleles(self.h))

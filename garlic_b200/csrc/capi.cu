@@ -55,6 +55,9 @@ struct garlic_gpu {
     int64_t gl_stride = 0;
     double *d_freq0 = nullptr, *d_freq = nullptr, *d_lut = nullptr, *d_gpos = nullptr;
     double *d_nomut = nullptr, *d_norec = nullptr, *d_wlut = nullptr, *d_invld = nullptr, *d_homf = nullptr;
+    char* d_text = nullptr;           // K0 staging: raw tped line tails, their offsets, non-blank counts
+    long long* d_textoff = nullptr;
+    int* d_nonblank = nullptr;
     StitchScratch stitch_scratch;     // host buffers of call_roh kept between calls
     std::vector<RohRec> recs_buf, ambs_buf, merged_buf;
     uint64_t* d_ldplanes = nullptr;   // LD scratch: bit-planes and the ordered pair matrix (kept between calls)
@@ -204,7 +207,7 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     cudaStreamSynchronize(h->stream);
     dev_free(h->d_alleles); dev_free(h->d_key); dev_free(h->d_geno0); dev_free(h->d_geno); dev_free(h->d_counts);
     dev_free(h->d_gl0); dev_free(h->d_gl); dev_free(h->d_freq0); dev_free(h->d_freq); dev_free(h->d_lut);
-    dev_free(h->d_ldplanes); dev_free(h->d_ldpairs);
+    dev_free(h->d_ldplanes); dev_free(h->d_ldpairs); dev_free(h->d_text); dev_free(h->d_textoff); dev_free(h->d_nonblank);
     dev_free(h->d_gpos); dev_free(h->d_nomut); dev_free(h->d_norec); dev_free(h->d_wlut); dev_free(h->d_invld);
     dev_free(h->d_homf); dev_free(h->d_keep); dev_free(h->d_src); dev_free(h->d_pos0); dev_free(h->d_chr_of0);
     dev_free(h->d_pos); dev_free(h->d_chr_of); dev_free(h->d_chr_start); dev_free(h->d_chr_param);
@@ -312,6 +315,37 @@ int garlic_gpu_put_alleles(garlic_gpu_t* h, const uint8_t* alleles, int64_t snp0
     CK(cudaMemcpyAsync(dst, alleles, (size_t)n_snp * h->n_ind * 2, cudaMemcpyHostToDevice, h->stream));
     LAUNCH(launch_first_allele(dst, n_snp, h->n_ind, h->ind_offset, (unsigned char)missing, h->d_key + snp0, h->stream));
     h->missing_char = (unsigned char)missing;
+    return 0;
+}
+
+int garlic_gpu_put_tped_text(garlic_gpu_t* h, const char* text, const int64_t* line_off, int64_t snp0, int n_snp,
+                             char missing, int32_t* nonblank)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->L0) FAIL("put_tped_text: call set_shape first");
+    if (snp0 % 32 != 0 || snp0 < 0 || snp0 + n_snp > h->L0) FAIL("put_tped_text: bad SNP range (snp0 must be a multiple of 32)");
+    if (n_snp <= 0) return 0;
+    if (!h->d_alleles) {
+        if (dev_alloc(h, &h->d_alleles, (size_t)h->L0 * h->n_ind * 2)) return 1;
+        if (dev_alloc(h, &h->d_key, (size_t)h->L0)) return 1;
+    }
+    const int64_t bytes = line_off[n_snp] - line_off[0];
+    if (bytes < 0) FAIL("put_tped_text: line offsets must ascend");
+    if (dev_alloc(h, &h->d_text, (size_t)bytes + 16)) return 1;
+    if (dev_alloc(h, &h->d_textoff, (size_t)n_snp + 1)) return 1;
+    if (dev_alloc(h, &h->d_nonblank, (size_t)n_snp)) return 1;
+    std::vector<long long> rel(n_snp + 1);
+    for (int i = 0; i <= n_snp; ++i) rel[i] = (long long)(line_off[i] - line_off[0]);
+    CK(cudaMemcpyAsync(h->d_text, text + line_off[0], (size_t)bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_textoff, rel.data(), rel.size() * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    uint8_t* dst = h->d_alleles + (size_t)snp0 * h->n_ind * 2;
+    // a short line leaves its tail untouched: pre-fill with the missing character so that nothing undefined is coded
+    CK(cudaMemsetAsync(dst, (unsigned char)missing, (size_t)n_snp * h->n_ind * 2, h->stream));
+    LAUNCH(launch_tokenize_tped(h->d_text, h->d_textoff, n_snp, h->n_ind, h->ind_offset, dst, h->d_nonblank, h->stream));
+    LAUNCH(launch_first_allele(dst, n_snp, h->n_ind, h->ind_offset, (unsigned char)missing, h->d_key + snp0, h->stream));
+    h->missing_char = (unsigned char)missing;
+    if (nonblank) CK(cudaMemcpyAsync(nonblank, h->d_nonblank, (size_t)n_snp * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // the caller may reuse its text buffer
     return 0;
 }
 

@@ -792,6 +792,70 @@ __global__ void first_allele_kernel(const uint8_t* __restrict__ alleles, int n_s
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K0: tped tokeniser.  The reference reads a line's genotype columns with `stringstream >> char`, i.e. the k-th
+// non-blank character after the 4th field is allele k (garlic-data.cpp:105-133).  The host keeps those line tails as
+// raw text; here one CTA per line ranks the non-blank characters (per-thread count, block scan) and scatters the ones
+// belonging to this GPU's individuals [ind_lo, ind_lo + n_ind) into the [n_snp][n_ind][2] allele block K1 works on.
+// nonblank[l] = number of non-blank characters of line l (the host checks it against 2 x individuals).
+// ------------------------------------------------------------------------------------------
+constexpr int kTokChars = 16;   // characters per thread per tile
+__global__ void __launch_bounds__(256)
+tokenize_tped_kernel(const char* __restrict__ text, const long long* __restrict__ off, int n_snp, int n_ind, int ind_lo,
+                     uint8_t* __restrict__ alleles, int* __restrict__ nonblank)
+{
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long k_lo = 2ll * ind_lo, k_hi = 2ll * (ind_lo + n_ind);
+    for (int l = blockIdx.x; l < n_snp; l += gridDim.x) {
+        const char* line = text + off[l];
+        const long long len = off[l + 1] - off[l];
+        uint8_t* dst = alleles + (size_t)l * n_ind * 2;
+        if (threadIdx.x == 0) s_base = 0;
+        __syncthreads();
+        for (long long t0 = 0; t0 < len; t0 += 256 * kTokChars) {
+            const long long i0 = t0 + (long long)threadIdx.x * kTokChars;
+            char c[kTokChars];
+            int n = 0;
+#pragma unroll
+            for (int k = 0; k < kTokChars; ++k) {
+                c[k] = (i0 + k < len) ? line[i0 + k] : ' ';
+                n += (c[k] != ' ' && c[k] != '\t' && c[k] != '\r' && c[k] != '\n');
+            }
+            // exclusive scan of n over the block
+            int incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            int wbase = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) if (w < warp) wbase += s_warp[w];
+            long long k = (long long)s_base + wbase + incl - n;      // rank of this thread's first non-blank character
+#pragma unroll
+            for (int q = 0; q < kTokChars; ++q)
+                if (c[q] != ' ' && c[q] != '\t' && c[q] != '\r' && c[q] != '\n') {
+                    if (k >= k_lo && k < k_hi) dst[k - k_lo] = (uint8_t)c[q];
+                    ++k;
+                }
+            __syncthreads();
+            if (threadIdx.x == 255) s_base += wbase + incl;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) nonblank[l] = s_base;
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_tokenize_tped(const char* text, const long long* off, int n_snp, int n_ind, int ind_lo, uint8_t* alleles,
+                                 int* nonblank, cudaStream_t st)
+{
+    if (!n_snp) return cudaSuccess;
+    tokenize_tped_kernel<<<n_snp < 148 * 8 ? n_snp : 148 * 8, 256, 0, st>>>(text, off, n_snp, n_ind, ind_lo, alleles, nonblank);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_first_allele(const uint8_t* alleles, int n_snp, int n_ind, int ind_offset, int missing,
                                 unsigned long long* key, cudaStream_t st)
 {

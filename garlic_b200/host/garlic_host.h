@@ -44,6 +44,7 @@ struct Options {
     int device = 0;              // extension: first CUDA device (--device)
     int gpus = 1;                // extension: shard the individuals over this many GPUs (--gpus)
     bool device_lut = false;     // extension: build the per-SNP LOD table on the GPU (--device-lut)
+    bool host_tokenize = false;  // extension: extract the tped allele characters on the host instead of K0 (--host-tokenize)
     bool kde_direct = false;     // extension: exact (reproducible) Gauss transform for the KDE (--kde-direct)
     long seed = -1;              // extension: RNG seed for the KDE / LD subsamples (--seed; default time)
 };
@@ -58,9 +59,12 @@ struct Tped {
     std::vector<int64_t> chr_off;                // [C+1]
     std::vector<int32_t> pos;
     std::vector<std::string> snp_id;
-    std::vector<uint8_t> alleles;                // [L0][N][2]
+    std::vector<uint8_t> alleles;                // [L0][N][2]  (only with --host-tokenize)
+    std::vector<char> text;                      // raw genotype columns of every line (what follows the 4th field) …
+    std::vector<int64_t> text_off;               // … line l = text[text_off[l], text_off[l+1]): tokenised on the GPU (K0)
 };
-bool load_tped(const std::string& path, char missing, Tped& t);
+// host_tokenize: extract the allele characters here (the pre-K0 path, kept for A/B timing) instead of keeping raw text
+bool load_tped(const std::string& path, char missing, Tped& t, bool host_tokenize = false);
 struct Tfam { std::string pop; std::vector<std::string> ids; };
 bool load_tfam(const std::string& path, Tfam& f);
 struct Scaffold { std::string chr; std::vector<int32_t> pos; std::vector<double> gen; };

@@ -15,29 +15,50 @@ namespace gh {
 
 namespace {
 
+// Line reader over zlib (plain files pass through gzread untouched): 8 MB refills, newlines found with memchr,
+// lines handed out as views into the buffer — the tped genotype columns are copied once (into Tped::text) and never
+// looked at character by character on the host.
 struct GzLines {
     gzFile f = nullptr;
     std::vector<char> buf;
+    size_t pos = 0, end = 0;
+    bool eof = false;
     bool open(const std::string& p)
     {
         f = gzopen(p.c_str(), "rb");
         if (f) gzbuffer(f, 1 << 20);
-        buf.resize(1 << 16);
+        buf.resize((size_t)8 << 20);
+        pos = end = 0;
+        eof = false;
         return f != nullptr;
+    }
+    // next line as [p, p+n) without the newline / trailing CR; valid until the following call; false at EOF
+    bool next_view(const char*& p, size_t& n)
+    {
+        for (;;) {
+            const char* nl = end > pos ? (const char*)memchr(buf.data() + pos, '\n', end - pos) : nullptr;
+            if (nl || (eof && end > pos)) {
+                const size_t stop = nl ? (size_t)(nl - buf.data()) : end;
+                p = buf.data() + pos;
+                n = stop - pos;
+                pos = nl ? stop + 1 : end;
+                if (n && p[n - 1] == '\r') --n;
+                return true;
+            }
+            if (eof) return false;
+            if (pos > 0) { memmove(buf.data(), buf.data() + pos, end - pos); end -= pos; pos = 0; }
+            if (end == buf.size()) buf.resize(buf.size() * 2);          // a line longer than the buffer
+            const int got = gzread(f, buf.data() + end, (unsigned)std::min<size_t>(buf.size() - end, (size_t)1 << 30));
+            if (got <= 0) eof = true; else end += (size_t)got;
+        }
     }
     // reads one line (without the newline) of any length; false at EOF
     bool next(std::string& line)
     {
-        line.clear();
-        bool got = false;
-        while (gzgets(f, buf.data(), (int)buf.size())) {
-            got = true;
-            const size_t n = strlen(buf.data());
-            line.append(buf.data(), n);
-            if (n && buf[n - 1] == '\n') { line.pop_back(); break; }
-        }
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        return got;
+        const char* p; size_t n;
+        if (!next_view(p, n)) return false;
+        line.assign(p, n);
+        return true;
     }
     ~GzLines() { if (f) gzclose(f); }
 };
@@ -69,7 +90,7 @@ std::string chr_label(const std::string& name) { return (!name.empty() && name[0
 
 // loadTPEDData's parsing (garlic-data.cpp:57-153): <chr> <id> <cM> <bp> then allele characters; the coding
 // and counting of those characters is done on the GPU (K1).
-bool load_tped(const std::string& path, char missing, Tped& t)
+bool load_tped(const std::string& path, char missing, Tped& t, bool host_tokenize)
 {
     (void)missing;
     GzLines in;
@@ -77,15 +98,20 @@ bool load_tped(const std::string& path, char missing, Tped& t)
     std::string line, prev_chr;
     t = Tped();
     t.chr_off.push_back(0);
+    t.text_off.push_back(0);
     int64_t cur = 0;
     while (in.next(line)) {
-        const int ncols = count_fields(line) - 4;
-        if (ncols < 2) { LOG.error("ERROR: line " + std::to_string(t.n_loci + 1) + " of " + path + " has no genotypes."); return false; }
-        const int n_ind = ncols / 2;
-        if (t.n_loci == 0) t.n_ind = n_ind;
-        else if (n_ind != t.n_ind) {
-            LOG.error("ERROR: line " + std::to_string(t.n_loci + 1) + " of " + path + " has a different number of columns.");
-            return false;
+        if (host_tokenize || t.n_loci == 0) {
+            // column count: every line on the host path; with K0 only the first line is counted here (it fixes the
+            // number of individuals) and the GPU reports each line's allele count (main.cpp checks it)
+            const int ncols = count_fields(line) - 4;
+            if (ncols < 2) { LOG.error("ERROR: line " + std::to_string(t.n_loci + 1) + " of " + path + " has no genotypes."); return false; }
+            const int n_ind = ncols / 2;
+            if (t.n_loci == 0) t.n_ind = n_ind;
+            else if (n_ind != t.n_ind) {
+                LOG.error("ERROR: line " + std::to_string(t.n_loci + 1) + " of " + path + " has a different number of columns.");
+                return false;
+            }
         }
         const char* p = skip_ws(line.c_str());
         const char* e = skip_tok(p);
@@ -105,13 +131,19 @@ bool load_tped(const std::string& path, char missing, Tped& t)
         p = skip_ws(e); e = skip_tok(p);
         t.pos.push_back((int32_t)strtod(std::string(p, e).c_str(), nullptr));   // read as double, stored as int (:96-99)
         p = e;
-        const size_t base = t.alleles.size();
-        t.alleles.resize(base + (size_t)2 * t.n_ind);
-        uint8_t* dst = t.alleles.data() + base;
-        int k = 0;
-        for (; *p && k < 2 * t.n_ind; ++p)      // operator>>(char&): successive non-blank characters
-            if (*p != ' ' && *p != '\t') dst[k++] = (uint8_t)*p;
-        if (k != 2 * t.n_ind) { LOG.error("ERROR: line " + std::to_string(t.n_loci + 1) + " of " + path + " is truncated."); return false; }
+        if (host_tokenize) {
+            const size_t base = t.alleles.size();
+            t.alleles.resize(base + (size_t)2 * t.n_ind);
+            uint8_t* dst = t.alleles.data() + base;
+            int k = 0;
+            for (; *p && k < 2 * t.n_ind; ++p)      // operator>>(char&): successive non-blank characters
+                if (*p != ' ' && *p != '\t') dst[k++] = (uint8_t)*p;
+            if (k != 2 * t.n_ind) { LOG.error("ERROR: line " + std::to_string(t.n_loci + 1) + " of " + path + " is truncated."); return false; }
+        } else {
+            if (p == e && *p == 0) { LOG.error("ERROR: line " + std::to_string(t.n_loci + 1) + " of " + path + " has no genotypes."); return false; }
+            t.text.insert(t.text.end(), p, line.c_str() + line.size());     // raw tail: tokenised by K0 on the GPU
+            t.text_off.push_back((int64_t)t.text.size());
+        }
         ++t.n_loci;
     }
     if (t.n_loci == 0) { LOG.error("ERROR: " + path + " is empty."); return false; }

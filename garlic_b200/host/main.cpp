@@ -365,7 +365,7 @@ int main(int argc, char** argv)
 
     // ---- inputs ----
     if (!load_centromeres(o.build, o.centromere, c.cen)) return -1;
-    if (!load_tped(o.tped, o.tped_missing, c.tped)) return 1;
+    if (!load_tped(o.tped, o.tped_missing, c.tped, o.host_tokenize)) return 1;
     Tped& t = c.tped;
     LOG.line("Total loci: " + std::to_string(t.n_loci));
     if (!load_tfam(o.tfam, c.tfam)) return 1;
@@ -406,14 +406,26 @@ int main(int argc, char** argv)
     const int per = (t.n_ind + G - 1) / G;
     for (int r = 0; r < G; ++r) { team.ranks[r].rank = r; team.ranks[r].lo = std::min(t.n_ind, r * per); team.ranks[r].hi = std::min(t.n_ind, (r + 1) * per); }
     auto fail = [&](int code) { LOG.error("ERROR: " + team.first_error()); team.stop(); return code; };
-    const int64_t blk = 1 << 16;
+    const int64_t blk = 1 << 12;                       // tped lines per upload (multiple of 32)
     if (!team.all([&](Rank& R) {
             if (garlic_gpu_create(o.device + R.rank, &R.g)) { R.err = "no usable CUDA device " + std::to_string(o.device + R.rank) + "; garlic_b200 has no CPU path"; return false; }
             if (G > 1 && !rank_ok(R, garlic_gpu_comm_init(R.g, comm_id, R.rank, G), "comm_init")) return false;
             const int n = R.hi - R.lo;
             if (!rank_ok(R, garlic_gpu_set_shape(R.g, n, R.lo, t.n_loci, C, t.chr_off.data(), t.pos.data()), "set_shape")) return false;
             std::vector<uint8_t> slice;
-            for (int64_t s0 = 0; s0 < t.n_loci; s0 += blk) {
+            std::vector<int32_t> nb;
+            for (int64_t s0 = 0; s0 < t.n_loci && !o.host_tokenize; s0 += blk) {
+                // K0: the raw genotype columns go to every rank, which keeps its own individuals' characters
+                const int ns = (int)std::min(blk, t.n_loci - s0);
+                nb.resize(ns);
+                if (!rank_ok(R, garlic_gpu_put_tped_text(R.g, t.text.data(), t.text_off.data() + s0, s0, ns, o.tped_missing, nb.data()), "put_tped_text")) return false;
+                for (int k = 0; k < ns; ++k)
+                    if (nb[k] != 2 * t.n_ind) {      // loadTPEDData's column check (garlic-data.cpp:73-80), per line
+                        R.err = "line " + std::to_string(s0 + k + 1) + " of " + o.tped + (nb[k] < 2 * t.n_ind ? " is truncated." : " has a different number of columns.");
+                        return false;
+                    }
+            }
+            for (int64_t s0 = 0; s0 < t.n_loci && o.host_tokenize; s0 += blk) {
                 const int ns = (int)std::min(blk, t.n_loci - s0);
                 const uint8_t* src_ = t.alleles.data() + (size_t)s0 * t.n_ind * 2;
                 if (G > 1) {                                   // this rank's columns of the block
@@ -432,6 +444,7 @@ int main(int argc, char** argv)
         })) return fail(1);
     c.g = team.ranks[0].g;
     std::vector<uint8_t>().swap(t.alleles);
+    std::vector<char>().swap(t.text);
     std::vector<double>().swap(gl);
     std::vector<int32_t> chr_param;
     if (oob)

@@ -75,6 +75,12 @@ int garlic_gpu_put_alleles(garlic_gpu_t *h, const uint8_t *alleles, int64_t snp0
  * between put_alleles and code_alleles */
 void *garlic_gpu_first_allele_keys_dev(garlic_gpu_t *h);
 /* phase b: code every call to 2 bits (individual-major packed matrix), count alleles */
+/* K0: the same from raw text.  text + line_off[i] .. line_off[i+1] is what follows the 4th field of tped line snp0 + i
+ * (blanks, tabs, CR allowed anywhere): its k-th non-blank character is allele k, as `stringstream >> char` reads it
+ * (src/garlic-data.cpp:105-133).  Every rank gets the whole line and keeps its own individuals' characters.
+ * nonblank (may be NULL): [n_snp] number of non-blank characters found per line, for the caller's column-count check. */
+int garlic_gpu_put_tped_text(garlic_gpu_t *h, const char *text, const int64_t *line_off, int64_t snp0, int n_snp,
+                             char missing, int32_t *nonblank);
 int garlic_gpu_code_alleles(garlic_gpu_t *h);
 
 /* ---- pre-coded input: packed 2-bit rows (codes 0/1/2, 3 = missing) -------------------------

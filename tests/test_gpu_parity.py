@@ -410,3 +410,65 @@ def test_gl_relay_warps_equal_single_warp(W, n_ind, L0):
     assert np.array_equal(g.call_roh(W, 1.0, 0.25), ref)          # default K
     assert np.array_equal(g.call_roh(W, 1.0, 0.25, exact=True), ref)
     hp.close()
+
+
+def test_k0_tped_text_tokeniser_equals_allele_upload():
+    """K0: raw tped genotype columns (single blanks, tabs, runs of blanks, CR, leading blanks) tokenised on the GPU give
+    the same packed matrix, counts and "1" alleles as uploading the allele characters; two shards of individuals
+    each keep their own columns; a short line is reported through the non-blank count."""
+    from garlic_b200.api import GarlicGPU
+    ds, args = load_case("lod_small")
+    L0, N = ds.n_loci, ds.n_ind
+    rng = np.random.default_rng(11)
+    seps = [b" ", b"\t", b"  ", b" \t "]
+    lines, off = [], [0]
+    for l in range(L0):
+        a = ds.alleles[l].reshape(-1)
+        style = l % 4
+        if style == 0:
+            tail = b" " + b" ".join(bytes([x]) for x in a)
+        elif style == 1:
+            tail = b"\t" + b"\t".join(bytes([x]) for x in a) + b"\r"
+        else:
+            tail = b"".join(seps[int(rng.integers(0, 4))] + bytes([x]) for x in a) + (b"  " if style == 3 else b"")
+        lines.append(tail)
+        off.append(off[-1] + len(tail))
+    text = b"".join(lines)
+    ref = GarlicGPU(0)
+    ref.set_shape(N, L0, ds.chr_offsets, ds.pos)
+    ref.put_alleles(ds.alleles, 0)
+    ref.code_alleles()
+    want_geno, want_counts, want_one = ref.get_genotypes(), [c.copy() for c in ref.get_counts()], ref.get_one_allele().copy()
+    ref.close()
+    g = GarlicGPU(0)
+    g.set_shape(N, L0, ds.chr_offsets, ds.pos)
+    blk = 992                                                   # several uploads, multiple of 32
+    for s0 in range(0, L0, blk):
+        n = min(blk, L0 - s0)
+        nb = g.put_tped_text(text, off[s0:s0 + n + 1], s0)
+        assert np.all(nb == 2 * N)
+    g.code_alleles()
+    assert np.array_equal(g.get_genotypes(), want_geno)
+    assert all(np.array_equal(a, b) for a, b in zip(g.get_counts(), want_counts))
+    assert np.array_equal(g.get_one_allele(), want_one)
+    g.close()
+    # a shard holding the middle half of the individuals: only its columns, same codes
+    lo, hi = N // 4, N // 4 + N // 2
+    g = GarlicGPU(0)
+    g.set_shape(hi - lo, L0, ds.chr_offsets, ds.pos, ind_offset=lo)
+    g.put_tped_text(text, off, 0)
+    g.code_alleles()
+    sub = g.get_genotypes()
+    # the "1" allele of a shard is the first non-missing character among ITS individuals (the cross-GPU MIN all-reduce
+    # restores the global one); compare codes where both agree on it
+    one_s = g.get_one_allele()
+    same = one_s == want_one
+    def codes(rows):                                            # packed rows → uint8[n][L0] genotype codes
+        b = rows[:, :(L0 + 3) // 4]
+        return np.stack([(b >> (2 * k)) & 3 for k in range(4)], axis=2).reshape(b.shape[0], -1)[:, :L0]
+    assert same.mean() > 0.5 and np.array_equal(codes(sub)[:, same], codes(want_geno)[lo:hi][:, same])
+    # truncated line: one allele short
+    short = text[:off[1] - 2]
+    nb = g.put_tped_text(short + b" ", [0, len(short) + 1], 0)
+    assert nb[0] == 2 * N - 1
+    g.close()
