@@ -293,8 +293,8 @@ int main(int argc, char** argv)
         return -1;
     }
     LOG.line("User defined centromere file: " + o.centromere);
-    if (o.resample > 0 || o.phased) {
-        LOG.error("ERROR: --resample and --phased are not built in this round (DESIGN.md §9).");
+    if (o.phased) {
+        LOG.error("ERROR: --phased (r2 LD from phased haplotypes) is not built in this round (DESIGN.md §9).");
         return -1;
     }
     const bool auto_freq = (o.freq_file == "none");
@@ -302,7 +302,8 @@ int main(int argc, char** argv)
     LOG.line("Calculate allele frequencies only: " + fmt_bool(o.freq_only));
     LOG.line("Calculate allele frequencies from data: " + fmt_bool(auto_freq));
     if (!auto_freq) LOG.line("Allele frequencies file: " + o.freq_file);
-    else LOG.line("Allele frequencies resampled: FALSE");
+    else if (o.resample <= 0) LOG.line("Allele frequencies resampled: FALSE");
+    else LOG.line("Allele frequencies resampled: " + std::to_string(o.resample));
     bool explore = false;
     if (o.winsize_multi[0] != -1) {
         for (int w : o.winsize_multi)
@@ -467,6 +468,25 @@ int main(int argc, char** argv)
             if (R.rank == 0) c.L = L;
             return ok;
         })) return fail(1);
+    if (auto_freq && o.resample > 0) {
+        // --resample n (garlic-data.cpp:140-148, 296-303): each frequency is replaced by a binomial draw count/n made of
+        // n uniform deviates (gsl_rng_uniform = mt19937()/2^32, seeded from the clock in the reference; --seed here);
+        // the filter, tables and everything downstream then use the resampled frequencies
+        for (int64_t s = 0; s < t.n_loci; ++s) {
+            // total != 0 (garlic-data.cpp:142) <=> some non-missing allele <=> the line has a "1" allele
+            if (one[s] == (uint8_t)o.tped_missing) continue;
+            int count = 0;
+            for (int i = 0; i < o.resample; ++i) count += (c.rng() / 4294967296.0) <= freq0[s];
+            freq0[s] = double(count) / double(o.resample);
+        }
+        panel = freq0;
+        if (!team.all([&](Rank& R) {
+                int64_t L = 0;
+                const bool ok = rank_ok(R, garlic_gpu_filter(R.g, oob, oob ? chr_param.data() : nullptr, panel.data(), nullptr, nullptr, &L), "filter");
+                if (R.rank == 0) c.L = L;
+                return ok;
+            })) return fail(1);
+    }
     if (auto_freq && !write_freq_gz(o.out + ".freq.gz", t, one, freq0)) { team.stop(); return 1; }
     auto shutdown = [&]() { team.all([](Rank& R) { garlic_gpu_destroy(R.g); R.g = nullptr; return true; }); team.stop(); };
     if (o.freq_only) { shutdown(); return 0; }   // freqOnly (garlic-data.cpp:238-315): the .freq.gz is the output

@@ -251,3 +251,39 @@ def test_cli_exact_mode_and_errors():
         assert r.returncode != 0 and "not a valid double" in r.stderr
         r = subprocess.run(base + ["--error", "0.001", "--winsize", "31"], capture_output=True, text=True)
         assert r.returncode != 0 and "Duplicate" in r.stderr
+
+
+def test_cli_resample_frequencies():
+    """--resample n (garlic-data.cpp:140-148): every frequency becomes a binomial draw count/n around the sample
+    frequency (the reference seeds its generator from the clock, so parity is distributional); everything downstream
+    must be exactly what the same frequencies give when handed in through --freq-file."""
+    name, n = "lod_small", 50
+    with tempfile.TemporaryDirectory() as tmp:
+        ds, args, r = run_cli(name, tmp, extra=["--resample", str(n), "--seed", "7"])
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        out = os.path.join(tmp, "out")
+        assert "Allele frequencies resampled: %d" % n in open(out + ".log").read()
+        rows = [l.split("\t") for l in gzip.open(out + ".freq.gz", "rt").read().splitlines()[1:]]
+        want = [l.split("\t") for l in golden_text(name, "out.freq").splitlines()[1:]]
+        f1 = np.array([float(x[4]) for x in rows])
+        f0 = np.array([float(x[4]) for x in want])
+        assert [x[:4] for x in rows] == [x[:4] for x in want]
+        assert np.allclose(f1 * n, np.round(f1 * n), atol=1e-4)                    # multiples of 1/n (6 digits printed)
+        assert np.any(f1 != f0)
+        assert np.all(np.abs(f1 - f0) <= 6.0 * np.sqrt(f0 * (1 - f0) / n) + 1e-6)    # binomial spread
+        assert np.all(f1[(f0 == 0) | (f0 == 1)] == f0[(f0 == 0) | (f0 == 1)])
+        assert abs(np.mean(f1 - f0)) < 4.0 * 0.5 / np.sqrt(n * len(f0))              # unbiased
+        bed1 = open(out + ".roh.bed").read()
+        # same seed → same draw; the draw handed back through --freq-file → same ROH
+        with gzip.open(out + ".freq.gz", "rt") as fi, open(os.path.join(tmp, "re.freq"), "w") as fo:
+            fo.write(fi.read())
+        with open(os.path.join(GOLDEN, name, "cmd.txt")) as f:
+            cmd = [a.replace("<tmp>", tmp) for a in f.readline().split()[1:] if a != "--raw-lod"]
+        cmd[cmd.index("--out") + 1] = os.path.join(tmp, "out2")
+        r2 = subprocess.run([BIN] + cmd + ["--freq-file", os.path.join(tmp, "re.freq")], capture_output=True, text=True, timeout=180)
+        assert r2.returncode == 0, r2.stdout[-2000:] + r2.stderr[-2000:]
+        # count/n with n = 50 prints exactly (two decimals), so the file carries the very same doubles
+        assert bed1.count("\n") > 3 and open(os.path.join(tmp, "out2.roh.bed")).read() == bed1
+        r3 = subprocess.run([BIN] + cmd + ["--resample", str(n), "--seed", "7"], capture_output=True, text=True, timeout=180)
+        assert r3.returncode == 0
+        assert open(os.path.join(tmp, "out2.roh.bed")).read() == bed1              # deterministic given --seed
