@@ -20,7 +20,7 @@ GL_TYPES = {"GQ": 0, "GL": 1, "PL": 2, "ERROR": -1}
 EXPORTS = [
     "garlic_gpu_create", "garlic_gpu_destroy", "garlic_gpu_last_error", "garlic_gpu_launch_count",
     "garlic_gpu_stream", "garlic_gpu_sync", "garlic_gpu_host_alloc", "garlic_gpu_host_free", "garlic_gpu_set_shape", "garlic_gpu_put_alleles",
-    "garlic_gpu_first_allele_keys_dev", "garlic_gpu_code_alleles", "garlic_gpu_put_tped_text", "garlic_gpu_put_packed",
+    "garlic_gpu_first_allele_keys_dev", "garlic_gpu_code_alleles", "garlic_gpu_put_tped_text", "garlic_gpu_set_phased", "garlic_gpu_put_packed",
     "garlic_gpu_put_packed_dev", "garlic_gpu_count_packed", "garlic_gpu_counts_dev", "garlic_gpu_get_counts",
     "garlic_gpu_get_one_allele", "garlic_gpu_put_gl", "garlic_gpu_put_gl_dev", "garlic_gpu_filter",
     "garlic_gpu_set_tables", "garlic_gpu_set_lut", "garlic_gpu_get_lut", "garlic_gpu_get_hom_freq",
@@ -219,6 +219,9 @@ class GarlicGPU:
         return s
 
     # ---------------------------------------------------------------- weighted
+    def set_phased(self, on=True):
+        self._ck(self.lib.garlic_gpu_set_phased(self.h, C.c_int(int(on))))
+
     def set_wlod(self, mu, M):
         self._ck(self.lib.garlic_gpu_set_wlod(self.h, C.c_double(mu), C.c_int(M)))
 

@@ -85,6 +85,7 @@ struct garlic_gpu {
     int* d_cand_list = nullptr;
     unsigned* d_cand_cnt = nullptr;
     bool prune = true;             // GARLIC_NO_PRUNE=1 disables the pruning pass
+    bool phased = false;           // --phased: LD band from r2 between haplotypes instead of hr2
     bool wlod_mma = true;          // GARLIC_NO_MMA=1: weighted pass 2 with the exact kernel only
     ncclComm_t comm = nullptr;     // one rank per GPU, individuals sharded across ranks
     int comm_rank = 0, comm_world = 1;
@@ -687,6 +688,13 @@ int garlic_gpu_get_hom_freq(garlic_gpu_t* h, double* hom_freq)
     return 0;
 }
 
+int garlic_gpu_set_phased(garlic_gpu_t* h, int phased)
+{
+    h->phased = phased != 0;
+    h->have_ld = false;
+    return 0;
+}
+
 int garlic_gpu_set_wlod(garlic_gpu_t* h, double mu, int M)
 {
     h->mu = mu; h->M = M;
@@ -1107,7 +1115,12 @@ int garlic_gpu_ld_band(garlic_gpu_t* h, int winsize, const int32_t* ld_individua
     // zero-padded weight rows (wlod.h); rows of windows that do not exist stay all-zero
     if (dev_alloc(h, &h->d_invld, (size_t)(L + kPad) * inv_stride(W))) return 1;
     CK(cudaMemsetAsync(h->d_invld, 0, (size_t)(L + kPad) * inv_stride(W) * sizeof(double), h->stream));
-    if (dev_alloc(h, &h->d_ldplanes, ld_planes_words(L, n_ld))) return 1;
+    LdPhase ph;
+    if (h->phased) {
+        if (!h->d_alleles || !h->d_key) FAIL("ld_band: --phased needs the allele characters (put_alleles / put_tped_text), not pre-packed genotypes");
+        ph.alleles = h->d_alleles; ph.key = h->d_key; ph.src = h->d_src; ph.missing = h->missing_char; ph.freq = h->d_freq;
+    }
+    if (dev_alloc(h, &h->d_ldplanes, ld_planes_words(L, n_ld, h->phased))) return 1;
     if (dev_alloc(h, &h->d_ldpairs, ld_pairs_doubles(L, W))) return 1;
     double* d_ld = nullptr;
     if (out_ld) CK(cudaMalloc(&d_ld, (size_t)L * W * sizeof(double)));
@@ -1115,7 +1128,7 @@ int garlic_gpu_ld_band(garlic_gpu_t* h, int winsize, const int32_t* ld_individua
     int launches = 0;
     cudaError_t e = launch_ld_band(h->d_geno, h->row_words, h->d_indlist, n_ld, h->d_homf, h->d_chr_of, h->d_chr_start,
                                    h->n_chr, L, W, h->d_invld, d_ld, h->stream, &launches, h->comm,
-                                   h->comm ? h->ind_offset : 0, h->n_ind, h->d_ldplanes, h->d_ldpairs);
+                                   h->comm ? h->ind_offset : 0, h->n_ind, h->d_ldplanes, h->d_ldpairs, ph);
     h->launches += launches + 1;
     if (e != cudaSuccess) { if (d_ld) cudaFree(d_ld); h->err = std::string("ld_band: ") + cudaGetErrorString(e); return 1; }
     if (out_ld) {

@@ -16,22 +16,44 @@ namespace garlic {
 // ------------------------------------------------------------------------------------------
 // ld_ind holds indices into the WHOLE sample; this GPU owns individuals [ind_lo, ind_lo + n_local) (its rows 0..) and
 // fills only their bits — the other ranks' bits are zero here and arrive by the all-reduce in launch_ld_band.
+// ph (--phased): four planes per SNP instead of two — non-missing, g==2, g==1 and the first-copy bit
+// firstCopy = (first allele character == the "1" allele), garlic-data.cpp:129, read from the allele block K1 coded.
 __global__ void ld_planes_kernel(const uint64_t* __restrict__ geno, int64_t row_words, const int* __restrict__ ld_ind,
-                                 int n_ld, long long L, int nw, uint64_t* __restrict__ planes, int ind_lo, int n_local)
+                                 int n_ld, long long L, int nw, uint64_t* __restrict__ planes, int ind_lo, int n_local,
+                                 LdPhase ph)
 {
+    const int np = ph.alleles ? 4 : 2;
     for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < L; s += (long long)gridDim.x * blockDim.x) {
+        int one = 0;
+        const uint8_t* arow = nullptr;
+        if (ph.alleles) {
+            const int s0 = ph.src[s];
+            const unsigned long long k = ph.key[s0];
+            one = (k == ~0ull) ? ph.missing : (int)(k & 0xff);
+            arow = ph.alleles + (size_t)s0 * n_local * 2;
+        }
         for (int w = 0; w < nw; ++w) {
-            uint64_t nm = 0, hm = 0;
+            uint64_t nm = 0, hm = 0, g1 = 0, fc = 0;
             const int jmax = min(64, n_ld - w * 64);
             for (int j = 0; j < jmax; ++j) {
                 const int ind = ld_ind[w * 64 + j] - ind_lo;
                 if (ind < 0 || ind >= n_local) continue;
                 const int g = (int)(geno[(int64_t)ind * row_words + (s >> 5)] >> (2 * (s & 31))) & 3;
                 nm |= (uint64_t)(g != 3) << j;
-                hm |= (uint64_t)(g == 0 || g == 2) << j;
+                if (ph.alleles) {
+                    hm |= (uint64_t)(g == 2) << j;
+                    g1 |= (uint64_t)(g == 1) << j;
+                    fc |= (uint64_t)(arow[2 * ind] == one) << j;
+                } else {
+                    hm |= (uint64_t)(g == 0 || g == 2) << j;
+                }
             }
-            planes[s * 2 * nw + w] = nm;
-            planes[s * 2 * nw + nw + w] = hm;
+            planes[s * np * nw + w] = nm;
+            planes[s * np * nw + nw + w] = hm;
+            if (ph.alleles) {
+                planes[s * np * nw + 2 * nw + w] = g1;
+                planes[s * np * nw + 3 * nw + w] = fc;
+            }
         }
     }
 }
@@ -71,6 +93,46 @@ __global__ void ld_pairs_kernel(const uint64_t* __restrict__ planes, int nw, con
                 const double H = HAB - HA * HB;
                 const double HR2 = H * H / (HA * (1 - HA) * HB * (1 - HB));
                 v = (HR2 > 1) ? 1.0 : HR2;
+            }
+        }
+        P[t] = v;
+    }
+}
+
+// --phased: the same ordered pair matrix with r2 between haplotypes (garlic-data.cpp:585-617):
+//   x11 = 2·|G2i∧G2j| + |G1i∧G2j| + |G2i∧G1j| + |G1i∧G1j∧¬(Fi⊕Fj)|,  total = 2·|NMi∧NMj|  (popcounts over the LD
+//   individuals), then the reference's divisions and multiplications in its order; p = the allele frequencies in use.
+__global__ void ld_pairs_r2_kernel(const uint64_t* __restrict__ planes, int nw, const double* __restrict__ freq,
+                                   const int* __restrict__ chr_of, const int* __restrict__ chr_start, int n_chr,
+                                   long long L, int W, double* __restrict__ P)
+{
+    const int D = 2 * W - 1;
+    const long long total = L * D;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long j = t / D;
+        const int d = (int)(t % D);
+        const long long i = j + d - (W - 1);
+        double v = 0.0;
+        const int c = chr_of[j];
+        const long long lo = chr_start[c], hi = (c + 1 < n_chr) ? chr_start[c + 1] : L;
+        if (i == j) v = 1.0;
+        else if (i >= lo && i < hi) {
+            const double pi = freq[i], pj = freq[j];
+            if (pi > 0 && pi < 1 && pj > 0 && pj < 1) {
+                const uint64_t* a = planes + i * 4 * nw;
+                const uint64_t* b = planes + j * 4 * nw;
+                int tot = 0, x = 0;
+                for (int w = 0; w < nw; ++w) {
+                    tot += __popcll(a[w] & b[w]);
+                    const uint64_t a2 = a[nw + w], b2 = b[nw + w], a1 = a[2 * nw + w], b1 = b[2 * nw + w];
+                    x += 2 * __popcll(a2 & b2) + __popcll(a1 & b2) + __popcll(a2 & b1) +
+                         __popcll(a1 & b1 & ~(a[3 * nw + w] ^ b[3 * nw + w]));
+                }
+                double x11 = (double)x;
+                x11 /= (double)(2 * tot);
+                const double Dv = x11 - pi * pj;
+                const double R2 = Dv * Dv / (pi * (1 - pi) * pj * (1 - pj));
+                v = (R2 > 1) ? 1.0 : R2;
             }
         }
         P[t] = v;
@@ -123,25 +185,27 @@ cudaError_t launch_hom_freq(const int* counts, long long L0, const int* src, lon
     return cudaGetLastError();
 }
 
-size_t ld_planes_words(long long L, int n_ld) { return (size_t)L * 2 * ((n_ld + 63) / 64); }
+size_t ld_planes_words(long long L, int n_ld, bool phased) { return (size_t)L * (phased ? 4 : 2) * ((n_ld + 63) / 64); }
 size_t ld_pairs_doubles(long long L, int W) { return (size_t)L * (2 * W - 1); }
 
 cudaError_t launch_ld_band(const uint64_t* geno, int64_t row_words, const int* ld_ind, int n_ld,
                            const double* homf, const int* chr_of, const int* chr_start, int n_chr,
                            long long L, int W, double* invld, double* ld_out, cudaStream_t st, int* n_launches,
-                           ncclComm_t comm, int ind_lo, int n_local, uint64_t* planes, double* P)
+                           ncclComm_t comm, int ind_lo, int n_local, uint64_t* planes, double* P, const LdPhase& ph)
 {
     *n_launches = 0;
     const int nw = (n_ld + 63) / 64;
     auto blocks = [](long long n) { long long b = (n + 255) / 256; return (unsigned)(b > 148 * 64 ? 148 * 64 : b); };
-    ld_planes_kernel<<<blocks(L), 256, 0, st>>>(geno, row_words, ld_ind, n_ld, L, nw, planes, ind_lo, n_local);
+    const int np = ph.alleles ? 4 : 2;
+    ld_planes_kernel<<<blocks(L), 256, 0, st>>>(geno, row_words, ld_ind, n_ld, L, nw, planes, ind_lo, n_local, ph);
     // individuals are sharded over GPUs: every rank sets the bits of the LD individuals it holds, the planes are
     // combined over NVLink (bits are disjoint, so SUM is OR) and each rank then builds the whole band itself
     if (comm) {
-        const ncclResult_t nr = ncclAllReduce(planes, planes, (size_t)L * 2 * nw, ncclUint64, ncclSum, comm, st);
+        const ncclResult_t nr = ncclAllReduce(planes, planes, (size_t)L * np * nw, ncclUint64, ncclSum, comm, st);
         if (nr != ncclSuccess) return cudaErrorUnknown;
     }
-    ld_pairs_kernel<<<blocks(L * (2 * W - 1)), 256, 0, st>>>(planes, nw, homf, chr_of, chr_start, n_chr, L, W, P);
+    if (ph.alleles) ld_pairs_r2_kernel<<<blocks(L * (2 * W - 1)), 256, 0, st>>>(planes, nw, ph.freq, chr_of, chr_start, n_chr, L, W, P);
+    else ld_pairs_kernel<<<blocks(L * (2 * W - 1)), 256, 0, st>>>(planes, nw, homf, chr_of, chr_start, n_chr, L, W, P);
     if (ld_out) cudaMemsetAsync(ld_out, 0, (size_t)L * W * sizeof(double), st);
     ld_sum_kernel<<<blocks(L * W), 256, 0, st>>>(P, chr_of, chr_start, n_chr, L, W, invld, ld_out);
     *n_launches = 3;

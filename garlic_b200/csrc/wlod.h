@@ -20,6 +20,16 @@ struct WlodParams {
     const double* norec;   // [L+pad]
 };
 
+// --phased LD (r2 between haplotypes, garlic-data.cpp:585-617): where the first-copy bits and frequencies come from.
+// alleles == nullptr: unphased (hr2).
+struct LdPhase {
+    const uint8_t* alleles = nullptr;          // [L0][n_local][2] allele characters as K0/K1 left them
+    const unsigned long long* key = nullptr;   // [L0] first-allele keys (low byte = the "1" allele, ~0 = none)
+    const int* src = nullptr;                  // [L] kept SNP -> source SNP
+    int missing = '0';
+    const double* freq = nullptr;              // [L] allele frequencies in use
+};
+
 cudaError_t launch_wlod_walk(const WlodParams& Q, const Item* items, int n_items, bool gl_mode, bool roh,
                              bool dump, cudaStream_t st);
 
@@ -33,9 +43,9 @@ cudaError_t launch_wlod_mma(const WlodParams& Q, const Item* items, int n_items,
 cudaError_t launch_ld_band(const uint64_t* geno, int64_t row_words, const int* ld_ind, int n_ld,
                            const double* homf, const int* chr_of, const int* chr_start, int n_chr,
                            long long L, int W, double* invld, double* ld_out, cudaStream_t st, int* n_launches,
-                           ncclComm_t comm, int ind_lo, int n_local, uint64_t* planes, double* P);
+                           ncclComm_t comm, int ind_lo, int n_local, uint64_t* planes, double* P, const LdPhase& ph);
 // scratch the caller provides: bit-planes [L][2][ceil(n_ld/64)] words, ordered pair matrix [L][2W-1] doubles
-size_t ld_planes_words(long long L, int n_ld);
+size_t ld_planes_words(long long L, int n_ld, bool phased);
 size_t ld_pairs_doubles(long long L, int W);
 cudaError_t launch_hom_freq(const int* counts, long long L0, const int* src, long long L, double* homf, cudaStream_t st);
 

@@ -145,6 +145,7 @@ bool ld_band_all(Ctx& c, int W, const std::vector<int32_t>& ld)
 {
     if (!c.team.all([&](Rank& R) {
             garlic_gpu_set_wlod(R.g, c.o.mu, c.o.M);
+            garlic_gpu_set_phased(R.g, c.o.phased ? 1 : 0);     // calcR2LD instead of calcHR2LD (garlic-data.cpp:371)
             return rank_ok(R, garlic_gpu_ld_band(R.g, W, ld.empty() ? nullptr : ld.data(), (int)ld.size(), nullptr), "ld_band");
         })) { LOG.error("ERROR: " + c.team.first_error()); return false; }
     return true;
@@ -293,10 +294,7 @@ int main(int argc, char** argv)
         return -1;
     }
     LOG.line("User defined centromere file: " + o.centromere);
-    if (o.phased) {
-        LOG.error("ERROR: --phased (r2 LD from phased haplotypes) is not built in this round (DESIGN.md §9).");
-        return -1;
-    }
+
     const bool auto_freq = (o.freq_file == "none");
     if (!auto_freq && o.freq_only) { LOG.error("ERROR: Specifying a frequency file and --freq-only is redundant."); return -1; }
     LOG.line("Calculate allele frequencies only: " + fmt_bool(o.freq_only));

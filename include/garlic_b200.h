@@ -135,6 +135,9 @@ int garlic_gpu_get_hom_freq(garlic_gpu_t *h, double *hom_freq);
  * of the ranks' shards are combined by one ncclAllReduce inside the call; otherwise they are this handle's rows.
  * out_ld (may be NULL): the LD sums [L][W] as the reference's LDData (rows ≥ L_c-W+1 are 0). */
 int garlic_gpu_ld_band(garlic_gpu_t *h, int winsize, const int32_t *ld_individuals, int n_ld, double *out_ld);
+/* --phased: the LD band is built from r2 between haplotypes (calcR2LD / r2, src/garlic-data.cpp:426-471,585-617) with
+ * the first-copy bit of every call = (first allele character == the "1" allele) (:129); needs allele input. */
+int garlic_gpu_set_phased(garlic_gpu_t *h, int phased);
 /* wLOD parameters (--mu, --M), call before weighted windows */
 int garlic_gpu_set_wlod(garlic_gpu_t *h, double mu, int M);
 

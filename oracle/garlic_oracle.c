@@ -244,6 +244,52 @@ void orc_calc_hr2_ld(const int8_t *geno, const double *hom_freq, int L, int N, i
     }
 }
 
+/* ---- garlic-data.cpp:585-617 r2 (--phased): first_copy[l*N+ind] = (first allele character == the "1" allele) ---- */
+static double orc_r2(const int8_t *geno, const uint8_t *first_copy, const double *freq, int N, int i, int j,
+                     const int32_t *ind_index, int nsub)
+{
+    double pi = freq[i], pj = freq[j];
+    if (pi > 0 && pi < 1 && pj > 0 && pj < 1) {
+        double x11 = 0, total = 0;
+        for (int k = 0; k < nsub; k++) {
+            int ind = ind_index[k];
+            int gi = G(i, ind), gj = G(j, ind);
+            if (gi != 3 && gj != 3) {
+                total += 2;
+                if (gi == 2 && gj == 2) x11 += 2;
+                else if (gi == 1 && gj == 2) x11++;
+                else if (gi == 2 && gj == 1) x11++;
+                else if (gi == 1 && gj == 1 &&
+                         first_copy[(size_t)j * N + ind] == first_copy[(size_t)i * N + ind]) x11++;
+            }
+        }
+        x11 /= total;
+        double D = x11 - pi * pj;
+        double R2 = D * D / (pi * (1 - pi) * pj * (1 - pj));
+        if (R2 > 1) return 1;
+        return R2;
+    }
+    return 0;
+}
+
+/* ---- garlic-data.cpp:426-471,497-519,529-535 calcR2LD (one chromosome), layout as orc_calc_hr2_ld ---- */
+void orc_calc_r2_ld(const int8_t *geno, const uint8_t *first_copy, const double *freq, int L, int N, int W,
+                    const int32_t *ind_index, int nsub, double *LD)
+{
+    memset(LD, 0, sizeof(double) * (size_t)L * W);
+    int stop = L;
+    if (L - stop < W) stop = L - W + 1;
+    for (int locus = 0; locus < stop; locus++) {
+        for (int site = locus; site < locus + W; site++) {
+            double *cell = &LD[(size_t)locus * W + (site - locus)];
+            for (int i = locus; i <= locus + W - 1; i++) {
+                if (i != site) *cell += orc_r2(geno, first_copy, freq, N, i, site, ind_index, nsub);
+                else *cell += 1;
+            }
+        }
+    }
+}
+
 /* ---- garlic-roh.cpp:134-140 nomut / norec ---------------------------------------------- */
 static double orc_nomut(double M, double mu, double interval) { return exp(-2.0 * M * mu * interval); }
 static double orc_norec(double M, double interval) { return orc_nomut(M, 1, interval); }

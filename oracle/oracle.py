@@ -124,6 +124,16 @@ def calc_hr2_ld(geno, homf, W, ind_index):
     return LD
 
 
+def calc_r2_ld(geno, first_copy, freq, W, ind_index):
+    """--phased: r2 between haplotypes (garlic-data.cpp:426-471,585-617); first_copy uint8[L,N]."""
+    L, N = geno.shape
+    LD = np.empty((L, W), np.float64)
+    idx = np.ascontiguousarray(ind_index, np.int32)
+    lib().orc_calc_r2_ld(_p(np.ascontiguousarray(geno)), _p(np.ascontiguousarray(first_copy, np.uint8)),
+                         _p(np.ascontiguousarray(freq)), C.c_int(L), C.c_int(N), C.c_int(W), _p(idx), C.c_int(len(idx)), _p(LD))
+    return LD
+
+
 def wlod_weights(pos, gpos, mu, M):
     L = len(pos)
     a = np.empty(L)
@@ -195,7 +205,7 @@ def chr_label(name):
 # ------------------------------------------------------------------------------------------------
 def run_pipeline(ds, W, error=None, cutoff=None, overlap_frac=0.25, max_gap=200000, weighted=False,
                  cm=False, mu=1e-9, M=7, ld_individuals=None, kde_individuals=None, thin_step=None,
-                 auto_overlap=False, keep_windows=True):
+                 auto_overlap=False, keep_windows=True, phased=False):
     """Oracle run over a synth.Dataset.  Returns a dict with per-chromosome arrays and the ROH
     list [(ind, chr_index, start_bp, stop_bp, length)] in the reference's (ind, chr, pos) order."""
     geno0, na, tot, one, freq0 = code_tped(ds.alleles, ds.tped_missing)
@@ -215,7 +225,10 @@ def run_pipeline(ds, W, error=None, cutoff=None, overlap_frac=0.25, max_gap=2000
             keep = keep_mask(freq0[lo:hi], pos, True, sp[0], sp[-1], cen)
         else:
             keep = keep_mask(freq0[lo:hi], pos)
-        ch = dict(name=label, cen=cen, keep=keep, lo=lo, pos=np.ascontiguousarray(pos[keep]),
+        fc = None
+        if phased:      # firstCopy[i] = (alleleStr1 == oneAllele), garlic-data.cpp:129
+            fc = np.ascontiguousarray((ds.alleles[lo:hi, :, 0] == one[lo:hi, None])[keep]).astype(np.uint8)
+        ch = dict(name=label, cen=cen, keep=keep, lo=lo, first_copy=fc, pos=np.ascontiguousarray(pos[keep]),
                   geno=np.ascontiguousarray(geno0[lo:hi][keep]), freq=np.ascontiguousarray(freq0[lo:hi][keep]),
                   gl=np.ascontiguousarray(gl0[lo:hi][keep]) if use_gl else None, gpos=None)
         if weighted or cm:
@@ -235,7 +248,8 @@ def run_pipeline(ds, W, error=None, cutoff=None, overlap_frac=0.25, max_gap=2000
     ldi = np.arange(N, dtype=np.int32) if ld_individuals is None else np.asarray(ld_individuals, np.int32)
     for ch in chroms:
         if weighted:
-            ch["LD"] = calc_hr2_ld(ch["geno"], ch["homf"], W, ldi)
+            ch["LD"] = calc_r2_ld(ch["geno"], ch["first_copy"], ch["freq"], W, ldi) if phased else \
+                calc_hr2_ld(ch["geno"], ch["homf"], W, ldi)
             ch["win"] = calc_wlod(ch["geno"], ch["freq"], ch["pos"], ch["gpos"], W,
                                   -1.0 if error is None else error, max_gap, ch["cen"], ch["LD"], mu, M, ch["gl"])
         else:

@@ -128,6 +128,10 @@ def main():
     run_case("wlod_cm", ds, ["--winsize", "25", "--error", "0.001", "--weighted", "--cm", "--threads", "3",
                              "--ld-subsample", "0", "--lod-cutoff", "0.5",
                              "--size-bounds", "0.5", "1.5"], raw=True)
+    # 3b. the same data read as phased haplotypes: r2 LD from the first-copy bits instead of hr2 (--phased)
+    run_case("wlod_phased", ds, ["--winsize", "25", "--error", "0.001", "--weighted", "--cm", "--phased", "--threads", "2",
+                                 "--ld-subsample", "0", "--lod-cutoff", "0.5",
+                                 "--size-bounds", "0.5", "1.5"], raw=True)
     run_case("lod_cm", ds, ["--winsize", "30", "--error", "0.001", "--cm", "--lod-cutoff", "1.0",
                             "--size-bounds", "0.5", "1.5"])
     # 4. genotype likelihoods, all three encodings

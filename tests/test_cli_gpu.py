@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "garlic_b200", "host", "garlic_b200")
 
-CASES = ["lod_0", "lod_1", "lod_2", "lod_3", "lod_small", "lod_cm", "wlod_cm", "gl_pl", "gl_gl", "gl_gq",
+CASES = ["lod_0", "lod_1", "lod_2", "lod_3", "lod_small", "lod_cm", "wlod_cm", "wlod_phased", "gl_pl", "gl_gl", "gl_gq",
          "auto_overlap_hg19", "auto_cutoff", "winsize_multi", "freq_file"]
 
 

@@ -472,3 +472,46 @@ def test_k0_tped_text_tokeniser_equals_allele_upload():
     nb = g.put_tped_text(short + b" ", [0, len(short) + 1], 0)
     assert nb[0] == 2 * N - 1
     g.close()
+
+
+def test_phased_r2_ld_band_wlod_and_roh():
+    """--weighted --phased: the LD band from r2 between haplotypes (first-copy bits read from the allele block, four
+    bit-planes, popcounts) is bit-identical to the oracle's restatement of calcR2LD; windows within 1e-9, ROH and BED
+    equal the reference binary's."""
+    ds, args = load_case("wlod_phased")
+    W = arg(args, "--winsize", cast=int)
+    cutoff = arg(args, "--lod-cutoff", None, float)
+    res = orc.run_pipeline(ds, W, 0.001, cutoff, 0.25, weighted=True, cm=True, phased=True)
+    hp = HotPath().load(ds, weighted=True, cm=True, error=0.001)
+    hp.g.set_phased(True)
+    ld = hp.g.ld_band(W, None, want_ld=True)
+    assert np.array_equal(ld, np.concatenate([c["LD"] for c in res["chroms"]], axis=0), equal_nan=True)
+    close_windows(hp.g.windows(W, 1, weighted=True), oracle_windows_matrix(res))
+    for exact in (False, True):
+        got = hp.roh(W, cutoff, res["overlap_frac"], weighted=True, cm=True, exact=exact)
+        assert [(r[0], r[1], r[5], r[6]) for r in got] == oracle_roh_idx(res)
+    bed = orc.format_bed(got, ds.ind_ids, hp.labels, arg_list(args, "--size-bounds"), ds.pop, cm=True)
+    assert bed == golden_text("wlod_phased", "out.roh.bed")
+    # an LD subsample, and hr2 again after switching back
+    sub = np.array([0, 3, 4, 9, 10, 17, 20], np.int32)
+    res2 = orc.run_pipeline(ds, W, 0.001, cutoff, 0.25, weighted=True, cm=True, phased=True, ld_individuals=sub)
+    assert np.array_equal(hp.g.ld_band(W, sub, want_ld=True), np.concatenate([c["LD"] for c in res2["chroms"]], axis=0), equal_nan=True)
+    hp.g.set_phased(False)
+    res3 = orc.run_pipeline(ds, W, 0.001, cutoff, 0.25, weighted=True, cm=True)
+    assert np.array_equal(hp.g.ld_band(W, None, want_ld=True), np.concatenate([c["LD"] for c in res3["chroms"]], axis=0), equal_nan=True)
+    hp.close()
+    # pre-packed genotypes carry no phase
+    codes = synth.make_codes(3, 8, 4000)
+    names, offs, pos, cens = synth.make_positions_genomewide(3, 4000, n_chr=2)
+
+    class DS:
+        pass
+    d2 = DS()
+    d2.chr_names, d2.chr_offsets, d2.pos, d2.centromeres, d2.gl = names, offs, pos, cens, None
+    d2.map_pos = [pos[offs[c]:offs[c + 1]][::5].astype(np.int64) for c in range(2)]
+    d2.map_cm = [p * 1.2e-6 for p in d2.map_pos]
+    hp = HotPath().load(d2, weighted=True, cm=True, error=0.001, packed_rows=synth.pack_codes(codes))
+    hp.g.set_phased(True)
+    with pytest.raises(Exception):
+        hp.g.ld_band(25, None)
+    hp.close()

@@ -162,7 +162,7 @@ def test_two_gpu_weighted_ld_band_and_roh(ld_list):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("name", ["lod_0", "lod_2", "lod_small", "gl_pl", "auto_overlap_hg19", "freq_file", "lod_cm", "wlod_cm"])
+@pytest.mark.parametrize("name", ["lod_0", "lod_2", "lod_small", "gl_pl", "auto_overlap_hg19", "freq_file", "lod_cm", "wlod_cm", "wlod_phased"])
 def test_cli_two_gpus_equals_reference_binary(name):
     """garlic_b200 --gpus 2 (individuals sharded over two GPUs, NCCL exchanges inside the library): every output
     file equals the single-process reference binary's."""
