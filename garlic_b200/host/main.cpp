@@ -225,10 +225,15 @@ bool write_raw_lod(Ctx& c, int W)
     std::vector<double> m((size_t)blk * slots);
     std::vector<int32_t> idx(blk);
     std::string line;
-    for (int i0 = 0; i0 < N; i0 += blk) {
-        const int n = std::min(blk, N - i0);
+    // individuals in file order = rank order; each rank dumps the windows of its own shard (no exchange involved)
+    for (Rank& R : c.team.ranks)
+    for (int i0 = 0; i0 < R.hi - R.lo; i0 += blk) {
+        const int n = std::min(blk, R.hi - R.lo - i0);
         for (int i = 0; i < n; ++i) idx[i] = i0 + i;
-        if (!gpu_ok(c, garlic_gpu_windows(c.g, W, 1, c.o.weighted, idx.data(), n, 1, m.data()), "windows")) return false;
+        if (garlic_gpu_windows(R.g, W, 1, c.o.weighted, idx.data(), n, 1, m.data())) {
+            LOG.error(std::string("ERROR: windows: ") + garlic_gpu_last_error(R.g));
+            return false;
+        }
         for (int ch = 0; ch < C; ++ch) {
             const int64_t lo = c.chr_off[ch], hi = c.chr_off[ch + 1];
             for (int i = 0; i < n; ++i) {
@@ -397,7 +402,6 @@ int main(int argc, char** argv)
     // ---- GPU: coding, counts, freq, filter (K1-K3), individuals sharded over --gpus ranks ----
     const int G = o.gpus;
     if (G < 1 || G > t.n_ind) { LOG.error("ERROR: --gpus must be between 1 and the number of individuals."); return -1; }
-    if (G > 1 && o.raw_lod) { LOG.error("ERROR: --raw-lod runs on one GPU in this round (DESIGN.md §9)."); return -1; }
     Team& team = c.team;
     team.start(G);
     uint8_t comm_id[128];

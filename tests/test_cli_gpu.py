@@ -130,10 +130,14 @@ def test_cli_auto_cutoff_path(name):
 
 @pytest.mark.parametrize("name", ["lod_small", "gl_pl", "wlod_cm"])
 def test_cli_raw_lod(name):
+    check_raw_lod(name, [])
+
+
+def check_raw_lod(name, more):
     """--raw-lod: one gz file per chromosome, a line per individual, NA for MISSING, 6 significant digits — compared
     with the reference binary's own dump (tests/golden/*/rawlod.npz)."""
     with tempfile.TemporaryDirectory() as tmp:
-        ds, args, r = run_cli(name, tmp, extra=["--raw-lod"])
+        ds, args, r = run_cli(name, tmp, extra=["--raw-lod"] + list(more))
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         raw = np.load(os.path.join(GOLDEN, name, "rawlod.npz"))
         for c, nm in enumerate(ds.chr_names):

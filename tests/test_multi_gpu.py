@@ -178,3 +178,11 @@ def test_cli_two_gpus_equals_reference_binary(name):
         assert open(out + ".roh.bed").read() == golden_text(name, "out.roh.bed")
         if os.path.exists(os.path.join(GOLDEN, name, "out.freq")):
             assert gzip.open(out + ".freq.gz", "rt").read() == golden_text(name, "out.freq")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("name", ["lod_small", "wlod_cm"])
+def test_cli_two_gpus_raw_lod(name):
+    """--raw-lod --gpus 2: every rank dumps the windows of its own individuals, lines in individual order."""
+    from tests.test_cli_gpu import check_raw_lod
+    check_raw_lod(name, ["--gpus", "2"])
