@@ -59,13 +59,15 @@ struct garlic_gpu {
     long long* d_textoff = nullptr;
     int* d_nonblank = nullptr;
     StitchScratch stitch_scratch;     // host buffers of call_roh kept between calls
-    std::vector<RohRec> recs_buf, ambs_buf, merged_buf;
+    std::vector<RohRec> recs_buf, ambs_buf, merged_buf, tmp_buf;
     uint64_t* d_ldplanes = nullptr;   // LD scratch: bit-planes and the ordered pair matrix (kept between calls)
     double* d_ldpairs = nullptr;
     uint8_t* d_keep = nullptr;
     int *d_src = nullptr, *d_pos0 = nullptr, *d_chr_of0 = nullptr, *d_pos = nullptr, *d_chr_of = nullptr,
         *d_chr_start = nullptr, *d_chr_param = nullptr;
-    RohRec *d_out = nullptr, *d_amb = nullptr;
+    RohRec *d_out = nullptr, *d_amb = nullptr, *d_sorted = nullptr;
+    unsigned* d_hist = nullptr;       // run records per individual → bucket offsets
+    size_t sorted_cap = 0;
     unsigned out_cap = 0, amb_cap = 0;
     unsigned* d_cnt = nullptr;
     Item* d_items = nullptr;
@@ -212,7 +214,7 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     dev_free(h->d_gpos); dev_free(h->d_nomut); dev_free(h->d_norec); dev_free(h->d_wlut); dev_free(h->d_invld);
     dev_free(h->d_homf); dev_free(h->d_keep); dev_free(h->d_src); dev_free(h->d_pos0); dev_free(h->d_chr_of0);
     dev_free(h->d_pos); dev_free(h->d_chr_of); dev_free(h->d_chr_start); dev_free(h->d_chr_param);
-    dev_free(h->d_out); dev_free(h->d_amb); dev_free(h->d_cnt); dev_free(h->d_items); dev_free(h->d_indlist); dev_free(h->d_dump);
+    dev_free(h->d_out); dev_free(h->d_amb); dev_free(h->d_sorted); dev_free(h->d_hist); dev_free(h->d_cnt); dev_free(h->d_items); dev_free(h->d_indlist); dev_free(h->d_dump);
     dev_free(h->d_keepw); dev_free(h->d_first_word); dev_free(h->d_first_skip); dev_free(h->d_scan); dev_free(h->d_breaks); dev_free(h->d_thin);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -732,6 +734,7 @@ static WalkParams base_params(const garlic_gpu* h, int W)
     P.lut = h->d_lut; P.gl = h->have_gl ? h->d_gl : nullptr; P.freq = h->d_freq; P.gl_stride = h->gl_stride;
     P.ind_list = nullptr; P.n_lanes = h->n_ind; P.W = W; P.thr = 1; P.cutoff = 0; P.tol = 0;
     P.out = h->d_out; P.out_count = h->d_cnt; P.out_cap = h->out_cap; P.amb = h->d_amb; P.amb_cap = h->amb_cap;
+    P.hist = nullptr;
     P.dump = nullptr; P.dump_stride = 0; P.dump_step = 1;
     return P;
 }
@@ -922,6 +925,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     }
     laps.lap("items");
     std::vector<RohRec>&recs = h->recs_buf, &ambs = h->ambs_buf;
+    size_t n_stage = 0;            // records waiting in the pinned staging buffer
     float ms = 0, ms_coarse = 0;
     bool pruned = false;
     for (int attempt = 0; attempt < 3; ++attempt) {
@@ -969,8 +973,14 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
             cl.list = h->d_cand_list; cl.cnt = h->d_cand_cnt; cl.stride = h->n_ind;
         }
         CK(cudaEventRecord(h->ev2, h->stream));
+        // run records are bucketed by individual on the device (kernels.cu:launch_bucket_by_individual)
+        if (dev_alloc(h, &h->d_hist, (size_t)h->n_ind + 1)) return 1;
+        if (dev_alloc(h, &h->d_sorted, (size_t)h->out_cap)) return 1;
+        CK(cudaMemsetAsync(h->d_hist, 0, ((size_t)h->n_ind + 1) * sizeof(unsigned), h->stream));
+        P.hist = h->d_hist;
         if (launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, true, false, tile_snps, cl)) return 1;
         CK(cudaEventRecord(h->ev1, h->stream));
+        LAUNCH(launch_bucket_by_individual(h->d_out, h->d_cnt, h->out_cap, h->d_hist, h->n_ind, h->d_sorted, thr, h->stream));
         unsigned cnt[4];
         CK(cudaMemcpyAsync(cnt, h->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -993,10 +1003,13 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         if (cnt[0] + cnt[1]) {   // through the pinned staging buffer (a pageable copy is several times slower)
             if (pin_alloc(h, ((size_t)cnt[0] + cnt[1]) * sizeof(RohRec))) return 1;
             RohRec* stage = reinterpret_cast<RohRec*>(h->pin);
-            if (cnt[0]) CK(cudaMemcpyAsync(stage, h->d_out, cnt[0] * sizeof(RohRec), cudaMemcpyDeviceToHost, h->stream));
+            if (cnt[0]) CK(cudaMemcpyAsync(stage, h->d_sorted, cnt[0] * sizeof(RohRec), cudaMemcpyDeviceToHost, h->stream));
             if (cnt[1]) CK(cudaMemcpyAsync(stage + cnt[0], h->d_amb, cnt[1] * sizeof(RohRec), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
-            memcpy(recs.data(), stage, cnt[0] * sizeof(RohRec));
+            n_stage = cnt[0];
+            // runs arrive ordered and stitched by the device (bucket_stitch_kernel); with ambiguous pairs the exact
+            // re-evaluation below splices its runs in and the host sorts once more
+            if (cnt[1]) take_stitched(stage, cnt[0], recs);
             memcpy(ambs.data(), stage + cnt[0], cnt[1] * sizeof(RohRec));
         }
         break;
@@ -1042,8 +1055,10 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     // sort by (individual, start) and stitch runs that were cut at chunk boundaries
     laps.lap("ambiguous");
     std::vector<RohRec>& merged = h->merged_buf;
-    stitch_runs(recs, thr, merged, &h->stitch_scratch);
+    if (ambs.empty()) take_stitched(reinterpret_cast<RohRec*>(h->pin), n_stage, merged);
+    else stitch_runs(recs, thr, merged, &h->stitch_scratch);             // re-evaluated pairs were spliced in: full sort
     laps.lap("stitch");
+    if (laps.on) fprintf(stderr, "[garlic_b200] call_roh: %zu raw records, %zu ambiguous pairs, %zu runs after stitching\n", n_stage, ambs.size(), merged.size());
     const int64_t n_out = (int64_t)merged.size();
     for (int64_t r = 0; r < n_out && r < cap && out; ++r) {
         out[r].ind = merged[r].ind;

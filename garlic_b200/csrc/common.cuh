@@ -56,6 +56,7 @@ struct WalkParams {
     RohRec* out;            // ROH records
     unsigned* out_count;    // [0]=records appended, [1]=ambiguous (lane,item) pairs
     unsigned out_cap;
+    unsigned* hist;         // optional [n_ind]: records appended per individual (for the device-side bucketing)
     RohRec* amb;            // ambiguous pairs (ind, seg) recorded as RohRec{ind,0,0,seg}
     unsigned amb_cap;
     double* dump;           // window dump matrix [n_lanes][dump_stride] or nullptr

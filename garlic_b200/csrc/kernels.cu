@@ -743,6 +743,79 @@ cudaError_t launch_thin_windows(const uint64_t* geno, int64_t row_words, const d
 }
 
 // ------------------------------------------------------------------------------------------
+// Run records leave the walkers in arbitrary order (one atomic append each).  The reference's output order is
+// (individual, chromosome, start): the counting sort on the individual is done here — emit_run kept a histogram —
+// and each individual's handful of runs is then ordered and stitched by one thread.  hist: [n_ind] counts → offsets.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(unsigned* __restrict__ hist, int n)
+{
+    __shared__ unsigned s_part[1024];
+    const int per = (n + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(n, lo + per);
+    unsigned sum = 0;
+    for (int i = lo; i < hi; ++i) sum += hist[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned run = s_part[threadIdx.x] - sum;
+    for (int i = lo; i < hi; ++i) { const unsigned c = hist[i]; hist[i] = run; run += c; }
+}
+
+__global__ void bucket_scatter_kernel(const RohRec* __restrict__ in, const unsigned* __restrict__ count, unsigned cap,
+                                      unsigned* __restrict__ offs, RohRec* __restrict__ out)
+{
+    const unsigned n = min(*count, cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const RohRec r = in[i];
+        out[atomicAdd(offs + r.ind, 1u)] = r;
+    }
+}
+
+// One thread per individual: order its runs by start, merge the pieces of runs that were cut at chunk borders and
+// apply the minimum-length rule (garlic-roh.cpp:477) — segments.h:stitch_runs, in place; dropped slots get ind = -1.
+// ends: the bucket offsets after the scatter (= end of every individual's bucket).
+__global__ void bucket_stitch_kernel(RohRec* __restrict__ recs, const unsigned* __restrict__ ends, int n_ind, int thr)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ind; i += gridDim.x * blockDim.x) {
+        const unsigned lo = i ? ends[i - 1] : 0u, hi = ends[i];
+        for (unsigned a = lo + 1; a < hi; ++a) {
+            const RohRec v = recs[a];
+            unsigned b = a;
+            while (b > lo && recs[b - 1].a > v.a) { recs[b] = recs[b - 1]; --b; }
+            recs[b] = v;
+        }
+        unsigned w = lo, k = lo;
+        while (k < hi) {
+            RohRec cur = recs[k++];
+            while ((cur.tag & 2) && k < hi) {
+                const RohRec nx = recs[k];
+                if (!((nx.tag & 1) && nx.a == cur.b + 1 && (nx.tag >> 2) == (cur.tag >> 2))) break;
+                cur.b = nx.b;
+                cur.tag = (cur.tag & ~2) | (nx.tag & 2);
+                ++k;
+            }
+            if (cur.b - cur.a + 1 >= thr) recs[w++] = cur;
+        }
+        for (; w < hi; ++w) recs[w].ind = -1;
+    }
+}
+
+cudaError_t launch_bucket_by_individual(const RohRec* in, const unsigned* count, unsigned cap, unsigned* hist, int n_ind,
+                                        RohRec* out, int thr, cudaStream_t st)
+{
+    if (!n_ind) return cudaSuccess;
+    bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, n_ind);
+    bucket_scatter_kernel<<<148, 256, 0, st>>>(in, count, cap, hist, out);
+    bucket_stitch_kernel<<<(n_ind + 63) / 64, 64, 0, st>>>(out, hist, n_ind, thr);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // fill
 // ------------------------------------------------------------------------------------------
 __global__ void fill_f64_kernel(double* p, size_t n, double v)
@@ -1025,19 +1098,28 @@ count_packed_kernel(const uint64_t* __restrict__ geno, int64_t row_words, int n_
         int groups = 0;
         const uint64_t* col = geno + word;
         int* mine = s_cnt + threadIdx.x;
-        for (int rb = r0; rb < r1; rb += 8) {
-            uint64_t xa[8], xm[8];
+        for (int rb = r0; rb < r1; rb += 16) {
+            // 16 rows in flight per thread (128 B each from 16 different DRAM pages), consumed as two groups of 8
+            uint64_t w[16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 16; ++i) {
                 const int r = rb + i;
-                const uint64_t w = r < r1 ? col[(int64_t)r * row_words] : 0ull;   // 0 = g==0: adds to no counter
-                const uint64_t lo = w & M, hi = (w >> 1) & M;
-                xa[i] = (lo & ~hi) | ((hi & ~lo) << 1);       // g==1 at the even bit, g==2 at the odd bit
-                xm[i] = lo & hi;                              // missing at the even bit
+                w[i] = r < r1 ? col[(int64_t)r * row_words] : 0ull;                 // 0 = g==0: adds to no counter
             }
-            vc_add8(va, xa);
-            vc_add8(vm, xm);
-            if (++groups == 31) {                             // 248 rows: the planes hold at most 255
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint64_t xa[8], xm[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint64_t lo = w[8 * h + i] & M, hi = (w[8 * h + i] >> 1) & M;
+                    xa[i] = (lo & ~hi) | ((hi & ~lo) << 1);   // g==1 at the even bit, g==2 at the odd bit
+                    xm[i] = lo & hi;                          // missing at the even bit
+                }
+                vc_add8(va, xa);
+                vc_add8(vm, xm);
+            }
+            groups += 2;
+            if (groups >= 30) {                               // 240 rows: the planes hold at most 255
                 vc_flush(va, mine, mine + 32 * 256);
                 vc_flush(vm, mine + 2 * 32 * 256, nullptr);
                 groups = 0;
@@ -1072,7 +1154,7 @@ cudaError_t launch_count_packed(const uint64_t* geno, int64_t row_words, int n_i
     int gy = (int)((148ll * 2 + gx - 1) / gx);            // about one wave of 2 CTAs per SM
     gy = std::max(1, std::min(gy, (n_ind + 63) / 64));
     int rpb = (n_ind + gy - 1) / gy;
-    rpb = ((rpb + 7) / 8) * 8;
+    rpb = ((rpb + 15) / 16) * 16;
     gy = (n_ind + rpb - 1) / rpb;
     dim3 grid(gx, gy);
     const size_t smem = 3 * 32 * 256 * sizeof(int);           // 96 KB

@@ -28,6 +28,8 @@ cudaError_t launch_thin_windows(const uint64_t* geno, int64_t row_words, const d
                                 const int3* segs, int n_segs, const int2* meta, int n_chr, long long n_slots, int step, int W,
                                 double* dump, int64_t dump_stride, const double* gl, int64_t gl_stride, cudaStream_t st);
 cudaError_t launch_fill_f64(double* p, size_t n, double v, cudaStream_t st);
+cudaError_t launch_bucket_by_individual(const RohRec* in, const unsigned* count, unsigned cap, unsigned* hist, int n_ind,
+                                        RohRec* out, int thr, cudaStream_t st);
 cudaError_t launch_tokenize_tped(const char* text, const long long* off, int n_snp, int n_ind, int ind_lo, uint8_t* alleles,
                                  int* nonblank, cudaStream_t st);
 cudaError_t launch_first_allele(const uint8_t* alleles, int n_snp, int n_ind, int ind_offset, int missing,

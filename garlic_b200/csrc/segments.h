@@ -173,4 +173,18 @@ inline void stitch_runs(std::vector<RohRec>& recs, int thr, std::vector<RohRec>&
     }
 }
 
+// Records stitched on the device (kernels.cu:bucket_stitch_kernel) arrive ordered by (individual, start) with the
+// dropped slots marked ind = -1: keep the rest.
+inline void take_stitched(const RohRec* recs, size_t n, std::vector<RohRec>& out)
+{
+    out.resize(n);
+    RohRec* o = out.data();
+    size_t m = 0;
+    for (size_t i = 0; i < n; ++i) {
+        o[m] = recs[i];
+        m += recs[i].ind >= 0;
+    }
+    out.resize(m);
+}
+
 }  // namespace garlic

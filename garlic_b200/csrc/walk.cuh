@@ -80,6 +80,9 @@ GHD void emit_run(const WalkParams& P, const Item& it, int ind, bool active, int
         RohRec r;
         r.ind = ind; r.a = a; r.b = b; r.tag = (it.seg << 2) | (orr << 1) | ol;
         P.out[p] = r;
+#ifdef __CUDA_ARCH__
+        if (P.hist) atomicAdd(P.hist + ind, 1u);
+#endif
     }
 }
 
