@@ -247,7 +247,12 @@ static cudaError_t launch_walk_t(const WalkParams& P, const Item* items, int n_i
         }
         kern<<<(unsigned)grid, threads, smem, st>>>(P, items, n_items, n_groups, tile_bytes, cl.list, cl.cnt, cl.stride);
     } else {
-        walk_kernel<SRC, ROH, DUMP, false><<<(unsigned)grid, threads, smem, st>>>(P, items, n_items, n_groups, 0, cl.list, cl.cnt, cl.stride);
+        auto kern = walk_kernel<SRC, ROH, DUMP, false>;
+        if (smem > 48 * 1024) {                                // flag history of very large windows
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<(unsigned)grid, threads, smem, st>>>(P, items, n_items, n_groups, 0, cl.list, cl.cnt, cl.stride);
     }
     return cudaGetLastError();
 }

@@ -469,6 +469,11 @@ cudaError_t launch_wlod_mma(const WlodParams& Q, const Item* items, int n_items,
     long long grid = total;
     const long long cap = 148ll * 16 * 8;
     if (grid > cap) grid = cap;
+    if (smem > 48 * 1024) {                                    // flag history of very large windows
+        cudaError_t e = gl_mode ? cudaFuncSetAttribute(wlod_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                : cudaFuncSetAttribute(wlod_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     if (gl_mode) wlod_mma_kernel<1><<<(unsigned)grid, threads, smem, st>>>(Q, items, n_items, n_groups);
     else wlod_mma_kernel<0><<<(unsigned)grid, threads, smem, st>>>(Q, items, n_items, n_groups);
     return cudaGetLastError();
@@ -507,6 +512,10 @@ static cudaError_t launch_wlod_t(const WlodParams& Q, const Item* items, int n_i
     long long grid = total;
     const long long cap = 148ll * 16 * 8;
     if (grid > cap) grid = cap;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(wlod_walk_kernel<SRC, ROH, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     wlod_walk_kernel<SRC, ROH, DUMP><<<(unsigned)grid, threads, smem, st>>>(Q, items, n_items, n_groups);
     return cudaGetLastError();
 }

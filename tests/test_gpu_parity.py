@@ -515,3 +515,29 @@ def test_phased_r2_ld_band_wlod_and_roh():
     with pytest.raises(Exception):
         hp.g.ld_band(25, None)
     hp.close()
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_largest_window_sizes(weighted):
+    """Window sizes up to the C ABI's limit (4096): the flag-history ring then needs more than the default 48 KB of
+    dynamic shared memory; fast pass == exact pass, and a few ROH come out of the planted homozygous stretches."""
+    names, offs, pos, cens = synth.make_positions_genomewide(41, 60000, n_chr=2, big_gap_frac=0.0)
+    codes = synth.make_codes(41, 40, 60000, n_roh=3, roh_snps=(6000, 9000))
+
+    class DS:
+        pass
+    ds = DS()
+    ds.chr_names, ds.chr_offsets, ds.pos, ds.centromeres, ds.gl = names, offs, pos, {}, None
+    ds.map_pos = [pos[offs[c]:offs[c + 1]][::5].astype(np.int64) for c in range(2)]
+    ds.map_cm = [p * 1.2e-6 for p in ds.map_pos]
+    hp = HotPath().load(ds, weighted=weighted, cm=weighted, error=0.001, packed_rows=synth.pack_codes(codes), max_gap=10 ** 9)
+    for W in ((1600, 4096) if not weighted else (1600,)):
+        if weighted:
+            hp.g.ld_band(W, np.arange(0, 40, 4, dtype=np.int32))
+        win = hp.g.windows(W, 1, weighted=weighted, individuals=np.array([1], np.int32))[0]
+        v = np.sort(win[(win != orc.MISSING) & ~np.isnan(win)])
+        cutoff = float(v[int(0.9 * len(v))])
+        a = hp.g.call_roh(W, cutoff, 0.25, weighted=weighted, exact=False)
+        b = hp.g.call_roh(W, cutoff, 0.25, weighted=weighted, exact=True)
+        assert np.array_equal(a, b) and len(a) > 0
+    hp.close()
