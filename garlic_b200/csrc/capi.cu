@@ -94,6 +94,8 @@ struct garlic_gpu {
     bool counts_reduced = false;   // d_counts already holds the sum over all ranks
     double* d_gather = nullptr;    // all-gathered thinned windows
     cudaEvent_t ev2 = nullptr;
+    cudaStream_t copy_stream = nullptr;   // device-to-host copies that overlap the kernels behind them (filter)
+    cudaEvent_t ev_copy = nullptr;
     int* d_first_word = nullptr;
     uint8_t* d_first_skip = nullptr;
     uint8_t* pin = nullptr;        // pinned host staging buffer
@@ -196,6 +198,8 @@ int garlic_gpu_create(int device, garlic_gpu_t** out)
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
     cudaEventCreate(&h->ev2);
+    cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming);
     h->prune = getenv("GARLIC_NO_PRUNE") == nullptr;
     h->wlod_mma = getenv("GARLIC_NO_MMA") == nullptr;
     cudaMalloc((void**)&h->d_cnt, 4 * sizeof(unsigned));
@@ -220,6 +224,8 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     dev_free(h->d_cmask); dev_free(h->d_ccb); dev_free(h->d_cand_list); dev_free(h->d_cand_cnt);
     if (h->comm) ncclCommDestroy(h->comm);
     dev_free(h->d_gather);
@@ -473,7 +479,7 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     if (oob && !chr_param) FAIL("filter: oob filtering needs chr_param");
     const int64_t L0 = h->L0;
     Laps laps("filter");
-    bool freq_direct = false, keep_direct = false;
+    bool freq_direct = false, keep_direct = false, copies_in_flight = false;
     if (dev_alloc(h, &h->d_freq0, (size_t)L0)) return 1;
     if (dev_alloc(h, &h->d_keep, (size_t)L0)) return 1;
     if (oob) {
@@ -513,8 +519,15 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
         // page-locked caller buffers (garlic_gpu_host_alloc) are written by the copy engine directly
         freq_direct = freq_out && is_pinned(freq_out);
         keep_direct = keep_out && is_pinned(keep_out);
-        if (freq_out) CK(cudaMemcpyAsync(freq_direct ? freq_out : freq0, h->d_freq0, L0 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        if (keep_out) CK(cudaMemcpyAsync(keep_direct ? keep_out : keep, h->d_keep, L0, cudaMemcpyDeviceToHost, h->stream));
+        // freq[] / keep[] travel to the host on a second stream, behind the kernel that made them, while the keep-mask
+        // scan and the compaction run on: the host only waits for them at the end of this call
+        if (freq_out || keep_out) {
+            CK(cudaEventRecord(h->ev_copy, h->stream));
+            CK(cudaStreamWaitEvent(h->copy_stream, h->ev_copy, 0));
+            if (freq_out) CK(cudaMemcpyAsync(freq_direct ? freq_out : freq0, h->d_freq0, L0 * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+            if (keep_out) CK(cudaMemcpyAsync(keep_direct ? keep_out : keep, h->d_keep, L0, cudaMemcpyDeviceToHost, h->copy_stream));
+            copies_in_flight = true;
+        }
     }
     // exclusive scan of the keep mask on the device: gather list, keep bits per input word, per output word
     // the input word it starts in, kept offset of every chromosome
@@ -530,10 +543,11 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     h->launches += 3;
     CK(cudaMemcpyAsync(meta, d_total, (size_t)(h->n_chr + 2) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    laps.lap("freq_keep+scan+d2h");
-    if (freq_out && !freq_direct) memcpy(freq_out, freq0, L0 * sizeof(double));
-    if (keep_out && !keep_direct) memcpy(keep_out, keep, L0);
-    laps.lap("copy_out");
+    laps.lap("freq_keep+scan");
+    if (freq_override) {
+        if (freq_out) memcpy(freq_out, freq0, L0 * sizeof(double));
+        if (keep_out) memcpy(keep_out, keep, L0);
+    }
     const int64_t L = meta[0];
     h->chr_off.assign(h->n_chr + 1, 0);
     for (int c = 0; c <= h->n_chr; ++c) h->chr_off[c] = meta[1 + c];
@@ -571,6 +585,12 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     LAUNCH(launch_gather_i32(h->d_chr_of0, h->d_src, L, h->d_chr_of, h->stream));
     CK(cudaMemcpyAsync(h->d_chr_start, chr_start.data(), h->n_chr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     laps.lap("enqueue");   // compaction and gathers run stream-ordered behind this call
+    if (copies_in_flight) {
+        CK(cudaStreamSynchronize(h->copy_stream));
+        if (freq_out && !freq_direct) memcpy(freq_out, freq0, L0 * sizeof(double));
+        if (keep_out && !keep_direct) memcpy(keep_out, keep, L0);
+        laps.lap("freq/keep d2h");
+    }
     h->filtered = true; h->tables = false; h->have_ld = false;
     return 0;
 }
