@@ -781,32 +781,58 @@ __global__ void bucket_scatter_kernel(const RohRec* __restrict__ in, const unsig
     }
 }
 
-// One thread per individual: order its runs by start, merge the pieces of runs that were cut at chunk borders and
+// One warp per individual: order its runs by start, merge the pieces of runs that were cut at chunk borders and
 // apply the minimum-length rule (garlic-roh.cpp:477) — segments.h:stitch_runs, in place; dropped slots get ind = -1.
+// Up to 32 runs: every lane takes one record, ranks it against the others by shuffles and drops it into shared memory
+// in order; lane 0 then merges from there.  Larger buckets are sorted serially in global memory.
 // ends: the bucket offsets after the scatter (= end of every individual's bucket).
-__global__ void bucket_stitch_kernel(RohRec* __restrict__ recs, const unsigned* __restrict__ ends, int n_ind, int thr)
+__global__ void __launch_bounds__(128)
+bucket_stitch_kernel(RohRec* __restrict__ recs, const unsigned* __restrict__ ends, int n_ind, int thr)
 {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ind; i += gridDim.x * blockDim.x) {
+    __shared__ RohRec s_rec[4][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = blockIdx.x * 4 + warp; i < n_ind; i += gridDim.x * 4) {
         const unsigned lo = i ? ends[i - 1] : 0u, hi = ends[i];
-        for (unsigned a = lo + 1; a < hi; ++a) {
-            const RohRec v = recs[a];
-            unsigned b = a;
-            while (b > lo && recs[b - 1].a > v.a) { recs[b] = recs[b - 1]; --b; }
-            recs[b] = v;
-        }
-        unsigned w = lo, k = lo;
-        while (k < hi) {
-            RohRec cur = recs[k++];
-            while ((cur.tag & 2) && k < hi) {
-                const RohRec nx = recs[k];
-                if (!((nx.tag & 1) && nx.a == cur.b + 1 && (nx.tag >> 2) == (cur.tag >> 2))) break;
-                cur.b = nx.b;
-                cur.tag = (cur.tag & ~2) | (nx.tag & 2);
-                ++k;
+        const unsigned n = hi - lo;
+        const RohRec* src = recs + lo;
+        if (n <= 32u) {
+            RohRec mine;
+            mine.ind = i; mine.a = 0x7fffffff; mine.b = 0; mine.tag = 0;
+            if ((unsigned)lane < n) mine = recs[lo + lane];
+            // rank among the bucket (starts of one individual's runs are distinct; ties broken by lane anyway)
+            int rank = 0;
+            for (unsigned j = 0; j < n; ++j) {
+                const int aj = __shfl_sync(0xffffffffu, mine.a, (int)j);
+                rank += (aj < mine.a) || (aj == mine.a && (int)j < lane);
             }
-            if (cur.b - cur.a + 1 >= thr) recs[w++] = cur;
+            __syncwarp();
+            if ((unsigned)lane < n) s_rec[warp][rank] = mine;
+            __syncwarp();
+            src = s_rec[warp];
+        } else if (lane == 0) {
+            for (unsigned a = lo + 1; a < hi; ++a) {
+                const RohRec v = recs[a];
+                unsigned b = a;
+                while (b > lo && recs[b - 1].a > v.a) { recs[b] = recs[b - 1]; --b; }
+                recs[b] = v;
+            }
         }
-        for (; w < hi; ++w) recs[w].ind = -1;
+        if (lane == 0) {
+            unsigned w = lo, k = 0;
+            while (k < n) {
+                RohRec cur = src[k++];
+                while ((cur.tag & 2) && k < n) {
+                    const RohRec nx = src[k];
+                    if (!((nx.tag & 1) && nx.a == cur.b + 1 && (nx.tag >> 2) == (cur.tag >> 2))) break;
+                    cur.b = nx.b;
+                    cur.tag = (cur.tag & ~2) | (nx.tag & 2);
+                    ++k;
+                }
+                if (cur.b - cur.a + 1 >= thr) recs[w++] = cur;   // w <= lo + k: never ahead of the records still to be read
+            }
+            for (; w < hi; ++w) recs[w].ind = -1;
+        }
+        __syncwarp();
     }
 }
 
@@ -816,7 +842,7 @@ cudaError_t launch_bucket_by_individual(const RohRec* in, const unsigned* count,
     if (!n_ind) return cudaSuccess;
     bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, n_ind);
     bucket_scatter_kernel<<<148, 256, 0, st>>>(in, count, cap, hist, out);
-    bucket_stitch_kernel<<<(n_ind + 63) / 64, 64, 0, st>>>(out, hist, n_ind, thr);
+    bucket_stitch_kernel<<<(n_ind + 3) / 4 < 148 * 8 ? (n_ind + 3) / 4 : 148 * 8, 128, 0, st>>>(out, hist, n_ind, thr);
     return cudaGetLastError();
 }
 
