@@ -891,7 +891,7 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
         if (e != cudaSuccess) { h->err = std::string("windows: ") + cudaGetErrorString(e); rc = 1; }
     } else if (!rc) {
         const size_t bytes = (size_t)n_lanes * slots * sizeof(double);
-        const bool staged = bytes <= ((size_t)64 << 20) && !pin_alloc(h, bytes);
+        const bool staged = !is_pinned(out) && bytes <= ((size_t)64 << 20) && !pin_alloc(h, bytes);
         cudaError_t e = cudaMemcpyAsync(staged ? (void*)h->pin : (void*)out, d_dump, bytes, cudaMemcpyDeviceToHost, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) { h->err = std::string("windows: ") + cudaGetErrorString(e); rc = 1; }
