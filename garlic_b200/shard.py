@@ -77,3 +77,26 @@ def merge_roh(per_rank, n_total: int, world: int):
         a[:, 0] += shard_range(n_total, world, r)[0]
         parts.append(a)
     return np.concatenate(parts, axis=0) if parts else np.empty((0, 4), np.int32)
+
+
+def ld_planes_local(codes_local, ld_individuals, lo):
+    """What ld_planes_kernel builds on one rank (wlod.cu): bit j of word j>>6 of the (non-missing, homozygous) planes of
+    every SNP, set only for the LD individuals this rank holds (global indices in ld_individuals, rank holds [lo, lo+n)).
+    codes_local: uint8[n_local, L] genotype codes.  → int64[L, 2, nw] (the all-reduce payload, as signed words)."""
+    n_local, L = codes_local.shape
+    nw = (len(ld_individuals) + 63) // 64
+    planes = np.zeros((L, 2, nw), np.uint64)
+    for j, g in enumerate(ld_individuals):
+        k = int(g) - lo
+        if 0 <= k < n_local:
+            c = codes_local[k]
+            bit = np.uint64(1) << np.uint64(j & 63)
+            planes[:, 0, j >> 6] |= np.where(c != 3, bit, np.uint64(0))
+            planes[:, 1, j >> 6] |= np.where((c == 0) | (c == 2), bit, np.uint64(0))
+    return planes.view(np.int64)
+
+
+def allreduce_ld_planes(dist, planes):
+    """The weighted path's exchange (garlic_gpu_ld_band): ranks own disjoint bits, so SUM is OR."""
+    dist.all_reduce(planes, op=dist.ReduceOp.SUM)
+    return planes

@@ -68,8 +68,13 @@ def _worker(rank, world, port, q):
     roh = np.array([(r[0] - lo, r[1], r[5], r[6]) for r in res["roh"] if lo <= r[0] < hi], np.int32).reshape(-1, 4)
     gathered = [None] * world
     dist.all_gather_object(gathered, roh)
+    # --weighted: bit-planes of the LD individuals (a list over the whole sample), SUM (= OR) all-reduce
+    ld = np.array([0, 3, 4, 9, 10, 17, 20, 29])
+    planes = torch.from_numpy(shard.ld_planes_local(code[:, :].T.astype(np.uint8).copy(), ld, lo))
+    shard.allreduce_ld_planes(dist, planes)
     if rank == 0:
-        q.put(dict(one=one, counts=counts.numpy(), thin=allv.numpy(), roh=shard.merge_roh(gathered, N, world)))
+        q.put(dict(one=one, counts=counts.numpy(), thin=allv.numpy(), roh=shard.merge_roh(gathered, N, world),
+                   planes=planes.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -100,6 +105,14 @@ def test_two_rank_exchanges_equal_single_rank():
     assert np.array_equal(got, win[kde][:, ::25])
     want = np.array([(r[0], r[1], r[5], r[6]) for r in res["roh"]], np.int32).reshape(-1, 4)
     assert np.array_equal(out["roh"], want)
+    # the reduced planes are the single-rank planes, and give the oracle's pair counts (hr2's total / HAB popcounts)
+    ld = np.array([0, 3, 4, 9, 10, 17, 20, 29])
+    whole = shard.ld_planes_local(codes.T.copy(), ld, 0)
+    assert np.array_equal(out["planes"], whole)
+    pl = out["planes"].view(np.uint64)
+    i, j = 100, 117
+    both = sum(bin(int(pl[i, 0, w] & pl[j, 0, w])).count("1") for w in range(pl.shape[2]))
+    assert both == int(((codes[i, ld] != 3) & (codes[j, ld] != 3)).sum())
 
 
 def test_shard_ranges_cover_everything():
