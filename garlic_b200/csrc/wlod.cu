@@ -299,7 +299,7 @@ wlod_mma_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items,
     const int gpb = blockDim.x >> 5;
     const int gblocks = (n_groups + gpb - 1) / gpb;
     const long long total = (long long)n_items * gblocks;
-    const int NW = ((W + 31) >> 5) + 1, nwords = (W + 31) >> 5, r = (32 - (W & 31)) & 31;
+    const int NW = ((W + 31) >> 5) + 1, r = (32 - (W & 31)) & 31;
     uint32_t* ring = ring_smem + threadIdx.x;
     const int rstride = blockDim.x;
     const double cut_hi = P.cutoff + P.tol, cut_lo = P.cutoff - P.tol;
@@ -443,7 +443,6 @@ wlod_mma_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items,
                 ring[wr * rstride] = fhi;
                 if (++wr >= NW) wr = 0;
             }
-            (void)nwords;
         }
         if (S.run_start >= 0) emit_run(P, it, ind, active, S.run_start, it.own_hi - 1);
         if (S.ambig && active) {
