@@ -87,6 +87,7 @@ struct garlic_gpu {
     int* d_cand_list = nullptr;
     unsigned* d_cand_cnt = nullptr;
     bool prune = true;             // GARLIC_NO_PRUNE=1 disables the pruning pass
+    bool precounted = false;       // d_counts already holds K2's counts of the rows put_packed copied
     bool phased = false;           // --phased: LD band from r2 between haplotypes instead of hr2
     bool wlod_mma = true;          // GARLIC_NO_MMA=1: weighted pass 2 with the exact kernel only
     ncclComm_t comm = nullptr;     // one rank per GPU, individuals sharded across ranks
@@ -387,6 +388,30 @@ static int put_packed_common(garlic_gpu* h, const void* rows, int64_t stride, cu
     if (!h->L0) FAIL("put_packed: call set_shape first");
     const int64_t need = (h->L0 + 3) / 4;
     if (stride < need) FAIL("put_packed: row stride smaller than ceil(n_loci/4)");
+    h->precounted = false;
+    if (kind == cudaMemcpyHostToDevice && h->n_ind >= 256 && h->d_counts) {
+        // host rows: the copy goes in slices of individuals on the copy stream and K2 counts each slice as soon as it has
+        // landed, so the column reduction hides behind the PCIe transfer (garlic_gpu_count_packed then has nothing to do)
+        const int n_slices = 8;
+        const int per = ((h->n_ind + n_slices - 1) / n_slices + 15) / 16 * 16;
+        CK(cudaMemsetAsync(h->d_counts, 0, (size_t)4 * h->L0 * sizeof(int), h->stream));
+        CK(cudaEventRecord(h->ev_copy, h->stream));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->ev_copy, 0));            // earlier work on the rows is done
+        for (int r0 = 0; r0 < h->n_ind; r0 += per) {
+            const int n = std::min(per, h->n_ind - r0);
+            uint64_t* dst = h->d_geno0 + (size_t)r0 * h->row_words0;
+            CK(cudaMemcpy2DAsync(dst, (size_t)h->row_words0 * 8, (const char*)rows + (size_t)r0 * stride, (size_t)stride, (size_t)need,
+                                 (size_t)n, kind, h->copy_stream));
+            CK(cudaEventRecord(h->ev_copy, h->copy_stream));
+            CK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+            LAUNCH(launch_count_packed(dst, h->row_words0, n, h->L0, h->d_counts, h->stream));
+        }
+        CK(cudaStreamSynchronize(h->copy_stream));                          // the caller may reuse its buffer
+        h->precounted = true;
+        h->counts_reduced = false;
+        h->have_geno0 = true;
+        return 0;
+    }
     CK(cudaMemcpy2DAsync(h->d_geno0, (size_t)h->row_words0 * 8, rows, (size_t)stride, (size_t)need, (size_t)h->n_ind, kind, h->stream));
     // bits of the last partial word beyond n_loci may hold anything; they are never read as SNPs < L0
     CK(cudaStreamSynchronize(h->stream));
@@ -417,8 +442,12 @@ int garlic_gpu_count_packed(garlic_gpu_t* h, const int32_t* nalleles_corr, const
     CK(cudaSetDevice(h->device));
     if (!h->have_geno0) FAIL("count_packed: no genotypes loaded");
     h->counts_reduced = false;
-    CK(cudaMemsetAsync(h->d_counts, 0, (size_t)4 * h->L0 * sizeof(int), h->stream));
-    LAUNCH(launch_count_packed(h->d_geno0, h->row_words0, h->n_ind, h->L0, h->d_counts, h->stream));
+    if (h->precounted) {
+        h->precounted = false;             // garlic_gpu_put_packed counted the rows while they arrived
+    } else {
+        CK(cudaMemsetAsync(h->d_counts, 0, (size_t)4 * h->L0 * sizeof(int), h->stream));
+        LAUNCH(launch_count_packed(h->d_geno0, h->row_words0, h->n_ind, h->L0, h->d_counts, h->stream));
+    }
     if (nalleles_corr || total_corr) {
         int *d_a = nullptr, *d_t = nullptr;
         if (nalleles_corr) { CK(cudaMalloc(&d_a, h->L0 * sizeof(int))); CK(cudaMemcpyAsync(d_a, nalleles_corr, h->L0 * sizeof(int), cudaMemcpyHostToDevice, h->stream)); }
