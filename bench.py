@@ -89,15 +89,19 @@ class ClockSampler:
     the region lasts tens of milliseconds, too short for `nvidia-smi -lms`.  Falls back to one nvidia-smi query."""
     REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20))
 
-    def __init__(self, index):
+    def __init__(self, index, n_devices=1):
+        """index: first local GPU; n_devices: how many consecutive local GPUs this (one) thread watches — under
+        torchrun rank 0 watches every GPU of the job so that the other ranks' host cores stay free."""
         self.index, self.sm, self.mask, self.mx, self.h, self.t = index, [], 0, None, None, None
         self.run = False
         try:
             import pynvml
             pynvml.nvmlInit()
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
-            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            ids = [int(x) for x in vis.split(",")] if vis and all(x.strip().isdigit() for x in vis.split(",")) else None
+            self.nv = pynvml
+            self.hs = [pynvml.nvmlDeviceGetHandleByIndex(ids[index + k] if ids else index + k) for k in range(n_devices)]
+            self.h = self.hs[0]
             self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
             self.h = None
@@ -105,11 +109,12 @@ class ClockSampler:
     def _poll(self):
         nv = self.nv
         while self.run:
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-            except Exception:
-                pass
+            for h in self.hs:
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    pass
             time.sleep(0.001)
 
     def start(self):
@@ -133,6 +138,26 @@ class ClockSampler:
         reasons = sorted(nm for nm, bit in self.REASONS if self.mask & bit)
         return dict(sm_mhz=float(np.median(self.sm)) if self.sm else None, sm_max_mhz=self.mx, reasons=reasons,
                     samples=len(self.sm), how="NVML polled every ms during the timed region")
+
+
+def bind_near_gpu(index):
+    """Run this rank on the host cores next to its GPU (NVML's ideal CPU set) before any page-locked buffer is
+    allocated: with 8 ranks on a two-socket host, pinned buffers on the wrong socket make every H2D copy cross it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        ids = [int(x) for x in vis.split(",")] if vis and all(x.strip().isdigit() for x in vis.split(",")) else None
+        h = pynvml.nvmlDeviceGetHandleByIndex(ids[index] if ids else index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1 and 64 * w + b < n_cpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
 
 
 # ------------------------------------------------------------------------------------------------
@@ -297,6 +322,7 @@ def main():
         return 1
     from garlic_b200.api import GarlicGPU
     from garlic_b200 import shard
+    near = bind_near_gpu(local) if world > 1 else 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
@@ -369,7 +395,8 @@ def main():
         for _ in range(warmup):
             step(resident)
         kms, launches0 = [], g.launch_count()
-        cs = ClockSampler(local) if sample_clocks else None
+        # one sampling thread for the whole job: rank 0 watches every GPU
+        cs = ClockSampler(0, world) if (sample_clocks and rank == 0) else None
         barrier()
         if cs:
             cs.start()
@@ -432,7 +459,7 @@ def main():
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
                 ms_per_step=ms_res / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                 data="synthetic", config=config, e2e=e2e, gpu_launches=int(launches), roofline=roofline,
-                clocks=clocks, roh_found=int(n_roh), loci_used=int(Lk), ambiguous_pairs_reevaluated=int(n_amb),
+                clocks=clocks, host_cores_bound_per_rank=int(near), roh_found=int(n_roh), loci_used=int(Lk), ambiguous_pairs_reevaluated=int(n_amb),
                 individual_windows_per_step=int(units_total),
                 phases_ms_one_synchronised_step={k: round(v, 3) for k, v in phases.items()})
 
