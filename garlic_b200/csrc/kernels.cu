@@ -1048,8 +1048,8 @@ cudaError_t launch_code_alleles(const uint8_t* alleles, int n_snp, int n_ind, in
 // K2: per-SNP counts from the packed matrix (pre-coded input path): column reduction over the GPU's
 // individuals (replaces the counting inside loadTPEDData, garlic-data.cpp:115-127, and calculateGenoFreq,
 // :656-676).  A thread owns one 64-bit word column (32 SNPs) for every 8th row of its block's row range; lanes of a
-// warp read 256 contiguous bytes of one row.  Counting is bit-sliced: per row two indicator words (g==1 / g==2
-// interleaved, and missing) are fed 8 rows at a time through a carry-save adder tree (LOP3: sum 0x96, carry 0xE8)
+// warp read 256 contiguous bytes of one row.  Counting is bit-sliced: per row two words (the packed word itself — even
+// bits = g in {1, missing}, odd bits = g in {2, missing} — and a missing indicator) are fed 8 rows at a time through a carry-save adder tree (LOP3: sum 0x96, carry 0xE8)
 // into vertical counters ones/twos/fours/eights…; every 248 rows the 8 bit-planes are turned into per-SNP byte
 // counts (nibble → 4 bytes by multiplication) and added to shared, then global, integer counters.
 // counts: [4][L0] = nalleles (Σ g over g<3), total (2·nonmiss), hom, nonmiss.
@@ -1142,9 +1142,10 @@ count_packed_kernel(const uint64_t* __restrict__ geno, int64_t row_words, int n_
                 uint64_t xa[8], xm[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const uint64_t lo = w[8 * h + i] & M, hi = (w[8 * h + i] >> 1) & M;
-                    xa[i] = (lo & ~hi) | ((hi & ~lo) << 1);   // g==1 at the even bit, g==2 at the odd bit
-                    xm[i] = lo & hi;                          // missing at the even bit
+                    // the packed word itself is counted: its even bits are set for g in {1, missing}, its odd bits for
+                    // g in {2, missing}; the missing calls are counted separately and taken off at the end
+                    xa[i] = w[8 * h + i];
+                    xm[i] = w[8 * h + i] & (w[8 * h + i] >> 1) & M;   // missing at the even bit
                 }
                 vc_add8(va, xa);
                 vc_add8(vm, xm);
@@ -1167,7 +1168,8 @@ count_packed_kernel(const uint64_t* __restrict__ geno, int64_t row_words, int n_
         const long long s = (long long)blockIdx.x * 8192 + i;
         if (s >= L0) continue;
         const int slot = (i & 31) * 256 + (i >> 5);
-        const int n1 = s_cnt[slot], n2 = s_cnt[32 * 256 + slot], nm = s_cnt[2 * 32 * 256 + slot];
+        const int nm = s_cnt[2 * 32 * 256 + slot];
+        const int n1 = s_cnt[slot] - nm, n2 = s_cnt[32 * 256 + slot] - nm;
         const int nonmiss = rows - nm;
         atomicAdd(&counts[0 * L0 + s], n1 + 2 * n2);
         atomicAdd(&counts[1 * L0 + s], 2 * nonmiss);
