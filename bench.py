@@ -248,6 +248,7 @@ def main():
     ap.add_argument("--n-ind", type=int, default=CFG["n_ind"])
     ap.add_argument("--n-loci", type=int, default=CFG["n_loci"])
     ap.add_argument("--cpu-sample", type=int, default=400, help="individuals in the cpu_baseline sample")
+    ap.add_argument("--cpu-sample-multi", type=int, default=48, help="individuals per rank in the N>1 parity sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--exact", action="store_true", help="whole-segment chains in pass 2")
     a = ap.parse_args()
@@ -394,7 +395,7 @@ def main():
     def timed(resident, steps, warmup, sample_clocks):
         for _ in range(warmup):
             step(resident)
-        kms, launches0 = [], g.launch_count()
+        kms, sqms, launches0 = [], [], g.launch_count()
         # one sampling thread for the whole job: rank 0 watches every GPU
         cs = ClockSampler(0, world) if (sample_clocks and rank == 0) else None
         barrier()
@@ -403,7 +404,9 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
-            kms.append(step(resident)["kernel_ms"])
+            st = step(resident)
+            kms.append(st["kernel_ms"])
+            sqms.append(st["squeeze_ms"])
         e1.record(stream)
         barrier()
         clocks = cs.stop() if cs else None
@@ -411,10 +414,10 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), float(np.mean(kms)), g.launch_count() - launches0, clocks
+        return float(t.item()), (float(np.mean(kms)), float(np.mean(sqms))), g.launch_count() - launches0, clocks
 
     g.put_packed_dev(rows_dev.data_ptr(), row_bytes)
-    ms_res, kms, launches, clocks = timed(True, a.steps, a.warmup, True)
+    ms_res, (kms, sqms), launches, clocks = timed(True, a.steps, a.warmup, True)
     units_local = state["stats"]["units"]
     units_total = units_local * world
     value = units_total * a.steps / (ms_res / 1e3)
@@ -429,27 +432,36 @@ def main():
     step(False)
     phases.pop("on")
 
-    # roofline of the dominant kernel (K5 pass 2, walk_kernel): algorithmic bytes per launch
+    # roofline of the dominant kernel: the fused compaction + pruning-bound pass (squeeze_bound_kernel, K3 + the bound of
+    # K5 pass 2), timed live with CUDA events on the library's stream around its launch in every step.  Algorithmic
+    # bytes per launch: the uncompacted matrix read once, the compacted matrix written once, the piece
+    # maxima written once, the per-SNP tables read once.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    alg_bytes = n_ind * Lk / 4.0 + Lk * 32.0 + n_items * 32.0 + n_roh * 16.0
-    achieved = alg_bytes / (kms / 1e3) / 1e9
+    n_pieces = (Lk + 255) // 256
+    alg_bytes = n_ind * L0 / 4.0 + n_ind * Lk / 4.0 + n_pieces * n_ind * 4.0 + (Lk / 16.0) * (16 + 4 + 16) + L0 * 4.0
+    achieved = alg_bytes / (sqms / 1e3) / 1e9
+    cand = (state["stats"]["candidate_pairs"] / state["stats"]["all_pairs"]) if state["stats"]["candidate_pairs"] >= 0 else None
+    walk_bytes = (cand or 1.0) * n_ind * Lk / 4.0 + n_pieces * n_ind * 4.0 + n_items * 32.0 + n_roh * 16.0
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
-                    kernel="walk_kernel<0,true,false> (K5 pass 2: windows->cutoff->coverage->ROH)",
-                    kernel_ms=kms, algorithmic_bytes_per_launch=alg_bytes,
+                    kernel="squeeze_bound_kernel<1,1,C2> (K3 column compaction fused with the pruning bound of K5 pass 2)",
+                    kernel_ms=sqms, algorithmic_bytes_per_launch=alg_bytes,
                     bytes_per_individual_window=alg_bytes / units_local,
                     peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                    kernel_units_per_s=units_local / (kms / 1e3),
-                pruning_pass_ms=state["stats"]["coarse_ms"],
-                candidate_pair_fraction=(state["stats"]["candidate_pairs"] / state["stats"]["all_pairs"]
-                                         if state["stats"]["candidate_pairs"] >= 0 else None),
-                    note="2-bit genotypes + per-SNP table: 0.27 B per individual-window, so this kernel is bound by "
-                         "fp64-add / L1 issue, not HBM (SURVEY §8d); frac is reported against HBM as the contract asks")
-    tr = os.path.join(ROOT, "profiles", "r01_walk_traffic.json")
+                    kernel_units_per_s=units_local / (sqms / 1e3),
+                    pass2=dict(kernels="select_kernel + walk_units_kernel (windows -> cutoff -> coverage -> ROH on the "
+                                       "candidates the bound leaves)", ms=kms, select_ms=state["stats"]["select_ms"],
+                               candidate_pair_fraction=cand, algorithmic_bytes=walk_bytes,
+                               achieved_gbs=walk_bytes / (kms / 1e3) / 1e9),
+                    pair_ms=sqms + kms,
+                    pair_achieved_gbs=(alg_bytes + walk_bytes) / ((sqms + kms) / 1e3) / 1e9,
+                    pair_frac=(alg_bytes + walk_bytes) / ((sqms + kms) / 1e3) / 1e9 / peak,
+                    note="traffic: dram__bytes of one ncu --set full capture of this kernel (profiles/), per launch")
+    tr = os.path.join(ROOT, "profiles", "r02_squeeze_traffic.json")
     if os.path.exists(tr):
         try:
             roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
@@ -463,21 +475,54 @@ def main():
                 individual_windows_per_step=int(units_total),
                 phases_ms_one_synchronised_step={k: round(v, 3) for k, v in phases.items()})
 
-    # cpu_baseline: rank 0, N=1 only, bounded sample of the same workload; doubles as a parity check
-    if rank == 0 and world == 1 and not a.no_cpu:
-        n_s = min(a.cpu_sample, n_ind)
+    # cpu_baseline: rank 0, N=1 only, bounded sample of the same workload; the same run doubles as the parity check.
+    # At N > 1 every rank checks a (smaller) sample of ITS OWN individuals against the reference's functions, and rank 0
+    # checks the all-reduced frequencies against counts made on the host from all ranks' rows.
+    if not a.no_cpu:
+        n_s = min(a.cpu_sample if world == 1 else a.cpu_sample_multi, n_ind)
         codes = unpack_rows(rows_host_np[:n_s], L0)
         chroms = cpu_chroms(codes, state["keep"], state["freq"], pos0, chr_off0, names, cens)
         cs = CpuSample(chroms, n_s, W, err, cutoff, ov, max_gap, 1)
         secs, roh_cpu = cs.run()
         rate, kind = cs.units / secs, cs.kind
-        line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=1, kind=kind, seconds=secs,
-                                    sample="first %d of the %d individuals x %d SNPs, same tables; the reference's "
-                                           "unweighted calcLOD/assembleROHWindows are single-threaded" % (n_s, n_ind, Lk))
+        if rank == 0 and world == 1:
+            line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=1, kind=kind, seconds=secs,
+                                        sample="first %d of the %d individuals x %d SNPs, same tables; the reference's "
+                                               "unweighted calcLOD/assembleROHWindows are single-threaded" % (n_s, n_ind, Lk))
         pos_k = pos0[state["keep"]]
         got = sorted((int(r[0]), int(r[1]), int(pos_k[r[2]]), int(pos_k[r[3]])) for r in roh_dev if r[0] < n_s)
-        line["parity_vs_cpu_sample"] = "identical ROH (%d)" % len(got) if got == sorted(roh_cpu) else \
+        mine = "identical ROH (%d)" % len(got) if got == sorted(roh_cpu) else \
             "MISMATCH: gpu %d vs cpu %d" % (len(got), len(roh_cpu))
+        # frequencies: host-side counts of this rank's packed rows, summed over ranks, against the library's freq[]
+        na = np.zeros(L0, np.int64)
+        tot = np.zeros(L0, np.int64)
+        L4 = (L0 + 3) // 4
+        for i0 in range(0, n_ind, 250):
+            b = rows_host_np[i0:i0 + 250, :L4]
+            for k in range(4):
+                gk = (b >> (2 * k)) & 3
+                cols = np.arange(k, L0, 4)
+                na[cols] += np.where(gk != 3, gk, 0).sum(0, dtype=np.int64)[:len(cols)]
+                tot[cols] += 2 * (gk != 3).sum(0, dtype=np.int64)[:len(cols)]
+        if dist is not None:
+            t = torch.from_numpy(np.stack([na, tot])).to(dev)
+            dist.all_reduce(t)
+            na, tot = t.cpu().numpy()
+        freq_cpu = np.where(tot > 0, na / np.maximum(tot, 1), 0.0)
+        freq_ok = bool(np.array_equal(freq_cpu, state["freq"]))
+        if dist is not None:
+            allp = [None] * world
+            dist.all_gather_object(allp, mine)
+        else:
+            allp = [mine]
+        kind_s = "reference functions" if kind == "reference" else "C port of the reference"
+        if all(x.startswith("identical") for x in allp):
+            line["parity_vs_cpu_sample"] = "identical ROH on %s (%s; first %d individuals of every rank vs the %s)" % (
+                "all %d ranks" % world if world > 1 else "the sample", ", ".join(x.split("(")[1].rstrip(")") for x in allp), n_s, kind_s)
+        else:
+            line["parity_vs_cpu_sample"] = "; ".join("rank %d: %s" % (r, x) for r, x in enumerate(allp))
+        line["parity_freq_vs_host_counts"] = ("identical freq[] (%d SNPs, counts of all %d ranks' rows)" % (L0, world)) if freq_ok \
+            else "MISMATCH in freq[]"
     if rank == 0:
         emit(line)
     g.close()

@@ -27,7 +27,7 @@ EXPORTS = [
     "garlic_gpu_ld_band", "garlic_gpu_set_wlod", "garlic_gpu_window_slots", "garlic_gpu_windows",
     "garlic_gpu_windows_dev", "garlic_gpu_windows_gather", "garlic_gpu_comm_id", "garlic_gpu_comm_init",
     "garlic_gpu_call_roh", "garlic_gpu_last_stats", "garlic_gpu_n_kept", "garlic_gpu_get_kept_index",
-    "garlic_gpu_get_genotypes",
+    "garlic_gpu_get_genotypes", "garlic_gpu_get_piece_bounds",
 ]
 
 
@@ -294,8 +294,17 @@ class GarlicGPU:
     def last_stats(self):
         s = (C.c_double * 8)()
         self.lib.garlic_gpu_last_stats(self.h, s)
-        return dict(items=s[0], units=s[1], ambiguous_pairs=s[2], kernel_ms=s[3], coarse_ms=s[4],
-                    candidate_pairs=s[5], all_pairs=s[6])
+        return dict(items=s[0], units=s[1], ambiguous_pairs=s[2], kernel_ms=s[3], select_ms=s[4],
+                    candidate_pairs=s[5], all_pairs=s[6], squeeze_ms=s[7])
+
+    def piece_bounds(self, W):
+        """uint32[n_pieces, n_ind]: the pruning bound's piece maxima (low / high int16, 1/64 LOD)."""
+        n_pieces = (self.L + 255) // 256
+        out = np.empty((n_pieces, self.n_ind), np.uint32)
+        n = C.c_int64(0)
+        self._ck(self.lib.garlic_gpu_get_piece_bounds(self.h, C.c_int(W), _p(out), C.c_int64(out.size), C.byref(n)))
+        assert n.value == n_pieces
+        return out
 
     def launch_count(self):
         return int(self.lib.garlic_gpu_launch_count(self.h))

@@ -18,7 +18,7 @@
 #include "kernels.h"
 #include "wlod.h"
 #include "segments.h"
-#include "coarse.cuh"
+#include "bound.cuh"
 
 using namespace garlic;
 
@@ -43,7 +43,9 @@ struct garlic_gpu {
     int gl_type = GARLIC_GL_ERROR;
     double error = -1, mu = 1e-9;
     int max_gap = 200000, M = 7, ld_W = 0;
-    double amax = 0;   // max |LOD table entry| (ambiguity tolerance)
+    double amax = 0;   // bound on |LOD table entry| of the table in use (ambiguity tolerance, see lod_bound())
+    double fmin = 0.5; // smallest min(f, 1-f) a caller-supplied frequency vector held (freq_override)
+    int* d_corr = nullptr;   // count_packed's correction vectors (2 x L0)
     int missing_char = '0';
     // device
     uint8_t* d_alleles = nullptr;
@@ -77,15 +79,28 @@ struct garlic_gpu {
     size_t indlist_cap = 0;
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t stats_items = 0;
-    uint32_t* d_keepw = nullptr;
     int* d_scan = nullptr;         // block counts of the keep scan, total, kept chromosome offsets
     int* d_breaks = nullptr;       // bad-pair list
     int* d_thin = nullptr;         // segment + chromosome tables of the thinned pass 1
-    uint32_t* d_cmask = nullptr;   // pruning tables (coarse.cuh), valid for coarse_W
-    int2* d_ccb = nullptr;         // 16 zero entries in front: blocks k >= -16 are addressable
-    int coarse_W = 0;
+    // K3 is deferred to the first consumer of the compacted rows so that it can run fused with the pruning bound
+    // (squeeze.cu): filter() only builds the plan
+    bool geno_pending = false;
+    uint4 *d_plan_head = nullptr, *d_plan_seg = nullptr;
+    int4* d_plan_rng = nullptr;
+    uint4* d_bhw = nullptr;        // bound tables (bound.cuh) per half-word, valid for bound_tables_W
+    int2* d_bbc = nullptr;         // per half-word q: {Bmax of block q - C2, chet}
+    int* d_bflag = nullptr;        // != 0: the table in use breaks the bound's assumptions (every pair is a candidate)
+    int bound_tables_W = 0;
+    uint32_t* d_pmax = nullptr;    // [n_pieces][pmax_stride] piece maxima of every individual, valid for bound_W
+    int64_t pmax_stride = 0;
+    int n_pieces = 0, bound_W = 0;
     int* d_cand_list = nullptr;
     unsigned* d_cand_cnt = nullptr;
+    int2* d_units = nullptr;       // work queue of the pruned pass 2: (item, first candidate)
+    unsigned* d_nunits = nullptr;  // [0] units appended, [1] candidate pairs
+    cudaEvent_t ev_sq0 = nullptr, ev_sq1 = nullptr;   // around the last fused compaction + bound launch
+    bool sq_timed = false;
+    int item_pieces = 1;           // pieces per item of the pruned pass (GARLIC_ITEM_PIECES)
     bool prune = true;             // GARLIC_NO_PRUNE=1 disables the pruning pass
     bool precounted = false;       // d_counts already holds K2's counts of the rows put_packed copied
     bool phased = false;           // --phased: LD band from r2 between haplotypes instead of hr2
@@ -97,8 +112,6 @@ struct garlic_gpu {
     cudaEvent_t ev2 = nullptr;
     cudaStream_t copy_stream = nullptr;   // device-to-host copies that overlap the kernels behind them (filter)
     cudaEvent_t ev_copy = nullptr;
-    int* d_first_word = nullptr;
-    uint8_t* d_first_skip = nullptr;
     uint8_t* pin = nullptr;        // pinned host staging buffer
     size_t pin_cap = 0;
     std::map<void*, size_t> cap;   // bytes behind each device pointer slot (keyed by the slot's address)
@@ -161,6 +174,19 @@ static int pin_alloc(garlic_gpu* h, size_t bytes)
     return 0;
 }
 
+// Bound on |lod()| for the table in use (garlic-roh.cpp:355-386).  With e in [1e-16, 1] (readTGLSData's clamp, or the
+// global --error) and f in (0,1):  lod(het) = log10(e) >= log10(e_min);  lod(hom) = log10((1-e)/(1-f) + e) lies in
+// [0, -log10(min(f,1-f))].  Frequencies made from counts are multiples of 1/(2 N_total); caller-supplied ones
+// (--freq-file) are scanned in garlic_gpu_filter.  One decade of slack on top.
+static double lod_bound(const garlic_gpu* h)
+{
+    const double n_total = 2.0 * ((double)h->n_ind + 1.0) * (double)std::max(1, h->comm_world);
+    double fmin = 1.0 / n_total;
+    if (h->fmin > 0 && h->fmin < fmin) fmin = h->fmin;
+    const double emin = h->have_gl ? 1e-16 : ((h->error > 0 && h->error < 1) ? h->error : 1e-16);
+    return std::max(-std::log10(emin), -std::log10(fmin)) + 1.0;
+}
+
 static bool is_pinned(const void* p)
 {
     cudaPointerAttributes a;
@@ -178,6 +204,8 @@ static int fetch_src(garlic_gpu* h)
     CK(cudaMemcpy(h->src.data(), h->d_src, h->L * sizeof(int), cudaMemcpyDeviceToHost));
     return 0;
 }
+
+static int ensure_geno(garlic_gpu* h, int W_hint);   // runs the deferred compaction (K3), fused with the bound when it can be
 
 extern "C" {
 
@@ -202,6 +230,9 @@ int garlic_gpu_create(int device, garlic_gpu_t** out)
     cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming);
     h->prune = getenv("GARLIC_NO_PRUNE") == nullptr;
+    cudaEventCreate(&h->ev_sq0);
+    cudaEventCreate(&h->ev_sq1);
+    if (const char* e = getenv("GARLIC_ITEM_PIECES")) { const int m = atoi(e); if (m >= 1 && m <= 16) h->item_pieces = m; }
     h->wlod_mma = getenv("GARLIC_NO_MMA") == nullptr;
     cudaMalloc((void**)&h->d_cnt, 4 * sizeof(unsigned));
     *out = h;
@@ -220,16 +251,19 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     dev_free(h->d_homf); dev_free(h->d_keep); dev_free(h->d_src); dev_free(h->d_pos0); dev_free(h->d_chr_of0);
     dev_free(h->d_pos); dev_free(h->d_chr_of); dev_free(h->d_chr_start); dev_free(h->d_chr_param);
     dev_free(h->d_out); dev_free(h->d_amb); dev_free(h->d_sorted); dev_free(h->d_hist); dev_free(h->d_cnt); dev_free(h->d_items); dev_free(h->d_indlist); dev_free(h->d_dump);
-    dev_free(h->d_keepw); dev_free(h->d_first_word); dev_free(h->d_first_skip); dev_free(h->d_scan); dev_free(h->d_breaks); dev_free(h->d_thin);
+    dev_free(h->d_scan); dev_free(h->d_breaks); dev_free(h->d_thin);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->ev_copy) cudaEventDestroy(h->ev_copy);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    dev_free(h->d_cmask); dev_free(h->d_ccb); dev_free(h->d_cand_list); dev_free(h->d_cand_cnt);
+    dev_free(h->d_plan_head); dev_free(h->d_plan_seg); dev_free(h->d_plan_rng); dev_free(h->d_bhw); dev_free(h->d_bbc); dev_free(h->d_bflag);
+    dev_free(h->d_pmax); dev_free(h->d_cand_list); dev_free(h->d_cand_cnt); dev_free(h->d_units); dev_free(h->d_nunits);
+    if (h->ev_sq0) cudaEventDestroy(h->ev_sq0);
+    if (h->ev_sq1) cudaEventDestroy(h->ev_sq1);
     if (h->comm) ncclCommDestroy(h->comm);
-    dev_free(h->d_gather);
+    dev_free(h->d_gather); dev_free(h->d_corr);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -323,8 +357,10 @@ int garlic_gpu_put_alleles(garlic_gpu_t* h, const uint8_t* alleles, int64_t snp0
     }
     uint8_t* dst = h->d_alleles + (size_t)snp0 * h->n_ind * 2;
     CK(cudaMemcpyAsync(dst, alleles, (size_t)n_snp * h->n_ind * 2, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->ev_copy, h->stream));
     LAUNCH(launch_first_allele(dst, n_snp, h->n_ind, h->ind_offset, (unsigned char)missing, h->d_key + snp0, h->stream));
     h->missing_char = (unsigned char)missing;
+    CK(cudaEventSynchronize(h->ev_copy));   // the copy has left the caller's buffer (it may be page-locked and reused)
     return 0;
 }
 
@@ -449,15 +485,14 @@ int garlic_gpu_count_packed(garlic_gpu_t* h, const int32_t* nalleles_corr, const
         LAUNCH(launch_count_packed(h->d_geno0, h->row_words0, h->n_ind, h->L0, h->d_counts, h->stream));
     }
     if (nalleles_corr || total_corr) {
-        int *d_a = nullptr, *d_t = nullptr;
-        if (nalleles_corr) { CK(cudaMalloc(&d_a, h->L0 * sizeof(int))); CK(cudaMemcpyAsync(d_a, nalleles_corr, h->L0 * sizeof(int), cudaMemcpyHostToDevice, h->stream)); }
-        if (total_corr) { CK(cudaMalloc(&d_t, h->L0 * sizeof(int))); CK(cudaMemcpyAsync(d_t, total_corr, h->L0 * sizeof(int), cudaMemcpyHostToDevice, h->stream)); }
+        if (dev_alloc(h, &h->d_corr, (size_t)2 * h->L0)) return 1;     // scratch kept on the handle
+        int *d_a = nalleles_corr ? h->d_corr : nullptr, *d_t = total_corr ? h->d_corr + h->L0 : nullptr;
+        if (d_a) CK(cudaMemcpyAsync(d_a, nalleles_corr, h->L0 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        if (d_t) CK(cudaMemcpyAsync(d_t, total_corr, h->L0 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         add_corr_kernel<<<(unsigned)std::min<int64_t>((h->L0 + 255) / 256, 148 * 16), 256, 0, h->stream>>>(h->d_counts, h->L0, d_a, d_t);
         CK(cudaGetLastError());
         h->launches++;
-        CK(cudaStreamSynchronize(h->stream));
-        if (d_a) cudaFree(d_a);
-        if (d_t) cudaFree(d_t);
+        CK(cudaStreamSynchronize(h->stream));                          // the caller may reuse its vectors
     }
     return 0;
 }
@@ -508,6 +543,7 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     if (oob && !chr_param) FAIL("filter: oob filtering needs chr_param");
     const int64_t L0 = h->L0;
     Laps laps("filter");
+    if (!freq_override) h->fmin = 0.5;
     bool freq_direct = false, keep_direct = false, copies_in_flight = false;
     if (dev_alloc(h, &h->d_freq0, (size_t)L0)) return 1;
     if (dev_alloc(h, &h->d_keep, (size_t)L0)) return 1;
@@ -516,7 +552,6 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
         CK(cudaMemcpyAsync(h->d_chr_param, chr_param, 4 * h->n_chr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     }
     // pinned staging: freq0[L0] doubles | keep[L0] bytes | total, chr_off_kept[C+1] ints
-    const int64_t n_in_words = (L0 + 31) >> 5;
     const int n_blocks = (int)((L0 + 1023) / 1024);
     const size_t off_keep = (size_t)L0 * 8, off_meta = (off_keep + (size_t)L0 + 63) & ~(size_t)63;
     if (pin_alloc(h, off_meta + (size_t)(h->n_chr + 2) * 4 + 64)) return 1;
@@ -525,9 +560,11 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     int32_t* meta = reinterpret_cast<int32_t*>(h->pin + off_meta);
     if (freq_override) {
         // --freq-file: frequencies come from the caller; the predicate is evaluated on the host copy
+        h->fmin = 0.5;
         for (int64_t s = 0; s < L0; ++s) {
             const double f = freq_override[s];
             bool k = (f > 0 && f < 1);
+            if (k) h->fmin = std::min(h->fmin, std::min(f, 1.0 - f));
             if (oob) {
                 int c = (int)(std::upper_bound(h->chr_off0.begin(), h->chr_off0.end(), s) - h->chr_off0.begin()) - 1;
                 const int32_t* cp = chr_param + 4 * c;
@@ -561,14 +598,10 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     // exclusive scan of the keep mask on the device: gather list, keep bits per input word, per output word
     // the input word it starts in, kept offset of every chromosome
     if (dev_alloc(h, &h->d_src, (size_t)L0)) return 1;
-    if (dev_alloc(h, &h->d_keepw, (size_t)n_in_words)) return 1;
-    if (dev_alloc(h, &h->d_first_word, (size_t)n_in_words)) return 1;
-    if (dev_alloc(h, &h->d_first_skip, (size_t)n_in_words)) return 1;
     if (dev_alloc(h, &h->d_scan, (size_t)n_blocks + h->n_chr + 8)) return 1;
     int* d_total = h->d_scan + n_blocks;
     int* d_chr_off_kept = d_total + 1;
-    CK(launch_keep_scan(h->d_keep, L0, h->d_chr_of0, h->n_chr, h->d_scan, d_total, h->d_src, h->d_keepw, h->d_first_word,
-                        h->d_first_skip, d_chr_off_kept, h->stream));
+    CK(launch_keep_scan(h->d_keep, L0, h->d_chr_of0, h->n_chr, h->d_scan, d_total, h->d_src, d_chr_off_kept, h->stream));
     h->launches += 3;
     CK(cudaMemcpyAsync(meta, d_total, (size_t)(h->n_chr + 2) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -592,8 +625,16 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
                        h->cap[(void*)&h->d_geno] < (size_t)h->n_ind * h->row_words * 8;
     if (dev_alloc(h, &h->d_geno, (size_t)h->n_ind * h->row_words)) return 1;
     if (fresh) CK(cudaMemsetAsync(h->d_geno, 0xff, (size_t)h->n_ind * h->row_words * 8, h->stream));
-    LAUNCH(launch_compact_geno(h->d_geno0, h->row_words0, n_in_words, h->d_keepw, h->d_first_word, h->d_first_skip, L,
-                               h->d_geno, h->row_words, h->n_ind, h->stream));
+    // the compaction itself waits for its first consumer (ensure_geno): here only its plan, from the gather list
+    h->n_pieces = (int)((L + kPiece - 1) / kPiece);
+    {
+        const long long n_q = 16ll * (h->n_pieces + 2);
+        if (dev_alloc(h, &h->d_plan_head, (size_t)n_q)) return 1;
+        if (dev_alloc(h, &h->d_plan_seg, (size_t)n_q * kPlanSegMax)) return 1;
+        if (dev_alloc(h, &h->d_plan_rng, (size_t)h->n_pieces + 2)) return 1;
+        LAUNCH(launch_plan(h->d_src, d_total, n_q, h->d_plan_head, h->d_plan_seg, h->d_plan_rng, h->stream));
+    }
+    h->geno_pending = true; h->bound_W = 0; h->bound_tables_W = 0;
     if (dev_alloc(h, &h->d_freq, (size_t)L + kPad)) return 1;
     CK(cudaMemsetAsync(h->d_freq, 0, (size_t)(L + kPad) * sizeof(double), h->stream));
     LAUNCH(launch_gather_f64(h->d_freq0, h->d_src, L, h->d_freq, h->stream));
@@ -633,6 +674,7 @@ int garlic_gpu_get_genotypes(garlic_gpu_t* h, int filtered, uint8_t* rows, int64
     const int64_t n = filtered ? h->L : h->L0;
     const int64_t need = (n + 3) / 4;
     if (row_stride_bytes < need) FAIL("get_genotypes: row stride too small");
+    if (filtered && ensure_geno(h, 0)) return 1;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy2D(rows, (size_t)row_stride_bytes, filtered ? h->d_geno : h->d_geno0,
                     (size_t)(filtered ? h->row_words : h->row_words0) * 8, (size_t)need, (size_t)h->n_ind, cudaMemcpyDeviceToHost));
@@ -666,9 +708,7 @@ int garlic_gpu_set_tables(garlic_gpu_t* h, double error, int max_gap, const int3
         CK(cudaMemcpyAsync(h->d_gpos, gpos, L * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
-    // bound on |LOD| for the ambiguity tolerance: with a global error the largest magnitudes are
-    // log10(error) (heterozygote) and log10 of 1/f-type terms; freq ∈ [1/(2N_total), 1-1/(2N_total)]
-    h->amax = 20.0;
+    h->amax = lod_bound(h);   // enters the ambiguity tolerance of the chunked / tensor-core passes
     laps.lap("lut");
     // gap/centromere-free stretches: bad adjacent pairs found on the device (a short list), sorted here
     {
@@ -701,7 +741,7 @@ int garlic_gpu_set_tables(garlic_gpu_t* h, double error, int max_gap, const int3
         }
     }
     laps.lap("stretches");
-    h->tables = true; h->have_ld = false; h->coarse_W = 0;
+    h->tables = true; h->have_ld = false; h->bound_W = 0; h->bound_tables_W = 0;
     return 0;
 }
 
@@ -710,8 +750,11 @@ int garlic_gpu_set_lut(garlic_gpu_t* h, const double* lut)
     CK(cudaSetDevice(h->device));
     if (!h->tables) FAIL("set_lut: call set_tables first");
     CK(cudaMemcpy(h->d_lut, lut, (size_t)h->L * 4 * sizeof(double), cudaMemcpyHostToDevice));
+    double m = 0;                                           // the caller's table: its own largest magnitude
+    for (int64_t i = 0; i < h->L * 4; ++i) { const double a = std::fabs(lut[i]); if (a > m && std::isfinite(a)) m = a; }
+    h->amax = std::max(lod_bound(h), m + 1.0);
     dev_free(h->d_wlut);   // the weighted score table is rebuilt on demand
-    h->coarse_W = 0;       // and so are the pruning tables
+    h->bound_W = 0; h->bound_tables_W = 0;   // and so are the pruning tables and the piece maxima
     return 0;
 }
 
@@ -805,6 +848,84 @@ static int launch_any_walk(garlic_gpu* h, const WalkParams& P, const Item* items
     return 0;
 }
 
+// ---- deferred compaction (K3) and the pruning bound (squeeze.cu, bound.cuh) ----
+static bool can_bound(const garlic_gpu* h, int W)
+{
+    return h->prune && h->tables && !h->have_gl && W >= kBoundMinW && bound_c2(W) <= kBoundMaxC2;
+}
+
+static int ensure_bound_tables(garlic_gpu* h, int W)
+{
+    if (h->bound_tables_W == W) return 0;
+    const long long n_hw = 16ll * (h->n_pieces + 2);           // 256 (n_pieces + 2) + W + 16 < L + kPad table entries
+    if (dev_alloc(h, &h->d_bhw, (size_t)n_hw)) return 1;
+    if (dev_alloc(h, &h->d_bbc, (size_t)n_hw)) return 1;
+    if (dev_alloc(h, &h->d_bflag, (size_t)4)) return 1;
+    CK(cudaMemsetAsync(h->d_bflag, 0, 4 * sizeof(int), h->stream));
+    LAUNCH(launch_bound_tables(h->d_lut, n_hw, h->L, W, h->d_bhw, h->d_bbc, h->d_bflag, h->stream));
+    h->bound_tables_W = W;
+    return 0;
+}
+
+static SqueezeParams squeeze_params(garlic_gpu* h, bool squeeze, int W)
+{
+    SqueezeParams Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.gin = squeeze ? h->d_geno0 : h->d_geno;
+    Q.in_words = squeeze ? h->row_words0 : h->row_words;
+    Q.gout = h->d_geno; Q.out_words = h->row_words;
+    Q.plan_head = h->d_plan_head; Q.plan_seg = h->d_plan_seg; Q.piece_rng = h->d_plan_rng; Q.src = h->d_src; Q.n_kept = h->d_scan + (int)((h->L0 + 1023) / 1024);
+    Q.n_ind = h->n_ind;
+    Q.hw = h->d_bhw; Q.bc = h->d_bbc;
+    Q.lag = bound_lag(W);
+    Q.pmax = h->d_pmax; Q.pmax_stride = h->pmax_stride;
+    Q.n_pieces = h->n_pieces;
+    return Q;
+}
+
+static int alloc_pmax(garlic_gpu* h)
+{
+    h->pmax_stride = ((int64_t)h->n_ind + 31) & ~(int64_t)31;
+    return dev_alloc(h, &h->d_pmax, (size_t)h->n_pieces * h->pmax_stride);
+}
+
+// The compacted rows are needed now.  W_hint > 0: the caller is about to work with unweighted table-mode windows of
+// that size, so the pruning bound for it rides along in the same pass over the matrix.
+static int ensure_geno(garlic_gpu* h, int W_hint)
+{
+    if (!h->geno_pending) return 0;
+    int c2 = 0;
+    if (W_hint > 0 && can_bound(h, W_hint)) {
+        if (ensure_bound_tables(h, W_hint)) return 1;
+        if (alloc_pmax(h)) return 1;
+        c2 = bound_c2(W_hint);
+    }
+    const SqueezeParams Q = squeeze_params(h, true, W_hint);
+    CK(cudaEventRecord(h->ev_sq0, h->stream));
+    LAUNCH(launch_squeeze_bound(Q, true, c2, h->stream));
+    CK(cudaEventRecord(h->ev_sq1, h->stream));
+    h->sq_timed = true;
+    h->geno_pending = false;
+    if (c2) h->bound_W = W_hint;
+    return 0;
+}
+
+// piece maxima for window size W present (fused with the compaction if that is still pending)
+static int ensure_bound(garlic_gpu* h, int W)
+{
+    if (ensure_geno(h, W)) return 1;
+    if (h->bound_W == W) return 0;
+    if (ensure_bound_tables(h, W)) return 1;
+    if (alloc_pmax(h)) return 1;
+    const SqueezeParams Q = squeeze_params(h, false, W);
+    CK(cudaEventRecord(h->ev_sq0, h->stream));
+    LAUNCH(launch_squeeze_bound(Q, false, bound_c2(W), h->stream));
+    CK(cudaEventRecord(h->ev_sq1, h->stream));
+    h->sq_timed = true;
+    h->bound_W = W;
+    return 0;
+}
+
 extern "C" {
 
 int64_t garlic_gpu_window_slots(garlic_gpu_t* h, int step)
@@ -867,6 +988,7 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
     if (winsize < 2 || winsize > kMaxW) FAIL("windows: winsize out of range [2,4096]");
     if (step < 1) FAIL("windows: step must be >= 1");
     if (weighted && ensure_weighted(h, winsize)) return 1;
+    if (ensure_geno(h, weighted ? 0 : winsize)) return 1;
     const int W = winsize;
     const int n_lanes = individuals ? n : h->n_ind;
     if (individuals) {
@@ -941,6 +1063,11 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     if (weighted && ensure_weighted(h, winsize)) return 1;
     const int W = winsize;
     Laps laps("call_roh");
+    // pruned pass (bound.cuh): unweighted table mode, window sizes the bound covers, cutoffs inside its fixed-point range
+    int cut_ok = 0;
+    bound_cut_store(cutoff, 1.0, &cut_ok);
+    bool prune = !exact && !weighted && can_bound(h, W) && cut_ok;
+    if (ensure_geno(h, prune ? W : 0)) return 1;
     // garlic-roh.cpp:422-424, compared against integers at :466 and :477
     double thr_d = overlap_frac * W;
     thr_d = (thr_d >= 1) ? thr_d : 1;
@@ -956,7 +1083,13 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     if (weighted) chunk = (!exact && h->wlod_mma && W >= kWlodMmaMinW) ? std::max(256, pick_chunk(h->L, W, h->n_ind, 0) / 2)
                                                                       : std::max(64, pick_chunk(h->L, W, h->n_ind, 0) / 8);
     else if (!exact) chunk = pick_chunk(h->L, W, h->n_ind, h->have_gl ? 0 : kTileSnpsMax);
-    build_items(h->chr_off, W, segs, chunk, 0, items);
+    if (prune) {
+        build_items_aligned(h->chr_off, W, segs, kPiece * h->item_pieces, items);
+        chunk = 0;
+        for (const Item& it : items) chunk = std::max(chunk, it.own_hi - it.own_lo);
+        prune = items_tile_snps(items, W) <= kTileSnpsMax && (int64_t)items.size() * h->n_ind < (1ll << 31);
+    }
+    if (!prune) build_items(h->chr_off, W, segs, chunk, 0, items);
     if (upload_items(h, items)) return 1;
     int64_t n_win = 0;
     for (const Segment& s : segs) n_win += s.we - s.ws;
@@ -974,17 +1107,20 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     }
     laps.lap("items");
     std::vector<RohRec>&recs = h->recs_buf, &ambs = h->ambs_buf;
+    recs.clear(); ambs.clear();
     size_t n_stage = 0;            // records waiting in the pinned staging buffer
+    bool done = false;
     float ms = 0, ms_coarse = 0;
     bool pruned = false;
     for (int attempt = 0; attempt < 3; ++attempt) {
         WalkParams P = base_params(h, W);
         P.cutoff = cutoff; P.thr = thr;
         if (!exact && !weighted) {
-            // |fast − reference chain| ≤ (chain length + 2W)·2·2^-53·(W+1)·amax — see DESIGN.md §6
+            // |fast − reference chain| ≤ |reference chain − exact sum| + |chunked chain − exact sum|
+            //   ≤ (longest + W)·2ε·(W+1)·amax + (chunk + 2W)·2ε·(W+1)·amax,  2ε = 2^-52 — see DESIGN.md §5
             int64_t longest = 0;
             for (const Segment& s : segs) longest = std::max<int64_t>(longest, s.we - s.ws);
-            P.tol = (double)(longest + 2 * W) * 2.220446049250313e-16 * (W + 1) * h->amax;
+            P.tol = (double)(longest + chunk + 3 * W) * 2.220446049250313e-16 * (W + 1) * h->amax;
         }
         if (!exact && weighted && h->wlod_mma && W >= kWlodMmaMinW) {
             // |DMMA sum − reference mul-then-add sum| ≤ (W+8)·2ε·W·amax: scores are bounded by amax (nomut, norec ≤ 1)
@@ -992,33 +1128,26 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
             P.tol = (double)(W + 8) * 2.0 * 2.220446049250313e-16 * W * h->amax;
         }
         CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
-        // pruning pass (coarse.cuh): drop (individual, item) pairs that provably hold no window >= cutoff - tol
+        // pruned pass: the piece maxima (computed with the compaction, or now) are thresholded into dense per-item
+        // candidate lists and a queue of work units; the walker below only visits those
         const int tile_snps = items_tile_snps(items, W);
-        const bool prune = h->prune && !exact && !weighted && !h->have_gl && W >= kCoarseMinW && W <= kCoarseMaxW &&
-                           tile_snps <= kTileSnpsMax && (int64_t)items.size() * h->n_ind < (1ll << 31);
+        const bool prune_now = prune && !exact;
         CandList cl;
+        unsigned unit_cap = 0;
         CK(cudaEventRecord(h->ev0, h->stream));
-        if (prune) {
-            const int64_t n_hw = (h->L + kPad - 512) >> 4;
-            if (h->coarse_W != W) {
-                if (dev_alloc(h, &h->d_cmask, (size_t)n_hw)) return 1;
-                if (dev_alloc(h, &h->d_ccb, (size_t)n_hw + 16)) return 1;
-                CK(cudaMemsetAsync(h->d_ccb, 0, 16 * sizeof(int2), h->stream));
-                LAUNCH(launch_coarse_tables(h->d_lut, n_hw, W, h->d_cmask, h->d_ccb + 16, h->stream));
-                h->coarse_W = W;
-            }
+        if (prune_now) {
+            if (ensure_bound(h, W)) return 1;
+            int ok = 0;
+            const int cut_store = bound_cut_store(cutoff, P.tol, &ok);
+            const int per_item = (h->n_ind + kUnitThreads - 1) / kUnitThreads;
+            unit_cap = (unsigned)std::min<int64_t>((int64_t)items.size() * per_item, 1ll << 28);
             if (dev_alloc(h, &h->d_cand_list, (size_t)items.size() * h->n_ind)) return 1;
             if (dev_alloc(h, &h->d_cand_cnt, items.size() + 1)) return 1;
-            CK(cudaMemsetAsync(h->d_cand_cnt, 0, (items.size() + 1) * sizeof(unsigned), h->stream));
-            CoarseParams Q;
-            Q.geno = h->d_geno; Q.row_words = h->row_words; Q.mask = h->d_cmask; Q.cb = h->d_ccb + 16;
-            Q.W = W; Q.c1 = (W - 16) >> 4; Q.c2 = (W + 14) >> 4; Q.n_lanes = h->n_ind;
-            // c_het = log10(error) (lod() of a heterozygote, garlic-roh.cpp:368-372), rounded toward zero
-            const double fx = (double)(1 << kCoarseShift);
-            Q.chet_fixed = (int)std::ceil((std::log10(h->error) + 1e-9) * fx);
-            const double cl_ = (cutoff - P.tol) * fx - 2.0;
-            Q.cut_fixed = cl_ > 2.0e9 ? 2000000000 : (cl_ < -2.0e9 ? -2000000000 : (int)std::floor(cl_));
-            LAUNCH(launch_coarse(Q, h->d_items, (int)items.size(), h->d_cand_list, h->d_cand_cnt, h->n_ind, h->stream));
+            if (dev_alloc(h, &h->d_units, (size_t)unit_cap)) return 1;
+            if (dev_alloc(h, &h->d_nunits, (size_t)4)) return 1;
+            CK(cudaMemsetAsync(h->d_nunits, 0, 4 * sizeof(unsigned), h->stream));
+            LAUNCH(launch_select(h->d_items, (int)items.size(), h->d_pmax, h->pmax_stride, h->n_ind, cut_store, h->d_bflag,
+                                 h->d_cand_list, h->n_ind, h->d_cand_cnt, h->d_units, h->d_nunits, unit_cap, kUnitThreads, h->stream));
             cl.list = h->d_cand_list; cl.cnt = h->d_cand_cnt; cl.stride = h->n_ind;
         }
         CK(cudaEventRecord(h->ev2, h->stream));
@@ -1027,7 +1156,8 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         if (dev_alloc(h, &h->d_sorted, (size_t)h->out_cap)) return 1;
         CK(cudaMemsetAsync(h->d_hist, 0, ((size_t)h->n_ind + 1) * sizeof(unsigned), h->stream));
         P.hist = h->d_hist;
-        if (launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, true, false, tile_snps, cl)) return 1;
+        if (prune_now) LAUNCH(launch_walk_units(P, h->d_items, h->d_units, h->d_nunits, unit_cap, tile_snps, cl, h->stream));
+        else if (launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, true, false, tile_snps)) return 1;
         CK(cudaEventRecord(h->ev1, h->stream));
         LAUNCH(launch_bucket_by_individual(h->d_out, h->d_cnt, h->out_cap, h->d_hist, h->n_ind, h->d_sorted, thr, h->stream));
         unsigned cnt[4];
@@ -1035,7 +1165,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         CK(cudaStreamSynchronize(h->stream));
         CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         CK(cudaEventElapsedTime(&ms_coarse, h->ev0, h->ev2));
-        pruned = prune;
+        pruned = prune_now;
         if (cnt[0] > h->out_cap) {
             h->out_cap = cnt[0] + cnt[0] / 4 + 1024;
             if (dev_alloc(h, &h->d_out, h->out_cap)) return 1;
@@ -1061,8 +1191,10 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
             if (cnt[1]) take_stitched(stage, cnt[0], recs);
             memcpy(ambs.data(), stage + cnt[0], cnt[1] * sizeof(RohRec));
         }
+        done = true;
         break;
     }
+    if (!done) FAIL("call_roh: record buffers still overflowing after three attempts");
     laps.lap("kernel+d2h");
     // exact re-evaluation of (individual, segment) pairs that had a window within rounding
     // distance of the cutoff: one whole-segment launch per distinct segment
@@ -1130,17 +1262,36 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
 
 int garlic_gpu_last_stats(garlic_gpu_t* h, double* s)
 {
-    if (h->stats_items > 0) {   // candidate (individual, item) pairs that went to the exact walker
-        std::vector<unsigned> cc(h->stats_items);
+    if (h->stats_items > 0) {   // candidate (individual, item) pairs that went to the walker
+        unsigned nu[2] = {0, 0};
         CK(cudaSetDevice(h->device));
         CK(cudaStreamSynchronize(h->stream));
-        CK(cudaMemcpy(cc.data(), h->d_cand_cnt, cc.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
-        double tot = 0;
-        for (unsigned v : cc) tot += v;
-        h->stats[5] = tot;
+        CK(cudaMemcpy(nu, h->d_nunits, sizeof(nu), cudaMemcpyDeviceToHost));
+        h->stats[5] = (double)nu[1];
         h->stats_items = 0;
     }
+    if (h->sq_timed) {          // the last compaction (+ bound) launch
+        float ms = 0;
+        CK(cudaSetDevice(h->device));
+        CK(cudaEventSynchronize(h->ev_sq1));
+        CK(cudaEventElapsedTime(&ms, h->ev_sq0, h->ev_sq1));
+        h->stats[7] = ms;
+    }
     for (int i = 0; i < 8; ++i) s[i] = h->stats[i];
+    return 0;
+}
+
+int garlic_gpu_get_piece_bounds(garlic_gpu_t* h, int winsize, uint32_t* out, int64_t cap_entries, int64_t* n_pieces)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->tables) FAIL("get_piece_bounds: call set_tables first");
+    if (!can_bound(h, winsize)) FAIL("get_piece_bounds: no bound for this mode / window size (unweighted table mode, 32 <= winsize <= 209)");
+    if (ensure_bound(h, winsize)) return 1;
+    if (n_pieces) *n_pieces = h->n_pieces;
+    if ((int64_t)h->n_pieces * h->n_ind > cap_entries) FAIL("get_piece_bounds: output buffer too small");
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy2D(out, (size_t)h->n_ind * 4, h->d_pmax, (size_t)h->pmax_stride * 4, (size_t)h->n_ind * 4, (size_t)h->n_pieces,
+                    cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -1149,6 +1300,7 @@ int garlic_gpu_ld_band(garlic_gpu_t* h, int winsize, const int32_t* ld_individua
     CK(cudaSetDevice(h->device));
     if (!h->tables) FAIL("ld_band: call set_tables first");
     if (winsize < 2 || winsize > kMaxW) FAIL("ld_band: winsize out of range [2,4096]");
+    if (ensure_geno(h, 0)) return 1;
     const int64_t L = h->L;
     const int W = winsize;
     // sharded run: indices address the whole sample (this rank holds [ind_offset, ind_offset + n_ind))

@@ -7,7 +7,6 @@
 #include <algorithm>
 #include "common.cuh"
 #include "walk.cuh"
-#include "coarse.cuh"
 #include "kernels.h"
 
 namespace garlic {
@@ -108,115 +107,66 @@ walk_kernel(const WalkParams P, const Item* __restrict__ items, int n_items, int
 }
 
 // ------------------------------------------------------------------------------------------
-// Pruning pass (coarse.cuh): tables per window size, then one warp = 32 individuals scanning one item.
+// K5 pass 2 on the candidates the bound left (squeeze.cu:select_kernel): one CTA of two warps per work unit = up to 64
+// candidate individuals of one piece-sized item, taken from a device-resident queue (the host never learns its length).
+// The item's slice of the per-SNP table (about 14 KB at W = 50) is staged by one bulk copy per unit; two-warp CTAs keep
+// the barrier around it cheap and let some twenty units share an SM.
 // ------------------------------------------------------------------------------------------
-__global__ void coarse_tables_kernel(const double* __restrict__ lut, long long n_hw, int W, int c2,
-                                     uint32_t* __restrict__ mask, int2* __restrict__ cb)
+__global__ void __launch_bounds__(kUnitThreads, 16)
+walk_units_kernel(const WalkParams P, const Item* __restrict__ items, const int2* __restrict__ units,
+                  const unsigned* __restrict__ n_units, unsigned unit_cap, int tile_bytes, const int* __restrict__ cand_list,
+                  const unsigned* __restrict__ cand_cnt, int cand_stride)
 {
-    const double scale = (double)(1 << kCoarseShift);
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n_hw; k += (long long)gridDim.x * blockDim.x) {
-        const long long s0 = k * 16;
-        // base[s] = min(lut[s][0], lut[s][2]); sliding window sums B(t), t = s0 .. s0+15
-        double b = 0.0;
-        for (int i = 0; i < W; ++i) { const double* e = lut + (s0 + i) * 4; b += fmin(e[0], e[2]); }
-        double bmax = b;
-        for (int j = 1; j < 16; ++j) {
-            const double* eo = lut + (s0 + j - 1) * 4;
-            const double* ei = lut + (s0 + j - 1 + W) * 4;
-            b = b - fmin(eo[0], eo[2]) + fmin(ei[0], ei[2]);
-            bmax = fmax(bmax, b);
-        }
-        double dlo = 0.0, dhi = 0.0;
-        const long long s_end = s0 + 16 * (c2 + 1);
-        for (long long s = s0; s < s_end; ++s) {
-            const double* e = lut + s * 4;
-            const double d = fabs(e[0] - e[2]);
-            if (d > kCoarseSplit) dhi = fmax(dhi, d); else dlo = fmax(dlo, d);
-        }
-        uint32_t m = 0u;
-        for (int j = 0; j < 16; ++j) {
-            const double* e = lut + (s0 + j) * 4;
-            if (e[2] > e[0]) m |= 1u << (2 * j);
-            if (fabs(e[0] - e[2]) > kCoarseSplit) m |= 2u << (2 * j);
-        }
-        const double qlo = fmin(ceil(dlo * scale) + 1.0, 65535.0), qhi = fmin(ceil(dhi * scale) + 1.0, 65535.0);
-        mask[k] = m;
-        int2 o;
-        o.x = (int)ceil(bmax * scale) + 2;
-        o.y = (int)((uint32_t)qlo | ((uint32_t)qhi << 16));
-        cb[k] = o;
-    }
-}
-
-template <int C2>
-__global__ void __launch_bounds__(kWalkThreads)
-coarse_kernel(const CoarseParams P, const Item* __restrict__ items, int n_items, int n_groups,
-              int* __restrict__ cand_list, unsigned* __restrict__ cand_cnt, int cand_stride)
-{
+    extern __shared__ __align__(128) unsigned char walk_smem[];
+    unsigned char* tile_s = walk_smem;
+    uint32_t* ring_smem = reinterpret_cast<uint32_t*>(walk_smem + tile_bytes);
+    const int NW = ((P.W + 31) >> 5) + 1;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(ring_smem + NW * kUnitThreads);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gpb = blockDim.x >> 5;
-    const int gblocks = (n_groups + gpb - 1) / gpb;
-    const long long total = (long long)n_items * gblocks;
-    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
-        const int item = (int)(u / gblocks);
-        const int group = (int)(u % gblocks) * gpb + warp;
-        if (group >= n_groups) continue;
-        const int ind = group * 32 + lane;
-        const bool active = ind < P.n_lanes;
-        const Item it = items[item];
-        const bool cand = coarse_item<C2>(P, it, active ? ind : P.n_lanes - 1) && active;
-        const unsigned m = __ballot_sync(0xffffffffu, cand);
-        if (m) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&cand_cnt[item], (unsigned)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (cand) cand_list[(int64_t)item * cand_stride + base + __popc(m & ((1u << lane) - 1u))] = ind;
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    unsigned nu = *n_units;
+    nu = nu < unit_cap ? nu : unit_cap;
+    uint32_t phase = 0;
+    for (unsigned u = blockIdx.x; u < nu; u += gridDim.x) {
+        const int2 un = units[u];
+        const Item it = items[un.x];
+        int n_lanes = (int)cand_cnt[un.x] - un.y;
+        n_lanes = n_lanes < kUnitThreads ? n_lanes : kUnitThreads;
+        const int* list = cand_list + (int64_t)un.x * cand_stride + un.y;
+        const int nblk = (it.own_hi - 1 - it.w0 + 31) >> 5;
+        const uint32_t bytes = (uint32_t)(32 * nblk + P.W) * 32u;
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(tile_s, P.lut + (int64_t)it.w0 * 4, bytes, bar);
         }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        if (warp * 32 < n_lanes) {
+            const int k = warp * 32 + lane;
+            const bool active = k < n_lanes;
+            const int kk = active ? k : n_lanes - 1;
+            walk_item<0, true, false>(P, it, kk, active, ring_smem + threadIdx.x, kUnitThreads,
+                                      reinterpret_cast<const char*>(tile_s), it.w0, list[kk]);
+        }
+        __syncthreads();   // both warps are done with the tile before the next copy lands
     }
 }
 
-cudaError_t launch_coarse_tables(const double* lut, long long n_hw, int W, uint32_t* mask, int2* cb, cudaStream_t st)
+cudaError_t launch_walk_units(const WalkParams& P, const Item* items, const int2* units, const unsigned* n_units,
+                              unsigned unit_cap, int tile_snps, const CandList& cl, cudaStream_t st)
 {
-    if (!n_hw) return cudaSuccess;
-    long long blocks = (n_hw + 127) / 128;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    coarse_tables_kernel<<<(unsigned)blocks, 128, 0, st>>>(lut, n_hw, W, (W + 14) >> 4, mask, cb);
-    return cudaGetLastError();
-}
-
-template <int C2>
-static void launch_coarse_t(const CoarseParams& P, const Item* items, int n_items, int n_groups, unsigned grid,
-                            int* cand_list, unsigned* cand_cnt, int cand_stride, cudaStream_t st)
-{
-    coarse_kernel<C2><<<grid, kWalkThreads, 0, st>>>(P, items, n_items, n_groups, cand_list, cand_cnt, cand_stride);
-}
-
-cudaError_t launch_coarse(const CoarseParams& P, const Item* items, int n_items, int* cand_list, unsigned* cand_cnt,
-                          int cand_stride, cudaStream_t st)
-{
-    if (!n_items || !P.n_lanes) return cudaSuccess;
-    const int n_groups = (P.n_lanes + 31) / 32;
-    const int gpb = kWalkThreads / 32;
-    const long long total = (long long)n_items * ((n_groups + gpb - 1) / gpb);
-    long long grid = total;
-    const long long cap = 148ll * 8 * 16;
-    if (grid > cap) grid = cap;
-    const unsigned g = (unsigned)grid;
-    switch (P.c2) {
-        case 2: launch_coarse_t<2>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
-        case 3: launch_coarse_t<3>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
-        case 4: launch_coarse_t<4>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
-        case 5: launch_coarse_t<5>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
-        case 6: launch_coarse_t<6>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
-        case 7: launch_coarse_t<7>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
-        case 8: launch_coarse_t<8>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
-        case 9: launch_coarse_t<9>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
-        case 10: launch_coarse_t<10>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
-        case 11: launch_coarse_t<11>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
-        case 12: launch_coarse_t<12>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
-        case 13: launch_coarse_t<13>(P, items, n_items, n_groups, g, cand_list, cand_cnt, cand_stride, st); break;
-        default: return cudaErrorInvalidValue;
+    const int NW = ((P.W + 31) >> 5) + 1;
+    const int tile_bytes = tile_snps * 32;
+    const size_t smem = (size_t)tile_bytes + (size_t)NW * kUnitThreads * sizeof(uint32_t) + 16;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(walk_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
     }
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    per_sm = per_sm > 16 ? 16 : (per_sm < 1 ? 1 : per_sm);
+    walk_units_kernel<<<148 * per_sm, kUnitThreads, smem, st>>>(P, items, units, n_units, unit_cap, tile_bytes, cl.list, cl.cnt,
+                                                               cl.stride);
     return cudaGetLastError();
 }
 
@@ -781,41 +731,46 @@ __global__ void bucket_scatter_kernel(const RohRec* __restrict__ in, const unsig
     }
 }
 
-// One warp per individual: order its runs by start, merge the pieces of runs that were cut at chunk borders and
+// One warp per individual: order its runs by start, merge the pieces of runs that were cut at item borders and
 // apply the minimum-length rule (garlic-roh.cpp:477) — segments.h:stitch_runs, in place; dropped slots get ind = -1.
-// Up to 32 runs: every lane takes one record, ranks it against the others by shuffles and drops it into shared memory
-// in order; lane 0 then merges from there.  Larger buckets are sorted serially in global memory.
+// Up to kStitchSmem runs (the piece-sized items of the pruned pass cut a long ROH into several): the bucket is ranked
+// by all lanes against a copy in shared memory, dropped into a second shared array in order, and lane 0 merges from
+// there.  Larger buckets (cutoffs that flag nearly everything) are ranked in global memory through `scratch`.
 // ends: the bucket offsets after the scatter (= end of every individual's bucket).
+constexpr int kStitchSmem = 256;
 __global__ void __launch_bounds__(128)
-bucket_stitch_kernel(RohRec* __restrict__ recs, const unsigned* __restrict__ ends, int n_ind, int thr)
+bucket_stitch_kernel(RohRec* __restrict__ recs, RohRec* __restrict__ scratch, const unsigned* __restrict__ ends, int n_ind, int thr)
 {
-    __shared__ RohRec s_rec[4][32];
+    __shared__ RohRec s_in[4][kStitchSmem];
+    __shared__ RohRec s_rec[4][kStitchSmem];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = blockIdx.x * 4 + warp; i < n_ind; i += gridDim.x * 4) {
         const unsigned lo = i ? ends[i - 1] : 0u, hi = ends[i];
         const unsigned n = hi - lo;
-        const RohRec* src = recs + lo;
-        if (n <= 32u) {
-            RohRec mine;
-            mine.ind = i; mine.a = 0x7fffffff; mine.b = 0; mine.tag = 0;
-            if ((unsigned)lane < n) mine = recs[lo + lane];
-            // rank among the bucket (starts of one individual's runs are distinct; ties broken by lane anyway)
-            int rank = 0;
-            for (unsigned j = 0; j < n; ++j) {
-                const int aj = __shfl_sync(0xffffffffu, mine.a, (int)j);
-                rank += (aj < mine.a) || (aj == mine.a && (int)j < lane);
-            }
+        if (n == 0u) continue;
+        const RohRec* src;
+        if (n <= (unsigned)kStitchSmem) {
+            for (unsigned j = lane; j < n; j += 32) s_in[warp][j] = recs[lo + j];
             __syncwarp();
-            if ((unsigned)lane < n) s_rec[warp][rank] = mine;
+            for (unsigned j = lane; j < n; j += 32) {
+                const RohRec mine = s_in[warp][j];
+                unsigned rank = 0;
+                // starts of one individual's runs are distinct; ties are broken by position anyway
+                for (unsigned k = 0; k < n; ++k) { const int ak = s_in[warp][k].a; rank += (ak < mine.a) || (ak == mine.a && k < j); }
+                s_rec[warp][rank] = mine;
+            }
             __syncwarp();
             src = s_rec[warp];
-        } else if (lane == 0) {
-            for (unsigned a = lo + 1; a < hi; ++a) {
-                const RohRec v = recs[a];
-                unsigned b = a;
-                while (b > lo && recs[b - 1].a > v.a) { recs[b] = recs[b - 1]; --b; }
-                recs[b] = v;
+        } else {
+            for (unsigned j = lane; j < n; j += 32) {
+                const RohRec mine = recs[lo + j];
+                unsigned rank = 0;
+                for (unsigned k = 0; k < n; ++k) { const int ak = recs[lo + k].a; rank += (ak < mine.a) || (ak == mine.a && k < j); }
+                scratch[lo + rank] = mine;
             }
+            __threadfence_block();
+            __syncwarp();
+            src = scratch + lo;
         }
         if (lane == 0) {
             unsigned w = lo, k = 0;
@@ -828,7 +783,7 @@ bucket_stitch_kernel(RohRec* __restrict__ recs, const unsigned* __restrict__ end
                     cur.tag = (cur.tag & ~2) | (nx.tag & 2);
                     ++k;
                 }
-                if (cur.b - cur.a + 1 >= thr) recs[w++] = cur;   // w <= lo + k: never ahead of the records still to be read
+                if (cur.b - cur.a + 1 >= thr) recs[w++] = cur;   // src is a copy: no record still to be read is overwritten
             }
             for (; w < hi; ++w) recs[w].ind = -1;
         }
@@ -836,13 +791,14 @@ bucket_stitch_kernel(RohRec* __restrict__ recs, const unsigned* __restrict__ end
     }
 }
 
-cudaError_t launch_bucket_by_individual(const RohRec* in, const unsigned* count, unsigned cap, unsigned* hist, int n_ind,
+cudaError_t launch_bucket_by_individual(RohRec* in, const unsigned* count, unsigned cap, unsigned* hist, int n_ind,
                                         RohRec* out, int thr, cudaStream_t st)
 {
     if (!n_ind) return cudaSuccess;
     bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, n_ind);
     bucket_scatter_kernel<<<148, 256, 0, st>>>(in, count, cap, hist, out);
-    bucket_stitch_kernel<<<(n_ind + 3) / 4 < 148 * 8 ? (n_ind + 3) / 4 : 148 * 8, 128, 0, st>>>(out, hist, n_ind, thr);
+    // `in` is free once scattered: the stitch kernel's scratch for buckets too large for shared memory
+    bucket_stitch_kernel<<<(n_ind + 3) / 4 < 148 * 8 ? (n_ind + 3) / 4 : 148 * 8, 128, 0, st>>>(out, in, hist, n_ind, thr);
     return cudaGetLastError();
 }
 
@@ -1229,151 +1185,12 @@ cudaError_t launch_freq_keep(const int* counts, long long L0, const int* pos, co
 }
 
 // ------------------------------------------------------------------------------------------
-// K3: column compaction of the packed matrix (filterMonomorphic[AndOOB]Sites, garlic-data.cpp:871-1195,
-// as a bit-level gather).  The keep mask is the same for every individual, so a thread that owns one OUTPUT word
-// column first turns the keep bits of its 1-3 source words into a short plan of segments
-//     out |= ((in[j] >> rs) & mask(len)) << ls          (one segment per run of kept SNPs)
-// held in registers, and then replays that plan for every row of its block's row range: per row a couple of
-// cached loads, a few shifts and one coalesced store (a CTA covers 2 KB of each row, contiguous).  Columns whose
-// plan needs more than kSegMax segments (many isolated drops) take the generic per-field path.
-// ------------------------------------------------------------------------------------------
-constexpr int kSegMax = 8;
-
-__device__ __forceinline__ uint64_t squeeze_generic(const uint64_t* __restrict__ row, long long n_in_words,
-                                                    const uint32_t* __restrict__ keepw, long long j, int skip)
-{
-    uint64_t o = 0;
-    int pos = 0;
-    while (pos < 32 && j < n_in_words) {
-        const uint32_t m = keepw[j];
-        uint64_t x = row[j];
-        uint32_t drop = ~m;
-        while (drop) {                       // highest dropped field first: lower positions stay valid
-            const int d = 31 - __clz((int)drop);
-            drop &= ~(1u << d);
-            const uint64_t low = (1ull << (2 * d)) - 1ull;
-            x = (x & low) | ((x >> 2) & ~low);
-        }
-        int c = __popc(m) - skip;
-        x >>= 2 * skip;
-        skip = 0;
-        if (c > 0) {
-            if (c < 32) x &= (1ull << (2 * c)) - 1ull;
-            o |= x << (2 * pos);
-            pos += c;
-        }
-        ++j;
-    }
-    if (pos < 32) o |= ~0ull << (2 * pos);   // fields past the last kept SNP read as missing
-    return o;
-}
-
-__global__ void __launch_bounds__(256)
-compact_geno_kernel(const uint64_t* __restrict__ gin, int64_t in_words, long long n_in_words,
-                    const uint32_t* __restrict__ keepw, const int* __restrict__ first_word,
-                    const uint8_t* __restrict__ first_skip, long long L, uint64_t* __restrict__ gout,
-                    int64_t out_words, int n_ind, int rows_per_block)
-{
-    const long long n_w = (L + 31) >> 5;
-    const long long w = (long long)blockIdx.x * 256 + threadIdx.x;
-    const int r0 = blockIdx.y * rows_per_block, r1 = min(n_ind, r0 + rows_per_block);
-    if (w >= n_w || r0 >= r1) return;
-    // ---- plan (static slots so that it stays in registers) ----
-    int sj[kSegMax], sh[kSegMax];            // source word; rs | ls << 8 | len << 16
-    int nseg = 0, pos = 0;
-    const long long j0 = first_word[w];
-    long long j = j0;
-    uint32_t m = j < n_in_words ? keepw[j] : 0u;
-    for (int skip = first_skip[w]; skip > 0; --skip) m &= m - 1;      // kept fields that belong to earlier output words
-#pragma unroll
-    for (int s = 0; s < kSegMax; ++s) {
-        sj[s] = 0; sh[s] = 0;
-        while (m == 0u && pos < 32 && j + 1 < n_in_words) m = keepw[++j];
-        if (m != 0u && pos < 32) {
-            const int a = __ffs((int)m) - 1;
-            const uint32_t inv = ~(m >> a);
-            const int run = inv ? __ffs((int)inv) - 1 : 32 - a;
-            const int len = min(run, 32 - pos);
-            sj[s] = (int)j;
-            sh[s] = (2 * a) | ((2 * pos) << 8) | (len << 16);
-            nseg = s + 1;
-            pos += len;
-            m = (run + a >= 32) ? 0u : (m & ~(((1u << run) - 1u) << a));
-        }
-    }
-    // anything left to place after kSegMax segments?
-    while (m == 0u && pos < 32 && j + 1 < n_in_words) m = keepw[++j];
-    if (m != 0u && pos < 32) nseg = kSegMax + 1;
-    const uint64_t tail = pos < 32 ? (~0ull << (2 * pos)) : 0ull;
-    if (nseg > kSegMax) {                    // rare: too fragmented for the register plan
-        const int skip0 = first_skip[w];
-        for (int r = r0; r < r1; ++r)
-            gout[(int64_t)r * out_words + w] = squeeze_generic(gin + (int64_t)r * in_words, n_in_words, keepw, j0, skip0);
-        return;
-    }
-    // ---- replay, four rows at a time (independent loads in flight) ----
-    int r = r0;
-    for (; r + 3 < r1; r += 4) {
-        const uint64_t* row = gin + (int64_t)r * in_words;
-        uint64_t o0 = tail, o1 = tail, o2 = tail, o3 = tail, x0 = 0, x1 = 0, x2 = 0, x3 = 0;
-        int lastj = -1;
-#pragma unroll
-        for (int sg = 0; sg < kSegMax; ++sg) {
-            if (sg < nseg) {
-                if (sj[sg] != lastj) {
-                    lastj = sj[sg];
-                    x0 = row[lastj]; x1 = row[in_words + lastj]; x2 = row[2 * in_words + lastj]; x3 = row[3 * in_words + lastj];
-                }
-                const int rs = sh[sg] & 0xff, ls = (sh[sg] >> 8) & 0xff, len = sh[sg] >> 16;
-                const uint64_t mk = len >= 32 ? ~0ull : ((1ull << (2 * len)) - 1ull);
-                o0 |= ((x0 >> rs) & mk) << ls; o1 |= ((x1 >> rs) & mk) << ls;
-                o2 |= ((x2 >> rs) & mk) << ls; o3 |= ((x3 >> rs) & mk) << ls;
-            }
-        }
-        uint64_t* out = gout + (int64_t)r * out_words + w;
-        out[0] = o0; out[out_words] = o1; out[2 * out_words] = o2; out[3 * out_words] = o3;
-    }
-    for (; r < r1; ++r) {
-        const uint64_t* row = gin + (int64_t)r * in_words;
-        uint64_t o = tail, x = 0;
-        int lastj = -1;
-#pragma unroll
-        for (int sg = 0; sg < kSegMax; ++sg) {
-            if (sg < nseg) {
-                if (sj[sg] != lastj) { x = row[sj[sg]]; lastj = sj[sg]; }
-                const int rs = sh[sg] & 0xff, ls = (sh[sg] >> 8) & 0xff, len = sh[sg] >> 16;
-                const uint64_t mk = len >= 32 ? ~0ull : ((1ull << (2 * len)) - 1ull);
-                o |= ((x >> rs) & mk) << ls;
-            }
-        }
-        gout[(int64_t)r * out_words + w] = o;
-    }
-}
-
-cudaError_t launch_compact_geno(const uint64_t* gin, int64_t in_words, long long n_in_words, const uint32_t* keepw,
-                                const int* first_word, const uint8_t* first_skip, long long L, uint64_t* gout,
-                                int64_t out_words, int n_ind, cudaStream_t st)
-{
-    const long long n_w = (L + 31) >> 5;
-    if (!n_w || !n_ind) return cudaSuccess;
-    const unsigned gx = (unsigned)((n_w + 255) / 256);
-    int gy = (int)((148ll * 8 + gx - 1) / gx);
-    gy = std::max(1, std::min(gy, (n_ind + 31) / 32));
-    const int rpb = (n_ind + gy - 1) / gy;
-    gy = (n_ind + rpb - 1) / rpb;
-    dim3 grid(gx, gy);
-    compact_geno_kernel<<<grid, 256, 0, st>>>(gin, in_words, n_in_words, keepw, first_word, first_skip, L, gout, out_words,
-                                              n_ind, rpb);
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------
 // Keep-mask bookkeeping on the device (the exclusive scan behind filterMonomorphic*Sites' compaction):
 // one thread per SNP, a warp = one 32-SNP input word, so the keep bits of a word are a ballot.
 //   keep_count_kernel   : kept SNPs per 1024-SNP block
 //   keep_scan_kernel    : exclusive scan of the block counts (single CTA), total → *total
-//   keep_scatter_kernel : gather list src[], keep bits per input word, per output word the input word it starts
-//                         in and the kept fields of that word already consumed, kept offset of each chromosome
+//   keep_scatter_kernel : gather list src[] (kept SNP -> source SNP; the compaction plan of squeeze.cu is made from it),
+//                         kept offset of each chromosome
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 keep_count_kernel(const uint8_t* __restrict__ keep, long long L0, int* __restrict__ block_counts)
@@ -1430,7 +1247,6 @@ keep_scan_kernel(int* __restrict__ block_counts, int n_blocks, int* __restrict__
 __global__ void __launch_bounds__(1024)
 keep_scatter_kernel(const uint8_t* __restrict__ keep, long long L0, const int* __restrict__ block_offsets,
                     const int* __restrict__ chr_of0, int n_chr, const int* __restrict__ total, int* __restrict__ src,
-                    uint32_t* __restrict__ keepw, int* __restrict__ first_word, uint8_t* __restrict__ first_skip,
                     int* __restrict__ chr_off_kept)
 {
     __shared__ int s_w[32];
@@ -1439,10 +1255,7 @@ keep_scatter_kernel(const uint8_t* __restrict__ keep, long long L0, const int* _
     const bool k = s < L0 && keep[s];
     const unsigned m = __ballot_sync(0xffffffffu, k);
     const int before = __popc(m & ((1u << lane) - 1u));
-    if (lane == 0) {
-        s_w[warp] = __popc(m);
-        if (s < L0) keepw[s >> 5] = m;
-    }
+    if (lane == 0) s_w[warp] = __popc(m);
     __syncthreads();
     if (threadIdx.x < 32) {
         const int w = s_w[threadIdx.x];
@@ -1456,24 +1269,19 @@ keep_scatter_kernel(const uint8_t* __restrict__ keep, long long L0, const int* _
     __syncthreads();
     if (s >= L0) return;
     const int d = block_offsets[blockIdx.x] + s_w[warp] + before;   // kept SNPs before s
-    if (k) {
-        src[d] = (int)s;
-        if ((d & 31) == 0) { first_word[d >> 5] = (int)(s >> 5); first_skip[d >> 5] = (uint8_t)before; }
-    }
+    if (k) src[d] = (int)s;
     if (s == 0 || chr_of0[s] != chr_of0[s - 1]) chr_off_kept[chr_of0[s]] = d;
     if (s == 0) chr_off_kept[n_chr] = *total;
 }
 
 cudaError_t launch_keep_scan(const uint8_t* keep, long long L0, const int* chr_of0, int n_chr, int* block_counts,
-                             int* total, int* src, uint32_t* keepw, int* first_word, uint8_t* first_skip,
-                             int* chr_off_kept, cudaStream_t st)
+                             int* total, int* src, int* chr_off_kept, cudaStream_t st)
 {
     if (!L0) return cudaSuccess;
     const int n_blocks = (int)((L0 + 1023) / 1024);
     keep_count_kernel<<<n_blocks, 1024, 0, st>>>(keep, L0, block_counts);
     keep_scan_kernel<<<1, 1024, 0, st>>>(block_counts, n_blocks, total);
-    keep_scatter_kernel<<<n_blocks, 1024, 0, st>>>(keep, L0, block_counts, chr_of0, n_chr, total, src, keepw, first_word,
-                                                  first_skip, chr_off_kept);
+    keep_scatter_kernel<<<n_blocks, 1024, 0, st>>>(keep, L0, block_counts, chr_of0, n_chr, total, src, chr_off_kept);
     return cudaGetLastError();
 }
 

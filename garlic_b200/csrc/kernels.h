@@ -9,6 +9,7 @@ namespace garlic {
 
 constexpr int kWalkThreads = 256;     // 8 individual groups (warps) of one item per CTA
 constexpr int kTileSnpsMax = 1536;    // table tile staged per CTA: 1536 SNPs × 32 B = 48 KB
+constexpr int kUnitThreads = 64;      // pruned pass 2: two warps = up to 64 candidate individuals per work unit
 
 // dense per-item individual lists produced by the pruning pass (list == nullptr: every individual)
 struct CandList {
@@ -20,15 +21,43 @@ struct CandList {
 // tile_snps > 0: every item touches at most tile_snps SNPs → stage its table slice in shared memory
 cudaError_t launch_walk(const WalkParams& P, const Item* items, int n_items, bool gl_mode, bool roh,
                         bool dump, int tile_snps, const CandList& cl, cudaStream_t st);
-struct CoarseParams;
-cudaError_t launch_coarse_tables(const double* lut, long long n_hw, int W, uint32_t* mask, int2* cb, cudaStream_t st);
-cudaError_t launch_coarse(const CoarseParams& P, const Item* items, int n_items, int* cand_list, unsigned* cand_cnt,
-                          int cand_stride, cudaStream_t st);
+// the walker over the queue of (item, 64 candidates) work units left by the bound (squeeze.cu)
+cudaError_t launch_walk_units(const WalkParams& P, const Item* items, const int2* units, const unsigned* n_units,
+                              unsigned unit_cap, int tile_snps, const CandList& cl, cudaStream_t st);
+
+// K3 + pruning bound, fused (squeeze.cu, bound.cuh)
+struct SqueezeParams {
+    const uint64_t* gin;       // rows to read: the uncompacted matrix (squeeze) or the compacted one (bound only)
+    int64_t in_words;
+    uint64_t* gout;            // compacted rows (squeeze)
+    int64_t out_words;
+    const uint4* plan_head;    // compaction plan per output half-word (bound.cuh:plan_half)
+    const uint4* plan_seg;
+    const int4* piece_rng;     // per piece: first / last input half-word it reads, bit mask of slow-path half-words
+    const int* src;            // gather list (kept SNP -> source SNP)
+    const int* n_kept;         // device-resident number of kept SNPs
+    int n_ind;
+    const uint4* hw;           // bound tables per half-word (bound.cuh:bound_hw_entry)
+    const int2* bc;            // per half-word q: {Bmax of block q - C2, chet of half-word q}
+    int lag;                   // C2 - c1: 1 or 2
+    uint32_t* pmax;            // [n_pieces][pmax_stride]: piece maxima per individual (bound.cuh:bound_pack)
+    int64_t pmax_stride;
+    int n_pieces, pieces_per_task, n_col_tasks;
+};
+cudaError_t launch_bound_tables(const double* lut, long long n_hw, long long L, int W, uint4* hw, int2* bc, int* invalid,
+                                cudaStream_t st);
+cudaError_t launch_plan(const int* src, const int* n_kept, long long n_q, uint4* head, uint4* segs, int4* piece_rng,
+                        cudaStream_t st);
+// c2 > 0: with the bound for that window size class; squeeze = false: bound only, over compacted rows
+cudaError_t launch_squeeze_bound(SqueezeParams P, bool squeeze, int c2, cudaStream_t st);
+cudaError_t launch_select(const Item* items, int n_items, const uint32_t* pmax, int64_t stride, int n_ind, int cut_store,
+                          const int* invalid, int* cand_list, int cand_stride, unsigned* cand_cnt, int2* units, unsigned* n_units,
+                          unsigned unit_cap, int lanes_per_unit, cudaStream_t st);
 cudaError_t launch_thin_windows(const uint64_t* geno, int64_t row_words, const double* lut, const int* ind_list, int n_lanes,
                                 const int3* segs, int n_segs, const int2* meta, int n_chr, long long n_slots, int step, int W,
                                 double* dump, int64_t dump_stride, const double* gl, int64_t gl_stride, cudaStream_t st);
 cudaError_t launch_fill_f64(double* p, size_t n, double v, cudaStream_t st);
-cudaError_t launch_bucket_by_individual(const RohRec* in, const unsigned* count, unsigned cap, unsigned* hist, int n_ind,
+cudaError_t launch_bucket_by_individual(RohRec* in, const unsigned* count, unsigned cap, unsigned* hist, int n_ind,
                                         RohRec* out, int thr, cudaStream_t st);
 cudaError_t launch_tokenize_tped(const char* text, const long long* off, int n_snp, int n_ind, int ind_lo, uint8_t* alleles,
                                  int* nonblank, cudaStream_t st);
@@ -41,12 +70,8 @@ cudaError_t launch_count_packed(const uint64_t* geno, int64_t row_words, int n_i
                                 int* counts, cudaStream_t st);
 cudaError_t launch_freq_keep(const int* counts, long long L0, const int* pos, const int* chr_of,
                              const int* chr_param, int oob, double* freq, uint8_t* keep, cudaStream_t st);
-cudaError_t launch_compact_geno(const uint64_t* gin, int64_t in_words, long long n_in_words, const uint32_t* keepw,
-                                const int* first_word, const uint8_t* first_skip, long long L, uint64_t* gout,
-                                int64_t out_words, int n_ind, cudaStream_t st);
 cudaError_t launch_keep_scan(const uint8_t* keep, long long L0, const int* chr_of0, int n_chr, int* block_counts,
-                             int* total, int* src, uint32_t* keepw, int* first_word, uint8_t* first_skip,
-                             int* chr_off_kept, cudaStream_t st);
+                             int* total, int* src, int* chr_off_kept, cudaStream_t st);
 cudaError_t launch_bad_pairs(const int* pos, const int* chr_of, const int* cen, int max_gap, long long L, int* list,
                              unsigned* count, unsigned cap, cudaStream_t st);
 cudaError_t launch_gather_i32(const int* in, const int* src, long long L, int* out, cudaStream_t st);

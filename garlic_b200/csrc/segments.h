@@ -117,6 +117,37 @@ inline void build_items(const std::vector<int64_t>& chr_off, int W, const std::v
     }
 }
 
+// Items aligned to the pruning pieces (bound.cuh): a segment's SNP stretch is cut at the multiples of `piece` that lie
+// inside it, except those closer than piece/4 to either end (no sliver items).
+inline void build_items_aligned(const std::vector<int64_t>& chr_off, int W, const std::vector<Segment>& segs, int piece,
+                                std::vector<Item>& items)
+{
+    items.clear();
+    std::vector<int> cuts;
+    for (size_t si = 0; si < segs.size(); ++si) {
+        const Segment& s = segs[si];
+        const int a = s.ws, b = s.we + W - 1;
+        cuts.clear();
+        cuts.push_back(a);
+        for (int c = (a / piece + 1) * piece; c < b; c += piece)
+            if (c - a >= piece / 4 && b - c >= piece / 4) cuts.push_back(c);
+        cuts.push_back(b);
+        const int n = (int)cuts.size() - 1;
+        for (int i = 0; i < n; ++i) {
+            Item it;
+            it.own_lo = cuts[i];
+            it.own_hi = cuts[i + 1];
+            it.w0 = std::max(a, it.own_lo - W + 1);
+            it.we = s.we;
+            it.seg = (int)si;
+            it.flags = (i > 0 ? 1 : 0) | (i + 1 < n ? 2 : 0);
+            it.chr_start = (int)chr_off[s.chr];
+            it.thin_base = 0;
+            items.push_back(it);
+        }
+    }
+}
+
 // buffers of stitch_runs kept between calls (a fresh 400 KB vector per call costs more than the sort)
 struct StitchScratch {
     std::vector<uint32_t> first, cur;

@@ -493,7 +493,7 @@ int main(int argc, char** argv)
     auto shutdown = [&]() { team.all([](Rank& R) { garlic_gpu_destroy(R.g); R.g = nullptr; return true; }); team.stop(); };
     if (o.freq_only) { shutdown(); return 0; }   // freqOnly (garlic-data.cpp:238-315): the .freq.gz is the output
     std::vector<int32_t> src(c.L);
-    garlic_gpu_get_kept_index(c.g, src.data());
+    if (!gpu_ok(c, garlic_gpu_get_kept_index(c.g, src.data()), "get_kept_index")) return fail(1);
     c.pos.resize(c.L);
     c.chr_off.assign(C + 1, 0);
     {

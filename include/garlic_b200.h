@@ -167,10 +167,16 @@ int garlic_gpu_windows_gather(garlic_gpu_t *h, int winsize, int step, int weight
 int garlic_gpu_call_roh(garlic_gpu_t *h, int winsize, double cutoff, double overlap_frac, int weighted,
                         int exact, garlic_roh_t *out, int64_t cap, int64_t *count);
 /* statistics of the last call_roh, 8 doubles: [0] items, [1] individual-windows decided (N·Σ_c(L_c-W+1)),
- * [2] ambiguous (individual, segment) pairs re-evaluated exactly, [3] kernel milliseconds (pruning pass +
- * walker), [4] of which pruning pass, [5] (individual, item) pairs that went to the walker (-1: no pruning),
- * [6] all (individual, item) pairs, [7] reserved */
+ * [2] ambiguous (individual, segment) pairs re-evaluated exactly, [3] kernel milliseconds of pass 2 (candidate
+ * selection + walker), [4] of which selection, [5] (individual, item) pairs that went to the walker (-1: no
+ * pruning), [6] all (individual, item) pairs, [7] milliseconds of the last compaction (K3) launch — fused with the
+ * pruning bound when the first consumer of the compacted rows was an unweighted table-mode pass */
 int garlic_gpu_last_stats(garlic_gpu_t *h, double *stats8);
+/* the pruning bound of pass 2 (a sufficient test that an individual has NO window >= cutoff in a 256-SNP piece,
+ * evaluated from the packed genotypes alone): out [n_pieces][n_ind], per entry two int16 — low = maximum over the
+ * piece's 16-SNP blocks of window starts, high = over its last (winsize+14)/16 blocks — in units of 1/64 LOD,
+ * rounded up; *n_pieces = ceil(L/256).  Unweighted table mode, 32 <= winsize <= 209.  Introspection / parity tests. */
+int garlic_gpu_get_piece_bounds(garlic_gpu_t *h, int winsize, uint32_t *out, int64_t cap_entries, int64_t *n_pieces);
 
 /* packed 2-bit genotype rows back to the host (parity checks; --phased / debugging): filtered = 0 →
  * the matrix as ingested [n_ind][ceil(n_loci/4)], 1 → after compaction [n_ind][ceil(L/4)];

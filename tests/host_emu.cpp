@@ -8,7 +8,7 @@
 #include "../garlic_b200/csrc/common.cuh"
 #include "../garlic_b200/csrc/walk.cuh"
 #include "../garlic_b200/csrc/segments.h"
-#include "../garlic_b200/csrc/coarse.cuh"
+#include "../garlic_b200/csrc/bound.cuh"
 #include <cmath>
 
 using namespace garlic;
@@ -95,13 +95,65 @@ int emu_windows(const uint64_t* geno, int64_t row_words, const double* lut, cons
         }
     return (int)items.size();
 }
+}  // extern "C"
 
+// ---------------------------------------------------------------------------------------------------------------
+// pruning bound (bound.cuh) on the CPU: the same table construction, per-half-word step and candidate predicate the
+// kernels of squeeze.cu run.  pmax[n_pieces][n_ind] as the fused kernel stores it.
+// ---------------------------------------------------------------------------------------------------------------
+template <int C2, int LAG>
+static void emu_bound_row(const uint32_t* hw_row, long long n_hw, const std::vector<uint4>& hw, const std::vector<int2>& bc,
+                          int n_pieces, uint32_t* pmax, int64_t stride, int ind)
+{
+    BoundState S;
+    bound_reset(S);
+    for (int pi = 0; pi <= n_pieces; ++pi) {
+        for (int I = 0; I < 16; ++I) {
+            const long long q = (long long)pi * 16 + I;
+            const uint32_t h = q < n_hw ? hw_row[q] : 0xffffffffu;
+            bound_step<C2, LAG>(S, h, hw[q], bc[q], I);
+            if (((I - C2) & 15) == 15) {
+                const long long piece = (q - C2) >> 4;
+                if (piece >= 0 && piece < n_pieces) pmax[piece * stride + ind] = bound_pack(S.pm_all, S.pm_tail);
+                S.pm_all = -0x40000000; S.pm_tail = -0x40000000;
+            }
+        }
+    }
+}
 
-// pruning pass (coarse.cuh) on the CPU: out[n_items][n_ind] = candidate flag; items as the chunked fast pass
-// builds them.  The table construction restates coarse_tables_kernel (kernels.cu).
-int emu_coarse(const uint64_t* geno, int64_t row_words, const double* lut, int n_ind, int n_chr, const int64_t* chr_off_,
-               const int32_t* pos_, const int32_t* cen_, int max_gap, int W, double cutoff, double tol, double error,
-               int chunk, uint8_t* out, int32_t* item_bounds /* [n_items][3] = w0, own_hi, we */, int cap_items)
+extern "C" {
+
+// returns 0, or 1 if the table breaks the bound's assumptions
+int emu_bound(const uint64_t* geno, int64_t row_words, const double* lut, long long L, int n_ind, int W, uint32_t* pmax,
+              int n_pieces)
+{
+    const int c2 = bound_c2(W), lag = bound_lag(W);
+    if (W < kBoundMinW || (lag != 1 && lag != 2)) return -1;
+    const long long n_hw = 16ll * (n_pieces + 2);
+    std::vector<uint4> hw(n_hw);
+    std::vector<int2> bc(n_hw);
+    int invalid = 0;
+    for (long long k = 0; k < n_hw; ++k) {
+        hw[k] = bound_hw_entry(lut, k, L, &bc[k].y, &invalid);
+        bc[k].x = k >= c2 ? bound_block_max(lut, k - c2, W) : 0;
+    }
+    for (int i = 0; i < n_ind; ++i) {
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(geno + (int64_t)i * row_words);
+        const long long row_hw = row_words * 2;
+        switch (c2) {
+#define CASE(C) case C: if (lag == 1) emu_bound_row<C, 1>(row, row_hw, hw, bc, n_pieces, pmax, n_ind, i); \
+                        else emu_bound_row<C, 2>(row, row_hw, hw, bc, n_pieces, pmax, n_ind, i); break;
+            CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+#undef CASE
+            default: return -1;
+        }
+    }
+    return invalid;
+}
+
+// piece-aligned items and their candidate flags: out[n_items][n_ind]; item_bounds[n_items][3] = w0, own_hi, we
+int emu_select(const uint32_t* pmax, int n_ind, int n_chr, const int64_t* chr_off_, const int32_t* pos_, const int32_t* cen_,
+               int max_gap, int W, double cutoff, double tol, int item_pieces, uint8_t* out, int32_t* item_bounds, int cap_items)
 {
     std::vector<int64_t> chr_off(chr_off_, chr_off_ + n_chr + 1);
     const int64_t L = chr_off[n_chr];
@@ -109,52 +161,38 @@ int emu_coarse(const uint64_t* geno, int64_t row_words, const double* lut, int n
     std::vector<Segment> segs;
     std::vector<Item> items;
     build_segments(chr_off, pos, cen, max_gap, W, segs);
-    build_items(chr_off, W, segs, chunk, 0, items);
+    build_items_aligned(chr_off, W, segs, kPiece * item_pieces, items);
     if ((int)items.size() > cap_items) return -1;
-    const int c1 = (W - 16) >> 4, c2 = (W + 14) >> 4;
-    const int64_t n_hw = (L + 4160 - 512) >> 4;
-    const double scale = (double)(1 << kCoarseShift);
-    std::vector<uint32_t> mask(n_hw);
-    std::vector<int2> cbv(n_hw + 16);
-    for (int i = 0; i < 16; ++i) { cbv[i].x = 0; cbv[i].y = 0; }
-    for (int64_t k = 0; k < n_hw; ++k) {
-        const int64_t s0 = k * 16;
-        double b = 0.0;
-        for (int i = 0; i < W; ++i) { const double* e = lut + (s0 + i) * 4; b += std::fmin(e[0], e[2]); }
-        double bmax = b;
-        for (int j = 1; j < 16; ++j) {
-            const double* eo = lut + (s0 + j - 1) * 4;
-            const double* ei = lut + (s0 + j - 1 + W) * 4;
-            b = b - std::fmin(eo[0], eo[2]) + std::fmin(ei[0], ei[2]);
-            bmax = std::fmax(bmax, b);
-        }
-        double dlo = 0.0, dhi = 0.0;
-        for (int64_t s = s0; s < s0 + 16 * (c2 + 1); ++s) {
-            const double* e = lut + s * 4;
-            const double d = std::fabs(e[0] - e[2]);
-            if (d > kCoarseSplit) dhi = std::fmax(dhi, d); else dlo = std::fmax(dlo, d);
-        }
-        uint32_t m = 0;
-        for (int j = 0; j < 16; ++j) {
-            const double* e = lut + (s0 + j) * 4;
-            if (e[2] > e[0]) m |= 1u << (2 * j);
-            if (std::fabs(e[0] - e[2]) > kCoarseSplit) m |= 2u << (2 * j);
-        }
-        const double qlo = std::fmin(std::ceil(dlo * scale) + 1.0, 65535.0), qhi = std::fmin(std::ceil(dhi * scale) + 1.0, 65535.0);
-        mask[k] = m;
-        cbv[16 + k].x = (int)std::ceil(bmax * scale) + 2;
-        cbv[16 + k].y = (int)((uint32_t)qlo | ((uint32_t)qhi << 16));
-    }
-    CoarseParams P;
-    P.geno = geno; P.row_words = row_words; P.mask = mask.data(); P.cb = cbv.data() + 16;
-    P.W = W; P.c1 = c1; P.c2 = c2; P.n_lanes = n_ind;
-    P.chet_fixed = (int)std::ceil((std::log10(error) + 1e-9) * scale);
-    P.cut_fixed = (int)std::floor((cutoff - tol) * scale - 2.0);
+    int ok = 0;
+    const int cut = bound_cut_store(cutoff, tol, &ok);
+    if (!ok) return -2;
     for (size_t i = 0; i < items.size(); ++i) {
         item_bounds[3 * i] = items[i].w0; item_bounds[3 * i + 1] = items[i].own_hi; item_bounds[3 * i + 2] = items[i].we;
-        for (int k = 0; k < n_ind; ++k) out[i * n_ind + k] = coarse_item_any(P, items[i], k) ? 1 : 0;
+        for (int k = 0; k < n_ind; ++k) out[i * n_ind + k] = bound_item_candidate(pmax, n_ind, k, items[i], cut) ? 1 : 0;
     }
     return (int)items.size();
+}
+
+// K3 by plan (bound.cuh:plan_half): rows_in [n_ind][in_words] → rows_out [n_ind][out_words] (pre-filled by the caller)
+void emu_squeeze(const uint64_t* rows_in, int64_t in_words, const int32_t* src, long long L, int n_ind, uint64_t* rows_out,
+                 int64_t out_words)
+{
+    const long long n_q = (L + 15) / 16;
+    uint4 head, segs[kPlanSegMax];
+    for (long long q = 0; q < n_q; ++q) {
+        plan_half(src, L, q, &head, segs);
+        for (int i = 0; i < n_ind; ++i) {
+            const uint32_t* hin = reinterpret_cast<const uint32_t*>(rows_in + (int64_t)i * in_words);
+            uint32_t h;
+            if (head.x & 0x100u) {
+                h = plan_window(head, hin[head.y], plan_need1(head) ? hin[head.y + 1] : 0u, plan_need2(head) ? hin[head.y + 2] : 0u);
+            } else {
+                h = head.w;
+                for (uint32_t s = 0; s < head.x; ++s) h |= ((hin[segs[s].x] >> segs[s].y) & segs[s].z) << segs[s].w;
+            }
+            reinterpret_cast<uint32_t*>(rows_out + (int64_t)i * out_words)[q] = h;
+        }
+    }
 }
 
 }

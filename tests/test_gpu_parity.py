@@ -293,6 +293,89 @@ def test_repeated_runs_are_identical_and_equal_exact_chains():
     hp.close()
 
 
+def _emu_bounds(codes_kept, lut, L, W):
+    """bound.cuh on the CPU (tests/host_emu.cpp): the piece maxima the fused kernel must reproduce bit for bit."""
+    import ctypes as C
+    from tests.test_host_emu import emu, _p
+    N = codes_kept.shape[0]
+    row_words = (((L + 4160 + 31) >> 5) + 3) & ~1
+    rows = synth.pack_codes(codes_kept, row_bytes=row_words * 8).view(np.uint64).reshape(N, row_words)
+    lut_pad = np.zeros((L + 4160, 4))
+    lut_pad[:L] = lut
+    n_pieces = (L + 255) // 256
+    pmax = np.zeros((n_pieces, N), np.uint32)
+    rc = emu().emu_bound(_p(rows), C.c_int64(row_words), _p(lut_pad), C.c_longlong(L), C.c_int(N), C.c_int(W), _p(pmax),
+                         C.c_int(n_pieces))
+    assert rc == 0
+    return pmax
+
+
+@pytest.mark.parametrize("n_ind,L0,W,W2", [(300, 80000, 50, 100), (77, 30011, 32, 209), (513, 20000, 64, 33)])
+def test_fused_compaction_and_bound_equal_host_emulation(n_ind, L0, W, W2):
+    """squeeze.cu: the compacted matrix equals the column gather, and the piece maxima written by the fused pass
+    (window size W, first consumer = thinned windows) and by the bound-only pass (W2, same data) equal the CPU
+    emulation of bound.cuh bit for bit; ragged individual counts and SNP counts included."""
+    names, offs, pos, cens = synth.make_positions_genomewide(11, L0)
+    codes = synth.make_codes(11, n_ind, L0)
+    hp = HotPath()
+    g = hp.g
+    g.set_shape(n_ind, L0, offs, pos)
+    g.put_packed(synth.pack_codes(codes))
+    g.count_packed()
+    freq, keep, L = g.filter()
+    keep = keep.copy()
+    g.set_tables(0.001, 200000, np.array([cens["chr" + n] for n in names], np.int32))
+    g.windows(W, W, individuals=np.arange(0, n_ind, 37, dtype=np.int32), exact=False)    # compaction + bound(W), fused
+    st = g.last_stats()
+    assert st["squeeze_ms"] > 0
+    packed = g.get_genotypes(True)
+    assert np.array_equal(synth.unpack_codes(packed, L), codes[:, keep])
+    lut = g.get_lut()
+    want = _emu_bounds(codes[:, keep], lut, L, W)
+    assert np.array_equal(g.piece_bounds(W), want)
+    want2 = _emu_bounds(codes[:, keep], lut, L, W2)
+    assert np.array_equal(g.piece_bounds(W2), want2)                                     # bound only, compacted rows
+    hp.close()
+
+
+@pytest.mark.parametrize("W,cutoff", [(50, 2.0), (32, 0.5), (100, 5.0), (209, 20.0), (60, -3.0)])
+def test_pruned_pass_equals_exact_chains_and_unpruned_pass(W, cutoff):
+    """Pass 2 over the candidates the bound leaves == whole-segment exact chains == the pass without pruning, for
+    several window-size classes and cutoffs (a negative cutoff makes nearly every pair a candidate)."""
+    import os
+    names, offs, pos, cens = synth.make_positions_genomewide(4, 70000)
+    codes = synth.make_codes(4, 330, 70000)
+    rows = synth.pack_codes(codes)
+    cen = np.array([cens["chr" + n] for n in names], np.int32)
+    outs = {}
+    for mode in ("pruned", "unpruned"):
+        if mode == "unpruned":
+            os.environ["GARLIC_NO_PRUNE"] = "1"
+        try:
+            hp = HotPath()
+        finally:
+            os.environ.pop("GARLIC_NO_PRUNE", None)
+        g = hp.g
+        g.set_shape(330, 70000, offs, pos)
+        g.put_packed(rows)
+        g.count_packed()
+        g.filter()
+        g.set_tables(0.001, 200000, cen)
+        outs[mode] = g.call_roh(W, cutoff, 0.25).copy()
+        st = g.last_stats()
+        if mode == "pruned":
+            assert 0 <= st["candidate_pairs"] <= st["all_pairs"]
+            if cutoff >= 2.0:
+                assert st["candidate_pairs"] < 0.5 * st["all_pairs"]
+            outs["exact"] = g.call_roh(W, cutoff, 0.25, exact=True).copy()
+        else:
+            assert st["candidate_pairs"] < 0
+        hp.close()
+    assert len(outs["exact"]) > 50
+    assert np.array_equal(outs["pruned"], outs["exact"])
+    assert np.array_equal(outs["unpruned"], outs["exact"])
+
+
 def _weighted_handle(n_ind, L0, seed, gl=False):
     names, offs, pos, cens = synth.make_positions_genomewide(seed, L0, n_chr=3)
     codes = synth.make_codes(seed, n_ind, L0)

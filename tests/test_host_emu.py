@@ -22,7 +22,7 @@ def emu():
     if _EMU is None:
         so = os.path.join(HERE, "_hostemu.so")
         srcs = [os.path.join(HERE, "host_emu.cpp")] + [os.path.join(ROOT, "garlic_b200", "csrc", f)
-                                                       for f in ("walk.cuh", "segments.h", "common.cuh")]
+                                                       for f in ("walk.cuh", "segments.h", "common.cuh", "bound.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC",
                                    "-o", so, srcs[0]])
@@ -144,10 +144,19 @@ def test_ambiguity_detection_and_cutoff_on_window_value():
     assert got_exact == oracle_roh_idx(res)
 
 
-@pytest.mark.parametrize("name,chunk", [("lod_2", 256), ("lod_small", 128), ("auto_overlap_hg19", 320), ("lod_2", 1376)])
-def test_pruning_bound_never_drops_a_flagged_window(name, chunk):
-    """coarse.cuh: every (individual, item) pair that holds a window >= cutoff - tol must survive the pruning
-    pass; and the pass must actually prune something on data with planted ROH."""
+def emu_piece_bounds(F, W):
+    n_pieces = (F["L"] + 255) // 256
+    pmax = np.zeros((n_pieces, F["N"]), np.uint32)
+    rc = emu().emu_bound(_p(F["rows"]), C.c_int64(F["row_words"]), _p(F["lut"]), C.c_longlong(F["L"]), C.c_int(F["N"]),
+                         C.c_int(W), _p(pmax), C.c_int(n_pieces))
+    assert rc == 0
+    return pmax
+
+
+@pytest.mark.parametrize("name,item_pieces", [("lod_2", 1), ("lod_small", 1), ("auto_overlap_hg19", 2), ("lod_2", 4)])
+def test_pruning_bound_never_drops_a_flagged_window(name, item_pieces):
+    """bound.cuh: every (individual, item) pair that holds a window >= cutoff - tol must survive the pruning
+    bound; and the bound must actually prune something on data with planted ROH."""
     ds, args = load_case(name)
     W = arg(args, "--winsize", cast=int)
     err = arg(args, "--error", cast=float)
@@ -156,14 +165,14 @@ def test_pruning_bound_never_drops_a_flagged_window(name, chunk):
     F = flatten(res, err)
     win = oracle_windows_matrix(res)
     vals = np.sort(win[win != orc.MISSING])
+    pmax = emu_piece_bounds(F, W)
     for cutoff in (float(vals[int(0.9 * len(vals))]), float(vals[int(0.5 * len(vals))]), 2.0, float(vals[-1])):
-        cap = 4096
+        cap = 8192
         out = np.zeros((cap, F["N"]), np.uint8)
         bounds = np.zeros((cap, 3), np.int32)
-        n = emu().emu_coarse(_p(F["rows"]), C.c_int64(F["row_words"]), _p(F["lut"]), C.c_int(F["N"]),
-                             C.c_int(len(F["chr_off"]) - 1), _p(F["chr_off"]), _p(F["pos"]), _p(F["cen"]), C.c_int(200000),
-                             C.c_int(W), C.c_double(cutoff), C.c_double(1e-9), C.c_double(err), C.c_int(chunk), _p(out),
-                             _p(bounds), C.c_int(cap))
+        n = emu().emu_select(_p(pmax), C.c_int(F["N"]), C.c_int(len(F["chr_off"]) - 1), _p(F["chr_off"]), _p(F["pos"]),
+                             _p(F["cen"]), C.c_int(200000), C.c_int(W), C.c_double(cutoff), C.c_double(1e-9),
+                             C.c_int(item_pieces), _p(out), _p(bounds), C.c_int(cap))
         assert n > 0
         dropped_flagged = 0
         for i in range(n):
@@ -175,3 +184,55 @@ def test_pruning_bound_never_drops_a_flagged_window(name, chunk):
         assert dropped_flagged == 0
         if cutoff == float(vals[-1]):
             assert out[:n].mean() < 0.9      # something is pruned when almost nothing passes the cutoff
+
+
+@pytest.mark.parametrize("W", [32, 33, 49, 50, 64, 100, 177, 208, 209])
+def test_pruning_bound_dominates_every_window_of_its_block(W):
+    """The stored piece maximum is an upper bound (fixed point, >> 2 rounded up) of every window starting in the piece,
+    for every window-size class the kernel is instantiated for; the tail maximum covers the piece's last C2 blocks."""
+    ds, args = load_case("lod_small")
+    err = 0.001
+    res = orc.run_pipeline(ds, W, err, None)
+    F = flatten(res, err)
+    lut, codes, L, N = F["lut"], F["codes"], F["L"], F["N"]
+    val = np.take_along_axis(np.broadcast_to(lut[None, :L], (N, L, 4)), codes[:, :, None].astype(np.int64), 2)[:, :, 0]
+    cs = np.concatenate([np.zeros((N, 1)), np.cumsum(val, 1)], 1)
+    win = cs[:, W:] - cs[:, :-W]                      # every window start, chromosome borders ignored (a superset)
+    pmax = emu_piece_bounds(F, W)
+    all_ = (pmax & 0xffff).astype(np.uint16).view(np.int16).astype(np.int64) * 4 / 256.0
+    tail = (pmax >> 16).astype(np.uint16).view(np.int16).astype(np.int64) * 4 / 256.0
+    c2 = (W + 14) >> 4
+    for p in range(pmax.shape[0]):
+        lo, hi = 256 * p, min(256 * (p + 1), win.shape[1])
+        if lo >= hi:
+            continue
+        assert np.all(win[:, lo:hi].max(1) <= all_[p] + 1e-9), (W, p)
+        tl = 256 * (p + 1) - 16 * c2
+        if tl < hi:
+            assert np.all(win[:, max(lo, tl):hi].max(1) <= tail[p] + 1e-9), (W, p)
+
+
+def test_compaction_plan_equals_column_gather():
+    """bound.cuh:plan_half (K3 as funnel shifts / masked segments of 16-SNP half-words) == dropping the columns."""
+    rng = np.random.default_rng(5)
+    N, L0 = 37, 5000
+    codes = rng.integers(0, 4, (N, L0)).astype(np.uint8)
+    for drop in (0.0, 0.02, 0.5, 0.97):
+        keep = rng.random(L0) >= drop
+        keep[100:400] = drop < 0.9            # a long kept run and, with heavy dropping, a long dropped one
+        keep[1000:1700] = False
+        src = np.flatnonzero(keep).astype(np.int32)
+        L = len(src)
+        in_words = (((L0 + 4160 + 31) >> 5) + 3) & ~1
+        rows_in = synth_pack(codes, in_words)
+        out_words = (((L + 4160 + 31) >> 5) + 3) & ~1
+        rows_out = np.full((N, out_words), 0xFFFFFFFFFFFFFFFF, np.uint64)
+        emu().emu_squeeze(_p(rows_in), C.c_int64(in_words), _p(src), C.c_longlong(L), C.c_int(N), _p(rows_out),
+                          C.c_int64(out_words))
+        want = synth_pack(codes[:, keep], out_words)
+        assert np.array_equal(rows_out, want), drop
+
+
+def synth_pack(codes, row_words):
+    from garlic_b200 import synth
+    return synth.pack_codes(codes, row_bytes=row_words * 8).view(np.uint64).reshape(codes.shape[0], row_words)
