@@ -44,9 +44,12 @@ GHD int bound_c2(int W) { return (W + 14) >> 4; }
 GHD int bound_c1(int W) { const int c = (W - 16) >> 4; return c > 0 ? c : 0; }
 GHD int bound_lag(int W) { return bound_c2(W) - bound_c1(W); }   // 1 or 2 for W >= kBoundMinW
 
-// per half-word table entry: x = orientation (bit 2i set <=> genotype 2 is the "rare" homozygote at SNP 16q+i),
-// y = plane p0, z = plane p1 (even bits), w = step; *chet_fx = chet — both fixed point, rounded towards a larger bound
-GHD uint4 bound_hw_entry(const double* lut, long long q, long long L, int* chet_fx, int* invalid)
+// Per half-word table entry, one 16-byte load per step:
+//   x = orientation (even bits: bit 2i set <=> genotype 2 is the "rare" homozygote at SNP 16q+i) | plane p0 << 1 (odd bits)
+//   y = plane p1 (even bits)
+//   z = step (low 16 bits) | -chet (high 16 bits), fixed point, rounded towards a larger bound
+//   w = filled in by the caller: Bmax of block q - C2 (what the step at half-word q evaluates)
+GHD uint4 bound_hw_entry(const double* lut, long long q, long long L, int* invalid)
 {
     const double scale = (double)(1 << kBoundShift);
     double D[16], dmax = 0.0, chet = -1e300;
@@ -82,8 +85,7 @@ GHD uint4 bound_hw_entry(const double* lut, long long q, long long L, int* chet_
     uint32_t ch = 0u;                                 // magnitude, rounded towards zero (a less negative coefficient)
     if (chet > -1e299 && chet < 0.0) { const double m = floor(-chet * scale); ch = m > 65535.0 ? 0xffffu : (uint32_t)m; }
     uint4 o;
-    o.x = mo; o.y = p0; o.z = p1; o.w = step;
-    *chet_fx = -(int)ch;
+    o.x = mo | (p0 << 1); o.y = p1; o.z = step | (ch << 16); o.w = 0u;
     return o;
 }
 
@@ -123,20 +125,20 @@ GHD void bound_reset(BoundState& S)
 }
 
 // One half-word h (16 genotypes) at ring position I = q & 15 (a constant after unrolling: the ring stays in registers);
-// evaluates block k = q - C2 with Bmax bm.
-// bc = {Bmax of block q - C2, chet of half-word q}.  LAG = C2 - c1: 1 or 2 (window sizes >= 32: the core is not empty).
+// evaluates block k = q - C2, whose Bmax is t.w.  LAG = C2 - c1: 1 or 2 (window sizes >= 32: the core is not empty).
+// PH accumulates the magnitude of the (negative) het term.
 template <int C2, int LAG>
-GHD void bound_step(BoundState& S, uint32_t h, const uint4& t, const int2& bc, const int I)
+GHD void bound_step(BoundState& S, uint32_t h, const uint4& t, const int I)
 {
     const uint32_t M = 0x55555555u;
     const uint32_t s = h >> 1;
     const uint32_t het = h & ~s & M;                   // g == 1
     const uint32_t x = ~h & ~(s ^ t.x);                // even bits: homozygous with the "rare" orientation
-    const int n0 = popc32(x & t.y), n1 = popc32(x & t.z), nh = popc32(het);
-    S.pr += (uint32_t)(n0 + 2 * n1) * t.w;
-    S.ph += (uint32_t)nh * (uint32_t)bc.y;
+    const int n0 = popc32(x & (t.x >> 1) & M), n1 = popc32(x & t.y), nh = popc32(het);
+    S.pr += (uint32_t)(n0 + 2 * n1) * (t.z & 0xffffu);
+    S.ph += (uint32_t)nh * (t.z >> 16);
     S.PR[I] = S.pr; S.PH[I] = S.ph;
-    const int ub = bc.x + (int)(S.pr - S.PR[(I - C2 - 1) & 15]) + (int)(S.PH[(I - LAG) & 15] - S.PH[(I - C2) & 15]);
+    const int ub = (int)t.w + (int)(S.pr - S.PR[(I - C2 - 1) & 15]) + (int)(S.PH[(I - C2) & 15] - S.PH[(I - LAG) & 15]);
     S.pm_all = ub > S.pm_all ? ub : S.pm_all;
     if (((I - C2) & 15) >= 16 - C2) S.pm_tail = ub > S.pm_tail ? ub : S.pm_tail;   // compile-time condition
 }
@@ -221,8 +223,28 @@ GHD void plan_half(const int* src, long long L, long long q, uint4* head, uint4*
 }
 
 // the window form: x0, x1, x2 = input half-words y, y+1, y+2 (x1 / x2 only read when plan_need1 / plan_need2)
-// does the kernel's branch-free path (window form, at most one deletion) get half-word hd right?
-GHD bool plan_is_fast(const uint4& hd) { return (hd.x & 0x100u) && ((hd.x >> 4) & 15u) <= 1u; }
+// The kernel's branch-free path: the piece's input window sits in 20 registers (half-words a_base … a_base + 19,
+// a_base even = the piece's first source half-word rounded down); output half-word I of the piece takes the 64-bit window at
+// register I + k shifted right by sh bits, and the fields from p on move down by one (p = 16: no deletion).
+// Two bytes per half-word: k | sh << 2, then 2 p.  0xffff: not expressible (several deletions, general form, a window
+// further than two half-words ahead after many dropped SNPs) — the half-word takes the slow path.
+GHD uint32_t plan_fast_code(const uint4& hd, int a_base, int I)
+{
+    if (!(hd.x & 0x100u) || ((hd.x >> 4) & 15u) > 1u) return 0xffffu;
+    const int rel = 32 * ((int)hd.y - a_base - I) + (int)(hd.z & 255u);
+    if (rel < 0 || rel >= 96) return 0xffffu;
+    const uint32_t p = ((hd.x >> 4) & 15u) ? ((hd.z >> 8) & 255u) : 16u;
+    return (uint32_t)(rel >> 5) | ((uint32_t)(rel & 31) << 2) | ((2u * p) << 8);
+}
+// r[0..4] = window registers I .. I + 4
+GHD uint32_t plan_fast_apply(uint32_t code, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4)
+{
+    const uint32_t k = code & 3u, sh = (code >> 2) & 31u, p2 = (code >> 8) & 255u;
+    const uint32_t x0 = k == 0u ? r0 : (k == 1u ? r1 : r2), x1 = k == 0u ? r1 : (k == 1u ? r2 : r3), x2 = k == 0u ? r2 : (k == 1u ? r3 : r4);
+    const uint32_t lo = sh ? ((x0 >> sh) | (x1 << (32u - sh))) : x0, hi = sh ? ((x1 >> sh) | (x2 << (32u - sh))) : x1;
+    const uint32_t m = p2 >= 32u ? 0xffffffffu : ((1u << p2) - 1u);
+    return (lo & m) | (((lo >> 2) | (hi << 30)) & ~m);
+}
 GHD bool plan_need1(const uint4& hd) { return ((hd.z & 255u) != 0u) || ((hd.x >> 4) & 15u); }
 GHD bool plan_need2(const uint4& hd) { return ((hd.z & 255u) >> 1) + 15u + ((hd.x >> 4) & 15u) >= 32u; }
 GHD uint32_t plan_window(const uint4& hd, uint32_t x0, uint32_t x1, uint32_t x2)

@@ -86,9 +86,9 @@ struct garlic_gpu {
     // (squeeze.cu): filter() only builds the plan
     bool geno_pending = false;
     uint4 *d_plan_head = nullptr, *d_plan_seg = nullptr;
-    int4* d_plan_rng = nullptr;
+    int2* d_plan_rng = nullptr;
     uint4* d_bhw = nullptr;        // bound tables (bound.cuh) per half-word, valid for bound_tables_W
-    int2* d_bbc = nullptr;         // per half-word q: {Bmax of block q - C2, chet}
+    uint16_t* d_plan_fast = nullptr;
     int* d_bflag = nullptr;        // != 0: the table in use breaks the bound's assumptions (every pair is a candidate)
     int bound_tables_W = 0;
     uint32_t* d_pmax = nullptr;    // [n_pieces][pmax_stride] piece maxima of every individual, valid for bound_W
@@ -258,7 +258,7 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->ev_copy) cudaEventDestroy(h->ev_copy);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    dev_free(h->d_plan_head); dev_free(h->d_plan_seg); dev_free(h->d_plan_rng); dev_free(h->d_bhw); dev_free(h->d_bbc); dev_free(h->d_bflag);
+    dev_free(h->d_plan_head); dev_free(h->d_plan_seg); dev_free(h->d_plan_rng); dev_free(h->d_bhw); dev_free(h->d_plan_fast); dev_free(h->d_bflag);
     dev_free(h->d_pmax); dev_free(h->d_cand_list); dev_free(h->d_cand_cnt); dev_free(h->d_units); dev_free(h->d_nunits);
     if (h->ev_sq0) cudaEventDestroy(h->ev_sq0);
     if (h->ev_sq1) cudaEventDestroy(h->ev_sq1);
@@ -628,11 +628,12 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     // the compaction itself waits for its first consumer (ensure_geno): here only its plan, from the gather list
     h->n_pieces = (int)((L + kPiece - 1) / kPiece);
     {
-        const long long n_q = 16ll * (h->n_pieces + 2);
+        const long long n_q = 16ll * (h->n_pieces + 4);
         if (dev_alloc(h, &h->d_plan_head, (size_t)n_q)) return 1;
         if (dev_alloc(h, &h->d_plan_seg, (size_t)n_q * kPlanSegMax)) return 1;
-        if (dev_alloc(h, &h->d_plan_rng, (size_t)h->n_pieces + 2)) return 1;
-        LAUNCH(launch_plan(h->d_src, d_total, n_q, h->d_plan_head, h->d_plan_seg, h->d_plan_rng, h->stream));
+        if (dev_alloc(h, &h->d_plan_rng, (size_t)h->n_pieces + 4)) return 1;
+        if (dev_alloc(h, &h->d_plan_fast, (size_t)n_q)) return 1;
+        LAUNCH(launch_plan(h->d_src, d_total, n_q, h->d_plan_head, h->d_plan_seg, h->d_plan_fast, h->d_plan_rng, h->stream));
     }
     h->geno_pending = true; h->bound_W = 0; h->bound_tables_W = 0;
     if (dev_alloc(h, &h->d_freq, (size_t)L + kPad)) return 1;
@@ -857,12 +858,11 @@ static bool can_bound(const garlic_gpu* h, int W)
 static int ensure_bound_tables(garlic_gpu* h, int W)
 {
     if (h->bound_tables_W == W) return 0;
-    const long long n_hw = 16ll * (h->n_pieces + 2);           // 256 (n_pieces + 2) + W + 16 < L + kPad table entries
+    const long long n_hw = 16ll * (h->n_pieces + 4);           // 256 (n_pieces + 4) + W + 16 < L + kPad table entries
     if (dev_alloc(h, &h->d_bhw, (size_t)n_hw)) return 1;
-    if (dev_alloc(h, &h->d_bbc, (size_t)n_hw)) return 1;
     if (dev_alloc(h, &h->d_bflag, (size_t)4)) return 1;
     CK(cudaMemsetAsync(h->d_bflag, 0, 4 * sizeof(int), h->stream));
-    LAUNCH(launch_bound_tables(h->d_lut, n_hw, h->L, W, h->d_bhw, h->d_bbc, h->d_bflag, h->stream));
+    LAUNCH(launch_bound_tables(h->d_lut, n_hw, h->L, W, h->d_bhw, h->d_bflag, h->stream));
     h->bound_tables_W = W;
     return 0;
 }
@@ -874,9 +874,10 @@ static SqueezeParams squeeze_params(garlic_gpu* h, bool squeeze, int W)
     Q.gin = squeeze ? h->d_geno0 : h->d_geno;
     Q.in_words = squeeze ? h->row_words0 : h->row_words;
     Q.gout = h->d_geno; Q.out_words = h->row_words;
-    Q.plan_head = h->d_plan_head; Q.plan_seg = h->d_plan_seg; Q.piece_rng = h->d_plan_rng; Q.src = h->d_src; Q.n_kept = h->d_scan + (int)((h->L0 + 1023) / 1024);
+    Q.plan_head = h->d_plan_head; Q.plan_seg = h->d_plan_seg; Q.piece_rng = h->d_plan_rng;
+    Q.plan_fast = reinterpret_cast<const uint32_t*>(h->d_plan_fast); Q.src = h->d_src; Q.n_kept = h->d_scan + (int)((h->L0 + 1023) / 1024);
     Q.n_ind = h->n_ind;
-    Q.hw = h->d_bhw; Q.bc = h->d_bbc;
+    Q.hw = h->d_bhw;
     Q.lag = bound_lag(W);
     Q.pmax = h->d_pmax; Q.pmax_stride = h->pmax_stride;
     Q.n_pieces = h->n_pieces;

@@ -31,23 +31,22 @@ struct SqueezeParams {
     int64_t in_words;
     uint64_t* gout;            // compacted rows (squeeze)
     int64_t out_words;
-    const uint4* plan_head;    // compaction plan per output half-word (bound.cuh:plan_half)
+    const uint4* plan_head;    // compaction plan per output half-word (bound.cuh:plan_half): the slow path's
     const uint4* plan_seg;
-    const int4* piece_rng;     // per piece: first / last input half-word it reads, bit mask of slow-path half-words
+    const uint32_t* plan_fast; // two-byte codes of the branch-free path (bound.cuh:plan_fast_code), two per word
+    const int2* piece_rng;     // per piece: first input half-word it reads; span << 16 | bit mask of slow-path half-words
     const int* src;            // gather list (kept SNP -> source SNP)
     const int* n_kept;         // device-resident number of kept SNPs
     int n_ind;
-    const uint4* hw;           // bound tables per half-word (bound.cuh:bound_hw_entry)
-    const int2* bc;            // per half-word q: {Bmax of block q - C2, chet of half-word q}
+    const uint4* hw;           // bound tables per half-word (bound.cuh:bound_hw_entry; w = Bmax of block q - C2)
     int lag;                   // C2 - c1: 1 or 2
     uint32_t* pmax;            // [n_pieces][pmax_stride]: piece maxima per individual (bound.cuh:bound_pack)
     int64_t pmax_stride;
     int n_pieces, pieces_per_task, n_col_tasks;
 };
-cudaError_t launch_bound_tables(const double* lut, long long n_hw, long long L, int W, uint4* hw, int2* bc, int* invalid,
-                                cudaStream_t st);
-cudaError_t launch_plan(const int* src, const int* n_kept, long long n_q, uint4* head, uint4* segs, int4* piece_rng,
-                        cudaStream_t st);
+cudaError_t launch_bound_tables(const double* lut, long long n_hw, long long L, int W, uint4* hw, int* invalid, cudaStream_t st);
+cudaError_t launch_plan(const int* src, const int* n_kept, long long n_q, uint4* head, uint4* segs, uint16_t* fast,
+                        int2* piece_rng, cudaStream_t st);
 // c2 > 0: with the bound for that window size class; squeeze = false: bound only, over compacted rows
 cudaError_t launch_squeeze_bound(SqueezeParams P, bool squeeze, int c2, cudaStream_t st);
 cudaError_t launch_select(const Item* items, int n_items, const uint32_t* pmax, int64_t stride, int n_ind, int cut_store,

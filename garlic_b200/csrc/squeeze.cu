@@ -20,14 +20,15 @@
 namespace garlic {
 
 namespace {
-constexpr int kSqWarps = 2;                               // 43 KB of shared memory per CTA: five CTAs = ten warps per SM
-constexpr int kSqStages = 4;                              // ring = 4 stages of 32 input half-words (128 B) per row
-constexpr int kSqRingHw = kSqStages * 32;                 // input half-word a of a row sits at ring position a & 127
+constexpr int kSqWarps = 4;                               // 54 KB of shared memory per CTA: four CTAs = sixteen warps per SM
+constexpr int kSqStages = 4;                              // ring = 4 stages of 16 input half-words (64 B) per row
+constexpr int kSqStageHw = 16, kSqStageShift = 4;
+constexpr int kSqRingHw = kSqStages * kSqStageHw;         // input half-word a of a row sits at ring position a & 63
 constexpr int kSqRowBytes = kSqRingHw * 4 + 8;            // + 8 B pad: rows start 2 banks apart
 constexpr int kSqRingBytes = 32 * kSqRowBytes;            // 32 rows
-constexpr int kSqOutRowBytes = 136;                       // output staging: 16 words (128 B) per row + pad
+constexpr int kSqOutRowBytes = 144;                       // output staging: 16 words (128 B) per row + 16 B pad
 constexpr int kSqOutBytes = 32 * kSqOutRowBytes;
-constexpr int kSqStashBytes = 640;                        // the current piece's plan heads, bound tables, block maxima
+constexpr int kSqStashBytes = 32 + 256 + 256;             // the current piece's plan codes, bound tables, full plan heads
 constexpr int kSqWarpBytes = kSqRingBytes + kSqOutBytes + kSqStashBytes;
 
 __device__ __forceinline__ uint32_t sq_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -35,13 +36,17 @@ __device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_dyn(int pending)     // at most `pending` (0..3) newest groups still in flight
+__device__ __forceinline__ void cp_async_wait_dyn(int pending)     // at most `pending` (0..7) newest groups still in flight
 {
     switch (pending) {
         case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
         case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
         case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
     }
 }
 }  // namespace
@@ -50,26 +55,24 @@ __device__ __forceinline__ void cp_async_wait_dyn(int pending)     // at most `p
 // tables of the bound for window size W (bound.cuh): one thread per half-word / block
 // ------------------------------------------------------------------------------------------
 __global__ void bound_tables_kernel(const double* __restrict__ lut, long long n_hw, long long L, int W,
-                                    uint4* __restrict__ hw, int2* __restrict__ bc, int* __restrict__ invalid)
+                                    uint4* __restrict__ hw, int* __restrict__ invalid)
 {
-    // bc[q] = {Bmax of block q - C2, chet of half-word q}: what the step at half-word q needs next to hw[q]
     const int c2 = bound_c2(W);
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n_hw; k += (long long)gridDim.x * blockDim.x) {
-        int bad = 0, chet = 0;
-        hw[k] = bound_hw_entry(lut, k, L, &chet, &bad);
-        bc[k].y = chet;
-        bc[k].x = k >= c2 ? bound_block_max(lut, k - c2, W) : 0;
+        int bad = 0;
+        uint4 e = bound_hw_entry(lut, k, L, &bad);
+        e.w = k >= c2 ? (uint32_t)bound_block_max(lut, k - c2, W) : 0u;   // what the step at half-word k evaluates
+        hw[k] = e;
         if (bad) atomicOr(invalid, 1);
     }
 }
 
-cudaError_t launch_bound_tables(const double* lut, long long n_hw, long long L, int W, uint4* hw, int2* bc, int* invalid,
-                                cudaStream_t st)
+cudaError_t launch_bound_tables(const double* lut, long long n_hw, long long L, int W, uint4* hw, int* invalid, cudaStream_t st)
 {
     if (!n_hw) return cudaSuccess;
     long long blocks = (n_hw + 127) / 128;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    bound_tables_kernel<<<(unsigned)blocks, 128, 0, st>>>(lut, n_hw, L, W, hw, bc, invalid);
+    bound_tables_kernel<<<(unsigned)blocks, 128, 0, st>>>(lut, n_hw, L, W, hw, invalid);
     return cudaGetLastError();
 }
 
@@ -77,32 +80,43 @@ cudaError_t launch_bound_tables(const double* lut, long long n_hw, long long L, 
 // compaction plan: one thread per output half-word (bound.cuh:plan_half) from the gather list src[]
 // ------------------------------------------------------------------------------------------
 __global__ void plan_kernel(const int* __restrict__ src, const int* __restrict__ n_kept, long long n_q,
-                            uint4* __restrict__ head, uint4* __restrict__ segs, int4* __restrict__ piece_rng)
+                            uint4* __restrict__ head, uint4* __restrict__ segs, uint16_t* __restrict__ fast,
+                            int2* __restrict__ piece_rng)
 {
     const long long L = *n_kept;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n_q; q += (long long)gridDim.x * blockDim.x) {
         uint4 hd;
         plan_half(src, L, q, &hd, segs + q * kPlanSegMax);
         head[q] = hd;
-        // per piece: first / last input half-word it reads, and which of its 16 half-words need the slow path
-        const unsigned slow = __ballot_sync(__activemask(), !plan_is_fast(hd));
+        const long long d0 = (q & ~15ll) * 16;             // first kept SNP of the piece
+        const int a0 = d0 < L ? src[d0] >> 4 : -1;         // first input half-word the piece reads
+        const uint32_t code = a0 >= 0 ? plan_fast_code(hd, a0 & ~1, (int)(q & 15)) : 0xffffu;
+        fast[q] = (uint16_t)code;
+        // per piece: x = first input half-word (-1: nothing to read), y = (last - first, saturated) << 16 | mask of the
+        // half-words that need the slow path — eight bytes, both used: a wider load with a dead component would make
+        // its register wait for the load at once
+        const unsigned slow = __ballot_sync(__activemask(), code == 0xffffu);
         if ((q & 15) == 0) {
-            const long long d0 = q * 16;
-            int4 r = make_int4(0, -1, 0, 0);               // nothing to read
-            if (d0 < L) { const long long d1 = d0 + kPiece - 1 < L ? d0 + kPiece - 1 : L - 1; r.x = src[d0] >> 4; r.y = src[d1] >> 4; }
-            r.z = (int)((slow >> (threadIdx.x & 16)) & 0xffffu);
+            int2 r = make_int2(-1, 0);
+            if (a0 >= 0) {
+                const long long d1 = d0 + kPiece - 1 < L ? d0 + kPiece - 1 : L - 1;
+                const int a1 = src[d1] >> 4;
+                r.x = a0;
+                r.y = (int)((unsigned)(a1 - a0 < 0xffff ? a1 - a0 : 0xffff) << 16);
+            }
+            r.y |= (int)((slow >> (threadIdx.x & 16)) & 0xffffu);
             piece_rng[q >> 4] = r;
         }
     }
 }
 
-cudaError_t launch_plan(const int* src, const int* n_kept, long long n_q, uint4* head, uint4* segs, int4* piece_rng,
-                        cudaStream_t st)
+cudaError_t launch_plan(const int* src, const int* n_kept, long long n_q, uint4* head, uint4* segs, uint16_t* fast,
+                        int2* piece_rng, cudaStream_t st)
 {
     if (!n_q) return cudaSuccess;
     long long blocks = (n_q + 127) / 128;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    plan_kernel<<<(unsigned)blocks, 128, 0, st>>>(src, n_kept, n_q, head, segs, piece_rng);
+    plan_kernel<<<(unsigned)blocks, 128, 0, st>>>(src, n_kept, n_q, head, segs, fast, piece_rng);
     return cudaGetLastError();
 }
 
@@ -121,10 +135,10 @@ squeeze_bound_kernel(const SqueezeParams P)
     const uint32_t* my_ring = reinterpret_cast<const uint32_t*>(ring_s + lane * kSqRowBytes);
     const uint2* my_ring64 = reinterpret_cast<const uint2*>(ring_s + lane * kSqRowBytes);
     uint32_t* my_out = reinterpret_cast<uint32_t*>(out_s + lane * kSqOutRowBytes);   // this lane's 32 output half-words
-    uint4* sh_head = reinterpret_cast<uint4*>(out_s + kSqOutBytes);
-    uint4* sh_hw = sh_head + 16;
-    int2* sh_bc = reinterpret_cast<int2*>(sh_hw + 16);
-    const int c8 = lane & 15, rsel = lane >> 4;           // copies / flushes: a half-warp covers 128 B of one row
+    uint32_t* sh_fast = reinterpret_cast<uint32_t*>(out_s + kSqOutBytes);   // the piece's 16 two-byte plan codes
+    uint4* sh_tab = reinterpret_cast<uint4*>(sh_fast + 8);                 // its 16 bound table entries (lanes 0..15)
+    uint4* sh_head = sh_tab + 16;                                          // its 16 full plan heads (lanes 16..31): slow path
+    const int c4 = lane & 7, rsel4 = lane >> 3;           // copies and flushes: a quarter-warp covers one row
     const uint32_t ring_u32 = sq_smem_u32(ring_s);
     const int n_rg = (P.n_ind + 31) >> 5;
     const long long n_kept = SQUEEZE ? (long long)*P.n_kept : 0;
@@ -137,29 +151,33 @@ squeeze_bound_kernel(const SqueezeParams P)
         const int row = rg * 32 + lane;
         const bool active = row < P.n_ind;
         const uint32_t* grow32 = reinterpret_cast<const uint32_t*>(P.gin + (int64_t)(active ? row : P.n_ind - 1) * P.in_words);
-        // ---- input ring: stage t = input half-words [32 t, 32 t + 32) of the 32 rows, in ring positions (32 t) & 127 …
+        // ---- input ring: stage t = input half-words [16 t, 16 t + 16) of the 32 rows, in ring positions (16 t) & 63 …
         int issued = 0;                                    // stages below this one have been issued (or skipped)
-        auto issue = [&](int t) {
-            const long long w0 = (long long)t * 16;        // first 64-bit word of the stage
-            if (w0 + 16 <= P.in_words) {
-                const uint32_t dst = ring_u32 + (uint32_t)((t & (kSqStages - 1)) * 128 + c8 * 8);
+        // the eight rows this lane copies for every stage (row 4 i + lane / 8, eight bytes at column lane % 8)
+        const uint64_t* cp_src[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int r = 2 * i + rsel;
-                    int gr = rg * 32 + r;
-                    gr = gr < P.n_ind ? gr : P.n_ind - 1;
-                    cp_async8(dst + r * kSqRowBytes, P.gin + (int64_t)gr * P.in_words + w0 + c8);
-                }
+        for (int i = 0; i < 8; ++i) {
+            int gr = rg * 32 + 4 * i + rsel4;
+            gr = gr < P.n_ind ? gr : P.n_ind - 1;
+            cp_src[i] = P.gin + (int64_t)gr * P.in_words + c4;
+        }
+        const uint32_t cp_dst = ring_u32 + (uint32_t)(rsel4 * kSqRowBytes + c4 * 8);
+        auto issue = [&](int t) {
+            const long long w0 = (long long)t * (kSqStageHw / 2);   // first 64-bit word of the stage
+            if (w0 + kSqStageHw / 2 <= P.in_words) {
+                const uint32_t dst = cp_dst + (uint32_t)((t & (kSqStages - 1)) * (kSqStageHw * 4));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cp_async8(dst + i * 4 * kSqRowBytes, cp_src[i] + w0);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        // Input half-words [a_lo, a_hi] must be readable: at most two stages (the usual case: a piece reads about 17
-        // consecutive input half-words), the other two ring stages stay in flight ahead.  Returns false when the range is
+        // Input half-words [a_lo, a_hi] must be readable: at most three stages (the usual case: a piece reads about 17
+        // consecutive input half-words), the fourth ring stage stays in flight ahead.  Returns false when the range is
         // wider (a long run of dropped SNPs inside the piece): that piece reads global memory directly.
         auto stage_in = [&](int a_lo, int a_hi) -> bool {
             if (a_hi < a_lo) return true;                  // nothing to read
-            const int lo_st = a_lo >> 5, hi_st = a_hi >> 5;
-            if (hi_st - lo_st > 1) return false;
+            const int lo_st = a_lo >> kSqStageShift, hi_st = a_hi >> kSqStageShift;
+            if (hi_st - lo_st > 2) return false;           // (the register window of phase A spans at most three stages)
             if (issued < lo_st) {                          // stages nobody reads are never copied; what is still in
                 asm volatile("cp.async.wait_group 0;" ::: "memory");   // flight lands before its slot gets a new owner
                 issued = lo_st;
@@ -174,19 +192,18 @@ squeeze_bound_kernel(const SqueezeParams P)
 
         BoundState S;
         bound_reset(S);
-        // The plan heads and bound tables of a piece are the same for every individual: 16 lanes fetch them with one
+        // The plan codes and bound tables of a piece are the same for every individual: a few lanes fetch them with one
         // coalesced load each, one piece ahead (the L2 latency hides behind a whole piece of work), and park them in
         // shared memory, from where every half-word step takes them with broadcast reads.
-        uint4 r_head = make_uint4(0u, 0u, 0u, 0u), r_hw = make_uint4(0u, 0u, 0u, 0u);
-        int2 r_bc = make_int2(0, 0);
-        int4 r_rng = make_int4(0, -1, 0, 0);
+        uint32_t r_fast = 0u;
+        uint4 r_tab = make_uint4(0u, 0u, 0u, 0u);         // lanes 0..15: bound table entry; lanes 16..31: full plan head
+        int2 r_rng = make_int2(-1, 0);
+        const uint4* tab_src = lane < 16 ? P.hw + lane : P.plan_head + (lane - 16);
+        const bool tab_on = lane < 16 ? BOUND : SQUEEZE;
         auto fetch = [&](int piece) {
-            if (lane < 16) {
-                const long long q = (long long)piece * 16 + lane;
-                if (SQUEEZE) r_head = P.plan_head[q];
-                if (BOUND) { r_hw = P.hw[q]; r_bc = P.bc[q]; }
-            }
-            r_rng = SQUEEZE ? P.piece_rng[piece] : make_int4(piece * 16, piece * 16 + 15, 0, 0);
+            if (SQUEEZE && lane < 8) r_fast = P.plan_fast[(long long)piece * 8 + lane];
+            if (tab_on) r_tab = tab_src[(long long)piece * 16];
+            r_rng = SQUEEZE ? P.piece_rng[piece] : make_int2(piece * 16, 15 << 16);
         };
         fetch(pc_lo);
         const int pi_end = BOUND ? pc_hi + 1 : pc_hi;     // one more piece drains the bound's C2 half-words of lag
@@ -194,68 +211,81 @@ squeeze_bound_kernel(const SqueezeParams P)
         for (int pi = pc_lo; pi < pi_end; ++pi) {
             const long long qb = (long long)pi * 16;
             __syncwarp();                                  // the previous piece's stash has been read
-            const int4 rng = r_rng;
-            const bool ring_ok = stage_in(rng.x, rng.y);
-            if (lane < 16) {
-                if (SQUEEZE) sh_head[lane] = r_head;
-                if (BOUND) { sh_hw[lane] = r_hw; sh_bc[lane] = r_bc; }
-            }
+            const int2 rng = r_rng;
+            const bool ring_ok = stage_in(rng.x, rng.x < 0 ? -2 : rng.x + (int)((unsigned)rng.y >> 16));
+            if (SQUEEZE && lane < 8) sh_fast[lane] = r_fast;
+            if (tab_on) sh_tab[lane] = r_tab;              // lanes 16..31 land in sh_head
             __syncwarp();
-            fetch(pi + 1);                                 // the tables have two pieces of slack
-            const uint32_t* hsrc;                          // where the bound reads the piece's 16 half-words
+            fetch(pi + 1);                                 // the tables have four pieces of slack
+            uint32_t hreg[16];                             // the piece's 16 half-words (registers: every index is static)
+            uint32_t* dst = my_out + ((pi & 1) << 4);
             if (SQUEEZE) {
-                // ---- phase A: the piece's 16 output half-words, by plan.  Branch-free for the usual half-word — 16
-                // consecutive sources with at most one dropped SNP in between: a funnel shift of the 64-bit window at
-                // input half-word a, then the fields above the dropped one move down by one; the two 8-byte reads are
-                // conflict-free (rows start two banks apart) — the others (slow bits of the piece) are redone after.
-                uint32_t* dst = my_out + ((pi & 1) << 4);
-                unsigned slow = ring_ok ? (unsigned)rng.z : 0xffffu;
-                if (ring_ok) {
+                // ---- phase A: the piece's 16 output half-words.  Its input window — 20 half-words from the (even) first
+                // source half-word on — is read into registers with ten conflict-free 8-byte loads; the usual output
+                // half-word (16 consecutive sources, at most one dropped SNP in between) is then a funnel shift of the
+                // 64-bit window at register I + k, k <= 2, with the fields above the dropped SNP moved down by one: no
+                // branches, no further shared-memory traffic.  The others (`slow` bits of the piece) are redone below.
+                uint32_t w[20];
+                const uint32_t u0 = (uint32_t)rng.x >> 1;
 #pragma unroll
-                    for (int I = 0; I < 16; ++I) {
+                for (int j = 0; j < 10; ++j) {
+                    const uint2 v = my_ring64[(u0 + j) & (kSqRingHw / 2 - 1)];
+                    w[2 * j] = v.x; w[2 * j + 1] = v.y;
+                }
+#pragma unroll
+                for (int I = 0; I < 16; ++I) {
+                    const uint32_t cw = sh_fast[I >> 1];
+                    const uint32_t b0 = __byte_perm(cw, 0u, (I & 1) ? 0x4442u : 0x4440u);   // k | sh << 2
+                    const uint32_t p2 = __byte_perm(cw, 0u, (I & 1) ? 0x4443u : 0x4441u);   // 2 p
+                    const uint32_t k = b0 & 3u, sh = b0 >> 2;
+                    const uint32_t x0 = k == 0u ? w[I] : (k == 1u ? w[I + 1] : w[I + 2]);
+                    const uint32_t x1 = k == 0u ? w[I + 1] : (k == 1u ? w[I + 2] : w[I + 3]);
+                    const uint32_t x2 = k == 0u ? w[I + 2] : (k == 1u ? w[I + 3] : w[I + 4]);
+                    const uint32_t lo = __funnelshift_r(x0, x1, sh), hi = __funnelshift_r(x1, x2, sh);
+                    const uint32_t m = __funnelshift_lc(0xffffffffu, 0u, p2);             // the fields below the dropped one
+                    hreg[I] = (lo & m) | (__funnelshift_r(lo, hi, 2u) & ~m);
+                }
+#pragma unroll
+                for (int I = 0; I < 16; I += 4) *reinterpret_cast<uint4*>(dst + I) = make_uint4(hreg[I], hreg[I + 1], hreg[I + 2], hreg[I + 3]);
+                unsigned slow = ring_ok ? ((unsigned)rng.y & 0xffffu) : 0xffffu;
+                if (slow) {                                // several dropped SNPs, long dropped runs, the end of the data
+#pragma unroll 1
+                    for (; slow; slow &= slow - 1u) {
+                        const int I = __ffs((int)slow) - 1;
                         const uint4 hd = sh_head[I];
-                        const uint32_t u = hd.y >> 1;
-                        const uint2 p0 = my_ring64[u & (kSqRingHw / 2 - 1)], p1 = my_ring64[(u + 1) & (kSqRingHw / 2 - 1)];
-                        const bool odd = hd.y & 1u;
-                        const uint32_t x0 = odd ? p0.y : p0.x, x1 = odd ? p1.x : p0.y, x2 = odd ? p1.y : p1.x;
-                        const uint32_t sh = hd.z & 255u;
-                        const uint32_t lo = __funnelshift_r(x0, x1, sh), hi = __funnelshift_r(x1, x2, sh);
-                        const uint32_t slo = __funnelshift_r(lo, hi, 2u);
-                        dst[I] = (lo & hd.w) | (slo & ~hd.w);
-                    }
-                }
+                        uint32_t h;
+                        if (hd.x & 0x100u) {
+                            const uint32_t a = hd.y;
+                            if (ring_ok) h = plan_window(hd, my_ring[a & (kSqRingHw - 1)], my_ring[(a + 1) & (kSqRingHw - 1)], my_ring[(a + 2) & (kSqRingHw - 1)]);
+                            else h = plan_window(hd, grow32[a], plan_need1(hd) ? grow32[a + 1] : 0u, plan_need2(hd) ? grow32[a + 2] : 0u);
+                        } else {
+                            h = hd.w;
+                            const uint4* sg = P.plan_seg + (qb + I) * kPlanSegMax;
+                            const int ns = (int)hd.x;
 #pragma unroll 1
-                for (; slow; slow &= slow - 1u) {          // several dropped SNPs, long dropped runs, the end of the data
-                    const int I = __ffs((int)slow) - 1;
-                    const uint4 hd = sh_head[I];
-                    uint32_t h;
-                    if (hd.x & 0x100u) {
-                        const uint32_t a = hd.y;
-                        if (ring_ok) h = plan_window(hd, my_ring[a & (kSqRingHw - 1)], my_ring[(a + 1) & (kSqRingHw - 1)], my_ring[(a + 2) & (kSqRingHw - 1)]);
-                        else h = plan_window(hd, grow32[a], plan_need1(hd) ? grow32[a + 1] : 0u, plan_need2(hd) ? grow32[a + 2] : 0u);
-                    } else {
-                        h = hd.w;
-                        const uint4* sg = P.plan_seg + (qb + I) * kPlanSegMax;
-                        const int ns = (int)hd.x;
-#pragma unroll 1
-                        for (int k = 0; k < ns; ++k) {
-                            const uint4 g = sg[k];
-                            const uint32_t x = ring_ok ? my_ring[g.x & (kSqRingHw - 1)] : grow32[g.x];
-                            h |= ((x >> g.y) & g.z) << g.w;
+                            for (int k = 0; k < ns; ++k) {
+                                const uint4 g = sg[k];
+                                const uint32_t x = ring_ok ? my_ring[g.x & (kSqRingHw - 1)] : grow32[g.x];
+                                h |= ((x >> g.y) & g.z) << g.w;
+                            }
                         }
+                        dst[I] = h;
                     }
-                    dst[I] = h;
+                    __syncwarp();
+#pragma unroll
+                    for (int I = 0; I < 16; ++I) hreg[I] = dst[I];
                 }
-                hsrc = dst;
             } else {
-                hsrc = my_ring + (qb & (kSqRingHw - 1));   // a piece is half a stage: never wraps
+                const uint4* hsrc = reinterpret_cast<const uint4*>(my_ring + (qb & (kSqRingHw - 1)));   // a piece = one stage
+#pragma unroll
+                for (int I = 0; I < 16; I += 4) { const uint2 v0 = reinterpret_cast<const uint2*>(hsrc)[I >> 1], v1 = reinterpret_cast<const uint2*>(hsrc)[(I >> 1) + 1]; hreg[I] = v0.x; hreg[I + 1] = v0.y; hreg[I + 2] = v1.x; hreg[I + 3] = v1.y; }
             }
             if (BOUND) {
                 // ---- phase B: the bound over the 16 half-words, ring indices compile-time
 #pragma unroll
                 for (int I = 0; I < 16; ++I) {
                     const long long q = qb + I;
-                    bound_step<C2, LAG>(S, hsrc[I], sh_hw[I], sh_bc[I], I);
+                    bound_step<C2, LAG>(S, hreg[I], sh_tab[I], I);
                     if (((I - C2) & 15) == 15) {           // block k = q - C2 closes its piece
                         const int piece = (int)((q - C2) >> 4);
                         if (piece >= pc_lo && piece < pc_hi && active)
@@ -264,18 +294,17 @@ squeeze_bound_kernel(const SqueezeParams P)
                     }
                 }
             }
-            // ---- two pieces = 16 output words per row: flush through shared memory, 128 B per row per store
+            // ---- two pieces = 16 output words per row: flush through shared memory, 128 B per row and quarter-warp
             if (SQUEEZE && pi < pc_hi && ((pi & 1) || pi == pc_hi - 1)) {
                 __syncwarp();
-                const long long wbase = 16ll * (pi >> 1);
-                const int nw = (pi & 1) ? 16 : 8;
+                const long long wd = 16ll * (pi >> 1) + 2 * c4;
+                if (2 * c4 < ((pi & 1) ? 16 : 8) && wd < n_out_words) {
+                    const unsigned char* sp = out_s + rsel4 * kSqOutRowBytes + c4 * 16;
+                    uint64_t* gp = P.gout + (int64_t)(rg * 32 + rsel4) * P.out_words + wd;
+                    const int rows = min(32, P.n_ind - rg * 32);           // rows of this group that exist
 #pragma unroll 4
-                for (int i = 0; i < 16; ++i) {
-                    const int r = 2 * i + rsel;
-                    const uint64_t v = *reinterpret_cast<const uint64_t*>(out_s + r * kSqOutRowBytes + c8 * 8);
-                    const int gr = rg * 32 + r;
-                    const long long w = wbase + c8;
-                    if (gr < P.n_ind && c8 < nw && w < n_out_words) P.gout[(int64_t)gr * P.out_words + w] = v;
+                    for (int r = rsel4; r < rows; r += 4, sp += 4 * kSqOutRowBytes, gp += 4 * P.out_words)
+                        *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(sp);
                 }
                 __syncwarp();
             }
@@ -320,7 +349,7 @@ static cudaError_t launch_sq_c2(const SqueezeParams& P, int c2, unsigned grid, s
 int squeeze_pieces_per_task(int n_ind, int n_pieces)
 {
     const int n_rg = (n_ind + 31) / 32;
-    const int want_tasks = 148 * 10 * 4;
+    const int want_tasks = 148 * 16 * 3;
     int n_col = std::max(1, (want_tasks + n_rg - 1) / n_rg);
     int ppt = (n_pieces + n_col - 1) / n_col;
     ppt = std::max(ppt, 16);
@@ -336,7 +365,7 @@ cudaError_t launch_squeeze_bound(SqueezeParams P, bool squeeze, int c2, cudaStre
     const int n_rg = (P.n_ind + 31) / 32;
     const long long n_tasks = (long long)n_rg * P.n_col_tasks;
     long long grid = (n_tasks + kSqWarps - 1) / kSqWarps;
-    if (grid > 148ll * 5 * 8) grid = 148ll * 5 * 8;
+    if (grid > 148ll * 4 * 8) grid = 148ll * 4 * 8;
     const size_t smem = (size_t)kSqWarps * kSqWarpBytes;
     if (c2 <= 0) {
         if (!squeeze) return cudaErrorInvalidValue;

@@ -102,7 +102,7 @@ int emu_windows(const uint64_t* geno, int64_t row_words, const double* lut, cons
 // kernels of squeeze.cu run.  pmax[n_pieces][n_ind] as the fused kernel stores it.
 // ---------------------------------------------------------------------------------------------------------------
 template <int C2, int LAG>
-static void emu_bound_row(const uint32_t* hw_row, long long n_hw, const std::vector<uint4>& hw, const std::vector<int2>& bc,
+static void emu_bound_row(const uint32_t* hw_row, long long n_hw, const std::vector<uint4>& hw,
                           int n_pieces, uint32_t* pmax, int64_t stride, int ind)
 {
     BoundState S;
@@ -111,7 +111,7 @@ static void emu_bound_row(const uint32_t* hw_row, long long n_hw, const std::vec
         for (int I = 0; I < 16; ++I) {
             const long long q = (long long)pi * 16 + I;
             const uint32_t h = q < n_hw ? hw_row[q] : 0xffffffffu;
-            bound_step<C2, LAG>(S, h, hw[q], bc[q], I);
+            bound_step<C2, LAG>(S, h, hw[q], I);
             if (((I - C2) & 15) == 15) {
                 const long long piece = (q - C2) >> 4;
                 if (piece >= 0 && piece < n_pieces) pmax[piece * stride + ind] = bound_pack(S.pm_all, S.pm_tail);
@@ -131,18 +131,17 @@ int emu_bound(const uint64_t* geno, int64_t row_words, const double* lut, long l
     if (W < kBoundMinW || (lag != 1 && lag != 2)) return -1;
     const long long n_hw = 16ll * (n_pieces + 2);
     std::vector<uint4> hw(n_hw);
-    std::vector<int2> bc(n_hw);
     int invalid = 0;
     for (long long k = 0; k < n_hw; ++k) {
-        hw[k] = bound_hw_entry(lut, k, L, &bc[k].y, &invalid);
-        bc[k].x = k >= c2 ? bound_block_max(lut, k - c2, W) : 0;
+        hw[k] = bound_hw_entry(lut, k, L, &invalid);
+        hw[k].w = k >= c2 ? (uint32_t)bound_block_max(lut, k - c2, W) : 0u;
     }
     for (int i = 0; i < n_ind; ++i) {
         const uint32_t* row = reinterpret_cast<const uint32_t*>(geno + (int64_t)i * row_words);
         const long long row_hw = row_words * 2;
         switch (c2) {
-#define CASE(C) case C: if (lag == 1) emu_bound_row<C, 1>(row, row_hw, hw, bc, n_pieces, pmax, n_ind, i); \
-                        else emu_bound_row<C, 2>(row, row_hw, hw, bc, n_pieces, pmax, n_ind, i); break;
+#define CASE(C) case C: if (lag == 1) emu_bound_row<C, 1>(row, row_hw, hw, n_pieces, pmax, n_ind, i); \
+                        else emu_bound_row<C, 2>(row, row_hw, hw, n_pieces, pmax, n_ind, i); break;
             CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
 #undef CASE
             default: return -1;
@@ -181,10 +180,15 @@ void emu_squeeze(const uint64_t* rows_in, int64_t in_words, const int32_t* src, 
     uint4 head, segs[kPlanSegMax];
     for (long long q = 0; q < n_q; ++q) {
         plan_half(src, L, q, &head, segs);
+        const int a_base = (src[(q & ~15ll) * 16] >> 4) & ~1, I = (int)(q & 15);
+        const uint32_t code = plan_fast_code(head, a_base, I);
         for (int i = 0; i < n_ind; ++i) {
             const uint32_t* hin = reinterpret_cast<const uint32_t*>(rows_in + (int64_t)i * in_words);
             uint32_t h;
-            if (head.x & 0x100u) {
+            if (code != 0xffffu) {                         // the kernel's branch-free path
+                const uint32_t* w = hin + a_base + I;
+                h = plan_fast_apply(code, w[0], w[1], w[2], w[3], w[4]);
+            } else if (head.x & 0x100u) {
                 h = plan_window(head, hin[head.y], plan_need1(head) ? hin[head.y + 1] : 0u, plan_need2(head) ? hin[head.y + 2] : 0u);
             } else {
                 h = head.w;
