@@ -380,7 +380,7 @@ def main():
         g.set_tables(err, max_gap, cen_arr)                  # K4
         t0 = lap("set_tables", t0)
         if dist is None:
-            thin = g.windows(W, W, individuals=kde_local, exact=False)
+            thin = g.windows(W, W, individuals=kde_local, exact=False, reuse=True)
         else:                                                # every rank gets all KDE individuals' thinned LODs
             thin = g.windows_gather(W, W, kde_local, kde_max, world)
         t0 = lap("pass1_thinned_windows", t0)

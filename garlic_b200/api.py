@@ -96,7 +96,7 @@ class GarlicGPU:
         for ptr in getattr(self, "_pinned", []):
             self.lib.garlic_gpu_host_free(C.c_void_p(ptr))
         self._pinned = []
-        self._freq_buf = self._keep_buf = None
+        self._freq_buf = self._keep_buf = self._win_buf = None
         if self.h:
             self.lib.garlic_gpu_destroy(self.h)
             self.h = C.c_void_p()
@@ -235,10 +235,19 @@ class GarlicGPU:
     def window_slots(self, step):
         return int(self.lib.garlic_gpu_window_slots(self.h, C.c_int(step)))
 
-    def windows(self, W, step=1, weighted=False, individuals=None, exact=True):
+    def windows(self, W, step=1, weighted=False, individuals=None, exact=True, reuse=False):
+        """reuse=True: the result is a view of a page-locked buffer owned by this object, overwritten by the next call."""
         idx = None if individuals is None else np.ascontiguousarray(individuals, np.int32)
         n = self.n_ind if idx is None else len(idx)
-        out = np.empty((n, self.window_slots(step)), np.float64)
+        shape = (n, self.window_slots(step))
+        if reuse and shape[0] * shape[1] <= (1 << 23):
+            # small results (the KDE's thinned windows) land in a page-locked buffer kept between calls: a fresh
+            # pageable array costs more in page faults than the whole pass
+            if getattr(self, "_win_buf", None) is None or self._win_buf.size < shape[0] * shape[1]:
+                self._win_buf = self.host_array(max(shape[0] * shape[1], 1), np.float64)
+            out = self._win_buf[:shape[0] * shape[1]].reshape(shape)
+        else:
+            out = np.empty(shape, np.float64)
         self._ck(self.lib.garlic_gpu_windows(self.h, C.c_int(W), C.c_int(step), C.c_int(int(weighted)), _p(idx),
                                              C.c_int(n), C.c_int(int(exact)), _p(out)))
         return out

@@ -69,6 +69,14 @@ struct garlic_gpu {
         *d_chr_start = nullptr, *d_chr_param = nullptr;
     RohRec *d_out = nullptr, *d_amb = nullptr, *d_sorted = nullptr;
     unsigned* d_hist = nullptr;       // run records per individual → bucket offsets
+    unsigned* d_kept = nullptr;       // final runs per individual → offsets of the dense output
+    size_t last_final = 0;            // final runs of the previous call_roh (size of the speculative first copy)
+    // pass-2 items of the pruned pass, built (and uploaded) while the GPU is busy with pass 1 (windows_common)
+    std::vector<Segment> p2_segs;
+    std::vector<Item> p2_items;
+    Item* d_items_p2 = nullptr;
+    int p2_W = 0, p2_tile = 0, p2_chunk = 0;
+    uint64_t tables_gen = 0, p2_gen = 0;
     size_t sorted_cap = 0;
     unsigned out_cap = 0, amb_cap = 0;
     unsigned* d_cnt = nullptr;
@@ -250,7 +258,7 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     dev_free(h->d_gpos); dev_free(h->d_nomut); dev_free(h->d_norec); dev_free(h->d_wlut); dev_free(h->d_invld);
     dev_free(h->d_homf); dev_free(h->d_keep); dev_free(h->d_src); dev_free(h->d_pos0); dev_free(h->d_chr_of0);
     dev_free(h->d_pos); dev_free(h->d_chr_of); dev_free(h->d_chr_start); dev_free(h->d_chr_param);
-    dev_free(h->d_out); dev_free(h->d_amb); dev_free(h->d_sorted); dev_free(h->d_hist); dev_free(h->d_cnt); dev_free(h->d_items); dev_free(h->d_indlist); dev_free(h->d_dump);
+    dev_free(h->d_out); dev_free(h->d_amb); dev_free(h->d_sorted); dev_free(h->d_hist); dev_free(h->d_kept); dev_free(h->d_items_p2); dev_free(h->d_cnt); dev_free(h->d_items); dev_free(h->d_indlist); dev_free(h->d_dump);
     dev_free(h->d_scan); dev_free(h->d_breaks); dev_free(h->d_thin);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -708,26 +716,31 @@ int garlic_gpu_set_tables(garlic_gpu_t* h, double error, int max_gap, const int3
         if (dev_alloc(h, &h->d_gpos, (size_t)L)) return 1;
         CK(cudaMemcpyAsync(h->d_gpos, gpos, L * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     }
-    CK(cudaStreamSynchronize(h->stream));
     h->amax = lod_bound(h);   // enters the ambiguity tolerance of the chunked / tensor-core passes
-    laps.lap("lut");
-    // gap/centromere-free stretches: bad adjacent pairs found on the device (a short list), sorted here
+    // gap/centromere-free stretches: bad adjacent pairs found on the device (a short list), sorted here; the count and
+    // the first entries come back in one copy behind the kernels above (one synchronisation per call)
     {
-        const unsigned cap = 1u << 20;
+        const unsigned cap = 1u << 20, first = 4096;
         if (dev_alloc(h, &h->d_breaks, (size_t)cap + 2 * h->n_chr + 4)) return 1;
         int* d_cen = h->d_breaks + cap;
         unsigned* d_n = reinterpret_cast<unsigned*>(d_cen + 2 * h->n_chr);
         CK(cudaMemcpyAsync(d_cen, h->cen.data(), 2 * h->n_chr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemsetAsync(d_n, 0, sizeof(unsigned), h->stream));
         LAUNCH(launch_bad_pairs(h->d_pos, h->d_chr_of, d_cen, max_gap, L, h->d_breaks, d_n, cap, h->stream));
-        if (pin_alloc(h, 64)) return 1;
+        if (pin_alloc(h, 64 + first * sizeof(int))) return 1;
         unsigned* n_host = reinterpret_cast<unsigned*>(h->pin);
+        int* first_host = reinterpret_cast<int*>(h->pin + 64);
         CK(cudaMemcpyAsync(n_host, d_n, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(first_host, h->d_breaks, first * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        laps.lap("lut+gaps");
         const unsigned nb = *n_host;
         if (nb > cap) FAIL("set_tables: more than 2^20 gaps; raise --max-gap");
-        std::vector<int> breaks(nb);
-        if (nb) CK(cudaMemcpy(breaks.data(), h->d_breaks, nb * sizeof(int), cudaMemcpyDeviceToHost));
+        std::vector<int> breaks(first_host, first_host + std::min(nb, first));
+        if (nb > first) {
+            breaks.resize(nb);
+            CK(cudaMemcpy(breaks.data() + first, h->d_breaks + first, (nb - first) * sizeof(int), cudaMemcpyDeviceToHost));
+        }
         std::sort(breaks.begin(), breaks.end());
         h->stretches.clear();
         size_t bi = 0;
@@ -742,7 +755,7 @@ int garlic_gpu_set_tables(garlic_gpu_t* h, double error, int max_gap, const int3
         }
     }
     laps.lap("stretches");
-    h->tables = true; h->have_ld = false; h->bound_W = 0; h->bound_tables_W = 0;
+    h->tables = true; h->have_ld = false; h->bound_W = 0; h->bound_tables_W = 0; h->tables_gen++;
     return 0;
 }
 
@@ -911,6 +924,23 @@ static int ensure_geno(garlic_gpu* h, int W_hint)
     return 0;
 }
 
+// Items of the pruned pass 2 for window size W: piece-aligned chunks of the segments, uploaded to their own buffer.
+// Built once per (tables, W) — windows_common calls this while the GPU is busy with pass 1, call_roh finds them ready.
+static int prepare_p2_items(garlic_gpu* h, int W)
+{
+    if (h->p2_gen == h->tables_gen && h->p2_W == W) return 0;
+    segments_from_stretches(h->stretches, W, h->p2_segs);
+    build_items_aligned(h->chr_off, W, h->p2_segs, kPiece * h->item_pieces, h->p2_items);
+    h->p2_chunk = 0;
+    for (const Item& it : h->p2_items) h->p2_chunk = std::max(h->p2_chunk, it.own_hi - it.own_lo);
+    h->p2_tile = items_tile_snps(h->p2_items, W);
+    if (dev_alloc(h, &h->d_items_p2, h->p2_items.size() + 1)) return 1;
+    if (!h->p2_items.empty())
+        CK(cudaMemcpyAsync(h->d_items_p2, h->p2_items.data(), h->p2_items.size() * sizeof(Item), cudaMemcpyHostToDevice, h->stream));
+    h->p2_gen = h->tables_gen; h->p2_W = W;
+    return 0;
+}
+
 // piece maxima for window size W present (fused with the compaction if that is still pending)
 static int ensure_bound(garlic_gpu* h, int W)
 {
@@ -1023,6 +1053,8 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
         LAUNCH(launch_thin_windows(h->d_geno, h->row_words, h->d_lut, individuals ? h->d_indlist : nullptr, n_lanes, d_segs,
                                    (int)segs.size(), d_meta, h->n_chr, slots, step, W, d_dump, slots,
                                    h->have_gl ? h->d_gl : nullptr, h->gl_stride, h->stream));
+        // the GPU is busy (compaction + bound, thinned windows): the host gets pass 2's items ready meanwhile
+        if (h->bound_W == W && prepare_p2_items(h, W)) return 1;
     } else {
     int chunk = 0;
     if (weighted) chunk = std::max(64, pick_chunk(h->L, W, n_lanes, 0) / 8);   // every wLOD window is a fresh sum
@@ -1085,13 +1117,19 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
                                                                       : std::max(64, pick_chunk(h->L, W, h->n_ind, 0) / 8);
     else if (!exact) chunk = pick_chunk(h->L, W, h->n_ind, h->have_gl ? 0 : kTileSnpsMax);
     if (prune) {
-        build_items_aligned(h->chr_off, W, segs, kPiece * h->item_pieces, items);
-        chunk = 0;
-        for (const Item& it : items) chunk = std::max(chunk, it.own_hi - it.own_lo);
-        prune = items_tile_snps(items, W) <= kTileSnpsMax && (int64_t)items.size() * h->n_ind < (1ll << 31);
+        if (prepare_p2_items(h, W)) return 1;
+        prune = h->p2_tile <= kTileSnpsMax && (int64_t)h->p2_items.size() * h->n_ind < (1ll << 31);
+        if (prune) chunk = h->p2_chunk;
     }
-    if (!prune) build_items(h->chr_off, W, segs, chunk, 0, items);
-    if (upload_items(h, items)) return 1;
+    const Item* d_its = h->d_items;                    // the items in use: the cached piece-aligned ones, or `items`
+    const std::vector<Item>* its = &items;
+    if (prune) {
+        d_its = h->d_items_p2; its = &h->p2_items;
+    } else {
+        build_items(h->chr_off, W, segs, chunk, 0, items);
+        if (upload_items(h, items)) return 1;
+        d_its = h->d_items;                            // (the upload may have moved the buffer)
+    }
     int64_t n_win = 0;
     for (const Segment& s : segs) n_win += s.we - s.ws;
     // note: the reference also "evaluates" invalid window starts (they come out MISSING); the unit
@@ -1131,8 +1169,9 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
         // pruned pass: the piece maxima (computed with the compaction, or now) are thresholded into dense per-item
         // candidate lists and a queue of work units; the walker below only visits those
-        const int tile_snps = items_tile_snps(items, W);
+        const int tile_snps = prune ? h->p2_tile : items_tile_snps(*its, W);
         const bool prune_now = prune && !exact;
+        const int n_its = (int)its->size();
         CandList cl;
         unsigned unit_cap = 0;
         CK(cudaEventRecord(h->ev0, h->stream));
@@ -1141,57 +1180,65 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
             int ok = 0;
             const int cut_store = bound_cut_store(cutoff, P.tol, &ok);
             const int per_item = (h->n_ind + kUnitThreads - 1) / kUnitThreads;
-            unit_cap = (unsigned)std::min<int64_t>((int64_t)items.size() * per_item, 1ll << 28);
-            if (dev_alloc(h, &h->d_cand_list, (size_t)items.size() * h->n_ind)) return 1;
-            if (dev_alloc(h, &h->d_cand_cnt, items.size() + 1)) return 1;
+            unit_cap = (unsigned)std::min<int64_t>((int64_t)n_its * per_item, 1ll << 28);
+            if (dev_alloc(h, &h->d_cand_list, (size_t)n_its * h->n_ind)) return 1;
+            if (dev_alloc(h, &h->d_cand_cnt, (size_t)n_its + 1)) return 1;
             if (dev_alloc(h, &h->d_units, (size_t)unit_cap)) return 1;
             if (dev_alloc(h, &h->d_nunits, (size_t)4)) return 1;
             CK(cudaMemsetAsync(h->d_nunits, 0, 4 * sizeof(unsigned), h->stream));
-            LAUNCH(launch_select(h->d_items, (int)items.size(), h->d_pmax, h->pmax_stride, h->n_ind, cut_store, h->d_bflag,
+            LAUNCH(launch_select(d_its, n_its, h->d_pmax, h->pmax_stride, h->n_ind, cut_store, h->d_bflag,
                                  h->d_cand_list, h->n_ind, h->d_cand_cnt, h->d_units, h->d_nunits, unit_cap, kUnitThreads, h->stream));
             cl.list = h->d_cand_list; cl.cnt = h->d_cand_cnt; cl.stride = h->n_ind;
         }
         CK(cudaEventRecord(h->ev2, h->stream));
-        // run records are bucketed by individual on the device (kernels.cu:launch_bucket_by_individual)
+        // run records are bucketed by individual, ordered, stitched and packed on the device
+        // (kernels.cu:launch_bucket_by_individual): the final runs end up dense in d_out, their number in d_cnt[2]
         if (dev_alloc(h, &h->d_hist, (size_t)h->n_ind + 1)) return 1;
+        if (dev_alloc(h, &h->d_kept, (size_t)h->n_ind + 1)) return 1;
         if (dev_alloc(h, &h->d_sorted, (size_t)h->out_cap)) return 1;
         CK(cudaMemsetAsync(h->d_hist, 0, ((size_t)h->n_ind + 1) * sizeof(unsigned), h->stream));
+        CK(cudaMemsetAsync(h->d_kept, 0, ((size_t)h->n_ind + 1) * sizeof(unsigned), h->stream));
         P.hist = h->d_hist;
-        if (prune_now) LAUNCH(launch_walk_units(P, h->d_items, h->d_units, h->d_nunits, unit_cap, tile_snps, cl, h->stream));
-        else if (launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, true, false, tile_snps)) return 1;
+        if (prune_now) LAUNCH(launch_walk_units(P, d_its, h->d_units, h->d_nunits, unit_cap, tile_snps, cl, h->stream));
+        else if (launch_any_walk(h, P, d_its, n_its, weighted, true, false, tile_snps)) return 1;
         CK(cudaEventRecord(h->ev1, h->stream));
-        LAUNCH(launch_bucket_by_individual(h->d_out, h->d_cnt, h->out_cap, h->d_hist, h->n_ind, h->d_sorted, thr, h->stream));
-        unsigned cnt[4];
-        CK(cudaMemcpyAsync(cnt, h->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+        LAUNCH(launch_bucket_by_individual(h->d_out, h->d_cnt, h->out_cap, h->d_hist, h->n_ind, h->d_sorted, thr, h->d_kept,
+                                           h->d_cnt + 2, h->stream));
+        // one synchronisation: the counters and — speculatively, sized by the previous call — the final runs and the
+        // ambiguous pairs travel together; only a larger result costs a second copy
+        const size_t guess = std::min<size_t>(h->out_cap, std::max<size_t>(4096, h->last_final + h->last_final / 4));
+        const size_t amb_guess = 256;
+        if (pin_alloc(h, 64 + (guess + std::max<size_t>(amb_guess, h->amb_cap)) * sizeof(RohRec))) return 1;
+        unsigned* cnt = reinterpret_cast<unsigned*>(h->pin);
+        RohRec* stage = reinterpret_cast<RohRec*>(h->pin + 64);
+        CK(cudaMemcpyAsync(cnt, h->d_cnt, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(stage, h->d_out, guess * sizeof(RohRec), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(stage + guess, h->d_amb, amb_guess * sizeof(RohRec), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         CK(cudaEventElapsedTime(&ms_coarse, h->ev0, h->ev2));
         pruned = prune_now;
-        if (cnt[0] > h->out_cap) {
-            h->out_cap = cnt[0] + cnt[0] / 4 + 1024;
+        const unsigned n_raw = cnt[0], n_amb = cnt[1], n_fin = cnt[2];
+        if (n_raw > h->out_cap) {
+            h->out_cap = n_raw + n_raw / 4 + 1024;
             if (dev_alloc(h, &h->d_out, h->out_cap)) return 1;
             continue;
         }
-        if (cnt[1] > h->amb_cap) {   // pathological: (nearly) everything ambiguous → exact everywhere
-            exact = 1;
+        if (n_amb > h->amb_cap) {   // pathological: (nearly) everything ambiguous → exact everywhere
+            exact = 1; prune = false;
             build_items(h->chr_off, W, segs, 0, 0, items);
             if (upload_items(h, items)) return 1;
+            d_its = h->d_items; its = &items;
             continue;
         }
-        recs.resize(cnt[0]);
-        ambs.resize(cnt[1]);
-        if (cnt[0] + cnt[1]) {   // through the pinned staging buffer (a pageable copy is several times slower)
-            if (pin_alloc(h, ((size_t)cnt[0] + cnt[1]) * sizeof(RohRec))) return 1;
-            RohRec* stage = reinterpret_cast<RohRec*>(h->pin);
-            if (cnt[0]) CK(cudaMemcpyAsync(stage, h->d_sorted, cnt[0] * sizeof(RohRec), cudaMemcpyDeviceToHost, h->stream));
-            if (cnt[1]) CK(cudaMemcpyAsync(stage + cnt[0], h->d_amb, cnt[1] * sizeof(RohRec), cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-            n_stage = cnt[0];
-            // runs arrive ordered and stitched by the device (bucket_stitch_kernel); with ambiguous pairs the exact
-            // re-evaluation below splices its runs in and the host sorts once more
-            if (cnt[1]) take_stitched(stage, cnt[0], recs);
-            memcpy(ambs.data(), stage + cnt[0], cnt[1] * sizeof(RohRec));
-        }
+        recs.resize(n_fin);
+        ambs.resize(n_amb);
+        if (n_fin) memcpy(recs.data(), stage, std::min<size_t>(n_fin, guess) * sizeof(RohRec));
+        if (n_fin > guess) CK(cudaMemcpy(recs.data() + guess, h->d_out + guess, (n_fin - guess) * sizeof(RohRec), cudaMemcpyDeviceToHost));
+        if (n_amb) memcpy(ambs.data(), stage + guess, std::min<size_t>(n_amb, amb_guess) * sizeof(RohRec));
+        if (n_amb > amb_guess) CK(cudaMemcpy(ambs.data() + amb_guess, h->d_amb + amb_guess, (n_amb - amb_guess) * sizeof(RohRec), cudaMemcpyDeviceToHost));
+        n_stage = n_raw;
+        h->last_final = n_fin;
         done = true;
         break;
     }
@@ -1236,9 +1283,10 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     }
     // sort by (individual, start) and stitch runs that were cut at chunk boundaries
     laps.lap("ambiguous");
-    std::vector<RohRec>& merged = h->merged_buf;
-    if (ambs.empty()) take_stitched(reinterpret_cast<RohRec*>(h->pin), n_stage, merged);
-    else stitch_runs(recs, thr, merged, &h->stitch_scratch);             // re-evaluated pairs were spliced in: full sort
+    // the device's runs are final (ordered, stitched, minimum length applied); with re-evaluated pairs spliced in the
+    // host sorts and stitches once more
+    std::vector<RohRec>& merged = ambs.empty() ? recs : h->merged_buf;
+    if (!ambs.empty()) stitch_runs(recs, thr, merged, &h->stitch_scratch);
     laps.lap("stitch");
     if (laps.on) fprintf(stderr, "[garlic_b200] call_roh: %zu raw records, %zu ambiguous pairs, %zu runs after stitching\n", n_stage, ambs.size(), merged.size());
     const int64_t n_out = (int64_t)merged.size();
@@ -1249,14 +1297,14 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         out[r].stop_idx = merged[r].b;
     }
     if (count) *count = n_out;
-    h->stats[0] = (double)items.size();
+    h->stats[0] = (double)its->size();
     h->stats[1] = (double)units;
     h->stats[2] = (double)n_amb_pairs;
     h->stats[3] = ms;
     h->stats[4] = ms_coarse;
     h->stats[5] = -1;
-    h->stats[6] = (double)items.size() * h->n_ind;
-    h->stats_items = pruned ? (int64_t)items.size() : 0;   // candidate counts are fetched by last_stats on demand
+    h->stats[6] = (double)its->size() * h->n_ind;
+    h->stats_items = pruned ? (int64_t)its->size() : 0;    // candidate counts are fetched by last_stats on demand
     laps.lap("out");
     return 0;
 }

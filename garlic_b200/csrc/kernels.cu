@@ -674,7 +674,20 @@ __global__ void thin_windows_kernel(const uint64_t* __restrict__ geno, int64_t r
         if (glrow) {
             for (int i = 0; i < W; ++i) win += glrow[(int64_t)(t + i) * kGlLanes];
         } else {
-            for (int i = 0; i < W; ++i) {
+            // eight table lookups in flight at a time; the sum itself stays ascending (a fresh sum of calcLOD)
+            int i = 0;
+            for (; i + 8 <= W; i += 8) {
+                double v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int s = t + i + k;
+                    const int g = (int)(row[s >> 5] >> (2 * (s & 31))) & 3;
+                    v[k] = lut[(int64_t)s * 4 + g];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) win += v[k];
+            }
+            for (; i < W; ++i) {
                 const int s = t + i;
                 const int g = (int)(row[s >> 5] >> (2 * (s & 31))) & 3;
                 win += lut[(int64_t)s * 4 + g];
@@ -739,7 +752,8 @@ __global__ void bucket_scatter_kernel(const RohRec* __restrict__ in, const unsig
 // ends: the bucket offsets after the scatter (= end of every individual's bucket).
 constexpr int kStitchSmem = 256;
 __global__ void __launch_bounds__(128)
-bucket_stitch_kernel(RohRec* __restrict__ recs, RohRec* __restrict__ scratch, const unsigned* __restrict__ ends, int n_ind, int thr)
+bucket_stitch_kernel(RohRec* __restrict__ recs, RohRec* __restrict__ scratch, const unsigned* __restrict__ ends, int n_ind, int thr,
+                     unsigned* __restrict__ kept)
 {
     __shared__ RohRec s_in[4][kStitchSmem];
     __shared__ RohRec s_rec[4][kStitchSmem];
@@ -747,7 +761,7 @@ bucket_stitch_kernel(RohRec* __restrict__ recs, RohRec* __restrict__ scratch, co
     for (int i = blockIdx.x * 4 + warp; i < n_ind; i += gridDim.x * 4) {
         const unsigned lo = i ? ends[i - 1] : 0u, hi = ends[i];
         const unsigned n = hi - lo;
-        if (n == 0u) continue;
+        if (n == 0u) { if (lane == 0) kept[i] = 0u; continue; }
         const RohRec* src;
         if (n <= (unsigned)kStitchSmem) {
             for (unsigned j = lane; j < n; j += 32) s_in[warp][j] = recs[lo + j];
@@ -785,20 +799,40 @@ bucket_stitch_kernel(RohRec* __restrict__ recs, RohRec* __restrict__ scratch, co
                 }
                 if (cur.b - cur.a + 1 >= thr) recs[w++] = cur;   // src is a copy: no record still to be read is overwritten
             }
+            kept[i] = w - lo;                                    // the individual's final runs sit at recs[lo, lo + kept)
             for (; w < hi; ++w) recs[w].ind = -1;
         }
         __syncwarp();
     }
 }
 
+// final runs of all individuals, dense and in (individual, start) order: kept_off = exclusive scan of kept[]
+__global__ void __launch_bounds__(128)
+bucket_compact_kernel(const RohRec* __restrict__ recs, const unsigned* __restrict__ ends, const unsigned* __restrict__ kept_off,
+                      int n_ind, RohRec* __restrict__ out, unsigned* __restrict__ total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = blockIdx.x * 4 + warp; i < n_ind; i += gridDim.x * 4) {
+        const unsigned lo = i ? ends[i - 1] : 0u;
+        const unsigned o0 = kept_off[i], o1 = kept_off[i + 1];
+        for (unsigned j = lane; j < o1 - o0; j += 32) out[o0 + j] = recs[lo + j];
+        if (i == n_ind - 1 && lane == 0) *total = o1;
+    }
+}
+
+// in: the walkers' records (arbitrary order) → out: bucketed by individual, ordered, stitched → in: the final runs, dense;
+// *total = their number.  hist: [n_ind + 1] records per individual (by emit_run); kept: [n_ind + 1] scratch.
 cudaError_t launch_bucket_by_individual(RohRec* in, const unsigned* count, unsigned cap, unsigned* hist, int n_ind,
-                                        RohRec* out, int thr, cudaStream_t st)
+                                        RohRec* out, int thr, unsigned* kept, unsigned* total, cudaStream_t st)
 {
     if (!n_ind) return cudaSuccess;
+    const int grid = (n_ind + 3) / 4 < 148 * 8 ? (n_ind + 3) / 4 : 148 * 8;
     bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, n_ind);
     bucket_scatter_kernel<<<148, 256, 0, st>>>(in, count, cap, hist, out);
-    // `in` is free once scattered: the stitch kernel's scratch for buckets too large for shared memory
-    bucket_stitch_kernel<<<(n_ind + 3) / 4 < 148 * 8 ? (n_ind + 3) / 4 : 148 * 8, 128, 0, st>>>(out, in, hist, n_ind, thr);
+    // `in` is free once scattered: the stitch kernel's scratch for buckets too large for shared memory, then the output
+    bucket_stitch_kernel<<<grid, 128, 0, st>>>(out, in, hist, n_ind, thr, kept);
+    bucket_scan_kernel<<<1, 1024, 0, st>>>(kept, n_ind + 1);      // kept[n_ind] = 0 → the total lands there
+    bucket_compact_kernel<<<grid, 128, 0, st>>>(out, hist, kept, n_ind, in, total);
     return cudaGetLastError();
 }
 

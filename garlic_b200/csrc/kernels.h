@@ -57,7 +57,7 @@ cudaError_t launch_thin_windows(const uint64_t* geno, int64_t row_words, const d
                                 double* dump, int64_t dump_stride, const double* gl, int64_t gl_stride, cudaStream_t st);
 cudaError_t launch_fill_f64(double* p, size_t n, double v, cudaStream_t st);
 cudaError_t launch_bucket_by_individual(RohRec* in, const unsigned* count, unsigned cap, unsigned* hist, int n_ind,
-                                        RohRec* out, int thr, cudaStream_t st);
+                                        RohRec* out, int thr, unsigned* kept, unsigned* total, cudaStream_t st);
 cudaError_t launch_tokenize_tped(const char* text, const long long* off, int n_snp, int n_ind, int ind_lo, uint8_t* alleles,
                                  int* nonblank, cudaStream_t st);
 cudaError_t launch_first_allele(const uint8_t* alleles, int n_snp, int n_ind, int ind_offset, int missing,
