@@ -150,6 +150,17 @@ def main():
     ds = synth.make_dataset(seed=17, n_ind=24, chr_sizes=(3000, 2500), n_roh=6)
     run_case("winsize_multi", ds, ["--winsize-multi", "20", "30", "40", "--auto-winsize", "--error", "0.001",
                                   "--kde-subsample", "0"] + SB, keep_kde=True)
+    # 7b. --auto-winsize alone: selectWinsize steps the window size up from --winsize until the KDE is smooth
+    #     (garlic-roh.cpp:766-850); --auto-winsize --weighted: the size comes from the SNP density (:3-9);
+    #     --no-kde-thinning: every window of every individual goes into the KDE (garlic-cli.cpp:171-174)
+    ds = synth.make_dataset(seed=19, n_ind=24, chr_sizes=(3000, 2500), n_roh=6)
+    run_case("auto_winsize", ds, ["--auto-winsize", "--winsize", "20", "--error", "0.001", "--kde-subsample", "0"] + SB,
+             keep_kde=True)
+    run_case("no_kde_thinning", ds, ["--winsize", "30", "--error", "0.001", "--kde-subsample", "0", "--no-kde-thinning"] + SB,
+             keep_kde=True)
+    ds = synth.make_dataset(seed=20, n_ind=24, chr_sizes=(1600, 1400), with_map=True)
+    run_case("auto_winsize_weighted", ds, ["--auto-winsize", "--weighted", "--cm", "--error", "0.001", "--threads", "2",
+                                           "--ld-subsample", "0", "--lod-cutoff", "0.5", "--size-bounds", "0.5", "1.5"])
     # 8. --freq-file: frequencies from a "panel" (differ from the sample's), 30 % of the rows name the other allele
     #    (the program must flip them, garlic-data.cpp:1422), a few rows are 0 / 1 (filtered although polymorphic here)
     ds = synth.make_dataset(seed=18, n_ind=20, chr_sizes=(2000, 1500))

@@ -19,7 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "garlic_b200", "host", "garlic_b200")
 
 CASES = ["lod_0", "lod_1", "lod_2", "lod_3", "lod_small", "lod_cm", "wlod_cm", "wlod_phased", "gl_pl", "gl_gl", "gl_gq",
-         "auto_overlap_hg19", "auto_cutoff", "winsize_multi", "freq_file"]
+         "auto_overlap_hg19", "auto_cutoff", "winsize_multi", "freq_file", "auto_winsize", "no_kde_thinning",
+         "auto_winsize_weighted"]
 
 
 def run_cli(name, tmp, extra=()):
@@ -35,7 +36,8 @@ def run_cli(name, tmp, extra=()):
     return ds, args, r
 
 
-FIXED = [c for c in CASES if c not in ("auto_cutoff", "winsize_multi")]
+KDE_CASES = ("auto_cutoff", "winsize_multi", "auto_winsize", "no_kde_thinning")   # cutoff from the (clock-seeded) FIGTree KDE
+FIXED = [c for c in CASES if c not in KDE_CASES]
 
 
 def _log_value(log, key):
@@ -65,7 +67,7 @@ def test_cli_outputs_match_reference_binary(name):
         assert my_lines == ref_lines
 
 
-@pytest.mark.parametrize("name", ["auto_cutoff", "winsize_multi"])
+@pytest.mark.parametrize("name", ["auto_cutoff", "winsize_multi", "auto_winsize", "no_kde_thinning"])
 def test_cli_auto_cutoff_path(name):
     """KDE → cutoff → ROH → GMM.  FIGTree's transform is clock-seeded inside the library: the REFERENCE BINARY's
     own .kde changes from run to run by ~0.3 % of the peak and its cutoff on `auto_cutoff` flips between two grid
@@ -98,7 +100,8 @@ def test_cli_auto_cutoff_path(name):
         y = got[:, 1]
         assert y[i] <= y[i - 1] and y[i] <= y[i + 1]
         assert y[:i].max() > y[i] and y[i + 1:].max() > y[i]
-        if name == "winsize_multi":
+        if name in ("winsize_multi", "auto_winsize"):      # the window-size search: same sizes tried, same smoothness
+            assert _log_value(log, "Selected window size:") == log_value(name, "Selected window size:")
             ref = [l.split() for l in golden_text(name, "out.log").splitlines() if l.startswith(" ")]
             mine = [l.split() for l in log.splitlines() if l.startswith(" ")]
             assert [m[0] for m in mine] == [x[0] for x in ref]

@@ -186,3 +186,29 @@ def test_cli_two_gpus_raw_lod(name):
     """--raw-lod --gpus 2: every rank dumps the windows of its own individuals, lines in individual order."""
     from tests.test_cli_gpu import check_raw_lod
     check_raw_lod(name, ["--gpus", "2"])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("name", ["winsize_multi", "auto_winsize", "auto_winsize_weighted"])
+def test_cli_two_gpus_window_size_search(name):
+    """The window-size drivers (--winsize-multi … --auto-winsize, --auto-winsize alone, --auto-winsize --weighted)
+    over two GPUs: with the reproducible KDE (--kde-direct) every output file equals the one-GPU run's, so the
+    thinned-window all-gather, the per-size passes and the sharded ROH calling follow the same path."""
+    import os
+    import tempfile
+    from tests.test_cli_gpu import run_cli
+    outs = []
+    for extra in (["--kde-direct"], ["--kde-direct", "--gpus", "2"]):
+        with tempfile.TemporaryDirectory() as tmp:
+            ds, args, r = run_cli(name, tmp, extra=extra)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            files = {}
+            for fn in sorted(os.listdir(tmp)):
+                if fn.startswith("out.") and (fn.endswith(".roh.bed") or fn.endswith(".kde")):
+                    files[fn] = open(os.path.join(tmp, fn)).read()
+            log = [l for l in open(os.path.join(tmp, "out.log")).read().splitlines()[1:] if tmp not in l and "GPU" not in l]
+            outs.append((files, log))
+    assert outs[0][0].keys() == outs[1][0].keys() and any(k.endswith(".roh.bed") for k in outs[0][0])
+    for k in outs[0][0]:
+        assert outs[0][0][k] == outs[1][0][k], k
+    assert outs[0][1] == outs[1][1]
