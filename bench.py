@@ -251,6 +251,7 @@ def main():
     ap.add_argument("--cpu-sample-multi", type=int, default=48, help="individuals per rank in the N>1 parity sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--exact", action="store_true", help="whole-segment chains in pass 2")
+    ap.add_argument("--no-configs", action="store_true", help="skip the full-size C4 / C3 runs that follow the headline at N=1")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 0)
     # exactly one JSON line on stdout: libraries (NCCL prints its version) get stderr
@@ -523,9 +524,32 @@ def main():
             line["parity_vs_cpu_sample"] = "; ".join("rank %d: %s" % (r, x) for r, x in enumerate(allp))
         line["parity_freq_vs_host_counts"] = ("identical freq[] (%d SNPs, counts of all %d ranks' rows)" % (L0, world)) if freq_ok \
             else "MISMATCH in freq[]"
+    g.close()
+    # The other single-GPU configs of BASELINE.json at FULL size, after the headline (N = 1 only): C4 (500 x 10 M,
+    # per-genotype PL likelihoods, W 200: the HBM-bound pass) and C3 (5,000 x 1 M, --weighted wLOD with an LD band over 500
+    # individuals, W 72: the fp64 tensor-core pass), each with its kernel time, roofline and a parity check against the
+    # reference's own functions (tools/run_configs.py).  Data are generated on the device.
+    if rank == 0 and world == 1 and not a.no_configs and not a.no_cpu and (n_ind, L0) == (CFG["n_ind"], CFG["n_loci"]):
+        del rows_dev
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        cfgs = {}
+        try:
+            import run_configs
+            for key, fn, args_ in (("c4", run_configs.c4, (500, 10_000_000)), ("c3", run_configs.c3, (5000, 1_000_000, 500, False))):
+                t0 = time.perf_counter()
+                try:
+                    r = fn(*args_)
+                    r["wall_s"] = round(time.perf_counter() - t0, 1)
+                    cfgs[key] = r
+                except Exception as e:          # the headline line must survive a failure here
+                    cfgs[key] = dict(error=repr(e)[:300])
+                torch.cuda.empty_cache()
+        except Exception as e:
+            cfgs["error"] = repr(e)[:300]
+        line["configs"] = cfgs
     if rank == 0:
         emit(line)
-    g.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -5,6 +5,7 @@ fit one GPU comfortably, with a parity check of a few individuals against the re
 
     python tools/run_configs.py [c3] [c4] [c5]
 """
+import ctypes
 import json
 import os
 import sys
@@ -51,6 +52,13 @@ def setup(n_ind, L0, seed):
 def oracle_sample(rows, n_s, L0, keep, freq, pos0, chr_off0, names, cens):
     codes = bench.unpack_rows(rows[:n_s].cpu().numpy(), L0)
     return bench.cpu_chroms(codes, keep, freq, pos0, chr_off0, names, cens)
+
+
+def bench_peak_hbm():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
 
 
 def units_of(chr_off, W, n):
@@ -104,7 +112,7 @@ def c4(n_ind=500, L0=2_000_000):
     del idx
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
-    g._ck(g.lib.garlic_gpu_put_gl_dev(g.h, bench.C_void(gl.data_ptr()), 2))
+    g._ck(g.lib.garlic_gpu_put_gl_dev(g.h, ctypes.c_void_p(gl.data_ptr()), 2))
     n_s = min(16 if L0 > 4_000_000 else 40, n_ind)
     gl_sample = gl[:n_s].cpu().numpy()
     del gl
@@ -125,6 +133,11 @@ def c4(n_ind=500, L0=2_000_000):
                         units_per_s_kernel=st["units"] / (st["kernel_ms"] / 1e3),
                         hbm_gbs_algorithmic=st["units"] * bytes_unit / (st["kernel_ms"] / 1e3) / 1e9,
                         hbm_gbs_at_8_bytes=st["units"] * 8.0 / (st["kernel_ms"] / 1e3) / 1e9, ambiguous=st["ambiguous_pairs"])
+    peak = bench_peak_hbm()
+    res["pass2"]["roofline"] = dict(bound="hbm", unit="GB/s", achieved=res["pass2"]["hbm_gbs_at_8_bytes"], peak=peak,
+                                    frac=res["pass2"]["hbm_gbs_at_8_bytes"] / peak,
+                                    algorithmic="8 bytes (one fp64 per-genotype LOD) per individual-window",
+                                    peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy)")
     codes = bench.unpack_rows(rows[:n_s].cpu().numpy(), L0)
     chroms = bench.cpu_chroms(codes, keep.copy(), freq.copy(), pos0, chr_off0, names, cens)
     glh = orc.gl_error(gl_sample, "PL")
@@ -142,7 +155,10 @@ def c4(n_ind=500, L0=2_000_000):
     return res
 
 
-def c3(n_ind=5000, L0=200_000, n_ld=500):
+FP64_DMMA_PEAK = 37.1   # TFLOP/s, mma.sync.m8n8k4.f64 on this pool's B200 (tools/fp64_peak.cu, profiles/r01m)
+
+
+def c3(n_ind=5000, L0=200_000, n_ld=500, exact_check=True):
     """C3 at reduced L: --weighted wLOD with hr2 LD band over an LD subsample, --cm, W=72."""
     g, rows, names, chr_off0, pos0, cens = setup(n_ind, L0, 3)
     cen_arr = np.array([cens["chr" + nm] for nm in names], np.int32)
@@ -170,17 +186,51 @@ def c3(n_ind=5000, L0=200_000, n_ld=500):
     res["pass2_wlod"] = dict(ms=ms, kernel_ms=st["kernel_ms"], roh=len(roh), units=st["units"],
                              units_per_s_kernel=st["units"] / (st["kernel_ms"] / 1e3),
                              fp64_gflops=st["units"] * 2 * W / (st["kernel_ms"] / 1e3) / 1e9, ambiguous=st["ambiguous_pairs"])
-    # the tensor-core pass against exact mul-then-add sums on the same handle (whole result, every individual)
-    roh_exact, ms_x = timed(g, lambda: g.call_roh(W, 1.0, 0.25, weighted=True, exact=True), reps=1)
-    res["exact_kernel_ms"] = g.last_stats()["kernel_ms"]
-    res["parity_all_individuals"] = "tensor-core pass == exact sums (%d ROH)" % len(roh) if np.array_equal(roh, roh_exact) else "MISMATCH"
+    res["pass2_wlod"]["roofline"] = dict(bound="tensor", unit="TFLOP/s", achieved=res["pass2_wlod"]["fp64_gflops"] / 1e3, peak=FP64_DMMA_PEAK,
+                                         frac=res["pass2_wlod"]["fp64_gflops"] / 1e3 / FP64_DMMA_PEAK,
+                                         peak_source="fp64 mma.sync m8n8k4 peak measured on this pool by tools/fp64_peak.cu (no fp64 entry in MEASURED_PEAKS.json)")
+    if exact_check:
+        # the tensor-core pass against exact mul-then-add sums on the same handle (whole result, every individual)
+        roh_exact, ms_x = timed(g, lambda: g.call_roh(W, 1.0, 0.25, weighted=True, exact=True), reps=1)
+        res["exact_kernel_ms"] = g.last_stats()["kernel_ms"]
+        res["parity_all_individuals"] = "tensor-core pass == exact sums (%d ROH)" % len(roh) if np.array_equal(roh, roh_exact) else "MISMATCH"
+    # … and against the REFERENCE's own functions (calculateGenoFreq + calcHR2LD + calcwLODWindows + assembleROHWindows,
+    # oracle/_ref/ref_driver) on the last chromosomes (as many as keep the reference's L·W²·n_LD pair loop at about a
+    # minute of host time): every individual, the same LD individuals, bit-identical ROH required
+    from oracle import refdrv
+    if refdrv.available():
+        budget, c0 = 30_000, C
+        while c0 > 0 and (chr_off[C] - chr_off[c0 - 1]) <= budget:
+            c0 -= 1
+        c0 = min(c0, C - 1)
+        chroms = []
+        keep_h, freq_h = keep.copy(), freq.copy()
+        for c in range(c0, C):
+            lo0, hi0 = int(chr_off0[c]), int(chr_off0[c + 1])
+            b0, b1 = lo0 // 4, (hi0 + 3) // 4
+            sub = rows[:, b0:b1].cpu().numpy()
+            codes = bench.unpack_rows(sub, (b1 - b0) * 4)[:, lo0 - 4 * b0:hi0 - 4 * b0]
+            k = keep_h[lo0:hi0]
+            lo, hi = int(chr_off[c]), int(chr_off[c + 1])
+            chroms.append(dict(name="chr" + names[c], cen=cens["chr" + names[c]], pos=np.ascontiguousarray(pos[lo:hi]),
+                               freq=np.ascontiguousarray(freq_h[lo0:hi0][k]), gpos=np.ascontiguousarray(gpos[lo:hi]), gl=None,
+                               geno=np.ascontiguousarray(codes[:, k].T.astype(np.int8))))
+        t0 = time.perf_counter()
+        out = refdrv.run(chroms, n_ind, W, 0.001, cutoff=1.0, overlap_frac=0.25, weighted=True, cm=True, mu=1e-9, M=7,
+                         threads=min(32, os.cpu_count() or 1), ld_individuals=ld_ind, dump_windows=False)
+        want = sorted((r[0], r[1] + c0, r[2], r[3]) for r in out["roh"])
+        got = sorted((int(r[0]), int(r[1]), int(pos[r[2]]), int(pos[r[3]])) for r in roh if r[1] >= c0)
+        n_snps = int(chr_off[C] - chr_off[c0])
+        res["parity_vs_reference_functions"] = (
+            "identical ROH (%d) on chromosomes %s (%d SNPs), all %d individuals, LD over the same %d individuals; reference "
+            "calcHR2LD + calcwLODWindows + assembleROHWindows took %.1f s on the host" % (
+                len(got), "+".join(names[c0:]), n_snps, n_ind, n_ld, time.perf_counter() - t0)) if got == want else \
+            "MISMATCH: gpu %d vs reference %d ROH on chromosomes %s" % (len(got), len(want), "+".join(names[c0:]))
     g.close()
     return res
 
 
 if __name__ == "__main__":
-    import ctypes
-    bench.C_void = ctypes.c_void_p
     # e.g.  c4   c4:500:10000000   c3:5000:1000000   c5:12500:600000   (name[:individuals[:SNPs]])
     which = sys.argv[1:] or ["c5", "c4", "c3"]
     for w in which:
