@@ -373,9 +373,8 @@ def main():
         if not resident:
             g.put_packed(rows_host_np)                       # H2D from pinned host memory
             t0 = lap("put_packed_h2d", t0)
-        g.count_packed()                                     # K2
-        t0 = lap("count_packed", t0)
-        t0 = lap("allreduce_counts", t0)
+        g.count_packed()                                     # K2; N>1: + the all-reduce of the allele counters, in stream order
+        t0 = lap("count_packed_allreduce" if dist is not None else "count_packed", t0)
         freq, keep, L = g.filter()                           # freq, keep mask -> host; K3 compaction
         t0 = lap("filter_compact", t0)
         g.set_tables(err, max_gap, cen_arr)                  # K4
@@ -432,6 +431,22 @@ def main():
     phases["on"] = 1                                         # one extra, untimed step with a sync after each call
     step(False)
     phases.pop("on")
+    # how much the headline depends on the cutoff: pass-2 kernel time and candidate fraction at three cutoffs and
+    # with the pruning bound switched off (every pair walked) — same data, same tables, pass 2 only
+    sens = {}
+    if rank == 0:
+        def p2(c):
+            for _ in range(2):
+                r = g.call_roh(W, c, ov)
+            st = g.last_stats()
+            return dict(kernel_ms=round(st["kernel_ms"], 4), roh=len(r),
+                        candidate_pair_fraction=(st["candidate_pairs"] / st["all_pairs"]) if st["candidate_pairs"] >= 0 else None)
+        for c in (0.0, 1.0, 2.0):
+            sens["cutoff_%g" % c] = p2(c)
+        g.set_prune(False)
+        sens["pruning_off_cutoff_%g" % cutoff] = p2(cutoff)
+        g.set_prune(True)
+        sens["note"] = "pass-2 kernels only (selection + walker); the compaction + bound pass (roofline.kernel_ms) does not depend on the cutoff"
 
     # roofline of the dominant kernel: the fused compaction + pruning-bound pass (squeeze_bound_kernel, K3 + the bound of
     # K5 pass 2), timed live with CUDA events on the library's stream around its launch in every step.  Algorithmic
@@ -473,7 +488,7 @@ def main():
                 ms_per_step=ms_res / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                 data="synthetic", config=config, e2e=e2e, gpu_launches=int(launches), roofline=roofline,
                 clocks=clocks, host_cores_bound_per_rank=int(near), roh_found=int(n_roh), loci_used=int(Lk), ambiguous_pairs_reevaluated=int(n_amb),
-                individual_windows_per_step=int(units_total),
+                individual_windows_per_step=int(units_total), pruning_sensitivity=sens,
                 phases_ms_one_synchronised_step={k: round(v, 3) for k, v in phases.items()})
 
     # cpu_baseline: rank 0, N=1 only, bounded sample of the same workload; the same run doubles as the parity check.

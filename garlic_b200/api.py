@@ -27,7 +27,7 @@ EXPORTS = [
     "garlic_gpu_ld_band", "garlic_gpu_set_wlod", "garlic_gpu_window_slots", "garlic_gpu_windows",
     "garlic_gpu_windows_dev", "garlic_gpu_windows_gather", "garlic_gpu_comm_id", "garlic_gpu_comm_init",
     "garlic_gpu_call_roh", "garlic_gpu_last_stats", "garlic_gpu_n_kept", "garlic_gpu_get_kept_index",
-    "garlic_gpu_get_genotypes", "garlic_gpu_get_piece_bounds",
+    "garlic_gpu_get_genotypes", "garlic_gpu_get_piece_bounds", "garlic_gpu_set_prune",
 ]
 
 
@@ -305,6 +305,9 @@ class GarlicGPU:
         self.lib.garlic_gpu_last_stats(self.h, s)
         return dict(items=s[0], units=s[1], ambiguous_pairs=s[2], kernel_ms=s[3], select_ms=s[4],
                     candidate_pairs=s[5], all_pairs=s[6], squeeze_ms=s[7])
+
+    def set_prune(self, on=True):
+        self._ck(self.lib.garlic_gpu_set_prune(self.h, C.c_int(int(on))))
 
     def piece_bounds(self, W):
         """uint32[n_pieces, n_ind]: the pruning bound's piece maxima (low / high int16, 1/64 LOD)."""

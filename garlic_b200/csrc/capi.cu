@@ -115,7 +115,9 @@ struct garlic_gpu {
     bool wlod_mma = true;          // GARLIC_NO_MMA=1: weighted pass 2 with the exact kernel only
     ncclComm_t comm = nullptr;     // one rank per GPU, individuals sharded across ranks
     int comm_rank = 0, comm_world = 1;
-    bool counts_reduced = false;   // d_counts already holds the sum over all ranks
+    // d_counts = [nalleles, total, hom, nonmiss] x L0.  Across ranks the first two rows (what freq and the filter need)
+    // are summed as soon as the local counts exist; the other two (homFreq: only --weighted) when the LD band asks
+    bool counts_reduced = false, counts_hi_reduced = false;
     double* d_gather = nullptr;    // all-gathered thinned windows
     cudaEvent_t ev2 = nullptr;
     cudaStream_t copy_stream = nullptr;   // device-to-host copies that overlap the kernels behind them (filter)
@@ -193,6 +195,31 @@ static double lod_bound(const garlic_gpu* h)
     if (h->fmin > 0 && h->fmin < fmin) fmin = h->fmin;
     const double emin = h->have_gl ? 1e-16 : ((h->error > 0 && h->error < 1) ? h->error : 1e-16);
     return std::max(-std::log10(emin), -std::log10(fmin)) + 1.0;
+}
+
+#define NCK(call)                                                                             \
+    do {                                                                                      \
+        ncclResult_t r_ = (call);                                                             \
+        if (r_ != ncclSuccess) {                                                              \
+            h->err = std::string(#call) + ": " + ncclGetErrorString(r_);                      \
+            return 1;                                                                         \
+        }                                                                                     \
+    } while (0)
+
+// the path's one data collective, stream-ordered on the library's stream: every rank calls it at the same
+// points of the call sequence (count_packed / filter; ld_band / get_hom_freq for the second half)
+static int reduce_counts(garlic_gpu* h, bool hi)
+{
+    if (!h->comm) return 0;
+    if (!h->counts_reduced) {
+        NCK(ncclAllReduce(h->d_counts, h->d_counts, (size_t)2 * h->L0, ncclInt32, ncclSum, h->comm, h->stream));
+        h->counts_reduced = true;
+    }
+    if (hi && !h->counts_hi_reduced) {
+        NCK(ncclAllReduce(h->d_counts + 2 * h->L0, h->d_counts + 2 * h->L0, (size_t)2 * h->L0, ncclInt32, ncclSum, h->comm, h->stream));
+        h->counts_hi_reduced = true;
+    }
+    return 0;
 }
 
 static bool is_pinned(const void* p)
@@ -286,15 +313,6 @@ void* garlic_gpu_host_alloc(size_t bytes)
     return p;
 }
 void garlic_gpu_host_free(void* p) { if (p) cudaFreeHost(p); }
-
-#define NCK(call)                                                                             \
-    do {                                                                                      \
-        ncclResult_t r_ = (call);                                                             \
-        if (r_ != ncclSuccess) {                                                              \
-            h->err = std::string(#call) + ": " + ncclGetErrorString(r_);                      \
-            return 1;                                                                         \
-        }                                                                                     \
-    } while (0)
 
 int garlic_gpu_comm_id(uint8_t* id128)
 {
@@ -410,7 +428,7 @@ int garlic_gpu_code_alleles(garlic_gpu_t* h)
     CK(cudaSetDevice(h->device));
     if (!h->d_alleles) FAIL("code_alleles: no alleles uploaded");
     const int missing = h->missing_char;
-    h->counts_reduced = false;
+    h->counts_reduced = false; h->counts_hi_reduced = false;
     // the "1" allele is the first non-missing character over ALL individuals: MIN over the shards' keys
     if (h->comm) NCK(ncclAllReduce(h->d_key, h->d_key, (size_t)h->L0, ncclUint64, ncclMin, h->comm, h->stream));
     CK(cudaMemsetAsync(h->d_counts, 0, (size_t)4 * h->L0 * sizeof(int), h->stream));
@@ -452,7 +470,7 @@ static int put_packed_common(garlic_gpu* h, const void* rows, int64_t stride, cu
         }
         CK(cudaStreamSynchronize(h->copy_stream));                          // the caller may reuse its buffer
         h->precounted = true;
-        h->counts_reduced = false;
+        h->counts_reduced = false; h->counts_hi_reduced = false;
         h->have_geno0 = true;
         return 0;
     }
@@ -485,7 +503,7 @@ int garlic_gpu_count_packed(garlic_gpu_t* h, const int32_t* nalleles_corr, const
 {
     CK(cudaSetDevice(h->device));
     if (!h->have_geno0) FAIL("count_packed: no genotypes loaded");
-    h->counts_reduced = false;
+    h->counts_reduced = false; h->counts_hi_reduced = false;
     if (h->precounted) {
         h->precounted = false;             // garlic_gpu_put_packed counted the rows while they arrived
     } else {
@@ -502,7 +520,7 @@ int garlic_gpu_count_packed(garlic_gpu_t* h, const int32_t* nalleles_corr, const
         h->launches++;
         CK(cudaStreamSynchronize(h->stream));                          // the caller may reuse its vectors
     }
-    return 0;
+    return reduce_counts(h, false);        // starts right behind the count kernel; filter() finds the sums ready
 }
 
 void* garlic_gpu_counts_dev(garlic_gpu_t* h) { return h ? (void*)h->d_counts : nullptr; }
@@ -585,10 +603,7 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
         CK(cudaMemcpyAsync(h->d_keep, keep, L0, cudaMemcpyHostToDevice, h->stream));
     } else {
         // the one data-path collective: per-SNP counters of all shards, summed in place on this stream
-        if (h->comm && !h->counts_reduced) {
-            NCK(ncclAllReduce(h->d_counts, h->d_counts, (size_t)4 * L0, ncclInt32, ncclSum, h->comm, h->stream));
-            h->counts_reduced = true;
-        }
+        if (reduce_counts(h, false)) return 1;
         LAUNCH(launch_freq_keep(h->d_counts, L0, h->d_pos0, h->d_chr_of0, h->d_chr_param, oob, h->d_freq0, h->d_keep, h->stream));
         // page-locked caller buffers (garlic_gpu_host_alloc) are written by the copy engine directly
         freq_direct = freq_out && is_pinned(freq_out);
@@ -786,6 +801,7 @@ int garlic_gpu_get_hom_freq(garlic_gpu_t* h, double* hom_freq)
     CK(cudaSetDevice(h->device));
     if (!h->filtered) FAIL("get_hom_freq: call filter first");
     std::vector<int> hom(h->L0), nm(h->L0);
+    if (reduce_counts(h, true)) return 1;      // (with a communicator attached: a collective, every rank calls it)
     if (garlic_gpu_get_counts(h, nullptr, nullptr, hom.data(), nm.data())) return 1;
     if (fetch_src(h)) return 1;
     for (int64_t d = 0; d < h->L; ++d) {
@@ -793,6 +809,12 @@ int garlic_gpu_get_hom_freq(garlic_gpu_t* h, double* hom_freq)
         fh /= total;   // 0/0 → NaN exactly as the reference (garlic-data.cpp:672)
         hom_freq[d] = fh;
     }
+    return 0;
+}
+
+int garlic_gpu_set_prune(garlic_gpu_t* h, int on)
+{
+    h->prune = on != 0;
     return 0;
 }
 
@@ -1375,6 +1397,7 @@ int garlic_gpu_ld_band(garlic_gpu_t* h, int winsize, const int32_t* ld_individua
     if (upload_indlist(h, ld_individuals, n_ld)) return 1;
     Laps laps("ld_band");
     // homFreq over ALL individuals from the reduced counts (garlic-data.cpp:656-676)
+    if (reduce_counts(h, true)) return 1;
     if (dev_alloc(h, &h->d_homf, (size_t)L)) return 1;
     LAUNCH(launch_hom_freq(h->d_counts, h->L0, h->d_src, L, h->d_homf, h->stream));
     // zero-padded weight rows (wlod.h); rows of windows that do not exist stay all-zero

@@ -126,7 +126,8 @@ int garlic_gpu_set_tables(garlic_gpu_t *h, double error, int max_gap, const int3
  * it to evaluate lod() with the host libm, so whole-segment chains are bit-identical to the reference's */
 int garlic_gpu_set_lut(garlic_gpu_t *h, const double *lut);
 int garlic_gpu_get_lut(garlic_gpu_t *h, double *lut);
-/* homFreq per kept SNP (calculateGenoFreq) from the reduced counts */
+/* homFreq per kept SNP (calculateGenoFreq) from the reduced counts.  With a communicator attached this sums the
+ * hom / non-missing counters across ranks first (a collective: every rank calls it, as with garlic_gpu_ld_band) */
 int garlic_gpu_get_hom_freq(garlic_gpu_t *h, double *hom_freq);
 
 /* ---- K6: calcLDData / calcHR2LD (src/garlic-data.cpp:330-424,474-527,558-583) ---------------
@@ -166,6 +167,8 @@ int garlic_gpu_windows_gather(garlic_gpu_t *h, int winsize, int step, int weight
  * cutoff (same ROH as exact), 1 = whole-segment chains everywhere. */
 int garlic_gpu_call_roh(garlic_gpu_t *h, int winsize, double cutoff, double overlap_frac, int weighted,
                         int exact, garlic_roh_t *out, int64_t cap, int64_t *count);
+/* pruning bound of pass 2 on (default) / off: off walks every (individual, item) pair — same ROH, for measurements */
+int garlic_gpu_set_prune(garlic_gpu_t *h, int on);
 /* statistics of the last call_roh, 8 doubles: [0] items, [1] individual-windows decided (N·Σ_c(L_c-W+1)),
  * [2] ambiguous (individual, segment) pairs re-evaluated exactly, [3] kernel milliseconds of pass 2 (candidate
  * selection + walker), [4] of which selection, [5] (individual, item) pairs that went to the walker (-1: no
