@@ -27,7 +27,7 @@ EXPORTS = [
     "garlic_gpu_ld_band", "garlic_gpu_set_wlod", "garlic_gpu_window_slots", "garlic_gpu_windows",
     "garlic_gpu_windows_dev", "garlic_gpu_windows_gather", "garlic_gpu_comm_id", "garlic_gpu_comm_init",
     "garlic_gpu_call_roh", "garlic_gpu_last_stats", "garlic_gpu_n_kept", "garlic_gpu_get_kept_index",
-    "garlic_gpu_get_genotypes", "garlic_gpu_get_piece_bounds", "garlic_gpu_set_prune",
+    "garlic_gpu_get_genotypes", "garlic_gpu_get_piece_bounds", "garlic_gpu_set_prune", "garlic_gpu_kde", "garlic_gpu_put_tgls_text",
 ]
 
 
@@ -171,6 +171,16 @@ class GarlicGPU:
         self._ck(self.lib.garlic_gpu_put_gl(self.h, _p(v), C.c_int(GL_TYPES[gl_type])))
 
     # ---------------------------------------------------------------- filter / tables
+    def put_tgls_text(self, text: bytes, line_off, gl_type, snp0=0):
+        """K0-GL: tgls value columns from raw text (what follows the 4th field of each line).  → tokens per line."""
+        t = {"GQ": 0, "GL": 1, "PL": 2, None: -1}[gl_type] if not isinstance(gl_type, int) else gl_type
+        off = np.ascontiguousarray(line_off, np.int64)
+        n = len(off) - 1
+        ntok = np.zeros(n, np.int32)
+        buf = np.frombuffer(text, np.uint8)
+        self._ck(self.lib.garlic_gpu_put_tgls_text(self.h, _p(buf), _p(off), C.c_int64(snp0), C.c_int(n), C.c_int(t), _p(ntok)))
+        return ntok
+
     def filter(self, oob=False, chr_param=None, freq_override=None, want_freq=True, want_keep=True):
         """→ (freq float64[L0], keep bool[L0], L).  The two arrays are views of buffers owned by this object and
         are overwritten by the next filter() call (repeated runs then touch no fresh pages)."""
@@ -272,6 +282,18 @@ class GarlicGPU:
                                                     C.c_int(len(idx)), C.c_int(rows_per_rank), C.c_int(int(exact)),
                                                     _p(self._gather_buf)))
         return self._gather_buf
+
+    def kde(self, values=None, m=512):
+        """computeKDE (garlic-kde.cpp:14-101) on the device, of `values` or — None — of the window matrix the last
+        windows / windows_dev / windows_gather call left on the GPU.  → (x[m], y[m] normalised as the reference's
+        .kde, n, bandwidth)."""
+        v = None if values is None else np.ascontiguousarray(values, np.float64)
+        x, y = np.empty(m, np.float64), np.empty(m, np.float64)
+        n, h = C.c_int64(0), C.c_double(0)
+        self._ck(self.lib.garlic_gpu_kde(self.h, _p(v), C.c_int64(0 if v is None else v.size), C.c_int(m), _p(x), _p(y),
+                                         C.byref(n), C.byref(h)))
+        y = y / (y.sum() * (x[1] - x[0]))                       # garlic-kde.cpp:86-95
+        return x, y, n.value, h.value
 
     @staticmethod
     def comm_id():

@@ -60,6 +60,7 @@ struct garlic_gpu {
     char* d_text = nullptr;           // K0 staging: raw tped line tails, their offsets, non-blank counts
     long long* d_textoff = nullptr;
     int* d_nonblank = nullptr;
+    int2* d_hard = nullptr;           // K0-GL: tokens the device conversion leaves to strtod
     StitchScratch stitch_scratch;     // host buffers of call_roh kept between calls
     std::vector<RohRec> recs_buf, ambs_buf, merged_buf, tmp_buf;
     uint64_t* d_ldplanes = nullptr;   // LD scratch: bit-planes and the ordered pair matrix (kept between calls)
@@ -119,6 +120,9 @@ struct garlic_gpu {
     // are summed as soon as the local counts exist; the other two (homFreq: only --weighted) when the LD band asks
     bool counts_reduced = false, counts_hi_reduced = false;
     double* d_gather = nullptr;    // all-gathered thinned windows
+    const double* kde_src = nullptr;   // the window matrix the last pass-1 call left on the device (garlic_gpu_kde)
+    int64_t kde_src_n = 0;
+    double *d_kde = nullptr, *d_kde_in = nullptr;   // scratch of the device KDE; uploaded host values
     cudaEvent_t ev2 = nullptr;
     cudaStream_t copy_stream = nullptr;   // device-to-host copies that overlap the kernels behind them (filter)
     cudaEvent_t ev_copy = nullptr;
@@ -298,7 +302,7 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     if (h->ev_sq0) cudaEventDestroy(h->ev_sq0);
     if (h->ev_sq1) cudaEventDestroy(h->ev_sq1);
     if (h->comm) ncclCommDestroy(h->comm);
-    dev_free(h->d_gather); dev_free(h->d_corr);
+    dev_free(h->d_gather); dev_free(h->d_corr); dev_free(h->d_kde); dev_free(h->d_kde_in); dev_free(h->d_hard);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -558,6 +562,79 @@ static int put_gl_common(garlic_gpu* h, const void* v, int gl_type, cudaMemcpyKi
     h->have_gl = true;
     return 0;
 }
+int garlic_gpu_put_tgls_text(garlic_gpu_t* h, const char* text, const int64_t* line_off, int64_t snp0, int n_snp,
+                             int gl_type, int32_t* n_tokens)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->L0) FAIL("put_tgls_text: call set_shape first");
+    if (gl_type < -1 || gl_type > 2) FAIL("put_tgls_text: bad gl_type");
+    if (snp0 < 0 || n_snp < 0 || snp0 + n_snp > h->L0) FAIL("put_tgls_text: bad SNP range");
+    if (n_snp == 0) return 0;
+    const int64_t bytes = line_off[n_snp] - line_off[0];
+    if (bytes < 0) FAIL("put_tgls_text: line offsets must ascend");
+    if (dev_alloc(h, &h->d_gl0, (size_t)h->n_ind * h->L0)) return 1;
+    if (dev_alloc(h, &h->d_text, (size_t)bytes + 16)) return 1;
+    if (dev_alloc(h, &h->d_textoff, (size_t)n_snp + 1)) return 1;
+    if (dev_alloc(h, &h->d_nonblank, (size_t)n_snp)) return 1;
+    const unsigned hard_cap = 1u << 16;
+    if (dev_alloc(h, &h->d_hard, (size_t)hard_cap + 1)) return 1;
+    unsigned* d_hard_n = reinterpret_cast<unsigned*>(h->d_hard + hard_cap);
+    std::vector<long long> rel(n_snp + 1);
+    for (int i = 0; i <= n_snp; ++i) rel[i] = (long long)(line_off[i] - line_off[0]);
+    const char* base = text + line_off[0];
+    CK(cudaMemcpyAsync(h->d_text, base, (size_t)bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_textoff, rel.data(), rel.size() * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(d_hard_n, 0, sizeof(unsigned), h->stream));
+    LAUNCH(launch_tokenize_tgls(h->d_text, h->d_textoff, n_snp, h->n_ind, h->ind_offset, h->d_gl0, h->L0, snp0, h->d_nonblank,
+                                h->d_hard, d_hard_n, hard_cap, h->stream));
+    std::vector<int32_t> ntok_local;
+    if (!n_tokens) { ntok_local.resize(n_snp); n_tokens = ntok_local.data(); }
+    unsigned n_hard = 0;
+    CK(cudaMemcpyAsync(n_tokens, h->d_nonblank, (size_t)n_snp * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&n_hard, d_hard_n, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // the caller may reuse its text buffer
+    if (n_hard) {
+        // tokens outside the exact fast path: converted here with strtod, exactly what the host reader does.  More of them
+        // than the list holds: every token of this rank's columns is converted on the host (correct, only slow).
+        auto token_at = [&](int l, int k) -> const char* {
+            const char* p = base + rel[l];
+            const char* e = base + rel[l + 1];
+            for (int t = 0;; ++t) {
+                while (p < e && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n')) ++p;
+                if (p >= e) return nullptr;
+                if (t == k) return p;
+                while (p < e && !(*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n')) ++p;
+            }
+        };
+        auto convert = [&](const char* p, int l) -> double {
+            const char* e = base + rel[l + 1];
+            const char* q = p;
+            while (q < e && !(*q == ' ' || *q == '\t' || *q == '\r' || *q == '\n')) ++q;
+            const std::string tok(p, q);                                   // strtod needs a terminated string
+            return strtod(tok.c_str(), nullptr);
+        };
+        std::vector<int2> list;
+        if (n_hard <= hard_cap) {
+            list.resize(n_hard);
+            CK(cudaMemcpy(list.data(), h->d_hard, n_hard * sizeof(int2), cudaMemcpyDeviceToHost));
+        } else {
+            for (int l = 0; l < n_snp; ++l)
+                for (int k = h->ind_offset; k < h->ind_offset + h->n_ind; ++k) list.push_back(make_int2(l, k));
+        }
+        std::sort(list.begin(), list.end(), [](const int2& a, const int2& b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+        for (const int2& t : list) {
+            const char* p = token_at(t.x, t.y);
+            if (!p) continue;
+            const double v = convert(p, t.x);
+            CK(cudaMemcpyAsync(h->d_gl0 + (size_t)(t.y - h->ind_offset) * h->L0 + snp0 + t.x, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));                          // v lives on this stack frame
+        }
+    }
+    h->gl_type = gl_type;
+    h->have_gl = true;
+    return 0;
+}
+
 int garlic_gpu_put_gl(garlic_gpu_t* h, const double* values, int gl_type) { return put_gl_common(h, values, gl_type, cudaMemcpyHostToDevice); }
 int garlic_gpu_put_gl_dev(garlic_gpu_t* h, const void* values_dev, int gl_type) { return put_gl_common(h, values_dev, gl_type, cudaMemcpyDeviceToDevice); }
 
@@ -1024,6 +1101,7 @@ int garlic_gpu_windows_gather(garlic_gpu_t* h, int winsize, int step, int weight
     if (n > 0) CK(cudaMemcpyAsync(send, dptr, (size_t)n * slots * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     if (h->comm) NCK(ncclAllGather(send, h->d_gather, blk, ncclDouble, h->comm, h->stream));
     else CK(cudaMemcpyAsync(h->d_gather, send, blk * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    h->kde_src = h->d_gather; h->kde_src_n = (int64_t)(blk * h->comm_world);
     const size_t bytes = blk * h->comm_world * sizeof(double);
     const bool direct = is_pinned(out);
     const bool staged = !direct && bytes <= ((size_t)64 << 20) && !pin_alloc(h, bytes);
@@ -1091,6 +1169,7 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
     CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
     rc = launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, false, true, items_tile_snps(items, W));
     }
+    if (!rc) { h->kde_src = d_dump; h->kde_src_n = (int64_t)n_lanes * slots; }
     if (!rc && out_dev) {
         *out_dev = d_dump;
         cudaError_t e = cudaStreamSynchronize(h->stream);
@@ -1104,6 +1183,39 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
         else if (staged) memcpy(out, h->pin, bytes);
     }
     return rc;
+}
+
+int garlic_gpu_kde(garlic_gpu_t* h, const double* values, int64_t n_values, int m_targets, double* x, double* y,
+                   int64_t* n_used, double* bandwidth)
+{
+    CK(cudaSetDevice(h->device));
+    if (m_targets < 2 || m_targets > 1024) FAIL("kde: number of targets out of range [2,1024]");
+    if (!x || !y) FAIL("kde: null output");
+    const double* src = h->kde_src;
+    int64_t n = h->kde_src_n;
+    if (values) {
+        if (n_values < 1) FAIL("kde: no values");
+        if (dev_alloc(h, &h->d_kde_in, (size_t)n_values)) return 1;
+        CK(cudaMemcpyAsync(h->d_kde_in, values, (size_t)n_values * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        src = h->d_kde_in; n = n_values;
+    }
+    if (!src || n < 1) FAIL("kde: no window matrix on the device (call garlic_gpu_windows first, or pass values)");
+    if (dev_alloc(h, &h->d_kde, kde_scratch_doubles(m_targets))) return 1;
+    double* d_res = nullptr;
+    int launches = 0;
+    CK(launch_kde(src, (long long)n, m_targets, h->d_kde, &d_res, &launches, h->stream));
+    h->launches += launches;
+    const size_t bytes = (size_t)(8 + 2 * m_targets) * sizeof(double);
+    if (pin_alloc(h, bytes)) return 1;
+    CK(cudaMemcpyAsync(h->pin, d_res, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const double* r = reinterpret_cast<const double*>(h->pin);
+    if (n_used) *n_used = (int64_t)r[0];
+    if (bandwidth) *bandwidth = r[5];
+    if (r[0] < 2) FAIL("kde: fewer than two valid window values");
+    memcpy(x, r + 8, (size_t)m_targets * sizeof(double));
+    memcpy(y, r + 8 + m_targets, (size_t)m_targets * sizeof(double));
+    return 0;
 }
 
 int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double overlap_frac, int weighted, int exact,

@@ -1386,7 +1386,34 @@ __device__ __forceinline__ double gl_to_error(double gl, int type)
 // (common.cuh:gl_lane): out[group][d][lane].  A CTA transposes a tile of 32 individuals x 64 kept SNPs through shared
 // memory: reads run along the SNP axis of the caller's individual-major matrix, writes are whole 16 KB slabs.
 // Covers d in [0, out_stride) and all 32 lanes of the last group: pad SNPs and absent individuals are written as 0.
+//
+// The error transform is a pow() per genotype, and likelihood files hold few distinct values (phred-scaled integers):
+// every warp keeps a direct-mapped memo of (raw value -> error) in shared memory, filled with the results of the same
+// gl_to_error() call, so a hit returns bit for bit what the call would.  One lane per slot writes (match_any), the
+// warp synchronises between the write and the next probe: no torn entries.  All-distinct data only pay the probe.
 constexpr int kGlTile = 64;
+constexpr int kGlMemo = 128;                // entries per warp (16 B each): 8 warps x 2 KB
+struct GlMemoEntry { unsigned long long key; double val; };
+
+__device__ __forceinline__ double gl_error_memo(double raw, int type, bool on, GlMemoEntry* memo)
+{
+    // every lane of the warp calls this (inactive ones with on = false)
+    const unsigned long long key = (unsigned long long)__double_as_longlong(raw);
+    const unsigned slot = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 57);       // 7 bits
+    const GlMemoEntry e = memo[slot];
+    const bool hit = on && e.key == key;
+    double v = e.val;
+    const bool miss = on && !hit;
+    if (__any_sync(0xffffffffu, miss)) {
+        if (miss) v = gl_to_error(raw, type);
+        // one writer per slot: the lowest missing lane among those that map to it
+        const unsigned peers = __match_any_sync(0xffffffffu, miss ? slot : 0xffffffffu);
+        if (miss && (int)(__ffs((int)peers) - 1) == (int)(threadIdx.x & 31)) { memo[slot].key = key; memo[slot].val = v; }
+        __syncwarp();
+    }
+    return v;
+}
+
 __global__ void __launch_bounds__(256)
 compact_gl_kernel(const double* __restrict__ in, int64_t in_stride, const int* __restrict__ src,
                   long long L, const uint64_t* __restrict__ geno0, int64_t row_words0,
@@ -1394,7 +1421,14 @@ compact_gl_kernel(const double* __restrict__ in, int64_t in_stride, const int* _
                   int n_ind, int type)
 {
     __shared__ double tile[kGlTile][33];
+    __shared__ GlMemoEntry memo_s[8][kGlMemo];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    GlMemoEntry* memo = memo_s[warp];
+    // an impossible key: the bit pattern of a NaN payload no text or caller value produces by accident matters little —
+    // a raw value with exactly these bits would read val = 0 once; use the one pattern gl_to_error maps to itself
+    for (int i = lane; i < kGlMemo; i += 32) { memo[i].key = 0xfff8dead0000beefull; memo[i].val = gl_to_error(__longlong_as_double((long long)0xfff8dead0000beefull), type); }
+    __syncwarp();
+    const bool use_memo = type >= 0;
     const long long tiles_per_group = (out_stride + kGlTile - 1) / kGlTile;
     const long long total = tiles_per_group * ((n_ind + 31) / 32);
     for (long long u = blockIdx.x; u < total; u += gridDim.x) {
@@ -1405,15 +1439,24 @@ compact_gl_kernel(const double* __restrict__ in, int64_t in_stride, const int* _
             const long long d = d0 + lane + 32 * h;
             const int s = d < L ? src[d] : -1;
             const double f = s >= 0 ? freq0[s] : 0.0;
+            // the four rows' raw values and genotype words first: independent loads in flight before any arithmetic
+            double raw[4];
+            uint64_t gw[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = group * 32 + warp + 8 * r;
+                const bool on = s >= 0 && i < n_ind;
+                raw[r] = on ? in[(int64_t)i * in_stride + s] : 0.0;
+                gw[r] = on ? geno0[(int64_t)i * row_words0 + (s >> 5)] : 0ull;
+            }
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int il = warp + 8 * r, i = group * 32 + il;
+                const bool on = s >= 0 && i < n_ind;
                 double v = 0.0;
-                if (s >= 0 && i < n_ind) {
-                    const int g = (int)(geno0[(int64_t)i * row_words0 + (s >> 5)] >> (2 * (s & 31))) & 3;
-                    // per-genotype error (readTGLSData) → per-genotype LOD (lod(), garlic-roh.cpp:355-386)
-                    v = lod_eval(g, f, gl_to_error(in[(int64_t)i * in_stride + s], type));
-                }
+                // per-genotype error (readTGLSData) → per-genotype LOD (lod(), garlic-roh.cpp:355-386)
+                const double e = use_memo ? gl_error_memo(raw[r], type, on, memo) : raw[r];
+                if (on) v = lod_eval((int)(gw[r] >> (2 * (s & 31))) & 3, f, e);
                 tile[lane + 32 * h][il] = v;
             }
         }

@@ -83,5 +83,12 @@ cudaError_t launch_wlod_weights(const int* pos, const double* gpos, const int* c
                                 long long L, double mu, int M, double* nomut, double* norec, cudaStream_t st);
 cudaError_t launch_build_wlut(const double* lut, const double* nomut, const double* norec, long long L,
                               double* wlut, cudaStream_t st);
+// K0-GL (ingest.cu): tgls value columns from raw text into the individual-major matrix out[(k - ind_lo) * out_stride + snp0 + l]
+cudaError_t launch_tokenize_tgls(const char* text, const long long* off, int n_snp, int n_ind, int ind_lo, double* out,
+                                 int64_t out_stride, long long snp0, int* n_tokens, int2* hard_list, unsigned* hard_count,
+                                 unsigned hard_cap, cudaStream_t st);
+// computeKDE on the device (kde.cu): scratch size in doubles; out → state[8] | x[m] | y[m] inside the scratch
+size_t kde_scratch_doubles(int m);
+cudaError_t launch_kde(const double* v, long long n, int m, double* scratch, double** out, int* launches, cudaStream_t st);
 
 }  // namespace garlic

@@ -76,7 +76,7 @@ static const char* kHelp =
     "  --winsize --winsize-multi --auto-winsize --auto-winsize-step --overlap-frac --auto-overlap-frac --error\n"
     "  --max-gap --lod-cutoff --size-bounds --kde-subsample --ld-subsample --no-kde-thinning --nclust --M --mu\n"
     "  --build --centromere --tped-missing --threads --resample --out --raw-lod\n"
-    "Extensions: --gpus <n> (shard individuals over n GPUs), --exact (whole-segment chains), --device <n>, --seed <n> (subsample RNG seed), --device-lut, --kde-direct, --host-tokenize (tped allele columns extracted on the host instead of the GPU tokeniser)\n";
+    "Extensions: --gpus <n> (shard individuals over n GPUs), --exact (whole-segment chains), --device <n>, --seed <n> (subsample RNG seed), --device-lut, --kde-direct, --kde-gpu (the KDE itself on the GPU: exact Gauss transform of the thinned windows still in HBM), --host-tokenize (tped allele columns extracted on the host instead of the GPU tokeniser)\n";
 
 int parse_cli(int argc, char** argv, Options& o, std::string& cmdline)
 {
@@ -84,7 +84,7 @@ int parse_cli(int argc, char** argv, Options& o, std::string& cmdline)
     for (int i = 0; i < argc; ++i) { cmdline += argv[i]; cmdline += " "; }
     std::map<std::string, bool*> fb = {{"--weighted", &o.weighted}, {"--cm", &o.cm}, {"--auto-winsize", &o.auto_winsize},
         {"--auto-overlap-frac", &o.auto_overlap}, {"--raw-lod", &o.raw_lod}, {"--freq-only", &o.freq_only},
-        {"--phased", &o.phased}, {"--no-kde-thinning", &o.no_kde_thinning}, {"--exact", &o.exact}, {"--device-lut", &o.device_lut}, {"--kde-direct", &o.kde_direct}, {"--host-tokenize", &o.host_tokenize}};
+        {"--phased", &o.phased}, {"--no-kde-thinning", &o.no_kde_thinning}, {"--exact", &o.exact}, {"--device-lut", &o.device_lut}, {"--kde-direct", &o.kde_direct}, {"--kde-gpu", &o.kde_gpu}, {"--host-tokenize", &o.host_tokenize}};
     std::map<std::string, int*> fi = {{"--winsize", &o.winsize}, {"--auto-winsize-step", &o.auto_winsize_step},
         {"--max-gap", &o.max_gap}, {"--resample", &o.resample}, {"--threads", &o.threads}, {"--M", &o.M},
         {"--nclust", &o.nclust}, {"--kde-subsample", &o.kde_subsample}, {"--ld-subsample", &o.ld_subsample},

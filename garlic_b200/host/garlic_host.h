@@ -46,6 +46,7 @@ struct Options {
     bool device_lut = false;     // extension: build the per-SNP LOD table on the GPU (--device-lut)
     bool host_tokenize = false;  // extension: extract the tped allele characters on the host instead of K0 (--host-tokenize)
     bool kde_direct = false;     // extension: exact (reproducible) Gauss transform for the KDE (--kde-direct)
+    bool kde_gpu = false;        // extension: computeKDE on the GPU, from the thinned windows still in HBM (--kde-gpu)
     long seed = -1;              // extension: RNG seed for the KDE / LD subsamples (--seed; default time)
 };
 // returns 0 = run, 1 = help printed (exit 0), -1 = error

@@ -189,6 +189,25 @@ bool thinned_windows(Ctx& c, int W, int step, const std::vector<int32_t>* inds, 
     return true;
 }
 
+// --kde-gpu: computeKDE (garlic-kde.cpp:14-101) on the GPU, from the thinned windows the gather left in rank 0's HBM
+// (every rank holds the whole gathered matrix); the 512 sums come back, the normalisation (:86-95) is done here.
+bool compute_kde_gpu(Ctx& c, size_t n_expected, Kde& k)
+{
+    const int M = 512;
+    LOG.line("KDE with " + std::to_string(n_expected) + " points.");
+    k.x.assign(M, 0.0);
+    k.y.assign(M, 0.0);
+    int64_t n = 0;
+    double h = 0;
+    if (!gpu_ok(c, garlic_gpu_kde(c.g, nullptr, 0, M, k.x.data(), k.y.data(), &n, &h), "kde")) return false;
+    if ((size_t)n != n_expected) { LOG.error("ERROR: device KDE saw " + std::to_string(n) + " values, expected " + std::to_string(n_expected)); return false; }
+    const double spacing = k.x[1] - k.x[0];
+    double sum = 0;
+    for (int i = 0; i < M; ++i) sum += k.y[i];
+    for (int i = 0; i < M; ++i) k.y[i] /= (sum * spacing);
+    return true;
+}
+
 double lod_host(int g, double freq, double error)   // garlic-roh.cpp:355-386
 {
     double a, na;
@@ -554,6 +573,7 @@ int main(int argc, char** argv)
             std::vector<double> data;
             if (!thinned_windows(c, W, thin ? W : 1, subp, data)) return false;
             if (data.size() < 2) { LOG.error("ERROR: no valid windows for window size " + std::to_string(W)); return false; }
+            if (o.kde_gpu) return compute_kde_gpu(c, data.size(), k);
             compute_kde(data, k, o.kde_direct);
             return true;
         };
@@ -630,7 +650,8 @@ int main(int argc, char** argv)
             if (!thinned_windows(c, winsize, thin ? winsize : 1, subp, data)) return 1;
             if (data.size() < 2) { LOG.error("ERROR: no valid windows to estimate the LOD score density."); return 1; }
             fprintf(stderr, "Estimating distribution of raw LOD score windows:\n");
-            compute_kde(data, selected, o.kde_direct);
+            if (o.kde_gpu) { if (!compute_kde_gpu(c, data.size(), selected)) return 1; }
+            else compute_kde(data, selected, o.kde_direct);
             if (!write_kde(selected, o.out + "." + std::to_string(winsize) + "SNPs.kde")) return -1;
         }
         cutoff = min_between_modes(selected, winsize);

@@ -106,6 +106,14 @@ int garlic_gpu_get_one_allele(garlic_gpu_t *h, uint8_t *allele, char missing);
  * error on the device during garlic_gpu_filter. */
 int garlic_gpu_put_gl(garlic_gpu_t *h, const double *values, int gl_type);
 int garlic_gpu_put_gl_dev(garlic_gpu_t *h, const void *values_dev, int gl_type);
+/* K0-GL: the same matrix from raw text.  text + line_off[i] .. line_off[i+1] is what follows the 4th field of tgls line
+ * snp0 + i; its k-th blank-separated token is individual k's value (`ss >> gl`, src/garlic-data.cpp:1538-1554).  Every
+ * rank gets the whole line and keeps its own individuals' tokens.  Tokens are converted on the device where one IEEE
+ * operation is exact (<= 15 significant digits, |power of ten| <= 22); the few others by the host's strtod, so the
+ * values equal the host reader's bit for bit.  n_tokens (may be NULL): [n_snp] tokens found per line, for the caller's
+ * column check (:1531-1536).  Call for every SNP range before garlic_gpu_filter. */
+int garlic_gpu_put_tgls_text(garlic_gpu_t *h, const char *text, const int64_t *line_off, int64_t snp0, int n_snp,
+                             int gl_type, int32_t *n_tokens);
 
 /* ---- freq + filterMonomorphic[AndOOB]Sites + K3 compaction (src/garlic-data.cpp:141,871-1195)
  * freq = nalleles/total from the (all-reduced) counts; keep iff 0<freq<1 [and, if oob, inside
@@ -159,6 +167,17 @@ int garlic_gpu_windows_dev(garlic_gpu_t *h, int winsize, int step, int weighted,
  * collects every rank's MISSING-padded block; out: [world*rows_per_rank][n_slots] in rank order */
 int garlic_gpu_windows_gather(garlic_gpu_t *h, int winsize, int step, int weighted, const int32_t *individuals,
                               int n, int rows_per_rank, int exact, double *out);
+
+/* ---- computeKDE on the device (src/garlic-kde.cpp:14-101, nrd0 :130-140) --------------------------
+ * Density of the window values pass 1 left on this GPU — values == NULL: the matrix of the last garlic_gpu_windows /
+ * _windows_dev / _windows_gather call, MISSING and NaN slots skipped in place — or of n_values host values.
+ * Bandwidth = nrd0 (gsl_stats_sd, gsl quantiles), m_targets (the reference: 512; 2..1024) equally spaced targets
+ * from min - 3h to max + 3h, and the Gauss transform  y[j] = sum_i (1/n) exp(-(x[j] - v_i)^2 / h^2)  evaluated
+ * exactly (the sum FIGTree approximates to eps = 1e-2 for the reference).  x[m], y[m] (not yet divided by
+ * sum(y) * spacing: garlic-kde.cpp:86-95 stays with the caller), *n_used values, *bandwidth = h.  Reproducible:
+ * every reduction runs in a fixed order. */
+int garlic_gpu_kde(garlic_gpu_t *h, const double *values, int64_t n_values, int m_targets, double *x, double *y,
+                   int64_t *n_used, double *bandwidth);
 
 /* ---- K5 pass 2: calc[w]LODWindows + assembleROHWindows fused (src/garlic-roh.cpp:279-347,409-546)
  * overlap_frac as --overlap-frac. out: capacity cap records, sorted by (ind, chr, start);

@@ -277,6 +277,74 @@ COLORS = ["228,26,28", "77,175,74", "55,126,184", "152,78,163", "255,127,0", "25
           "166,86,40", "247,129,191", "153,153,153"]
 
 
+
+# ------------------------------------------------------------------------------------------------
+# KDE and cutoff heuristic (garlic-kde.cpp), restated with the EXACT Gauss transform
+# ------------------------------------------------------------------------------------------------
+def compute_kde(data, M=512):
+    """computeKDE (garlic-kde.cpp:14-101) with nrd0 (:130-140): sorted data, gsl_stats_sd (N-1), gsl quantiles at
+    f(n-1) with linear interpolation, h = 0.9 min(sd, iqr/1.34) n^-0.2; M targets (i+1)/M (max-min)+min over
+    [min-3h, max+3h]; y = sum_i (1/n) exp(-(t-x_i)^2/h^2) — the sum FIGTree evaluates (to eps = 1e-2 in the reference,
+    exactly with FIGTREE_EVAL_DIRECT) — divided by sum(y)*spacing.  -> (t, y, h)"""
+    x = np.sort(np.asarray(data, np.float64))
+    n = len(x)
+    sd = np.std(x, ddof=1)
+
+    def q(f):
+        idx = f * (n - 1)
+        lo = int(idx)
+        d = idx - lo
+        return x[lo] if lo == n - 1 else (1 - d) * x[lo] + d * x[lo + 1]
+    h = 0.9 * min(sd, (q(0.75) - q(0.25)) / 1.34) * n ** -0.2
+    mn, mx = x[0] - 3 * h, x[-1] + 3 * h
+    t = (np.arange(1, M + 1) / float(M)) * (mx - mn) + mn
+    y = np.array([np.exp(-((ti - x) / h) ** 2).sum() / n for ti in t])
+    y /= y.sum() * (t[1] - t[0])
+    return t, y, h
+
+
+def min_between_modes(t, y, W):
+    """get_min_btw_modes (garlic-kde.cpp:142-234), behaviour for behaviour (including the i == 1 case)."""
+    size, win = len(y), 20
+    m = size - win
+    umax, ucnt, index = np.zeros(m), np.zeros(m), 0
+    for i in range(m):
+        seg = y[i:i + win]
+        mxv = seg[np.argmax(seg)] if seg.max() > np.finfo(float).tiny else y[i - 1]
+        if i == 1:
+            umax[i] = mxv
+            ucnt[i] += 1
+        elif umax[index] == mxv:
+            ucnt[index] += 1
+        else:
+            index += 1
+            umax[index] = mxv
+            ucnt[index] += 1
+    c1, c2 = int(ucnt[0]), 0
+    for i in range(1, m):
+        if c1 <= ucnt[i]:
+            c2, c1 = c1, int(ucnt[i])
+        elif c2 <= ucnt[i]:
+            c2 = int(ucnt[i])
+    vals = [umax[i] for i in range(m) if ucnt[i] == c1 or ucnt[i] == c2]
+    first = second = -1.0
+    for v in vals:
+        if first <= v:
+            second, first = first, v
+        elif second <= v:
+            second = v
+    li = ri = -1
+    for i in range(size):
+        if y[i] == first:
+            li = i
+        if y[i] == second:
+            ri = i
+    if ri < li:
+        li, ri = ri, li
+    mi = int(np.argmin(y[li:ri + 1])) + li
+    return t[mi] if abs(t[mi] / W) < 1 else 0.0
+
+
 def _fmt_g6(x):
     """C++ ostream default formatting of a double (precision 6, %g)."""
     return "%g" % x

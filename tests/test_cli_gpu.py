@@ -168,60 +168,10 @@ def test_cli_freq_only():
 
 
 def _py_kde_cutoff(data, W):
-    """Restatement of computeKDE (exact Gauss transform, FIGTree's exp(-(t-x)^2/h^2) kernel) + get_min_btw_modes
-    (garlic-kde.cpp:14-234) for the deterministic --kde-direct check."""
-    x = np.sort(np.asarray(data, np.float64))
-    n = len(x)
-    sd = np.std(x, ddof=1)
-
-    def q(f):
-        idx = f * (n - 1)
-        lo = int(idx)
-        d = idx - lo
-        return x[lo] if lo == n - 1 else (1 - d) * x[lo] + d * x[lo + 1]
-    h = 0.9 * min(sd, (q(0.75) - q(0.25)) / 1.34) * n ** -0.2
-    mn, mx = x[0] - 3 * h, x[-1] + 3 * h
-    t = (np.arange(1, 513) / 512.0) * (mx - mn) + mn
-    y = np.array([np.exp(-((ti - x) / h) ** 2).sum() / n for ti in t])
-    y /= y.sum() * (t[1] - t[0])
-    size, win = 512, 20
-    m = size - win
-    umax, ucnt, index = np.zeros(m), np.zeros(m), 0
-    for i in range(m):
-        seg = y[i:i + win]
-        mxv = seg[np.argmax(seg)] if seg.max() > np.finfo(float).tiny else y[i - 1]
-        if i == 1:
-            umax[i] = mxv
-            ucnt[i] += 1
-        elif umax[index] == mxv:
-            ucnt[index] += 1
-        else:
-            index += 1
-            umax[index] = mxv
-            ucnt[index] += 1
-    c1, c2 = int(ucnt[0]), 0
-    for i in range(1, m):
-        if c1 <= ucnt[i]:
-            c2, c1 = c1, int(ucnt[i])
-        elif c2 <= ucnt[i]:
-            c2 = int(ucnt[i])
-    vals = [umax[i] for i in range(m) if ucnt[i] == c1 or ucnt[i] == c2]
-    first = second = -1.0
-    for v in vals:
-        if first <= v:
-            second, first = first, v
-        elif second <= v:
-            second = v
-    li = ri = -1
-    for i in range(size):
-        if y[i] == first:
-            li = i
-        if y[i] == second:
-            ri = i
-    if ri < li:
-        li, ri = ri, li
-    mi = int(np.argmin(y[li:ri + 1])) + li
-    return (t[mi] if abs(t[mi] / W) < 1 else 0.0), t, y
+    """computeKDE (exact Gauss transform) + get_min_btw_modes as restated in oracle/oracle.py (garlic-kde.cpp:14-234)."""
+    from oracle import oracle as orc
+    t, y, _ = orc.compute_kde(data)
+    return orc.min_between_modes(t, y, W), t, y
 
 
 def test_cli_kde_direct_is_deterministic_and_matches_restatement():
@@ -241,6 +191,26 @@ def test_cli_kde_direct_is_deterministic_and_matches_restatement():
             assert np.allclose(got[:, 0], t, rtol=1e-5) and np.allclose(got[:, 1], y, rtol=2e-5, atol=1e-9)
     assert cuts[0] == cuts[1]
     assert abs(cuts[0] - want_cut) <= 1e-9 * max(1.0, abs(want_cut))
+
+
+def test_cli_kde_gpu_equals_kde_direct():
+    """--kde-gpu (computeKDE on the device) against --kde-direct (FIGTree's exact evaluation on the host):
+    same .kde to print precision, same selected cutoff, identical ROH; thinned and un-thinned KDE input."""
+    for case, extra in (("auto_cutoff", []), ("no_kde_thinning", [])):
+        outs = []
+        for flag in ("--kde-direct", "--kde-gpu"):
+            with tempfile.TemporaryDirectory() as tmp:
+                _, _, r = run_cli(case, tmp, extra=extra + [flag])
+                assert r.returncode == 0, r.stderr[-1500:]
+                cut = float(r.stdout.split("(17 digits): ")[1].split()[0])
+                kde_name = [f for f in os.listdir(tmp) if f.endswith(".kde")][0]
+                outs.append((cut, np.loadtxt(os.path.join(tmp, kde_name)), open(os.path.join(tmp, "out.roh.bed")).read(),
+                             [l for l in open(os.path.join(tmp, "out.log")) if l.startswith("KDE with")]))
+        (c0, k0, b0, l0), (c1, k1, b1, l1) = outs
+        assert l0 == l1 and len(l0) >= 1
+        assert abs(c0 - c1) <= 1e-9 * max(1.0, abs(c0))
+        assert np.allclose(k0[:, 0], k1[:, 0], rtol=1e-5) and np.allclose(k0[:, 1], k1[:, 1], rtol=2e-5, atol=1e-9)
+        assert b0 == b1
 
 
 def test_cli_exact_mode_and_errors():

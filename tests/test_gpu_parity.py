@@ -204,6 +204,36 @@ def test_thinned_windows_for_kde_subsample():
     hp.close()
 
 
+def test_kde_on_device_matches_restatement():
+    """garlic_gpu_kde (computeKDE on the device): nrd0 bandwidth by radix selection of the quantiles, 512
+    targets, exact Gauss transform — of the window matrix pass 1 left on the GPU (MISSING slots skipped in place) and of
+    host values — against the restatement of garlic-kde.cpp:14-140 on the oracle's thinned windows; same cutoff from
+    get_min_btw_modes; two runs bit-identical (fixed reduction order)."""
+    ds, args = load_case("auto_cutoff")
+    W = 30
+    res = orc.run_pipeline(ds, W, 0.001, None, thin_step=W)
+    t, y, h = orc.compute_kde(res["thinned"])
+    hp = HotPath().load(ds, error=0.001)
+    data = hp.thinned(W, W)                                   # leaves the thinned matrix on the device
+    x1, y1, n1, h1 = hp.g.kde()
+    assert n1 == len(res["thinned"]) == len(data)
+    assert abs(h1 - h) <= 1e-12 * h
+    assert np.allclose(x1, t, rtol=1e-12, atol=1e-12)
+    assert np.max(np.abs(y1 - y)) <= 1e-9 * np.max(y)
+    assert orc.min_between_modes(x1, y1, W) == pytest.approx(orc.min_between_modes(t, y, W), rel=1e-12)
+    x2, y2, n2, h2 = hp.g.kde()
+    assert np.array_equal(y1, y2) and h1 == h2
+    # host values (several GPUs: the gathered thinned windows), odd target count, duplicates and negative values
+    rng = np.random.default_rng(5)
+    v = np.concatenate([rng.normal(-8, 2, 3001), rng.normal(3, 1, 1500), np.full(40, 1.25)])
+    for m in (512, 333, 1024):
+        t3, y3, h3 = orc.compute_kde(v, m)
+        x4, y4, n4, h4 = hp.g.kde(v, m)
+        assert n4 == len(v) and abs(h4 - h3) <= 1e-12 * h3
+        assert np.allclose(x4, t3, rtol=1e-12, atol=1e-12) and np.max(np.abs(y4 - y3)) <= 1e-9 * np.max(y3)
+    hp.close()
+
+
 def test_cutoff_on_a_window_value_is_resolved_exactly():
     """A cutoff equal to an actual window value: the chunked pass must detect the ambiguity and the
     exact re-evaluation must reproduce the reference's decision."""

@@ -212,3 +212,24 @@ def test_cli_two_gpus_window_size_search(name):
     for k in outs[0][0]:
         assert outs[0][0][k] == outs[1][0][k], k
     assert outs[0][1] == outs[1][1]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_cli_two_gpus_kde_on_device():
+    """--kde-gpu over two GPUs: rank 0 runs computeKDE on the all-gathered thinned windows in its HBM; the .kde and the
+    cutoff equal the one-GPU run's to rounding (the gathered matrix holds the same values, padded differently, so the
+    fixed-order sums group them differently), the ROH are identical."""
+    import os
+    import tempfile
+    from tests.test_cli_gpu import run_cli
+    outs = []
+    for extra in (["--kde-gpu"], ["--kde-gpu", "--gpus", "2"]):
+        with tempfile.TemporaryDirectory() as tmp:
+            ds, args, r = run_cli("auto_cutoff", tmp, extra=extra)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            cut = float(r.stdout.split("(17 digits): ")[1].split()[0])
+            kde = np.loadtxt(os.path.join(tmp, [f for f in os.listdir(tmp) if f.endswith(".kde")][0]))
+            outs.append((cut, kde, open(os.path.join(tmp, "out.roh.bed")).read()))
+    assert abs(outs[0][0] - outs[1][0]) <= 1e-9 * max(1.0, abs(outs[0][0]))
+    assert np.allclose(outs[0][1], outs[1][1], rtol=1e-6, atol=1e-12)
+    assert outs[0][2] == outs[1][2]
