@@ -27,7 +27,7 @@ EXPORTS = [
     "garlic_gpu_ld_band", "garlic_gpu_set_wlod", "garlic_gpu_window_slots", "garlic_gpu_windows",
     "garlic_gpu_windows_dev", "garlic_gpu_windows_gather", "garlic_gpu_comm_id", "garlic_gpu_comm_init",
     "garlic_gpu_call_roh", "garlic_gpu_last_stats", "garlic_gpu_n_kept", "garlic_gpu_get_kept_index",
-    "garlic_gpu_get_genotypes", "garlic_gpu_get_piece_bounds", "garlic_gpu_set_prune", "garlic_gpu_kde", "garlic_gpu_put_tgls_text",
+    "garlic_gpu_get_genotypes", "garlic_gpu_get_piece_bounds", "garlic_gpu_set_prune", "garlic_gpu_kde", "garlic_gpu_put_tgls_text", "garlic_gpu_get_gl",
 ]
 
 
@@ -180,6 +180,11 @@ class GarlicGPU:
         buf = np.frombuffer(text, np.uint8)
         self._ck(self.lib.garlic_gpu_put_tgls_text(self.h, _p(buf), _p(off), C.c_int64(snp0), C.c_int(n), C.c_int(t), _p(ntok)))
         return ntok
+
+    def get_gl(self):
+        out = np.empty((self.n_ind, self.L0), np.float64)
+        self._ck(self.lib.garlic_gpu_get_gl(self.h, _p(out)))
+        return out
 
     def filter(self, oob=False, chr_param=None, freq_override=None, want_freq=True, want_keep=True):
         """→ (freq float64[L0], keep bool[L0], L).  The two arrays are views of buffers owned by this object and

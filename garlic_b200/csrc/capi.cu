@@ -635,6 +635,15 @@ int garlic_gpu_put_tgls_text(garlic_gpu_t* h, const char* text, const int64_t* l
     return 0;
 }
 
+int garlic_gpu_get_gl(garlic_gpu_t* h, double* values)
+{
+    CK(cudaSetDevice(h->device));
+    if (!h->have_gl || !h->d_gl0) FAIL("get_gl: no likelihoods loaded");
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(values, h->d_gl0, (size_t)h->n_ind * h->L0 * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int garlic_gpu_put_gl(garlic_gpu_t* h, const double* values, int gl_type) { return put_gl_common(h, values, gl_type, cudaMemcpyHostToDevice); }
 int garlic_gpu_put_gl_dev(garlic_gpu_t* h, const void* values_dev, int gl_type) { return put_gl_common(h, values_dev, gl_type, cudaMemcpyDeviceToDevice); }
 

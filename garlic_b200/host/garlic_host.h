@@ -72,6 +72,16 @@ struct Scaffold { std::string chr; std::vector<int32_t> pos; std::vector<double>
 bool load_map(const std::string& path, std::vector<Scaffold>& s);
 // values individual-major [N][L0]
 bool load_tgls(const std::string& path, const Tped& t, std::vector<double>& values);
+// K0-GL: the tgls file streamed in blocks of lines; per block the raw value columns (what follows the 4th field of every
+// line) and their offsets, converted on the GPU (garlic_gpu_put_tgls_text).  A missing line yields an empty tail, which
+// fails the column check exactly as the reference's getline on a short file does (garlic-data.cpp:1529-1536).
+struct TglsBlocks {
+    void* impl = nullptr;
+    bool open(const std::string& path);
+    // up to max_lines lines: text / off[n+1]; returns the number of lines delivered (short files: padded with empty lines)
+    int next(int max_lines, std::vector<char>& text, std::vector<int64_t>& off);
+    ~TglsBlocks();
+};
 // readFreqData (garlic-data.cpp:1345-1440): CHR SNP POS ALLELE FREQ rows in tped order; 1 - freq where ALLELE is not the tped's "1" allele
 bool load_freq_file(const std::string& path, const Tped& t, const std::vector<uint8_t>& one_allele, std::vector<double>& freq);
 std::string chr_label(const std::string& name);   // checkChrName, garlic-data.cpp:1886-1891

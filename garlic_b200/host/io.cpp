@@ -233,6 +233,36 @@ bool load_tgls(const std::string& path, const Tped& t, std::vector<double>& v)
     return true;
 }
 
+bool TglsBlocks::open(const std::string& path)
+{
+    GzLines* g = new GzLines;
+    fprintf(stderr, "Loading genotype likelihoods from %s\n", path.c_str());
+    if (!g->open(path)) { delete g; LOG.error("ERROR: Failed to open " + path); return false; }
+    impl = g;
+    return true;
+}
+int TglsBlocks::next(int max_lines, std::vector<char>& text, std::vector<int64_t>& off)
+{
+    GzLines* g = static_cast<GzLines*>(impl);
+    text.clear();
+    off.assign(1, 0);
+    for (int l = 0; l < max_lines; ++l) {
+        const char* p; size_t n;
+        if (g->next_view(p, n)) {
+            const char* e = p + n;
+            const char* q = p;
+            for (int k = 0; k < 4; ++k) {                       // <chr> <id> <cM> <bp>
+                while (q < e && (*q == ' ' || *q == '\t')) ++q;
+                while (q < e && *q != ' ' && *q != '\t') ++q;
+            }
+            text.insert(text.end(), q, e);
+        }
+        off.push_back((int64_t)text.size());
+    }
+    return max_lines;
+}
+TglsBlocks::~TglsBlocks() { delete static_cast<GzLines*>(impl); }
+
 bool load_freq_file(const std::string& path, const Tped& t, const std::vector<uint8_t>& one, std::vector<double>& freq)
 {
     GzLines in;

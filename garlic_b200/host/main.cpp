@@ -396,7 +396,7 @@ int main(int argc, char** argv)
     LOG.line("Population: " + c.tfam.pop);
     LOG.line("Total diploid individuals: " + std::to_string(t.n_ind));
     std::vector<double> gl;
-    if (use_gl && !load_tgls(o.tgls, t, gl)) return 1;
+    if (use_gl && o.host_tokenize && !load_tgls(o.tgls, t, gl)) return 1;   // (K0-GL streams the file to the GPUs below)
     const bool oob = o.weighted || o.cm;
     if (oob) {
         if (!load_map(o.map, c.scaffold)) return 1;
@@ -458,12 +458,37 @@ int main(int argc, char** argv)
                 if (!rank_ok(R, garlic_gpu_put_alleles(R.g, src_, s0, ns, o.tped_missing), "put_alleles")) return false;
             }
             if (!rank_ok(R, garlic_gpu_code_alleles(R.g), "code_alleles")) return false;     // MIN all-reduce of the first-allele keys
-            if (use_gl) {
+            if (use_gl && o.host_tokenize) {
                 const int type = o.gl_type == "GQ" ? GARLIC_GL_GQ : o.gl_type == "GL" ? GARLIC_GL_GL : GARLIC_GL_PL;
                 if (!rank_ok(R, garlic_gpu_put_gl(R.g, gl.data() + (size_t)R.lo * t.n_loci, type), "put_gl")) return false;
             }
             return true;
         })) return fail(1);
+    if (use_gl && !o.host_tokenize) {
+        // K0-GL: the likelihood file goes to the GPUs as raw text, a block of lines at a time; every rank converts its
+        // own individuals' columns (readTGLSData's parsing, garlic-data.cpp:1516-1554)
+        const int type = o.gl_type == "GQ" ? GARLIC_GL_GQ : o.gl_type == "GL" ? GARLIC_GL_GL : GARLIC_GL_PL;
+        TglsBlocks in;
+        if (!in.open(o.tgls)) { team.stop(); return 1; }
+        std::vector<char> text;
+        std::vector<int64_t> off;
+        std::vector<std::vector<int32_t>> ntok(G);
+        for (int64_t s0 = 0; s0 < t.n_loci; s0 += blk) {
+            const int ns = (int)std::min(blk, t.n_loci - s0);
+            in.next(ns, text, off);
+            if (text.empty()) text.push_back(' ');
+            if (!team.all([&](Rank& R) {
+                    ntok[R.rank].resize(ns);
+                    return rank_ok(R, garlic_gpu_put_tgls_text(R.g, text.data(), off.data(), s0, ns, type, ntok[R.rank].data()), "put_tgls_text");
+                })) return fail(1);
+            for (int k = 0; k < ns; ++k)
+                if (ntok[0][k] != t.n_ind) {                   // the reference counts the 4 leading fields as well (:1531)
+                    LOG.error("ERROR: Incorrect number of columns in tgls file:  " + std::to_string(ntok[0][k] ? ntok[0][k] + 4 : 0) + ". Expected:  " + std::to_string(t.n_ind));
+                    team.stop();
+                    return 1;
+                }
+        }
+    }
     c.g = team.ranks[0].g;
     std::vector<uint8_t>().swap(t.alleles);
     std::vector<char>().swap(t.text);

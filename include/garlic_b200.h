@@ -115,6 +115,9 @@ int garlic_gpu_put_gl_dev(garlic_gpu_t *h, const void *values_dev, int gl_type);
 int garlic_gpu_put_tgls_text(garlic_gpu_t *h, const char *text, const int64_t *line_off, int64_t snp0, int n_snp,
                              int gl_type, int32_t *n_tokens);
 
+/* the raw likelihood matrix back to the host, [n_ind][n_loci] individual-major, as put_gl / put_tgls_text stored it (parity checks) */
+int garlic_gpu_get_gl(garlic_gpu_t *h, double *values);
+
 /* ---- freq + filterMonomorphic[AndOOB]Sites + K3 compaction (src/garlic-data.cpp:141,871-1195)
  * freq = nalleles/total from the (all-reduced) counts; keep iff 0<freq<1 [and, if oob, inside
  * the map scaffold and not strictly inside the centromere]. chr_param: [n_chr][4] =

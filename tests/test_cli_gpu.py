@@ -193,6 +193,34 @@ def test_cli_kde_direct_is_deterministic_and_matches_restatement():
     assert abs(cuts[0] - want_cut) <= 1e-9 * max(1.0, abs(want_cut))
 
 
+@pytest.mark.parametrize("name", ["lod_small", "gl_pl", "gl_gl"])
+def test_cli_host_tokenize_equals_device_ingest(name):
+    """--host-tokenize (allele characters / likelihood values extracted by the host readers) against the default
+    (K0 / K0-GL: raw text tokenised and converted on the GPU): identical output files."""
+    outs = []
+    for extra in ([], ["--host-tokenize"]):
+        with tempfile.TemporaryDirectory() as tmp:
+            _, _, r = run_cli(name, tmp, extra=extra)
+            assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+            outs.append((open(os.path.join(tmp, "out.roh.bed")).read(), gzip.open(os.path.join(tmp, "out.freq.gz"), "rt").read()))
+    assert outs[0] == outs[1]
+    assert outs[0][0] == golden_text(name, "out.roh.bed")
+
+
+def test_cli_tgls_column_check():
+    """A tgls line with a missing column stops the run with the reference's message (garlic-data.cpp:1531-1536)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        ds, args = load_case("gl_pl")
+        p = ds.write(tmp)
+        lines = open(p["tgls"]).read().splitlines()
+        lines[5] = " ".join(lines[5].split()[:-1])
+        open(p["tgls"], "w").write("\n".join(lines) + "\n")
+        with open(os.path.join(GOLDEN, "gl_pl", "cmd.txt")) as f:
+            cmd = [a.replace("<tmp>", tmp) for a in f.readline().split()[1:]]
+        r = subprocess.run([BIN] + cmd, capture_output=True, text=True, timeout=180)
+        assert r.returncode != 0 and "Incorrect number of columns in tgls file" in r.stderr
+
+
 def test_cli_kde_gpu_equals_kde_direct():
     """--kde-gpu (computeKDE on the device) against --kde-direct (FIGTree's exact evaluation on the host):
     same .kde to print precision, same selected cutoff, identical ROH; thinned and un-thinned KDE input."""

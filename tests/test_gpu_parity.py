@@ -155,6 +155,84 @@ def test_gl_path(name):
     hp.close()
 
 
+def _tgls_text(tokens_by_line, rng):
+    """Raw value columns of a tgls file (what follows the 4th field): tokens separated by random blanks / tabs."""
+    text, off = bytearray(), [0]
+    for toks in tokens_by_line:
+        line = ""
+        for t in toks:
+            line += rng.choice([" ", "\t", "  ", " \t "]) + t
+        line += rng.choice(["", " ", "\r"])
+        text += line.encode()
+        off.append(len(text))
+    return bytes(text), np.array(off, np.int64)
+
+
+def test_k0_tgls_text_on_device_equals_host_strtod():
+    """K0-GL (garlic_gpu_put_tgls_text): the likelihood columns converted on the GPU equal strtod of every token bit for
+    bit — fast-path tokens (phred integers, short decimals, exponents) on the device, the others (19+ digits, huge
+    exponents, 16-digit mantissas, hex) through the host list — for a whole shard and for a shard that starts at
+    individual 7; token counts per line come back for the column check (garlic-data.cpp:1531-1554)."""
+    rng = np.random.default_rng(11)
+    n_ind, L0 = 37, 300
+    fmts = [lambda r: str(int(r.integers(0, 256))), lambda r: "%.4f" % r.uniform(0, 3), lambda r: "%g" % r.uniform(1e-6, 1e3),
+            lambda r: "-%.3f" % r.uniform(0, 12), lambda r: "%.6e" % r.uniform(1e-12, 1e12), lambda r: "+%d" % r.integers(0, 99),
+            lambda r: "0.%018d" % r.integers(0, 10 ** 18), lambda r: "%.17g" % r.uniform(0, 1), lambda r: "1e%d" % r.integers(-330, 310),
+            lambda r: "000%d.500" % r.integers(0, 999), lambda r: ".5", lambda r: "7.", lambda r: "0x1.8p3", lambda r: "0", lambda r: "-0.0",
+            lambda r: "123456789012345678901234", lambda r: "9007199254740993", lambda r: "1E5"]
+    toks = [[fmts[int(rng.integers(0, len(fmts)))](rng) for _ in range(n_ind)] for _ in range(L0)]
+    want = np.array([[float.fromhex(t) if t.startswith("0x") else float(t) for t in line] for line in toks]).T   # [ind][snp]
+    text, off = _tgls_text(toks, rng)
+    from garlic_b200.api import GarlicGPU
+    pos = np.arange(1, L0 + 1, dtype=np.int32) * 100
+    for lo, n in ((0, n_ind), (7, 20)):
+        g = GarlicGPU(0)
+        g.set_shape(n, L0, np.array([0, L0], np.int64), pos, ind_offset=lo)
+        for s0 in range(0, L0, 128):                       # blocks of lines, as the driver streams them
+            s1 = min(L0, s0 + 128)
+            ntok = g.put_tgls_text(text, off[s0:s1 + 1], "PL", snp0=s0)
+            assert np.all(ntok == n_ind)
+        got = g.get_gl()
+        assert got.tobytes() == np.ascontiguousarray(want[lo:lo + n]).tobytes()
+        g.close()
+    # a short and a long line are reported through the token counts
+    toks2 = [toks[0][:-2], toks[1] + ["5"]]
+    text2, off2 = _tgls_text(toks2, rng)
+    g = GarlicGPU(0)
+    g.set_shape(n_ind, L0, np.array([0, L0], np.int64), pos)
+    assert list(g.put_tgls_text(text2, off2, "PL")) == [n_ind - 2, n_ind + 1]
+    g.close()
+
+
+@pytest.mark.parametrize("name", ["gl_pl", "gl_gq"])
+def test_gl_path_from_tgls_text(name):
+    """The GL golden cases with the likelihood matrix ingested as text: same windows and ROH as the oracle."""
+    ds, args, res, p = run_oracle(name)
+    hp = HotPath()
+    gl = ds.gl
+    ds.gl = None
+    try:
+        g = hp.g
+        # HotPath.load without the matrix, the text goes in between the genotype upload and the filter
+        rng = np.random.default_rng(3)
+        toks = [[("%d" % v if float(v).is_integer() else repr(float(v))) for v in row] for row in np.asarray(gl)]   # [snp][ind]
+        text, off = _tgls_text(toks, rng)
+        orig_filter = g.filter
+
+        def filter_with_text(*a, **k):
+            ntok = g.put_tgls_text(text, off, ds.gl_type)
+            assert np.all(ntok == ds.n_ind)
+            return orig_filter(*a, **k)
+        g.filter = filter_with_text
+        hp.load(ds, error=None)
+    finally:
+        ds.gl = gl
+    close_windows(hp.g.windows(p["W"], 1, exact=True), oracle_windows_matrix(res))
+    got = hp.roh(p["W"], p["cutoff"], res["overlap_frac"])
+    assert [(r[0], r[1], r[5], r[6]) for r in got] == oracle_roh_idx(res)
+    hp.close()
+
+
 def test_weighted_ld_wlod_and_roh():
     ds, args, res, p = run_oracle("wlod_cm")
     hp = HotPath().load(ds, weighted=True, cm=True, error=p["err"])
