@@ -25,6 +25,7 @@ using namespace garlic;
 namespace {
 constexpr int kPad = 4096 + 64;   // over-read slack (SNP entries) behind every per-SNP array / row
 constexpr int kMaxW = 4096;
+constexpr unsigned kBreakCap = 1u << 20, kBreakFirst = 4096;   // bad-pair list of set_tables: capacity, entries copied eagerly
 
 }
 
@@ -38,7 +39,10 @@ struct garlic_gpu {
     std::vector<int64_t> chr_off0, chr_off;
     std::vector<int32_t> pos0, pos, src, cen;
     std::vector<double> gpos;
-    std::vector<Stretch> stretches;   // gap/centromere-free SNP stretches (built in set_tables)
+    std::vector<Stretch> stretches;   // gap/centromere-free SNP stretches (set_tables finds the breaks, the first consumer sorts them)
+    bool stretches_pending = false;   // the break list is on its way to brk_pin; ev_tables marks its arrival
+    uint8_t* brk_pin = nullptr;       // page-locked: count + the first breaks
+    cudaEvent_t ev_tables = nullptr;
     bool have_geno0 = false, filtered = false, tables = false, have_gl = false, have_ld = false;
     int gl_type = GARLIC_GL_ERROR;
     double error = -1, mu = 1e-9;
@@ -268,6 +272,7 @@ int garlic_gpu_create(int device, garlic_gpu_t** out)
     cudaEventCreate(&h->ev2);
     cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_tables, cudaEventDisableTiming);
     h->prune = getenv("GARLIC_NO_PRUNE") == nullptr;
     cudaEventCreate(&h->ev_sq0);
     cudaEventCreate(&h->ev_sq1);
@@ -296,6 +301,8 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+    if (h->ev_tables) cudaEventDestroy(h->ev_tables);
+    if (h->brk_pin) cudaFreeHost(h->brk_pin);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     dev_free(h->d_plan_head); dev_free(h->d_plan_seg); dev_free(h->d_plan_rng); dev_free(h->d_bhw); dev_free(h->d_plan_fast); dev_free(h->d_bflag);
     dev_free(h->d_pmax); dev_free(h->d_cand_list); dev_free(h->d_cand_cnt); dev_free(h->d_units); dev_free(h->d_nunits);
@@ -818,44 +825,24 @@ int garlic_gpu_set_tables(garlic_gpu_t* h, double error, int max_gap, const int3
         CK(cudaMemcpyAsync(h->d_gpos, gpos, L * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     }
     h->amax = lod_bound(h);   // enters the ambiguity tolerance of the chunked / tensor-core passes
-    // gap/centromere-free stretches: bad adjacent pairs found on the device (a short list), sorted here; the count and
-    // the first entries come back in one copy behind the kernels above (one synchronisation per call)
+    // gap/centromere-free stretches: bad adjacent pairs found on the device (a short list); the count and the first
+    // entries travel to a page-locked block behind the kernels above.  Nobody waits here: the first consumer of the
+    // stretches (ensure_stretches) does, after it has put its own first kernels — the compaction — on the stream.
     {
-        const unsigned cap = 1u << 20, first = 4096;
-        if (dev_alloc(h, &h->d_breaks, (size_t)cap + 2 * h->n_chr + 4)) return 1;
-        int* d_cen = h->d_breaks + cap;
+        if (dev_alloc(h, &h->d_breaks, (size_t)kBreakCap + 2 * h->n_chr + 4)) return 1;
+        int* d_cen = h->d_breaks + kBreakCap;
         unsigned* d_n = reinterpret_cast<unsigned*>(d_cen + 2 * h->n_chr);
         CK(cudaMemcpyAsync(d_cen, h->cen.data(), 2 * h->n_chr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemsetAsync(d_n, 0, sizeof(unsigned), h->stream));
-        LAUNCH(launch_bad_pairs(h->d_pos, h->d_chr_of, d_cen, max_gap, L, h->d_breaks, d_n, cap, h->stream));
-        if (pin_alloc(h, 64 + first * sizeof(int))) return 1;
-        unsigned* n_host = reinterpret_cast<unsigned*>(h->pin);
-        int* first_host = reinterpret_cast<int*>(h->pin + 64);
-        CK(cudaMemcpyAsync(n_host, d_n, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(first_host, h->d_breaks, first * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        laps.lap("lut+gaps");
-        const unsigned nb = *n_host;
-        if (nb > cap) FAIL("set_tables: more than 2^20 gaps; raise --max-gap");
-        std::vector<int> breaks(first_host, first_host + std::min(nb, first));
-        if (nb > first) {
-            breaks.resize(nb);
-            CK(cudaMemcpy(breaks.data() + first, h->d_breaks + first, (nb - first) * sizeof(int), cudaMemcpyDeviceToHost));
-        }
-        std::sort(breaks.begin(), breaks.end());
+        LAUNCH(launch_bad_pairs(h->d_pos, h->d_chr_of, d_cen, max_gap, L, h->d_breaks, d_n, kBreakCap, h->stream));
+        if (!h->brk_pin) CK(cudaMallocHost((void**)&h->brk_pin, 64 + kBreakFirst * sizeof(int)));
+        CK(cudaMemcpyAsync(h->brk_pin, d_n, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->brk_pin + 64, h->d_breaks, kBreakFirst * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev_tables, h->stream));
+        h->stretches_pending = true;
         h->stretches.clear();
-        size_t bi = 0;
-        for (int c = 0; c < h->n_chr; ++c) {
-            int a = (int)h->chr_off[c];
-            const int hi = (int)h->chr_off[c + 1];
-            while (bi < breaks.size() && breaks[bi] < hi) {
-                if (breaks[bi] > a) h->stretches.push_back({c, a, breaks[bi]});
-                a = breaks[bi++];
-            }
-            if (hi > a) h->stretches.push_back({c, a, hi});
-        }
     }
-    laps.lap("stretches");
+    laps.lap("enqueue");
     h->tables = true; h->have_ld = false; h->bound_W = 0; h->bound_tables_W = 0; h->tables_gen++;
     return 0;
 }
@@ -919,6 +906,36 @@ int garlic_gpu_set_wlod(garlic_gpu_t* h, double mu, int M)
 }
 
 }  // extern "C"
+
+// the break list of set_tables has arrived: sort it into the per-chromosome stretches
+static int ensure_stretches(garlic_gpu* h)
+{
+    if (!h->stretches_pending) return 0;
+    CK(cudaEventSynchronize(h->ev_tables));
+    const unsigned nb = *reinterpret_cast<const unsigned*>(h->brk_pin);
+    const int* first_host = reinterpret_cast<const int*>(h->brk_pin + 64);
+    if (nb > kBreakCap) FAIL("set_tables: more than 2^20 gaps; raise --max-gap");
+    std::vector<int> breaks(first_host, first_host + std::min(nb, kBreakFirst));
+    if (nb > kBreakFirst) {
+        breaks.resize(nb);
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(breaks.data() + kBreakFirst, h->d_breaks + kBreakFirst, (nb - kBreakFirst) * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    std::sort(breaks.begin(), breaks.end());
+    h->stretches.clear();
+    size_t bi = 0;
+    for (int c = 0; c < h->n_chr; ++c) {
+        int a = (int)h->chr_off[c];
+        const int hi = (int)h->chr_off[c + 1];
+        while (bi < breaks.size() && breaks[bi] < hi) {
+            if (breaks[bi] > a) h->stretches.push_back({c, a, breaks[bi]});
+            a = breaks[bi++];
+        }
+        if (hi > a) h->stretches.push_back({c, a, hi});
+    }
+    h->stretches_pending = false;
+    return 0;
+}
 
 static int upload_items(garlic_gpu* h, const std::vector<Item>& items)
 {
@@ -1037,6 +1054,7 @@ static int ensure_geno(garlic_gpu* h, int W_hint)
 static int prepare_p2_items(garlic_gpu* h, int W)
 {
     if (h->p2_gen == h->tables_gen && h->p2_W == W) return 0;
+    if (ensure_stretches(h)) return 1;
     segments_from_stretches(h->stretches, W, h->p2_segs);
     build_items_aligned(h->chr_off, W, h->p2_segs, kPiece * h->item_pieces, h->p2_items);
     h->p2_chunk = 0;
@@ -1137,6 +1155,7 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
     }
     std::vector<Segment> segs;
     std::vector<Item> items;
+    if (ensure_stretches(h)) return 1;                 // (the compaction above is already on the stream)
     segments_from_stretches(h->stretches, W, segs);
     const int64_t slots = garlic_gpu_window_slots(h, step);
     if (dev_alloc(h, &h->d_dump, (size_t)n_lanes * slots)) return 1;
@@ -1252,6 +1271,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
 
     std::vector<Segment> segs;
     std::vector<Item> items;
+    if (ensure_stretches(h)) return 1;
     segments_from_stretches(h->stretches, W, segs);
     int chunk = 0;
     // weighted windows are fresh sums: a chunk only pays its W-1 lead-in windows, so chunks are kept long for the

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <type_traits>
+#include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "walk.cuh"
 #include "wlod.h"
@@ -185,6 +187,183 @@ cudaError_t launch_hom_freq(const int* counts, long long L0, const int* src, lon
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// K6, fused: pair values and window sums of a tile of 32 SNPs j in one CTA, nothing but the weight rows written.
+// LD[w][k] for w + k = j only needs row j of the ordered pair matrix (P[j][d] = pair(i = j + d - (W-1), j)), so the row
+// never has to leave the SM:
+//   stage   the bit-planes of SNPs [j0 - (W-1), j0 + 31 + (W-1)] (contiguous in global memory) and their homFreq /
+//           frequencies go to shared memory, plane rows padded by one word (consecutive SNPs = consecutive lanes:
+//           conflict-free 8-byte reads);
+//   phase 1 a warp takes a row j, keeps j's plane words in registers, lanes take d = lane, lane + 32, …: AND + POPC over
+//           the words of SNP i, then hr2 (garlic-data.cpp:558-583) or, --phased, r2 (:585-617) in the reference's operation
+//           order → P tile in shared memory (row stride 2W-1 doubles, odd);
+//   phase 2 lanes = rows, a thread forms four neighbouring window sums LD[j-k][k], k = 4g … 4g+3, from one pass over the
+//           W+3 entries they share — each sum ascending from 0.0 as the reference adds (:489-494, 521-527);
+//   write   the reciprocals leave through shared memory so that every weight row receives its 32 consecutive k at once.
+// The popcounts are the only part a tensor-core contraction could replace: they are about a third
+// of this kernel, the rest is fp64 division and addition in a fixed order.
+// ------------------------------------------------------------------------------------------
+constexpr int kLdRows = 32;            // SNPs j per CTA
+constexpr int kLdMaxWords = 8;         // plane words per SNP held in registers: n_ld <= 512
+
+struct LdFusedParams {
+    const uint64_t* planes; int nw;    // [L][np * nw]
+    const double* hf;                  // homFreq[L] (hr2) or freq[L] (r2)
+    const int* chr_of; const int* chr_start; int n_chr;
+    long long L; int W;
+    double* invld; double* ld_out;
+};
+
+// shared-memory layout: [planes | homFreq] and, aliasing them once phase 1 is over, the result tile [32][W + 1]; then P
+__host__ __device__ inline size_t ld_fused_p_offset(int W, int nw, int np)
+{
+    const size_t span = kLdRows + 2 * (size_t)(W - 1);
+    const size_t a = span * (size_t)(np * nw + 1) * 8 + (span + (span & 1)) * 8;
+    const size_t b = (size_t)kLdRows * (W + 1) * 8;
+    return ((a > b ? a : b) + 15) & ~(size_t)15;
+}
+
+template <bool PHASED>
+__global__ void __launch_bounds__(256)
+ld_band_fused_kernel(const LdFusedParams Q)
+{
+    extern __shared__ __align__(16) unsigned char ld_smem[];
+    constexpr int NP = PHASED ? 4 : 2;
+    const int W = Q.W, D = 2 * W - 1, nw = Q.nw;
+    const int span = kLdRows + 2 * (W - 1);                 // SNPs whose planes the tile touches
+    const int rw = NP * nw + 1;                             // padded plane row, in words
+    uint64_t* s_pl = reinterpret_cast<uint64_t*>(ld_smem);                       // [span][rw]
+    double* s_hf = reinterpret_cast<double*>(s_pl + (size_t)span * rw);           // [span]
+    double* s_P = reinterpret_cast<double*>(ld_smem + ld_fused_p_offset(W, nw, NP));  // [32][D]
+    double* s_R = reinterpret_cast<double*>(ld_smem);                             // [32][W + 1], aliases the planes after phase 1
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long n_tiles = (Q.L + kLdRows - 1) / kLdRows;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long j0 = tile * kLdRows, s_lo = j0 - (W - 1);
+        __syncthreads();                                    // the previous tile's results have been written out
+        // ---- stage
+        for (long long e = threadIdx.x; e < (long long)span * NP * nw; e += 256) {
+            const int r = (int)(e / (NP * nw)), c = (int)(e % (NP * nw));
+            const long long s = s_lo + r;
+            s_pl[(size_t)r * rw + c] = (s >= 0 && s < Q.L) ? Q.planes[s * NP * nw + c] : 0ull;
+        }
+        for (int r = threadIdx.x; r < span; r += 256) {
+            const long long s = s_lo + r;
+            s_hf[r] = (s >= 0 && s < Q.L) ? Q.hf[s] : 0.0;
+        }
+        __syncthreads();
+        // ---- phase 1: P[jj][d]
+        for (int jj = warp; jj < kLdRows; jj += 8) {
+            const long long j = j0 + jj;
+            if (j >= Q.L) break;                            // (warp-uniform)
+            const int rj = jj + (W - 1);
+            uint64_t bj[NP * kLdMaxWords];
+#pragma unroll
+            for (int c = 0; c < NP * kLdMaxWords; ++c) bj[c] = (c % kLdMaxWords) < nw ? s_pl[(size_t)rj * rw + (c / kLdMaxWords) * nw + (c % kLdMaxWords)] : 0ull;
+            const int cj = Q.chr_of[j];
+            const long long lo = Q.chr_start[cj], hi = (cj + 1 < Q.n_chr) ? Q.chr_start[cj + 1] : Q.L;
+            const double HB = s_hf[rj];
+            for (int d = lane; d < D; d += 32) {
+                const long long i = j + d - (W - 1);
+                const int ri = jj + d;
+                double v = 0.0;
+                if (i == j) v = 1.0;
+                else if (i >= lo && i < hi) {
+                    const double HA = s_hf[ri];
+                    if (HA > 0 && HA < 1 && HB > 0 && HB < 1) {
+                        const uint64_t* a = s_pl + (size_t)ri * rw;
+                        int tot = 0, x = 0;
+#pragma unroll
+                        for (int w = 0; w < kLdMaxWords; ++w) {
+                            if (w < nw) {
+                                tot += __popcll(a[w] & bj[w]);
+                                if (PHASED) {
+                                    const uint64_t a2 = a[nw + w], b2 = bj[kLdMaxWords + w], a1 = a[2 * nw + w], b1 = bj[2 * kLdMaxWords + w];
+                                    x += 2 * __popcll(a2 & b2) + __popcll(a1 & b2) + __popcll(a2 & b1) +
+                                         __popcll(a1 & b1 & ~(a[3 * nw + w] ^ bj[3 * kLdMaxWords + w]));
+                                } else {
+                                    x += __popcll(a[nw + w] & bj[kLdMaxWords + w]);
+                                }
+                            }
+                        }
+                        if (PHASED) {                       // r2(), garlic-data.cpp:585-617 (A = SNP i, B = SNP j)
+                            double x11 = (double)x;
+                            x11 /= (double)(2 * tot);
+                            const double Dv = x11 - HA * HB;
+                            const double R2 = Dv * Dv / (HA * (1 - HA) * HB * (1 - HB));
+                            v = (R2 > 1) ? 1.0 : R2;
+                        } else {                            // hr2(), garlic-data.cpp:558-583
+                            double HAB = (double)x, total_d = (double)tot;
+                            HAB /= total_d;
+                            const double H = HAB - HA * HB;
+                            const double HR2 = H * H / (HA * (1 - HA) * HB * (1 - HB));
+                            v = (HR2 > 1) ? 1.0 : HR2;
+                        }
+                    }
+                }
+                s_P[(size_t)jj * D + d] = v;
+            }
+        }
+        __syncthreads();                                    // P complete; the planes are dead from here on
+        // ---- phase 2: window sums, lanes = rows
+        {
+            const int jj = lane;
+            const long long j = j0 + jj;
+            const bool row_on = j < Q.L;
+            long long lo = 0, hi = 0;
+            if (row_on) { const int cj = Q.chr_of[j]; lo = Q.chr_start[cj]; hi = (cj + 1 < Q.n_chr) ? Q.chr_start[cj + 1] : Q.L; }
+            const double* prow = s_P + (size_t)jj * D;
+            const int n_groups = (W + 3) >> 2;
+            for (int g = warp; g < n_groups; g += 8) {
+                const int k0 = 4 * g;                       // k0 … k0+3; the slice of k starts at W-1-k
+                const int base = W - 1 - (k0 + 3);          // first entry any of the four slices reads (may be < 0 for k > W-1)
+                double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+                if (row_on) {
+                    for (int n = 0; n < W + 3; ++n) {
+                        const int idx = base + n;
+                        const double v = (idx >= 0 && idx < D) ? prow[idx] : 0.0;
+                        if (n >= 3 && n < 3 + W) acc0 += v;     // k0:     entries base+3 … base+3+W-1
+                        if (n >= 2 && n < 2 + W) acc1 += v;     // k0 + 1
+                        if (n >= 1 && n < 1 + W) acc2 += v;     // k0 + 2
+                        if (n < W) acc3 += v;                   // k0 + 3
+                    }
+                }
+                double* r = s_R + (size_t)jj * (W + 1) + k0;
+                r[0] = acc0;
+                if (k0 + 1 < W) r[1] = acc1;
+                if (k0 + 2 < W) r[2] = acc2;
+                if (k0 + 3 < W) r[3] = acc3;
+            }
+            (void)lo; (void)hi;
+        }
+        __syncthreads();
+        // ---- write: weight row w receives k = j - w for the tile's j: consecutive k, consecutive lanes
+        {
+            const int ldw = W + kInvFront + kInvBack;
+            const int n_w = kLdRows + W - 1;                // rows w = j0 - (W-1) … j0 + 31
+            for (int wi = warp; wi < n_w; wi += 8) {
+                const long long w = j0 - (W - 1) + wi;
+                if (w < 0 || w >= Q.L) continue;
+                const int cw = Q.chr_of[w];
+                const long long lo = Q.chr_start[cw], hi = (cw + 1 < Q.n_chr) ? Q.chr_start[cw + 1] : Q.L;
+                if (w < lo || w >= hi - W + 1) continue;    // no window starts here (the row stays zero)
+                const int jj = lane;                        // j = j0 + jj, k = j - w
+                const long long k = j0 + jj - w;
+                if (k >= 0 && k < W && j0 + jj < Q.L) {
+                    const double acc = s_R[(size_t)jj * (W + 1) + k];
+                    Q.invld[w * ldw + kInvFront + k] = 1.0 / acc;
+                    if (Q.ld_out) Q.ld_out[w * W + k] = acc;
+                }
+            }
+        }
+    }
+}
+
+static size_t ld_fused_smem(int W, int nw, bool phased)
+{
+    return ld_fused_p_offset(W, nw, phased ? 4 : 2) + (size_t)kLdRows * (2 * W - 1) * 8;
+}
+
 size_t ld_planes_words(long long L, int n_ld, bool phased) { return (size_t)L * (phased ? 4 : 2) * ((n_ld + 63) / 64); }
 size_t ld_pairs_doubles(long long L, int W) { return (size_t)L * (2 * W - 1); }
 
@@ -203,6 +382,29 @@ cudaError_t launch_ld_band(const uint64_t* geno, int64_t row_words, const int* l
     if (comm) {
         const ncclResult_t nr = ncclAllReduce(planes, planes, (size_t)L * np * nw, ncclUint64, ncclSum, comm, st);
         if (nr != ncclSuccess) return cudaErrorUnknown;
+    }
+    // fused pair values + window sums while a tile's rows fit in shared memory (n_ld <= 512 and moderate W); the ordered pair
+    // matrix in global memory (P) is the general form
+    const size_t fused_smem = ld_fused_smem(W, nw, ph.alleles != nullptr);
+    if (nw <= kLdMaxWords && fused_smem <= 200 * 1024 && getenv("GARLIC_LD_UNFUSED") == nullptr) {
+        LdFusedParams Q;
+        Q.planes = planes; Q.nw = nw; Q.hf = ph.alleles ? ph.freq : homf; Q.chr_of = chr_of; Q.chr_start = chr_start; Q.n_chr = n_chr;
+        Q.L = L; Q.W = W; Q.invld = invld; Q.ld_out = ld_out;
+        if (ld_out) cudaMemsetAsync(ld_out, 0, (size_t)L * W * sizeof(double), st);
+        const long long n_tiles = (L + kLdRows - 1) / kLdRows;
+        const unsigned grid = (unsigned)std::min<long long>(n_tiles, 148ll * 16);
+        cudaError_t e;
+        if (ph.alleles) {
+            e = cudaFuncSetAttribute(ld_band_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem);
+            if (e != cudaSuccess) return e;
+            ld_band_fused_kernel<true><<<grid, 256, fused_smem, st>>>(Q);
+        } else {
+            e = cudaFuncSetAttribute(ld_band_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem);
+            if (e != cudaSuccess) return e;
+            ld_band_fused_kernel<false><<<grid, 256, fused_smem, st>>>(Q);
+        }
+        *n_launches = 2;
+        return cudaGetLastError();
     }
     if (ph.alleles) ld_pairs_r2_kernel<<<blocks(L * (2 * W - 1)), 256, 0, st>>>(planes, nw, ph.freq, chr_of, chr_start, n_chr, L, W, P);
     else ld_pairs_kernel<<<blocks(L * (2 * W - 1)), 256, 0, st>>>(planes, nw, homf, chr_of, chr_start, n_chr, L, W, P);

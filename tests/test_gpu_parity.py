@@ -665,6 +665,30 @@ def test_k0_tped_text_tokeniser_equals_allele_upload():
     g.close()
 
 
+@pytest.mark.parametrize("n_ld,W", [(500, 40), (130, 25), (64, 33), (350, 72)])
+def test_ld_band_fused_kernel_many_individuals(n_ld, W):
+    """K6 with several plane words per SNP (the C3 shape: 500 LD individuals = 8 words): the fused pair + window-sum kernel
+    is bit-identical to the oracle's calcHR2LD restatement (garlic-data.cpp:474-527,558-583) and to the unfused
+    kernels (ordered pair matrix in global memory, GARLIC_LD_UNFUSED=1)."""
+    import os
+    ds = synth.make_dataset(seed=21, n_ind=520, chr_sizes=(420, 380), with_map=True, n_roh=2, roh_snps=(40, 120))
+    sub = np.sort(np.random.default_rng(2).choice(520, n_ld, replace=False)).astype(np.int32)
+    res = orc.run_pipeline(ds, W, 0.001, 0.5, 0.25, weighted=True, cm=True, ld_individuals=sub)
+    want = np.concatenate([c["LD"] for c in res["chroms"]], axis=0)
+    hp = HotPath().load(ds, weighted=True, cm=True, error=0.001)
+    got = hp.g.ld_band(W, sub, want_ld=True)
+    assert np.array_equal(got, want, equal_nan=True)
+    os.environ["GARLIC_LD_UNFUSED"] = "1"
+    try:
+        assert np.array_equal(hp.g.ld_band(W, sub, want_ld=True), want, equal_nan=True)
+    finally:
+        os.environ.pop("GARLIC_LD_UNFUSED")
+    close_windows(hp.g.windows(W, 1, weighted=True), oracle_windows_matrix(res))
+    got_roh = hp.roh(W, 0.5, 0.25, weighted=True, cm=True)
+    assert [(r[0], r[1], r[5], r[6]) for r in got_roh] == oracle_roh_idx(res)
+    hp.close()
+
+
 def test_phased_r2_ld_band_wlod_and_roh():
     """--weighted --phased: the LD band from r2 between haplotypes (first-copy bits read from the allele block, four
     bit-planes, popcounts) is bit-identical to the oracle's restatement of calcR2LD; windows within 1e-9, ROH and BED
