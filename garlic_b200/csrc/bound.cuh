@@ -36,13 +36,21 @@ namespace garlic {
 constexpr int kBoundShift = 8;          // fixed-point scale of the bound: 1/256
 constexpr int kBoundStoreShift = 2;     // the stored maxima are >> 2 (rounded up): int16 covers +-512 LOD
 constexpr int kPiece = 256;             // SNPs per piece = 16 half-words = 8 packed words
-constexpr int kBoundMinW = 32;          // below: no half-word lies inside every window of a block (empty core)
-constexpr int kBoundMaxC2 = 13;         // ring of 16 prefix sums per lane: W <= 209
+constexpr int kBoundMinW = 16;          // below: the windows of a 16-start block share no SNP but one
+constexpr int kBoundPartialW = 32;      // below: no whole half-word lies inside every window of a block — the core is the
+                                        // block's last SNP plus the first W - 16 SNPs of the next half-word (bound_step<…, true>)
+constexpr int kBoundMaxC2 = 13;         // ring of 16 prefix sums per lane: geometry of window sizes up to 209
+constexpr int kBoundGeomMaxW = 209;     // larger windows: this geometry for their first 209 SNPs, the remaining W - 209 SNPs
+                                        // enter Bmax with the larger homozygote's value (bound_block_max), whatever the genotype
 constexpr int kPlanSegMax = 16;
 
-GHD int bound_c2(int W) { return (W + 14) >> 4; }
-GHD int bound_c1(int W) { const int c = (W - 16) >> 4; return c > 0 ? c : 0; }
+GHD int bound_geom_w(int W) { return W > kBoundGeomMaxW ? kBoundGeomMaxW : W; }
+GHD int bound_c2(int W) { return (bound_geom_w(W) + 14) >> 4; }
+GHD int bound_c1(int W) { const int c = (bound_geom_w(W) - 16) >> 4; return c > 0 ? c : 0; }
 GHD int bound_lag(int W) { return bound_c2(W) - bound_c1(W); }   // 1 or 2 for W >= kBoundMinW
+GHD bool bound_partial(int W) { return W < kBoundPartialW; }
+// even-bit mask of the SNPs of half-word k + c1 + 1 that every window of block k contains: its first (W - 16) & 15
+GHD uint32_t bound_low_mask(int W) { const int r = (bound_geom_w(W) - 16) & 15; return r ? ((1u << (2 * r)) - 1u) & 0x55555555u : 0u; }
 
 // Per half-word table entry, one 16-byte load per step:
 //   x = orientation (even bits: bit 2i set <=> genotype 2 is the "rare" homozygote at SNP 16q+i) | plane p0 << 1 (odd bits)
@@ -89,17 +97,29 @@ GHD uint4 bound_hw_entry(const double* lut, long long q, long long L, int* inval
     return o;
 }
 
-// Bmax[k] in fixed point, rounded up (+2 of slack for the fp64 sums)
+// Bmax[k] in fixed point, rounded up (+2 of slack for the fp64 sums): the largest, over the 16 window starts t of
+// block k, of  sum_{s in [t, t+Wg)} base[s]  +  sum_{s in [t+Wg, t+W)} top[s],  Wg = bound_geom_w(W) — the second sum
+// (window sizes beyond the ring's geometry) takes every SNP at its best genotype, top[s] = max(lut[s][0], lut[s][2]).
 GHD int bound_block_max(const double* lut, long long k, int W)
 {
+    const int Wg = bound_geom_w(W);
     const long long s0 = k * 16;
     double b = 0.0;
-    for (int i = 0; i < W; ++i) { const double* e = lut + (s0 + i) * 4; b += e[0] < e[2] ? e[0] : e[2]; }
+    for (int i = 0; i < Wg; ++i) { const double* e = lut + (s0 + i) * 4; b += e[0] < e[2] ? e[0] : e[2]; }
+    for (int i = Wg; i < W; ++i) { const double* e = lut + (s0 + i) * 4; b += e[0] < e[2] ? e[2] : e[0]; }
     double bmax = b;
     for (int j = 1; j < 16; ++j) {
-        const double* eo = lut + (s0 + j - 1) * 4;
-        const double* ei = lut + (s0 + j - 1 + W) * 4;
-        b = b - (eo[0] < eo[2] ? eo[0] : eo[2]) + (ei[0] < ei[2] ? ei[0] : ei[2]);
+        const double* eo = lut + (s0 + j - 1) * 4;            // leaves the base part
+        const double* ei = lut + (s0 + j - 1 + W) * 4;        // enters the last part
+        b -= (eo[0] < eo[2] ? eo[0] : eo[2]);
+        if (W > Wg) {
+            const double* em = lut + (s0 + j - 1 + Wg) * 4;   // moves from the optimistic part to the base part
+            b -= (em[0] < em[2] ? em[2] : em[0]);
+            b += (em[0] < em[2] ? em[0] : em[2]);
+            b += (ei[0] < ei[2] ? ei[2] : ei[0]);
+        } else {
+            b += (ei[0] < ei[2] ? ei[0] : ei[2]);
+        }
         if (b > bmax) bmax = b;
     }
     const double v = ceil(bmax * (double)(1 << kBoundShift)) + 2.0;
@@ -111,6 +131,7 @@ GHD int bound_block_max(const double* lut, long long k, int W)
 struct BoundState {
     uint32_t PH[16], PR[16];   // modular arithmetic: only differences over at most 16 half-words are used
     uint32_t ph, pr;
+    uint32_t top1, top2, low1; // PARTIAL: het term of the last SNP of the previous two half-words, low-mask term of the previous one
     int pm_all, pm_tail;
 };
 
@@ -121,14 +142,19 @@ GHD void bound_reset(BoundState& S)
 #endif
     for (int i = 0; i < 16; ++i) { S.PH[i] = 0u; S.PR[i] = 0u; }
     S.ph = 0u; S.pr = 0u;
+    S.top1 = 0u; S.top2 = 0u; S.low1 = 0u;
     S.pm_all = -0x40000000; S.pm_tail = -0x40000000;
 }
 
 // One half-word h (16 genotypes) at ring position I = q & 15 (a constant after unrolling: the ring stays in registers);
-// evaluates block k = q - C2, whose Bmax is t.w.  LAG = C2 - c1: 1 or 2 (window sizes >= 32: the core is not empty).
-// PH accumulates the magnitude of the (negative) het term.
-template <int C2, int LAG>
-GHD void bound_step(BoundState& S, uint32_t h, const uint4& t, const int I)
+// evaluates block k = q - C2, whose Bmax is t.w.  LAG = C2 - c1: 1 or 2.  PH accumulates the magnitude of the (negative)
+// het term.
+// PARTIAL = false (W >= 32): the het term counts the whole half-words k+1 … k+c1 every window of the block contains.
+// PARTIAL = true (16 <= W < 32, where c1 = 0): it counts exactly the SNPs those windows share, [16k + 15, 16k + W) — the
+// last SNP of half-word k and the first W - 16 of half-word k + 1 (low_mask).  The ring then holds the prefix up to
+// SNP 14 of each half-word, the two scalars the last-SNP terms of the two half-words before this one.
+template <int C2, int LAG, bool PARTIAL = false>
+GHD void bound_step(BoundState& S, uint32_t h, const uint4& t, const int I, const uint32_t low_mask = 0u)
 {
     const uint32_t M = 0x55555555u;
     const uint32_t s = h >> 1;
@@ -136,9 +162,24 @@ GHD void bound_step(BoundState& S, uint32_t h, const uint4& t, const int I)
     const uint32_t x = ~h & ~(s ^ t.x);                // even bits: homozygous with the "rare" orientation
     const int n0 = popc32(x & (t.x >> 1) & M), n1 = popc32(x & t.y), nh = popc32(het);
     S.pr += (uint32_t)(n0 + 2 * n1) * (t.z & 0xffffu);
-    S.ph += (uint32_t)nh * (t.z >> 16);
-    S.PR[I] = S.pr; S.PH[I] = S.ph;
-    const int ub = (int)t.w + (int)(S.pr - S.PR[(I - C2 - 1) & 15]) + (int)(S.PH[(I - C2) & 15] - S.PH[(I - LAG) & 15]);
+    S.PR[I] = S.pr;
+    int ub;
+    if (!PARTIAL) {
+        S.ph += (uint32_t)nh * (t.z >> 16);
+        S.PH[I] = S.ph;
+        ub = (int)t.w + (int)(S.pr - S.PR[(I - C2 - 1) & 15]) + (int)(S.PH[(I - C2) & 15] - S.PH[(I - LAG) & 15]);
+    } else {
+        const uint32_t ch = t.z >> 16;
+        const uint32_t top = ((het >> 30) & 1u) * ch, low = (uint32_t)popc32(het & low_mask) * ch;
+        S.PH[I] = S.ph + (uint32_t)nh * ch - top;      // prefix up to SNP 14 of this half-word
+        S.ph += (uint32_t)nh * ch;
+        // het magnitude over [16k + 15, end of half-word q - LAG] + the low part of half-word q - LAG + 1
+        const uint32_t top_lag = LAG == 1 ? S.top1 : S.top2;
+        const uint32_t low_next = LAG == 1 ? low : S.low1;
+        const uint32_t core = (S.PH[(I - LAG) & 15] + top_lag) - S.PH[(I - C2) & 15] + low_next;
+        ub = (int)t.w + (int)(S.pr - S.PR[(I - C2 - 1) & 15]) - (int)core;
+        S.top2 = S.top1; S.top1 = top; S.low1 = low;
+    }
     S.pm_all = ub > S.pm_all ? ub : S.pm_all;
     if (((I - C2) & 15) >= 16 - C2) S.pm_tail = ub > S.pm_tail ? ub : S.pm_tail;   // compile-time condition
 }
@@ -163,14 +204,19 @@ GHD int bound_cut_store(double cutoff, double tol, int* ok)
     return s;
 }
 
-// Is (individual, item) a candidate?  Windows the item's walk evaluates start in [w0, own_hi): pieces own_lo>>8 ..
-// (own_hi-1)>>8 in full, and — when the lead-in starts in the piece before — that piece's last C2 blocks.
-GHD bool bound_item_candidate(const uint32_t* pmax, int64_t stride, int ind, const Item& it, int cut_store)
+// Is (individual, item) a candidate?  Windows the item's walk evaluates start in [w0, own_hi): the pieces of own_lo …
+// own_hi - 1 in full; of the lead-in (w0 < own_lo) the pieces before them in full too, except that the piece of w0 only
+// contributes its last C2 blocks when the lead-in starts inside those (always, for window sizes up to 209).
+GHD bool bound_item_candidate(const uint32_t* pmax, int64_t stride, int ind, const Item& it, int cut_store, int c2)
 {
     const int p_own = it.own_lo >> 8, p_hi = (it.own_hi - 1) >> 8, p_w0 = it.w0 >> 8;
     bool c = false;
-    for (int p = p_own; p <= p_hi; ++p) c |= (int)(int16_t)(pmax[(int64_t)p * stride + ind] & 0xffffu) >= cut_store;
-    if (p_w0 < p_own) c |= (int)(int16_t)(pmax[(int64_t)p_w0 * stride + ind] >> 16) >= cut_store;
+    for (int p = (p_w0 < p_own ? p_w0 + 1 : p_own); p <= p_hi; ++p) c |= (int)(int16_t)(pmax[(int64_t)p * stride + ind] & 0xffffu) >= cut_store;
+    if (p_w0 < p_own) {
+        const uint32_t v = pmax[(int64_t)p_w0 * stride + ind];
+        const bool tail_covers = it.w0 >= 256 * (p_w0 + 1) - 16 * c2;
+        c |= (int)(int16_t)(tail_covers ? (v >> 16) : (v & 0xffffu)) >= cut_store;
+    }
     return c;
 }
 

@@ -990,7 +990,7 @@ static int launch_any_walk(garlic_gpu* h, const WalkParams& P, const Item* items
 // ---- deferred compaction (K3) and the pruning bound (squeeze.cu, bound.cuh) ----
 static bool can_bound(const garlic_gpu* h, int W)
 {
-    return h->prune && h->tables && !h->have_gl && W >= kBoundMinW && bound_c2(W) <= kBoundMaxC2;
+    return h->prune && h->tables && !h->have_gl && W >= kBoundMinW && W <= 1280;   // (a piece plus its lead-in must fit the walker's table tile)
 }
 
 static int ensure_bound_tables(garlic_gpu* h, int W)
@@ -1017,6 +1017,8 @@ static SqueezeParams squeeze_params(garlic_gpu* h, bool squeeze, int W)
     Q.n_ind = h->n_ind;
     Q.hw = h->d_bhw;
     Q.lag = bound_lag(W);
+    Q.partial = (W > 0 && bound_partial(W)) ? 1 : 0;
+    Q.low_mask = W > 0 ? bound_low_mask(W) : 0u;
     Q.pmax = h->d_pmax; Q.pmax_stride = h->pmax_stride;
     Q.n_pieces = h->n_pieces;
     return Q;
@@ -1350,7 +1352,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
             if (dev_alloc(h, &h->d_nunits, (size_t)4)) return 1;
             CK(cudaMemsetAsync(h->d_nunits, 0, 4 * sizeof(unsigned), h->stream));
             LAUNCH(launch_select(d_its, n_its, h->d_pmax, h->pmax_stride, h->n_ind, cut_store, h->d_bflag,
-                                 h->d_cand_list, h->n_ind, h->d_cand_cnt, h->d_units, h->d_nunits, unit_cap, kUnitThreads, h->stream));
+                                 h->d_cand_list, h->n_ind, h->d_cand_cnt, h->d_units, h->d_nunits, unit_cap, kUnitThreads, bound_c2(W), h->stream));
             cl.list = h->d_cand_list; cl.cnt = h->d_cand_cnt; cl.stride = h->n_ind;
         }
         CK(cudaEventRecord(h->ev2, h->stream));
@@ -1497,7 +1499,7 @@ int garlic_gpu_get_piece_bounds(garlic_gpu_t* h, int winsize, uint32_t* out, int
 {
     CK(cudaSetDevice(h->device));
     if (!h->tables) FAIL("get_piece_bounds: call set_tables first");
-    if (!can_bound(h, winsize)) FAIL("get_piece_bounds: no bound for this mode / window size (unweighted table mode, 32 <= winsize <= 209)");
+    if (!can_bound(h, winsize)) FAIL("get_piece_bounds: no bound for this mode / window size (unweighted table mode, winsize >= 16)");
     if (ensure_bound(h, winsize)) return 1;
     if (n_pieces) *n_pieces = h->n_pieces;
     if ((int64_t)h->n_pieces * h->n_ind > cap_entries) FAIL("get_piece_bounds: output buffer too small");

@@ -40,6 +40,8 @@ struct SqueezeParams {
     int n_ind;
     const uint4* hw;           // bound tables per half-word (bound.cuh:bound_hw_entry; w = Bmax of block q - C2)
     int lag;                   // C2 - c1: 1 or 2
+    int partial;               // window sizes below 32: partial-half-word core (bound.cuh)
+    uint32_t low_mask;         // bound_low_mask(W)
     uint32_t* pmax;            // [n_pieces][pmax_stride]: piece maxima per individual (bound.cuh:bound_pack)
     int64_t pmax_stride;
     int n_pieces, pieces_per_task, n_col_tasks;
@@ -51,7 +53,7 @@ cudaError_t launch_plan(const int* src, const int* n_kept, long long n_q, uint4*
 cudaError_t launch_squeeze_bound(SqueezeParams P, bool squeeze, int c2, cudaStream_t st);
 cudaError_t launch_select(const Item* items, int n_items, const uint32_t* pmax, int64_t stride, int n_ind, int cut_store,
                           const int* invalid, int* cand_list, int cand_stride, unsigned* cand_cnt, int2* units, unsigned* n_units,
-                          unsigned unit_cap, int lanes_per_unit, cudaStream_t st);
+                          unsigned unit_cap, int lanes_per_unit, int c2, cudaStream_t st);
 cudaError_t launch_thin_windows(const uint64_t* geno, int64_t row_words, const double* lut, const int* ind_list, int n_lanes,
                                 const int3* segs, int n_segs, const int2* meta, int n_chr, long long n_slots, int step, int W,
                                 double* dump, int64_t dump_stride, const double* gl, int64_t gl_stride, cudaStream_t st);

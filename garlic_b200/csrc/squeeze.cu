@@ -123,7 +123,7 @@ cudaError_t launch_plan(const int* src, const int* n_kept, long long n_q, uint4*
 // ------------------------------------------------------------------------------------------
 // the fused pass
 // ------------------------------------------------------------------------------------------
-template <bool SQUEEZE, bool BOUND, int C2, int LAG>
+template <bool SQUEEZE, bool BOUND, int C2, int LAG, bool PARTIAL>
 __global__ void __launch_bounds__(kSqWarps * 32)
 squeeze_bound_kernel(const SqueezeParams P)
 {
@@ -285,7 +285,7 @@ squeeze_bound_kernel(const SqueezeParams P)
 #pragma unroll
                 for (int I = 0; I < 16; ++I) {
                     const long long q = qb + I;
-                    bound_step<C2, LAG>(S, hreg[I], sh_tab[I], I);
+                    bound_step<C2, LAG, PARTIAL>(S, hreg[I], sh_tab[I], I, P.low_mask);
                     if (((I - C2) & 15) == 15) {           // block k = q - C2 closes its piece
                         const int piece = (int)((q - C2) >> 4);
                         if (piece >= pc_lo && piece < pc_hi && active)
@@ -314,10 +314,10 @@ squeeze_bound_kernel(const SqueezeParams P)
     }
 }
 
-template <bool SQUEEZE, bool BOUND, int C2, int LAG>
+template <bool SQUEEZE, bool BOUND, int C2, int LAG, bool PARTIAL>
 static cudaError_t launch_sq_t(const SqueezeParams& P, unsigned grid, size_t smem, cudaStream_t st)
 {
-    auto kern = squeeze_bound_kernel<SQUEEZE, BOUND, C2, LAG>;
+    auto kern = squeeze_bound_kernel<SQUEEZE, BOUND, C2, LAG, PARTIAL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kSqWarps * 32, smem, st>>>(P);
@@ -328,20 +328,29 @@ template <bool SQUEEZE, int LAG>
 static cudaError_t launch_sq_c2(const SqueezeParams& P, int c2, unsigned grid, size_t smem, cudaStream_t st)
 {
     switch (c2) {
-        case 2: return launch_sq_t<SQUEEZE, true, 2, LAG>(P, grid, smem, st);
-        case 3: return launch_sq_t<SQUEEZE, true, 3, LAG>(P, grid, smem, st);
-        case 4: return launch_sq_t<SQUEEZE, true, 4, LAG>(P, grid, smem, st);
-        case 5: return launch_sq_t<SQUEEZE, true, 5, LAG>(P, grid, smem, st);
-        case 6: return launch_sq_t<SQUEEZE, true, 6, LAG>(P, grid, smem, st);
-        case 7: return launch_sq_t<SQUEEZE, true, 7, LAG>(P, grid, smem, st);
-        case 8: return launch_sq_t<SQUEEZE, true, 8, LAG>(P, grid, smem, st);
-        case 9: return launch_sq_t<SQUEEZE, true, 9, LAG>(P, grid, smem, st);
-        case 10: return launch_sq_t<SQUEEZE, true, 10, LAG>(P, grid, smem, st);
-        case 11: return launch_sq_t<SQUEEZE, true, 11, LAG>(P, grid, smem, st);
-        case 12: return launch_sq_t<SQUEEZE, true, 12, LAG>(P, grid, smem, st);
-        case 13: return launch_sq_t<SQUEEZE, true, 13, LAG>(P, grid, smem, st);
+        case 2: return launch_sq_t<SQUEEZE, true, 2, LAG, false>(P, grid, smem, st);
+        case 3: return launch_sq_t<SQUEEZE, true, 3, LAG, false>(P, grid, smem, st);
+        case 4: return launch_sq_t<SQUEEZE, true, 4, LAG, false>(P, grid, smem, st);
+        case 5: return launch_sq_t<SQUEEZE, true, 5, LAG, false>(P, grid, smem, st);
+        case 6: return launch_sq_t<SQUEEZE, true, 6, LAG, false>(P, grid, smem, st);
+        case 7: return launch_sq_t<SQUEEZE, true, 7, LAG, false>(P, grid, smem, st);
+        case 8: return launch_sq_t<SQUEEZE, true, 8, LAG, false>(P, grid, smem, st);
+        case 9: return launch_sq_t<SQUEEZE, true, 9, LAG, false>(P, grid, smem, st);
+        case 10: return launch_sq_t<SQUEEZE, true, 10, LAG, false>(P, grid, smem, st);
+        case 11: return launch_sq_t<SQUEEZE, true, 11, LAG, false>(P, grid, smem, st);
+        case 12: return launch_sq_t<SQUEEZE, true, 12, LAG, false>(P, grid, smem, st);
+        case 13: return launch_sq_t<SQUEEZE, true, 13, LAG, false>(P, grid, smem, st);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// window sizes below 32: the core is a partial half-word (bound.cuh: bound_step<…, true>), C2 = LAG = 1 or 2
+template <bool SQUEEZE>
+static cudaError_t launch_sq_partial(const SqueezeParams& P, int c2, unsigned grid, size_t smem, cudaStream_t st)
+{
+    if (c2 == 1) return launch_sq_t<SQUEEZE, true, 1, 1, true>(P, grid, smem, st);
+    if (c2 == 2) return launch_sq_t<SQUEEZE, true, 2, 2, true>(P, grid, smem, st);
+    return cudaErrorInvalidValue;
 }
 
 // pieces per warp task: enough tasks for a few waves of 12 warps per SM, an even number of pieces (the output
@@ -369,8 +378,9 @@ cudaError_t launch_squeeze_bound(SqueezeParams P, bool squeeze, int c2, cudaStre
     const size_t smem = (size_t)kSqWarps * kSqWarpBytes;
     if (c2 <= 0) {
         if (!squeeze) return cudaErrorInvalidValue;
-        return launch_sq_t<true, false, 2, 1>(P, (unsigned)grid, smem, st);
+        return launch_sq_t<true, false, 2, 1, false>(P, (unsigned)grid, smem, st);
     }
+    if (P.partial) return squeeze ? launch_sq_partial<true>(P, c2, (unsigned)grid, smem, st) : launch_sq_partial<false>(P, c2, (unsigned)grid, smem, st);
     if (P.lag == 1) return squeeze ? launch_sq_c2<true, 1>(P, c2, (unsigned)grid, smem, st) : launch_sq_c2<false, 1>(P, c2, (unsigned)grid, smem, st);
     if (P.lag == 2) return squeeze ? launch_sq_c2<true, 2>(P, c2, (unsigned)grid, smem, st) : launch_sq_c2<false, 2>(P, c2, (unsigned)grid, smem, st);
     return cudaErrorInvalidValue;
@@ -385,7 +395,7 @@ __global__ void __launch_bounds__(256)
 select_kernel(const Item* __restrict__ items, int n_items, const uint32_t* __restrict__ pmax, int64_t stride, int n_ind,
               int cut_store, const int* __restrict__ invalid, int* __restrict__ cand_list, int cand_stride,
               unsigned* __restrict__ cand_cnt, int2* __restrict__ units, unsigned* __restrict__ n_units, unsigned unit_cap,
-              int lanes_per_unit)
+              int lanes_per_unit, int c2)
 {
     __shared__ int s_w[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -395,7 +405,7 @@ select_kernel(const Item* __restrict__ items, int n_items, const uint32_t* __res
         // a thread takes individuals t, t + 256, …: all of its loads are independent, one block scan per item; the
         // list comes out ordered by (thread, individual) — any order will do, the runs are sorted afterwards
         int mine = 0;
-        for (int ind = threadIdx.x; ind < n_ind; ind += 256) mine += bound_item_candidate(pmax, stride, ind, it, cut_store) ? 1 : 0;
+        for (int ind = threadIdx.x; ind < n_ind; ind += 256) mine += bound_item_candidate(pmax, stride, ind, it, cut_store, c2) ? 1 : 0;
         int incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -409,7 +419,7 @@ select_kernel(const Item* __restrict__ items, int n_items, const uint32_t* __res
         if (mine) {
             int* list = cand_list + (int64_t)item * cand_stride;
             for (int ind = threadIdx.x; ind < n_ind; ind += 256)
-                if (bound_item_candidate(pmax, stride, ind, it, cut_store)) list[pos++] = ind;
+                if (bound_item_candidate(pmax, stride, ind, it, cut_store, c2)) list[pos++] = ind;
         }
         if (threadIdx.x == 0) {
             cand_cnt[item] = (unsigned)total;
@@ -426,12 +436,12 @@ select_kernel(const Item* __restrict__ items, int n_items, const uint32_t* __res
 
 cudaError_t launch_select(const Item* items, int n_items, const uint32_t* pmax, int64_t stride, int n_ind, int cut_store,
                           const int* invalid, int* cand_list, int cand_stride, unsigned* cand_cnt, int2* units, unsigned* n_units,
-                          unsigned unit_cap, int lanes_per_unit, cudaStream_t st)
+                          unsigned unit_cap, int lanes_per_unit, int c2, cudaStream_t st)
 {
     if (!n_items || !n_ind) return cudaSuccess;
     const int grid = n_items < 148 * 8 ? n_items : 148 * 8;
     select_kernel<<<grid, 256, 0, st>>>(items, n_items, pmax, stride, n_ind, cut_store, invalid, cand_list, cand_stride, cand_cnt, units,
-                                        n_units, unit_cap, lanes_per_unit);
+                                        n_units, unit_cap, lanes_per_unit, c2);
     return cudaGetLastError();
 }
 

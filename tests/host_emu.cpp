@@ -101,9 +101,9 @@ int emu_windows(const uint64_t* geno, int64_t row_words, const double* lut, cons
 // pruning bound (bound.cuh) on the CPU: the same table construction, per-half-word step and candidate predicate the
 // kernels of squeeze.cu run.  pmax[n_pieces][n_ind] as the fused kernel stores it.
 // ---------------------------------------------------------------------------------------------------------------
-template <int C2, int LAG>
+template <int C2, int LAG, bool PARTIAL = false>
 static void emu_bound_row(const uint32_t* hw_row, long long n_hw, const std::vector<uint4>& hw,
-                          int n_pieces, uint32_t* pmax, int64_t stride, int ind)
+                          int n_pieces, uint32_t* pmax, int64_t stride, int ind, uint32_t low_mask = 0u)
 {
     BoundState S;
     bound_reset(S);
@@ -111,7 +111,7 @@ static void emu_bound_row(const uint32_t* hw_row, long long n_hw, const std::vec
         for (int I = 0; I < 16; ++I) {
             const long long q = (long long)pi * 16 + I;
             const uint32_t h = q < n_hw ? hw_row[q] : 0xffffffffu;
-            bound_step<C2, LAG>(S, h, hw[q], I);
+            bound_step<C2, LAG, PARTIAL>(S, h, hw[q], I, low_mask);
             if (((I - C2) & 15) == 15) {
                 const long long piece = (q - C2) >> 4;
                 if (piece >= 0 && piece < n_pieces) pmax[piece * stride + ind] = bound_pack(S.pm_all, S.pm_tail);
@@ -139,6 +139,11 @@ int emu_bound(const uint64_t* geno, int64_t row_words, const double* lut, long l
     for (int i = 0; i < n_ind; ++i) {
         const uint32_t* row = reinterpret_cast<const uint32_t*>(geno + (int64_t)i * row_words);
         const long long row_hw = row_words * 2;
+        if (bound_partial(W)) {
+            if (c2 == 1) emu_bound_row<1, 1, true>(row, row_hw, hw, n_pieces, pmax, n_ind, i, bound_low_mask(W));
+            else emu_bound_row<2, 2, true>(row, row_hw, hw, n_pieces, pmax, n_ind, i, bound_low_mask(W));
+            continue;
+        }
         switch (c2) {
 #define CASE(C) case C: if (lag == 1) emu_bound_row<C, 1>(row, row_hw, hw, n_pieces, pmax, n_ind, i); \
                         else emu_bound_row<C, 2>(row, row_hw, hw, n_pieces, pmax, n_ind, i); break;
@@ -167,7 +172,7 @@ int emu_select(const uint32_t* pmax, int n_ind, int n_chr, const int64_t* chr_of
     if (!ok) return -2;
     for (size_t i = 0; i < items.size(); ++i) {
         item_bounds[3 * i] = items[i].w0; item_bounds[3 * i + 1] = items[i].own_hi; item_bounds[3 * i + 2] = items[i].we;
-        for (int k = 0; k < n_ind; ++k) out[i * n_ind + k] = bound_item_candidate(pmax, n_ind, k, items[i], cut) ? 1 : 0;
+        for (int k = 0; k < n_ind; ++k) out[i * n_ind + k] = bound_item_candidate(pmax, n_ind, k, items[i], cut, bound_c2(W)) ? 1 : 0;
     }
     return (int)items.size();
 }

@@ -418,7 +418,8 @@ def _emu_bounds(codes_kept, lut, L, W):
     return pmax
 
 
-@pytest.mark.parametrize("n_ind,L0,W,W2", [(300, 80000, 50, 100), (77, 30011, 32, 209), (513, 20000, 64, 33)])
+@pytest.mark.parametrize("n_ind,L0,W,W2", [(300, 80000, 50, 100), (77, 30011, 32, 209), (513, 20000, 64, 33), (130, 25000, 30, 16),
+                                           (90, 22000, 17, 300), (64, 40000, 250, 24)])
 def test_fused_compaction_and_bound_equal_host_emulation(n_ind, L0, W, W2):
     """squeeze.cu: the compacted matrix equals the column gather, and the piece maxima written by the fused pass
     (window size W, first consumer = thinned windows) and by the bound-only pass (W2, same data) equal the CPU
@@ -446,7 +447,8 @@ def test_fused_compaction_and_bound_equal_host_emulation(n_ind, L0, W, W2):
     hp.close()
 
 
-@pytest.mark.parametrize("W,cutoff", [(50, 2.0), (32, 0.5), (100, 5.0), (209, 20.0), (60, -3.0)])
+@pytest.mark.parametrize("W,cutoff", [(50, 2.0), (32, 0.5), (100, 5.0), (209, 20.0), (60, -3.0), (10, 1.0), (16, 1.0), (30, 1.5), (31, 2.0),
+                                      (250, 25.0), (400, 40.0), (1000, 80.0)])
 def test_pruned_pass_equals_exact_chains_and_unpruned_pass(W, cutoff):
     """Pass 2 over the candidates the bound leaves == whole-segment exact chains == the pass without pruning, for
     several window-size classes and cutoffs (a negative cutoff makes nearly every pair a candidate)."""
@@ -471,15 +473,18 @@ def test_pruned_pass_equals_exact_chains_and_unpruned_pass(W, cutoff):
         g.set_tables(0.001, 200000, cen)
         outs[mode] = g.call_roh(W, cutoff, 0.25).copy()
         st = g.last_stats()
-        if mode == "pruned":
+        if mode == "pruned" and W < 16:
+            assert st["candidate_pairs"] < 0               # below the bound's range: every pair is walked
+            outs["exact"] = g.call_roh(W, cutoff, 0.25, exact=True).copy()
+        elif mode == "pruned":
             assert 0 <= st["candidate_pairs"] <= st["all_pairs"]
-            if cutoff >= 2.0:
+            if cutoff >= 2.0 and W >= 32:
                 assert st["candidate_pairs"] < 0.5 * st["all_pairs"]
             outs["exact"] = g.call_roh(W, cutoff, 0.25, exact=True).copy()
         else:
             assert st["candidate_pairs"] < 0
         hp.close()
-    assert len(outs["exact"]) > 50
+    assert len(outs["exact"]) > (50 if W <= 400 else 0)
     assert np.array_equal(outs["pruned"], outs["exact"])
     assert np.array_equal(outs["unpruned"], outs["exact"])
 

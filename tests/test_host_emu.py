@@ -153,14 +153,16 @@ def emu_piece_bounds(F, W):
     return pmax
 
 
-@pytest.mark.parametrize("name,item_pieces", [("lod_2", 1), ("lod_small", 1), ("auto_overlap_hg19", 2), ("lod_2", 4)])
-def test_pruning_bound_never_drops_a_flagged_window(name, item_pieces):
+@pytest.mark.parametrize("name,item_pieces,W_over", [("lod_2", 1, None), ("lod_small", 1, None), ("auto_overlap_hg19", 2, None), ("lod_2", 4, None),
+                                                     ("lod_small", 1, 16), ("lod_small", 1, 17), ("lod_small", 1, 24), ("lod_small", 1, 30),
+                                                     ("lod_small", 2, 31), ("lod_small", 1, 250), ("lod_small", 1, 300), ("lod_2", 2, 530)])
+def test_pruning_bound_never_drops_a_flagged_window(name, item_pieces, W_over):
     """bound.cuh: every (individual, item) pair that holds a window >= cutoff - tol must survive the pruning
     bound; and the bound must actually prune something on data with planted ROH."""
     ds, args = load_case(name)
-    W = arg(args, "--winsize", cast=int)
+    W = W_over or arg(args, "--winsize", cast=int)
     err = arg(args, "--error", cast=float)
-    assert W >= 32
+    assert W >= 16
     res = orc.run_pipeline(ds, W, err, None, cm="--cm" in args)
     F = flatten(res, err)
     win = oracle_windows_matrix(res)
@@ -186,7 +188,7 @@ def test_pruning_bound_never_drops_a_flagged_window(name, item_pieces):
             assert out[:n].mean() < 0.9      # something is pruned when almost nothing passes the cutoff
 
 
-@pytest.mark.parametrize("W", [32, 33, 49, 50, 64, 100, 177, 208, 209])
+@pytest.mark.parametrize("W", [16, 17, 18, 23, 30, 31, 32, 33, 49, 50, 64, 100, 177, 208, 209, 210, 240, 400])
 def test_pruning_bound_dominates_every_window_of_its_block(W):
     """The stored piece maximum is an upper bound (fixed point, >> 2 rounded up) of every window starting in the piece,
     for every window-size class the kernel is instantiated for; the tail maximum covers the piece's last C2 blocks."""
@@ -201,7 +203,7 @@ def test_pruning_bound_dominates_every_window_of_its_block(W):
     pmax = emu_piece_bounds(F, W)
     all_ = (pmax & 0xffff).astype(np.uint16).view(np.int16).astype(np.int64) * 4 / 256.0
     tail = (pmax >> 16).astype(np.uint16).view(np.int16).astype(np.int64) * 4 / 256.0
-    c2 = (W + 14) >> 4
+    c2 = (min(W, 209) + 14) >> 4
     for p in range(pmax.shape[0]):
         lo, hi = 256 * p, min(256 * (p + 1), win.shape[1])
         if lo >= hi:
