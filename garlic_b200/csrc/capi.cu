@@ -123,6 +123,9 @@ struct garlic_gpu {
     // d_counts = [nalleles, total, hom, nonmiss] x L0.  Across ranks the first two rows (what freq and the filter need)
     // are summed as soon as the local counts exist; the other two (homFreq: only --weighted) when the LD band asks
     bool counts_reduced = false, counts_hi_reduced = false;
+    bool counts_nccl_mem = false;      // d_counts came from ncclMemAlloc (symmetric-window capable)
+    ncclWindow_t counts_win = nullptr; // d_counts registered with the communicator as a symmetric window
+    bool counts_win_tried = false;
     double* d_gather = nullptr;    // all-gathered thinned windows
     const double* kde_src = nullptr;   // the window matrix the last pass-1 call left on the device (garlic_gpu_kde)
     int64_t kde_src_n = 0;
@@ -139,6 +142,7 @@ struct garlic_gpu {
 // GARLIC_TIMING=1: wall-clock laps of the host-side phases of an entry point, to stderr
 struct Laps {
     bool on;
+    int rank = 0;
     const char* name;
     std::chrono::steady_clock::time_point t0;
     std::string out;
@@ -152,7 +156,7 @@ struct Laps {
         out += b;
         t0 = t1;
     }
-    ~Laps() { if (on) fprintf(stderr, "[garlic_b200] %s:%s ms\n", name, out.c_str()); }
+    ~Laps() { if (on) fprintf(stderr, "[garlic_b200 r%d] %s:%s ms\n", rank, name, out.c_str()); }
 };
 
 #define CK(call)                                                                              \
@@ -219,6 +223,17 @@ static double lod_bound(const garlic_gpu* h)
 static int reduce_counts(garlic_gpu* h, bool hi)
 {
     if (!h->comm) return 0;
+    // The counters live in memory from ncclMemAlloc and are registered with the communicator as a symmetric window (same
+    // buffer, same offset on every rank): NCCL then runs its low-latency symmetric kernels for this all-reduce, which sits
+    // on the critical path of every pass.  Registration is a collective, done once per shape; if it is refused the
+    // all-reduce simply runs unregistered.
+    if (!h->counts_win_tried && h->counts_nccl_mem) {
+        h->counts_win_tried = true;
+        if (getenv("GARLIC_NCCL_NO_WINDOW") == nullptr) {
+            if (ncclCommWindowRegister(h->comm, h->d_counts, (size_t)4 * h->L0 * sizeof(int), &h->counts_win, NCCL_WIN_COLL_SYMMETRIC) != ncclSuccess)
+                h->counts_win = nullptr;
+        }
+    }
     if (!h->counts_reduced) {
         NCK(ncclAllReduce(h->d_counts, h->d_counts, (size_t)2 * h->L0, ncclInt32, ncclSum, h->comm, h->stream));
         h->counts_reduced = true;
@@ -227,6 +242,35 @@ static int reduce_counts(garlic_gpu* h, bool hi)
         NCK(ncclAllReduce(h->d_counts + 2 * h->L0, h->d_counts + 2 * h->L0, (size_t)2 * h->L0, ncclInt32, ncclSum, h->comm, h->stream));
         h->counts_hi_reduced = true;
     }
+    return 0;
+}
+
+static void free_counts(garlic_gpu* h)
+{
+    if (!h->d_counts) return;
+    if (h->counts_win && h->comm) ncclCommWindowDeregister(h->comm, h->counts_win);
+    h->counts_win = nullptr; h->counts_win_tried = false;
+    if (h->counts_nccl_mem) ncclMemFree(h->d_counts); else cudaFree(h->d_counts);
+    h->d_counts = nullptr; h->counts_nccl_mem = false;
+    h->cap.erase((void*)&h->d_counts);
+}
+
+// the per-SNP counters [4][L0]: from NCCL's allocator so that they can become a symmetric window (reduce_counts)
+static int alloc_counts(garlic_gpu* h, size_t n)
+{
+    const size_t bytes = n * sizeof(int);
+    auto it = h->cap.find((void*)&h->d_counts);
+    if (h->d_counts && it != h->cap.end() && it->second == bytes) return 0;   // (a window is registered with its exact size)
+    free_counts(h);
+    void* p = nullptr;
+    if (getenv("GARLIC_NCCL_NO_WINDOW") == nullptr && ncclMemAlloc(&p, bytes) == ncclSuccess && p) {
+        h->d_counts = static_cast<int*>(p);
+        h->counts_nccl_mem = true;
+    } else {
+        cudaGetLastError();
+        CK(cudaMalloc((void**)&h->d_counts, bytes));
+    }
+    h->cap[(void*)&h->d_counts] = bytes;
     return 0;
 }
 
@@ -288,7 +332,7 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    dev_free(h->d_alleles); dev_free(h->d_key); dev_free(h->d_geno0); dev_free(h->d_geno); dev_free(h->d_counts);
+    dev_free(h->d_alleles); dev_free(h->d_key); dev_free(h->d_geno0); dev_free(h->d_geno); free_counts(h);
     dev_free(h->d_gl0); dev_free(h->d_gl); dev_free(h->d_freq0); dev_free(h->d_freq); dev_free(h->d_lut);
     dev_free(h->d_ldplanes); dev_free(h->d_ldpairs); dev_free(h->d_text); dev_free(h->d_textoff); dev_free(h->d_nonblank);
     dev_free(h->d_gpos); dev_free(h->d_nomut); dev_free(h->d_norec); dev_free(h->d_wlut); dev_free(h->d_invld);
@@ -338,7 +382,11 @@ int garlic_gpu_comm_init(garlic_gpu_t* h, const uint8_t* id128, int rank, int wo
 {
     CK(cudaSetDevice(h->device));
     if (world < 1 || rank < 0 || rank >= world) FAIL("comm_init: bad rank / world size");
-    if (h->comm) { ncclCommDestroy(h->comm); h->comm = nullptr; }
+    if (h->comm) {
+        if (h->counts_win) ncclCommWindowDeregister(h->comm, h->counts_win);
+        ncclCommDestroy(h->comm); h->comm = nullptr;
+    }
+    h->counts_win = nullptr; h->counts_win_tried = false;
     h->comm_rank = rank; h->comm_world = world;
     if (world == 1) return 0;
     ncclUniqueId id;
@@ -368,7 +416,7 @@ int garlic_gpu_set_shape(garlic_gpu_t* h, int n_ind, int ind_offset, int64_t n_l
     h->row_words0 = (((n_loci + kPad + 31) >> 5) + 3) & ~(int64_t)1;
     if (dev_alloc(h, &h->d_geno0, (size_t)n_ind * h->row_words0)) return 1;
     CK(cudaMemsetAsync(h->d_geno0, 0xff, (size_t)n_ind * h->row_words0 * 8, h->stream));
-    if (dev_alloc(h, &h->d_counts, (size_t)4 * n_loci)) return 1;
+    if (alloc_counts(h, (size_t)4 * n_loci)) return 1;
     CK(cudaMemsetAsync(h->d_counts, 0, (size_t)4 * n_loci * sizeof(int), h->stream));
     if (dev_alloc(h, &h->d_pos0, (size_t)n_loci)) return 1;
     CK(cudaMemcpyAsync(h->d_pos0, pos, n_loci * sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -662,6 +710,7 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     if (oob && !chr_param) FAIL("filter: oob filtering needs chr_param");
     const int64_t L0 = h->L0;
     Laps laps("filter");
+    laps.rank = h->comm_rank;
     if (!freq_override) h->fmin = 0.5;
     bool freq_direct = false, keep_direct = false, copies_in_flight = false;
     if (dev_alloc(h, &h->d_freq0, (size_t)L0)) return 1;
@@ -812,6 +861,7 @@ int garlic_gpu_set_tables(garlic_gpu_t* h, double error, int max_gap, const int3
     if (!h->filtered) FAIL("set_tables: call filter first");
     h->error = error; h->max_gap = max_gap;
     Laps laps("set_tables");
+    laps.rank = h->comm_rank;
     h->cen.assign(2 * h->n_chr, 0);
     if (centromeres) h->cen.assign(centromeres, centromeres + 2 * h->n_chr);
     const int64_t L = h->L;
@@ -1260,6 +1310,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     if (weighted && ensure_weighted(h, winsize)) return 1;
     const int W = winsize;
     Laps laps("call_roh");
+    laps.rank = h->comm_rank;
     // pruned pass (bound.cuh): unweighted table mode, window sizes the bound covers, cutoffs inside its fixed-point range
     int cut_ok = 0;
     bound_cut_store(cutoff, 1.0, &cut_ok);

@@ -490,8 +490,8 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-template <int SRC>
-__global__ void __launch_bounds__(128)
+template <int SRC, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 wlod_mma_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items, int n_groups)
 {
     extern __shared__ uint32_t ring_smem[];   // [NW][blockDim.x] flag-word history (W > 32)
@@ -670,14 +670,19 @@ cudaError_t launch_wlod_mma(const WlodParams& Q, const Item* items, int n_items,
     long long grid = total;
     const long long cap = 148ll * 16 * 8;
     if (grid > cap) grid = cap;
-    if (smem > 48 * 1024) {                                    // flag history of very large windows
-        cudaError_t e = gl_mode ? cudaFuncSetAttribute(wlod_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                : cudaFuncSetAttribute(wlod_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    if (gl_mode) wlod_mma_kernel<1><<<(unsigned)grid, threads, smem, st>>>(Q, items, n_items, n_groups);
-    else wlod_mma_kernel<0><<<(unsigned)grid, threads, smem, st>>>(Q, items, n_items, n_groups);
-    return cudaGetLastError();
+    // MINB = 4 caps the kernel at 128 registers (four CTAs = sixteen warps per SM instead of twelve) at the price of a
+    // few spilled values outside the quad loop; GARLIC_MMA_MINB=3 selects the uncapped build for A/B timing
+    static const bool lb4 = []() { const char* e = getenv("GARLIC_MMA_MINB"); return !(e && atoi(e) == 3); }();
+    auto launch = [&](auto kern) -> cudaError_t {
+        if (smem > 48 * 1024) {                                // flag history of very large windows
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<(unsigned)grid, threads, smem, st>>>(Q, items, n_items, n_groups);
+        return cudaGetLastError();
+    };
+    if (gl_mode) return lb4 ? launch(wlod_mma_kernel<1, 4>) : launch(wlod_mma_kernel<1, 3>);
+    return lb4 ? launch(wlod_mma_kernel<0, 4>) : launch(wlod_mma_kernel<0, 3>);
 }
 
 template <int SRC, bool ROH, bool DUMP>
