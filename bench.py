@@ -368,28 +368,35 @@ def main():
             phases[name] = phases.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
         return time.perf_counter()
 
-    def step(resident):
+    def step(resident, all_outputs=False):
+        """One pass of the hot path.  As in the reference's main() — and in garlic_b200's own driver (host/main.cpp) — the
+        per-SNP outputs that are identical on every rank (freq[] for the .freq file, the keep mask, the thinned windows of
+        the KDE individuals) travel to the host of rank 0 only; every rank fetches its own ROH records.  all_outputs:
+        every rank fetches everything (the untimed step that feeds the parity checks)."""
+        lead = rank == 0 or all_outputs
         t0 = time.perf_counter()
         if not resident:
             g.put_packed(rows_host_np)                       # H2D from pinned host memory
             t0 = lap("put_packed_h2d", t0)
         g.count_packed()                                     # K2; N>1: + the all-reduce of the allele counters, in stream order
         t0 = lap("count_packed_allreduce" if dist is not None else "count_packed", t0)
-        freq, keep, L = g.filter()                           # freq, keep mask -> host; K3 compaction
+        freq, keep, L = g.filter(want_freq=lead, want_keep=lead, wait=False)   # freq, keep mask -> page-locked host buffers
+        # (rank 0), filled behind the call and complete when pass 1 returns; K3's plan
         t0 = lap("filter_compact", t0)
         g.set_tables(err, max_gap, cen_arr)                  # K4
         t0 = lap("set_tables", t0)
         if dist is None:
             thin = g.windows(W, W, individuals=kde_local, exact=False, reuse=True)
-        else:                                                # every rank gets all KDE individuals' thinned LODs
-            thin = g.windows_gather(W, W, kde_local, kde_max, world)
+        else:                                                # rank 0 gets all KDE individuals' thinned LODs
+            thin = g.windows_gather(W, W, kde_local, kde_max, world, want=lead)
         t0 = lap("pass1_thinned_windows", t0)
         roh = g.call_roh(W, cutoff, ov, exact=a.exact)       # K5 pass 2 (fused) -> ROH records on the host
         t0 = lap("pass2_call_roh", t0)
         st = g.last_stats()
+        nb = lambda x: 0 if x is None else x.nbytes
         state.update(freq=freq, keep=keep, L=L, thin=thin, roh=roh, stats=st,
                      h2d=(0 if resident else rows_host_np.nbytes) + pos0.nbytes + chr_off0.nbytes,
-                     d2h=freq.nbytes + keep.nbytes + thin.nbytes + roh.nbytes + 16)
+                     d2h=nb(freq) + nb(keep) + nb(thin) + roh.nbytes + 16)
         return st
 
     def timed(resident, steps, warmup, sample_clocks):
@@ -426,11 +433,18 @@ def main():
     ms_e2e, _, _, _ = timed(False, a.steps, min(a.warmup, 2) if a.warmup else 0, False)
     e2e_val = units_total * a.steps / (ms_e2e / 1e3)
     e2e = dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(state["h2d"]), d2h_bytes_per_step=int(state["d2h"]),
-               ms_per_step=ms_e2e / a.steps)
+               ms_per_step=ms_e2e / a.steps,
+               note="bytes of rank 0 (freq[], keep mask and the thinned windows go to rank 0's host only; every rank "
+                    "uploads its own packed rows and fetches its own ROH records)" if world > 1 else "")
     assert np.array_equal(roh_dev, state["roh"]), "resident and host-buffer runs disagree"
     phases["on"] = 1                                         # one extra, untimed step with a sync after each call
     step(False)
     phases.pop("on")
+    saved_phases = dict(phases)
+    phases.clear()
+    step(True, all_outputs=True)                             # untimed: every rank fetches freq / keep for its parity check below
+    g.sync()
+    phases.update(saved_phases)
     # how much the headline depends on the cutoff: pass-2 kernel time and candidate fraction at three cutoffs and
     # with the pruning bound switched off (every pair walked) — same data, same tables, pass 2 only
     sens = {}

@@ -186,9 +186,11 @@ class GarlicGPU:
         self._ck(self.lib.garlic_gpu_get_gl(self.h, _p(out)))
         return out
 
-    def filter(self, oob=False, chr_param=None, freq_override=None, want_freq=True, want_keep=True):
-        """→ (freq float64[L0], keep bool[L0], L).  The two arrays are views of buffers owned by this object and
-        are overwritten by the next filter() call (repeated runs then touch no fresh pages)."""
+    def filter(self, oob=False, chr_param=None, freq_override=None, want_freq=True, want_keep=True, wait=True):
+        """→ (freq float64[L0], keep bool[L0], L).  The two arrays are views of page-locked buffers owned by this object
+        and are overwritten by the next filter() call (repeated runs then touch no fresh pages).  The library fills
+        page-locked buffers behind the call; wait=False leaves it at that (they are complete once the next windows /
+        call_roh / sync call has returned), wait=True synchronises before returning."""
         if getattr(self, "_freq_buf", None) is None or len(self._freq_buf) != self.L0:
             self._freq_buf = self.host_array(self.L0, np.float64)      # page-locked: no staging copy
             self._keep_buf = self.host_array(self.L0, np.uint8)
@@ -198,6 +200,8 @@ class GarlicGPU:
         cp = None if chr_param is None else np.ascontiguousarray(chr_param, np.int32)
         fo = None if freq_override is None else np.ascontiguousarray(freq_override, np.float64)
         self._ck(self.lib.garlic_gpu_filter(self.h, C.c_int(int(oob)), _p(cp), _p(fo), _p(freq), _p(keep), C.byref(n)))
+        if wait and (want_freq or want_keep):
+            self.sync()
         self.L = n.value
         return freq, (keep.view(np.bool_) if keep is not None else None), n.value
 
@@ -276,17 +280,18 @@ class GarlicGPU:
                                                  C.c_int(n), C.c_int(int(exact)), C.byref(ptr)))
         return ptr.value, n, self.window_slots(step)
 
-    def windows_gather(self, W, step, individuals, rows_per_rank, world, weighted=False, exact=False):
-        """All ranks' thinned windows: float64[world*rows_per_rank, slots] (MISSING rows = padding)."""
+    def windows_gather(self, W, step, individuals, rows_per_rank, world, weighted=False, exact=False, want=True):
+        """All ranks' thinned windows: float64[world*rows_per_rank, slots] (MISSING rows = padding).  want=False: this
+        rank only contributes (returns None; the gathered matrix stays on its GPU)."""
         idx = np.ascontiguousarray(individuals, np.int32)
         slots = self.window_slots(step)
         key = (world * rows_per_rank, slots)
-        if getattr(self, "_gather_buf", None) is None or self._gather_buf.shape != key:
+        if want and (getattr(self, "_gather_buf", None) is None or self._gather_buf.shape != key):
             self._gather_buf = self.host_array(key[0] * key[1], np.float64).reshape(key)
         self._ck(self.lib.garlic_gpu_windows_gather(self.h, C.c_int(W), C.c_int(step), C.c_int(int(weighted)), _p(idx),
                                                     C.c_int(len(idx)), C.c_int(rows_per_rank), C.c_int(int(exact)),
-                                                    _p(self._gather_buf)))
-        return self._gather_buf
+                                                    _p(self._gather_buf) if want else None))
+        return self._gather_buf if want else None
 
     def kde(self, values=None, m=512):
         """computeKDE (garlic-kde.cpp:14-101) on the device, of `values` or — None — of the window matrix the last

@@ -133,6 +133,7 @@ struct garlic_gpu {
     cudaEvent_t ev2 = nullptr;
     cudaStream_t copy_stream = nullptr;   // device-to-host copies that overlap the kernels behind them (filter)
     cudaEvent_t ev_copy = nullptr;
+    bool out_pending = false;      // filter's freq / keep copies into page-locked caller buffers are still in flight
     uint8_t* pin = nullptr;        // pinned host staging buffer
     size_t pin_cap = 0;
     std::map<void*, size_t> cap;   // bytes behind each device pointer slot (keyed by the slot's address)
@@ -223,13 +224,13 @@ static double lod_bound(const garlic_gpu* h)
 static int reduce_counts(garlic_gpu* h, bool hi)
 {
     if (!h->comm) return 0;
-    // The counters live in memory from ncclMemAlloc and are registered with the communicator as a symmetric window (same
-    // buffer, same offset on every rank): NCCL then runs its low-latency symmetric kernels for this all-reduce, which sits
-    // on the critical path of every pass.  Registration is a collective, done once per shape; if it is refused the
-    // all-reduce simply runs unregistered.
+    // GARLIC_NCCL_WINDOW=1: the counters live in memory from ncclMemAlloc and are registered with the communicator as a
+    // symmetric window (same buffer, same offset on every rank) so that NCCL may run its symmetric kernels for this
+    // all-reduce.  Measured on 8 B200 (profiles/r02i): no gain at 4.8 MB (1.28 ms per step against 1.24 without), hence
+    // opt-in.  Registration is a collective, done once per shape; if it is refused the all-reduce runs unregistered.
     if (!h->counts_win_tried && h->counts_nccl_mem) {
         h->counts_win_tried = true;
-        if (getenv("GARLIC_NCCL_NO_WINDOW") == nullptr) {
+        if (getenv("GARLIC_NCCL_WINDOW") != nullptr) {
             if (ncclCommWindowRegister(h->comm, h->d_counts, (size_t)4 * h->L0 * sizeof(int), &h->counts_win, NCCL_WIN_COLL_SYMMETRIC) != ncclSuccess)
                 h->counts_win = nullptr;
         }
@@ -263,7 +264,7 @@ static int alloc_counts(garlic_gpu* h, size_t n)
     if (h->d_counts && it != h->cap.end() && it->second == bytes) return 0;   // (a window is registered with its exact size)
     free_counts(h);
     void* p = nullptr;
-    if (getenv("GARLIC_NCCL_NO_WINDOW") == nullptr && ncclMemAlloc(&p, bytes) == ncclSuccess && p) {
+    if (getenv("GARLIC_NCCL_WINDOW") != nullptr && ncclMemAlloc(&p, bytes) == ncclSuccess && p) {
         h->d_counts = static_cast<int*>(p);
         h->counts_nccl_mem = true;
     } else {
@@ -271,6 +272,16 @@ static int alloc_counts(garlic_gpu* h, size_t n)
         CK(cudaMalloc((void**)&h->d_counts, bytes));
     }
     h->cap[(void*)&h->d_counts] = bytes;
+    return 0;
+}
+
+// filter() does not wait for its copies into page-locked caller buffers; every later call that hands data to the host
+// (windows, call_roh, kde, the get_* accessors) and garlic_gpu_sync complete them first
+static int finish_outputs(garlic_gpu* h)
+{
+    if (!h->out_pending) return 0;
+    CK(cudaStreamSynchronize(h->copy_stream));
+    h->out_pending = false;
     return 0;
 }
 
@@ -399,7 +410,7 @@ int garlic_gpu_sync(garlic_gpu_t* h)
 {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    return finish_outputs(h);
 }
 
 int garlic_gpu_set_shape(garlic_gpu_t* h, int n_ind, int ind_offset, int64_t n_loci, int n_chr,
@@ -711,6 +722,7 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     const int64_t L0 = h->L0;
     Laps laps("filter");
     laps.rank = h->comm_rank;
+    if (finish_outputs(h)) return 1;
     if (!freq_override) h->fmin = 0.5;
     bool freq_direct = false, keep_direct = false, copies_in_flight = false;
     if (dev_alloc(h, &h->d_freq0, (size_t)L0)) return 1;
@@ -822,9 +834,15 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     CK(cudaMemcpyAsync(h->d_chr_start, chr_start.data(), h->n_chr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     laps.lap("enqueue");   // compaction and gathers run stream-ordered behind this call
     if (copies_in_flight) {
-        CK(cudaStreamSynchronize(h->copy_stream));
-        if (freq_out && !freq_direct) memcpy(freq_out, freq0, L0 * sizeof(double));
-        if (keep_out && !keep_direct) memcpy(keep_out, keep, L0);
+        const bool all_direct = (!freq_out || freq_direct) && (!keep_out || keep_direct);
+        if (all_direct) {
+            // page-locked caller buffers: the copy engine fills them behind this call (include/garlic_b200.h)
+            h->out_pending = true;
+        } else {
+            CK(cudaStreamSynchronize(h->copy_stream));
+            if (freq_out && !freq_direct) memcpy(freq_out, freq0, L0 * sizeof(double));
+            if (keep_out && !keep_direct) memcpy(keep_out, keep, L0);
+        }
         laps.lap("freq/keep d2h");
     }
     h->filtered = true; h->tables = false; h->have_ld = false;
@@ -1181,11 +1199,13 @@ int garlic_gpu_windows_gather(garlic_gpu_t* h, int winsize, int step, int weight
     if (h->comm) NCK(ncclAllGather(send, h->d_gather, blk, ncclDouble, h->comm, h->stream));
     else CK(cudaMemcpyAsync(h->d_gather, send, blk * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     h->kde_src = h->d_gather; h->kde_src_n = (int64_t)(blk * h->comm_world);
+    if (!out) return 0;                     // a rank that only contributes: nothing travels to its host, nobody waits
     const size_t bytes = blk * h->comm_world * sizeof(double);
     const bool direct = is_pinned(out);
     const bool staged = !direct && bytes <= ((size_t)64 << 20) && !pin_alloc(h, bytes);
     CK(cudaMemcpyAsync(direct ? (void*)out : (staged ? (void*)h->pin : (void*)out), h->d_gather, bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (finish_outputs(h)) return 1;
     if (staged) memcpy(out, h->pin, bytes);
     return 0;
 }
@@ -1250,6 +1270,7 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
     rc = launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, false, true, items_tile_snps(items, W));
     }
     if (!rc) { h->kde_src = d_dump; h->kde_src_n = (int64_t)n_lanes * slots; }
+    if (!rc && finish_outputs(h)) rc = 1;
     if (!rc && out_dev) {
         *out_dev = d_dump;
         cudaError_t e = cudaStreamSynchronize(h->stream);
@@ -1289,6 +1310,7 @@ int garlic_gpu_kde(garlic_gpu_t* h, const double* values, int64_t n_values, int 
     if (pin_alloc(h, bytes)) return 1;
     CK(cudaMemcpyAsync(h->pin, d_res, bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (finish_outputs(h)) return 1;
     const double* r = reinterpret_cast<const double*>(h->pin);
     if (n_used) *n_used = (int64_t)r[0];
     if (bandwidth) *bandwidth = r[5];
@@ -1367,6 +1389,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     bool done = false;
     float ms = 0, ms_coarse = 0;
     bool pruned = false;
+    double n_cand = -1.0;
     for (int attempt = 0; attempt < 3; ++attempt) {
         WalkParams P = base_params(h, W);
         P.cutoff = cutoff; P.thr = thr;
@@ -1428,12 +1451,16 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         unsigned* cnt = reinterpret_cast<unsigned*>(h->pin);
         RohRec* stage = reinterpret_cast<RohRec*>(h->pin + 64);
         CK(cudaMemcpyAsync(cnt, h->d_cnt, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+        cnt[4] = 0; cnt[5] = 0;                                // work units / candidate pairs of the pruned pass ride along
+        if (prune_now) CK(cudaMemcpyAsync(cnt + 4, h->d_nunits, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(stage, h->d_out, guess * sizeof(RohRec), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(stage + guess, h->d_amb, amb_guess * sizeof(RohRec), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        if (finish_outputs(h)) return 1;
         CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         CK(cudaEventElapsedTime(&ms_coarse, h->ev0, h->ev2));
         pruned = prune_now;
+        n_cand = prune_now ? (double)cnt[5] : -1.0;
         const unsigned n_raw = cnt[0], n_amb = cnt[1], n_fin = cnt[2];
         if (n_raw > h->out_cap) {
             h->out_cap = n_raw + n_raw / 4 + 1024;
@@ -1518,9 +1545,9 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     h->stats[2] = (double)n_amb_pairs;
     h->stats[3] = ms;
     h->stats[4] = ms_coarse;
-    h->stats[5] = -1;
+    h->stats[5] = pruned ? n_cand : -1;
     h->stats[6] = (double)its->size() * h->n_ind;
-    h->stats_items = pruned ? (int64_t)its->size() : 0;    // candidate counts are fetched by last_stats on demand
+    h->stats_items = 0;
     laps.lap("out");
     return 0;
 }

@@ -123,7 +123,10 @@ int garlic_gpu_get_gl(garlic_gpu_t *h, double *values);
  * the map scaffold and not strictly inside the centromere]. chr_param: [n_chr][4] =
  * scaffold first bp, scaffold last bp, centromere start, centromere end (NULL if !oob).
  * freq_override (may be NULL): use these frequencies instead (--freq-file).
- * Outputs: freq_out[n_loci] (may be NULL), keep_out[n_loci] (may be NULL); returns L via n_kept. */
+ * Outputs: freq_out[n_loci] (may be NULL), keep_out[n_loci] (may be NULL); returns L via n_kept.
+ * Ordinary host buffers are complete on return.  Page-locked ones (garlic_gpu_host_alloc) are filled by the copy engine
+ * behind the call — the path goes on without waiting for 5 MB to cross PCIe — and are complete when the next call that
+ * hands data to the host returns (garlic_gpu_windows*, garlic_gpu_call_roh, garlic_gpu_kde) or after garlic_gpu_sync. */
 int garlic_gpu_filter(garlic_gpu_t *h, int oob, const int32_t *chr_param, const double *freq_override,
                       double *freq_out, uint8_t *keep_out, int64_t *n_kept);
 
@@ -167,7 +170,8 @@ int garlic_gpu_windows(garlic_gpu_t *h, int winsize, int step, int weighted, con
 int garlic_gpu_windows_dev(garlic_gpu_t *h, int winsize, int step, int weighted, const int32_t *individuals,
                            int n, int exact, void **out_dev);
 /* the KDE individuals of ALL ranks: this rank computes its n <= rows_per_rank local individuals, one all-gather
- * collects every rank's MISSING-padded block; out: [world*rows_per_rank][n_slots] in rank order */
+ * collects every rank's MISSING-padded block; out: [world*rows_per_rank][n_slots] in rank order, or NULL on ranks that
+ * only contribute (the gathered matrix stays on their GPU, the call does not wait) */
 int garlic_gpu_windows_gather(garlic_gpu_t *h, int winsize, int step, int weighted, const int32_t *individuals,
                               int n, int rows_per_rank, int exact, double *out);
 

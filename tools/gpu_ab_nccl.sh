@@ -13,5 +13,5 @@ try:
     print("$v", d["ms_per_step"], d["value"], d["phases_ms_one_synchronised_step"])
 except Exception as e: print("no json", e)
 PY
-  grep -E "r0\] filter" $out/${tag}_n${N}_${v}.err | tail -3
+  grep -E "r0\] (filter|call_roh:.*items)" $out/${tag}_n${N}_${v}.err | tail -4; grep -E "r5\] filter" $out/${tag}_n${N}_${v}.err | tail -2
 done

@@ -81,17 +81,19 @@ def c5(n_ind=20000, L0=600_000):
     for W in (30, 50, 70):
         roh, ms = timed(g, lambda: g.call_roh(W, 2.0, 0.25))
         st = g.last_stats()
-        res["pass2_W%d" % W] = dict(ms=ms, kernel_ms=st["kernel_ms"], roh=len(roh), units=st["units"],
-                                    units_per_s_kernel=st["units"] / (st["kernel_ms"] / 1e3), ambiguous=st["ambiguous_pairs"])
-    # parity of 8 individuals at W = 70 against the reference functions
+        res["pass2_W%d" % W] = dict(ms=ms, kernel_ms=st["kernel_ms"], bound_ms=st["squeeze_ms"], roh=len(roh), units=st["units"],
+                                    units_per_s_kernel=st["units"] / (st["kernel_ms"] / 1e3), ambiguous=st["ambiguous_pairs"],
+                                    candidate_pair_fraction=(st["candidate_pairs"] / st["all_pairs"]) if st["candidate_pairs"] >= 0 else None)
+    # parity of 8 individuals at W = 30 and W = 70 against the reference functions
     n_s = 8
     chroms = oracle_sample(rows, n_s, L0, keep.copy(), freq.copy(), pos0, chr_off0, names, cens)
-    cs = bench.CpuSample(chroms, n_s, 70, 0.001, 2.0, 0.25, 200000, 1)
-    _, roh_cpu = cs.run()
-    roh = g.call_roh(70, 2.0, 0.25)
     pos_k = pos0[keep]
-    got = sorted((int(r[0]), int(r[1]), int(pos_k[r[2]]), int(pos_k[r[3]])) for r in roh if r[0] < n_s)
-    res["parity_8_individuals_W70"] = "identical ROH (%d), cpu kind=%s" % (len(got), cs.kind) if got == sorted(roh_cpu) else "MISMATCH"
+    for W in (30, 70):
+        cs = bench.CpuSample(chroms, n_s, W, 0.001, 2.0, 0.25, 200000, 1)
+        _, roh_cpu = cs.run()
+        roh = g.call_roh(W, 2.0, 0.25)
+        got = sorted((int(r[0]), int(r[1]), int(pos_k[r[2]]), int(pos_k[r[3]])) for r in roh if r[0] < n_s)
+        res["parity_8_individuals_W%d" % W] = "identical ROH (%d), cpu kind=%s" % (len(got), cs.kind) if got == sorted(roh_cpu) else "MISMATCH"
     g.close()
     return res
 
