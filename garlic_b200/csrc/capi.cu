@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <unistd.h>
 #include <string>
 #include <vector>
 
@@ -110,7 +111,8 @@ struct garlic_gpu {
     int* d_cand_list = nullptr;
     unsigned* d_cand_cnt = nullptr;
     int2* d_units = nullptr;       // work queue of the pruned pass 2: (item, first candidate)
-    unsigned* d_nunits = nullptr;  // [0] units appended, [1] candidate pairs
+    unsigned* d_nunits = nullptr;  // [0] units appended, [1] candidate pairs (inside the block of d_cnt: ensure_zero_block)
+    size_t zero_cap = 0, zero_n = 0;
     cudaEvent_t ev_sq0 = nullptr, ev_sq1 = nullptr;   // around the last fused compaction + bound launch
     bool sq_timed = false;
     int item_pieces = 1;           // pieces per item of the pruned pass (GARLIC_ITEM_PIECES)
@@ -124,6 +126,12 @@ struct garlic_gpu {
     // are summed as soon as the local counts exist; the other two (homFreq: only --weighted) when the LD band asks
     bool counts_reduced = false, counts_hi_reduced = false;
     bool counts_nccl_mem = false;      // d_counts came from ncclMemAlloc (symmetric-window capable)
+    // NVLink exchange (xchg.cu): [flags | counters | freq0 | keep] of this rank in one IPC-exported block, peers' blocks mapped
+    uint8_t* xslab = nullptr;
+    void* xpeer[kXchgMaxRanks] = {nullptr};
+    size_t x_off_counts = 0, x_off_freq = 0, x_off_keep = 0;
+    bool xchg_tried = false, xchg_ok = false;
+    unsigned xchg_seq = 0;
     ncclWindow_t counts_win = nullptr; // d_counts registered with the communicator as a symmetric window
     bool counts_win_tried = false;
     double* d_gather = nullptr;    // all-gathered thinned windows
@@ -133,6 +141,11 @@ struct garlic_gpu {
     cudaEvent_t ev2 = nullptr;
     cudaStream_t copy_stream = nullptr;   // device-to-host copies that overlap the kernels behind them (filter)
     cudaEvent_t ev_copy = nullptr;
+    // GARLIC_TIMELINE=1: host clock and stream position (CUDA events) at marked points of the entry points, printed at destroy
+    bool tl_on = false;
+    std::vector<cudaEvent_t> tl_ev;
+    std::vector<const char*> tl_name;
+    std::vector<double> tl_host;
     bool out_pending = false;      // filter's freq / keep copies into page-locked caller buffers are still in flight
     uint8_t* pin = nullptr;        // pinned host staging buffer
     size_t pin_cap = 0;
@@ -159,6 +172,31 @@ struct Laps {
     }
     ~Laps() { if (on) fprintf(stderr, "[garlic_b200 r%d] %s:%s ms\n", rank, name, out.c_str()); }
 };
+
+static void tl_mark(garlic_gpu* h, const char* name)
+{
+    if (!h->tl_on) return;
+    if (h->tl_ev.size() >= 4096) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, h->stream);
+    h->tl_ev.push_back(e);
+    h->tl_name.push_back(name);
+    h->tl_host.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count());
+}
+static void tl_dump(garlic_gpu* h)
+{
+    if (!h->tl_on || h->tl_ev.empty()) return;
+    cudaStreamSynchronize(h->stream);
+    const size_t n = h->tl_ev.size(), first = n > 120 ? n - 120 : 0;
+    for (size_t i = first; i < n; ++i) {
+        float g = 0;
+        cudaEventElapsedTime(&g, h->tl_ev[first], h->tl_ev[i]);
+        fprintf(stderr, "[timeline r%d] %-28s host %9.3f  stream %9.3f ms\n", h->comm_rank, h->tl_name[i], h->tl_host[i] - h->tl_host[first], g);
+    }
+    for (cudaEvent_t e : h->tl_ev) cudaEventDestroy(e);
+    h->tl_ev.clear();
+}
 
 #define CK(call)                                                                              \
     do {                                                                                      \
@@ -249,6 +287,7 @@ static int reduce_counts(garlic_gpu* h, bool hi)
 static void free_counts(garlic_gpu* h)
 {
     if (!h->d_counts) return;
+    if (h->xchg_ok) return;                            // inside the exchange block: xchg_teardown owns it
     if (h->counts_win && h->comm) ncclCommWindowDeregister(h->comm, h->counts_win);
     h->counts_win = nullptr; h->counts_win_tried = false;
     if (h->counts_nccl_mem) ncclMemFree(h->d_counts); else cudaFree(h->d_counts);
@@ -272,6 +311,106 @@ static int alloc_counts(garlic_gpu* h, size_t n)
         CK(cudaMalloc((void**)&h->d_counts, bytes));
     }
     h->cap[(void*)&h->d_counts] = bytes;
+    return 0;
+}
+
+// ---- NVLink exchange of the counters (xchg.cu) ----------------------------------------------------------------
+static void xchg_teardown(garlic_gpu* h)
+{
+    if (!h->xslab) { h->xchg_tried = false; h->xchg_ok = false; return; }
+    cudaStreamSynchronize(h->stream);
+    for (int p = 0; p < kXchgMaxRanks; ++p) {
+        if (h->xpeer[p] && h->xpeer[p] != (void*)h->xslab) cudaIpcCloseMemHandle(h->xpeer[p]);
+        h->xpeer[p] = nullptr;
+    }
+    if (h->xchg_ok) {                                  // the three tables lived inside the block
+        h->d_counts = nullptr; h->d_freq0 = nullptr; h->d_keep = nullptr;
+        h->cap.erase((void*)&h->d_counts); h->cap.erase((void*)&h->d_freq0); h->cap.erase((void*)&h->d_keep);
+    }
+    cudaFree(h->xslab);
+    h->xslab = nullptr;
+    h->xchg_tried = false; h->xchg_ok = false; h->xchg_seq = 0;
+}
+
+// One-time, collective (every rank of the communicator calls it at the same point): allocate this rank's block, exchange
+// the IPC handles over the communicator, map the peers' blocks, agree that every rank succeeded, and move the counters /
+// freq / keep tables into the block.  Any failure (one process driving several GPUs, IPC not permitted, more than 16
+// ranks) leaves the NCCL all-reduce in place on every rank.
+static int ensure_xchg(garlic_gpu* h)
+{
+    if (h->xchg_tried) return 0;
+    h->xchg_tried = true;
+    h->xchg_ok = false;
+    if (!h->comm || h->comm_world < 2 || h->comm_world > kXchgMaxRanks || h->counts_nccl_mem) return 0;
+    if (getenv("GARLIC_NO_XCHG") != nullptr) return 0;
+    const int N = h->comm_world;
+    const size_t L0 = (size_t)h->L0;
+    h->x_off_counts = 256;
+    h->x_off_freq = (h->x_off_counts + 16 * L0 + 255) & ~(size_t)255;
+    h->x_off_keep = h->x_off_freq + 8 * L0;
+    const size_t total = ((h->x_off_keep + L0 + 255) & ~(size_t)255);
+    struct Rec { cudaIpcMemHandle_t hdl; int pid; int ok; long long L0; char pad[128 - sizeof(cudaIpcMemHandle_t) - 16]; };
+    static_assert(sizeof(Rec) == 128, "exchange record is 128 bytes");
+    Rec mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.pid = (int)getpid(); mine.L0 = h->L0; mine.ok = 1;
+    if (cudaMalloc((void**)&h->xslab, total) != cudaSuccess) { cudaGetLastError(); h->xslab = nullptr; mine.ok = 0; }
+    if (mine.ok) {
+        cudaMemsetAsync(h->xslab, 0, 256, h->stream);
+        cudaStreamSynchronize(h->stream);
+        if (cudaIpcGetMemHandle(&mine.hdl, h->xslab) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+    }
+    // the records travel over the communicator (the only channel the library has)
+    Rec* d_rec = nullptr;
+    std::vector<Rec> all(N);
+    CK(cudaMalloc((void**)&d_rec, (size_t)(N + 1) * sizeof(Rec)));
+    CK(cudaMemcpyAsync(d_rec + N, &mine, sizeof(Rec), cudaMemcpyHostToDevice, h->stream));
+    NCK(ncclAllGather(d_rec + N, d_rec, sizeof(Rec), ncclUint8, h->comm, h->stream));
+    CK(cudaMemcpyAsync(all.data(), d_rec, (size_t)N * sizeof(Rec), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int ok = 1;
+    for (int p = 0; p < N; ++p) {
+        if (!all[p].ok || all[p].L0 != h->L0) ok = 0;
+        if (p != h->comm_rank && all[p].pid == mine.pid) ok = 0;   // several GPUs driven by one process: no IPC mapping of one's own memory
+    }
+    for (int p = 0; p < N && ok; ++p) {
+        if (p == h->comm_rank) { h->xpeer[p] = h->xslab; continue; }
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[p].hdl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        h->xpeer[p] = ptr;
+    }
+    // agreement: every rank mapped every peer, or nobody uses the path
+    int* d_ok = reinterpret_cast<int*>(d_rec);
+    CK(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    NCK(ncclAllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, h->comm, h->stream));
+    CK(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_rec);
+    if (!ok) {
+        for (int p = 0; p < N; ++p) {
+            if (h->xpeer[p] && h->xpeer[p] != (void*)h->xslab) cudaIpcCloseMemHandle(h->xpeer[p]);
+            h->xpeer[p] = nullptr;
+        }
+        if (h->xslab) cudaFree(h->xslab);
+        h->xslab = nullptr;
+        return 0;
+    }
+    // the tables move into the block (the counters with what the count kernel has already put there)
+    int* nc = reinterpret_cast<int*>(h->xslab + h->x_off_counts);
+    if (h->d_counts) CK(cudaMemcpyAsync(nc, h->d_counts, 16 * L0, cudaMemcpyDeviceToDevice, h->stream));
+    else CK(cudaMemsetAsync(nc, 0, 16 * L0, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    free_counts(h);
+    if (h->d_freq0) { cudaFree(h->d_freq0); h->d_freq0 = nullptr; }
+    if (h->d_keep) { cudaFree(h->d_keep); h->d_keep = nullptr; }
+    h->d_counts = nc;
+    h->d_freq0 = reinterpret_cast<double*>(h->xslab + h->x_off_freq);
+    h->d_keep = h->xslab + h->x_off_keep;
+    h->cap[(void*)&h->d_counts] = 16 * L0;
+    h->cap[(void*)&h->d_freq0] = 8 * L0;
+    h->cap[(void*)&h->d_keep] = L0;
+    h->xchg_ok = true;
+    h->xchg_seq = 0;
     return 0;
 }
 
@@ -329,11 +468,13 @@ int garlic_gpu_create(int device, garlic_gpu_t** out)
     cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_tables, cudaEventDisableTiming);
     h->prune = getenv("GARLIC_NO_PRUNE") == nullptr;
+    h->tl_on = getenv("GARLIC_TIMELINE") != nullptr;
     cudaEventCreate(&h->ev_sq0);
     cudaEventCreate(&h->ev_sq1);
     if (const char* e = getenv("GARLIC_ITEM_PIECES")) { const int m = atoi(e); if (m >= 1 && m <= 16) h->item_pieces = m; }
     h->wlod_mma = getenv("GARLIC_NO_MMA") == nullptr;
-    cudaMalloc((void**)&h->d_cnt, 4 * sizeof(unsigned));
+    cudaMalloc((void**)&h->d_cnt, 8 * sizeof(unsigned));
+    h->zero_cap = 8;
     *out = h;
     return 0;
 }
@@ -343,13 +484,15 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    tl_dump(h);
+    xchg_teardown(h);
     dev_free(h->d_alleles); dev_free(h->d_key); dev_free(h->d_geno0); dev_free(h->d_geno); free_counts(h);
     dev_free(h->d_gl0); dev_free(h->d_gl); dev_free(h->d_freq0); dev_free(h->d_freq); dev_free(h->d_lut);
     dev_free(h->d_ldplanes); dev_free(h->d_ldpairs); dev_free(h->d_text); dev_free(h->d_textoff); dev_free(h->d_nonblank);
     dev_free(h->d_gpos); dev_free(h->d_nomut); dev_free(h->d_norec); dev_free(h->d_wlut); dev_free(h->d_invld);
     dev_free(h->d_homf); dev_free(h->d_keep); dev_free(h->d_src); dev_free(h->d_pos0); dev_free(h->d_chr_of0);
     dev_free(h->d_pos); dev_free(h->d_chr_of); dev_free(h->d_chr_start); dev_free(h->d_chr_param);
-    dev_free(h->d_out); dev_free(h->d_amb); dev_free(h->d_sorted); dev_free(h->d_hist); dev_free(h->d_kept); dev_free(h->d_items_p2); dev_free(h->d_cnt); dev_free(h->d_items); dev_free(h->d_indlist); dev_free(h->d_dump);
+    dev_free(h->d_out); dev_free(h->d_amb); dev_free(h->d_sorted); dev_free(h->d_items_p2); dev_free(h->d_cnt); dev_free(h->d_items); dev_free(h->d_indlist); dev_free(h->d_dump);
     dev_free(h->d_scan); dev_free(h->d_breaks); dev_free(h->d_thin);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -360,7 +503,7 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     if (h->brk_pin) cudaFreeHost(h->brk_pin);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     dev_free(h->d_plan_head); dev_free(h->d_plan_seg); dev_free(h->d_plan_rng); dev_free(h->d_bhw); dev_free(h->d_plan_fast); dev_free(h->d_bflag);
-    dev_free(h->d_pmax); dev_free(h->d_cand_list); dev_free(h->d_cand_cnt); dev_free(h->d_units); dev_free(h->d_nunits);
+    dev_free(h->d_pmax); dev_free(h->d_cand_list); dev_free(h->d_cand_cnt); dev_free(h->d_units);
     if (h->ev_sq0) cudaEventDestroy(h->ev_sq0);
     if (h->ev_sq1) cudaEventDestroy(h->ev_sq1);
     if (h->comm) ncclCommDestroy(h->comm);
@@ -393,6 +536,7 @@ int garlic_gpu_comm_init(garlic_gpu_t* h, const uint8_t* id128, int rank, int wo
 {
     CK(cudaSetDevice(h->device));
     if (world < 1 || rank < 0 || rank >= world) FAIL("comm_init: bad rank / world size");
+    xchg_teardown(h);
     if (h->comm) {
         if (h->counts_win) ncclCommWindowDeregister(h->comm, h->counts_win);
         ncclCommDestroy(h->comm); h->comm = nullptr;
@@ -427,6 +571,7 @@ int garlic_gpu_set_shape(garlic_gpu_t* h, int n_ind, int ind_offset, int64_t n_l
     h->row_words0 = (((n_loci + kPad + 31) >> 5) + 3) & ~(int64_t)1;
     if (dev_alloc(h, &h->d_geno0, (size_t)n_ind * h->row_words0)) return 1;
     CK(cudaMemsetAsync(h->d_geno0, 0xff, (size_t)n_ind * h->row_words0 * 8, h->stream));
+    if (h->xslab && (h->cap.find((void*)&h->d_counts) == h->cap.end() || h->cap[(void*)&h->d_counts] != (size_t)16 * n_loci)) xchg_teardown(h);
     if (alloc_counts(h, (size_t)4 * n_loci)) return 1;
     CK(cudaMemsetAsync(h->d_counts, 0, (size_t)4 * n_loci * sizeof(int), h->stream));
     if (dev_alloc(h, &h->d_pos0, (size_t)n_loci)) return 1;
@@ -573,6 +718,7 @@ int garlic_gpu_count_packed(garlic_gpu_t* h, const int32_t* nalleles_corr, const
 {
     CK(cudaSetDevice(h->device));
     if (!h->have_geno0) FAIL("count_packed: no genotypes loaded");
+    tl_mark(h, "count_packed:in");
     h->counts_reduced = false; h->counts_hi_reduced = false;
     if (h->precounted) {
         h->precounted = false;             // garlic_gpu_put_packed counted the rows while they arrived
@@ -590,6 +736,7 @@ int garlic_gpu_count_packed(garlic_gpu_t* h, const int32_t* nalleles_corr, const
         h->launches++;
         CK(cudaStreamSynchronize(h->stream));                          // the caller may reuse its vectors
     }
+    if (h->xchg_ok) return 0;              // the sums are formed by the NVLink exchange fused with freq + keep (filter)
     return reduce_counts(h, false);        // starts right behind the count kernel; filter() finds the sums ready
 }
 
@@ -723,6 +870,7 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     Laps laps("filter");
     laps.rank = h->comm_rank;
     if (finish_outputs(h)) return 1;
+    tl_mark(h, "filter:in");
     if (!freq_override) h->fmin = 0.5;
     bool freq_direct = false, keep_direct = false, copies_in_flight = false;
     if (dev_alloc(h, &h->d_freq0, (size_t)L0)) return 1;
@@ -757,20 +905,34 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
         CK(cudaMemcpyAsync(h->d_keep, keep, L0, cudaMemcpyHostToDevice, h->stream));
     } else {
         // the one data-path collective: per-SNP counters of all shards, summed in place on this stream
-        if (reduce_counts(h, false)) return 1;
-        LAUNCH(launch_freq_keep(h->d_counts, L0, h->d_pos0, h->d_chr_of0, h->d_chr_param, oob, h->d_freq0, h->d_keep, h->stream));
+        if (h->comm && !h->xchg_tried && ensure_xchg(h)) return 1;
+        if (h->xchg_ok && !h->counts_reduced) {
+            // one kernel over NVLink peer memory: counters of all ranks summed, freq and keep evaluated, all three stored
+            // into every rank's tables (xchg.cu) — instead of ncclAllReduce + freq_keep_kernel
+            XchgParams X;
+            memset(&X, 0, sizeof(X));
+            for (int p = 0; p < h->comm_world; ++p) {
+                uint8_t* base = static_cast<uint8_t*>(h->xpeer[p]);
+                X.flags[p] = reinterpret_cast<unsigned*>(base);
+                X.counts[p] = reinterpret_cast<int*>(base + h->x_off_counts);
+                X.freq[p] = reinterpret_cast<double*>(base + h->x_off_freq);
+                X.keep[p] = base + h->x_off_keep;
+            }
+            X.n = h->comm_world; X.rank = h->comm_rank; X.seq = ++h->xchg_seq; X.L0 = L0;
+            X.pos = h->d_pos0; X.chr_of = h->d_chr_of0; X.chr_param = h->d_chr_param; X.oob = oob;
+            X.done_counter = reinterpret_cast<unsigned*>(h->xslab) + 48;
+            LAUNCH(launch_xchg_freq_keep(X, h->stream));
+            h->counts_reduced = true;
+        } else {
+            if (reduce_counts(h, false)) return 1;
+            LAUNCH(launch_freq_keep(h->d_counts, L0, h->d_pos0, h->d_chr_of0, h->d_chr_param, oob, h->d_freq0, h->d_keep, h->stream));
+        }
         // page-locked caller buffers (garlic_gpu_host_alloc) are written by the copy engine directly
         freq_direct = freq_out && is_pinned(freq_out);
         keep_direct = keep_out && is_pinned(keep_out);
         // freq[] / keep[] travel to the host on a second stream, behind the kernel that made them, while the keep-mask
         // scan and the compaction run on: the host only waits for them at the end of this call
-        if (freq_out || keep_out) {
-            CK(cudaEventRecord(h->ev_copy, h->stream));
-            CK(cudaStreamWaitEvent(h->copy_stream, h->ev_copy, 0));
-            if (freq_out) CK(cudaMemcpyAsync(freq_direct ? freq_out : freq0, h->d_freq0, L0 * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
-            if (keep_out) CK(cudaMemcpyAsync(keep_direct ? keep_out : keep, h->d_keep, L0, cudaMemcpyDeviceToHost, h->copy_stream));
-            copies_in_flight = true;
-        }
+        copies_in_flight = freq_out || keep_out;     // (enqueued below, behind the few bytes this call itself waits for)
     }
     // exclusive scan of the keep mask on the device: gather list, keep bits per input word, per output word
     // the input word it starts in, kept offset of every chromosome
@@ -781,8 +943,18 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
     CK(launch_keep_scan(h->d_keep, L0, h->d_chr_of0, h->n_chr, h->d_scan, d_total, h->d_src, d_chr_off_kept, h->stream));
     h->launches += 3;
     CK(cudaMemcpyAsync(meta, d_total, (size_t)(h->n_chr + 2) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (copies_in_flight) {
+        // freq[] / keep[] travel to the host on a second stream while the path runs on.  They start behind the copy of
+        // the kept-SNP count above: device-to-host copies share one engine, and 5 MB in front of those few bytes would
+        // hold this call's synchronisation for 0.1 ms.
+        CK(cudaEventRecord(h->ev_copy, h->stream));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->ev_copy, 0));
+        if (freq_out) CK(cudaMemcpyAsync(freq_direct ? freq_out : freq0, h->d_freq0, L0 * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+        if (keep_out) CK(cudaMemcpyAsync(keep_direct ? keep_out : keep, h->d_keep, L0, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
     laps.lap("freq_keep+scan");
+    tl_mark(h, "filter:after-sync");
     if (freq_override) {
         if (freq_out) memcpy(freq_out, freq0, L0 * sizeof(double));
         if (keep_out) memcpy(keep_out, keep, L0);
@@ -846,6 +1018,7 @@ int garlic_gpu_filter(garlic_gpu_t* h, int oob, const int32_t* chr_param, const 
         laps.lap("freq/keep d2h");
     }
     h->filtered = true; h->tables = false; h->have_ld = false;
+    tl_mark(h, "filter:out");
     return 0;
 }
 
@@ -880,6 +1053,7 @@ int garlic_gpu_set_tables(garlic_gpu_t* h, double error, int max_gap, const int3
     h->error = error; h->max_gap = max_gap;
     Laps laps("set_tables");
     laps.rank = h->comm_rank;
+    tl_mark(h, "set_tables:in");
     h->cen.assign(2 * h->n_chr, 0);
     if (centromeres) h->cen.assign(centromeres, centromeres + 2 * h->n_chr);
     const int64_t L = h->L;
@@ -911,6 +1085,7 @@ int garlic_gpu_set_tables(garlic_gpu_t* h, double error, int max_gap, const int3
         h->stretches.clear();
     }
     laps.lap("enqueue");
+    tl_mark(h, "set_tables:out");
     h->tables = true; h->have_ld = false; h->bound_W = 0; h->bound_tables_W = 0; h->tables_gen++;
     return 0;
 }
@@ -1002,6 +1177,24 @@ static int ensure_stretches(garlic_gpu* h)
         if (hi > a) h->stretches.push_back({c, a, hi});
     }
     h->stretches_pending = false;
+    return 0;
+}
+
+// counters every pass 2 starts from zero, in one block (one memset): [cnt 4 | work units 4 | hist n_ind+1 | kept n_ind+1]
+static int ensure_zero_block(garlic_gpu* h)
+{
+    const size_t n = 8 + 2 * ((size_t)h->n_ind + 1);
+    if (h->zero_cap < n) {
+        if (h->d_cnt) cudaFree(h->d_cnt);
+        h->d_cnt = nullptr;
+        CK(cudaMalloc((void**)&h->d_cnt, n * sizeof(unsigned)));
+        CK(cudaMemsetAsync(h->d_cnt, 0, n * sizeof(unsigned), h->stream));
+        h->zero_cap = n;
+    }
+    h->d_nunits = h->d_cnt + 4;
+    h->d_hist = h->d_cnt + 8;
+    h->d_kept = h->d_hist + h->n_ind + 1;
+    h->zero_n = n;
     return 0;
 }
 
@@ -1217,8 +1410,10 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
     if (!h->tables) FAIL("windows: call set_tables first");
     if (winsize < 2 || winsize > kMaxW) FAIL("windows: winsize out of range [2,4096]");
     if (step < 1) FAIL("windows: step must be >= 1");
+    tl_mark(h, "windows:in");
     if (weighted && ensure_weighted(h, winsize)) return 1;
     if (ensure_geno(h, weighted ? 0 : winsize)) return 1;
+    tl_mark(h, "windows:squeeze-enqueued");
     const int W = winsize;
     const int n_lanes = individuals ? n : h->n_ind;
     if (individuals) {
@@ -1228,6 +1423,7 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
     std::vector<Segment> segs;
     std::vector<Item> items;
     if (ensure_stretches(h)) return 1;                 // (the compaction above is already on the stream)
+    tl_mark(h, "windows:stretches");
     segments_from_stretches(h->stretches, W, segs);
     const int64_t slots = garlic_gpu_window_slots(h, step);
     if (dev_alloc(h, &h->d_dump, (size_t)n_lanes * slots)) return 1;
@@ -1270,6 +1466,7 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
     rc = launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, false, true, items_tile_snps(items, W));
     }
     if (!rc) { h->kde_src = d_dump; h->kde_src_n = (int64_t)n_lanes * slots; }
+    tl_mark(h, "windows:enqueued");
     if (!rc && finish_outputs(h)) rc = 1;
     if (!rc && out_dev) {
         *out_dev = d_dump;
@@ -1283,6 +1480,7 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
         if (e != cudaSuccess) { h->err = std::string("windows: ") + cudaGetErrorString(e); rc = 1; }
         else if (staged) memcpy(out, h->pin, bytes);
     }
+    tl_mark(h, "windows:out");
     return rc;
 }
 
@@ -1333,6 +1531,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     const int W = winsize;
     Laps laps("call_roh");
     laps.rank = h->comm_rank;
+    tl_mark(h, "call_roh:in");
     // pruned pass (bound.cuh): unweighted table mode, window sizes the bound covers, cutoffs inside its fixed-point range
     int cut_ok = 0;
     bound_cut_store(cutoff, 1.0, &cut_ok);
@@ -1405,7 +1604,9 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
             // and 1/LD ≤ 1 because every LD sum contains the diagonal term 1 (garlic-data.cpp:521-527)
             P.tol = (double)(W + 8) * 2.0 * 2.220446049250313e-16 * W * h->amax;
         }
-        CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
+        if (ensure_zero_block(h)) return 1;
+        CK(cudaMemsetAsync(h->d_cnt, 0, h->zero_n * sizeof(unsigned), h->stream));
+        P.out_count = h->d_cnt;
         // pruned pass: the piece maxima (computed with the compaction, or now) are thresholded into dense per-item
         // candidate lists and a queue of work units; the walker below only visits those
         const int tile_snps = prune ? h->p2_tile : items_tile_snps(*its, W);
@@ -1423,8 +1624,6 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
             if (dev_alloc(h, &h->d_cand_list, (size_t)n_its * h->n_ind)) return 1;
             if (dev_alloc(h, &h->d_cand_cnt, (size_t)n_its + 1)) return 1;
             if (dev_alloc(h, &h->d_units, (size_t)unit_cap)) return 1;
-            if (dev_alloc(h, &h->d_nunits, (size_t)4)) return 1;
-            CK(cudaMemsetAsync(h->d_nunits, 0, 4 * sizeof(unsigned), h->stream));
             LAUNCH(launch_select(d_its, n_its, h->d_pmax, h->pmax_stride, h->n_ind, cut_store, h->d_bflag,
                                  h->d_cand_list, h->n_ind, h->d_cand_cnt, h->d_units, h->d_nunits, unit_cap, kUnitThreads, bound_c2(W), h->stream));
             cl.list = h->d_cand_list; cl.cnt = h->d_cand_cnt; cl.stride = h->n_ind;
@@ -1432,13 +1631,12 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         CK(cudaEventRecord(h->ev2, h->stream));
         // run records are bucketed by individual, ordered, stitched and packed on the device
         // (kernels.cu:launch_bucket_by_individual): the final runs end up dense in d_out, their number in d_cnt[2]
-        if (dev_alloc(h, &h->d_hist, (size_t)h->n_ind + 1)) return 1;
-        if (dev_alloc(h, &h->d_kept, (size_t)h->n_ind + 1)) return 1;
         if (dev_alloc(h, &h->d_sorted, (size_t)h->out_cap)) return 1;
-        CK(cudaMemsetAsync(h->d_hist, 0, ((size_t)h->n_ind + 1) * sizeof(unsigned), h->stream));
-        CK(cudaMemsetAsync(h->d_kept, 0, ((size_t)h->n_ind + 1) * sizeof(unsigned), h->stream));
         P.hist = h->d_hist;
-        if (prune_now) LAUNCH(launch_walk_units(P, d_its, h->d_units, h->d_nunits, unit_cap, tile_snps, cl, h->stream));
+        // window sizes below 32 leave a quarter of the pairs (a short window is homozygous by chance often enough): eight-warp
+        // CTAs over the candidate lists share one table tile among 256 candidates, where a work unit would stage it for 64
+        if (prune_now && !bound_partial(W)) LAUNCH(launch_walk_units(P, d_its, h->d_units, h->d_nunits, unit_cap, tile_snps, cl, h->stream));
+        else if (prune_now) LAUNCH(launch_walk(P, d_its, n_its, false, true, false, tile_snps, cl, h->stream));
         else if (launch_any_walk(h, P, d_its, n_its, weighted, true, false, tile_snps)) return 1;
         CK(cudaEventRecord(h->ev1, h->stream));
         LAUNCH(launch_bucket_by_individual(h->d_out, h->d_cnt, h->out_cap, h->d_hist, h->n_ind, h->d_sorted, thr, h->d_kept,
@@ -1455,8 +1653,10 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         if (prune_now) CK(cudaMemcpyAsync(cnt + 4, h->d_nunits, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(stage, h->d_out, guess * sizeof(RohRec), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(stage + guess, h->d_amb, amb_guess * sizeof(RohRec), cudaMemcpyDeviceToHost, h->stream));
+        tl_mark(h, "call_roh:enqueued");
         CK(cudaStreamSynchronize(h->stream));
         if (finish_outputs(h)) return 1;
+        tl_mark(h, "call_roh:synced");
         CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         CK(cudaEventElapsedTime(&ms_coarse, h->ev0, h->ev2));
         pruned = prune_now;
@@ -1549,6 +1749,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     h->stats[6] = (double)its->size() * h->n_ind;
     h->stats_items = 0;
     laps.lap("out");
+    tl_mark(h, "call_roh:out");
     return 0;
 }
 

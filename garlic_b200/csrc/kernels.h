@@ -89,6 +89,20 @@ cudaError_t launch_build_wlut(const double* lut, const double* nomut, const doub
 cudaError_t launch_tokenize_tgls(const char* text, const long long* off, int n_snp, int n_ind, int ind_lo, double* out,
                                  int64_t out_stride, long long snp0, int* n_tokens, int2* hard_list, unsigned* hard_count,
                                  unsigned hard_cap, cudaStream_t st);
+// the counter exchange over NVLink peer memory, fused with freq + keep (xchg.cu)
+constexpr int kXchgMaxRanks = 16, kXchgReady = 0, kXchgDone = 16;   // flag words per rank: ready[16] | done[16]
+struct XchgParams {
+    int* counts[kXchgMaxRanks];        // every rank's counters [4][L0] (rows 0, 1 are exchanged)
+    double* freq[kXchgMaxRanks];       // every rank's freq0[L0]
+    uint8_t* keep[kXchgMaxRanks];      // every rank's keep[L0]
+    unsigned* flags[kXchgMaxRanks];    // every rank's flag words
+    int n, rank;
+    unsigned seq;                      // call number, the same on every rank
+    long long L0;
+    const int* pos; const int* chr_of; const int* chr_param; int oob;
+    unsigned* done_counter;            // local: CTAs of this launch that have finished their slice
+};
+cudaError_t launch_xchg_freq_keep(const XchgParams& P, cudaStream_t st);
 // computeKDE on the device (kde.cu): scratch size in doubles; out → state[8] | x[m] | y[m] inside the scratch
 size_t kde_scratch_doubles(int m);
 cudaError_t launch_kde(const double* v, long long n, int m, double* scratch, double** out, int* launches, cudaStream_t st);
