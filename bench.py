@@ -84,60 +84,78 @@ def unpack_rows(rows_u8, L):
 # ------------------------------------------------------------------------------------------------
 # clocks sampling during the timed region (B200_PROFILING.md)
 # ------------------------------------------------------------------------------------------------
+_SAMPLER_SRC = r"""
+import json, sys, time
+import pynvml as nv
+nv.nvmlInit()
+hs = [nv.nvmlDeviceGetHandleByIndex(int(i)) for i in sys.argv[1:]]
+mx = float(nv.nvmlDeviceGetMaxClockInfo(hs[0], nv.NVML_CLOCK_SM))
+sys.stdout.write("ready\n"); sys.stdout.flush()
+sys.stdin.readline()                      # "go"
+import select
+sm, mask = [], 0
+while True:
+    for h in hs:
+        try:
+            sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            pass
+    if select.select([sys.stdin], [], [], 0.001)[0]:
+        break
+print(json.dumps(dict(sm=sm, mask=mask, mx=mx)))
+"""
+
+
 class ClockSampler:
-    """Polls NVML (SM clock, clocks-event reasons) from a thread every millisecond while the timed region runs:
-    the region lasts tens of milliseconds, too short for `nvidia-smi -lms`.  Falls back to one nvidia-smi query."""
+    """Polls NVML (SM clock, clocks-event reasons) about every millisecond while the timed region runs: the region lasts
+    tens of milliseconds, too short for `nvidia-smi -lms`.  The polling runs in a helper PROCESS — a thread inside rank 0
+    would take the interpreter lock from the thread that drives the GPU some sixteen times per millisecond when it watches
+    eight GPUs, and every rank waits for rank 0 at the next exchange.  Falls back to one nvidia-smi query."""
     REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20))
 
     def __init__(self, index, n_devices=1):
-        """index: first local GPU; n_devices: how many consecutive local GPUs this (one) thread watches — under
-        torchrun rank 0 watches every GPU of the job so that the other ranks' host cores stay free."""
-        self.index, self.sm, self.mask, self.mx, self.h, self.t = index, [], 0, None, None, None
-        self.run = False
+        """index: first local GPU; n_devices: how many consecutive local GPUs the helper watches — under torchrun rank 0
+        starts one helper for every GPU of the job."""
+        self.index, self.p = index, None
         try:
-            import pynvml
-            pynvml.nvmlInit()
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
             ids = [int(x) for x in vis.split(",")] if vis and all(x.strip().isdigit() for x in vis.split(",")) else None
-            self.nv = pynvml
-            self.hs = [pynvml.nvmlDeviceGetHandleByIndex(ids[index + k] if ids else index + k) for k in range(n_devices)]
-            self.h = self.hs[0]
-            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            phys = [str(ids[index + k] if ids else index + k) for k in range(n_devices)]
+            self.p = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC] + phys, stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+            if self.p.stdout.readline().strip() != "ready":
+                raise RuntimeError("sampler did not start")
         except Exception:
-            self.h = None
-
-    def _poll(self):
-        nv = self.nv
-        while self.run:
-            for h in self.hs:
-                try:
-                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
-                except Exception:
-                    pass
-            time.sleep(0.001)
+            if self.p is not None:
+                self.p.kill()
+            self.p = None
 
     def start(self):
-        if self.h is None:
+        if self.p is None:
             return
-        self.run = True
-        self.t = threading.Thread(target=self._poll, daemon=True)
-        self.t.start()
+        self.p.stdin.write("go\n")
+        self.p.stdin.flush()
 
     def stop(self):
-        if self.h is None:
+        if self.p is not None:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
-                a, b = [float(x) for x in out.strip().split(",")]
-                return dict(sm_mhz=a, sm_max_mhz=b, reasons=[], samples=1, how="one nvidia-smi query after the region")
+                self.p.stdin.write("stop\n")
+                self.p.stdin.flush()
+                r = json.loads(self.p.stdout.readline())
+                self.p.wait(timeout=5)
+                reasons = sorted(nm for nm, bit in self.REASONS if r["mask"] & bit)
+                return dict(sm_mhz=float(np.median(r["sm"])) if r["sm"] else None, sm_max_mhz=r["mx"], reasons=reasons,
+                            samples=len(r["sm"]), how="NVML polled about every ms by a helper process during the timed region")
             except Exception:
-                return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvml and nvidia-smi unavailable"], samples=0)
-        self.run = False
-        self.t.join(timeout=2)
-        reasons = sorted(nm for nm, bit in self.REASONS if self.mask & bit)
-        return dict(sm_mhz=float(np.median(self.sm)) if self.sm else None, sm_max_mhz=self.mx, reasons=reasons,
-                    samples=len(self.sm), how="NVML polled every ms during the timed region")
+                self.p.kill()
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+            a, b = [float(x) for x in out.strip().split(",")]
+            return dict(sm_mhz=a, sm_max_mhz=b, reasons=[], samples=1, how="one nvidia-smi query after the region")
+        except Exception:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvml and nvidia-smi unavailable"], samples=0)
 
 
 def bind_near_gpu(index):
@@ -390,7 +408,7 @@ def main():
         else:                                                # rank 0 gets all KDE individuals' thinned LODs
             thin = g.windows_gather(W, W, kde_local, kde_max, world, want=lead)
         t0 = lap("pass1_thinned_windows", t0)
-        roh = g.call_roh(W, cutoff, ov, exact=a.exact)       # K5 pass 2 (fused) -> ROH records on the host
+        roh = g.call_roh(W, cutoff, ov, exact=a.exact, copy=False)   # K5 pass 2 (fused) -> ROH records on the host
         t0 = lap("pass2_call_roh", t0)
         st = g.last_stats()
         nb = lambda x: 0 if x is None else x.nbytes

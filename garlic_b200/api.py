@@ -317,8 +317,9 @@ class GarlicGPU:
         buf = np.ascontiguousarray(comm_id, np.uint8)
         self._ck(self.lib.garlic_gpu_comm_init(self.h, _p(buf), C.c_int(rank), C.c_int(world)))
 
-    def call_roh(self, W, cutoff, overlap_frac, weighted=False, exact=False, cap=1 << 16):
-        """→ int32[n, 4] rows (ind, chr, start_idx, stop_idx), sorted by (ind, chr, start)."""
+    def call_roh(self, W, cutoff, overlap_frac, weighted=False, exact=False, cap=1 << 16, copy=True):
+        """→ int32[n, 4] rows (ind, chr, start_idx, stop_idx), sorted by (ind, chr, start).  copy=False: a view of a
+        buffer owned by this object, overwritten by the next call."""
         buf = getattr(self, "_roh_buf", None)
         if buf is None or len(buf) < cap:
             buf = self._roh_buf = np.empty((cap, 4), np.int32)
@@ -330,7 +331,7 @@ class GarlicGPU:
             if cnt.value <= len(buf):
                 break
             buf = self._roh_buf = np.empty((cnt.value + 1024, 4), np.int32)
-        return buf[:cnt.value].copy()
+        return buf[:cnt.value].copy() if copy else buf[:cnt.value]
 
     def last_stats(self):
         s = (C.c_double * 8)()

@@ -200,8 +200,8 @@ cudaError_t launch_hom_freq(const int* counts, long long L0, const int* src, lon
 //   phase 2 lanes = rows, a thread forms four neighbouring window sums LD[j-k][k], k = 4g … 4g+3, from one pass over the
 //           W+3 entries they share — each sum ascending from 0.0 as the reference adds (:489-494, 521-527);
 //   write   the reciprocals leave through shared memory so that every weight row receives its 32 consecutive k at once.
-// The popcounts are the only part a tensor-core contraction could replace: they are about a third
-// of this kernel, the rest is fp64 division and addition in a fixed order.
+// The popcounts are the only part a tensor-core contraction could replace: they are about a quarter
+// of this kernel's instructions, the rest is fp64 division and addition in a fixed order.
 // ------------------------------------------------------------------------------------------
 constexpr int kLdRows = 32;            // SNPs j per CTA
 constexpr int kLdMaxWords = 8;         // plane words per SNP held in registers: n_ld <= 512
