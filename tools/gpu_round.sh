@@ -12,7 +12,7 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu --no-configs > $out/${tag}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 if [ "$full" = full ]; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'squeeze_bound_kernel|walk_units_kernel|select_kernel|count_packed_kernel' -s 8 -c 4 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"squeeze_bound_kernel|walk_units_kernel|select_kernel|count_packed_kernel|thin_windows_kernel|bound_tables_kernel" -s 12 -c 6 \
     -o $out/${tag}_pass2 -f python bench.py --steps 2 --warmup 1 --no-cpu --no-configs > $out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
 head -c 3000 $out/${tag}_bench_own.json
