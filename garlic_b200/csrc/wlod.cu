@@ -162,7 +162,7 @@ __global__ void ld_sum_kernel(const double* __restrict__ P, const int* __restric
         const double* row = P + j * D + (W - 1 - k);
         double acc = 0.0;
         for (int n = 0; n < W; ++n) acc += row[n];
-        invld[w * (W + kInvFront + kInvBack) + kInvFront + k] = 1.0 / acc;
+        invld[w * inv_stride(W) + kInvFront + k] = 1.0 / acc;
         if (ld_out) ld_out[w * W + k] = acc;
     }
 }
@@ -339,7 +339,7 @@ ld_band_fused_kernel(const LdFusedParams Q)
         __syncthreads();
         // ---- write: weight row w receives k = j - w for the tile's j: consecutive k, consecutive lanes
         {
-            const int ldw = W + kInvFront + kInvBack;
+            const int ldw = inv_stride(W);
             const int n_w = kLdRows + W - 1;                // rows w = j0 - (W-1) … j0 + 31
             for (int wi = warp; wi < n_w; wi += 8) {
                 const long long w = j0 - (W - 1) + wi;
@@ -437,7 +437,7 @@ __device__ __forceinline__ void wlod_walk_item(const WlodParams& Q, const Item& 
     for (int t = it.w0, q = 0; t < t_end; ++t, ++q) {
         bool f = false;
         if (t < it.we) {
-            const double* inv = Q.invld + (int64_t)t * (W + kInvFront + kInvBack) + kInvFront;
+            const double* inv = Q.invld + (int64_t)t * inv_stride(W) + kInvFront;
             double acc = 0.0;
             for (int k = 0; k < W; ++k) {
                 const int s = t + k;
@@ -534,7 +534,7 @@ wlod_mma_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items,
         // {1,2,3},{2,3},{3} — no predicated tensor-core instructions; the operand loads need no predicates either
         // because weight rows are zero-padded (wlod.h) and windows past the segment end are masked afterwards.
         const int E2 = ((W + 6) / 4) | 1;
-        const int ldw = W + kInvFront + kInvBack;
+        const int ldw = inv_stride(W);
         // blocks start on a multiple of 4 SNPs (windows before w0 are masked off below): a quad then never straddles a
         // packed 64-bit genotype word and the word reload is a warp-uniform branch taken every 8th quad
         for (int tb = it.w0 & ~3; tb < it.own_hi; tb += 32) {
@@ -658,6 +658,229 @@ wlod_mma_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items,
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K5-W fast pass, operands through shared memory (table mode, moderate window sizes).
+// Same banded product, same tile schedule, same flag / coverage logic as wlod_mma_kernel above; what changes is where
+// the DMMA operands come from.  There every quad cost eight loads through L1 whose addresses the compiler rebuilt from
+// scratch (≈ 125 instructions per 16 DMMA, 4.4 long-scoreboard stall cycles per issue: the tensor pipe sat at 60 %).
+// Here the four warps of a CTA — four individual groups of the same item — walk the item's blocks of 32 windows
+// together, and per block ONE pair of bulk copies (cp.async.bulk, completing on an mbarrier) stages
+//   * the block's 32 weight rows (contiguous in global memory: 32 · inv_stride(W) doubles) and
+//   * the score-table entries of the SNPs the block touches ((W + 40) · 32 bytes)
+// into one of two buffers, the next block's copies in flight while this one is multiplied.  A fragments are then one
+// LDS.64 at  table + 32·m + 8·g  (conflict-free: a quad's four SNPs own eight banks each, equal genotypes broadcast), B
+// fragments one LDS.64 at  row·(stride − 1) + m, both one quad ahead of the DMMAs that consume them.
+// ------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ uint32_t wm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void wm_mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wm_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void wm_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void wm_bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(wm_smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(wm_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void wm_mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WM_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WM_WAIT_DONE;\n"
+        "bra WM_WAIT_LOOP;\n"
+        "WM_WAIT_DONE:\n"
+        "}\n" ::"r"(wm_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ double wm_lds(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(128, 3)
+wlod_mma_smem_kernel(const WlodParams Q, const Item* __restrict__ items, int n_items, int n_groups, int wt_bytes, int tab_bytes)
+{
+    extern __shared__ __align__(128) unsigned char wm_smem[];
+    const WalkParams& P = Q.base;
+    const int W = P.W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gblocks = (n_groups + 3) >> 2;
+    const long long total = (long long)n_items * gblocks;
+    const int NW = ((W + 31) >> 5) + 1, r = (32 - (W & 31)) & 31;
+    const int buf_bytes = wt_bytes + tab_bytes;
+    uint32_t* ring = reinterpret_cast<uint32_t*>(wm_smem + 2 * buf_bytes) + threadIdx.x;
+    const int rstride = 128;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wm_smem + 2 * buf_bytes + (size_t)NW * 128 * sizeof(uint32_t));
+    const uint32_t buf_u32 = wm_smem_u32(wm_smem);
+    const double cut_hi = P.cutoff + P.tol, cut_lo = P.cutoff - P.tol;
+    const int j = lane >> 2, mq = lane & 3;    // window column / SNP-within-k-step of this lane's B element; row j of A
+    const int ldw = inv_stride(W);
+    if (threadIdx.x == 0) { wm_mbar_init(bar, 1); wm_mbar_init(bar + 1, 1); }
+    __syncthreads();
+    uint32_t ph0 = 0, ph1 = 0;
+    // byte offsets inside a buffer: this lane's weight element of tile q at block-relative SNP m = 4 kq + mq sits at
+    // boff[q] + 32 kq; its table entry at wt_bytes + 32 mq + 128 kq (+ 8 g)
+    uint32_t boff[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) boff[q] = (uint32_t)(((8 * q + j) * (ldw - 1) + kInvFront + mq) * 8);
+    const uint32_t toff = (uint32_t)(wt_bytes + 32 * mq);
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const int item = (int)(u / gblocks);
+        const int group_raw = (int)(u % gblocks) * 4 + warp;
+        const bool warp_on = group_raw < n_groups;                 // a warp without a group runs along (barriers) and emits nothing
+        const int group = warp_on ? group_raw : n_groups - 1;
+        const Item it = items[item];
+        const int k_own = group * 32 + lane;
+        const bool active = warp_on && k_own < P.n_lanes;
+        const int ind = P.ind_list ? P.ind_list[k_own < P.n_lanes ? k_own : P.n_lanes - 1] : (k_own < P.n_lanes ? k_own : P.n_lanes - 1);
+        const uint64_t* rowA[4];
+#pragma unroll
+        for (int rg = 0; rg < 4; ++rg) {
+            int k = group * 32 + 8 * rg + j;
+            if (k >= P.n_lanes) k = P.n_lanes - 1;
+            const int ia = P.ind_list ? P.ind_list[k] : k;
+            rowA[rg] = P.geno + (int64_t)ia * P.row_words;
+        }
+        LaneState S;
+        S.win = 0; S.cov = 0; S.run_start = -1; S.fw = 0; S.hist = 0; S.ambig = false;
+        if (W > 32) for (int w = 0; w < NW; ++w) ring[w * rstride] = 0;
+        int wr = 1 % NW;
+        const int E2 = ((W + 6) / 4) | 1;
+        const int tb0 = it.w0 & ~3;
+        const int n_blk = (it.own_hi - tb0 + 31) >> 5;
+        auto issue = [&](int b) {                                  // thread 0: both copies of block b into buffer b & 1
+            const int tbb = tb0 + 32 * b;
+            unsigned char* d = wm_smem + (size_t)(b & 1) * buf_bytes;
+            wm_mbar_expect_tx(bar + (b & 1), (uint32_t)buf_bytes);
+            wm_bulk_load(d, Q.invld + (int64_t)tbb * ldw, (uint32_t)wt_bytes, bar + (b & 1));
+            wm_bulk_load(d + wt_bytes, Q.wlut + (int64_t)tbb * 4, (uint32_t)tab_bytes, bar + (b & 1));
+        };
+        if (threadIdx.x == 0) { issue(0); if (n_blk > 1) issue(1); }
+#pragma unroll 1
+        for (int b = 0; b < n_blk; ++b) {
+            const int tb = tb0 + 32 * b;
+            if (b & 1) { wm_mbar_wait(bar + 1, ph1); ph1 ^= 1u; } else { wm_mbar_wait(bar, ph0); ph0 ^= 1u; }
+            const uint32_t base = buf_u32 + (uint32_t)((b & 1) * buf_bytes);
+            uint32_t fhi = 0, flo = 0;
+            double c[4][4][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int rg = 0; rg < 4; ++rg) { c[q][rg][0] = 0.0; c[q][rg][1] = 0.0; }
+            uint64_t gw[4], gwn[4];                                    // packed genotype word in use / the next one, in flight
+            {
+                const int s0 = tb + mq;
+#pragma unroll
+                for (int rg = 0; rg < 4; ++rg) { gw[rg] = rowA[rg][s0 >> 5]; gwn[rg] = rowA[rg][(s0 >> 5) + 1]; }
+            }
+            const uint32_t tbase = base + toff;
+            auto load_quad = [&](auto mask, int kq, double (&a)[4], double (&bf)[4]) {
+                constexpr int MB = decltype(mask)::value;
+                const int s = tb + 4 * kq + mq;
+                const int sh = 2 * (s & 31);
+                if (kq > 0 && ((tb + 4 * kq) & 31) == 0) {
+#pragma unroll
+                    for (int rg = 0; rg < 4; ++rg) { gw[rg] = gwn[rg]; gwn[rg] = rowA[rg][(s >> 5) + 1]; }
+                }
+                const uint32_t ta = tbase + (uint32_t)(128 * kq);
+#pragma unroll
+                for (int rg = 0; rg < 4; ++rg) a[rg] = wm_lds(ta + (((uint32_t)(gw[rg] >> sh) & 3u) << 3));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if ((MB >> q) & 1) bf[q] = wm_lds(base + boff[q] + (uint32_t)(32 * kq));
+            };
+            auto mma_quad = [&](auto mask, const double (&a)[4], const double (&bf)[4]) {
+                constexpr int MB = decltype(mask)::value;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if ((MB >> q) & 1) {
+#pragma unroll
+                        for (int rg = 0; rg < 4; ++rg) dmma_m8n8k4(c[q][rg][0], c[q][rg][1], a[rg], bf[q]);
+                    }
+            };
+            using M1 = std::integral_constant<int, 0x1>; using M3 = std::integral_constant<int, 0x3>;
+            using M7 = std::integral_constant<int, 0x7>; using MF = std::integral_constant<int, 0xF>;
+            using ME = std::integral_constant<int, 0xE>; using MC = std::integral_constant<int, 0xC>;
+            using M8 = std::integral_constant<int, 0x8>;
+            double a0[4], b0[4], a1[4], b1[4];
+            load_quad(M1(), 0, a0, b0);
+            load_quad(M1(), 1, a1, b1); mma_quad(M1(), a0, b0);
+            load_quad(M3(), 2, a0, b0); mma_quad(M1(), a1, b1);
+            load_quad(M3(), 3, a1, b1); mma_quad(M3(), a0, b0);
+            load_quad(M7(), 4, a0, b0); mma_quad(M3(), a1, b1);
+            load_quad(M7(), 5, a1, b1); mma_quad(M7(), a0, b0);
+            load_quad(MF(), 6, a0, b0); mma_quad(M7(), a1, b1);
+            int kq = 6;
+#pragma unroll 1
+            for (; kq < E2; kq += 2) {
+                load_quad(MF(), kq + 1, a1, b1); mma_quad(MF(), a0, b0);
+                load_quad(MF(), kq + 2, a0, b0); mma_quad(MF(), a1, b1);
+            }
+            load_quad(ME(), kq + 1, a1, b1); mma_quad(ME(), a0, b0);
+            load_quad(MC(), kq + 2, a0, b0); mma_quad(ME(), a1, b1);
+            load_quad(MC(), kq + 3, a1, b1); mma_quad(MC(), a0, b0);
+            load_quad(M8(), kq + 4, a0, b0); mma_quad(MC(), a1, b1);
+            load_quad(M8(), kq + 5, a1, b1); mma_quad(M8(), a0, b0);
+            mma_quad(M8(), a1, b1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t myhi = 0, mylo = 0;
+#pragma unroll
+                for (int rg = 0; rg < 4; ++rg) {
+                    uint32_t bh = ((uint32_t)(c[q][rg][0] >= cut_hi) | ((uint32_t)(c[q][rg][1] >= cut_hi) << 1)) << (2 * mq);
+                    uint32_t bl = ((uint32_t)(c[q][rg][0] >= cut_lo) | ((uint32_t)(c[q][rg][1] >= cut_lo) << 1)) << (2 * mq);
+                    bh |= __shfl_xor_sync(0xffffffffu, bh, 1); bh |= __shfl_xor_sync(0xffffffffu, bh, 2);
+                    bl |= __shfl_xor_sync(0xffffffffu, bl, 1); bl |= __shfl_xor_sync(0xffffffffu, bl, 2);
+                    const uint32_t gh = __shfl_sync(0xffffffffu, bh, 4 * (lane & 7));
+                    const uint32_t gl_ = __shfl_sync(0xffffffffu, bl, 4 * (lane & 7));
+                    if (rg == (lane >> 3)) { myhi = gh; mylo = gl_; }
+                }
+                fhi |= myhi << (8 * q);
+                flo |= mylo << (8 * q);
+            }
+            const int nv = it.we - tb;                                 // valid windows of the block
+            uint32_t vm = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << nv) - 1u));
+            if (tb < it.w0) vm &= ~((1u << (it.w0 - tb)) - 1u);
+            fhi &= vm; flo &= vm;
+            S.ambig |= (fhi != flo);
+            uint32_t ow = 0;
+            if (W > 32) {
+                int r0 = wr + 1; if (r0 >= NW) r0 -= NW;
+                int r1 = r0 + 1; if (r1 >= NW) r1 -= NW;
+                const uint32_t w0_ = ring[r0 * rstride], w1_ = ring[r1 * rstride];
+                ow = r ? ((w0_ >> r) | (w1_ << (32 - r))) : w0_;
+            }
+            const bool full = (tb + 31 < it.we) && (tb >= it.own_lo) && (tb + 31 < it.own_hi);
+            if (full) cover_block<true>(P, it, S, ind, active, fhi, ow, tb);
+            else cover_block<false>(P, it, S, ind, active, fhi, ow, tb);
+            if (W > 32) {
+                ring[wr * rstride] = fhi;
+                if (++wr >= NW) wr = 0;
+            }
+            __syncthreads();                                       // every warp is done with this buffer …
+            if (threadIdx.x == 0 && b + 2 < n_blk) issue(b + 2);  // … so the block after next may land in it
+        }
+        if (S.run_start >= 0) emit_run(P, it, ind, active, S.run_start, it.own_hi - 1);
+        if (S.ambig && active) {
+            const unsigned p = atomicAdd(P.out_count + 1, 1u);
+            if (p < P.amb_cap) {
+                RohRec rr;
+                rr.ind = ind; rr.a = 0; rr.b = 0; rr.tag = it.seg;
+                P.amb[p] = rr;
+            }
+        }
+    }
+}
+
 cudaError_t launch_wlod_mma(const WlodParams& Q, const Item* items, int n_items, bool gl_mode, cudaStream_t st)
 {
     if (n_items == 0 || Q.base.n_lanes == 0) return cudaSuccess;
@@ -670,6 +893,19 @@ cudaError_t launch_wlod_mma(const WlodParams& Q, const Item* items, int n_items,
     long long grid = total;
     const long long cap = 148ll * 16 * 8;
     if (grid > cap) grid = cap;
+    // table mode and moderate windows: operands staged through shared memory (two buffers of 32 weight rows + the block's
+    // table entries per CTA; three CTAs per SM need <= 75 KB each)
+    if (!gl_mode && getenv("GARLIC_MMA_GLOBAL") == nullptr) {
+        const int ldw = inv_stride(Q.base.W);
+        const int wt_bytes = 32 * ldw * 8, tab_bytes = ((Q.base.W + 40 + 3) & ~3) * 32;
+        const size_t smem_s = 2 * (size_t)(wt_bytes + tab_bytes) + (size_t)NW * 128 * sizeof(uint32_t) + 16;
+        if (smem_s <= 75 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(wlod_mma_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+            if (e != cudaSuccess) return e;
+            wlod_mma_smem_kernel<<<(unsigned)grid, 128, smem_s, st>>>(Q, items, n_items, n_groups, wt_bytes, tab_bytes);
+            return cudaGetLastError();
+        }
+    }
     // MINB = 4 caps the kernel at 128 registers (four CTAs = sixteen warps per SM instead of twelve) at the price of a
     // few spilled values outside the quad loop; GARLIC_MMA_MINB=3 selects the uncapped build for A/B timing
     static const bool lb4 = []() { const char* e = getenv("GARLIC_MMA_MINB"); return !(e && atoi(e) == 3); }();

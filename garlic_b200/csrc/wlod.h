@@ -10,7 +10,8 @@ namespace garlic {
 // elements either side of the band and must find 0 there (no predicates on its operand loads).
 constexpr int kInvFront = 8, kInvBack = 24;
 constexpr int kWlodMmaMinW = 10;   // the tensor-core pass's tile schedule needs (W+6)/4 >= 4
-inline int inv_stride(int W) { return W + kInvFront + kInvBack; }
+// (even: a block of 32 weight rows then starts and ends on 16 bytes, what a bulk copy into shared memory needs)
+GHD int inv_stride(int W) { return W + kInvFront + kInvBack + (W & 1); }
 
 struct WlodParams {
     WalkParams base;
