@@ -331,6 +331,51 @@ def test_cutoff_on_a_window_value_is_resolved_exactly():
     hp.close()
 
 
+def test_tiny_panel_frequencies_widen_the_ambiguity_tolerance():
+    """--freq-file frequencies around 1e-25 give |lod| > 20: the bound on the table's entries behind the ambiguity
+    tolerance follows the smallest frequency supplied (capi.cu:lod_bound), so the chunked / pruned pass with a cutoff ON a
+    window value still marks the pair ambiguous and equals whole-segment exact chains; windows match a direct fp64 sum
+    over the device's own table."""
+    from garlic_b200.api import GarlicGPU
+    names, offs, pos, cens = synth.make_positions_genomewide(9, 30000)
+    codes = synth.make_codes(9, 96, 30000)
+    cen = np.array([cens["chr" + n] for n in names], np.int32)
+    g = GarlicGPU(0)
+    g.set_shape(96, 30000, offs, pos)
+    g.put_packed(synth.pack_codes(codes))
+    g.count_packed()
+    freq, keep, L = g.filter()
+    f = freq.copy()
+    poly = np.flatnonzero((f > 0) & (f < 1))
+    f[poly[::53]] = 1e-25
+    f[poly[7::211]] = 1.0 - 1e-13
+    g.filter(freq_override=f)
+    g.set_tables(0.001, 200000, cen)
+    lut = g.get_lut()
+    assert np.abs(lut).max() > 20.0
+    W = 50
+    win = g.windows(W, 1, exact=True)
+    # a window that holds a tiny-frequency SNP, of an individual homozygous there: its value is the cutoff
+    big = np.argwhere((win != orc.MISSING) & (win > 20.0))
+    assert len(big) > 0
+    i, t = big[len(big) // 2]
+    cutoff = float(win[i, t])
+    fast = g.call_roh(W, cutoff, 0.25)
+    st = g.last_stats()
+    assert st["ambiguous_pairs"] >= 1
+    exact = g.call_roh(W, cutoff, 0.25, exact=True)
+    assert len(exact) > 0 and np.array_equal(fast, exact)
+    # the device's windows against a direct sum over its own table
+    kept = g.get_kept_index()
+    ck = codes[:, kept]
+    val = np.take_along_axis(np.broadcast_to(lut[None], (96, L, 4)), ck[:, :, None].astype(np.int64), 2)[:, :, 0]
+    direct = np.lib.stride_tricks.sliding_window_view(val, W, axis=1).sum(-1)
+    ok = win[:, :direct.shape[1]] != orc.MISSING
+    d = np.abs(win[:, :direct.shape[1]][ok] - direct[ok]) / np.maximum(np.abs(direct[ok]), 1e-3)
+    assert d.max() <= 1e-9
+    g.close()
+
+
 def test_empty_and_ragged_inputs():
     # a chromosome shorter than the window, a single individual, nothing above the cutoff
     # (one individual: only heterozygous / half-missing sites survive the 0<freq<1 filter)
