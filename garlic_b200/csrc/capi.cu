@@ -1261,7 +1261,7 @@ static int ensure_bound_tables(garlic_gpu* h, int W)
     if (dev_alloc(h, &h->d_bhw, (size_t)n_hw)) return 1;
     if (dev_alloc(h, &h->d_bflag, (size_t)4)) return 1;
     CK(cudaMemsetAsync(h->d_bflag, 0, 4 * sizeof(int), h->stream));
-    LAUNCH(launch_bound_tables(h->d_lut, n_hw, h->L, W, h->d_bhw, h->d_bflag, h->stream));
+    LAUNCH(launch_bound_tables(h->d_lut, h->L + kPad, n_hw, h->L, W, h->d_bhw, h->d_bflag, h->stream));
     h->bound_tables_W = W;
     return 0;
 }

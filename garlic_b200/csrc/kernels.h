@@ -46,7 +46,8 @@ struct SqueezeParams {
     int64_t pmax_stride;
     int n_pieces, pieces_per_task, n_col_tasks;
 };
-cudaError_t launch_bound_tables(const double* lut, long long n_hw, long long L, int W, uint4* hw, int* invalid, cudaStream_t st);
+// n_tab: entries the table holds (L + padding); entries beyond read as zero
+cudaError_t launch_bound_tables(const double* lut, long long n_tab, long long n_hw, long long L, int W, uint4* hw, int* invalid, cudaStream_t st);
 cudaError_t launch_plan(const int* src, const int* n_kept, long long n_q, uint4* head, uint4* segs, uint16_t* fast,
                         int2* piece_rng, cudaStream_t st);
 // c2 > 0: with the bound for that window size class; squeeze = false: bound only, over compacted rows

@@ -54,25 +54,56 @@ __device__ __forceinline__ void cp_async_wait_dyn(int pending)     // at most `p
 // ------------------------------------------------------------------------------------------
 // tables of the bound for window size W (bound.cuh): one thread per half-word / block
 // ------------------------------------------------------------------------------------------
-__global__ void bound_tables_kernel(const double* __restrict__ lut, long long n_hw, long long L, int W,
-                                    uint4* __restrict__ hw, int* __restrict__ invalid)
+// A CTA makes the entries of kBtHw consecutive half-words.  The table rows they look at — 16 SNPs each for the level
+// planes, and the W + 15 SNPs behind block q - C2 for its Bmax — overlap almost completely between neighbours, so the
+// CTA's whole range of the per-SNP table is staged once with coalesced 16-byte loads and the (unchanged, strictly
+// ordered) arithmetic of bound.cuh then runs out of shared memory: one thread per half-word reading 512 contiguous
+// bytes of global memory per step had made this little kernel cost as much as the thinned pass 1.
+constexpr int kBtHw = 128;
+__global__ void __launch_bounds__(kBtHw)
+bound_tables_kernel(const double* __restrict__ lut, long long n_hw, long long L, int W, uint4* __restrict__ hw, int* __restrict__ invalid,
+                    int stage_snps, long long n_tab)
 {
+    extern __shared__ __align__(16) double bt_smem[];
     const int c2 = bound_c2(W);
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n_hw; k += (long long)gridDim.x * blockDim.x) {
-        int bad = 0;
-        uint4 e = bound_hw_entry(lut, k, L, &bad);
-        e.w = k >= c2 ? (uint32_t)bound_block_max(lut, k - c2, W) : 0u;   // what the step at half-word k evaluates
-        hw[k] = e;
-        if (bad) atomicOr(invalid, 1);
+    for (long long k0 = (long long)blockIdx.x * kBtHw; k0 < n_hw; k0 += (long long)gridDim.x * kBtHw) {
+        // SNPs [s_lo, s_lo + stage_snps): from block k0 - c2 (never below 0) to the end of half-word k0 + kBtHw - 1
+        const long long kb = k0 >= c2 ? k0 - c2 : 0;
+        const long long s_lo = kb * 16;
+        __syncthreads();
+        {
+            const double2* src = reinterpret_cast<const double2*>(lut + s_lo * 4);
+            double2* dst = reinterpret_cast<double2*>(bt_smem);
+            const long long lim = (n_tab - s_lo) * 2;         // table entries that exist (the rest reads as zero)
+            for (int i = threadIdx.x; i < stage_snps * 2; i += kBtHw) dst[i] = i < lim ? src[i] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        const long long k = k0 + threadIdx.x;
+        if (k < n_hw) {
+            const double* tab = bt_smem - s_lo * 4;           // tab + s * 4 is SNP s of the staged range
+            int bad = 0;
+            uint4 e = bound_hw_entry(tab, k, L, &bad);
+            e.w = k >= c2 ? (uint32_t)bound_block_max(tab, k - c2, W) : 0u;   // what the step at half-word k evaluates
+            hw[k] = e;
+            if (bad) atomicOr(invalid, 1);
+        }
     }
 }
 
-cudaError_t launch_bound_tables(const double* lut, long long n_hw, long long L, int W, uint4* hw, int* invalid, cudaStream_t st)
+cudaError_t launch_bound_tables(const double* lut, long long n_tab, long long n_hw, long long L, int W, uint4* hw, int* invalid, cudaStream_t st)
 {
     if (!n_hw) return cudaSuccess;
-    long long blocks = (n_hw + 127) / 128;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    bound_tables_kernel<<<(unsigned)blocks, 128, 0, st>>>(lut, n_hw, L, W, hw, invalid);
+    // staged SNPs: the kBtHw half-words themselves plus C2 blocks in front, and behind block k - C2 its last window
+    // (start + 15 + W); whichever reaches further
+    const int c2 = bound_c2(W);
+    const int stage_snps = std::max(16 * (kBtHw + c2), 16 * (kBtHw - 1) + 16 + W + 16);
+    const size_t smem = (size_t)stage_snps * 32;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(bound_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long blocks = (n_hw + kBtHw - 1) / kBtHw;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    bound_tables_kernel<<<(unsigned)blocks, kBtHw, smem, st>>>(lut, n_hw, L, W, hw, invalid, stage_snps, n_tab);
     return cudaGetLastError();
 }
 
