@@ -140,6 +140,8 @@ struct garlic_gpu {
     double *d_kde = nullptr, *d_kde_in = nullptr;   // scratch of the device KDE; uploaded host values
     cudaEvent_t ev2 = nullptr;
     cudaStream_t copy_stream = nullptr;   // device-to-host copies that overlap the kernels behind them (filter)
+    cudaStream_t aux_stream = nullptr;    // thinned pass 1 beside the compaction (windows_common)
+    cudaEvent_t ev_aux_in = nullptr, ev_aux_out = nullptr;
     cudaEvent_t ev_copy = nullptr;
     // GARLIC_TIMELINE=1: host clock and stream position (CUDA events) at marked points of the entry points, printed at destroy
     bool tl_on = false;
@@ -467,6 +469,9 @@ int garlic_gpu_create(int device, garlic_gpu_t** out)
     cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_tables, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_aux_in, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_aux_out, cudaEventDisableTiming);
     h->prune = getenv("GARLIC_NO_PRUNE") == nullptr;
     h->tl_on = getenv("GARLIC_TIMELINE") != nullptr;
     cudaEventCreate(&h->ev_sq0);
@@ -502,6 +507,9 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     if (h->ev_tables) cudaEventDestroy(h->ev_tables);
     if (h->brk_pin) cudaFreeHost(h->brk_pin);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
+    if (h->ev_aux_in) cudaEventDestroy(h->ev_aux_in);
+    if (h->ev_aux_out) cudaEventDestroy(h->ev_aux_out);
     dev_free(h->d_plan_head); dev_free(h->d_plan_seg); dev_free(h->d_plan_rng); dev_free(h->d_bhw); dev_free(h->d_plan_fast); dev_free(h->d_bflag);
     dev_free(h->d_pmax); dev_free(h->d_cand_list); dev_free(h->d_cand_cnt); dev_free(h->d_units);
     if (h->ev_sq0) cudaEventDestroy(h->ev_sq0);
@@ -1208,13 +1216,14 @@ static int upload_items(garlic_gpu* h, const std::vector<Item>& items)
     return 0;
 }
 
-static int upload_indlist(garlic_gpu* h, const int32_t* list, int n)
+static int upload_indlist(garlic_gpu* h, const int32_t* list, int n, cudaStream_t st = nullptr)
 {
+    if (!st) st = h->stream;
     if ((size_t)n > h->indlist_cap) {
         if (dev_alloc(h, &h->d_indlist, (size_t)n + 1024)) return 1;
         h->indlist_cap = (size_t)n + 1024;
     }
-    CK(cudaMemcpyAsync(h->d_indlist, list, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_indlist, list, n * sizeof(int), cudaMemcpyHostToDevice, st));
     return 0;
 }
 
@@ -1346,6 +1355,29 @@ static int ensure_bound(garlic_gpu* h, int W)
     return 0;
 }
 
+// Thinned pass 1 in table mode (what the KDE needs) does not depend on the compaction: it reads the uncompacted matrix
+// through the gather list, on a second stream, while the fused compaction + bound pass runs on the main one — the host
+// gets its windows 0.3 ms earlier and has pass 2 enqueued before the compaction is over.
+static bool side_pass1(const garlic_gpu* h, int weighted, int exact, int step)
+{
+    static const bool off = getenv("GARLIC_NO_SIDE_PASS1") != nullptr;
+    return !off && !weighted && !exact && step >= 8 && !h->have_gl && h->have_geno0 && h->aux_stream != nullptr;
+}
+// the side stream starts behind what the main stream holds now (tables, gather list), not behind what follows
+static int begin_side(garlic_gpu* h)
+{
+    CK(cudaEventRecord(h->ev_aux_in, h->stream));
+    CK(cudaStreamWaitEvent(h->aux_stream, h->ev_aux_in, 0));
+    return 0;
+}
+// … and the main stream's later work (the KDE on the device, another pass 1) sees the side stream's results
+static int end_side(garlic_gpu* h)
+{
+    CK(cudaEventRecord(h->ev_aux_out, h->aux_stream));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_aux_out, 0));
+    return 0;
+}
+
 extern "C" {
 
 int64_t garlic_gpu_window_slots(garlic_gpu_t* h, int step)
@@ -1384,20 +1416,25 @@ int garlic_gpu_windows_gather(garlic_gpu_t* h, int winsize, int step, int weight
     void* dptr = nullptr;
     if (n > 0 && windows_common(h, winsize, step, weighted, individuals, n, exact, nullptr, &dptr)) return 1;
     CK(cudaSetDevice(h->device));
+    // the exchange follows the windows on their stream (the side stream in table mode: not behind the compaction)
+    const bool side = h->filtered && h->tables && side_pass1(h, weighted, exact, step);
+    cudaStream_t ws = side ? h->aux_stream : h->stream;
+    if (side && n == 0 && begin_side(h)) return 1;
     const size_t blk = (size_t)rows_per_rank * slots;
     if (dev_alloc(h, &h->d_gather, blk * (h->comm_world + 1))) return 1;
     double* send = h->d_gather + blk * h->comm_world;
-    LAUNCH(launch_fill_f64(send, blk, kMissing, h->stream));
-    if (n > 0) CK(cudaMemcpyAsync(send, dptr, (size_t)n * slots * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    if (h->comm) NCK(ncclAllGather(send, h->d_gather, blk, ncclDouble, h->comm, h->stream));
-    else CK(cudaMemcpyAsync(h->d_gather, send, blk * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    LAUNCH(launch_fill_f64(send, blk, kMissing, ws));
+    if (n > 0) CK(cudaMemcpyAsync(send, dptr, (size_t)n * slots * sizeof(double), cudaMemcpyDeviceToDevice, ws));
+    if (h->comm) NCK(ncclAllGather(send, h->d_gather, blk, ncclDouble, h->comm, ws));
+    else CK(cudaMemcpyAsync(h->d_gather, send, blk * sizeof(double), cudaMemcpyDeviceToDevice, ws));
     h->kde_src = h->d_gather; h->kde_src_n = (int64_t)(blk * h->comm_world);
-    if (!out) return 0;                     // a rank that only contributes: nothing travels to its host, nobody waits
+    if (!out) return side ? end_side(h) : 0;   // a rank that only contributes: nothing travels to its host, nobody waits
     const size_t bytes = blk * h->comm_world * sizeof(double);
     const bool direct = is_pinned(out);
     const bool staged = !direct && bytes <= ((size_t)64 << 20) && !pin_alloc(h, bytes);
-    CK(cudaMemcpyAsync(direct ? (void*)out : (staged ? (void*)h->pin : (void*)out), h->d_gather, bytes, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(direct ? (void*)out : (staged ? (void*)h->pin : (void*)out), h->d_gather, bytes, cudaMemcpyDeviceToHost, ws));
+    CK(cudaStreamSynchronize(ws));
+    if (side && end_side(h)) return 1;
     if (finish_outputs(h)) return 1;
     if (staged) memcpy(out, h->pin, bytes);
     return 0;
@@ -1412,13 +1449,16 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
     if (step < 1) FAIL("windows: step must be >= 1");
     tl_mark(h, "windows:in");
     if (weighted && ensure_weighted(h, winsize)) return 1;
+    const bool side = side_pass1(h, weighted, exact, step);
+    if (side && begin_side(h)) return 1;
+    cudaStream_t ws = side ? h->aux_stream : h->stream;            // the stream this call's windows are made on
     if (ensure_geno(h, weighted ? 0 : winsize)) return 1;
     tl_mark(h, "windows:squeeze-enqueued");
     const int W = winsize;
     const int n_lanes = individuals ? n : h->n_ind;
     if (individuals) {
         for (int i = 0; i < n; ++i) if (individuals[i] < 0 || individuals[i] >= h->n_ind) FAIL("windows: individual index out of range");
-        if (upload_indlist(h, individuals, n)) return 1;
+        if (upload_indlist(h, individuals, n, ws)) return 1;
     }
     std::vector<Segment> segs;
     std::vector<Item> items;
@@ -1428,7 +1468,7 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
     const int64_t slots = garlic_gpu_window_slots(h, step);
     if (dev_alloc(h, &h->d_dump, (size_t)n_lanes * slots)) return 1;
     double* d_dump = h->d_dump;
-    LAUNCH(launch_fill_f64(d_dump, (size_t)n_lanes * slots, kMissing, h->stream));
+    LAUNCH(launch_fill_f64(d_dump, (size_t)n_lanes * slots, kMissing, ws));
     // thinned pass 1 (unweighted, table mode, tolerance 1e-9): sum only the windows the KDE will look at
     const bool direct = !weighted && !exact && step >= 8;
     int rc = 0;
@@ -1444,11 +1484,12 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
         if (dev_alloc(h, &h->d_thin, bytes / 4 + 8)) return 1;
         int3* d_segs = reinterpret_cast<int3*>(h->d_thin);
         int2* d_meta = reinterpret_cast<int2*>(h->d_thin + 3 * segs.size() + (segs.size() & 1));
-        if (!segs.empty()) CK(cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(int3), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
-        LAUNCH(launch_thin_windows(h->d_geno, h->row_words, h->d_lut, individuals ? h->d_indlist : nullptr, n_lanes, d_segs,
+        if (!segs.empty()) CK(cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(int3), cudaMemcpyHostToDevice, ws));
+        CK(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * sizeof(int2), cudaMemcpyHostToDevice, ws));
+        LAUNCH(launch_thin_windows(side ? h->d_geno0 : h->d_geno, side ? h->row_words0 : h->row_words, h->d_lut,
+                                   individuals ? h->d_indlist : nullptr, n_lanes, d_segs,
                                    (int)segs.size(), d_meta, h->n_chr, slots, step, W, d_dump, slots,
-                                   h->have_gl ? h->d_gl : nullptr, h->gl_stride, h->stream));
+                                   h->have_gl ? h->d_gl : nullptr, h->gl_stride, side ? h->d_src : nullptr, ws));
         // the GPU is busy (compaction + bound, thinned windows): the host gets pass 2's items ready meanwhile
         if (h->bound_W == W && prepare_p2_items(h, W)) return 1;
     } else {
@@ -1470,16 +1511,17 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
     if (!rc && finish_outputs(h)) rc = 1;
     if (!rc && out_dev) {
         *out_dev = d_dump;
-        cudaError_t e = cudaStreamSynchronize(h->stream);
+        cudaError_t e = cudaStreamSynchronize(ws);
         if (e != cudaSuccess) { h->err = std::string("windows: ") + cudaGetErrorString(e); rc = 1; }
     } else if (!rc) {
         const size_t bytes = (size_t)n_lanes * slots * sizeof(double);
         const bool staged = !is_pinned(out) && bytes <= ((size_t)64 << 20) && !pin_alloc(h, bytes);
-        cudaError_t e = cudaMemcpyAsync(staged ? (void*)h->pin : (void*)out, d_dump, bytes, cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        cudaError_t e = cudaMemcpyAsync(staged ? (void*)h->pin : (void*)out, d_dump, bytes, cudaMemcpyDeviceToHost, ws);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ws);
         if (e != cudaSuccess) { h->err = std::string("windows: ") + cudaGetErrorString(e); rc = 1; }
         else if (staged) memcpy(out, h->pin, bytes);
     }
+    if (!rc && side && end_side(h)) rc = 1;
     tl_mark(h, "windows:out");
     return rc;
 }

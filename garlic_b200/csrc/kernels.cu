@@ -656,8 +656,10 @@ __global__ void thin_windows_kernel(const uint64_t* __restrict__ geno, int64_t r
                                     const int* __restrict__ ind_list, const int3* __restrict__ segs, int n_segs,
                                     const int2* __restrict__ meta, int n_chr, long long n_slots, int step, int W,
                                     double* __restrict__ dump, int64_t dump_stride, const double* __restrict__ gl,
-                                    int64_t gl_stride)
+                                    int64_t gl_stride, const int* __restrict__ src)
 {
+    // src != nullptr: geno is the UNCOMPACTED matrix and kept SNP s sits at column src[s] (pass 1 then does not have to wait
+    // for the compaction: it runs beside it on a second stream)
     const int k = blockIdx.y;
     const int ind = ind_list ? ind_list[k] : k;
     const uint64_t* row = geno + (int64_t)ind * row_words;
@@ -681,7 +683,8 @@ __global__ void thin_windows_kernel(const uint64_t* __restrict__ geno, int64_t r
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int s = t + i + k;
-                    const int g = (int)(row[s >> 5] >> (2 * (s & 31))) & 3;
+                    const int c = src ? src[s] : s;
+                    const int g = (int)(row[c >> 5] >> (2 * (c & 31))) & 3;
                     v[k] = lut[(int64_t)s * 4 + g];
                 }
 #pragma unroll
@@ -689,7 +692,8 @@ __global__ void thin_windows_kernel(const uint64_t* __restrict__ geno, int64_t r
             }
             for (; i < W; ++i) {
                 const int s = t + i;
-                const int g = (int)(row[s >> 5] >> (2 * (s & 31))) & 3;
+                const int c = src ? src[s] : s;
+                const int g = (int)(row[c >> 5] >> (2 * (c & 31))) & 3;
                 win += lut[(int64_t)s * 4 + g];
             }
         }
@@ -699,14 +703,14 @@ __global__ void thin_windows_kernel(const uint64_t* __restrict__ geno, int64_t r
 
 cudaError_t launch_thin_windows(const uint64_t* geno, int64_t row_words, const double* lut, const int* ind_list, int n_lanes,
                                 const int3* segs, int n_segs, const int2* meta, int n_chr, long long n_slots, int step, int W,
-                                double* dump, int64_t dump_stride, const double* gl, int64_t gl_stride, cudaStream_t st)
+                                double* dump, int64_t dump_stride, const double* gl, int64_t gl_stride, const int* src, cudaStream_t st)
 {
     if (!n_lanes || !n_slots || !n_segs) return cudaSuccess;
     long long bx = (n_slots + 127) / 128;
     if (bx > 4096) bx = 4096;
     dim3 grid((unsigned)bx, (unsigned)n_lanes);
     thin_windows_kernel<<<grid, 128, 0, st>>>(geno, row_words, lut, ind_list, segs, n_segs, meta, n_chr, n_slots, step, W, dump,
-                                               dump_stride, gl, gl_stride);
+                                               dump_stride, gl, gl_stride, src);
     return cudaGetLastError();
 }
 

@@ -57,7 +57,7 @@ cudaError_t launch_select(const Item* items, int n_items, const uint32_t* pmax, 
                           unsigned unit_cap, int lanes_per_unit, int c2, cudaStream_t st);
 cudaError_t launch_thin_windows(const uint64_t* geno, int64_t row_words, const double* lut, const int* ind_list, int n_lanes,
                                 const int3* segs, int n_segs, const int2* meta, int n_chr, long long n_slots, int step, int W,
-                                double* dump, int64_t dump_stride, const double* gl, int64_t gl_stride, cudaStream_t st);
+                                double* dump, int64_t dump_stride, const double* gl, int64_t gl_stride, const int* src, cudaStream_t st);
 cudaError_t launch_fill_f64(double* p, size_t n, double v, cudaStream_t st);
 cudaError_t launch_bucket_by_individual(RohRec* in, const unsigned* count, unsigned cap, unsigned* hist, int n_ind,
                                         RohRec* out, int thr, unsigned* kept, unsigned* total, cudaStream_t st);

@@ -419,7 +419,7 @@ cudaError_t launch_squeeze_bound(SqueezeParams P, bool squeeze, int c2, cudaStre
 
 // ------------------------------------------------------------------------------------------
 // candidate selection: one CTA per item thresholds the piece maxima of every individual (bound.cuh:
-// bound_item_candidate), writes the item's dense candidate list in individual order and appends one work unit per
+// bound_item_candidate), writes the item's dense candidate list (in no particular order) and appends one work unit per
 // `lanes_per_unit` candidates to the walker's queue.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -428,31 +428,32 @@ select_kernel(const Item* __restrict__ items, int n_items, const uint32_t* __res
               unsigned* __restrict__ cand_cnt, int2* __restrict__ units, unsigned* __restrict__ n_units, unsigned unit_cap,
               int lanes_per_unit, int c2)
 {
-    __shared__ int s_w[8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int s_n;
+    const int lane = threadIdx.x & 31;
     if (*invalid) cut_store = -32768;                      // the table breaks the bound's assumptions: keep everybody
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const Item it = items[item];
-        // a thread takes individuals t, t + 256, …: all of its loads are independent, one block scan per item; the
-        // list comes out ordered by (thread, individual) — any order will do, the runs are sorted afterwards
-        int mine = 0;
-        for (int ind = threadIdx.x; ind < n_ind; ind += 256) mine += bound_item_candidate(pmax, stride, ind, it, cut_store, c2) ? 1 : 0;
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        __syncthreads();                                   // s_w of the previous item has been read
-        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();                                   // s_n of the previous item has been read
+        if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { const int v = s_w[w]; total += v; if (w < warp) before += v; }
-        int pos = before + incl - mine;
-        if (mine) {
-            int* list = cand_list + (int64_t)item * cand_stride;
-            for (int ind = threadIdx.x; ind < n_ind; ind += 256)
-                if (bound_item_candidate(pmax, stride, ind, it, cut_store, c2)) list[pos++] = ind;
+        // one pass: a thread takes individuals t, t + 256, … (independent loads), a warp appends its candidates with one
+        // shared atomic per round; the list comes out in no particular order — the runs are sorted afterwards
+        int* list = cand_list + (int64_t)item * cand_stride;
+        const int rounds = (n_ind + 255) >> 8;
+        for (int r = 0; r < rounds; ++r) {
+            const int ind = r * 256 + threadIdx.x;
+            const bool c = ind < n_ind && bound_item_candidate(pmax, stride, ind, it, cut_store, c2);
+            const unsigned m = __ballot_sync(0xffffffffu, c);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_n, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (c) list[base + __popc(m & ((1u << lane) - 1u))] = ind;
+            }
         }
+        __syncthreads();
         if (threadIdx.x == 0) {
+            const int total = s_n;
             cand_cnt[item] = (unsigned)total;
             const int nu = (total + lanes_per_unit - 1) / lanes_per_unit;
             if (nu) {
