@@ -1078,9 +1078,11 @@ __device__ __forceinline__ void vc_add8(VCounter& v, const uint64_t x[8])
 }
 
 // Turn the 8 planes (64 bit positions = 32 SNPs x {even, odd}) into counts and add them to this thread's slots of
-// the CTA's shared counters, laid out [kind][SNP within word (32)][column (256)] so that a warp's accesses are
-// consecutive and every slot has exactly one owner (plain adds, no atomics).
+// the CTA's shared counters, laid out [kind][SNP within word (32)][column (256, stride kCntCol = 257)] so that a warp's
+// accesses are consecutive and every slot has exactly one owner (plain adds, no atomics); the odd stride makes the final
+// read-out (consecutive SNPs = consecutive rows of this layout) conflict-free as well.
 // 4 bit positions at a time: nibble n of plane l → bytes (bit j → byte j) by (n * 0x00204081) & 0x01010101.
+constexpr int kCntCol = 257;
 __device__ __noinline__ void vc_flush(VCounter& v, int* __restrict__ even_cnt, int* __restrict__ odd_cnt)
 {
 #pragma unroll
@@ -1091,11 +1093,11 @@ __device__ __noinline__ void vc_flush(VCounter& v, int* __restrict__ even_cnt, i
             const uint32_t nib = (uint32_t)(v.p[l] >> (4 * g)) & 0xfu;
             acc += ((nib * 0x00204081u) & 0x01010101u) << l;
         }
-        even_cnt[(2 * g) * 256] += acc & 0xff;
-        even_cnt[(2 * g + 1) * 256] += (acc >> 16) & 0xff;
+        even_cnt[(2 * g) * kCntCol] += acc & 0xff;
+        even_cnt[(2 * g + 1) * kCntCol] += (acc >> 16) & 0xff;
         if (odd_cnt) {
-            odd_cnt[(2 * g) * 256] += (acc >> 8) & 0xff;
-            odd_cnt[(2 * g + 1) * 256] += acc >> 24;
+            odd_cnt[(2 * g) * kCntCol] += (acc >> 8) & 0xff;
+            odd_cnt[(2 * g + 1) * kCntCol] += acc >> 24;
         }
     }
 #pragma unroll
@@ -1108,8 +1110,8 @@ __global__ void __launch_bounds__(256, 2)
 count_packed_kernel(const uint64_t* __restrict__ geno, int64_t row_words, int n_ind, long long L0,
                     int rows_per_block, int* __restrict__ counts)
 {
-    extern __shared__ int s_cnt[];             // [3][32][256]: n1, n2, missing
-    for (int i = threadIdx.x; i < 3 * 32 * 256; i += 256) s_cnt[i] = 0;
+    extern __shared__ int s_cnt[];             // [3][32][kCntCol]: n1, n2, missing
+    for (int i = threadIdx.x; i < 3 * 32 * kCntCol; i += 256) s_cnt[i] = 0;
     __syncthreads();
     const long long word = (long long)blockIdx.x * 256 + threadIdx.x;
     const long long n_words = (L0 + 31) >> 5;
@@ -1146,14 +1148,14 @@ count_packed_kernel(const uint64_t* __restrict__ geno, int64_t row_words, int n_
             }
             groups += 2;
             if (groups >= 30) {                               // 240 rows: the planes hold at most 255
-                vc_flush(va, mine, mine + 32 * 256);
-                vc_flush(vm, mine + 2 * 32 * 256, nullptr);
+                vc_flush(va, mine, mine + 32 * kCntCol);
+                vc_flush(vm, mine + 2 * 32 * kCntCol, nullptr);
                 groups = 0;
             }
         }
         if (groups) {
-            vc_flush(va, mine, mine + 32 * 256);
-            vc_flush(vm, mine + 2 * 32 * 256, nullptr);
+            vc_flush(va, mine, mine + 32 * kCntCol);
+            vc_flush(vm, mine + 2 * 32 * kCntCol, nullptr);
         }
     }
     __syncthreads();
@@ -1161,9 +1163,9 @@ count_packed_kernel(const uint64_t* __restrict__ geno, int64_t row_words, int n_
     for (int i = threadIdx.x; i < 32 * 256; i += 256) {       // i = SNP within the CTA's 8192: consecutive → coalesced
         const long long s = (long long)blockIdx.x * 8192 + i;
         if (s >= L0) continue;
-        const int slot = (i & 31) * 256 + (i >> 5);
-        const int nm = s_cnt[2 * 32 * 256 + slot];
-        const int n1 = s_cnt[slot] - nm, n2 = s_cnt[32 * 256 + slot] - nm;
+        const int slot = (i & 31) * kCntCol + (i >> 5);
+        const int nm = s_cnt[2 * 32 * kCntCol + slot];
+        const int n1 = s_cnt[slot] - nm, n2 = s_cnt[32 * kCntCol + slot] - nm;
         const int nonmiss = rows - nm;
         atomicAdd(&counts[0 * L0 + s], n1 + 2 * n2);
         atomicAdd(&counts[1 * L0 + s], 2 * nonmiss);
@@ -1184,7 +1186,7 @@ cudaError_t launch_count_packed(const uint64_t* geno, int64_t row_words, int n_i
     rpb = ((rpb + 15) / 16) * 16;
     gy = (n_ind + rpb - 1) / rpb;
     dim3 grid(gx, gy);
-    const size_t smem = 3 * 32 * 256 * sizeof(int);           // 96 KB
+    const size_t smem = 3 * 32 * kCntCol * sizeof(int);       // 96 KB
     cudaError_t e = cudaFuncSetAttribute(count_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     count_packed_kernel<<<grid, 256, smem, st>>>(geno, row_words, n_ind, L0, rpb, counts);
