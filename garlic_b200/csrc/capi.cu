@@ -95,6 +95,7 @@ struct garlic_gpu {
     int64_t stats_items = 0;
     int* d_scan = nullptr;         // block counts of the keep scan, total, kept chromosome offsets
     int* d_breaks = nullptr;       // bad-pair list
+    uint32_t* d_badbits = nullptr; // bit i: no window may hold SNPs i-1 and i (gap / centromere pair, chromosome start)
     int* d_thin = nullptr;         // segment + chromosome tables of the thinned pass 1
     // K3 is deferred to the first consumer of the compacted rows so that it can run fused with the pruning bound
     // (squeeze.cu): filter() only builds the plan
@@ -498,7 +499,7 @@ void garlic_gpu_destroy(garlic_gpu_t* h)
     dev_free(h->d_homf); dev_free(h->d_keep); dev_free(h->d_src); dev_free(h->d_pos0); dev_free(h->d_chr_of0);
     dev_free(h->d_pos); dev_free(h->d_chr_of); dev_free(h->d_chr_start); dev_free(h->d_chr_param);
     dev_free(h->d_out); dev_free(h->d_amb); dev_free(h->d_sorted); dev_free(h->d_items_p2); dev_free(h->d_cnt); dev_free(h->d_items); dev_free(h->d_indlist); dev_free(h->d_dump);
-    dev_free(h->d_scan); dev_free(h->d_breaks); dev_free(h->d_thin);
+    dev_free(h->d_scan); dev_free(h->d_breaks); dev_free(h->d_thin); dev_free(h->d_badbits);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1084,7 +1085,8 @@ int garlic_gpu_set_tables(garlic_gpu_t* h, double error, int max_gap, const int3
         unsigned* d_n = reinterpret_cast<unsigned*>(d_cen + 2 * h->n_chr);
         CK(cudaMemcpyAsync(d_cen, h->cen.data(), 2 * h->n_chr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemsetAsync(d_n, 0, sizeof(unsigned), h->stream));
-        LAUNCH(launch_bad_pairs(h->d_pos, h->d_chr_of, d_cen, max_gap, L, h->d_breaks, d_n, kBreakCap, h->stream));
+        if (dev_alloc(h, &h->d_badbits, (size_t)((L + 31) >> 5) + 4)) return 1;
+        LAUNCH(launch_bad_pairs(h->d_pos, h->d_chr_of, d_cen, max_gap, L, h->d_breaks, d_n, kBreakCap, h->d_badbits, h->stream));
         if (!h->brk_pin) CK(cudaMallocHost((void**)&h->brk_pin, 64 + kBreakFirst * sizeof(int)));
         CK(cudaMemcpyAsync(h->brk_pin, d_n, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(h->brk_pin + 64, h->d_breaks, kBreakFirst * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -1449,62 +1451,69 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
     if (step < 1) FAIL("windows: step must be >= 1");
     tl_mark(h, "windows:in");
     if (weighted && ensure_weighted(h, winsize)) return 1;
-    const bool side = side_pass1(h, weighted, exact, step);
-    if (side && begin_side(h)) return 1;
-    cudaStream_t ws = side ? h->aux_stream : h->stream;            // the stream this call's windows are made on
-    if (ensure_geno(h, weighted ? 0 : winsize)) return 1;
-    tl_mark(h, "windows:squeeze-enqueued");
     const int W = winsize;
     const int n_lanes = individuals ? n : h->n_ind;
-    if (individuals) {
+    if (individuals)
         for (int i = 0; i < n; ++i) if (individuals[i] < 0 || individuals[i] >= h->n_ind) FAIL("windows: individual index out of range");
-        if (upload_indlist(h, individuals, n, ws)) return 1;
-    }
-    std::vector<Segment> segs;
-    std::vector<Item> items;
-    if (ensure_stretches(h)) return 1;                 // (the compaction above is already on the stream)
-    tl_mark(h, "windows:stretches");
-    segments_from_stretches(h->stretches, W, segs);
     const int64_t slots = garlic_gpu_window_slots(h, step);
-    if (dev_alloc(h, &h->d_dump, (size_t)n_lanes * slots)) return 1;
-    double* d_dump = h->d_dump;
-    LAUNCH(launch_fill_f64(d_dump, (size_t)n_lanes * slots, kMissing, ws));
-    // thinned pass 1 (unweighted, table mode, tolerance 1e-9): sum only the windows the KDE will look at
+    // thinned pass 1 (unweighted, tolerance 1e-9): sum only the windows the KDE will look at
     const bool direct = !weighted && !exact && step >= 8;
+    const bool side = direct && side_pass1(h, weighted, exact, step);
+    cudaStream_t ws = h->stream;                                   // the stream this call's copies to the host run on
     int rc = 0;
+    double* d_dump = nullptr;
     if (direct) {
-        static_assert(sizeof(Segment) == sizeof(int3), "Segment is uploaded as int3");
+        // Everything this pass reads is on the device already — the table, the gather list, the bad-pair bit map of
+        // set_tables — so in table mode (`side`) it goes FIRST, over the uncompacted matrix: its windows travel to the host
+        // on the side stream while the main stream runs the fused compaction + bound pass, and the host has pass 2
+        // enqueued before that is over.  (GL mode: the likelihood matrix was compacted by filter(); same kernel.)
+        if (!side && ensure_geno(h, winsize)) return 1;
+        if (individuals && upload_indlist(h, individuals, n)) return 1;
+        if (dev_alloc(h, &h->d_dump, (size_t)n_lanes * slots)) return 1;
+        d_dump = h->d_dump;
+        LAUNCH(launch_fill_f64(d_dump, (size_t)n_lanes * slots, kMissing, h->stream));
         std::vector<int2> meta(h->n_chr);
         int base = 0;
         for (int c = 0; c < h->n_chr; ++c) {
             meta[c].x = (int)h->chr_off[c]; meta[c].y = base;
             base += (int)((h->chr_off[c + 1] - h->chr_off[c] + step - 1) / step);
         }
-        const size_t bytes = segs.size() * sizeof(int3) + meta.size() * sizeof(int2);
-        if (dev_alloc(h, &h->d_thin, bytes / 4 + 8)) return 1;
-        int3* d_segs = reinterpret_cast<int3*>(h->d_thin);
-        int2* d_meta = reinterpret_cast<int2*>(h->d_thin + 3 * segs.size() + (segs.size() & 1));
-        if (!segs.empty()) CK(cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(int3), cudaMemcpyHostToDevice, ws));
-        CK(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * sizeof(int2), cudaMemcpyHostToDevice, ws));
+        if (dev_alloc(h, &h->d_thin, (size_t)2 * h->n_chr + 8)) return 1;
+        int2* d_meta = reinterpret_cast<int2*>(h->d_thin);
+        CK(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
         LAUNCH(launch_thin_windows(side ? h->d_geno0 : h->d_geno, side ? h->row_words0 : h->row_words, h->d_lut,
-                                   individuals ? h->d_indlist : nullptr, n_lanes, d_segs,
-                                   (int)segs.size(), d_meta, h->n_chr, slots, step, W, d_dump, slots,
-                                   h->have_gl ? h->d_gl : nullptr, h->gl_stride, side ? h->d_src : nullptr, ws));
-        // the GPU is busy (compaction + bound, thinned windows): the host gets pass 2's items ready meanwhile
+                                   individuals ? h->d_indlist : nullptr, n_lanes, h->d_badbits, h->L, d_meta, h->n_chr, slots, step, W,
+                                   d_dump, slots, h->have_gl ? h->d_gl : nullptr, h->gl_stride, side ? h->d_src : nullptr, h->stream));
+        if (side) {
+            if (begin_side(h)) return 1;                           // the side stream takes over behind the windows …
+            ws = h->aux_stream;
+            if (ensure_geno(h, winsize)) return 1;                 // … and the main stream goes on with the compaction
+        }
+        tl_mark(h, "windows:squeeze-enqueued");
+        // the GPU is busy: the host gets pass 2's items ready meanwhile
         if (h->bound_W == W && prepare_p2_items(h, W)) return 1;
     } else {
-    int chunk = 0;
-    if (weighted) chunk = std::max(64, pick_chunk(h->L, W, n_lanes, 0) / 8);   // every wLOD window is a fresh sum
-    else if (!exact) chunk = pick_chunk(h->L, W, n_lanes, h->have_gl ? 0 : kTileSnpsMax);   // GL mode has no table tile
-    build_items(h->chr_off, W, segs, chunk, step, items);
-    if (upload_items(h, items)) return 1;
-    WalkParams P = base_params(h, W);
-    P.ind_list = individuals ? h->d_indlist : nullptr;
-    P.n_lanes = n_lanes;
-    P.cutoff = 0; P.thr = 1; P.tol = 0;
-    P.dump = d_dump; P.dump_stride = slots; P.dump_step = step;
-    CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
-    rc = launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, false, true, items_tile_snps(items, W));
+        if (ensure_geno(h, weighted ? 0 : winsize)) return 1;
+        if (individuals && upload_indlist(h, individuals, n)) return 1;
+        std::vector<Segment> segs;
+        std::vector<Item> items;
+        if (ensure_stretches(h)) return 1;                 // (the compaction above is already on the stream)
+        segments_from_stretches(h->stretches, W, segs);
+        if (dev_alloc(h, &h->d_dump, (size_t)n_lanes * slots)) return 1;
+        d_dump = h->d_dump;
+        LAUNCH(launch_fill_f64(d_dump, (size_t)n_lanes * slots, kMissing, h->stream));
+        int chunk = 0;
+        if (weighted) chunk = std::max(64, pick_chunk(h->L, W, n_lanes, 0) / 8);   // every wLOD window is a fresh sum
+        else if (!exact) chunk = pick_chunk(h->L, W, n_lanes, h->have_gl ? 0 : kTileSnpsMax);   // GL mode has no table tile
+        build_items(h->chr_off, W, segs, chunk, step, items);
+        if (upload_items(h, items)) return 1;
+        WalkParams P = base_params(h, W);
+        P.ind_list = individuals ? h->d_indlist : nullptr;
+        P.n_lanes = n_lanes;
+        P.cutoff = 0; P.thr = 1; P.tol = 0;
+        P.dump = d_dump; P.dump_stride = slots; P.dump_step = step;
+        CK(cudaMemsetAsync(h->d_cnt, 0, 4 * sizeof(unsigned), h->stream));
+        rc = launch_any_walk(h, P, h->d_items, (int)items.size(), weighted, false, true, items_tile_snps(items, W));
     }
     if (!rc) { h->kde_src = d_dump; h->kde_src_n = (int64_t)n_lanes * slots; }
     tl_mark(h, "windows:enqueued");
@@ -1521,7 +1530,6 @@ static int windows_common(garlic_gpu_t* h, int winsize, int step, int weighted, 
         if (e != cudaSuccess) { h->err = std::string("windows: ") + cudaGetErrorString(e); rc = 1; }
         else if (staged) memcpy(out, h->pin, bytes);
     }
-    if (!rc && side && end_side(h)) rc = 1;
     tl_mark(h, "windows:out");
     return rc;
 }

@@ -653,13 +653,13 @@ cudaError_t launch_walk(const WalkParams& P, const Item* items, int n_items, boo
 // Valid windows are those inside a segment [ws, we); the others keep the MISSING the buffer was filled with.
 // ------------------------------------------------------------------------------------------
 __global__ void thin_windows_kernel(const uint64_t* __restrict__ geno, int64_t row_words, const double* __restrict__ lut,
-                                    const int* __restrict__ ind_list, const int3* __restrict__ segs, int n_segs,
+                                    const int* __restrict__ ind_list, const uint32_t* __restrict__ bad_bits, long long L,
                                     const int2* __restrict__ meta, int n_chr, long long n_slots, int step, int W,
                                     double* __restrict__ dump, int64_t dump_stride, const double* __restrict__ gl,
                                     int64_t gl_stride, const int* __restrict__ src)
 {
     // src != nullptr: geno is the UNCOMPACTED matrix and kept SNP s sits at column src[s] (pass 1 then does not have to wait
-    // for the compaction: it runs beside it on a second stream)
+    // for the compaction)
     const int k = blockIdx.y;
     const int ind = ind_list ? ind_list[k] : k;
     const uint64_t* row = geno + (int64_t)ind * row_words;
@@ -669,9 +669,18 @@ __global__ void thin_windows_kernel(const uint64_t* __restrict__ geno, int64_t r
         int lo = 0, hi = n_chr - 1;                       // chromosome of slot j: last c with meta[c].y <= j
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (meta[mid].y <= j) lo = mid; else hi = mid - 1; }
         const int t = meta[lo].x + (int)(j - meta[lo].y) * step;
-        int a = 0, b = n_segs - 1, sg = -1;               // segment holding t: last segment with ws <= t
-        while (a <= b) { const int mid = (a + b) >> 1; if (segs[mid].y <= t) { sg = mid; a = mid + 1; } else b = mid - 1; }
-        if (sg < 0 || t >= segs[sg].z) continue;
+        // a valid window: inside the data and no bad pair / chromosome start among SNPs t+1 … t+W-1 (the closed form of the
+        // reference's MISSING logic, DESIGN.md §4, tested on the bit map bad_pairs_kernel leaves)
+        if ((long long)t + W > L) continue;
+        bool ok = true;
+        const int b0 = t + 1, b1 = t + W - 1;
+        for (int w = b0 >> 5; w <= (b1 >> 5); ++w) {
+            uint32_t m = bad_bits[w];
+            if (w == (b0 >> 5)) m &= ~((1u << (b0 & 31)) - 1u);
+            if (w == (b1 >> 5) && (b1 & 31) != 31) m &= (1u << ((b1 & 31) + 1)) - 1u;
+            ok = ok && m == 0u;
+        }
+        if (!ok) continue;
         double win = 0.0;
         if (glrow) {
             for (int i = 0; i < W; ++i) win += glrow[(int64_t)(t + i) * kGlLanes];
@@ -702,14 +711,14 @@ __global__ void thin_windows_kernel(const uint64_t* __restrict__ geno, int64_t r
 }
 
 cudaError_t launch_thin_windows(const uint64_t* geno, int64_t row_words, const double* lut, const int* ind_list, int n_lanes,
-                                const int3* segs, int n_segs, const int2* meta, int n_chr, long long n_slots, int step, int W,
+                                const uint32_t* bad_bits, long long L, const int2* meta, int n_chr, long long n_slots, int step, int W,
                                 double* dump, int64_t dump_stride, const double* gl, int64_t gl_stride, const int* src, cudaStream_t st)
 {
-    if (!n_lanes || !n_slots || !n_segs) return cudaSuccess;
+    if (!n_lanes || !n_slots) return cudaSuccess;
     long long bx = (n_slots + 127) / 128;
     if (bx > 4096) bx = 4096;
     dim3 grid((unsigned)bx, (unsigned)n_lanes);
-    thin_windows_kernel<<<grid, 128, 0, st>>>(geno, row_words, lut, ind_list, segs, n_segs, meta, n_chr, n_slots, step, W, dump,
+    thin_windows_kernel<<<grid, 128, 0, st>>>(geno, row_words, lut, ind_list, bad_bits, L, meta, n_chr, n_slots, step, W, dump,
                                                dump_stride, gl, gl_stride, src);
     return cudaGetLastError();
 }
@@ -1328,26 +1337,38 @@ cudaError_t launch_keep_scan(const uint8_t* keep, long long L0, const int* chr_o
 // Bad adjacent pairs (gap > MAX_GAP or overlapping the centromere, inGap garlic-roh.cpp:11-16,60-61) of the kept
 // SNPs: appends i for every bad pair (i-1,i) inside a chromosome; the host sorts the short list into stretches.
 __global__ void bad_pairs_kernel(const int* __restrict__ pos, const int* __restrict__ chr_of, const int* __restrict__ cen,
-                                 int max_gap, long long L, int* __restrict__ list, unsigned* __restrict__ count, unsigned cap)
+                                 int max_gap, long long L, int* __restrict__ list, unsigned* __restrict__ count, unsigned cap,
+                                 uint32_t* __restrict__ bad_bits)
 {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x + 1; i < L; i += (long long)gridDim.x * blockDim.x) {
-        const int c = chr_of[i];
-        if (c != chr_of[i - 1]) continue;
-        const int qs = pos[i - 1], qe = pos[i], ts = cen[2 * c], te = cen[2 * c + 1];
-        const bool gap = (ts <= qs && te >= qs) || (ts <= qe && te >= qe) || (ts >= qs && te <= qe);
-        if ((qe - qs > max_gap) || gap) {
-            const unsigned p = atomicAdd(count, 1u);
-            if (p < cap) list[p] = (int)i;
+    // bad_bits: bit i set <=> no window may hold both SNP i-1 and SNP i (a gap / centromere pair, or a chromosome start):
+    // what the thinned pass 1 tests on the device, so that it needs nothing from the host (thin_windows_kernel)
+    const long long n_round = (L + 31) & ~31ll;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_round; i += (long long)gridDim.x * blockDim.x) {
+        bool bad = false;
+        if (i >= 1 && i < L) {
+            const int c = chr_of[i];
+            if (c != chr_of[i - 1]) bad = true;
+            else {
+                const int qs = pos[i - 1], qe = pos[i], ts = cen[2 * c], te = cen[2 * c + 1];
+                const bool gap = (ts <= qs && te >= qs) || (ts <= qe && te >= qe) || (ts >= qs && te <= qe);
+                if ((qe - qs > max_gap) || gap) {
+                    bad = true;
+                    const unsigned p = atomicAdd(count, 1u);
+                    if (p < cap) list[p] = (int)i;
+                }
+            }
         }
+        const unsigned m = __ballot_sync(0xffffffffu, bad);
+        if ((threadIdx.x & 31) == 0) bad_bits[i >> 5] = m;
     }
 }
 cudaError_t launch_bad_pairs(const int* pos, const int* chr_of, const int* cen, int max_gap, long long L, int* list,
-                             unsigned* count, unsigned cap, cudaStream_t st)
+                             unsigned* count, unsigned cap, uint32_t* bad_bits, cudaStream_t st)
 {
-    if (L < 2) return cudaSuccess;
+    if (L < 1) return cudaSuccess;
     long long blocks = (L + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    bad_pairs_kernel<<<(unsigned)blocks, 256, 0, st>>>(pos, chr_of, cen, max_gap, L, list, count, cap);
+    bad_pairs_kernel<<<(unsigned)blocks, 256, 0, st>>>(pos, chr_of, cen, max_gap, L, list, count, cap, bad_bits);
     return cudaGetLastError();
 }
 

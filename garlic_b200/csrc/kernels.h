@@ -56,7 +56,7 @@ cudaError_t launch_select(const Item* items, int n_items, const uint32_t* pmax, 
                           const int* invalid, int* cand_list, int cand_stride, unsigned* cand_cnt, int2* units, unsigned* n_units,
                           unsigned unit_cap, int lanes_per_unit, int c2, cudaStream_t st);
 cudaError_t launch_thin_windows(const uint64_t* geno, int64_t row_words, const double* lut, const int* ind_list, int n_lanes,
-                                const int3* segs, int n_segs, const int2* meta, int n_chr, long long n_slots, int step, int W,
+                                const uint32_t* bad_bits, long long L, const int2* meta, int n_chr, long long n_slots, int step, int W,
                                 double* dump, int64_t dump_stride, const double* gl, int64_t gl_stride, const int* src, cudaStream_t st);
 cudaError_t launch_fill_f64(double* p, size_t n, double v, cudaStream_t st);
 cudaError_t launch_bucket_by_individual(RohRec* in, const unsigned* count, unsigned cap, unsigned* hist, int n_ind,
@@ -75,7 +75,7 @@ cudaError_t launch_freq_keep(const int* counts, long long L0, const int* pos, co
 cudaError_t launch_keep_scan(const uint8_t* keep, long long L0, const int* chr_of0, int n_chr, int* block_counts,
                              int* total, int* src, int* chr_off_kept, cudaStream_t st);
 cudaError_t launch_bad_pairs(const int* pos, const int* chr_of, const int* cen, int max_gap, long long L, int* list,
-                             unsigned* count, unsigned cap, cudaStream_t st);
+                             unsigned* count, unsigned cap, uint32_t* bad_bits, cudaStream_t st);
 cudaError_t launch_gather_i32(const int* in, const int* src, long long L, int* out, cudaStream_t st);
 cudaError_t launch_compact_gl(const double* in, int64_t in_stride, const int* src, long long L, const uint64_t* geno0,
                               int64_t row_words0, const double* freq0, double* out, int64_t out_stride, int n_ind, int type,

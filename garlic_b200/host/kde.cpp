@@ -88,6 +88,7 @@ void compute_kde(std::vector<double>& data, Kde& k, bool direct)   // computeKDE
     figtree(1, n, M, 1, data.data(), h, q.data(), k.x.data(), 1e-2, k.y.data(), direct ? FIGTREE_EVAL_DIRECT : FIGTREE_EVAL_AUTO);
 #else
     (void)direct;
+    LOG.line("KDE: built without FIGTree (reference tree not present at build time): exact Gauss transform.");
     // FIGTree not available at build time: exact Gauss transform Σ q_j exp(-(t-x_j)²/h²) (FIGTree's kernel
     // convention); differs from the reference's ε = 1e-2 approximation in the last digits of the .kde
     for (int i = 0; i < M; ++i) {
