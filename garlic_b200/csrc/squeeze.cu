@@ -56,27 +56,56 @@ __device__ __forceinline__ void cp_async_wait_dyn(int pending)     // at most `p
 // ------------------------------------------------------------------------------------------
 // A CTA makes the entries of kBtHw consecutive half-words.  The table rows they look at — 16 SNPs each for the level
 // planes, and the W + 15 SNPs behind block q - C2 for its Bmax — overlap almost completely between neighbours, so the
-// CTA's whole range of the per-SNP table is staged once with coalesced 16-byte loads and the (unchanged, strictly
+// CTA's whole range of the per-SNP table is staged once by one bulk copy (cp.async.bulk) and the (unchanged, strictly
 // ordered) arithmetic of bound.cuh then runs out of shared memory: one thread per half-word reading 512 contiguous
 // bytes of global memory per step had made this little kernel cost as much as the thinned pass 1.
 constexpr int kBtHw = 128;
+namespace {
+__device__ __forceinline__ void bt_mbar_init(uint64_t* bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sq_smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bt_bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sq_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sq_smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(sq_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bt_mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "BT_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra BT_WAIT_DONE;\n"
+        "bra BT_WAIT_LOOP;\n"
+        "BT_WAIT_DONE:\n"
+        "}\n" ::"r"(sq_smem_u32(bar)), "r"(parity) : "memory");
+}
+}  // namespace
+
 __global__ void __launch_bounds__(kBtHw)
 bound_tables_kernel(const double* __restrict__ lut, long long n_hw, long long L, int W, uint4* __restrict__ hw, int* __restrict__ invalid,
                     int stage_snps, long long n_tab)
 {
-    extern __shared__ __align__(16) double bt_smem[];
+    extern __shared__ __align__(128) double bt_smem[];       // [stage_snps][4] | mbarrier
+    uint64_t* bar = reinterpret_cast<uint64_t*>(bt_smem + (size_t)stage_snps * 4);
     const int c2 = bound_c2(W);
+    if (threadIdx.x == 0) bt_mbar_init(bar);
+    __syncthreads();
+    uint32_t phase = 0;
     for (long long k0 = (long long)blockIdx.x * kBtHw; k0 < n_hw; k0 += (long long)gridDim.x * kBtHw) {
         // SNPs [s_lo, s_lo + stage_snps): from block k0 - c2 (never below 0) to the end of half-word k0 + kBtHw - 1
         const long long kb = k0 >= c2 ? k0 - c2 : 0;
         const long long s_lo = kb * 16;
-        __syncthreads();
-        {
-            const double2* src = reinterpret_cast<const double2*>(lut + s_lo * 4);
-            double2* dst = reinterpret_cast<double2*>(bt_smem);
-            const long long lim = (n_tab - s_lo) * 2;         // table entries that exist (the rest reads as zero)
-            for (int i = threadIdx.x; i < stage_snps * 2; i += kBtHw) dst[i] = i < lim ? src[i] : make_double2(0.0, 0.0);
-        }
+        __syncthreads();                                   // the previous range has been read
+        const long long have = n_tab - s_lo < stage_snps ? n_tab - s_lo : stage_snps;   // table entries that exist
+        if (threadIdx.x == 0) bt_bulk_load(bt_smem, lut + s_lo * 4, (uint32_t)(have * 32), bar);   // one bulk copy per range
+        for (long long i = have * 4 + threadIdx.x; i < (long long)stage_snps * 4; i += kBtHw) bt_smem[i] = 0.0;   // beyond the table: zero
+        bt_mbar_wait(bar, phase);
+        phase ^= 1u;
         __syncthreads();
         const long long k = k0 + threadIdx.x;
         if (k < n_hw) {
@@ -97,7 +126,7 @@ cudaError_t launch_bound_tables(const double* lut, long long n_tab, long long n_
     // (start + 15 + W); whichever reaches further
     const int c2 = bound_c2(W);
     const int stage_snps = std::max(16 * (kBtHw + c2), 16 * (kBtHw - 1) + 16 + W + 16);
-    const size_t smem = (size_t)stage_snps * 32;
+    const size_t smem = (size_t)stage_snps * 32 + 16;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(bound_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
