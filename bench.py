@@ -5,10 +5,12 @@ Own arm (default):  python bench.py --gpus N --steps K --warmup W
     Workload = BASELINE.json configs[1]: synthetic array, 2,000 individuals x 600k SNPs (22 autosomes,
     hg19 centromeres, 0.1 % gaps > 200 kb), --winsize 50, --error 0.001, unweighted LOD, --overlap-frac 0.25,
     fixed --lod-cutoff (host KDE excluded).  One step = one pass of the hot path over the batch:
-    [H2D of the packed genotypes, e2e only] -> K2 allele/missingness counts -> (N>1: NCCL all-reduce of the
-    counts, issued by the library on its own stream) -> freq + monomorphic filter + K3 compaction -> K4 LOD table -> K5 pass 1 (thinned windows of the
-    20 KDE individuals -> host; N>1: all-gather) -> K5 pass 2 (windows -> cutoff -> coverage -> ROH, fused)
-    -> ROH records to the host.  Sharded by individual: every rank holds 2,000 individuals (weak scaling).
+    [H2D of the packed genotypes, e2e only] -> K2 allele/missingness counts -> freq + monomorphic filter (N>1: the
+    counters of all ranks are summed, and freq / keep evaluated, by one kernel over NVLink peer memory inside the library)
+    -> keep-mask scan, K3's plan -> K4 LOD table, gap bit map -> K5 pass 1 (thinned windows of the 20 KDE individuals ->
+    host of rank 0; N>1: all-gather) beside K3 fused with the pruning bound of pass 2 -> K5 pass 2 (candidate selection,
+    windows -> cutoff -> coverage -> ROH, fused) -> ROH records to the host.  Sharded by individual: every rank holds
+    2,000 individuals (weak scaling).
     `value` has the packed matrix resident in HBM; `e2e` goes through the C ABI with pinned HOST buffers.
 
 Reference arm:      python bench.py --impl reference --gpus N --steps K --warmup W
