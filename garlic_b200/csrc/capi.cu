@@ -1636,7 +1636,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     recs.clear(); ambs.clear();
     size_t n_stage = 0;            // records waiting in the pinned staging buffer
     bool done = false;
-    float ms = 0, ms_coarse = 0;
+    float ms = 0, ms_select = 0;
     bool pruned = false;
     double n_cand = -1.0;
     for (int attempt = 0; attempt < 3; ++attempt) {
@@ -1708,7 +1708,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
         if (finish_outputs(h)) return 1;
         tl_mark(h, "call_roh:synced");
         CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-        CK(cudaEventElapsedTime(&ms_coarse, h->ev0, h->ev2));
+        CK(cudaEventElapsedTime(&ms_select, h->ev0, h->ev2));
         pruned = prune_now;
         n_cand = prune_now ? (double)cnt[5] : -1.0;
         const unsigned n_raw = cnt[0], n_amb = cnt[1], n_fin = cnt[2];
@@ -1794,7 +1794,7 @@ int garlic_gpu_call_roh(garlic_gpu_t* h, int winsize, double cutoff, double over
     h->stats[1] = (double)units;
     h->stats[2] = (double)n_amb_pairs;
     h->stats[3] = ms;
-    h->stats[4] = ms_coarse;
+    h->stats[4] = ms_select;
     h->stats[5] = pruned ? n_cand : -1;
     h->stats[6] = (double)its->size() * h->n_ind;
     h->stats_items = 0;

@@ -71,7 +71,7 @@ walk_kernel(const WalkParams P, const Item* __restrict__ items, int n_items, int
     for (long long u = blockIdx.x; u < total; u += gridDim.x) {
         const int item = (int)(u / gblocks);
         const int group = (int)(u % gblocks) * gpb + warp;
-        // pruned pass: this item's individuals are the dense candidate list written by coarse_kernel
+        // pruned pass: this item's individuals are the dense candidate list written by select_kernel (squeeze.cu)
         int n_lanes = P.n_lanes;
         const int* list = nullptr;
         if (cand_list) {
