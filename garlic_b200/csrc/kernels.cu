@@ -1,6 +1,7 @@
 // kernels.cu — hand-written sm_100a kernels for the GARLIC LOD/wLOD → ROH hot path.
-// Kernel inventory: K1 code_alleles, K2 count_packed, K3 compact_*, K4 build_lut,
-// K5 walk (fused windows→ROH / window dump), K6 ld_pairs + ld_band, K5-W wlod_walk.
+// Kernel inventory: here K0 tokenize_tped, K1 code_alleles, K2 count_packed, compact_gl, K4 build_lut,
+// K5 walk / walk_units (fused windows→ROH / window dump), thin_windows, the run-record bucketing; K3 + the pruning bound
+// live in squeeze.cu, K6 and K5-W in wlod.cu, the counter exchange in xchg.cu, K0-GL in ingest.cu, the KDE in kde.cu.
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #include <stdint.h>
