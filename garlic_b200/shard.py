@@ -100,3 +100,40 @@ def allreduce_ld_planes(dist, planes):
     """The weighted path's exchange (garlic_gpu_ld_band): ranks own disjoint bits, so SUM is OR."""
     dist.all_reduce(planes, op=dist.ReduceOp.SUM)
     return planes
+
+
+def xchg_slice(n_loci, world, rank):
+    """SNP slice rank `rank` owns in the counter exchange (csrc/xchg.cu: lo = L0*rank/N, hi = L0*(rank+1)/N)."""
+    return (n_loci * rank) // world, (n_loci * (rank + 1)) // world
+
+
+def exchange_counts_freq_keep(torch, dist, counts):
+    """The algorithm of xchg_freq_keep_kernel with torch.distributed carrying the bytes (tests, world_size > 1 on CPU):
+    every rank sums the two counter rows of ALL ranks over the slice it owns, evaluates freq = nalleles / total and the
+    keep predicate there, and every rank ends up with the summed rows (in place), freq[] and keep[] of the whole SNP axis.
+    counts: int32[>=2][L0] local counters (rows 0, 1 are exchanged).  -> (freq float64[L0], keep bool[L0])"""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    L0 = counts.shape[1]
+    theirs = [torch.empty_like(counts[:2]) for _ in range(world)]
+    dist.all_gather(theirs, counts[:2].contiguous())          # what the peer pointers give the kernel
+    lo, hi = xchg_slice(L0, world, rank)
+    na = sum(t[0, lo:hi].to(torch.int64) for t in theirs)
+    tot = sum(t[1, lo:hi].to(torch.int64) for t in theirs)
+    f = torch.where(tot == 0, torch.zeros(hi - lo, dtype=torch.float64), na.to(torch.float64) / tot.to(torch.float64))
+    k = (f > 0) & (f < 1)
+    mine = torch.stack([na.to(torch.float64), tot.to(torch.float64), f, k.to(torch.float64)])   # this rank's slice
+    sizes = [xchg_slice(L0, world, r)[1] - xchg_slice(L0, world, r)[0] for r in range(world)]
+    width = max(sizes)
+    pad = torch.zeros((4, width), dtype=torch.float64)
+    pad[:, :hi - lo] = mine
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)                               # the stores into every rank's block
+    freq = torch.empty(L0, dtype=torch.float64)
+    keep = torch.empty(L0, dtype=torch.bool)
+    for r in range(world):
+        a, b = xchg_slice(L0, world, r)
+        counts[0, a:b] = parts[r][0, :b - a].to(counts.dtype)
+        counts[1, a:b] = parts[r][1, :b - a].to(counts.dtype)
+        freq[a:b] = parts[r][2, :b - a]
+        keep[a:b] = parts[r][3, :b - a] != 0
+    return freq, keep

@@ -124,3 +124,60 @@ def test_shard_ranges_cover_everything():
         assert seen == list(range(n))
     parts = shard.split_individuals([0, 3, 9, 10, 44], 45, 8)
     assert sum(len(p) for p in parts) == 5 and list(parts[0]) == [0, 3] and list(parts[1]) == [3, 4]
+
+
+def _xchg_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ds, args = load_case("lod_0")
+    geno, na, tot, one, freq = orc.code_tped(ds.alleles)
+    codes = geno.astype(np.uint8)                              # [snp][ind]
+    lo, hi = shard.shard_range(ds.n_ind, world, rank)
+    c = codes[:, lo:hi]
+    sub = ds.alleles[:, lo:hi]                                 # allele counts per character, as K1 makes them (half-missing calls count)
+    a1, a2, miss = sub[:, :, 0], sub[:, :, 1], ord("0")
+    n_a = ((a1 == one[:, None]) & (a1 != miss)).sum(1) + ((a2 == one[:, None]) & (a2 != miss)).sum(1)
+    n_t = (a1 != miss).sum(1) + (a2 != miss).sum(1)
+    local = np.stack([n_a, n_t, ((c == 0) | (c == 2)).sum(1), (c != 3).sum(1)]).astype(np.int32)
+    counts = torch.from_numpy(local.copy())
+    f, k = shard.exchange_counts_freq_keep(torch, dist, counts)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (counts.numpy().copy(), f.numpy().copy(), k.numpy().copy()))
+    if rank == 0:
+        q.put(gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_counter_exchange_by_owned_slices_equals_single_rank(world):
+    """The algorithm of csrc/xchg.cu (the NVLink counter exchange fused with freq + keep): every rank owns a slice of the SNP
+    axis, sums all ranks' counters there, evaluates freq / keep and hands sums, freq and keep to everybody.  Run over gloo:
+    every rank ends with the single-shard counters (rows 0, 1 summed in place, rows 2, 3 untouched), the oracle's freq[] bit
+    for bit and its keep mask; the slices cover the axis exactly once also when it does not divide (world = 3)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_xchg_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    ds, args = load_case("lod_0")
+    geno, na, tot, one, freq = orc.code_tped(ds.alleles)
+    L0 = len(freq)
+    seen = []
+    for r in range(world):
+        a, b = shard.xchg_slice(L0, world, r)
+        seen += list(range(a, b))
+    assert seen == list(range(L0))
+    keep = orc.keep_mask(freq, np.asarray(ds.pos))
+    for r, (counts, f, k) in enumerate(out):
+        assert np.array_equal(counts[0], na) and np.array_equal(counts[1], tot), r
+        assert np.array_equal(f, freq) and np.array_equal(k, keep.astype(bool)), r
+    # rows 2, 3 stay local (they are summed by NCCL only when the LD band asks)
+    codes = geno.astype(np.uint8)
+    lo, hi = shard.shard_range(ds.n_ind, world, 1)
+    assert np.array_equal(out[1][0][3], (codes[:, lo:hi] != 3).sum(1))
