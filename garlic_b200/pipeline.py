@@ -144,3 +144,32 @@ class HotPath:
             vals.append(blk[(blk != -9999.0) & ~np.isnan(blk)])
             base += n
         return np.concatenate(vals) if vals else np.empty(0)
+
+
+def bad_pair_bits(pos, chr_off, cens, max_gap):
+    """bool[L]: bit i set <=> no window may hold both SNP i-1 and SNP i — a gap / centromere pair (inGap, garlic-roh.cpp:11-16)
+    or a chromosome start.  What csrc/kernels.cu:bad_pairs_kernel leaves on the device for the thinned pass 1."""
+    pos = np.asarray(pos, np.int64)
+    bad = np.zeros(len(pos), bool)
+    for c in range(len(chr_off) - 1):
+        lo, hi = int(chr_off[c]), int(chr_off[c + 1])
+        if hi <= lo:
+            continue
+        if lo > 0:
+            bad[lo] = True
+        qs, qe = pos[lo:hi - 1], pos[lo + 1:hi]
+        ts, te = cens[c]
+        gap = ((ts <= qs) & (te >= qs)) | ((ts <= qe) & (te >= qe)) | ((ts >= qs) & (te <= qe))
+        bad[lo + 1:hi] = (qe - qs > max_gap) | gap
+    return bad
+
+
+def window_valid(bad, W):
+    """bool[L]: window starting at t is not MISSING <=> t + W <= L and no bad pair among SNPs t+1 … t+W-1
+    (thin_windows_kernel's test on the bit map)."""
+    L = len(bad)
+    cs = np.concatenate([[0], np.cumsum(bad.astype(np.int64))])
+    ok = np.zeros(L, bool)
+    t = np.arange(0, max(0, L - W + 1))
+    ok[:len(t)] = (cs[t + W] - cs[t + 1]) == 0
+    return ok

@@ -34,3 +34,21 @@ def test_overlap_threshold_clamp():
     assert overlap_threshold(1.0, 50) == 50
     assert overlap_threshold(2.0, 50) == 50
     assert overlap_threshold(0.3, 25) == 8
+
+
+def test_bad_pair_bit_map_reproduces_the_reference_missing_pattern():
+    """The closed form pass 1 tests on the device (a bit per SNP pair that no window may span: gap, centromere, chromosome
+    start) against the MISSING pattern of the oracle's windows (calcLOD, garlic-roh.cpp:55-123), for data with gaps,
+    centromeres strictly between / swallowing SNPs, hg19 centromeres, and several window sizes."""
+    import pytest
+    for name, W in (("lod_2", 50), ("lod_small", 10), ("lod_small", 2), ("auto_overlap_hg19", 60), ("lod_0", 25), ("lod_3", 33)):
+        ds, args = load_case(name)
+        res = orc.run_pipeline(ds, W, 0.001, None)
+        chr_off = np.concatenate([[0], np.cumsum([len(c["pos"]) for c in res["chroms"]])])
+        pos = np.concatenate([c["pos"] for c in res["chroms"]])
+        bad = pipeline.bad_pair_bits(pos, chr_off, [c["cen"] for c in res["chroms"]], 200000)
+        ok = pipeline.window_valid(bad, W)
+        want = np.concatenate([c["win"][0] != orc.MISSING for c in res["chroms"]])
+        assert len(want) == len(ok)
+        assert np.array_equal(ok, want), (name, W)
+        assert (~ok).sum() > 0
