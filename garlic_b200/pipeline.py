@@ -173,3 +173,66 @@ def window_valid(bad, W):
     t = np.arange(0, max(0, L - W + 1))
     ok[:len(t)] = (cs[t + W] - cs[t + 1]) == 0
     return ok
+
+
+_POW10 = [10.0 ** k for k in range(23)]
+
+
+def parse_decimal_fast(tok):
+    """The decimal -> fp64 conversion of csrc/ingest.cu:parse_decimal, statement for statement: (value, hard).  hard = the
+    device leaves the token to the host's strtod (more than 15 significant digits, a power of ten beyond 10^22, inf / nan /
+    hex, malformed); otherwise value is exact — one correctly rounded IEEE operation on exact operands."""
+    n, i = len(tok), 0
+    neg = False
+    if i < n and tok[i] in "+-":
+        neg = tok[i] == "-"
+        i += 1
+    m, nd, e10 = 0, 0, 0
+    any_digit = dot = bad = False
+    while i < n:
+        c = tok[i]
+        if "0" <= c <= "9":
+            any_digit = True
+            if m == 0 and c == "0":
+                if dot:
+                    e10 -= 1
+            elif nd < 19:
+                m = m * 10 + (ord(c) - 48)
+                nd += 1
+                if dot:
+                    e10 -= 1
+            else:
+                bad = True
+                if not dot:
+                    e10 += 1
+        elif c == "." and not dot:
+            dot = True
+        else:
+            break
+        i += 1
+    if i < n and tok[i] in "eE":
+        i += 1
+        eneg = False
+        if i < n and tok[i] in "+-":
+            eneg = tok[i] == "-"
+            i += 1
+        ex = nex = 0
+        while i < n and "0" <= tok[i] <= "9":
+            ex = ex * 10 + (ord(tok[i]) - 48) if ex < 100000 else ex
+            nex += 1
+            i += 1
+        if not nex:
+            bad = True
+        e10 += -ex if eneg else ex
+    if i < n:
+        bad = True
+    if not any_digit:
+        bad = True
+    v = 0.0
+    if not bad and m != 0:
+        if nd <= 15 and -22 <= e10 <= 22:
+            v = float(m)
+            v = v / _POW10[-e10] if e10 < 0 else v * _POW10[e10]
+        else:
+            bad = True
+    return (-v if neg else v), bad

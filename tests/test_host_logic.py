@@ -52,3 +52,42 @@ def test_bad_pair_bit_map_reproduces_the_reference_missing_pattern():
         assert len(want) == len(ok)
         assert np.array_equal(ok, want), (name, W)
         assert (~ok).sum() > 0
+
+
+def test_decimal_fast_path_is_exact_or_hands_over():
+    """K0-GL's conversion rule (csrc/ingest.cu:parse_decimal, restated in pipeline.parse_decimal_fast): whatever it does not
+    hand to strtod it converts exactly — checked against Python's correctly rounded float() on 200,000 random tokens of the
+    shapes likelihood files hold, and on the edge cases of the rule."""
+    rng = np.random.default_rng(17)
+    n_fast = 0
+    for _ in range(200000):
+        kind = rng.integers(0, 8)
+        if kind == 0:
+            tok = str(int(rng.integers(0, 10 ** int(rng.integers(1, 17)))))
+        elif kind == 1:
+            tok = "%.*f" % (int(rng.integers(0, 12)), rng.uniform(-300, 300))
+        elif kind == 2:
+            tok = "%.*e" % (int(rng.integers(0, 17)), rng.uniform(-1, 1) * 10.0 ** int(rng.integers(-30, 30)))
+        elif kind == 3:
+            tok = "%d.%0*d" % (rng.integers(0, 1000), int(rng.integers(1, 18)), rng.integers(0, 10 ** 9))
+        elif kind == 4:
+            tok = "%.17g" % rng.uniform(0, 1)
+        elif kind == 5:
+            tok = "0.%s%d" % ("0" * int(rng.integers(0, 20)), rng.integers(1, 10 ** 6))
+        elif kind == 6:
+            tok = "%de%d" % (rng.integers(0, 10 ** 15), rng.integers(-25, 25))
+        else:
+            tok = "%s%d%s" % (["", "+", "-"][int(rng.integers(0, 3))], rng.integers(0, 256), ["", ".", ".0", ".50"][int(rng.integers(0, 4))])
+        v, hard = pipeline.parse_decimal_fast(tok)
+        if not hard:
+            n_fast += 1
+            assert v == float(tok) and np.signbit(v) == np.signbit(float(tok)), tok
+    assert n_fast > 100000
+    for tok, want_hard in (("0", False), ("-0.0", False), ("150", False), ("0.0004", False), ("1e22", False), ("1e23", True),
+                           ("123456789012345", False), ("1234567890123456", True), ("9007199254740993", True), ("nan", True),
+                           ("inf", True), ("0x10", True), ("1e", True), (".", True), ("", True), ("1.5x", True), ("1e-22", False),
+                           ("0.000000000000000000000001", True), ("5e-324", True)):
+        v, hard = pipeline.parse_decimal_fast(tok)
+        assert hard == want_hard, tok
+        if not hard:
+            assert v == float(tok), tok
