@@ -503,6 +503,7 @@ def main():
                     bytes_per_individual_window=alg_bytes / units_local,
                     peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                     kernel_units_per_s=units_local / (sqms / 1e3),
+                    frac_of_nominal_8000_gbs=achieved / 8000.0,     # BASELINE.json quotes "roughly 8 TB/s" (report both)
                     pass2=dict(kernels="select_kernel + walk_units_kernel (windows -> cutoff -> coverage -> ROH on the "
                                        "candidates the bound leaves)", ms=kms, select_ms=state["stats"]["select_ms"],
                                candidate_pair_fraction=cand, algorithmic_bytes=walk_bytes,
